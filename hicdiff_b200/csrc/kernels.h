@@ -1,0 +1,200 @@
+// Internal launcher interface between the plan/graph builder (plan.cu) and the kernels.
+// Everything here is device-pointer + stream based; no torch types anywhere in csrc/.
+//
+// Activation layout in HBM: NHWC, bf16, i.e. a [B*H*W, C] row-major matrix whose rows are
+// pixels.  The sample state x_t, eps and everything the posterior update touches stay fp32
+// in the reference's NCHW layout (C == 1, so NCHW == NHWC there).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hd {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------------
+// conv_gemm.cu -- tcgen05/TMEM implicit-GEMM convolution (3x3 pad 1, 1x1, pixel-unshuffle 1x1)
+// ---------------------------------------------------------------------------------------------
+struct ConvSrc {
+    const bf16* ptr;  // [B, H, W, C] NHWC
+    int C;            // channels (multiple of 64)
+};
+
+enum ConvMode : int {
+    CONV_TAPS = 0,       // kh x kw taps, stride 1, "same" zero padding (kh==kw in {1,3})
+    CONV_UNSHUFFLE = 1,  // 'b c (h p1) (w p2) -> b (c p1 p2) h w' followed by a 1x1 conv
+};
+
+struct ConvEpilogue {
+    const float* bias = nullptr;      // [N]
+    // per-step feature-wise modulation (HiCEDRN): v = v * (1 + scale[c]) + shift[c]
+    const float* film = nullptr;      // table base, row-major [rows, film_ld]
+    const int* film_row = nullptr;    // device row index (step counter) or per-sample rows
+    int film_row_stride = 0;          // 0: one row for the whole batch, 1: film_row[b]
+    int film_ld = 0;
+    int film_off = 0;                 // column offset of this layer's slice inside a row
+    int film_has_scale = 0;           // 1: [scale(N) | shift(N)], 0: [shift(N)] only
+    int silu = 0;                     // v = v * sigmoid(v)
+    float out_scale = 1.0f;           // v *= out_scale
+    const bf16* res = nullptr;        // v += res[m, c]   (row stride ldr)
+    int ldr = 0;
+    float* out_f32 = nullptr;         // if set: write fp32 [M, n_valid] instead of bf16
+    int n_valid = 0;
+};
+
+struct ConvGemmDesc {
+    ConvSrc src0, src1;       // src1.ptr == nullptr when there is no channel concat
+    int B, H, W;              // OUTPUT spatial size (== input size for CONV_TAPS; input is 2H x 2W for UNSHUFFLE)
+    int ksize;                // 1 or 3 (CONV_TAPS); ignored for UNSHUFFLE
+    ConvMode mode;
+    const bf16* weight;       // [Npad, Ktot] K-major; K order = (tap, concat channel)
+    int N;                    // rows of `weight` (multiple of the chosen N tile)
+    bf16* out;                // [B*H*W, N]
+    ConvEpilogue epi;
+};
+
+// Opaque prepared launch (tensor maps encoded once, replayed inside CUDA graphs).
+struct ConvGemmLaunch {
+    CUtensorMap tmA0, tmA1, tmB;
+    int bn;             // N tile (16, 64, 128 or 256)
+    int grid;
+    int smem_bytes;
+    // kernel scalar arguments
+    int M, N, num_m_tiles, num_n_tiles, nkb, chunks0, chunks1, mode, W, P, kw, pad;
+    ConvEpilogue epi;
+    bf16* out;
+    int ldo;
+};
+
+// Returns 0 on success; on failure fills `err` (size errlen).
+int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, char* err, int errlen);
+cudaError_t conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// norm.cu -- GroupNorm(8)+FiLM+SiLU (cluster/DSMEM two-pass), channel LayerNorm
+// ---------------------------------------------------------------------------------------------
+struct GroupNormArgs {
+    const bf16* x;        // [B, P, C]
+    bf16* y;              // [B, P, C]
+    int B, P, C;          // P = H*W pixels
+    const float* gamma;   // [C]
+    const float* beta;    // [C]
+    float eps;
+    // FiLM: y = gn * (scale + 1) + shift, row picked like ConvEpilogue
+    const float* film = nullptr;
+    const int* film_row = nullptr;
+    int film_row_stride = 0;
+    int film_ld = 0;
+    int film_off = 0;           // scale at film_off + c, shift at film_off + C + c
+    // SR3: additive per-channel noise embedding applied AFTER the activation
+    const float* postadd = nullptr;   // same row addressing as film; value at postadd_off + c
+    int postadd_off = 0;
+    const bf16* res = nullptr;        // + res[b, p, c] after the activation (ResnetBlock skip)
+};
+cudaError_t groupnorm_film_silu_run(const GroupNormArgs& a, cudaStream_t s);
+
+struct LayerNormArgs {
+    const bf16* x;    // [M, C]
+    bf16* y;          // [M, C] (or upsampled [B, 2H, 2W, C] when upsample2x)
+    int M, C;
+    const float* g;   // [C]
+    float eps;
+    const bf16* res = nullptr;  // + res[m, c] (Residual wrapper)
+    int upsample2x = 0;         // nearest x2: write each pixel to its 2x2 block
+    int H = 0, W = 0;           // needed for upsample2x
+};
+cudaError_t channel_layernorm_run(const LayerNormArgs& a, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// attention.cu
+// ---------------------------------------------------------------------------------------------
+struct LinAttnArgs {
+    const bf16* qkv;   // [B, n, 384]: q = [0,128), k = [128,256), v = [256,384); head h owns 32 channels
+    bf16* out;         // [B, n, 128]
+    float* ctx;        // scratch [B, 4, 32, 32] fp32
+    int B, n;
+};
+cudaError_t linear_attention_run(const LinAttnArgs& a, cudaStream_t s);
+
+struct FullAttnArgs {
+    const bf16* qkv;   // [B, n, 384], n <= 64
+    bf16* out;         // [B, n, 128]
+    int B, n;
+};
+cudaError_t full_attention_run(const FullAttnArgs& a, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// pointwise.cu -- stem conv (tiny Cin), 1x1 head to eps, DDPM posterior step, Philox noise
+// ---------------------------------------------------------------------------------------------
+struct StemConvArgs {
+    const float* x0;   // first input channel plane [B, H, W] fp32 (cond when self_condition, else x)
+    const float* x1;   // second plane or nullptr
+    const float* w;    // [Cout, Cin, k, k] fp32 (reference layout)
+    const float* bias; // [Cout]
+    bf16* y;           // [B, H, W, Cout]
+    int B, H, W, Cout, Cin, ksize;
+};
+cudaError_t stem_conv_run(const StemConvArgs& a, cudaStream_t s);
+
+struct HeadConvArgs {
+    const bf16* x;     // [M, C]
+    const float* w;    // [C]
+    const float* bias; // [1]
+    float* eps;        // [M]
+    int M, C;
+};
+cudaError_t head_conv1x1_run(const HeadConvArgs& a, cudaStream_t s);
+
+// Device-resident control block of a sampling run; written once per hd_sample / hd_ddpm_step call, advanced on
+// the device, so a single captured CUDA graph can be replayed for every step.
+struct SampleCtl {
+    int step;                        // current t (FiLM table row and coefficient row)
+    int noise_single;                // 1: `noise` is the z tensor of this very step; 0: base of [T, n], row T - t
+    const float* noise;              // nullptr -> Philox
+    unsigned long long seed;
+    unsigned long long tile_offset;  // first global tile id of this batch (world-size independent streams)
+};
+
+// coefficient table row: {sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1,
+//                         posterior_mean_coef2, exp(0.5 * posterior_log_variance_clipped), 0, 0, 0}, T rows
+struct PosteriorArgs {
+    float* x;               // [n] in/out sample state
+    const float* eps;       // [n]
+    const float* coef;      // [T, 8]
+    const SampleCtl* ctl;   // device
+    int T;
+    long long n;            // elements (B*H*W)
+    int tile_elems;         // H*W
+    float* x0_out;          // optional: clipped x_start
+};
+cudaError_t posterior_step_run(const PosteriorArgs& a, cudaStream_t s);
+
+cudaError_t philox_normal_run(float* out, long long n, unsigned long long seed, unsigned long long tile_offset,
+                              int tile_elems, unsigned long long stream_id, cudaStream_t s);
+cudaError_t step_advance_run(SampleCtl* ctl, int delta, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// prep.cu -- one-off weight preparation and the time-embedding tables
+// ---------------------------------------------------------------------------------------------
+// [Cout, Cin, k, k] fp32 -> [Npad, k*k*Cin] bf16 with K order (tap, cin); optional weight standardisation
+cudaError_t prep_conv_weight_run(const float* w, bf16* out, int Cout, int Cin, int ksize, int standardize, float eps,
+                                 int Npad, cudaStream_t s);
+// Downsample 1x1 weight [Cout, 4*C] with K order (c, p1, p2) -> (p1, p2, c)
+cudaError_t prep_unshuffle_weight_run(const float* w, bf16* out, int Cout, int C, cudaStream_t s);
+
+// y[r, ldy*r + off + j] = bias[j] + sum_k act(x[r, k]) * W[j, k];  act: 0 none, 1 SiLU (on input), out_act: 0 none, 1 GELU(erf)
+cudaError_t linear_rows_run(const float* x, int ldx, const float* W, const float* bias, float* y, int ldy, int off,
+                            int rows, int in_f, int out_f, int in_act, int out_act, cudaStream_t s);
+// mode 0: SinusoidalPosEmb(dim) of integer timesteps t[r] (as float); mode 1: SR3 PositionalEncoding of level[r]
+cudaError_t posenc_rows_run(const float* t, float* y, int rows, int dim, int mode, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// tiles.cu -- splitPieces-order tile extraction / reassembly
+// ---------------------------------------------------------------------------------------------
+cudaError_t tile_extract_run(const float* mat, int n, float* tiles, int piece, int band_blocks, cudaStream_t s);
+cudaError_t tile_scatter_run(const float* tiles, float* mat, int n, int piece, int band_blocks, cudaStream_t s);
+int tile_count(int n, int piece, int band_blocks);
+
+}  // namespace hd

@@ -1,0 +1,1107 @@
+// Plan = one eps-predictor + its schedule, resident on one GPU; C ABI of include/hicdiff_b200.h.
+//
+// The plan turns the reference's module tree (Unet: /root/reference/src/hicdiff_condition.py:255-384,
+// hicdiff_sr3.py:310-445; hicedrn_Diff: /root/reference/src/model/hicedrn_Diff.py:210-289) into a flat list of
+// kernel launches over a static activation arena, captures one denoising step (eps-net + posterior update +
+// step-counter decrement) into a CUDA graph per batch size and replays it T times
+// (p_sample_loop, hicdiff_condition.py:600-623).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/hicdiff_b200.h"
+#include "kernels.h"
+
+using namespace hd;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CUDA_TRY(expr)                                                                           \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(e__));    \
+    } while (0)
+
+struct WeightT {
+    float* d = nullptr;
+    std::vector<int64_t> shape;
+    size_t numel = 0;
+};
+
+struct Act {
+    bf16* p = nullptr;
+    int H = 0, W = 0, C = 0;
+};
+
+// First-fit arena over byte offsets.  Offsets are deterministic for a given op sequence, so a dry run sizes it.
+struct Arena {
+    struct Blk { size_t off, size; bool free; };
+    std::vector<Blk> blks;
+    size_t high = 0;
+    bool never_free = false;
+    size_t alloc(size_t bytes) {
+        bytes = (bytes + 1023) & ~size_t(1023);
+        for (size_t i = 0; i < blks.size(); ++i) {
+            if (blks[i].free && blks[i].size >= bytes) {
+                if (blks[i].size > bytes) {
+                    Blk rest{blks[i].off + bytes, blks[i].size - bytes, true};
+                    blks[i].size = bytes;
+                    blks.insert(blks.begin() + i + 1, rest);
+                }
+                blks[i].free = false;
+                return blks[i].off;
+            }
+        }
+        if (!blks.empty() && blks.back().free) {
+            blks.back().size = bytes;
+            blks.back().free = false;
+            high = blks.back().off + bytes;
+            return blks.back().off;
+        }
+        Blk b{high, bytes, false};
+        blks.push_back(b);
+        high += bytes;
+        return b.off;
+    }
+    void release(size_t off) {
+        if (never_free) return;
+        for (size_t i = 0; i < blks.size(); ++i) {
+            if (blks[i].off == off && !blks[i].free) {
+                blks[i].free = true;
+                if (i + 1 < blks.size() && blks[i + 1].free) {
+                    blks[i].size += blks[i + 1].size;
+                    blks.erase(blks.begin() + i + 1);
+                }
+                if (i > 0 && blks[i - 1].free) {
+                    blks[i - 1].size += blks[i].size;
+                    blks.erase(blks.begin() + i);
+                }
+                return;
+            }
+        }
+    }
+};
+
+struct Op {
+    std::function<cudaError_t(cudaStream_t)> fn;
+    std::string tag;
+};
+
+struct FilmSlot {
+    std::string wkey, bkey;  // Linear weight / bias keys
+    int off = 0;             // column offset in a FiLM row
+    int width = 0;           // 2*Cout (scale|shift) or Cout (SR3 additive)
+    bool silu_in = false;    // ResnetBlock.mlp = SiLU -> Linear; SR3 noise_func = Linear only
+};
+
+struct DebugEntry {
+    const bf16* p;
+    int H, W, C;
+};
+
+struct Exec {
+    int B = 0;
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+    float* x = nullptr;      // [B, 4096] sample state
+    float* cond = nullptr;   // [B, 4096]
+    float* eps = nullptr;    // [B, 4096]
+    float* time = nullptr;   // [B]
+    float* posenc = nullptr; // [B, fourier]
+    float* temb0 = nullptr;  // [B, time_dim]
+    float* temb = nullptr;   // [B, time_dim]
+    float* film_rows = nullptr;  // [B, film_ld]
+    int* iota = nullptr;     // [B]
+    float* ctx = nullptr;    // linear-attention scratch [B,4,32,32]
+    std::vector<Op> ops_rows, ops_table;
+    cudaGraphExec_t g_eps = nullptr, g_step = nullptr;
+    std::map<std::string, DebugEntry> dbg;
+    std::vector<std::string> dbg_order;
+    size_t extra_bytes = 0;
+};
+
+}  // namespace
+
+struct hd_plan {
+    hd_config cfg;
+    int device = 0;
+    int num_sms = 148;
+    std::map<std::string, WeightT> w;
+    std::map<std::string, bf16*> wq;      // GEMM-layout bf16 weights
+    std::map<std::string, float*> padded; // zero-padded fp32 vectors (bias of padded-N convs)
+    std::vector<FilmSlot> film;
+    std::map<std::string, int> film_index;  // block prefix -> slot
+    int film_ld = 0;
+    int fourier_dim = 0, time_dim = 0;
+    bool sr3 = false, hicedrn = false;
+    int T = 0;
+    float* coef = nullptr;        // [T, 8]
+    float* time_values = nullptr; // [T]
+    float* film_table = nullptr;  // [T, film_ld]
+    SampleCtl* ctl = nullptr;     // device control block (sampling)
+    SampleCtl* ctl_one = nullptr; // device control block (hd_ddpm_step)
+    bool finalized = false;
+    size_t weight_bytes = 0;
+    std::map<int, std::unique_ptr<Exec>> execs;
+};
+
+namespace {
+
+const WeightT* find_w(const hd_plan* P, const std::string& key) {
+    auto it = P->w.find(key);
+    return it == P->w.end() ? nullptr : &it->second;
+}
+
+bool ends_with(const std::string& s, const char* suf) {
+    const size_t n = strlen(suf);
+    return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Time embedding -> FiLM rows.  Reference: time_mlp (hicdiff_condition.py:300-305), ResnetBlock.mlp (:176-191),
+// SR3 FeatureWiseAffine (hicdiff_sr3.py:167-183); HiCEDRN: hicedrn_Diff.py:232-246,189-200.
+// ------------------------------------------------------------------------------------------------------------
+int enqueue_film(hd_plan* P, const float* time_values, int rows, float* posenc, float* temb0, float* temb,
+                 float* film_out, std::vector<Op>* ops) {
+    const WeightT *w1 = find_w(P, "time_mlp.1.weight"), *b1 = find_w(P, "time_mlp.1.bias");
+    const WeightT *w3 = find_w(P, "time_mlp.3.weight"), *b3 = find_w(P, "time_mlp.3.bias");
+    if (!w1 || !b1 || !w3 || !b3) return fail("time_mlp weights missing");
+    const int fd = P->fourier_dim, td = P->time_dim, ld = P->film_ld;
+    const int mode = P->sr3 ? 1 : 0;
+    ops->push_back({[=](cudaStream_t s) { return posenc_rows_run(time_values, posenc, rows, fd, mode, s); }, "posenc"});
+    const float *w1d = w1->d, *b1d = b1->d, *w3d = w3->d, *b3d = b3->d;
+    ops->push_back({[=](cudaStream_t s) { return linear_rows_run(posenc, fd, w1d, b1d, temb0, td, 0, rows, fd, td, 0, 1, s); },
+                    "time_mlp.1+gelu"});
+    ops->push_back({[=](cudaStream_t s) { return linear_rows_run(temb0, td, w3d, b3d, temb, td, 0, rows, td, td, 0, 0, s); },
+                    "time_mlp.3"});
+    for (const FilmSlot& f : P->film) {
+        const WeightT *fw = find_w(P, f.wkey), *fb = find_w(P, f.bkey);
+        if (!fw || !fb) return fail("weight %s missing", f.wkey.c_str());
+        const float *fwd = fw->d, *fbd = fb->d;
+        const int off = f.off, width = f.width, act = f.silu_in ? 1 : 0;
+        ops->push_back({[=](cudaStream_t s) { return linear_rows_run(temb, td, fwd, fbd, film_out, ld, off, rows, td, width, act, 0, s); },
+                        f.wkey});
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Graph builder
+// ------------------------------------------------------------------------------------------------------------
+struct FilmRef {
+    const float* base;
+    const int* row;
+    int row_stride;
+};
+
+struct Builder {
+    hd_plan* P;
+    Exec* ex;
+    int B;
+    bool dry;
+    Arena arena;
+    std::vector<Op>* ops;
+    FilmRef film;
+    std::string err;
+    bool ok = true;
+
+    Act alloc_act(int H, int W, int C) {
+        Act a;
+        a.H = H; a.W = W; a.C = C;
+        const size_t off = arena.alloc(static_cast<size_t>(B) * H * W * C * 2);
+        a.p = reinterpret_cast<bf16*>(static_cast<char*>(dry ? nullptr : ex->arena) + off);
+        return a;
+    }
+    void free_act(const Act& a) {
+        if (a.p == nullptr && !dry) return;
+        arena.release(reinterpret_cast<const char*>(a.p) - static_cast<const char*>(dry ? nullptr : ex->arena));
+    }
+    void note(const std::string& name, const Act& a) {
+        if (!dry && P->cfg.debug_keep) {
+            ex->dbg[name] = DebugEntry{a.p, a.H, a.W, a.C};
+            ex->dbg_order.push_back(name);
+        }
+    }
+    bool bad(const std::string& m) {
+        if (ok) { ok = false; err = m; }
+        return false;
+    }
+    const float* wf(const std::string& key) {
+        const WeightT* w = find_w(P, key);
+        if (!w) { bad("weight '" + key + "' missing from the plan"); return nullptr; }
+        return w->d;
+    }
+    const bf16* wq(const std::string& key) {
+        auto it = P->wq.find(key);
+        if (it == P->wq.end()) { bad("prepared weight '" + key + "' missing"); return nullptr; }
+        return it->second;
+    }
+
+    // conv on the tcgen05 path
+    Act conv(const std::string& wkey, const std::string& bkey, const Act& x0, const Act* x1, int Cout, int ksize,
+             ConvMode mode, ConvEpilogue epi, int n_rows = 0) {
+        const int Ho = mode == CONV_UNSHUFFLE ? x0.H / 2 : x0.H;
+        const int Wo = mode == CONV_UNSHUFFLE ? x0.W / 2 : x0.W;
+        const int N = n_rows ? n_rows : Cout;
+        Act y;
+        if (epi.out_f32 == nullptr) y = alloc_act(Ho, Wo, N); else { y.H = Ho; y.W = Wo; y.C = N; }
+        if (!bkey.empty()) epi.bias = n_rows ? padded_bias(bkey) : wf(bkey);
+        ConvGemmDesc d;
+        d.src0 = ConvSrc{x0.p, x0.C};
+        d.src1 = ConvSrc{x1 ? x1->p : nullptr, x1 ? x1->C : 0};
+        d.B = B; d.H = Ho; d.W = Wo; d.ksize = ksize; d.mode = mode;
+        d.weight = wq(wkey);
+        d.N = N;
+        d.out = y.p;
+        d.epi = epi;
+        if (!ok) return y;
+        if (!dry) {
+            ConvGemmLaunch l;
+            char e[256];
+            if (conv_gemm_prepare(d, P->num_sms, &l, e, sizeof(e))) { bad(std::string(wkey) + ": " + e); return y; }
+            ops->push_back({[l](cudaStream_t s) { return conv_gemm_run(l, s); }, wkey});
+        }
+        return y;
+    }
+    const float* padded_bias(const std::string& key) {
+        auto it = P->padded.find(key);
+        if (it == P->padded.end()) { bad("padded bias '" + key + "' missing"); return nullptr; }
+        return it->second;
+    }
+
+    void groupnorm(const Act& x, const std::string& prefix, int film_off, int postadd_off, const Act* res) {
+        GroupNormArgs g;
+        g.x = x.p; g.y = x.p;   // in place: each CTA stages its own slab in smem before writing it back
+        g.B = B; g.P = x.H * x.W; g.C = x.C;
+        g.gamma = wf(prefix + ".weight");
+        g.beta = wf(prefix + ".bias");
+        g.eps = 1e-5f;
+        g.film_row = film.row; g.film_row_stride = film.row_stride; g.film_ld = P->film_ld;
+        if (film_off >= 0) { g.film = film.base; g.film_off = film_off; }
+        if (postadd_off >= 0) { g.postadd = film.base; g.postadd_off = postadd_off; }
+        if (res) g.res = res->p;
+        if (!ok || dry) return;
+        ops->push_back({[g](cudaStream_t s) { return groupnorm_film_silu_run(g, s); }, prefix});
+    }
+
+    Act layernorm(const Act& x, const std::string& gkey, const Act* res, bool up2x) {
+        Act y = up2x ? alloc_act(x.H * 2, x.W * 2, x.C) : alloc_act(x.H, x.W, x.C);
+        LayerNormArgs l;
+        l.x = x.p; l.y = y.p; l.M = B * x.H * x.W; l.C = x.C; l.g = wf(gkey); l.eps = 1e-5f;
+        l.res = res ? res->p : nullptr; l.upsample2x = up2x ? 1 : 0; l.H = x.H; l.W = x.W;
+        if (ok && !dry) ops->push_back({[l](cudaStream_t s) { return channel_layernorm_run(l, s); }, gkey});
+        return y;
+    }
+
+    // ResnetBlock (hicdiff_condition.py:173-197 / hicdiff_sr3.py:235-251)
+    Act resblock(const std::string& p, const Act& x0, const Act* x1, int Cout) {
+        const int Cin = x0.C + (x1 ? x1->C : 0);
+        Act h = conv(p + ".block1.proj.weight", p + ".block1.proj.bias", x0, x1, Cout, 3, CONV_TAPS, ConvEpilogue());
+        note(p + ".block1.proj", h);
+        const int slot = P->film_index.count(p) ? P->film_index[p] : -1;
+        if (slot < 0) bad("no time-embedding slot for block " + p);
+        const int off = slot >= 0 ? P->film[slot].off : 0;
+        if (P->sr3) groupnorm(h, p + ".block1.norm", -1, off, nullptr);
+        else groupnorm(h, p + ".block1.norm", off, -1, nullptr);
+        note(p + ".block1", h);
+        Act h2 = conv(p + ".block2.proj.weight", p + ".block2.proj.bias", h, nullptr, Cout, 3, CONV_TAPS, ConvEpilogue());
+        free_act(h);
+        Act r;
+        bool own_r = false;
+        if (Cin != Cout) {
+            r = conv(p + ".res_conv.weight", p + ".res_conv.bias", x0, x1, Cout, 1, CONV_TAPS, ConvEpilogue());
+            own_r = true;
+        } else {
+            r = x0;
+        }
+        groupnorm(h2, p + ".block2.norm", -1, -1, &r);
+        if (own_r) free_act(r);
+        note(p, h2);
+        return h2;
+    }
+
+    // Residual(PreNorm(dim, LinearAttention(dim)))  (hicdiff_condition.py:199-227,319)
+    Act linattn(const std::string& p, const Act& x, bool up2x) {
+        Act xn = layernorm(x, p + ".fn.norm.g", nullptr, false);
+        Act qkv = conv(p + ".fn.fn.to_qkv.weight", "", xn, nullptr, 384, 1, CONV_TAPS, ConvEpilogue());
+        free_act(xn);
+        Act att = alloc_act(x.H, x.W, 128);
+        LinAttnArgs la;
+        la.qkv = qkv.p; la.out = att.p; la.ctx = dry ? nullptr : ex->ctx; la.B = B; la.n = x.H * x.W;
+        if (ok && !dry) ops->push_back({[la](cudaStream_t s) { return linear_attention_run(la, s); }, p + ".linattn"});
+        free_act(qkv);
+        note(p + ".attn_core", att);
+        Act o = conv(p + ".fn.fn.to_out.0.weight", p + ".fn.fn.to_out.0.bias", att, nullptr, x.C, 1, CONV_TAPS, ConvEpilogue());
+        free_act(att);
+        Act y = layernorm(o, p + ".fn.fn.to_out.1.g", &x, up2x);
+        free_act(o);
+        note(p, y);
+        return y;
+    }
+
+    // Residual(PreNorm(dim, Attention(dim)))  (hicdiff_condition.py:229-251,326)
+    Act fullattn(const std::string& p, const Act& x) {
+        Act xn = layernorm(x, p + ".fn.norm.g", nullptr, false);
+        Act qkv = conv(p + ".fn.fn.to_qkv.weight", "", xn, nullptr, 384, 1, CONV_TAPS, ConvEpilogue());
+        free_act(xn);
+        Act att = alloc_act(x.H, x.W, 128);
+        FullAttnArgs fa;
+        fa.qkv = qkv.p; fa.out = att.p; fa.B = B; fa.n = x.H * x.W;
+        if (ok && !dry) ops->push_back({[fa](cudaStream_t s) { return full_attention_run(fa, s); }, p + ".attn"});
+        free_act(qkv);
+        ConvEpilogue e;
+        e.res = x.p; e.ldr = x.C;
+        Act y = conv(p + ".fn.fn.to_out.weight", p + ".fn.fn.to_out.bias", att, nullptr, x.C, 1, CONV_TAPS, e);
+        free_act(att);
+        note(p, y);
+        return y;
+    }
+
+    Act stem(const std::string& wkey, const std::string& bkey, int Cout, int ksize) {
+        const int S = P->cfg.image_size;
+        Act y = alloc_act(S, S, Cout);
+        StemConvArgs a;
+        a.x0 = P->cfg.self_condition ? (dry ? nullptr : ex->cond) : (dry ? nullptr : ex->x);
+        a.x1 = P->cfg.self_condition ? (dry ? nullptr : ex->x) : nullptr;
+        a.w = wf(wkey); a.bias = wf(bkey); a.y = y.p;
+        a.B = B; a.H = S; a.W = S; a.Cout = Cout; a.Cin = P->cfg.self_condition ? 2 : 1; a.ksize = ksize;
+        if (ok && !dry) ops->push_back({[a](cudaStream_t s) { return stem_conv_run(a, s); }, wkey});
+        return y;
+    }
+
+    // Unet.forward (hicdiff_condition.py:345-384)
+    void build_unet() {
+        const hd_config& c = P->cfg;
+        const int dim = c.dim;
+        std::vector<int> dims;
+        dims.push_back(dim);
+        for (int i = 0; i < c.num_mults; ++i) dims.push_back(dim * c.dim_mults[i]);
+        const int L = c.num_mults;
+        Act x = stem("init_conv.weight", "init_conv.bias", dim, 7);
+        note("init_conv", x);
+        Act r = x;
+        std::vector<Act> hs;
+        bool x_is_r = true;
+        for (int i = 0; i < L; ++i) {
+            const int din = dims[i], dout = dims[i + 1];
+            const bool last = i == L - 1;
+            const std::string p = "downs." + std::to_string(i);
+            Act a = resblock(p + ".0", x, nullptr, din);
+            if (!x_is_r) free_act(x);
+            x_is_r = false;
+            hs.push_back(a);
+            Act b = resblock(p + ".1", a, nullptr, din);
+            Act cst = linattn(p + ".2", b, false);
+            free_act(b);
+            hs.push_back(cst);
+            if (!last) {
+                x = conv(p + ".3.1.weight", p + ".3.1.bias", cst, nullptr, dout, 1, CONV_UNSHUFFLE, ConvEpilogue());
+            } else {
+                x = conv(p + ".3.weight", p + ".3.bias", cst, nullptr, dout, 3, CONV_TAPS, ConvEpilogue());
+            }
+            note(p + ".3", x);
+        }
+        {
+            Act m1 = resblock("mid_block1", x, nullptr, dims[L]);
+            free_act(x);
+            Act m2 = fullattn("mid_attn", m1);
+            free_act(m1);
+            x = resblock("mid_block2", m2, nullptr, dims[L]);
+            free_act(m2);
+        }
+        for (int k = 0; k < L; ++k) {
+            const int i = L - 1 - k;            // reversed(in_out)
+            const int din = dims[i], dout = dims[i + 1];
+            const bool last = k == L - 1;
+            const std::string p = "ups." + std::to_string(k);
+            Act s1 = hs.back(); hs.pop_back();
+            Act a = resblock(p + ".0", x, &s1, dout);
+            free_act(x); free_act(s1);
+            Act s2 = hs.back(); hs.pop_back();
+            Act b = resblock(p + ".1", a, &s2, dout);
+            free_act(a); free_act(s2);
+            Act cst = linattn(p + ".2", b, !last);     // the attention's closing LayerNorm also does Upsample's x2
+            free_act(b);
+            if (!last) x = conv(p + ".3.1.weight", p + ".3.1.bias", cst, nullptr, din, 3, CONV_TAPS, ConvEpilogue());
+            else x = conv(p + ".3.weight", p + ".3.bias", cst, nullptr, din, 3, CONV_TAPS, ConvEpilogue());
+            free_act(cst);
+            note(p + ".3", x);
+        }
+        Act f = resblock("final_res_block", x, &r, dim);
+        free_act(x); free_act(r);
+        HeadConvArgs hca;
+        hca.x = f.p; hca.w = wf("final_conv.weight"); hca.bias = wf("final_conv.bias");
+        hca.eps = dry ? nullptr : ex->eps; hca.M = B * c.image_size * c.image_size; hca.C = dim;
+        if (ok && !dry) ops->push_back({[hca](cudaStream_t s) { return head_conv1x1_run(hca, s); }, "final_conv"});
+        free_act(f);
+    }
+
+    // hicedrn_Diff.forward (hicedrn_Diff.py:267-289; ResnetBlock :182-208)
+    void build_hicedrn() {
+        const hd_config& c = P->cfg;
+        const int F = 256;
+        Act x = stem("head.weight", "head.bias", F, 3);
+        note("head", x);
+        Act r = x;
+        bool x_is_r = true;
+        for (int i = 0; i < c.num_blocks; ++i) {
+            const std::string p = "body." + std::to_string(i);
+            const int slot = P->film_index.count(p) ? P->film_index[p] : -1;
+            if (slot < 0) { bad("no time-embedding slot for block " + p); return; }
+            ConvEpilogue e1;
+            e1.film = film.base; e1.film_row = film.row; e1.film_row_stride = film.row_stride; e1.film_ld = P->film_ld;
+            e1.film_off = P->film[slot].off; e1.film_has_scale = P->sr3 ? 0 : 1; e1.silu = 1;
+            Act h = conv(p + ".conv.proj.weight", p + ".conv.proj.bias", x, nullptr, F, 3, CONV_TAPS, e1);
+            ConvEpilogue e2;
+            e2.out_scale = 0.1f; e2.res = x.p; e2.ldr = F;
+            Act y = conv(p + ".conv.proj.weight", p + ".conv.proj.bias", h, nullptr, F, 3, CONV_TAPS, e2);
+            free_act(h);
+            if (!x_is_r) free_act(x);
+            x_is_r = false;
+            x = y;
+            note(p, x);
+        }
+        ConvEpilogue et;
+        et.res = r.p; et.ldr = F;
+        Act bt = conv("body_tail.weight", "body_tail.bias", x, nullptr, F, 3, CONV_TAPS, et);
+        if (!x_is_r) free_act(x);
+        free_act(r);
+        note("body_tail", bt);
+        ConvEpilogue eo;
+        eo.out_f32 = dry ? reinterpret_cast<float*>(1) : ex->eps;
+        eo.n_valid = 1;
+        conv("tail.weight", "tail.bias", bt, nullptr, 1, 3, CONV_TAPS, eo, 16);
+        free_act(bt);
+    }
+
+    void build() {
+        if (P->hicedrn) build_hicedrn(); else build_unet();
+    }
+};
+
+int ensure_device(hd_plan* P) {
+    CUDA_TRY(cudaSetDevice(P->device));
+    return 0;
+}
+
+void free_exec(Exec* ex) {
+    if (ex->g_eps) cudaGraphExecDestroy(ex->g_eps);
+    if (ex->g_step) cudaGraphExecDestroy(ex->g_step);
+    cudaFree(ex->arena); cudaFree(ex->x); cudaFree(ex->cond); cudaFree(ex->eps); cudaFree(ex->time);
+    cudaFree(ex->posenc); cudaFree(ex->temb0); cudaFree(ex->temb); cudaFree(ex->film_rows); cudaFree(ex->iota);
+    cudaFree(ex->ctx);
+}
+
+int run_ops(const std::vector<Op>& ops, cudaStream_t s) {
+    for (const Op& op : ops) {
+        cudaError_t e = op.fn(s);
+        if (e != cudaSuccess) return fail("launch of '%s' failed: %s", op.tag.c_str(), cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+int capture(const std::vector<Op>& ops, cudaStream_t s, cudaGraphExec_t* out) {
+    CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    int rc = run_ops(ops, s);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(s, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int get_exec(hd_plan* P, int B, cudaStream_t s, Exec** out) {
+    if (!P->finalized) return fail("hd_plan_finalize has not been called");
+    if (B <= 0) return fail("batch size must be positive (got %d)", B);
+    auto it = P->execs.find(B);
+    if (it != P->execs.end()) { *out = it->second.get(); return 0; }
+    std::unique_ptr<Exec> ex(new Exec());
+    ex->B = B;
+    const int S = P->cfg.image_size;
+    const size_t tile = static_cast<size_t>(S) * S;
+
+    // dry run sizes the arena
+    {
+        Builder d{P, ex.get(), B, true};
+        d.arena.never_free = P->cfg.debug_keep != 0;
+        std::vector<Op> none;
+        d.ops = &none;
+        d.film = FilmRef{nullptr, nullptr, 0};
+        d.build();
+        if (!d.ok) return fail("%s", d.err.c_str());
+        ex->arena_bytes = d.arena.high;
+    }
+    auto cleanup_fail = [&](int rc) { free_exec(ex.get()); return rc; };
+#define EX_TRY(expr)                                                                                      \
+    do {                                                                                                  \
+        cudaError_t e__ = (expr);                                                                         \
+        if (e__ != cudaSuccess) return cleanup_fail(fail("%s failed: %s", #expr, cudaGetErrorString(e__))); \
+    } while (0)
+    EX_TRY(cudaMalloc(&ex->arena, ex->arena_bytes));
+    EX_TRY(cudaMalloc(&ex->x, B * tile * 4));
+    EX_TRY(cudaMalloc(&ex->cond, B * tile * 4));
+    EX_TRY(cudaMalloc(&ex->eps, B * tile * 4));
+    EX_TRY(cudaMalloc(&ex->time, B * 4));
+    EX_TRY(cudaMalloc(&ex->posenc, static_cast<size_t>(B) * P->fourier_dim * 4));
+    EX_TRY(cudaMalloc(&ex->temb0, static_cast<size_t>(B) * P->time_dim * 4));
+    EX_TRY(cudaMalloc(&ex->temb, static_cast<size_t>(B) * P->time_dim * 4));
+    EX_TRY(cudaMalloc(&ex->film_rows, static_cast<size_t>(B) * P->film_ld * 4));
+    EX_TRY(cudaMalloc(&ex->iota, B * 4));
+    EX_TRY(cudaMalloc(&ex->ctx, static_cast<size_t>(B) * 4 * 32 * 32 * 4));
+    EX_TRY(cudaMemsetAsync(ex->x, 0, B * tile * 4, s));
+    EX_TRY(cudaMemsetAsync(ex->cond, 0, B * tile * 4, s));
+    EX_TRY(cudaMemsetAsync(ex->time, 0, B * 4, s));
+    ex->extra_bytes = 3 * B * tile * 4 + static_cast<size_t>(B) * (P->fourier_dim + 2 * P->time_dim + P->film_ld + 2 + 4096) * 4;
+    {
+        std::vector<int> h(B);
+        for (int i = 0; i < B; ++i) h[i] = i;
+        EX_TRY(cudaMemcpyAsync(ex->iota, h.data(), B * 4, cudaMemcpyHostToDevice, s));
+        EX_TRY(cudaStreamSynchronize(s));
+    }
+
+    // rows mode: time embedding evaluated per call for B rows (Unet.forward with arbitrary `time`)
+    if (enqueue_film(P, ex->time, B, ex->posenc, ex->temb0, ex->temb, ex->film_rows, &ex->ops_rows)) return cleanup_fail(1);
+    {
+        Builder b{P, ex.get(), B, false};
+        b.arena.never_free = P->cfg.debug_keep != 0;
+        b.ops = &ex->ops_rows;
+        b.film = FilmRef{ex->film_rows, ex->iota, 1};
+        b.build();
+        if (!b.ok) return cleanup_fail(fail("%s", b.err.c_str()));
+    }
+    // table mode: FiLM row picked by the device step counter; + posterior update + counter decrement
+    {
+        Builder b{P, ex.get(), B, false};
+        b.arena.never_free = P->cfg.debug_keep != 0;
+        b.ops = &ex->ops_table;
+        b.film = FilmRef{P->film_table, &P->ctl->step, 0};
+        const bool keep = P->cfg.debug_keep != 0;
+        P->cfg.debug_keep = 0;   // debug names refer to the rows-mode graph
+        b.build();
+        P->cfg.debug_keep = keep ? 1 : 0;
+        if (!b.ok) return cleanup_fail(fail("%s", b.err.c_str()));
+        PosteriorArgs pa;
+        pa.x = ex->x; pa.eps = ex->eps; pa.coef = P->coef; pa.ctl = P->ctl; pa.T = P->T;
+        pa.n = static_cast<long long>(B) * tile; pa.tile_elems = static_cast<int>(tile); pa.x0_out = nullptr;
+        ex->ops_table.push_back({[pa](cudaStream_t st) { return posterior_step_run(pa, st); }, "posterior"});
+        SampleCtl* ctl = P->ctl;
+        ex->ops_table.push_back({[ctl](cudaStream_t st) { return step_advance_run(ctl, -1, st); }, "step--"});
+    }
+    // eager validation pass (surfaces launch-configuration errors with the op name), then capture
+    {
+        SampleCtl h;
+        memset(&h, 0, sizeof(h));
+        h.step = 0;
+        EX_TRY(cudaMemcpyAsync(P->ctl, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+        if (run_ops(ex->ops_rows, s)) return cleanup_fail(1);
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return cleanup_fail(fail("eps-net validation run failed: %s", cudaGetErrorString(e)));
+        if (run_ops(ex->ops_table, s)) return cleanup_fail(1);
+        e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return cleanup_fail(fail("sampling-step validation run failed: %s", cudaGetErrorString(e)));
+        if (capture(ex->ops_rows, s, &ex->g_eps)) return cleanup_fail(1);
+        if (capture(ex->ops_table, s, &ex->g_step)) return cleanup_fail(1);
+    }
+#undef EX_TRY
+    *out = ex.get();
+    P->execs[B] = std::move(ex);
+    return 0;
+}
+
+int set_ctl(SampleCtl* dev, int step, int single, const float* noise, uint64_t seed, uint64_t tile_offset,
+            cudaStream_t s) {
+    SampleCtl h;
+    memset(&h, 0, sizeof(h));
+    h.step = step; h.noise_single = single; h.noise = noise; h.seed = seed; h.tile_offset = tile_offset;
+    CUDA_TRY(cudaMemcpyAsync(dev, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================= C ABI
+extern "C" {
+
+const char* hd_last_error(void) { return g_err.c_str(); }
+int hd_abi_version(void) { return HD_ABI_VERSION; }
+
+int hd_plan_create(const hd_config* cfg, hd_plan** out) {
+    if (!cfg || !out) return fail("hd_plan_create: null argument");
+    if (cfg->abi_version != HD_ABI_VERSION) return fail("ABI version mismatch: header %d, library %d", cfg->abi_version, HD_ABI_VERSION);
+    if (cfg->variant < HD_UNET || cfg->variant > HD_HICEDRN_SR3) return fail("unknown variant %d", cfg->variant);
+    if (cfg->image_size != 64) return fail("image_size must be 64 (the reference's piece_size); got %d", cfg->image_size);
+    if (cfg->timesteps <= 0) return fail("timesteps must be positive");
+    const bool hic = cfg->variant == HD_HICEDRN || cfg->variant == HD_HICEDRN_SR3;
+    if (!hic) {
+        if (cfg->dim <= 0 || cfg->dim % 64 != 0) return fail("Unet dim must be a positive multiple of 64 (got %d)", cfg->dim);
+        if (cfg->num_mults < 1 || cfg->num_mults > 4) return fail("len(dim_mults) must be 1..4 for 64x64 tiles (got %d)", cfg->num_mults);
+        for (int i = 0; i < cfg->num_mults; ++i)
+            if (cfg->dim_mults[i] < 1 || cfg->dim * cfg->dim_mults[i] > 512)
+                return fail("dim * dim_mults[%d] = %d exceeds the supported 512 channels", i, cfg->dim * cfg->dim_mults[i]);
+    } else if (cfg->num_blocks < 1) {
+        return fail("HiCEDRN needs num_blocks >= 1");
+    }
+    int dev = 0, cc_major = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (cc_major != 10) return fail("hicdiff_b200 needs an sm_100a GPU (compute capability 10.x); device %d is %d.x", dev, cc_major);
+    hd_plan* P = new hd_plan();
+    P->cfg = *cfg;
+    P->device = dev;
+    P->num_sms = sms;
+    P->sr3 = cfg->variant == HD_UNET_SR3 || cfg->variant == HD_HICEDRN_SR3;
+    P->hicedrn = hic;
+    P->T = cfg->timesteps;
+    P->fourier_dim = hic ? 256 : cfg->dim;
+    P->time_dim = hic ? 1024 : cfg->dim * 4;
+    *out = P;
+    return 0;
+}
+
+int hd_plan_set_weight(hd_plan* P, const char* key, const float* dev_ptr, const int64_t* shape, int32_t ndim, void* stream) {
+    if (!P || !key || !dev_ptr || (ndim > 0 && !shape)) return fail("hd_plan_set_weight: null argument");
+    if (ensure_device(P)) return 1;
+    size_t numel = 1;
+    std::vector<int64_t> sh;
+    for (int i = 0; i < ndim; ++i) { numel *= static_cast<size_t>(shape[i]); sh.push_back(shape[i]); }
+    WeightT& w = P->w[key];
+    if (w.d != nullptr && w.numel != numel) { cudaFree(w.d); w.d = nullptr; P->weight_bytes -= w.numel * 4; }
+    if (w.d == nullptr) { CUDA_TRY(cudaMalloc(&w.d, numel * 4)); P->weight_bytes += numel * 4; }
+    w.shape = sh;
+    w.numel = numel;
+    CUDA_TRY(cudaMemcpyAsync(w.d, dev_ptr, numel * 4, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    P->finalized = false;
+    return 0;
+}
+
+int hd_plan_set_schedule(hd_plan* P, const float* sqrt_recip, const float* sqrt_recipm1, const float* coef1,
+                         const float* coef2, const float* sigma, const float* time_values, int32_t T, void* stream) {
+    if (!P || !sqrt_recip || !sqrt_recipm1 || !coef1 || !coef2 || !sigma || !time_values) return fail("hd_plan_set_schedule: null argument");
+    if (T != P->T) return fail("schedule length %d does not match the plan's timesteps %d", T, P->T);
+    if (ensure_device(P)) return 1;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!P->coef) { CUDA_TRY(cudaMalloc(&P->coef, static_cast<size_t>(T) * 8 * 4)); }
+    if (!P->time_values) { CUDA_TRY(cudaMalloc(&P->time_values, static_cast<size_t>(T) * 4)); }
+    CUDA_TRY(cudaMemsetAsync(P->coef, 0, static_cast<size_t>(T) * 8 * 4, s));
+    const float* cols[5] = {sqrt_recip, sqrt_recipm1, coef1, coef2, sigma};
+    for (int c = 0; c < 5; ++c)
+        CUDA_TRY(cudaMemcpy2DAsync(P->coef + c, 8 * 4, cols[c], 4, 4, T, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(P->time_values, time_values, static_cast<size_t>(T) * 4, cudaMemcpyDeviceToDevice, s));
+    P->finalized = false;
+    return 0;
+}
+
+int hd_plan_finalize(hd_plan* P, void* stream) {
+    if (!P) return fail("hd_plan_finalize: null plan");
+    if (ensure_device(P)) return 1;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!P->coef) return fail("hd_plan_set_schedule must be called before hd_plan_finalize");
+    // drop executors built against older weights
+    for (auto& kv : P->execs) free_exec(kv.second.get());
+    P->execs.clear();
+
+    // ---- FiLM slots (one per ResnetBlock, in module order)
+    P->film.clear();
+    P->film_index.clear();
+    std::vector<std::pair<std::string, int>> blocks;   // prefix, Cout
+    if (P->hicedrn) {
+        for (int i = 0; i < P->cfg.num_blocks; ++i) blocks.push_back({"body." + std::to_string(i), 256});
+    } else {
+        const hd_config& c = P->cfg;
+        std::vector<int> dims;
+        dims.push_back(c.dim);
+        for (int i = 0; i < c.num_mults; ++i) dims.push_back(c.dim * c.dim_mults[i]);
+        const int L = c.num_mults;
+        for (int i = 0; i < L; ++i) {
+            blocks.push_back({"downs." + std::to_string(i) + ".0", dims[i]});
+            blocks.push_back({"downs." + std::to_string(i) + ".1", dims[i]});
+        }
+        blocks.push_back({"mid_block1", dims[L]});
+        blocks.push_back({"mid_block2", dims[L]});
+        for (int k = 0; k < L; ++k) {
+            blocks.push_back({"ups." + std::to_string(k) + ".0", dims[L - k]});
+            blocks.push_back({"ups." + std::to_string(k) + ".1", dims[L - k]});
+        }
+        blocks.push_back({"final_res_block", c.dim});
+    }
+    int off = 0;
+    for (auto& b : blocks) {
+        FilmSlot f;
+        if (P->sr3) {
+            f.wkey = b.first + ".noise_func.noise_func.0.weight";
+            f.bkey = b.first + ".noise_func.noise_func.0.bias";
+            f.width = b.second;
+            f.silu_in = false;
+        } else {
+            f.wkey = b.first + ".mlp.1.weight";
+            f.bkey = b.first + ".mlp.1.bias";
+            f.width = 2 * b.second;
+            f.silu_in = true;
+        }
+        f.off = off;
+        off += f.width;
+        const WeightT* fw = find_w(P, f.wkey);
+        if (!fw) return fail("weight '%s' missing (did you call hd_plan_set_weight for every state_dict entry?)", f.wkey.c_str());
+        if (fw->shape.size() != 2 || fw->shape[0] != f.width || fw->shape[1] != P->time_dim)
+            return fail("weight '%s' has an unexpected shape", f.wkey.c_str());
+        P->film_index[b.first] = static_cast<int>(P->film.size());
+        P->film.push_back(f);
+    }
+    P->film_ld = off;
+
+    // ---- GEMM-layout weights
+    for (auto& kv : P->wq) cudaFree(kv.second);
+    P->wq.clear();
+    for (auto& kv : P->padded) cudaFree(kv.second);
+    P->padded.clear();
+    size_t wq_bytes = 0;
+    for (auto& kv : P->w) {
+        const std::string& key = kv.first;
+        const WeightT& w = kv.second;
+        if (w.shape.size() != 4 || !ends_with(key, ".weight")) continue;
+        const int Cout = static_cast<int>(w.shape[0]), Cin = static_cast<int>(w.shape[1]), k = static_cast<int>(w.shape[2]);
+        if (Cin < 64 || key == "final_conv.weight") continue;   // stem / 1x1 head run on dedicated kernels
+        if (Cin % 64 != 0) return fail("conv weight '%s': Cin = %d is not a multiple of 64", key.c_str(), Cin);
+        const int Npad = Cout < 16 ? 16 : Cout;
+        bf16* q = nullptr;
+        const size_t bytes = static_cast<size_t>(Npad) * Cin * k * k * 2;
+        CUDA_TRY(cudaMalloc(&q, bytes));
+        wq_bytes += bytes;
+        P->wq[key] = q;
+        const bool is_down = !P->hicedrn && key.compare(0, 6, "downs.") == 0 && ends_with(key, ".3.1.weight");
+        if (is_down) {
+            if (k != 1 || Cin % 4 != 0) return fail("Downsample weight '%s' has an unexpected shape", key.c_str());
+            CUDA_TRY(prep_unshuffle_weight_run(w.d, q, Cout, Cin / 4, s));
+        } else {
+            const int standardize = (!P->hicedrn && ends_with(key, ".proj.weight")) ? 1 : 0;
+            CUDA_TRY(prep_conv_weight_run(w.d, q, Cout, Cin, k, standardize, 1e-5f, Npad, s));
+        }
+        if (Npad != Cout) {
+            const std::string bkey = key.substr(0, key.size() - 6) + "bias";
+            const WeightT* b = find_w(P, bkey);
+            if (b) {
+                float* pb = nullptr;
+                CUDA_TRY(cudaMalloc(&pb, Npad * 4));
+                CUDA_TRY(cudaMemsetAsync(pb, 0, Npad * 4, s));
+                CUDA_TRY(cudaMemcpyAsync(pb, b->d, Cout * 4, cudaMemcpyDeviceToDevice, s));
+                P->padded[bkey] = pb;
+            }
+        }
+    }
+
+    // ---- control blocks + [T, film_ld] table
+    if (!P->ctl) { CUDA_TRY(cudaMalloc(&P->ctl, sizeof(SampleCtl))); CUDA_TRY(cudaMemsetAsync(P->ctl, 0, sizeof(SampleCtl), s)); }
+    if (!P->ctl_one) { CUDA_TRY(cudaMalloc(&P->ctl_one, sizeof(SampleCtl))); CUDA_TRY(cudaMemsetAsync(P->ctl_one, 0, sizeof(SampleCtl), s)); }
+    if (P->film_table) { cudaFree(P->film_table); P->film_table = nullptr; }
+    CUDA_TRY(cudaMalloc(&P->film_table, static_cast<size_t>(P->T) * P->film_ld * 4));
+    {
+        float *pe = nullptr, *t0 = nullptr, *t1 = nullptr;
+        CUDA_TRY(cudaMalloc(&pe, static_cast<size_t>(P->T) * P->fourier_dim * 4));
+        CUDA_TRY(cudaMalloc(&t0, static_cast<size_t>(P->T) * P->time_dim * 4));
+        CUDA_TRY(cudaMalloc(&t1, static_cast<size_t>(P->T) * P->time_dim * 4));
+        std::vector<Op> ops;
+        int rc = enqueue_film(P, P->time_values, P->T, pe, t0, t1, P->film_table, &ops);
+        if (!rc) rc = run_ops(ops, s);
+        cudaError_t e = cudaStreamSynchronize(s);
+        cudaFree(pe); cudaFree(t0); cudaFree(t1);
+        if (rc) return rc;
+        if (e != cudaSuccess) return fail("time-embedding table build failed: %s", cudaGetErrorString(e));
+    }
+    P->weight_bytes += 0;
+    (void)wq_bytes;
+    P->finalized = true;
+    return 0;
+}
+
+void hd_plan_destroy(hd_plan* P) {
+    if (!P) return;
+    cudaSetDevice(P->device);
+    for (auto& kv : P->execs) free_exec(kv.second.get());
+    for (auto& kv : P->w) cudaFree(kv.second.d);
+    for (auto& kv : P->wq) cudaFree(kv.second);
+    for (auto& kv : P->padded) cudaFree(kv.second);
+    cudaFree(P->coef); cudaFree(P->time_values); cudaFree(P->film_table); cudaFree(P->ctl); cudaFree(P->ctl_one);
+    delete P;
+}
+
+int hd_eps_forward(hd_plan* P, const float* x, const float* cond, const float* time, float* eps, int32_t B, void* stream) {
+    if (!P || !x || !time || !eps) return fail("hd_eps_forward: null argument");
+    if (P->cfg.self_condition && !cond) return fail("hd_eps_forward: the plan is self-conditioned, cond must not be NULL");
+    if (ensure_device(P)) return 1;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Exec* ex = nullptr;
+    if (get_exec(P, B, s, &ex)) return 1;
+    const size_t bytes = static_cast<size_t>(B) * 4096 * 4;
+    CUDA_TRY(cudaMemcpyAsync(ex->x, x, bytes, cudaMemcpyDeviceToDevice, s));
+    if (cond) CUDA_TRY(cudaMemcpyAsync(ex->cond, cond, bytes, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(ex->time, time, B * 4, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaGraphLaunch(ex->g_eps, s));
+    CUDA_TRY(cudaMemcpyAsync(eps, ex->eps, bytes, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+int hd_ddpm_step(hd_plan* P, float* x, const float* eps, const float* noise, float* x0_out, int32_t t, int32_t B,
+                 uint64_t seed, uint64_t tile_offset, void* stream) {
+    if (!P || !x || !eps) return fail("hd_ddpm_step: null argument");
+    if (!P->coef || !P->ctl_one) return fail("hd_ddpm_step: plan not finalized");
+    if (t < 0 || t >= P->T) return fail("hd_ddpm_step: t = %d out of range [0, %d)", t, P->T);
+    if (ensure_device(P)) return 1;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (set_ctl(P->ctl_one, t, 1, noise, seed, tile_offset, s)) return 1;
+    PosteriorArgs pa;
+    pa.x = x; pa.eps = eps; pa.coef = P->coef; pa.ctl = P->ctl_one; pa.T = P->T;
+    pa.n = static_cast<long long>(B) * 4096; pa.tile_elems = 4096; pa.x0_out = x0_out;
+    CUDA_TRY(posterior_step_run(pa, s));
+    return 0;
+}
+
+int hd_sample(hd_plan* P, const float* cond, const float* noise, float* out, float* trace, int32_t B, uint64_t seed,
+              uint64_t tile_offset, int32_t t_start, int32_t t_end, void* stream) {
+    if (!P || !out) return fail("hd_sample: null argument");
+    if (P->cfg.self_condition && !cond) return fail("hd_sample: the plan is self-conditioned, cond must not be NULL");
+    if (t_start >= P->T || t_end < 0 || t_end > t_start) return fail("hd_sample: bad step range [%d, %d] for T = %d", t_start, t_end, P->T);
+    if (ensure_device(P)) return 1;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Exec* ex = nullptr;
+    if (get_exec(P, B, s, &ex)) return 1;
+    const size_t n = static_cast<size_t>(B) * 4096;
+    if (cond) CUDA_TRY(cudaMemcpyAsync(ex->cond, cond, n * 4, cudaMemcpyDeviceToDevice, s));
+    if (t_start == P->T - 1) {
+        if (noise) CUDA_TRY(cudaMemcpyAsync(ex->x, noise, n * 4, cudaMemcpyDeviceToDevice, s));
+        else CUDA_TRY(philox_normal_run(ex->x, static_cast<long long>(n), seed, tile_offset, 4096, 0, s));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(ex->x, out, n * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    if (set_ctl(P->ctl, t_start, 0, noise, seed, tile_offset, s)) return 1;
+    for (int t = t_start; t >= t_end; --t) {
+        CUDA_TRY(cudaGraphLaunch(ex->g_step, s));
+        if (trace) CUDA_TRY(cudaMemcpyAsync(trace + static_cast<size_t>(t_start - t) * n, ex->x, n * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    CUDA_TRY(cudaMemcpyAsync(out, ex->x, n * 4, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+int64_t hd_tile_count(int64_t n, int32_t piece, int32_t band_blocks) {
+    if (n < 0 || piece <= 0 || band_blocks < 0) return -1;
+    return tile_count(static_cast<int>(n), piece, band_blocks);
+}
+
+int hd_tile_extract(const float* mat, int64_t n, float* tiles, int32_t piece, int32_t band_blocks, void* stream) {
+    if (n < 0 || piece <= 0 || band_blocks < 0) return fail("hd_tile_extract: bad arguments");
+    if (n == 0) return 0;
+    if (!mat || !tiles) return fail("hd_tile_extract: null argument");
+    CUDA_TRY(tile_extract_run(mat, static_cast<int>(n), tiles, piece, band_blocks, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int hd_tile_scatter(const float* tiles, float* mat, int64_t n, int32_t piece, int32_t band_blocks, void* stream) {
+    if (n < 0 || piece <= 0 || band_blocks < 0) return fail("hd_tile_scatter: bad arguments");
+    if (n == 0) return 0;
+    if (!mat || !tiles) return fail("hd_tile_scatter: null argument");
+    CUDA_TRY(tile_scatter_run(tiles, mat, static_cast<int>(n), piece, band_blocks, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- single ops
+int hd_op_conv2d(const uint16_t* x0, int32_t C0, const uint16_t* x1, int32_t C1, const float* w, const float* bias,
+                 const uint16_t* res, uint16_t* out, int32_t B, int32_t H, int32_t W, int32_t Cout, int32_t ksize,
+                 int32_t mode, int32_t standardize, void* stream) {
+    if (!x0 || !w || !out) return fail("hd_op_conv2d: null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int Cin = C0 + (x1 ? C1 : 0);
+    const int taps = mode == CONV_UNSHUFFLE ? 4 : ksize * ksize;
+    bf16* q = nullptr;
+    CUDA_TRY(cudaMalloc(&q, static_cast<size_t>(Cout) * Cin * taps * 2));
+    cudaError_t e = mode == CONV_UNSHUFFLE ? prep_unshuffle_weight_run(w, q, Cout, Cin, s)
+                                           : prep_conv_weight_run(w, q, Cout, Cin, ksize, standardize, 1e-5f, Cout, s);
+    if (e != cudaSuccess) { cudaFree(q); return fail("weight prep failed: %s", cudaGetErrorString(e)); }
+    ConvGemmDesc d;
+    d.src0 = ConvSrc{reinterpret_cast<const bf16*>(x0), C0};
+    d.src1 = ConvSrc{reinterpret_cast<const bf16*>(x1), x1 ? C1 : 0};
+    d.B = B; d.H = H; d.W = W; d.ksize = ksize; d.mode = static_cast<ConvMode>(mode);
+    d.weight = q; d.N = Cout; d.out = reinterpret_cast<bf16*>(out);
+    d.epi.bias = bias;
+    if (res) { d.epi.res = reinterpret_cast<const bf16*>(res); d.epi.ldr = Cout; }
+    ConvGemmLaunch l;
+    char msg[256];
+    if (conv_gemm_prepare(d, sms, &l, msg, sizeof(msg))) { cudaFree(q); return fail("%s", msg); }
+    e = conv_gemm_run(l, s);
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    cudaFree(q);
+    if (e != cudaSuccess) return fail("conv launch failed: %s", cudaGetErrorString(e));
+    if (e2 != cudaSuccess) return fail("conv kernel failed: %s", cudaGetErrorString(e2));
+    return 0;
+}
+
+int hd_op_groupnorm_silu(const uint16_t* x, uint16_t* y, const float* gamma, const float* beta, const float* scale,
+                         const float* shift, const uint16_t* res, int32_t B, int32_t P, int32_t C, void* stream) {
+    if (!x || !y || !gamma || !beta) return fail("hd_op_groupnorm_silu: null argument");
+    if ((scale == nullptr) != (shift == nullptr)) return fail("hd_op_groupnorm_silu: scale and shift must come together");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    GroupNormArgs g;
+    g.x = reinterpret_cast<const bf16*>(x); g.y = reinterpret_cast<bf16*>(y);
+    g.B = B; g.P = P; g.C = C; g.gamma = gamma; g.beta = beta; g.eps = 1e-5f;
+    float* row = nullptr;
+    int* zero = nullptr;
+    if (scale) {   // pack [scale | shift] into one FiLM row
+        CUDA_TRY(cudaMalloc(&row, 2 * C * 4));
+        CUDA_TRY(cudaMalloc(&zero, 4));
+        CUDA_TRY(cudaMemsetAsync(zero, 0, 4, s));
+        CUDA_TRY(cudaMemcpyAsync(row, scale, C * 4, cudaMemcpyDeviceToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(row + C, shift, C * 4, cudaMemcpyDeviceToDevice, s));
+        g.film = row; g.film_row = zero; g.film_row_stride = 0; g.film_ld = 2 * C; g.film_off = 0;
+    }
+    if (res) g.res = reinterpret_cast<const bf16*>(res);
+    cudaError_t e = groupnorm_film_silu_run(g, s);
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    cudaFree(row); cudaFree(zero);
+    if (e != cudaSuccess) return fail("groupnorm launch failed: %s", cudaGetErrorString(e));
+    if (e2 != cudaSuccess) return fail("groupnorm kernel failed: %s", cudaGetErrorString(e2));
+    return 0;
+}
+
+int hd_op_channel_layernorm(const uint16_t* x, uint16_t* y, const float* g, const uint16_t* res, int32_t B, int32_t H,
+                            int32_t W, int32_t C, int32_t upsample2x, void* stream) {
+    if (!x || !y || !g) return fail("hd_op_channel_layernorm: null argument");
+    LayerNormArgs l;
+    l.x = reinterpret_cast<const bf16*>(x); l.y = reinterpret_cast<bf16*>(y); l.M = B * H * W; l.C = C; l.g = g;
+    l.eps = 1e-5f; l.res = reinterpret_cast<const bf16*>(res); l.upsample2x = upsample2x; l.H = H; l.W = W;
+    CUDA_TRY(channel_layernorm_run(l, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int hd_op_linear_attention(const uint16_t* qkv, uint16_t* out, int32_t B, int32_t n, void* stream) {
+    if (!qkv || !out) return fail("hd_op_linear_attention: null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float* ctx = nullptr;
+    CUDA_TRY(cudaMalloc(&ctx, static_cast<size_t>(B) * 4 * 32 * 32 * 4));
+    LinAttnArgs a;
+    a.qkv = reinterpret_cast<const bf16*>(qkv); a.out = reinterpret_cast<bf16*>(out); a.ctx = ctx; a.B = B; a.n = n;
+    cudaError_t e = linear_attention_run(a, s);
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    cudaFree(ctx);
+    if (e != cudaSuccess) return fail("linear attention launch failed: %s", cudaGetErrorString(e));
+    if (e2 != cudaSuccess) return fail("linear attention kernel failed: %s", cudaGetErrorString(e2));
+    return 0;
+}
+
+int hd_op_full_attention(const uint16_t* qkv, uint16_t* out, int32_t B, int32_t n, void* stream) {
+    if (!qkv || !out) return fail("hd_op_full_attention: null argument");
+    FullAttnArgs a;
+    a.qkv = reinterpret_cast<const bf16*>(qkv); a.out = reinterpret_cast<bf16*>(out); a.B = B; a.n = n;
+    CUDA_TRY(full_attention_run(a, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int hd_op_stem_conv(const float* x0, const float* x1, const float* w, const float* bias, uint16_t* y, int32_t B,
+                    int32_t Cout, int32_t Cin, int32_t ksize, void* stream) {
+    if (!x0 || !w || !bias || !y) return fail("hd_op_stem_conv: null argument");
+    StemConvArgs a;
+    a.x0 = x0; a.x1 = x1; a.w = w; a.bias = bias; a.y = reinterpret_cast<bf16*>(y);
+    a.B = B; a.H = 64; a.W = 64; a.Cout = Cout; a.Cin = Cin; a.ksize = ksize;
+    CUDA_TRY(stem_conv_run(a, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int hd_op_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t tile_offset, void* stream) {
+    if (!out) return fail("hd_op_philox_normal: null argument");
+    CUDA_TRY(philox_normal_run(out, n, seed, tile_offset, 4096, 0, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- debug / stats
+namespace {
+__global__ void nhwc_bf16_to_nchw_f32(const bf16* x, float* y, int B, int H, int W, int C) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(B) * H * W * C;
+    if (i >= total) return;
+    const int c = static_cast<int>(i % C);
+    const long long p = i / C;
+    const int w = static_cast<int>(p % W);
+    const int h = static_cast<int>((p / W) % H);
+    const int b = static_cast<int>(p / (static_cast<long long>(W) * H));
+    y[((static_cast<long long>(b) * C + c) * H + h) * W + w] = __bfloat162float(x[i]);
+}
+}  // namespace
+
+int hd_debug_read(hd_plan* P, int32_t B, const char* name, float* out, int64_t* numel, int32_t* shape4, void* stream) {
+    if (!P || !name) return fail("hd_debug_read: null argument");
+    auto it = P->execs.find(B);
+    if (it == P->execs.end()) return fail("hd_debug_read: no executor for batch %d (run hd_eps_forward first)", B);
+    auto d = it->second->dbg.find(name);
+    if (d == it->second->dbg.end()) return fail("hd_debug_read: unknown activation '%s' (is cfg.debug_keep set?)", name);
+    const DebugEntry& e = d->second;
+    const long long total = static_cast<long long>(B) * e.H * e.W * e.C;
+    if (numel) *numel = total;
+    if (shape4) { shape4[0] = B; shape4[1] = e.C; shape4[2] = e.H; shape4[3] = e.W; }
+    if (out) {
+        const int grid = static_cast<int>((total + 255) / 256);
+        nhwc_bf16_to_nchw_f32<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(e.p, out, B, e.H, e.W, e.C);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
+int hd_debug_names(hd_plan* P, int32_t B, char* buf, int64_t buflen) {
+    if (!P || !buf || buflen <= 0) return fail("hd_debug_names: null argument");
+    auto it = P->execs.find(B);
+    if (it == P->execs.end()) return fail("hd_debug_names: no executor for batch %d", B);
+    std::string all;
+    for (const std::string& n : it->second->dbg_order) { all += n; all += '\n'; }
+    if (static_cast<int64_t>(all.size()) + 1 > buflen) return fail("hd_debug_names: buffer too small (%zu needed)", all.size() + 1);
+    memcpy(buf, all.c_str(), all.size() + 1);
+    return 0;
+}
+
+int hd_plan_launches_per_step(hd_plan* P, int32_t B, int32_t* eps_launches, int32_t* step_launches) {
+    if (!P) return fail("null plan");
+    auto it = P->execs.find(B);
+    if (it == P->execs.end()) return fail("no executor for batch %d yet", B);
+    // linear attention is two kernels behind one op
+    auto count = [](const std::vector<Op>& ops) {
+        int n = 0;
+        for (const Op& o : ops) n += ends_with(o.tag, ".linattn") ? 2 : 1;
+        return n;
+    };
+    if (eps_launches) *eps_launches = count(it->second->ops_rows);
+    if (step_launches) *step_launches = count(it->second->ops_table);
+    return 0;
+}
+
+int64_t hd_plan_device_bytes(hd_plan* P) {
+    if (!P) return 0;
+    size_t total = P->weight_bytes;
+    for (auto& kv : P->w) {
+        auto q = P->wq.find(kv.first);
+        if (q != P->wq.end()) total += kv.second.numel * 2;
+    }
+    total += static_cast<size_t>(P->T) * (P->film_ld + 9) * 4;
+    for (auto& kv : P->execs) total += kv.second->arena_bytes + kv.second->extra_bytes;
+    return static_cast<int64_t>(total);
+}
+
+}  // extern "C"

@@ -1,0 +1,256 @@
+// Small bandwidth-bound kernels around the eps-predictor.
+//
+// stem_conv       Unet.init_conv (7x7, pad 3) incl. torch.cat((x_self_cond, x), 1)
+//                   /root/reference/src/hicdiff_condition.py:279,348-350
+//                 hicedrn_Diff.head (3x3, pad 1)  /root/reference/src/model/hicedrn_Diff.py:227,273-275
+//                 Cin is 1 or 2 fp32 planes, so this is a direct convolution (K = 98 or 18 is too thin for UMMA).
+// head_conv1x1    Unet.final_conv (64 -> 1)  hicdiff_condition.py:343,384
+// posterior_step  p_mean_variance + p_sample   hicdiff_condition.py:526-530,550-557,581-598
+//                   x0 = sqrt_recip_ac[t]*x - sqrt_recipm1_ac[t]*eps ; clamp(-1,1)
+//                   mean = coef1[t]*x0 + coef2[t]*x ; x <- mean + exp(0.5*logvar[t]) * z   (z = 0 at t == 0)
+//                 t comes from a DEVICE step counter so one captured CUDA graph replays for all T steps.
+// philox_normal   counter-based N(0,1) stream keyed by (seed, global tile id, step) -> results do not depend on
+//                 how tiles are sharded over GPUs.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace hd {
+namespace {
+
+// ------------------------------------------------------------------------------------------ stem conv
+constexpr int STEM_THREADS = 256;
+constexpr int STEM_W = 64;          // tiles are 64 x 64 (the reference's piece_size)
+constexpr int STEM_CO_STEP = 16;    // output channels accumulated per pass
+
+__global__ void __launch_bounds__(STEM_THREADS)
+stem_conv_kernel(const StemConvArgs a) {
+    extern __shared__ float stem_smem[];
+    const int k = a.ksize;
+    const int pad = k / 2;
+    const int taps = a.Cin * k * k;
+    const int WP = STEM_W + 2 * pad;
+    float* s_w = stem_smem;                        // [taps][Cout]
+    float* s_x = stem_smem + taps * a.Cout;        // [Cin][k][WP]
+    const int b = blockIdx.x / a.H;
+    const int h = blockIdx.x - b * a.H;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < taps * a.Cout; i += STEM_THREADS) {
+        const int co = i / taps;
+        const int t = i - co * taps;
+        s_w[t * a.Cout + co] = __ldg(a.w + i);     // transpose [Cout][taps] -> [taps][Cout]
+    }
+    for (int i = tid; i < a.Cin * k * WP; i += STEM_THREADS) {
+        const int ci = i / (k * WP);
+        const int rem = i - ci * k * WP;
+        const int ky = rem / WP;
+        const int xx = rem - ky * WP - pad;
+        const int yy = h + ky - pad;
+        const float* plane = ci == 0 ? a.x0 : a.x1;
+        float v = 0.f;
+        if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) v = __ldg(plane + (static_cast<size_t>(b) * a.H + yy) * a.W + xx);
+        s_x[i] = v;
+    }
+    __syncthreads();
+
+    const int w = tid & (STEM_W - 1);
+    const int cg = tid / STEM_W;                          // 0..3
+    const int co_per_thread = a.Cout / (STEM_THREADS / STEM_W);
+    bf16* yrow = a.y + ((static_cast<size_t>(b) * a.H + h) * a.W + w) * a.Cout;
+    for (int cbase = cg * co_per_thread; cbase < (cg + 1) * co_per_thread; cbase += STEM_CO_STEP) {
+        float acc[STEM_CO_STEP];
+#pragma unroll
+        for (int j = 0; j < STEM_CO_STEP; j += 4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + cbase + j));
+            acc[j] = bb.x; acc[j + 1] = bb.y; acc[j + 2] = bb.z; acc[j + 3] = bb.w;
+        }
+        int t = 0;
+        for (int ci = 0; ci < a.Cin; ++ci)
+            for (int ky = 0; ky < k; ++ky)
+                for (int kx = 0; kx < k; ++kx, ++t) {
+                    const float xv = s_x[(ci * k + ky) * WP + w + kx];
+                    const float* wp = s_w + t * a.Cout + cbase;
+#pragma unroll
+                    for (int j = 0; j < STEM_CO_STEP; j += 4) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(wp + j);
+                        acc[j] = fmaf(xv, w4.x, acc[j]);
+                        acc[j + 1] = fmaf(xv, w4.y, acc[j + 1]);
+                        acc[j + 2] = fmaf(xv, w4.z, acc[j + 2]);
+                        acc[j + 3] = fmaf(xv, w4.w, acc[j + 3]);
+                    }
+                }
+        uint4* op = reinterpret_cast<uint4*>(yrow + cbase);
+#pragma unroll
+        for (int j = 0; j < STEM_CO_STEP; j += 8) {
+            uint4 o;
+            o.x = ptx::pack_bf16x2(acc[j], acc[j + 1]);
+            o.y = ptx::pack_bf16x2(acc[j + 2], acc[j + 3]);
+            o.z = ptx::pack_bf16x2(acc[j + 4], acc[j + 5]);
+            o.w = ptx::pack_bf16x2(acc[j + 6], acc[j + 7]);
+            op[j / 8] = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ 1x1 head
+__global__ void __launch_bounds__(256)
+head_conv1x1_kernel(const HeadConvArgs a) {
+    const int lanes_per_pixel = a.C / 8;   // 8 for C = 64
+    const long long gt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long m = gt / lanes_per_pixel;
+    const int part = static_cast<int>(gt - m * lanes_per_pixel);
+    float acc = 0.f;
+    if (m < a.M) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(a.x + m * a.C + part * 8));
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w + part * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.w + part * 8 + 4));
+        float2 t;
+        t = ptx::unpack_bf16x2(u.x); acc = fmaf(t.x, w0.x, acc); acc = fmaf(t.y, w0.y, acc);
+        t = ptx::unpack_bf16x2(u.y); acc = fmaf(t.x, w0.z, acc); acc = fmaf(t.y, w0.w, acc);
+        t = ptx::unpack_bf16x2(u.z); acc = fmaf(t.x, w1.x, acc); acc = fmaf(t.y, w1.y, acc);
+        t = ptx::unpack_bf16x2(u.w); acc = fmaf(t.x, w1.z, acc); acc = fmaf(t.y, w1.w, acc);
+    }
+    for (int off = lanes_per_pixel >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (m < a.M && part == 0) a.eps[m] = acc + __ldg(a.bias);
+}
+
+// ------------------------------------------------------------------------------------------ Philox4x32-10
+struct Philox {
+    uint32_t c[4];
+    uint32_t k[2];
+};
+__device__ __forceinline__ void philox_round(Philox& p) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    const uint32_t hi0 = __umulhi(M0, p.c[0]), lo0 = M0 * p.c[0];
+    const uint32_t hi1 = __umulhi(M1, p.c[2]), lo1 = M1 * p.c[2];
+    const uint32_t n0 = hi1 ^ p.c[1] ^ p.k[0];
+    const uint32_t n2 = hi0 ^ p.c[3] ^ p.k[1];
+    p.c[0] = n0; p.c[1] = lo1; p.c[2] = n2; p.c[3] = lo0;
+    p.k[0] += 0x9E3779B9u; p.k[1] += 0xBB67AE85u;
+}
+// 4 standard normals for (seed, tile, quad-within-tile, stream id)
+__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned long long tile, uint32_t quad,
+                                                 uint32_t stream_id) {
+    Philox p;
+    p.c[0] = quad;
+    p.c[1] = stream_id;
+    p.c[2] = static_cast<uint32_t>(tile);
+    p.c[3] = static_cast<uint32_t>(tile >> 32);
+    p.k[0] = static_cast<uint32_t>(seed);
+    p.k[1] = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) philox_round(p);
+    const float two_pow_m32 = 2.3283064365386963e-10f;
+    const float u0 = (static_cast<float>(p.c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1), 24 bits
+    const float u1 = static_cast<float>(p.c[1]) * two_pow_m32;
+    const float u2 = (static_cast<float>(p.c[2] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u3 = static_cast<float>(p.c[3]) * two_pow_m32;
+    const float r0 = sqrtf(-2.0f * __logf(u0));
+    const float r1 = sqrtf(-2.0f * __logf(u2));
+    float s0, c0, s1, c1;
+    __sincosf(6.283185307179586f * u1, &s0, &c0);
+    __sincosf(6.283185307179586f * u3, &s1, &c1);
+    return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+}
+
+__global__ void __launch_bounds__(256)
+philox_normal_kernel(float* out, long long n, unsigned long long seed, unsigned long long tile_offset, int tile_elems,
+                     unsigned long long stream_id) {
+    const long long i4 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= n) return;
+    const unsigned long long tile = tile_offset + static_cast<unsigned long long>(i4 / tile_elems);
+    const uint32_t quad = static_cast<uint32_t>((i4 % tile_elems) >> 2);
+    const float4 z = philox_normal4(seed, tile, quad, static_cast<uint32_t>(stream_id));
+    *reinterpret_cast<float4*>(out + i4) = z;
+}
+
+// ------------------------------------------------------------------------------------------ posterior
+__global__ void __launch_bounds__(256)
+posterior_step_kernel(const PosteriorArgs a) {
+    const long long i4 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= a.n) return;
+    const int t = a.ctl->step;
+    const float* noise = a.ctl->noise;
+    const float* cf = a.coef + static_cast<size_t>(t) * 8;
+    const float c_recip = __ldg(cf + 0), c_recipm1 = __ldg(cf + 1), c1 = __ldg(cf + 2), c2 = __ldg(cf + 3),
+                sigma = __ldg(cf + 4);
+    const float4 x = *reinterpret_cast<const float4*>(a.x + i4);
+    const float4 e = *reinterpret_cast<const float4*>(a.eps + i4);
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t > 0) {
+        if (noise != nullptr) {
+            const size_t row = a.ctl->noise_single ? 0 : static_cast<size_t>(a.T - t);
+            z = __ldg(reinterpret_cast<const float4*>(noise + row * a.n + i4));
+        } else {
+            const unsigned long long tile = a.ctl->tile_offset + static_cast<unsigned long long>(i4 / a.tile_elems);
+            const uint32_t quad = static_cast<uint32_t>((i4 % a.tile_elems) >> 2);
+            z = philox_normal4(a.ctl->seed, tile, quad, static_cast<uint32_t>(t) + 1u);
+        }
+    }
+    const float xs[4] = {x.x, x.y, x.z, x.w};
+    const float es[4] = {e.x, e.y, e.z, e.w};
+    const float zs[4] = {z.x, z.y, z.z, z.w};
+    float o[4], x0s[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        // Same operation order as the reference (two roundings, no fused multiply-add) so fp32 results agree
+        // with torch bit-for-bit when eps is identical.
+        float x0 = __fsub_rn(__fmul_rn(c_recip, xs[j]), __fmul_rn(c_recipm1, es[j]));
+        x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+        const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xs[j]));
+        o[j] = __fadd_rn(mean, __fmul_rn(sigma, zs[j]));
+        x0s[j] = x0;
+    }
+    *reinterpret_cast<float4*>(a.x + i4) = make_float4(o[0], o[1], o[2], o[3]);
+    if (a.x0_out != nullptr) *reinterpret_cast<float4*>(a.x0_out + i4) = make_float4(x0s[0], x0s[1], x0s[2], x0s[3]);
+}
+
+__global__ void step_advance_kernel(SampleCtl* ctl, int delta) { ctl->step += delta; }
+
+}  // namespace
+
+cudaError_t stem_conv_run(const StemConvArgs& a, cudaStream_t s) {
+    if (a.W != STEM_W || a.Cout % (STEM_CO_STEP * (STEM_THREADS / STEM_W)) != 0 || a.Cin < 1 || a.Cin > 2)
+        return cudaErrorInvalidValue;
+    const int pad = a.ksize / 2;
+    const int taps = a.Cin * a.ksize * a.ksize;
+    const size_t smem = (static_cast<size_t>(taps) * a.Cout + static_cast<size_t>(a.Cin) * a.ksize * (STEM_W + 2 * pad)) * 4;
+    static size_t max_set = 0;
+    if (smem > 48 * 1024 && smem > max_set) {
+        cudaError_t e = cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        max_set = smem;
+    }
+    stem_conv_kernel<<<a.B * a.H, STEM_THREADS, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t head_conv1x1_run(const HeadConvArgs& a, cudaStream_t s) {
+    if (a.C % 8 != 0 || a.C > 256 || (32 % (a.C / 8)) != 0) return cudaErrorInvalidValue;
+    const long long threads = static_cast<long long>(a.M) * (a.C / 8);
+    const int grid = static_cast<int>((threads + 255) / 256);
+    head_conv1x1_kernel<<<grid, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t posterior_step_run(const PosteriorArgs& a, cudaStream_t s) {
+    if (a.n % 4 != 0 || a.tile_elems % 4 != 0) return cudaErrorInvalidValue;
+    const int grid = static_cast<int>((a.n / 4 + 255) / 256);
+    posterior_step_kernel<<<grid, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t philox_normal_run(float* out, long long n, unsigned long long seed, unsigned long long tile_offset,
+                              int tile_elems, unsigned long long stream_id, cudaStream_t s) {
+    if (n % 4 != 0 || tile_elems % 4 != 0) return cudaErrorInvalidValue;
+    const int grid = static_cast<int>((n / 4 + 255) / 256);
+    philox_normal_kernel<<<grid, 256, 0, s>>>(out, n, seed, tile_offset, tile_elems, stream_id);
+    return cudaGetLastError();
+}
+
+cudaError_t step_advance_run(SampleCtl* ctl, int delta, cudaStream_t s) {
+    step_advance_kernel<<<1, 1, 0, s>>>(ctl, delta);
+    return cudaGetLastError();
+}
+
+}  // namespace hd

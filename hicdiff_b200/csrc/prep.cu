@@ -1,0 +1,151 @@
+// One-off (per checkpoint) preparation kernels and the time-embedding path.
+//
+// prep_conv_weight    WeightStandardizedConv2d's weight normalisation, hoisted out of the step because it does
+//                     not depend on the input (/root/reference/src/hicdiff_condition.py:89-95): per output channel
+//                     w~ = (w - mean) * rsqrt(var_biased + 1e-5) in fp32, then re-laid out [Cout, (ky, kx, cin)]
+//                     bf16 = the K-major B operand of conv_gemm.cu.  standardize = 0 gives the plain re-layout.
+// prep_unshuffle      Downsample's 1x1 weight: K order (c, p1, p2) -> (p1, p2, c)   (:78-82)
+// posenc_rows         SinusoidalPosEmb (:122-134) / SR3 PositionalEncoding (hicdiff_sr3.py:155-165)
+// linear_rows         nn.Linear over a handful of rows with optional SiLU on the input (ResnetBlock.mlp :176-179)
+//                     or exact-erf GELU on the output (time_mlp :300-305)
+// Because p_sample feeds the SAME t to every sample (:594), the sampling path evaluates these once per
+// checkpoint for all T timesteps and keeps the [T, sum(2*Cout)] FiLM table resident in HBM.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace hd {
+namespace {
+
+__global__ void __launch_bounds__(256)
+prep_conv_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int ksize,
+                        int standardize, float eps, int Npad) {
+    __shared__ float s_red[8];
+    __shared__ float s_stat[2];
+    const int co = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int kk = ksize * ksize;
+    const int K = Cin * kk;
+    bf16* orow = out + static_cast<size_t>(co) * K;
+    if (co >= Cout) {   // zero padding rows (N padded up to the GEMM tile)
+        for (int i = tid; i < K; i += blockDim.x) orow[i] = __float2bfloat16(0.f);
+        return;
+    }
+    const float* wrow = w + static_cast<size_t>(co) * K;
+    float mean = 0.f, rstd = 1.f;
+    if (standardize) {
+        float s = 0.f;
+        for (int i = tid; i < K; i += blockDim.x) s += wrow[i];
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if ((tid & 31) == 0) s_red[tid >> 5] = s;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+            for (int i = 0; i < 8; ++i) t += s_red[i];
+            s_stat[0] = t / K;
+        }
+        __syncthreads();
+        mean = s_stat[0];
+        float ss = 0.f;
+        for (int i = tid; i < K; i += blockDim.x) ss += (wrow[i] - mean) * (wrow[i] - mean);
+        for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+        __syncthreads();
+        if ((tid & 31) == 0) s_red[tid >> 5] = ss;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+            for (int i = 0; i < 8; ++i) t += s_red[i];
+            s_stat[1] = rsqrtf(t / K + eps);
+        }
+        __syncthreads();
+        rstd = s_stat[1];
+    }
+    // reference layout [Cout][Cin][ky][kx]  ->  [Cout][(ky*ks + kx) * Cin + ci]
+    for (int i = tid; i < K; i += blockDim.x) {
+        const int tap = i / Cin;
+        const int ci = i - tap * Cin;
+        const float v = (wrow[ci * kk + tap] - mean) * rstd;
+        orow[i] = __float2bfloat16(v);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+prep_unshuffle_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int C) {
+    const int co = blockIdx.x;
+    const int K = 4 * C;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        const int tap = i / C;        // p1 * 2 + p2
+        const int c = i - tap * C;
+        out[static_cast<size_t>(co) * K + i] = __float2bfloat16(w[static_cast<size_t>(co) * K + c * 4 + tap]);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+posenc_rows_kernel(const float* __restrict__ t, float* __restrict__ y, int rows, int dim, int mode) {
+    const int r = blockIdx.x;
+    const int half = dim / 2;
+    const float tv = t[r];
+    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+        float freq;
+        if (mode == 0) {
+            const float emb = logf(10000.0f) / static_cast<float>(half - 1);
+            freq = expf(static_cast<float>(i) * -emb);
+        } else {
+            const float step = static_cast<float>(i) / static_cast<float>(half);
+            freq = expf(-logf(10000.0f) * step);
+        }
+        const float arg = tv * freq;
+        y[static_cast<size_t>(r) * dim + i] = sinf(arg);
+        y[static_cast<size_t>(r) * dim + half + i] = cosf(arg);
+    }
+}
+
+// one warp per output feature, grid.y = row
+__global__ void __launch_bounds__(256)
+linear_rows_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W, const float* __restrict__ bias,
+                   float* __restrict__ y, int ldy, int off, int rows, int in_f, int out_f, int in_act, int out_act) {
+    const int r = blockIdx.y;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (j >= out_f) return;
+    const float* xr = x + static_cast<size_t>(r) * ldx;
+    const float* wr = W + static_cast<size_t>(j) * in_f;
+    float acc = 0.f;
+    for (int k = lane; k < in_f; k += 32) {
+        float xv = xr[k];
+        if (in_act == 1) xv = xv / (1.0f + expf(-xv));
+        acc = fmaf(xv, wr[k], acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        float v = acc + (bias != nullptr ? bias[j] : 0.f);
+        if (out_act == 1) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+        y[static_cast<size_t>(r) * ldy + off + j] = v;
+    }
+}
+
+}  // namespace
+
+cudaError_t prep_conv_weight_run(const float* w, bf16* out, int Cout, int Cin, int ksize, int standardize, float eps,
+                                 int Npad, cudaStream_t s) {
+    prep_conv_weight_kernel<<<Npad, 256, 0, s>>>(w, out, Cout, Cin, ksize, standardize, eps, Npad);
+    return cudaGetLastError();
+}
+
+cudaError_t prep_unshuffle_weight_run(const float* w, bf16* out, int Cout, int C, cudaStream_t s) {
+    prep_unshuffle_weight_kernel<<<Cout, 256, 0, s>>>(w, out, Cout, C);
+    return cudaGetLastError();
+}
+
+cudaError_t linear_rows_run(const float* x, int ldx, const float* W, const float* bias, float* y, int ldy, int off,
+                            int rows, int in_f, int out_f, int in_act, int out_act, cudaStream_t s) {
+    dim3 grid((out_f + 7) / 8, rows);
+    linear_rows_kernel<<<grid, 256, 0, s>>>(x, ldx, W, bias, y, ldy, off, rows, in_f, out_f, in_act, out_act);
+    return cudaGetLastError();
+}
+
+cudaError_t posenc_rows_run(const float* t, float* y, int rows, int dim, int mode, cudaStream_t s) {
+    posenc_rows_kernel<<<rows, 128, 0, s>>>(t, y, rows, dim, mode);
+    return cudaGetLastError();
+}
+
+}  // namespace hd

@@ -1,0 +1,152 @@
+"""Single-operator entry points of the C ABI on torch tensors (used by the parity tests and for debugging).
+
+Activations are NHWC bf16 `[B, H, W, C]` CUDA tensors -- the layout the kernels keep in HBM.  Nothing here falls back
+to torch: every function launches the sm_100a kernel through `libhicdiff_b200.so` or raises.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("hicdiff_b200 ops need CUDA tensors (there is no CPU path)")
+
+
+def _bf16c(t):
+    if t is None:
+        return None
+    assert t.dtype == torch.bfloat16
+    return t.contiguous()
+
+
+def _f32c(t):
+    if t is None:
+        return None
+    return t.detach().to(torch.float32).contiguous()
+
+
+def conv2d_nhwc(x0, w, bias=None, x1=None, res=None, ksize=None, standardize=False, unshuffle=False):
+    """Implicit-GEMM conv. x0/x1: [B,H,W,C] bf16 (x1 = second operand of a channel concat); w: fp32
+    [Cout, Cin, k, k] in the reference layout.  `unshuffle=True` is Downsample (pixel-unshuffle + 1x1)."""
+    lib = _lib.load()
+    _need_cuda(x0, w)
+    x0, x1, res = _bf16c(x0), _bf16c(x1), _bf16c(res)
+    w, bias = _f32c(w), _f32c(bias)
+    B, H, W, C0 = x0.shape
+    C1 = x1.shape[-1] if x1 is not None else 0
+    Cout = w.shape[0]
+    k = int(w.shape[-1]) if ksize is None else ksize
+    Ho, Wo = (H // 2, W // 2) if unshuffle else (H, W)
+    out = torch.empty(B, Ho, Wo, Cout, device=x0.device, dtype=torch.bfloat16)
+    _lib.check(
+        lib.hd_op_conv2d(_lib.ptr(x0), C0, _lib.ptr(x1), C1, _lib.ptr(w), _lib.ptr(bias), _lib.ptr(res), _lib.ptr(out),
+                         B, Ho, Wo, Cout, k, 1 if unshuffle else 0, 1 if standardize else 0, _lib.stream_ptr()),
+        "hd_op_conv2d",
+    )
+    return out
+
+
+def groupnorm_silu_nhwc(x, gamma, beta, scale=None, shift=None, res=None):
+    lib = _lib.load()
+    _need_cuda(x)
+    x, res = _bf16c(x), _bf16c(res)
+    B, H, W, Cc = x.shape
+    y = torch.empty_like(x)
+    gamma, beta, scale, shift = _f32c(gamma), _f32c(beta), _f32c(scale), _f32c(shift)
+    _lib.check(
+        lib.hd_op_groupnorm_silu(_lib.ptr(x), _lib.ptr(y), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(scale),
+                                 _lib.ptr(shift), _lib.ptr(res), B, H * W, Cc, _lib.stream_ptr()),
+        "hd_op_groupnorm_silu",
+    )
+    return y
+
+
+def channel_layernorm_nhwc(x, g, res=None, upsample2x=False):
+    lib = _lib.load()
+    _need_cuda(x)
+    x, res = _bf16c(x), _bf16c(res)
+    B, H, W, Cc = x.shape
+    y = torch.empty(B, H * (2 if upsample2x else 1), W * (2 if upsample2x else 1), Cc, device=x.device, dtype=torch.bfloat16)
+    g = _f32c(g).reshape(-1)
+    _lib.check(
+        lib.hd_op_channel_layernorm(_lib.ptr(x), _lib.ptr(y), _lib.ptr(g), _lib.ptr(res), B, H, W, Cc,
+                                    1 if upsample2x else 0, _lib.stream_ptr()),
+        "hd_op_channel_layernorm",
+    )
+    return y
+
+
+def linear_attention_nhwc(qkv):
+    lib = _lib.load()
+    _need_cuda(qkv)
+    qkv = _bf16c(qkv)
+    B, H, W, Cc = qkv.shape
+    assert Cc == 384
+    out = torch.empty(B, H, W, 128, device=qkv.device, dtype=torch.bfloat16)
+    _lib.check(lib.hd_op_linear_attention(_lib.ptr(qkv), _lib.ptr(out), B, H * W, _lib.stream_ptr()), "hd_op_linear_attention")
+    return out
+
+
+def full_attention_nhwc(qkv):
+    lib = _lib.load()
+    _need_cuda(qkv)
+    qkv = _bf16c(qkv)
+    B, H, W, Cc = qkv.shape
+    assert Cc == 384
+    out = torch.empty(B, H, W, 128, device=qkv.device, dtype=torch.bfloat16)
+    _lib.check(lib.hd_op_full_attention(_lib.ptr(qkv), _lib.ptr(out), B, H * W, _lib.stream_ptr()), "hd_op_full_attention")
+    return out
+
+
+def stem_conv(x0, x1, w, bias):
+    """x0/x1: fp32 [B,1,64,64] planes (x1 may be None); w fp32 [Cout, Cin, k, k] -> NHWC bf16 [B,64,64,Cout]."""
+    lib = _lib.load()
+    _need_cuda(x0, w)
+    x0, x1, w, bias = _f32c(x0), _f32c(x1), _f32c(w), _f32c(bias)
+    B = x0.shape[0]
+    Cout, Cin, k, _ = w.shape
+    y = torch.empty(B, 64, 64, Cout, device=x0.device, dtype=torch.bfloat16)
+    _lib.check(lib.hd_op_stem_conv(_lib.ptr(x0), _lib.ptr(x1), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(y), B, Cout, Cin, k,
+                                   _lib.stream_ptr()), "hd_op_stem_conv")
+    return y
+
+
+def philox_normal(n_tiles, seed, tile_offset=0, device="cuda"):
+    lib = _lib.load()
+    out = torch.empty(n_tiles, 1, 64, 64, device=device, dtype=torch.float32)
+    _lib.check(lib.hd_op_philox_normal(_lib.ptr(out), out.numel(), seed, tile_offset, _lib.stream_ptr()), "hd_op_philox_normal")
+    return out
+
+
+def tile_count(n, piece=64, band_blocks=4):
+    return int(_lib.load().hd_tile_count(n, piece, band_blocks))
+
+
+def tile_extract(mat, piece=64, band_blocks=4):
+    """splitPieces on the GPU: mat fp32 [n, n] -> tiles fp32 [k, 1, piece, piece]."""
+    lib = _lib.load()
+    _need_cuda(mat)
+    mat = _f32c(mat)
+    n = mat.shape[0]
+    assert mat.shape == (n, n)
+    k = tile_count(n, piece, band_blocks)
+    tiles = torch.empty(k, 1, piece, piece, device=mat.device, dtype=torch.float32)
+    _lib.check(lib.hd_tile_extract(_lib.ptr(mat), n, _lib.ptr(tiles), piece, band_blocks, _lib.stream_ptr()), "hd_tile_extract")
+    return tiles
+
+
+def tile_scatter(tiles, n, piece=64, band_blocks=4):
+    """Inverse of tile_extract: tiles fp32 [k,1,piece,piece] -> symmetric band matrix fp32 [n, n]."""
+    lib = _lib.load()
+    _need_cuda(tiles)
+    tiles = _f32c(tiles)
+    k = tile_count(n, piece, band_blocks)
+    if tiles.shape[0] != k:
+        raise ValueError(f"expected {k} tiles for n={n}, got {tiles.shape[0]}")
+    mat = torch.zeros(n, n, device=tiles.device, dtype=torch.float32)
+    _lib.check(lib.hd_tile_scatter(_lib.ptr(tiles), _lib.ptr(mat), n, piece, band_blocks, _lib.stream_ptr()), "hd_tile_scatter")
+    return mat

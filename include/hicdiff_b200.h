@@ -1,0 +1,154 @@
+/*
+ * hicdiff_b200 -- C ABI of the B200-native HiCDiff reverse-diffusion sampling path.
+ *
+ * The reference (BioinfoMachineLearning/hicdiff) has no FFI / plugin layer: its boundary for this path is the
+ * Python class surface of `Unet` / `hicedrn_Diff` / `GaussianDiffusion`.  This header is the C boundary that sits
+ * directly UNDER that surface; every entry point below cites the reference code it replaces.  All pointers are
+ * plain device (or, where stated, host) pointers, all sizes are explicit, no torch / C++ types cross the boundary.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a non-zero code on failure; `hd_last_error()` then returns a
+ *     thread-local, human readable message (the Python layer raises RuntimeError with it);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises the device
+ *     unless stated;
+ *   - tiles are fp32 [B, 1, 64, 64] contiguous (the reference's NCHW with C == 1);
+ *   - there is NO CPU fallback anywhere behind this ABI.
+ */
+#ifndef HICDIFF_B200_H_
+#define HICDIFF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HD_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define HD_API __attribute__((visibility("default")))
+#else
+#define HD_API
+#endif
+
+typedef struct hd_plan hd_plan;
+
+/* eps-predictor variants. */
+enum hd_variant {
+    HD_UNET = 0,        /* Unet of src/hicdiff_condition.py:255-384 (self_condition=True) and src/hicdiff.py (False) */
+    HD_UNET_SR3 = 1,    /* Unet(noise_level_emb=True) of src/hicdiff_sr3.py:310-445                                   */
+    HD_HICEDRN = 2,     /* hicedrn_Diff of src/model/hicedrn_Diff.py:210-297                                          */
+    HD_HICEDRN_SR3 = 3  /* hicedrn_Diff of src/model/hicedrn_sr3_Diff.py                                              */
+};
+
+/* Mirrors the constructor arguments the reference scripts actually use. */
+typedef struct hd_config {
+    int32_t abi_version;      /* must be HD_ABI_VERSION                                                              */
+    int32_t variant;          /* enum hd_variant                                                                     */
+    int32_t self_condition;   /* 1: the conditional (noisy) tile is concatenated as input channel 0                  */
+    int32_t dim;              /* Unet `dim` (64); ignored for HiCEDRN (n_feat = 256)                                 */
+    int32_t num_mults;        /* len(dim_mults), <= 8                                                                */
+    int32_t dim_mults[8];     /* (1, 2, 4, 8)                                                                        */
+    int32_t image_size;       /* 64                                                                                  */
+    int32_t timesteps;        /* T (GaussianDiffusion.num_timesteps)                                                 */
+    int32_t num_blocks;       /* HiCEDRN number_resnet (32); ignored for Unet                                        */
+    int32_t debug_keep;       /* 1: keep every intermediate activation addressable via hd_debug_read               */
+    int32_t reserved[8];
+} hd_config;
+
+/* -------------------------------------------------------------------------------------------------------------
+ * Plan life cycle.  Replaces nn.Module construction + load_state_dict + .to(device) for the sampling path
+ * (inference.py:59-94).  hd_plan_set_weight is called once per state_dict entry under `model.` (key WITHOUT the
+ * `model.` prefix, e.g. "downs.0.0.block1.proj.weight"); the data is copied, the caller keeps ownership.
+ * ------------------------------------------------------------------------------------------------------------- */
+HD_API int hd_plan_create(const hd_config* cfg, hd_plan** out);
+HD_API int hd_plan_set_weight(hd_plan* plan, const char* key, const float* dev_ptr, const int64_t* shape, int32_t ndim,
+                       void* stream);
+/* Schedule tables of GaussianDiffusion.__init__ (hicdiff_condition.py:491-519), all fp32 [T] DEVICE pointers:
+ * sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1, posterior_mean_coef2 and
+ * sigma = exp(0.5 * posterior_log_variance_clipped) (p_sample :597).  `time_values` is what the eps-net receives as
+ * `time` at step t: float(t) for Unet/HiCEDRN (:594), sqrt_alphas_cumprod_prev[t+1] for SR3 (hicdiff_sr3.py:636). */
+HD_API int hd_plan_set_schedule(hd_plan* plan, const float* sqrt_recip, const float* sqrt_recipm1, const float* coef1,
+                         const float* coef2, const float* sigma, const float* time_values, int32_t T, void* stream);
+/* Standardises + re-lays-out weights (bf16 GEMM layout), builds the [T, .] time-embedding table.  Must be called
+ * after all weights and the schedule are set and again after any weight changes.  Synchronises `stream`. */
+HD_API int hd_plan_finalize(hd_plan* plan, void* stream);
+HD_API void hd_plan_destroy(hd_plan* plan);
+
+/* -------------------------------------------------------------------------------------------------------------
+ * eps-predictor forward.  Replaces Unet.forward / hicedrn_Diff.forward (hicdiff_condition.py:345-384,
+ * hicedrn_Diff.py:267-289).  `time` is fp32 [B] (integer timesteps converted to float, or SR3 noise levels).
+ * `cond` may be NULL iff self_condition == 0.  x, cond, eps: fp32 [B,1,64,64].
+ * ------------------------------------------------------------------------------------------------------------- */
+HD_API int hd_eps_forward(hd_plan* plan, const float* x, const float* cond, const float* time, float* eps, int32_t B,
+                   void* stream);
+
+/* One reverse step on a caller-owned state: replaces p_sample (hicdiff_condition.py:591-598) given eps.
+ * x is updated in place; `noise` is the z tensor for this step (ignored when t == 0) or NULL for Philox
+ * (seed, tile_offset).  x0_out (optional) receives the clipped x_start. */
+HD_API int hd_ddpm_step(hd_plan* plan, float* x, const float* eps, const float* noise, float* x0_out, int32_t t, int32_t B,
+                 uint64_t seed, uint64_t tile_offset, void* stream);
+
+/* Full reverse process.  Replaces p_sample_loop (hicdiff_condition.py:600-623, hicdiff.py:603-620,
+ * hicdiff_sr3.py:654-677): x_T ~ N(0, I), then t = T-1 .. 0.  One CUDA graph per step, replayed T times with a
+ * device-side step counter.
+ *   cond   fp32 [B,1,64,64] or NULL (unconditional)
+ *   noise  NULL -> Philox(seed) with per-tile streams keyed by (tile_offset + b), so results do not depend on
+ *          how tiles are sharded; else fp32 [T, B,1,64,64]: noise[0] = x_T, noise[i] = z of step t = T - i
+ *          (the exact draw order of the reference: :605 then :596, no draw at t == 0)
+ *   out    fp32 [B,1,64,64] final x_0
+ *   trace  optional fp32 [T, B,1,64,64]: x after each step (return_all_timesteps), or NULL
+ *   t_start / t_end: run steps t = t_start .. t_end (inclusive, descending); pass T-1, 0 for the full chain.
+ *          When t_start < T-1 the chain starts from `out`'s current content instead of fresh noise. */
+HD_API int hd_sample(hd_plan* plan, const float* cond, const float* noise, float* out, float* trace, int32_t B,
+              uint64_t seed, uint64_t tile_offset, int32_t t_start, int32_t t_end, void* stream);
+
+/* -------------------------------------------------------------------------------------------------------------
+ * Tiling.  hd_tile_extract replaces splitPieces (processdata/PrepareData_linear.py:25-46): zero-pad the n x n
+ * matrix to a multiple of `piece`, enumerate block rows i and block columns j >= i with (j - i) <= band_blocks
+ * (= 4 * int(40000 / res)), row-major.  hd_tile_scatter is its exact inverse (the reference has none): tile k is
+ * written at block (i, j) and, for i != j, transposed at (j, i); padding is cropped; cells outside the band are
+ * left untouched (zero them first).  Pure indexing: bit-exact.
+ * ------------------------------------------------------------------------------------------------------------- */
+HD_API int64_t hd_tile_count(int64_t n, int32_t piece, int32_t band_blocks);
+HD_API int hd_tile_extract(const float* mat, int64_t n, float* tiles, int32_t piece, int32_t band_blocks, void* stream);
+HD_API int hd_tile_scatter(const float* tiles, float* mat, int64_t n, int32_t piece, int32_t band_blocks, void* stream);
+
+/* -------------------------------------------------------------------------------------------------------------
+ * Single-operator entry points (same kernels the plan launches).  Used by the parity tests to pin each kernel
+ * against torch fp32 ops; layouts: activations bf16 NHWC [B,H,W,C] as raw uint16 device buffers.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* conv: w fp32 [Cout,Cin,k,k] in reference layout; standardize=1 applies WeightStandardizedConv2d's transform.
+ * x1 (second concat operand, C1 channels) may be NULL.  mode 0: k x k "same" conv; mode 1: Downsample (pixel
+ * unshuffle + 1x1, w is [Cout, 4*C0, 1, 1]; x0 is [B,2H,2W,C0], output [B,H,W,Cout]).  res (optional) is added. */
+HD_API int hd_op_conv2d(const uint16_t* x0, int32_t C0, const uint16_t* x1, int32_t C1, const float* w, const float* bias,
+                 const uint16_t* res, uint16_t* out, int32_t B, int32_t H, int32_t W, int32_t Cout, int32_t ksize,
+                 int32_t mode, int32_t standardize, void* stream);
+HD_API int hd_op_groupnorm_silu(const uint16_t* x, uint16_t* y, const float* gamma, const float* beta, const float* scale,
+                         const float* shift, const uint16_t* res, int32_t B, int32_t P, int32_t C, void* stream);
+HD_API int hd_op_channel_layernorm(const uint16_t* x, uint16_t* y, const float* g, const uint16_t* res, int32_t B, int32_t H,
+                            int32_t W, int32_t C, int32_t upsample2x, void* stream);
+HD_API int hd_op_linear_attention(const uint16_t* qkv, uint16_t* out, int32_t B, int32_t n, void* stream);
+HD_API int hd_op_full_attention(const uint16_t* qkv, uint16_t* out, int32_t B, int32_t n, void* stream);
+HD_API int hd_op_stem_conv(const float* x0, const float* x1, const float* w, const float* bias, uint16_t* y, int32_t B,
+                    int32_t Cout, int32_t Cin, int32_t ksize, void* stream);
+HD_API int hd_op_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t tile_offset, void* stream);
+
+/* Debug: copy a named intermediate of the last hd_eps_forward(B) as fp32 NCHW into `out` (device), needs
+ * cfg.debug_keep.  Returns its element count through *numel; out may be NULL to query. */
+HD_API int hd_debug_read(hd_plan* plan, int32_t B, const char* name, float* out, int64_t* numel, int32_t* shape4,
+                  void* stream);
+HD_API int hd_debug_names(hd_plan* plan, int32_t B, char* buf, int64_t buflen);
+
+/* Number of kernels the plan launches per hd_eps_forward / per sampling step at batch B (for gpu_launches). */
+HD_API int hd_plan_launches_per_step(hd_plan* plan, int32_t B, int32_t* eps_launches, int32_t* step_launches);
+/* Device bytes held by the plan (weights + tables + workspaces). */
+HD_API int64_t hd_plan_device_bytes(hd_plan* plan);
+
+HD_API const char* hd_last_error(void);
+HD_API int hd_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HICDIFF_B200_H_ */

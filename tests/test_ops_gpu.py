@@ -1,0 +1,214 @@
+"""Per-kernel parity tests (B200 only): every sm_100a kernel the plan launches, called through the C ABI
+(`hd_op_*`) and compared with a float64 torch evaluation of the reference's op on the SAME bf16-rounded inputs.
+
+Tolerances (stated, bf16 storage with fp32 accumulation): the only error sources are accumulation order and the
+final bf16 rounding of the output (2^-9 relative), so
+    rel-RMS(out - ref) <= 4e-3   and   max|out - ref| <= 2e-2 * max|ref| + 1e-3.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from hicdiff_b200 import ops
+
+    return ops
+
+
+def _rand_nhwc(B, H, W, C, g, scale=1.0):
+    return (torch.randn(B, H, W, C, generator=g) * scale).to(torch.bfloat16).to(DEV)
+
+
+def _nchw64(x):  # NHWC bf16 -> NCHW float64
+    return x.permute(0, 3, 1, 2).to(torch.float64)
+
+
+def _check(out_nhwc, ref_nchw, what, rel_rms=4e-3, max_rel=2e-2):
+    out = _nchw64(out_nhwc)
+    assert out.shape == ref_nchw.shape, f"{what}: shape {tuple(out.shape)} vs {tuple(ref_nchw.shape)}"
+    assert torch.isfinite(out).all(), f"{what}: non-finite output"
+    err = out - ref_nchw
+    rms = err.pow(2).mean().sqrt().item()
+    ref_rms = ref_nchw.pow(2).mean().sqrt().item()
+    mx = err.abs().max().item()
+    assert rms <= rel_rms * ref_rms + 1e-6, f"{what}: rel-RMS {rms / max(ref_rms, 1e-30):.3e} (rms {rms:.3e}, ref {ref_rms:.3e})"
+    assert mx <= max_rel * ref_nchw.abs().max().item() + 1e-3, f"{what}: max abs err {mx:.3e}"
+
+
+def _ws(w):  # WeightStandardizedConv2d, fp64
+    w = w.to(torch.float64)
+    mean = w.mean(dim=(1, 2, 3), keepdim=True)
+    var = w.var(dim=(1, 2, 3), unbiased=False, keepdim=True)
+    return (w - mean) * (var + 1e-5).rsqrt()
+
+
+def _bf16_round(w):
+    return w.to(torch.bfloat16).to(torch.float64)
+
+
+CONV_CASES = [
+    # B, H, C0, C1, Cout, k, standardize
+    (2, 64, 64, 0, 64, 3, True),
+    (1, 64, 64, 64, 64, 3, True),       # concat 128 -> 64
+    (2, 32, 128, 64, 128, 3, True),     # concat 192 -> 128
+    (3, 16, 256, 0, 256, 3, True),
+    (2, 8, 512, 0, 512, 3, True),
+    (1, 8, 256, 0, 512, 3, False),      # M = 64 < one tile (TMA OOB rows), plain conv (downs.3.3)
+    (3, 8, 512, 256, 512, 3, True),     # M = 192: partial last tile, concat 768
+    (2, 64, 64, 0, 384, 1, False),      # to_qkv
+    (2, 32, 128, 0, 64, 1, False),      # to_out
+    (2, 16, 256, 128, 256, 1, False),   # res_conv on a concat
+    (2, 64, 256, 0, 256, 3, False),     # HiCEDRN body conv
+]
+
+
+@pytest.mark.parametrize("B,H,C0,C1,Cout,k,std", CONV_CASES)
+def test_conv_gemm(B, H, C0, C1, Cout, k, std):
+    ops = _ops()
+    g = torch.Generator().manual_seed(1000 + B * 7 + H + C0 + C1 + Cout + k)
+    x0 = _rand_nhwc(B, H, H, C0, g)
+    x1 = _rand_nhwc(B, H, H, C1, g) if C1 else None
+    Cin = C0 + C1
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)).to(DEV)
+    bias = (torch.randn(Cout, generator=g) * 0.1).to(DEV)
+    out = ops.conv2d_nhwc(x0, w, bias, x1=x1, standardize=std)
+    torch.cuda.synchronize()
+    wr = _bf16_round(_ws(w).float() if std else w)
+    xin = _nchw64(x0) if x1 is None else torch.cat((_nchw64(x0), _nchw64(x1)), dim=1)
+    ref = F.conv2d(xin, wr, bias.to(torch.float64), padding=k // 2)
+    _check(out, ref, f"conv {C0}+{C1}->{Cout} k{k} @{H}")
+
+
+def test_conv_gemm_residual_epilogue():
+    ops = _ops()
+    g = torch.Generator().manual_seed(7)
+    x = _rand_nhwc(2, 8, 8, 128, g)
+    res = _rand_nhwc(2, 8, 8, 512, g)
+    w = (torch.randn(512, 128, 1, 1, generator=g) / math.sqrt(128)).to(DEV)
+    bias = (torch.randn(512, generator=g) * 0.1).to(DEV)
+    out = ops.conv2d_nhwc(x, w, bias, res=res)
+    ref = F.conv2d(_nchw64(x), _bf16_round(w), bias.to(torch.float64)) + _nchw64(res)
+    _check(out, ref, "conv 1x1 + residual")
+
+
+@pytest.mark.parametrize("B,Hout,C,Cout", [(2, 32, 64, 64), (2, 16, 64, 128), (3, 8, 128, 256)])
+def test_downsample_unshuffle(B, Hout, C, Cout):
+    from einops import rearrange
+
+    ops = _ops()
+    g = torch.Generator().manual_seed(11 + Hout)
+    x = _rand_nhwc(B, 2 * Hout, 2 * Hout, C, g)
+    w = (torch.randn(Cout, 4 * C, 1, 1, generator=g) / math.sqrt(4 * C)).to(DEV)
+    bias = (torch.randn(Cout, generator=g) * 0.1).to(DEV)
+    out = ops.conv2d_nhwc(x, w, bias, unshuffle=True, ksize=1)
+    xin = rearrange(_nchw64(x), "b c (h p1) (w p2) -> b (c p1 p2) h w", p1=2, p2=2)
+    ref = F.conv2d(xin, _bf16_round(w), bias.to(torch.float64))
+    _check(out, ref, f"downsample {C}->{Cout} @{Hout}")
+
+
+@pytest.mark.parametrize("B,H,C,film,res", [(2, 64, 64, True, False), (3, 32, 128, False, True), (2, 16, 256, True, True),
+                                            (5, 8, 512, True, False), (1, 64, 256, False, False)])
+def test_groupnorm_film_silu(B, H, C, film, res):
+    ops = _ops()
+    g = torch.Generator().manual_seed(5 + C)
+    x = _rand_nhwc(B, H, H, C, g, scale=1.7) + 0.3
+    x = x.to(torch.bfloat16)
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(C, generator=g)).to(DEV)
+    scale = (0.3 * torch.randn(C, generator=g)).to(DEV) if film else None
+    shift = (0.3 * torch.randn(C, generator=g)).to(DEV) if film else None
+    r = _rand_nhwc(B, H, H, C, g) if res else None
+    out = ops.groupnorm_silu_nhwc(x, gamma, beta, scale, shift, r)
+    ref = F.group_norm(_nchw64(x), 8, gamma.double(), beta.double(), eps=1e-5)
+    if film:
+        ref = ref * (scale.double().view(1, -1, 1, 1) + 1) + shift.double().view(1, -1, 1, 1)
+    ref = F.silu(ref)
+    if res:
+        ref = ref + _nchw64(r)
+    _check(out, ref, f"groupnorm C{C} @{H}")
+
+
+@pytest.mark.parametrize("B,H,C,res,up", [(2, 64, 64, True, False), (2, 32, 128, False, False), (2, 16, 256, True, True),
+                                          (3, 8, 512, True, False), (1, 32, 128, True, True)])
+def test_channel_layernorm(B, H, C, res, up):
+    ops = _ops()
+    g = torch.Generator().manual_seed(9 + C)
+    x = _rand_nhwc(B, H, H, C, g, scale=2.0)
+    gain = (1 + 0.2 * torch.randn(C, generator=g)).to(DEV)
+    r = _rand_nhwc(B, H, H, C, g) if res else None
+    out = ops.channel_layernorm_nhwc(x, gain, r, upsample2x=up)
+    xx = _nchw64(x)
+    var = xx.var(dim=1, unbiased=False, keepdim=True)
+    mean = xx.mean(dim=1, keepdim=True)
+    ref = (xx - mean) * (var + 1e-5).rsqrt() * gain.double().view(1, -1, 1, 1)
+    if res:
+        ref = ref + _nchw64(r)
+    if up:
+        ref = F.interpolate(ref, scale_factor=2, mode="nearest")
+    _check(out, ref, f"layernorm C{C} @{H}")
+
+
+@pytest.mark.parametrize("B,H", [(2, 64), (3, 32), (2, 16), (5, 8)])
+def test_linear_attention(B, H):
+    ops = _ops()
+    g = torch.Generator().manual_seed(21 + H)
+    qkv = _rand_nhwc(B, H, H, 384, g, scale=1.5)
+    out = ops.linear_attention_nhwc(qkv)
+    q, k, v = _nchw64(qkv).chunk(3, dim=1)
+    q, k, v = (t.reshape(B, 4, 32, H * H) for t in (q, k, v))
+    q = q.softmax(dim=-2) * 32 ** -0.5
+    k = k.softmax(dim=-1)
+    v = v / (H * H)
+    ctx = torch.einsum("bhdn,bhen->bhde", k, v)
+    o = torch.einsum("bhde,bhdn->bhen", ctx, q).reshape(B, 128, H, H)
+    _check(out, o, f"linear attention n={H * H}", rel_rms=6e-3, max_rel=3e-2)
+
+
+def test_full_attention():
+    ops = _ops()
+    g = torch.Generator().manual_seed(33)
+    B, H = 3, 8
+    qkv = _rand_nhwc(B, H, H, 384, g, scale=1.5)
+    out = ops.full_attention_nhwc(qkv)
+    q, k, v = _nchw64(qkv).chunk(3, dim=1)
+    q, k, v = (t.reshape(B, 4, 32, H * H) for t in (q, k, v))
+    sim = torch.einsum("bhdi,bhdj->bhij", q * 32 ** -0.5, k)
+    attn = sim.softmax(dim=-1)
+    o = torch.einsum("bhij,bhdj->bhid", attn, v)          # b h n d
+    o = o.permute(0, 1, 3, 2).reshape(B, 128, H, H)       # 'b h (x y) d -> b (h d) x y'
+    _check(out, o, "full attention", rel_rms=6e-3, max_rel=3e-2)
+
+
+@pytest.mark.parametrize("Cin,Cout,k", [(2, 64, 7), (1, 64, 7), (2, 256, 3), (1, 256, 3)])
+def test_stem_conv(Cin, Cout, k):
+    ops = _ops()
+    g = torch.Generator().manual_seed(41 + Cin + k)
+    B = 3
+    x0 = torch.randn(B, 1, 64, 64, generator=g).to(DEV)
+    x1 = torch.randn(B, 1, 64, 64, generator=g).to(DEV) if Cin == 2 else None
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)).to(DEV)
+    bias = (0.1 * torch.randn(Cout, generator=g)).to(DEV)
+    out = ops.stem_conv(x0, x1, w, bias)
+    xin = x0 if x1 is None else torch.cat((x0, x1), dim=1)
+    ref = F.conv2d(xin.double(), w.double(), bias.double(), padding=k // 2)
+    _check(out, ref, f"stem conv {Cin}->{Cout} k{k}")
+
+
+def test_philox_normal_statistics_and_sharding_invariance():
+    ops = _ops()
+    z = ops.philox_normal(64, seed=1234, tile_offset=0)
+    assert abs(z.mean().item()) < 0.01
+    assert abs(z.std().item() - 1.0) < 0.01
+    assert abs((z ** 3).mean().item()) < 0.05          # skewness
+    assert abs((z ** 4).mean().item() - 3.0) < 0.1     # kurtosis
+    # tile k of a batch starting at offset o equals tile (o + k) of the whole job, whatever the sharding
+    z2 = ops.philox_normal(16, seed=1234, tile_offset=40)
+    assert torch.equal(z2, z[40:56])
+    assert not torch.equal(ops.philox_normal(4, seed=1235), z[:4])
