@@ -1,0 +1,346 @@
+"""`GaussianDiffusion` with the reference's constructor, buffers, methods and return conventions; the reverse
+process itself (p_sample_loop and everything under it) runs as CUDA graphs inside libhicdiff_b200.so.
+
+Three flavours, one per reference file:
+  conditional   /root/reference/src/hicdiff_condition.py:429-750   (`super_resolution`, list-returning trace)
+  unconditional /root/reference/src/hicdiff.py:432-755             (`sample`, stacked trace, p_losses(x_start, t))
+  SR3           /root/reference/src/hicdiff_sr3.py:491-796          (noise-level conditioning, numpy RNG in p_losses)
+
+Noise: by default x_T and the per-step z come from an in-kernel Philox stream (seeded from torch's CUDA generator, so
+`torch.manual_seed` still controls reproducibility); passing `noise=[T,B,1,64,64]` injects the exact draws the
+reference would make (draw 0 = x_T, draw i = z of step T-i, none at t == 0) for parity runs.
+"""
+from __future__ import annotations
+
+import math
+from collections import namedtuple
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+ModelPrediction = namedtuple("ModelPrediction", ["pred_noise", "pred_x_start"])
+
+_BUFFERS = (
+    "betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+    "log_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_variance",
+    "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2", "p2_loss_weight",
+)
+
+
+def _betas(kind: str, T: int, **kw) -> torch.Tensor:
+    """float64 beta schedules (hicdiff_condition.py:393-427)."""
+    f64 = torch.float64
+    if kind == "linear":
+        s = 1000 / T
+        return torch.linspace(s * 0.0001, s * 0.02, T, dtype=f64)
+    grid = torch.linspace(0, T, T + 1, dtype=f64) / T
+    if kind == "cosine":
+        s = kw.get("s", 0.008)
+        abar = torch.cos((grid + s) / (1 + s) * math.pi * 0.5) ** 2
+    elif kind == "sigmoid":
+        start, end, tau = kw.get("start", -3), kw.get("end", 3), kw.get("tau", 1)
+        lo, hi = torch.tensor(start / tau).sigmoid(), torch.tensor(end / tau).sigmoid()
+        abar = (-((grid * (end - start) + start) / tau).sigmoid() + hi) / (hi - lo)
+    else:
+        raise ValueError(f"unknown beta schedule {kind}")
+    abar = abar / abar[0]
+    return torch.clip(1 - (abar[1:] / abar[:-1]), 0, 0.999)
+
+
+class _LossNeedsBackward(torch.autograd.Function):
+    """Makes the training loss a graph leaf whose backward explains what is (not) built yet."""
+
+    @staticmethod
+    def forward(ctx, loss, *params):
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, g):  # pragma: no cover - exercised only on GPU
+        raise NotImplementedError(
+            "hicdiff_b200: the eps-net backward (dgrad/wgrad kernels) is not built yet -- SURVEY.md 8(f) N2. "
+            "The forward loss value is exact; train with the reference until N2 lands."
+        )
+
+
+class _GaussianDiffusionBase(nn.Module):
+    _flavour = "conditional"
+    _default_loss, _default_schedule = "l1", "sigmoid"
+
+    def __init__(self, model, *, image_size, timesteps=1000, sampling_timesteps=None, loss_type=None,
+                 objective="pred_noise", beta_schedule=None, schedule_fn_kwargs=dict(), p2_loss_weight_gamma=0.0,
+                 p2_loss_weight_k=1, ddim_sampling_eta=0.0, auto_normalize=False):
+        super().__init__()
+        if model.channels != model.out_dim:
+            raise AssertionError("model.channels must equal model.out_dim")
+        if model.random_or_learned_sinusoidal_cond:
+            raise AssertionError("random/learned sinusoidal conditioning is not supported")
+        loss_type = self._default_loss if loss_type is None else loss_type
+        beta_schedule = self._default_schedule if beta_schedule is None else beta_schedule
+        if objective not in {"pred_noise", "pred_x0", "pred_v"}:
+            raise AssertionError("objective must be pred_noise, pred_x0 or pred_v")
+        if objective != "pred_noise":
+            raise NotImplementedError("only objective='pred_noise' is used by the reference scripts and built here")
+        if image_size != 64:
+            raise NotImplementedError("the sm_100a path is built for the reference's 64x64 tiles (image_size=64)")
+
+        self.model = model
+        self.channels = model.channels
+        self.self_condition = model.self_condition
+        self.image_size = image_size
+        self.objective = objective
+        self.loss_type = loss_type
+
+        betas = _betas(beta_schedule, timesteps, **schedule_fn_kwargs)
+        alphas = 1.0 - betas
+        abar = torch.cumprod(alphas, dim=0)
+        abar_prev = F.pad(abar[:-1], (1, 0), value=1.0)
+        self.num_timesteps = int(betas.shape[0])
+        self.sampling_timesteps = timesteps if sampling_timesteps is None else sampling_timesteps
+        assert self.sampling_timesteps <= timesteps
+        self.is_ddim_sampling = self.sampling_timesteps < timesteps
+        self.ddim_sampling_eta = ddim_sampling_eta
+        if self.is_ddim_sampling:
+            raise NotImplementedError("DDIM sampling (sampling_timesteps < timesteps) is not used by any reference "
+                                      "script and is not built")
+        post_var = betas * (1.0 - abar_prev) / (1.0 - abar)
+        vals = {
+            "betas": betas,
+            "alphas_cumprod": abar,
+            "alphas_cumprod_prev": abar_prev,
+            "sqrt_alphas_cumprod": torch.sqrt(abar),
+            "sqrt_one_minus_alphas_cumprod": torch.sqrt(1.0 - abar),
+            "log_one_minus_alphas_cumprod": torch.log(1.0 - abar),
+            "sqrt_recip_alphas_cumprod": torch.sqrt(1.0 / abar),
+            "sqrt_recipm1_alphas_cumprod": torch.sqrt(1.0 / abar - 1),
+            "posterior_variance": post_var,
+            "posterior_log_variance_clipped": torch.log(post_var.clamp(min=1e-20)),
+            "posterior_mean_coef1": betas * torch.sqrt(abar_prev) / (1.0 - abar),
+            "posterior_mean_coef2": (1.0 - abar_prev) * torch.sqrt(alphas) / (1.0 - abar),
+            "p2_loss_weight": (p2_loss_weight_k + abar / (1 - abar)) ** -p2_loss_weight_gamma,
+        }
+        for name in _BUFFERS:  # registration order == reference state_dict order
+            self.register_buffer(name, vals[name].to(torch.float32))
+        if self._flavour == "sr3":
+            # plain float64 attribute, NOT a buffer (hicdiff_sr3.py:536): [1, 1, sqrt(abar_0), ..., sqrt(abar_{T-2})]
+            self.sqrt_alphas_cumprod_prev = torch.sqrt(F.pad(abar_prev, (1, 0), value=1.0))
+        self.auto_normalize = auto_normalize
+        self._sample_calls = 0
+
+    # ------------------------------------------------------------------ helpers
+    def normalize(self, img):
+        if not self.auto_normalize:
+            return img
+        if isinstance(img, (list, tuple)):
+            return type(img)(i * 2 - 1 for i in img)
+        return img * 2 - 1
+
+    def unnormalize(self, t):
+        if not self.auto_normalize:
+            return t
+        if isinstance(t, list):
+            return [(i + 1) * 0.5 for i in t]
+        return (t + 1) * 0.5
+
+    def _time_values(self) -> torch.Tensor:
+        """What the eps-net sees as `time` at step t."""
+        T = self.num_timesteps
+        if self._flavour == "sr3":
+            # torch.FloatTensor([self.sqrt_alphas_cumprod_prev[t + 1]]) -- float64 -> float32 (hicdiff_sr3.py:636)
+            return self.sqrt_alphas_cumprod_prev[1:T + 1].to(torch.float32)
+        return torch.arange(T, dtype=torch.float32)
+
+    def _sync_plan(self):
+        plan = self.model.eps_plan
+        sid = (self.sqrt_recip_alphas_cumprod.data_ptr(), self.posterior_mean_coef1.data_ptr(), self.num_timesteps)
+        if plan._schedule_id != sid:
+            plan.set_schedule(self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod,
+                              self.posterior_mean_coef1, self.posterior_mean_coef2,
+                              self.posterior_log_variance_clipped, self._time_values())
+        return plan
+
+    def _next_seed(self, device) -> int:
+        # derive the Philox seed from torch's generator so torch.manual_seed governs reproducibility
+        return int(torch.randint(0, 2 ** 62, (1,), device="cpu").item())
+
+    def _eps_time(self, t_int: int, b: int, device):
+        if self._flavour == "sr3":
+            return self._time_values()[t_int].repeat(b, 1).to(device)
+        return torch.full((b,), t_int, device=device, dtype=torch.long)
+
+    # ------------------------------------------------------------------ reference API: single-step pieces
+    def predict_start_from_noise(self, x_t, t, noise):
+        if isinstance(t, int):
+            return self.sqrt_recip_alphas_cumprod[t] * x_t - self.sqrt_recipm1_alphas_cumprod[t] * noise
+        return _gather(self.sqrt_recip_alphas_cumprod, t, x_t) * x_t - _gather(self.sqrt_recipm1_alphas_cumprod, t, x_t) * noise
+
+    def q_posterior(self, x_start, x_t, t):
+        if isinstance(t, int):
+            return (self.posterior_mean_coef1[t] * x_start + self.posterior_mean_coef2[t] * x_t,
+                    self.posterior_variance[t], self.posterior_log_variance_clipped[t])
+        mean = _gather(self.posterior_mean_coef1, t, x_t) * x_start + _gather(self.posterior_mean_coef2, t, x_t) * x_t
+        return mean, _gather(self.posterior_variance, t, x_t), _gather(self.posterior_log_variance_clipped, t, x_t)
+
+    @torch.no_grad()
+    def model_predictions(self, x, t, x_self_cond=None, clip_x_start=False, t_real=None):
+        eps = self.model(x, t, x_self_cond)
+        x_start = self.predict_start_from_noise(x, t if t_real is None else t_real, eps)
+        if clip_x_start:
+            x_start = x_start.clamp(-1.0, 1.0)
+        return ModelPrediction(eps, x_start)
+
+    @torch.no_grad()
+    def p_sample(self, x, t: int, x_self_cond=None, noise=None):
+        """One reverse step (hicdiff_condition.py:591-598): returns (x_{t-1}, x_start).  `noise` injects z."""
+        t = int(t)
+        plan = self._sync_plan()
+        eps = self.model(x, self._eps_time(t, x.shape[0], x.device), x_self_cond)
+        return plan.ddpm_step(x, eps, t, noise=noise, seed=self._next_seed(x.device) if noise is None else 0,
+                              want_x0=True)
+
+    # ------------------------------------------------------------------ reference API: loops
+    def _run_chain(self, batch, cond, noise, return_all):
+        plan = self._sync_plan()
+        seed = 0 if noise is not None else self._next_seed(None)
+        self._last_seed = seed
+        return plan.sample(batch, cond=cond, noise=noise, seed=seed, trace=return_all)
+
+    def _x_T(self, batch, noise, device):
+        """The chain's starting point: injected draw 0, or the Philox stream 0 of the seed just used."""
+        if noise is not None:
+            return noise[0]
+        from .ops import philox_normal
+
+        return philox_normal(batch, self._last_seed, 0, device=device)
+
+    @torch.no_grad()
+    def p_sample_loop(self, x_in, return_all_timesteps=False, noise=None):
+        if self._flavour == "unconditional" or not self.self_condition:
+            shape = tuple(x_in)
+            if len(shape) != 4 or shape[1:] != (self.channels, self.image_size, self.image_size):
+                raise ValueError(f"shape must be (B, {self.channels}, {self.image_size}, {self.image_size})")
+            res = self._run_chain(shape[0], None, noise, return_all_timesteps)
+            if not return_all_timesteps:
+                return self.unnormalize(res)
+            img, trace = res
+            first = self._x_T(shape[0], noise, img.device)
+            if self._flavour == "unconditional":
+                # hicdiff.py:617 stacks [x_T, x_{T-1}, ..., x_0] on dim 1
+                return self.unnormalize(torch.cat((first[:, None], trace.transpose(0, 1)), dim=1))
+            return self.unnormalize([first] + list(trace.unbind(0)))
+        cond = x_in
+        res = self._run_chain(cond.shape[0], cond, noise, return_all_timesteps)
+        if not return_all_timesteps:
+            return self.unnormalize(res)
+        _, trace = res
+        return self.unnormalize([cond] + list(trace.unbind(0)))  # hicdiff_condition.py:607,617,620
+
+    @torch.no_grad()
+    def sample(self, x, return_all_timesteps=False, noise=None):
+        b = x.shape[0]
+        return self.p_sample_loop((b, self.channels, self.image_size, self.image_size),
+                                  return_all_timesteps=return_all_timesteps, noise=noise)
+
+    @torch.no_grad()
+    def super_resolution(self, x_in, continous=False, noise=None):
+        return self.p_sample_loop(x_in, continous, noise=noise)
+
+    # ------------------------------------------------------------------ training objective (forward value only)
+    def q_sample(self, x_start, t, noise=None):
+        noise = torch.randn_like(x_start) if noise is None else noise
+        return _gather(self.sqrt_alphas_cumprod, t, x_start) * x_start + \
+            _gather(self.sqrt_one_minus_alphas_cumprod, t, x_start) * noise
+
+    @property
+    def loss_fn(self):
+        if self.loss_type == "l1":
+            return F.l1_loss
+        if self.loss_type == "l2":
+            return F.mse_loss
+        raise ValueError(f"invalid loss type {self.loss_type}")
+
+    def _finish_loss(self, loss):
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        if torch.is_grad_enabled() and params:
+            return _LossNeedsBackward.apply(loss, *params)
+        return loss
+
+    def p_losses(self, x_in, t=None, noise=None):
+        noisy, clean = x_in
+        b, c, h, w = clean.shape
+        assert h == self.image_size and w == self.image_size, f"height and width of image must be {self.image_size}"
+        if t is None:
+            t = torch.randint(0, self.num_timesteps, (b,), device=clean.device).long()
+        noise = torch.randn_like(clean) if noise is None else noise
+        x = self.q_sample(clean, t, noise)
+        with torch.no_grad():
+            out = self.model(x, t, noisy if self.self_condition else None)
+        loss = self.loss_fn(out, noise, reduction="none").reshape(b, -1)  # 'b ... -> b (...)' keeps all elements
+        loss = loss * _gather(self.p2_loss_weight, t, loss)
+        return self._finish_loss(loss.mean())
+
+    def forward(self, img, *args, **kwargs):
+        return self.p_losses(self.normalize(img), *args, **kwargs)
+
+
+def _gather(table, t, like):
+    out = table.gather(-1, t)
+    return out.reshape(t.shape[0], *((1,) * (like.dim() - 1)))
+
+
+class GaussianDiffusionCond(_GaussianDiffusionBase):
+    _flavour = "conditional"
+    _default_loss, _default_schedule = "l1", "sigmoid"
+
+
+class GaussianDiffusionUncond(_GaussianDiffusionBase):
+    _flavour = "unconditional"
+    _default_loss, _default_schedule = "l1", "sigmoid"
+
+    def __init__(self, model, **kw):
+        if model.self_condition:
+            # torch.cat((None, x)) on the first step (hicdiff.py:352,613): the reference cannot run this either
+            raise NotImplementedError("src/hicdiff.py only works with self_condition=False (SURVEY.md C.12)")
+        super().__init__(model, **kw)
+
+    def p_losses(self, x_start, t, noise=None):  # hicdiff.py:711-747
+        b = x_start.shape[0]
+        noise = torch.randn_like(x_start) if noise is None else noise
+        x = self.q_sample(x_start, t, noise)
+        with torch.no_grad():
+            out = self.model(x, t, None)
+        loss = self.loss_fn(out, noise, reduction="none").reshape(b, -1)  # 'b ... -> b (...)' keeps all elements
+        loss = loss * _gather(self.p2_loss_weight, t, loss)
+        return self._finish_loss(loss.mean())
+
+    def forward(self, img, *args, **kwargs):  # hicdiff.py:749-755
+        b, c, h, w = img.shape
+        assert h == self.image_size and w == self.image_size, f"height and width of image must be {self.image_size}"
+        t = torch.randint(0, self.num_timesteps, (b,), device=img.device).long()
+        return self.p_losses(self.normalize(img), t, *args, **kwargs)
+
+
+class GaussianDiffusionSR3(_GaussianDiffusionBase):
+    _flavour = "sr3"
+    _default_loss, _default_schedule = "l2", "linear"
+
+    def q_sample(self, x_start, continuous_sqrt_alpha_cumprod, noise=None):  # hicdiff_sr3.py:735-739
+        noise = torch.randn_like(x_start) if noise is None else noise
+        return continuous_sqrt_alpha_cumprod * x_start + (1 - continuous_sqrt_alpha_cumprod ** 2).sqrt() * noise
+
+    def p_losses(self, x_in, noise=None, level=None):  # hicdiff_sr3.py:750-792 (numpy global RNG, no p2 weight)
+        noisy, clean = x_in
+        b, c, h, w = clean.shape
+        assert h == self.image_size and w == self.image_size, f"height and width of image must be {self.image_size}"
+        if level is None:
+            t = np.random.randint(1, self.num_timesteps + 1)
+            level = torch.FloatTensor(np.random.uniform(self.sqrt_alphas_cumprod_prev[t - 1],
+                                                        self.sqrt_alphas_cumprod_prev[t], size=b)).to(clean.device)
+        level = level.view(b, -1)
+        noise = torch.randn_like(clean) if noise is None else noise
+        x = self.q_sample(clean, level.view(-1, 1, 1, 1), noise)
+        with torch.no_grad():
+            out = self.model(x, level, noisy if self.self_condition else None)
+        return self._finish_loss(self.loss_fn(out, noise, reduction="none").mean())
