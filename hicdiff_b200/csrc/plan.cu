@@ -157,6 +157,7 @@ struct hd_plan {
     float* film_table = nullptr;  // [T, film_ld]
     SampleCtl* ctl = nullptr;     // device control block (sampling)
     SampleCtl* ctl_one = nullptr; // device control block (hd_ddpm_step)
+    cudaStream_t cap_stream = nullptr;  // private stream used only for graph capture
     bool finalized = false;
     size_t weight_bytes = 0;
     std::map<int, std::unique_ptr<Exec>> execs;
@@ -517,6 +518,8 @@ int run_ops(const std::vector<Op>& ops, cudaStream_t s) {
     return 0;
 }
 
+// Capture happens on a plan-private stream: the caller's stream may be the legacy default stream, which cannot be
+// captured; the instantiated graph is then launched on whatever stream the caller passes.
 int capture(const std::vector<Op>& ops, cudaStream_t s, cudaGraphExec_t* out) {
     CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     int rc = run_ops(ops, s);
@@ -619,8 +622,8 @@ int get_exec(hd_plan* P, int B, cudaStream_t s, Exec** out) {
         if (run_ops(ex->ops_table, s)) return cleanup_fail(1);
         e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) return cleanup_fail(fail("sampling-step validation run failed: %s", cudaGetErrorString(e)));
-        if (capture(ex->ops_rows, s, &ex->g_eps)) return cleanup_fail(1);
-        if (capture(ex->ops_table, s, &ex->g_step)) return cleanup_fail(1);
+        if (capture(ex->ops_rows, P->cap_stream, &ex->g_eps)) return cleanup_fail(1);
+        if (capture(ex->ops_table, P->cap_stream, &ex->g_step)) return cleanup_fail(1);
     }
 #undef EX_TRY
     *out = ex.get();
@@ -675,6 +678,8 @@ int hd_plan_create(const hd_config* cfg, hd_plan** out) {
     P->T = cfg->timesteps;
     P->fourier_dim = hic ? 256 : cfg->dim;
     P->time_dim = hic ? 1024 : cfg->dim * 4;
+    cudaError_t se = cudaStreamCreateWithFlags(&P->cap_stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess) { delete P; return fail("cudaStreamCreateWithFlags failed: %s", cudaGetErrorString(se)); }
     *out = P;
     return 0;
 }
@@ -842,6 +847,7 @@ void hd_plan_destroy(hd_plan* P) {
     for (auto& kv : P->wq) cudaFree(kv.second);
     for (auto& kv : P->padded) cudaFree(kv.second);
     cudaFree(P->coef); cudaFree(P->time_values); cudaFree(P->film_table); cudaFree(P->ctl); cudaFree(P->ctl_one);
+    if (P->cap_stream) cudaStreamDestroy(P->cap_stream);
     delete P;
 }
 

@@ -51,9 +51,11 @@ class EpsPlan:
     def set_schedule(self, sqrt_recip, sqrt_recipm1, coef1, coef2, log_var, time_values):
         """Schedule tables (fp32 [T]) of the owning GaussianDiffusion; sigma = exp(0.5 * log_var) is evaluated with
         torch so the table is bit-identical to what p_sample computes (hicdiff_condition.py:597)."""
+        # evaluated on the CPU so the table does not depend on the device's exp() (the CPU oracle is the referee)
+        sigma = (0.5 * log_var.detach().to("cpu", torch.float32)).exp()
         sched = dict(sqrt_recip=sqrt_recip, sqrt_recipm1=sqrt_recipm1, coef1=coef1, coef2=coef2,
-                     sigma=(0.5 * log_var).exp(), time_values=time_values)
-        self._schedule = {k: v.detach().to(torch.float32) for k, v in sched.items()}
+                     sigma=sigma, time_values=time_values)
+        self._schedule = {k: v.detach().to("cpu", torch.float32) for k, v in sched.items()}
         self._schedule_id = tuple(int(v.data_ptr()) for v in (sqrt_recip, coef1)) + (int(sqrt_recip.numel()),)
         self.invalidate()
 

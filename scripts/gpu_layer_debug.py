@@ -38,4 +38,6 @@ names = net.eps_plan.debug_names(B)
 for n in names:
     if n in taps:
         got = net.eps_plan.debug_read(B, n)
+        if got.shape != taps[n].shape:   # ups.k.2 is stored already 2x-upsampled (fused into the closing LayerNorm)
+            got = got[:, :, ::2, ::2]
         print(f"{n:28s} rel-rms {helpers.rel_rms(got, taps[n]):.4e}  shape {tuple(got.shape)}")
