@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Benchmark of the HiCDiff reverse-diffusion sampling hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+metric     denoised 64x64 Hi-C tiles/sec at T=1000 (+ UNet step ms = ms_per_step)
+step       ONE reverse-diffusion step (eps-net forward + DDPM posterior update) over the whole tile batch; every step
+           of the chain launches the identical kernel sequence, so tiles/s(T=1000) = tiles / (1000 * step seconds).
+           The default run (no flags) times a full K = 1000 step trajectory.
+workload   N=1: BASELINE.json configs[1] -- unconditional UNet DDPM (src/hicdiff.py), batch 256 synthetic tiles, bf16
+           operands.  N>1: the same per-GPU batch on every rank (weak scaling; tiles are independent units, there is no
+           collective inside the chain; the finished tiles are all-gathered once in the e2e leg).
+value      whole-job tiles/s with everything resident in HBM (CUDA events on the launching stream, max over ranks).
+e2e        the same metric through the public Python API (`GaussianDiffusion.sample` / `.super_resolution`) with HOST
+           buffers: pinned H2D of the call's inputs, the full T=1000 chain, (N>1: NCCL all-gather of the tiles), D2H of
+           the result.
+roofline   conv_gemm_kernel (the tcgen05 implicit-GEMM conv, >= 98% of the step's FLOPs): algorithmic FLOPs of all
+           its launches in one step / their summed CUDA-event durations, measured live by the plan's built-in profiler.
+cpu_baseline  the CPU oracle (port of the reference algorithm, oracle/hicdiff_oracle.py) on the host cores, bounded
+           sample, extrapolated to tiles/s (every step runs the identical op sequence).
+--impl reference  times that CPU implementation only (rank 0), same metric / config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+T_FULL = 1000
+FLOPS_PER_TILE_STEP = {  # algorithmic FLOPs per tile per denoising step (BASELINE.md / SURVEY.md 6)
+    "unet_uncond": 14.539e9, "unet_cond": 14.564e9, "unet_sr3": 14.562e9, "hicedrn_cond": 314.162e9, "hicedrn_sr3": 314.146e9,
+}
+WORKLOADS = {
+    "unet_uncond": dict(desc="unconditional UNet DDPM (src/hicdiff.py), T=1000 sampling", batch=256, schedule="linear"),
+    "unet_cond": dict(desc="conditional UNet HiCDiff (src/hicdiff_condition.py), T=1000 sampling", batch=256, schedule="sigmoid"),
+    "unet_sr3": dict(desc="SR3 conditional UNet (src/hicdiff_sr3.py), T=1000 sampling", batch=512, schedule="linear"),
+    "hicedrn_cond": dict(desc="HiCEDRN-backbone conditional diffusion, T=1000 sampling", batch=32, schedule="sigmoid"),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="unet_uncond", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="tiles per GPU (default: the workload's)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-reps", type=int, default=5)
+    ap.add_argument("--profile-out", default="", help="write the per-launch profile of one step (JSON) to this file")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(bf16=d.get("bf16_tflops", 1590.0), bf16_sustained=d.get("bf16_tflops_sustained", 1400.0),
+                    hbm=d.get("hbm_gbs", 6650.0), source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+# --------------------------------------------------------------------------------------------- CPU oracle arm
+VARIANTS = {  # name -> (module with Unet/hicedrn_Diff, ctor name, kwargs, diffusion module, oracle kwargs)
+    "unet_uncond": ("hicdiff_b200.hicdiff", "Unet", dict(dim=64, dim_mults=(1, 2, 4, 8), self_condition=False),
+                    "hicdiff_b200.hicdiff", dict(kind="unet", self_condition=False, sr3=False)),
+    "unet_cond": ("hicdiff_b200.hicdiff_condition", "Unet", dict(dim=64, dim_mults=(1, 2, 4, 8), self_condition=True),
+                  "hicdiff_b200.hicdiff_condition", dict(kind="unet", self_condition=True, sr3=False)),
+    "unet_sr3": ("hicdiff_b200.hicdiff_sr3", "Unet", dict(dim=64, dim_mults=(1, 2, 4, 8), self_condition=True, noise_level_emb=True),
+                 "hicdiff_b200.hicdiff_sr3", dict(kind="unet", self_condition=True, sr3=True)),
+    "hicedrn_cond": ("hicdiff_b200.model.hicedrn_Diff", "hicedrn_Diff", dict(self_condition=True),
+                     "hicdiff_b200.hicdiff_condition", dict(kind="hicedrn", self_condition=True, sr3=False)),
+}
+
+
+def build_variant(name):
+    """Random-init eps-net under torch seed 0 (the reference's default init; no checkpoints ship) + its diffusion class."""
+    import importlib
+
+    import torch
+
+    mod, ctor, kw, dmod, okw = VARIANTS[name]
+    torch.manual_seed(0)
+    net = getattr(importlib.import_module(mod), ctor)(**kw)
+    return net, okw, importlib.import_module(dmod).GaussianDiffusion
+
+
+def cpu_steps(name, schedule, batch, steps, warmup):
+    """Times `steps` p_sample steps of the CPU oracle (after `warmup`) at batch `batch`; returns seconds per step."""
+    import torch
+    from oracle import hicdiff_oracle as O
+
+    net, okw, _ = build_variant(name)
+    sd = {k: t.detach().clone() for k, t in net.state_dict().items()}
+    if okw["kind"] == "unet":
+        eps_fn = lambda x, t, c: O.unet_forward(sd, x, t, c, self_condition=okw["self_condition"], sr3=okw["sr3"])  # noqa: E731
+    else:
+        eps_fn = lambda x, t, c: O.hicedrn_forward(sd, x, t, c, self_condition=okw["self_condition"], sr3=okw["sr3"])  # noqa: E731
+    buf = O.diffusion_buffers(schedule, T_FULL)
+    levels = O.sr3_noise_levels(schedule, T_FULL) if okw["sr3"] else None
+    from hicdiff_b200.synthetic import synthetic_tiles
+
+    _, noisy = synthetic_tiles(batch, seed=1234)
+    cond = noisy if okw["self_condition"] else None
+    g = torch.Generator().manual_seed(2024)
+    x = torch.randn(batch, 1, 64, 64, generator=g)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t = T_FULL - 1 - i % T_FULL
+            z = torch.randn(batch, 1, 64, 64, generator=g)
+            t0 = time.perf_counter()
+            x, _, _ = O.p_sample(eps_fn, buf, x, t, cond, z, sr3_levels=levels)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return sum(times) / len(times)
+
+
+def run_reference_arm(args, rank):
+    import torch
+
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # bounded sample: keep the whole run within a few minutes whatever K is (~0.3 s per tile-step on 8 cores)
+    budget_s = 150.0
+    per_tile_step = 0.3 * 8 / max(cores, 1) if args.workload.startswith("unet") else 1.8 * 8 / max(cores, 1)
+    b = int(max(1, min(16, budget_s / ((args.steps + args.warmup) * per_tile_step))))
+    sec = cpu_steps(args.workload, wl["schedule"], b, args.steps, args.warmup)
+    tiles_s = b / (sec * T_FULL)
+    sample = f"{args.steps} p_sample steps of {b} tiles after {args.warmup} warm-up, extrapolated to T={T_FULL}"
+    line = {
+        "impl": "reference", "metric": "tiles_per_sec_T1000", "value": tiles_s, "unit": "tiles/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 * (wl["batch"] if not args.batch else args.batch) / b,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": f"{wl['desc']}, CPU oracle (port of the reference, torch fp32, {cores} threads)",
+                   "tiles_per_step": b, "timesteps": T_FULL, "schedule": wl["schedule"],
+                   "note": "ms_per_step is scaled to the GPU arm's per-GPU batch for comparability"},
+        "cpu_baseline": {"value": tiles_s, "unit": "tiles/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": tiles_s, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def run_b200_arm(args, rank, world):
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: hicdiff_b200 has no CPU fallback")
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = WORKLOADS[args.workload]
+    B = args.batch or wl["batch"]
+    K, W = args.steps, max(args.warmup, 3)
+    name = args.workload
+
+    net, okw, Diffusion = build_variant(name)
+    diff = Diffusion(net, image_size=64, timesteps=T_FULL, loss_type="l2", beta_schedule=wl["schedule"]).to(dev)
+    from hicdiff_b200.synthetic import synthetic_tiles
+
+    cond_host = None
+    if okw["self_condition"]:
+        _, noisy = synthetic_tiles(B, seed=1234 + rank)
+        cond_host = noisy.pin_memory()
+    cond = cond_host.to(dev, non_blocking=True) if cond_host is not None else None
+    plan = diff._sync_plan()
+    tile_offset = rank * B
+    seed = 20261018
+
+    # build executors / graphs, then W untimed warm-up steps (the first W steps of a chain)
+    done = 0
+    while done < W:
+        n = min(W - done, T_FULL)
+        plan.sample(B, cond=cond, seed=seed, tile_offset=tile_offset, t_start=T_FULL - 1, t_end=T_FULL - n)
+        done += n
+    torch.cuda.synchronize()
+    eps_launches, step_launches = plan.launches_per_step(B)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    stream = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    e0.record(stream)
+    # exactly K steps: chains of up to T steps each, starting at t = T-1 (x_T drawn by the in-kernel Philox)
+    done = 0
+    while done < K:
+        n = min(K - done, T_FULL)
+        x = plan.sample(B, cond=cond, seed=seed + done, tile_offset=tile_offset, t_start=T_FULL - 1, t_end=T_FULL - n)
+        done += n
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    ms_per_step = ms_max / K
+    tiles_s = B * world / (ms_per_step * 1e-3 * T_FULL)
+    assert torch.isfinite(x).all(), "sampling produced non-finite tiles"
+
+    peaks = measured_peaks()
+    flops_step = FLOPS_PER_TILE_STEP[name] * B
+    step_tflops = flops_step / (ms_per_step * 1e-3) / 1e12
+
+    # ---- roofline of the dominant kernel family, measured live with CUDA events by the plan's profiler
+    prof = plan.profile_step(B, reps=args.profile_reps)
+    if args.profile_out and rank == 0:
+        Path(args.profile_out).write_text(json.dumps(prof, indent=0))
+    fam = {}
+    for p in prof:
+        f = fam.setdefault(p["kernel"], dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+        f["ms"] += p["ms"]; f["flops"] += p["flops"]; f["bytes"] += p["bytes"]; f["launches"] += 1
+    total_ms = sum(f["ms"] for f in fam.values())
+    conv = fam.get("conv_gemm", dict(ms=1.0, flops=0.0, bytes=0.0, launches=0))
+    conv_tflops = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
+    roofline = {
+        "bound": "tensor", "kernel": "conv_gemm_kernel (all launches of one step)", "achieved": conv_tflops,
+        "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": conv_tflops / peaks["bf16_sustained"],
+        "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+        "launches_per_step": conv["launches"], "share_of_step_time": conv["ms"] / total_ms if total_ms else None,
+        "whole_step": {"achieved": step_tflops, "frac": step_tflops / peaks["bf16_sustained"],
+                       "flops_per_tile_step": FLOPS_PER_TILE_STEP[name]},
+        "families": {k: {"ms": round(f["ms"], 4), "launches": f["launches"],
+                         "tflops": (f["flops"] / (f["ms"] * 1e-3) / 1e12) if f["ms"] > 0 else 0.0,
+                         "gbs": (f["bytes"] / (f["ms"] * 1e-3) / 1e9) if f["ms"] > 0 else 0.0} for k, f in fam.items()},
+    }
+
+    # ---- e2e through the public API with host buffers (one full T=1000 call)
+    e2e = None
+    if not args.no_e2e:
+        host_in = (cond_host if cond_host is not None else torch.zeros(B, 1, 64, 64).pin_memory())
+        host_out = torch.empty(B * world if rank == 0 else B, 1, 64, 64).pin_memory()
+        torch.manual_seed(7 + rank)
+        barrier()
+        t0 = time.perf_counter()
+        dev_in = host_in.to(dev, non_blocking=True)
+        if okw["self_condition"]:
+            out = diff.super_resolution(dev_in)
+        else:
+            out = diff.sample(dev_in)
+        if world > 1:
+            gathered = torch.empty(B * world, 1, 64, 64, device=dev)
+            dist.all_gather_into_tensor(gathered, out)
+            if rank == 0:
+                host_out.copy_(gathered, non_blocking=True)
+        else:
+            host_out.copy_(out, non_blocking=True)
+        barrier()
+        wall = time.perf_counter() - t0
+        tw = torch.tensor([wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        wall = float(tw.item())
+        e2e = {"value": B * world / wall, "unit": "tiles/s",
+               "h2d_bytes_per_step": host_in.numel() * 4 / T_FULL, "d2h_bytes_per_step": B * world * 64 * 64 * 4 / T_FULL,
+               "call": ("GaussianDiffusion.super_resolution" if okw["self_condition"] else "GaussianDiffusion.sample")
+                       + f" (one call = {T_FULL} steps)", "seconds_per_call": wall, "steps_per_call": T_FULL,
+               "h2d_bytes_per_call": host_in.numel() * 4, "d2h_bytes_per_call": B * world * 64 * 64 * 4}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        b = 8 if name.startswith("unet") else 2
+        sec = cpu_steps(name, wl["schedule"], b, 3 if name.startswith("unet") else 1, 1)
+        cpu = {"value": b / (sec * T_FULL), "unit": "tiles/s", "cores": cores, "kind": "port",
+               "sample": f"3 p_sample steps of {b} tiles after 1 warm-up ({sec * 1e3:.0f} ms/step), extrapolated to T={T_FULL}"}
+
+    if rank == 0:
+        line = {
+            "metric": "tiles_per_sec_T1000", "value": tiles_s, "unit": "tiles/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"{wl['desc']}, batch {B} synthetic 64x64 tiles per GPU, random-init weights (seed 0)",
+                       "tiles_per_gpu": B, "timesteps": T_FULL, "schedule": wl["schedule"], "parallelism": f"tile-shard x{world}",
+                       "noise": "in-kernel Philox4x32-10", "cache": "working set >> 126 MB L2 (one 64-ch 64x64 activation = "
+                       f"{B * 4096 * 64 * 2 / 2**20:.0f} MiB); no flush needed",
+                       "step": "one reverse-diffusion step (eps-net + posterior) as one CUDA graph launch"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": step_launches * K + (K + T_FULL - 1) // T_FULL, "launches_per_step": step_launches, "clocks": clocks,
+            "device_bytes": plan.device_bytes(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run so `python bench.py --gpus N` also works
+        port = 29500 + os.getpid() % 1000
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), str(Path(__file__).resolve()), *sys.argv[1:]]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+    else:
+        run_b200_arm(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,7 @@ SIGNATURES = {
     "hd_debug_read": (C.c_int, [_vp, _i32, C.c_char_p, _vp, C.POINTER(_i64), C.POINTER(_i32), _vp]),
     "hd_debug_names": (C.c_int, [_vp, _i32, C.c_char_p, _i64]),
     "hd_plan_launches_per_step": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
+    "hd_plan_profile_step": (C.c_int, [_vp, _i32, _i32, C.c_char_p, _i64, _vp]),
     "hd_plan_device_bytes": (_i64, [_vp]),
     "hd_last_error": (C.c_char_p, []),
     "hd_abi_version": (C.c_int, []),

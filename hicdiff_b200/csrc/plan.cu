@@ -102,6 +102,9 @@ struct Arena {
 struct Op {
     std::function<cudaError_t(cudaStream_t)> fn;
     std::string tag;
+    const char* kernel = "";   // kernel family (for the profile breakdown)
+    double flops = 0;          // algorithmic FLOPs of one launch (2*M*N*K for the GEMMs)
+    double bytes = 0;          // algorithmic HBM bytes of one launch (each operand read / written once)
 };
 
 struct FilmSlot {
@@ -277,7 +280,14 @@ struct Builder {
             ConvGemmLaunch l;
             char e[256];
             if (conv_gemm_prepare(d, P->num_sms, &l, e, sizeof(e))) { bad(std::string(wkey) + ": " + e); return y; }
-            ops->push_back({[l](cudaStream_t s) { return conv_gemm_run(l, s); }, wkey});
+            Op op{[l](cudaStream_t s) { return conv_gemm_run(l, s); }, wkey};
+            op.kernel = "conv_gemm";
+            const double M = static_cast<double>(B) * Ho * Wo;
+            const double K = static_cast<double>(l.nkb) * 64;
+            op.flops = 2.0 * M * Cout * K;
+            op.bytes = 2.0 * (M * (x0.C + (x1 ? x1->C : 0)) * (mode == CONV_UNSHUFFLE ? 4 : 1) + static_cast<double>(N) * K) +
+                       (epi.out_f32 ? 4.0 * M * epi.n_valid : 2.0 * M * N) + (epi.res ? 2.0 * M * N : 0.0);
+            ops->push_back(op);
         }
         return y;
     }
@@ -299,7 +309,10 @@ struct Builder {
         if (postadd_off >= 0) { g.postadd = film.base; g.postadd_off = postadd_off; }
         if (res) g.res = res->p;
         if (!ok || dry) return;
-        ops->push_back({[g](cudaStream_t s) { return groupnorm_film_silu_run(g, s); }, prefix});
+        Op op{[g](cudaStream_t s) { return groupnorm_film_silu_run(g, s); }, prefix};
+        op.kernel = "groupnorm_film_silu";
+        op.bytes = 2.0 * B * x.H * x.W * x.C * (res ? 3 : 2);
+        ops->push_back(op);
     }
 
     Act layernorm(const Act& x, const std::string& gkey, const Act* res, bool up2x) {
@@ -307,7 +320,12 @@ struct Builder {
         LayerNormArgs l;
         l.x = x.p; l.y = y.p; l.M = B * x.H * x.W; l.C = x.C; l.g = wf(gkey); l.eps = 1e-5f;
         l.res = res ? res->p : nullptr; l.upsample2x = up2x ? 1 : 0; l.H = x.H; l.W = x.W;
-        if (ok && !dry) ops->push_back({[l](cudaStream_t s) { return channel_layernorm_run(l, s); }, gkey});
+        if (ok && !dry) {
+            Op op{[l](cudaStream_t s) { return channel_layernorm_run(l, s); }, gkey};
+            op.kernel = "channel_layernorm";
+            op.bytes = 2.0 * B * x.H * x.W * x.C * (1 + (up2x ? 4 : 1) + (res ? 1 : 0));
+            ops->push_back(op);
+        }
         return y;
     }
 
@@ -346,7 +364,14 @@ struct Builder {
         Act att = alloc_act(x.H, x.W, 128);
         LinAttnArgs la;
         la.qkv = qkv.p; la.out = att.p; la.ctx = dry ? nullptr : ex->ctx; la.B = B; la.n = x.H * x.W;
-        if (ok && !dry) ops->push_back({[la](cudaStream_t s) { return linear_attention_run(la, s); }, p + ".linattn"});
+        if (ok && !dry) {
+            Op op{[la](cudaStream_t s) { return linear_attention_run(la, s); }, p + ".linattn"};
+            op.kernel = "linear_attention";
+            const double n = static_cast<double>(x.H) * x.W;
+            op.flops = 2.0 * 2.0 * B * 4 * 32 * 32 * n;
+            op.bytes = 2.0 * B * n * (384 + 256 + 128);   // k,v twice (max pass + ctx pass), q once, out once
+            ops->push_back(op);
+        }
         free_act(qkv);
         note(p + ".attn_core", att);
         Act o = conv(p + ".fn.fn.to_out.0.weight", p + ".fn.fn.to_out.0.bias", att, nullptr, x.C, 1, CONV_TAPS, ConvEpilogue());
@@ -365,7 +390,14 @@ struct Builder {
         Act att = alloc_act(x.H, x.W, 128);
         FullAttnArgs fa;
         fa.qkv = qkv.p; fa.out = att.p; fa.B = B; fa.n = x.H * x.W;
-        if (ok && !dry) ops->push_back({[fa](cudaStream_t s) { return full_attention_run(fa, s); }, p + ".attn"});
+        if (ok && !dry) {
+            Op op{[fa](cudaStream_t s) { return full_attention_run(fa, s); }, p + ".attn"};
+            op.kernel = "full_attention";
+            const double n = static_cast<double>(x.H) * x.W;
+            op.flops = 2.0 * 2.0 * B * 4 * 32 * n * n;
+            op.bytes = 2.0 * B * n * (384 + 128);
+            ops->push_back(op);
+        }
         free_act(qkv);
         ConvEpilogue e;
         e.res = x.p; e.ldr = x.C;
@@ -383,7 +415,13 @@ struct Builder {
         a.x1 = P->cfg.self_condition ? (dry ? nullptr : ex->x) : nullptr;
         a.w = wf(wkey); a.bias = wf(bkey); a.y = y.p;
         a.B = B; a.H = S; a.W = S; a.Cout = Cout; a.Cin = P->cfg.self_condition ? 2 : 1; a.ksize = ksize;
-        if (ok && !dry) ops->push_back({[a](cudaStream_t s) { return stem_conv_run(a, s); }, wkey});
+        if (ok && !dry) {
+            Op op{[a](cudaStream_t s) { return stem_conv_run(a, s); }, wkey};
+            op.kernel = "stem_conv";
+            op.flops = 2.0 * B * S * S * Cout * a.Cin * ksize * ksize;
+            op.bytes = 4.0 * B * S * S * a.Cin + 2.0 * B * S * S * Cout;
+            ops->push_back(op);
+        }
         return y;
     }
 
@@ -450,7 +488,13 @@ struct Builder {
         HeadConvArgs hca;
         hca.x = f.p; hca.w = wf("final_conv.weight"); hca.bias = wf("final_conv.bias");
         hca.eps = dry ? nullptr : ex->eps; hca.M = B * c.image_size * c.image_size; hca.C = dim;
-        if (ok && !dry) ops->push_back({[hca](cudaStream_t s) { return head_conv1x1_run(hca, s); }, "final_conv"});
+        if (ok && !dry) {
+            Op op{[hca](cudaStream_t s) { return head_conv1x1_run(hca, s); }, "final_conv"};
+            op.kernel = "head_conv1x1";
+            op.flops = 2.0 * hca.M * dim;
+            op.bytes = 2.0 * hca.M * dim + 4.0 * hca.M;
+            ops->push_back(op);
+        }
         free_act(f);
     }
 
@@ -606,9 +650,14 @@ int get_exec(hd_plan* P, int B, cudaStream_t s, Exec** out) {
         PosteriorArgs pa;
         pa.x = ex->x; pa.eps = ex->eps; pa.coef = P->coef; pa.ctl = P->ctl; pa.T = P->T;
         pa.n = static_cast<long long>(B) * tile; pa.tile_elems = static_cast<int>(tile); pa.x0_out = nullptr;
-        ex->ops_table.push_back({[pa](cudaStream_t st) { return posterior_step_run(pa, st); }, "posterior"});
+        Op pop{[pa](cudaStream_t st) { return posterior_step_run(pa, st); }, "posterior"};
+        pop.kernel = "posterior_step";
+        pop.bytes = 12.0 * pa.n;   // x read + eps read + x write (Philox noise is generated in-kernel)
+        ex->ops_table.push_back(pop);
         SampleCtl* ctl = P->ctl;
-        ex->ops_table.push_back({[ctl](cudaStream_t st) { return step_advance_run(ctl, -1, st); }, "step--"});
+        Op aop{[ctl](cudaStream_t st) { return step_advance_run(ctl, -1, st); }, "step--"};
+        aop.kernel = "step_advance";
+        ex->ops_table.push_back(aop);
     }
     // eager validation pass (surfaces launch-configuration errors with the op name), then capture
     {
@@ -1095,6 +1144,44 @@ int hd_plan_launches_per_step(hd_plan* P, int32_t B, int32_t* eps_launches, int3
     };
     if (eps_launches) *eps_launches = count(it->second->ops_rows);
     if (step_launches) *step_launches = count(it->second->ops_table);
+    return 0;
+}
+
+int hd_plan_profile_step(hd_plan* P, int32_t B, int32_t reps, char* buf, int64_t buflen, void* stream) {
+    if (!P || !buf || buflen <= 0 || reps <= 0) return fail("hd_plan_profile_step: bad argument");
+    if (ensure_device(P)) return 1;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Exec* ex = nullptr;
+    if (get_exec(P, B, s, &ex)) return 1;
+    if (set_ctl(P->ctl, P->T - 1, 0, nullptr, 1, 0, s)) return 1;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    std::string out = "[";
+    bool first = true;
+    for (const Op& op : ex->ops_table) {
+        if (strcmp(op.kernel, "step_advance") == 0) continue;   // would walk the step counter off the table
+        cudaError_t e = op.fn(s);   // warm-up
+        if (e == cudaSuccess) e = cudaEventRecord(e0, s);
+        for (int r = 0; r < reps && e == cudaSuccess; ++r) e = op.fn(s);
+        if (e == cudaSuccess) e = cudaEventRecord(e1, s);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e != cudaSuccess) {
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+            return fail("profiling '%s' failed: %s", op.tag.c_str(), cudaGetErrorString(e));
+        }
+        char line[512];
+        snprintf(line, sizeof(line), "%s{\"tag\":\"%s\",\"kernel\":\"%s\",\"ms\":%.6f,\"flops\":%.6e,\"bytes\":%.6e}",
+                 first ? "" : ",", op.tag.c_str(), op.kernel, ms / reps, op.flops, op.bytes);
+        out += line;
+        first = false;
+    }
+    out += "]";
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (static_cast<int64_t>(out.size()) + 1 > buflen) return fail("hd_plan_profile_step: buffer too small (%zu needed)", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
     return 0;
 }
 

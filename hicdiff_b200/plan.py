@@ -189,6 +189,17 @@ class EpsPlan:
         _lib.check(lib.hd_plan_launches_per_step(h, batch, C.byref(a), C.byref(b)), "hd_plan_launches_per_step")
         return a.value, b.value
 
+    def profile_step(self, batch: int, reps: int = 10):
+        """Per-launch average ms + algorithmic FLOPs/bytes of one sampling step (list of dicts)."""
+        import json
+
+        lib = _lib.load()
+        h = self._ensure()
+        buf = C.create_string_buffer(1 << 18)
+        with torch.cuda.device(self._device()):
+            _lib.check(lib.hd_plan_profile_step(h, batch, reps, buf, len(buf), _lib.stream_ptr()), "hd_plan_profile_step")
+        return json.loads(buf.value.decode())
+
     def device_bytes(self) -> int:
         return int(_lib.load().hd_plan_device_bytes(self._ensure()))
 

@@ -142,6 +142,10 @@ HD_API int hd_debug_names(hd_plan* plan, int32_t B, char* buf, int64_t buflen);
 
 /* Number of kernels the plan launches per hd_eps_forward / per sampling step at batch B (for gpu_launches). */
 HD_API int hd_plan_launches_per_step(hd_plan* plan, int32_t B, int32_t* eps_launches, int32_t* step_launches);
+/* Built-in profiler: runs every kernel launch of one sampling step at batch B `reps` times between CUDA events on
+ * `stream` and writes a JSON array [{"tag","kernel","ms","flops","bytes"}, ...] (average ms per launch, algorithmic
+ * FLOPs / HBM bytes per launch) into buf.  Synchronises. */
+HD_API int hd_plan_profile_step(hd_plan* plan, int32_t B, int32_t reps, char* buf, int64_t buflen, void* stream);
 /* Device bytes held by the plan (weights + tables + workspaces). */
 HD_API int64_t hd_plan_device_bytes(hd_plan* plan);
 

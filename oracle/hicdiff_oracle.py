@@ -403,27 +403,9 @@ def reassemble(tiles: np.ndarray, n: int, piece: int = 64, res: int = 40000) -> 
 
 
 # --------------------------------------------------------------------------------------------------------------
-# Synthetic inputs shared by tests, bench and the golden generator
+# Synthetic inputs: plain data generators shared with the tests / bench
 # --------------------------------------------------------------------------------------------------------------
-
-
-def synthetic_tiles(batch: int, seed: int = 1234, sigma: float = 0.1):
-    """(clean, noisy): clean symmetric band-decay tiles in [-1, 1]; noisy = clean + sigma * randn
-    (mirrors processdata/PrepareData_linear.py:203-204)."""
-    g = torch.Generator().manual_seed(seed)
-    idx = torch.arange(64)
-    d = (idx[:, None] - idx[None, :]).abs().float()
-    u = torch.rand(batch, 1, 64, 64, generator=g)
-    u = 0.5 * (u + u.transpose(-1, -2))
-    clean = (2 * torch.exp(-d / 8) * (0.6 + 0.4 * u) - 1).clamp(-1, 1)
-    noisy = clean + sigma * torch.randn(batch, 1, 64, 64, generator=g)
-    return clean, noisy
-
-
-def synthetic_noise(timesteps: int, batch: int, seed: int = 2024):
-    g = torch.Generator().manual_seed(seed)
-    return torch.randn(timesteps, batch, 1, 64, 64, generator=g)
-
+from hicdiff_b200.synthetic import synthetic_noise, synthetic_tiles  # noqa: E402,F401
 
 # --------------------------------------------------------------------------------------------------------------
 # Quality metrics used for the 1e-3 SSIM/PSNR bar            src/Utils/loss/SSIM.py:6-74,
