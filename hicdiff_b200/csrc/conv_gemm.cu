@@ -30,7 +30,10 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                 // 64 bf16 = one 128-byte swizzle span
 constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_BUDGET = 192 * 1024;     // operand ring; + 32 KiB of epilogue staging stays under the 227 KiB limit
+constexpr int EPI_WARPS = 4;
+constexpr uint32_t EPI_BUF_BYTES = 32 * 128;                      // 32 rows x 64 bf16, 128B-swizzled TMA-store box
+constexpr uint32_t EPI_STAGE_BYTES = EPI_WARPS * 2 * EPI_BUF_BYTES;   // two buffers per epilogue warp
 
 template <int BN>
 struct TileCfg {
@@ -40,7 +43,7 @@ struct TileCfg {
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                           : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct KArgs {
@@ -50,12 +53,12 @@ struct KArgs {
     int ldo;
 };
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmB, const KArgs a) {
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD, const KArgs a) {
     using Cfg = TileCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
 
@@ -63,7 +66,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_STAGE_BYTES);
+    uint8_t* sEpi = sB + STAGES * Cfg::B_STAGE_BYTES;      // 1024-aligned: all stage sizes are multiples of 1 KiB
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpi + EPI_STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
@@ -77,6 +81,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             ptx::prefetch_tmap(&tmA0);
             ptx::prefetch_tmap(&tmA1);
             ptx::prefetch_tmap(&tmB);
+            ptx::prefetch_tmap(&tmD);
         }
         __syncwarp();
         ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -166,10 +171,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
     } else {
         // ------------------------------------------------------------------ epilogue (4 warps)
+        // Each warp owns 32 accumulator rows (its TMEM lane quarter).  bf16 output goes through a per-warp, 128B-swizzled
+        // staging buffer and leaves as TMA tensor stores of 32 x 64 boxes (full-line writes, rows past M are clipped
+        // by the TMA unit); the fp32 head path (N padded to 16, one valid column) stores directly.
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;            // accumulator row == pixel within the tile
         const ConvEpilogue& e = a.epi;
-        constexpr int CH = (BN >= 32) ? 32 : 16;
+        uint8_t* my_stage = sEpi + q * (2 * EPI_BUF_BYTES);
+        int buf = 0;
         int iter = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
             const int mt = tile / a.num_n_tiles;
@@ -192,18 +201,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
 
-#pragma unroll 1
-            for (int c = 0; c < BN; c += CH) {
-                uint32_t v[CH];
-                if constexpr (CH == 32) ptx::tmem_ld32(taddr + c, v); else ptx::tmem_ld16(taddr + c, v);
-                ptx::tmem_ld_wait();
-                const int n = n0 + c;
-                float f[CH];
-#pragma unroll
-                for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[j]);
+            auto finish = [&](float (&f)[32], int n) {      // bias / FiLM / SiLU / scale / residual on 32 columns
                 if (e.bias != nullptr) {
 #pragma unroll
-                    for (int j = 0; j < CH; j += 4) {
+                    for (int j = 0; j < 32; j += 4) {
                         const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + n + j));
                         f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
                     }
@@ -211,59 +212,157 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 if (frow != nullptr) {
                     if (e.film_has_scale) {
 #pragma unroll
-                        for (int j = 0; j < CH; j += 4) {
+                        for (int j = 0; j < 32; j += 4) {
                             const float4 sc = __ldg(reinterpret_cast<const float4*>(frow + n + j));
                             f[j] *= (sc.x + 1.0f); f[j + 1] *= (sc.y + 1.0f);
                             f[j + 2] *= (sc.z + 1.0f); f[j + 3] *= (sc.w + 1.0f);
                         }
                     }
 #pragma unroll
-                    for (int j = 0; j < CH; j += 4) {
+                    for (int j = 0; j < 32; j += 4) {
                         const float4 sh = __ldg(reinterpret_cast<const float4*>(frow + shift_off + n + j));
                         f[j] += sh.x; f[j + 1] += sh.y; f[j + 2] += sh.z; f[j + 3] += sh.w;
                     }
                 }
                 if (e.silu) {
 #pragma unroll
-                    for (int j = 0; j < CH; ++j) f[j] = silu_f(f[j]);
+                    for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
                 }
                 if (e.out_scale != 1.0f) {
 #pragma unroll
-                    for (int j = 0; j < CH; ++j) f[j] *= e.out_scale;
+                    for (int j = 0; j < 32; ++j) f[j] *= e.out_scale;
                 }
-                if (valid) {
-                    if (e.res != nullptr) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(e.res + static_cast<size_t>(m) * e.ldr + n);
+                if (e.res != nullptr && valid) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(e.res + static_cast<size_t>(m) * e.ldr + n);
 #pragma unroll
-                        for (int j = 0; j < CH; j += 8) {
-                            const uint4 rr = __ldg(rp + j / 8);
-                            float2 t;
-                            t = ptx::unpack_bf16x2(rr.x); f[j] += t.x; f[j + 1] += t.y;
-                            t = ptx::unpack_bf16x2(rr.y); f[j + 2] += t.x; f[j + 3] += t.y;
-                            t = ptx::unpack_bf16x2(rr.z); f[j + 4] += t.x; f[j + 5] += t.y;
-                            t = ptx::unpack_bf16x2(rr.w); f[j + 6] += t.x; f[j + 7] += t.y;
+                    for (int j = 0; j < 32; j += 8) {
+                        const uint4 rr = __ldg(rp + j / 8);
+                        float2 t;
+                        t = ptx::unpack_bf16x2(rr.x); f[j] += t.x; f[j + 1] += t.y;
+                        t = ptx::unpack_bf16x2(rr.y); f[j + 2] += t.x; f[j + 3] += t.y;
+                        t = ptx::unpack_bf16x2(rr.z); f[j + 4] += t.x; f[j + 5] += t.y;
+                        t = ptx::unpack_bf16x2(rr.w); f[j + 6] += t.x; f[j + 7] += t.y;
+                    }
+                }
+            };
+
+            if constexpr (BN < 64) {
+                // fp32 head (tail conv of HiCEDRN): 16 accumulator columns, n_valid of them real
+                uint32_t v[16];
+                ptx::tmem_ld16(taddr, v);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&tempty_bar[as]);
+                if (valid && e.out_f32 != nullptr) {
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + j < e.n_valid) {
+                            float val = __uint_as_float(v[j]) + (e.bias != nullptr ? __ldg(e.bias + n0 + j) : 0.f);
+                            if (e.res != nullptr) val += __bfloat162float(e.res[static_cast<size_t>(m) * e.ldr + n0 + j]);
+                            e.out_f32[static_cast<size_t>(m) * e.n_valid + n0 + j] = val;
+                        }
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 64) {
+                    uint32_t v0[32], v1[32];
+                    ptx::tmem_ld32(taddr + c, v0);
+                    ptx::tmem_ld32(taddr + c + 32, v1);
+                    ptx::tmem_ld_wait();
+                    if (c + 64 == BN) {          // accumulator fully drained: hand the TMEM stage back to the MMA warp
+                        ptx::tc_fence_before();
+                        ptx::mbar_arrive(&tempty_bar[as]);
+                    }
+                    float f0[32], f1[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { f0[j] = __uint_as_float(v0[j]); f1[j] = __uint_as_float(v1[j]); }
+                    finish(f0, n0 + c);
+                    finish(f1, n0 + c + 32);
+                    if (e.gn_part != nullptr) {
+                        // GroupNorm partials of this warp's 32 rows x 64 columns (rows are all valid: M % 32 == 0).
+                        const int lg = 31 - __clz(a.N >> 6);            // log2(pieces of 8 columns per group)
+                        float ps[8];
+#pragma unroll
+                        for (int p8 = 0; p8 < 8; ++p8) {
+                            float t = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) t += (p8 < 4) ? f0[8 * p8 + j] : f1[8 * (p8 - 4) + j];
+#pragma unroll
+                            for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+                            ps[p8] = t;
+                        }
+                        const float inv_cnt = 1.0f / (32.0f * static_cast<float>(a.N >> 3));
+                        float gsum[8], pmean[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            float t = 0.f;
+#pragma unroll
+                            for (int p8 = 0; p8 < 8; ++p8) t += ((p8 >> lg) == k) ? ps[p8] : 0.f;
+                            gsum[k] = t;
+                        }
+#pragma unroll
+                        for (int p8 = 0; p8 < 8; ++p8) {
+                            float t = 0.f;
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) t = ((p8 >> lg) == k) ? gsum[k] * inv_cnt : t;
+                            pmean[p8] = t;
+                        }
+#pragma unroll
+                        for (int p8 = 0; p8 < 8; ++p8) {
+                            float t = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float dlt = ((p8 < 4) ? f0[8 * p8 + j] : f1[8 * (p8 - 4) + j]) - pmean[p8];
+                                t = fmaf(dlt, dlt, t);
+                            }
+#pragma unroll
+                            for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+                            ps[p8] = t;
+                        }
+                        if (lane == 0 && valid) {
+                            const int ngroups = 8 >> lg;                         // groups inside this 64-column chunk
+                            const int g0 = (n0 + c) / (a.N >> 3);                // first global group of the chunk
+                            float2* dst = e.gn_part + (static_cast<size_t>(mt) * 4 + q) * 8 + g0;
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                float m2 = 0.f;
+#pragma unroll
+                                for (int p8 = 0; p8 < 8; ++p8) m2 += ((p8 >> lg) == k) ? ps[p8] : 0.f;
+                                if (k < ngroups) dst[k] = make_float2(gsum[k], m2);
+                            }
                         }
                     }
-                    if (e.out_f32 != nullptr) {
-                        for (int j = 0; j < CH; ++j)
-                            if (n + j < e.n_valid) e.out_f32[static_cast<size_t>(m) * e.n_valid + n + j] = f[j];
-                    } else {
-                        uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(m) * a.ldo + n);
+                    // staging buffer free?  (at most one older store of this warp may still be reading the OTHER buffer)
+                    if (lane == 0) ptx::bulk_wait_read<1>();
+                    __syncwarp();
+                    uint8_t* stage_row = my_stage + buf * EPI_BUF_BYTES + lane * 128;
+                    const int sw = lane & 7;
 #pragma unroll
-                        for (int j = 0; j < CH; j += 8) {
-                            uint4 o;
-                            o.x = ptx::pack_bf16x2(f[j], f[j + 1]);
-                            o.y = ptx::pack_bf16x2(f[j + 2], f[j + 3]);
-                            o.z = ptx::pack_bf16x2(f[j + 4], f[j + 5]);
-                            o.w = ptx::pack_bf16x2(f[j + 6], f[j + 7]);
-                            op[j / 8] = o;
-                        }
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 o;
+                        o.x = ptx::pack_bf16x2(f0[8 * j], f0[8 * j + 1]);
+                        o.y = ptx::pack_bf16x2(f0[8 * j + 2], f0[8 * j + 3]);
+                        o.z = ptx::pack_bf16x2(f0[8 * j + 4], f0[8 * j + 5]);
+                        o.w = ptx::pack_bf16x2(f0[8 * j + 6], f0[8 * j + 7]);
+                        *reinterpret_cast<uint4*>(stage_row + ((j ^ sw) << 4)) = o;
+                        uint4 p;
+                        p.x = ptx::pack_bf16x2(f1[8 * j], f1[8 * j + 1]);
+                        p.y = ptx::pack_bf16x2(f1[8 * j + 2], f1[8 * j + 3]);
+                        p.z = ptx::pack_bf16x2(f1[8 * j + 4], f1[8 * j + 5]);
+                        p.w = ptx::pack_bf16x2(f1[8 * j + 6], f1[8 * j + 7]);
+                        *reinterpret_cast<uint4*>(stage_row + (((j + 4) ^ sw) << 4)) = p;
                     }
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_2d(&tmD, my_stage + buf * EPI_BUF_BYTES, n0 + c, mt * BLOCK_M + q * 32);
+                        ptx::bulk_commit();
+                    }
+                    buf ^= 1;
                 }
             }
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(&tempty_bar[as]);
         }
+        if (lane == 0) ptx::bulk_wait_all();    // all tensor stores of this warp have landed before the CTA retires
+        __syncwarp();
     }
 
     ptx::tc_fence_before();
@@ -338,7 +437,7 @@ cudaError_t launch_bn(const ConvGemmLaunch& l, cudaStream_t s) {
     k.M = l.M; k.N = l.N; k.num_m_tiles = l.num_m_tiles; k.num_n_tiles = l.num_n_tiles; k.nkb = l.nkb;
     k.chunks0 = l.chunks0; k.chunks1 = l.chunks1; k.mode = l.mode; k.W = l.W; k.P = l.P; k.kw = l.kw; k.pad = l.pad;
     k.epi = l.epi; k.out = l.out; k.ldo = l.ldo;
-    conv_gemm_kernel<BN><<<l.grid, NUM_THREADS, TileCfg<BN>::SMEM_BYTES, s>>>(l.tmA0, l.tmA1, l.tmB, k);
+    conv_gemm_kernel<BN><<<l.grid, NUM_THREADS, TileCfg<BN>::SMEM_BYTES, s>>>(l.tmA0, l.tmA1, l.tmB, l.tmD, k);
     return cudaGetLastError();
 }
 
@@ -407,6 +506,22 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
     cuuint64_t ws[1] = {Ktot * 2};
     cuuint32_t wb[2] = {BLOCK_K, (cuuint32_t)bn};
     if (encode_map(&out->tmB, d.weight, 2, wd, ws, wb, err, errlen)) return 1;
+    if (d.epi.out_f32 == nullptr) {
+        if (bn < 64 || d.out == nullptr) {
+            snprintf(err, errlen, "conv_gemm: bf16 output needs an N tile >= 64 and an output buffer");
+            return 1;
+        }
+        cuuint64_t od[2] = {(cuuint64_t)d.N, (cuuint64_t)M};
+        cuuint64_t os[1] = {(cuuint64_t)d.N * 2};
+        cuuint32_t ob[2] = {64, 32};
+        if (encode_map(&out->tmD, d.out, 2, od, os, ob, err, errlen)) return 1;
+    } else {
+        if (bn >= 64) {
+            snprintf(err, errlen, "conv_gemm: the fp32 head path is built for N <= 48 (padded to 16-column tiles)");
+            return 1;
+        }
+        out->tmD = out->tmB;   // unused by the fp32 head path
+    }
     switch (bn) {
         case 256: out->smem_bytes = TileCfg<256>::SMEM_BYTES; break;
         case 128: out->smem_bytes = TileCfg<128>::SMEM_BYTES; break;

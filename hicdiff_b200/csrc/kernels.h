@@ -42,6 +42,9 @@ struct ConvEpilogue {
     int ldr = 0;
     float* out_f32 = nullptr;         // if set: write fp32 [M, n_valid] instead of bf16
     int n_valid = 0;
+    // GroupNorm(8) statistics of THIS conv's output, from the fp32 accumulators (+bias): one (sum, M2) pair per
+    // (32-row warp block, group), M2 = sum of squared deviations from the block's own mean (merged stably later).
+    float2* gn_part = nullptr;        // [M / 32][8]
 };
 
 struct ConvGemmDesc {
@@ -57,7 +60,7 @@ struct ConvGemmDesc {
 
 // Opaque prepared launch (tensor maps encoded once, replayed inside CUDA graphs).
 struct ConvGemmLaunch {
-    CUtensorMap tmA0, tmA1, tmB;
+    CUtensorMap tmA0, tmA1, tmB, tmD;
     int bn;             // N tile (16, 64, 128 or 256)
     int grid;
     int smem_bytes;
@@ -79,6 +82,7 @@ struct GroupNormArgs {
     const bf16* x;        // [B, P, C]
     bf16* y;              // [B, P, C]
     int B, P, C;          // P = H*W pixels
+    const float2* part;   // [B * P / 32][8] (sum, M2) partials written by the producing conv (or groupnorm_stats_run)
     const float* gamma;   // [C]
     const float* beta;    // [C]
     float eps;
@@ -94,6 +98,8 @@ struct GroupNormArgs {
     const bf16* res = nullptr;        // + res[b, p, c] after the activation (ResnetBlock skip)
 };
 cudaError_t groupnorm_film_silu_run(const GroupNormArgs& a, cudaStream_t s);
+// Stand-alone producer of the same partials from a bf16 tensor (used when the input does not come from conv_gemm).
+cudaError_t groupnorm_stats_run(const bf16* x, float2* part, int B, int P, int C, cudaStream_t s);
 
 struct LayerNormArgs {
     const bf16* x;    // [M, C]
@@ -113,7 +119,7 @@ cudaError_t channel_layernorm_run(const LayerNormArgs& a, cudaStream_t s);
 struct LinAttnArgs {
     const bf16* qkv;   // [B, n, 384]: q = [0,128), k = [128,256), v = [256,384); head h owns 32 channels
     bf16* out;         // [B, n, 128]
-    float* ctx;        // scratch [B, 4, 32, 32] fp32
+    float* ctx;        // scratch, >= B*4*32*32*2 bytes: normalised ctx^T[b][head][e][d] in bf16
     int B, n;
 };
 cudaError_t linear_attention_run(const LinAttnArgs& a, cudaStream_t s);

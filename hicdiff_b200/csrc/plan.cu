@@ -133,6 +133,7 @@ struct Exec {
     float* film_rows = nullptr;  // [B, film_ld]
     int* iota = nullptr;     // [B]
     float* ctx = nullptr;    // linear-attention scratch [B,4,32,32]
+    float2* gn_part = nullptr;  // GroupNorm partial statistics [B*4096/32][8], rewritten by every GN-feeding conv
     std::vector<Op> ops_rows, ops_table;
     cudaGraphExec_t g_eps = nullptr, g_step = nullptr;
     std::map<std::string, DebugEntry> dbg;
@@ -260,13 +261,14 @@ struct Builder {
 
     // conv on the tcgen05 path
     Act conv(const std::string& wkey, const std::string& bkey, const Act& x0, const Act* x1, int Cout, int ksize,
-             ConvMode mode, ConvEpilogue epi, int n_rows = 0) {
+             ConvMode mode, ConvEpilogue epi, int n_rows = 0, bool gn_stats = false) {
         const int Ho = mode == CONV_UNSHUFFLE ? x0.H / 2 : x0.H;
         const int Wo = mode == CONV_UNSHUFFLE ? x0.W / 2 : x0.W;
         const int N = n_rows ? n_rows : Cout;
         Act y;
         if (epi.out_f32 == nullptr) y = alloc_act(Ho, Wo, N); else { y.H = Ho; y.W = Wo; y.C = N; }
         if (!bkey.empty()) epi.bias = n_rows ? padded_bias(bkey) : wf(bkey);
+        if (gn_stats) epi.gn_part = dry ? nullptr : ex->gn_part;
         ConvGemmDesc d;
         d.src0 = ConvSrc{x0.p, x0.C};
         d.src1 = ConvSrc{x1 ? x1->p : nullptr, x1 ? x1->C : 0};
@@ -301,6 +303,7 @@ struct Builder {
         GroupNormArgs g;
         g.x = x.p; g.y = x.p;   // in place: each CTA stages its own slab in smem before writing it back
         g.B = B; g.P = x.H * x.W; g.C = x.C;
+        g.part = dry ? nullptr : ex->gn_part;
         g.gamma = wf(prefix + ".weight");
         g.beta = wf(prefix + ".bias");
         g.eps = 1e-5f;
@@ -332,7 +335,7 @@ struct Builder {
     // ResnetBlock (hicdiff_condition.py:173-197 / hicdiff_sr3.py:235-251)
     Act resblock(const std::string& p, const Act& x0, const Act* x1, int Cout) {
         const int Cin = x0.C + (x1 ? x1->C : 0);
-        Act h = conv(p + ".block1.proj.weight", p + ".block1.proj.bias", x0, x1, Cout, 3, CONV_TAPS, ConvEpilogue());
+        Act h = conv(p + ".block1.proj.weight", p + ".block1.proj.bias", x0, x1, Cout, 3, CONV_TAPS, ConvEpilogue(), 0, true);
         note(p + ".block1.proj", h);
         const int slot = P->film_index.count(p) ? P->film_index[p] : -1;
         if (slot < 0) bad("no time-embedding slot for block " + p);
@@ -340,8 +343,7 @@ struct Builder {
         if (P->sr3) groupnorm(h, p + ".block1.norm", -1, off, nullptr);
         else groupnorm(h, p + ".block1.norm", off, -1, nullptr);
         note(p + ".block1", h);
-        Act h2 = conv(p + ".block2.proj.weight", p + ".block2.proj.bias", h, nullptr, Cout, 3, CONV_TAPS, ConvEpilogue());
-        free_act(h);
+        // res_conv first: block2's conv must be the last writer of the shared partial-statistics buffer before its norm
         Act r;
         bool own_r = false;
         if (Cin != Cout) {
@@ -350,6 +352,8 @@ struct Builder {
         } else {
             r = x0;
         }
+        Act h2 = conv(p + ".block2.proj.weight", p + ".block2.proj.bias", h, nullptr, Cout, 3, CONV_TAPS, ConvEpilogue(), 0, true);
+        free_act(h);
         groupnorm(h2, p + ".block2.norm", -1, -1, &r);
         if (own_r) free_act(r);
         note(p, h2);
@@ -551,7 +555,7 @@ void free_exec(Exec* ex) {
     if (ex->g_step) cudaGraphExecDestroy(ex->g_step);
     cudaFree(ex->arena); cudaFree(ex->x); cudaFree(ex->cond); cudaFree(ex->eps); cudaFree(ex->time);
     cudaFree(ex->posenc); cudaFree(ex->temb0); cudaFree(ex->temb); cudaFree(ex->film_rows); cudaFree(ex->iota);
-    cudaFree(ex->ctx);
+    cudaFree(ex->ctx); cudaFree(ex->gn_part);
 }
 
 int run_ops(const std::vector<Op>& ops, cudaStream_t s) {
@@ -615,6 +619,7 @@ int get_exec(hd_plan* P, int B, cudaStream_t s, Exec** out) {
     EX_TRY(cudaMalloc(&ex->film_rows, static_cast<size_t>(B) * P->film_ld * 4));
     EX_TRY(cudaMalloc(&ex->iota, B * 4));
     EX_TRY(cudaMalloc(&ex->ctx, static_cast<size_t>(B) * 4 * 32 * 32 * 4));
+    EX_TRY(cudaMalloc(&ex->gn_part, static_cast<size_t>(B) * (tile / 32) * 8 * sizeof(float2)));
     EX_TRY(cudaMemsetAsync(ex->x, 0, B * tile * 4, s));
     EX_TRY(cudaMemsetAsync(ex->cond, 0, B * tile * 4, s));
     EX_TRY(cudaMemsetAsync(ex->time, 0, B * 4, s));
@@ -1031,9 +1036,13 @@ int hd_op_groupnorm_silu(const uint16_t* x, uint16_t* y, const float* gamma, con
         g.film = row; g.film_row = zero; g.film_row_stride = 0; g.film_ld = 2 * C; g.film_off = 0;
     }
     if (res) g.res = reinterpret_cast<const bf16*>(res);
-    cudaError_t e = groupnorm_film_silu_run(g, s);
+    float2* part = nullptr;
+    CUDA_TRY(cudaMalloc(&part, static_cast<size_t>(B) * (P / 32 + 1) * 8 * sizeof(float2)));
+    g.part = part;
+    cudaError_t e = groupnorm_stats_run(g.x, part, B, P, C, s);
+    if (e == cudaSuccess) e = groupnorm_film_silu_run(g, s);
     cudaError_t e2 = cudaStreamSynchronize(s);
-    cudaFree(row); cudaFree(zero);
+    cudaFree(row); cudaFree(zero); cudaFree(part);
     if (e != cudaSuccess) return fail("groupnorm launch failed: %s", cudaGetErrorString(e));
     if (e2 != cudaSuccess) return fail("groupnorm kernel failed: %s", cudaGetErrorString(e2));
     return 0;

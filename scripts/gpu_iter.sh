@@ -1,0 +1,18 @@
+#!/bin/bash
+# quick iteration: per-op parity (selected groups) + short bench with the per-launch profile
+mkdir -p gpurun_out
+rm -f gpurun_out/iter.log
+for t in ${TESTS:-test_groupnorm test_channel_layernorm test_linear_attention}; do
+  echo "=== $t" | tee -a gpurun_out/iter.log
+  timeout 600 python -m pytest tests/test_ops_gpu.py -m gpu -q -k "$t" -p no:cacheprovider 2>&1 | tail -${TAILN:-12} | tee -a gpurun_out/iter.log
+done
+echo "=== eps" | tee -a gpurun_out/iter.log
+timeout 900 python -m pytest tests/test_eps_gpu.py -m gpu -q -p no:cacheprovider -k "golden" 2>&1 | tail -8 | tee -a gpurun_out/iter.log
+python bench.py --steps 50 --warmup 3 --no-e2e --no-cpu-baseline --profile-out gpurun_out/profile_iter.json > gpurun_out/bench_iter.json 2> gpurun_out/bench_iter.err
+tail -2 gpurun_out/bench_iter.err
+python - <<'PY' | tee -a gpurun_out/iter.log
+import json
+d=json.loads(open("gpurun_out/bench_iter.json").read().strip().splitlines()[-1])
+print("tiles/s", round(d["value"],3), "ms/step", round(d["ms_per_step"],3), "conv TF/s", round(d["roofline"]["achieved"],1), "step frac", round(d["roofline"]["whole_step"]["frac"],3))
+for k,v in d["roofline"]["families"].items(): print("   ",k,{a:round(b,3) for a,b in v.items()})
+PY
