@@ -4,18 +4,28 @@
 //   WeightStandardizedConv2d / Block.proj      /root/reference/src/hicdiff_condition.py:84-97,158
 //   to_qkv / to_out / res_conv / final 3x3     :183,205,208,236,237,320,336
 //   Downsample (pixel-unshuffle + 1x1)         :78-82
-//   Upsample's 3x3 (input already upsampled)   :72-76
+//   Upsample (nearest x2 + 3x3)                :72-76
 //   hicedrn_Diff Block.proj / body_tail / tail /root/reference/src/model/hicedrn_Diff.py:169-180,259,263
 //
-// GEMM view: D[M = B*H*W pixels, N = Cout] = A[M, K] * W[N, K]^T with K = taps * Cin.
-//   * A is never materialised: one K block = (filter tap, 64-channel chunk) and is fetched by ONE TMA box
-//     load {64 ch, W, rows, imgs} from the NHWC activation at spatial offset (dy, dx); out-of-bounds rows /
-//     columns are zero-filled by the TMA unit, which is exactly the conv's zero padding.
+// GEMM view: D[M = B*H*W pixels, N = Cout] = A[M, K] * W[N, K]^T with K = taps * Cin.  A is never materialised:
+//   * GENERAL path: one K block = (filter tap, 64-channel chunk), fetched by ONE TMA box load {64 ch, W, rows, imgs}
+//     from the NHWC activation at spatial offset (dy, dx); out-of-bounds rows / columns are zero-filled by the TMA
+//     unit, which is exactly the conv's zero padding.
+//   * SLAB path (3x3, W >= 16, N <= 128): one TMA box {64 ch, W, R + 2 rows} per (chunk, dx) serves the three dy
+//     taps -- the A descriptor of tap dy starts (dy + 1) * W pixel rows (a multiple of 1 KiB, so swizzle atoms stay
+//     aligned) into the slab.  One pipeline stage then carries 12 MMAs instead of 4, and the L2 -> SM traffic of the
+//     A operand drops from 9 to 3 * (R + 2) / R loads per pixel.  When the whole weight matrix fits (N == 64,
+//     K <= 1152: 72 / 144 KiB) it is loaded into shared memory ONCE per persistent CTA (SLAB_RES).
 //   * A channel concat (torch.cat((x, skip), 1)) is two tensor maps walked back to back inside each tap.
-//   * The pixel-unshuffle of Downsample is a 5-D view [C, p2, W/2, p1, B*H/2] of the same NHWC buffer.
-//   * tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN, K=16) accumulates into TMEM; two accumulator
-//     stages so the epilogue of tile i overlaps the MMAs of tile i+1; persistent CTAs, one per SM.
-//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue (TMEM -> regs -> global).
+//   * Downsample's pixel-unshuffle is a 5-D view [C, p2, W/2, p1, B*H/2] of the same NHWC buffer.
+//   * Upsample's nearest x2 is folded into the conv: output phase (a, b) = (y & 1, x & 1) is a 2x2 conv over the
+//     LOW-resolution input with pre-summed weights (prep.cu), K = 4*Cin instead of 9*Cin, and the upsampled tensor
+//     never exists; the epilogue scatters each phase through a 5-D tensor map of the output.
+//   * tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN, K=16) accumulates into TMEM; two accumulator stages so the
+//     epilogue of tile i overlaps the MMAs of tile i+1; persistent CTAs, one per SM.
+//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue (TMEM -> regs -> smem -> TMA
+//     store).  Producer and issuer loops are warp-uniform with one elected lane issuing (ncu showed the earlier
+//     `if (lane == 0)` form issue-bound: ~650 cycles of scalar code per K block, profiles/r01_conv_gemm_ncu.md).
 #include <cstdio>
 #include <cstring>
 
@@ -27,51 +37,126 @@ namespace hd {
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;                 // 64 bf16 = one 128-byte swizzle span
-constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int BLOCK_K = 64;                           // 64 bf16 = one 128-byte swizzle span
+constexpr uint32_t A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
+constexpr uint32_t SLAB_CAP_BYTES = 32 * 1024;        // (R + 2) * W pixels * 128 B: 32 / 24 / 20 KiB at W = 64 / 32 / 16
 constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BUDGET = 192 * 1024;     // operand ring; + 32 KiB of epilogue staging stays under the 227 KiB limit
+constexpr int MAX_STAGES = 8;
 constexpr int EPI_WARPS = 4;
-constexpr uint32_t EPI_BUF_BYTES = 32 * 128;                      // 32 rows x 64 bf16, 128B-swizzled TMA-store box
-constexpr uint32_t EPI_STAGE_BYTES = EPI_WARPS * 2 * EPI_BUF_BYTES;   // two buffers per epilogue warp
+constexpr uint32_t EPI_BUF_BYTES = 32 * 128;          // 32 rows x 64 bf16, 128B-swizzled TMA-store box
+constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int BAR_BYTES = 256;
 
-template <int BN>
-struct TileCfg {
-    static constexpr uint32_t B_STAGE_BYTES = BN * BLOCK_K * 2;
+enum Kind : int { K_GENERAL = 0, K_SLAB = 1, K_SLAB_RES = 2 };
+
+template <int BN, int KIND>
+struct Cfg {
+    static constexpr uint32_t B_BLOCK_BYTES = BN * BLOCK_K * 2;                   // one (N tile, K block) of weights
+    static constexpr uint32_t A_STAGE_BYTES = KIND == K_GENERAL ? A_TILE_BYTES : SLAB_CAP_BYTES;
+    static constexpr uint32_t B_STAGE_BYTES = KIND == K_GENERAL ? B_BLOCK_BYTES : (KIND == K_SLAB ? 3 * B_BLOCK_BYTES : 0);
     static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int EPI_BUFS = BN <= 64 ? 1 : 2;                             // staging buffers per epilogue warp
+    static constexpr uint32_t EPI_BYTES = EPI_WARPS * EPI_BUFS * EPI_BUF_BYTES;
     static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                           : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static int stages(uint32_t res_b_bytes) {
+        const int avail = SMEM_LIMIT - 1024 - BAR_BYTES - static_cast<int>(EPI_BYTES) - static_cast<int>(res_b_bytes);
+        int s = avail / static_cast<int>(STAGE_BYTES);
+        return s > MAX_STAGES ? MAX_STAGES : s;
+    }
+    static int smem_bytes(int stages, uint32_t res_b_bytes) {
+        return stages * STAGE_BYTES + res_b_bytes + EPI_BYTES + 1024 /*align*/ + BAR_BYTES;
+    }
 };
 
 struct KArgs {
-    int M, N, num_m_tiles, num_n_tiles, nkb, chunks0, chunks1, mode, W, P, kw, pad;
+    int M, N, num_m_tiles, num_n_tiles, num_tiles, nkb, chunks0, chunks1, mode, W, P, kh, kw, pad, stages;
+    int Wl_box, rows_box;          // CONV_UPSAMPLE store box: low-res pixels per row / rows per 32-pixel warp block
+    uint32_t slab_bytes;           // bytes of one slab TMA box
+    uint32_t slab_dy_bytes;        // W * 128: A-descriptor advance per dy tap
+    uint32_t res_b_bytes;          // resident weight bytes (K_SLAB_RES)
     ConvEpilogue epi;
-    bf16* out;
-    int ldo;
 };
 
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
-template <int BN>
+struct TileCoord { int mt, nt, phase; };
+
+__device__ __forceinline__ TileCoord decode_tile(const KArgs& a, int tile) {
+    TileCoord t;
+    if (a.mode == CONV_UPSAMPLE) {
+        const int units = a.num_n_tiles * 4;
+        t.mt = tile / units;
+        const int rem = tile - t.mt * units;
+        t.phase = rem / a.num_n_tiles;
+        t.nt = rem - t.phase * a.num_n_tiles;
+    } else {
+        t.mt = tile / a.num_n_tiles;
+        t.nt = tile - t.mt * a.num_n_tiles;
+        t.phase = 0;
+    }
+    return t;
+}
+
+// Warp-wide sums of 16 per-lane values with 16 shuffles: afterwards lane L holds the total of value (L >> 1).
+__device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
+    constexpr unsigned FULL = 0xffffffffu;
+    {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float keep = up ? v[i + 8] : v[i];
+            const float send = up ? v[i] : v[i + 8];
+            v[i] = keep + __shfl_xor_sync(FULL, send, 16);
+        }
+    }
+    {
+        const bool up = (lane & 8) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float keep = up ? v[i + 4] : v[i];
+            const float send = up ? v[i] : v[i + 4];
+            v[i] = keep + __shfl_xor_sync(FULL, send, 8);
+        }
+    }
+    {
+        const bool up = (lane & 4) != 0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float keep = up ? v[i + 2] : v[i];
+            const float send = up ? v[i] : v[i + 2];
+            v[i] = keep + __shfl_xor_sync(FULL, send, 4);
+        }
+    }
+    {
+        const bool up = (lane & 2) != 0;
+        const float keep = up ? v[1] : v[0];
+        const float send = up ? v[0] : v[1];
+        v[0] = keep + __shfl_xor_sync(FULL, send, 2);
+    }
+    v[0] += __shfl_xor_sync(FULL, v[0], 1);
+    return v[0];
+}
+
+template <int BN, int KIND>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD, const KArgs a) {
-    using Cfg = TileCfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
+    using C = Cfg<BN, KIND>;
+    constexpr uint32_t B_BLOCK = C::B_BLOCK_BYTES;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stages = a.stages;
     uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-    uint8_t* sEpi = sB + STAGES * Cfg::B_STAGE_BYTES;      // 1024-aligned: all stage sizes are multiples of 1 KiB
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpi + EPI_STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint8_t* sB = smem + stages * C::A_STAGE_BYTES;                       // per-stage weights, or the resident matrix
+    uint8_t* sEpi = sB + (KIND == K_SLAB_RES ? a.res_b_bytes : stages * C::B_STAGE_BYTES);   // all sizes are KiB multiples
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpi + C::EPI_BYTES);
+    uint64_t* empty_bar = full_bar + MAX_STAGES;
+    uint64_t* tfull_bar = empty_bar + MAX_STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* res_bar = tempty_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -84,10 +169,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             ptx::prefetch_tmap(&tmD);
         }
         __syncwarp();
-        ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
         ptx::tmem_relinquish();
     } else if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) {
+        for (int i = 0; i < MAX_STAGES; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
             ptx::mbar_init(&empty_bar[i], 1);
         }
@@ -95,6 +180,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             ptx::mbar_init(&tfull_bar[i], 1);
             ptx::mbar_init(&tempty_bar[i], 128);
         }
+        ptx::mbar_init(res_bar, 1);
         ptx::fence_mbar_init();
     }
     ptx::tc_fence_before();
@@ -102,70 +188,138 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_tiles = a.num_m_tiles * a.num_n_tiles;
     const int chunks = a.chunks0 + a.chunks1;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int mt = tile / a.num_n_tiles;
-                const int nt = tile - mt * a.num_n_tiles;
-                const int m0 = mt * BLOCK_M;
-                const int n0 = nt * BN;
-                const int b0 = m0 / a.P;
-                const int h0 = (m0 - b0 * a.P) / a.W;
-                const int row0 = m0 / a.W;  // merged (b, h) row for the unshuffle view
-                int tap = 0, chunk = 0;
-                for (int kb = 0; kb < a.nkb; ++kb) {
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        // ------------------------------------------------------------------ TMA producer (warp-uniform, one lane issues)
+        if constexpr (KIND == K_SLAB_RES) {
+            if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(res_bar, a.res_b_bytes);
+                for (int kb = 0; kb < a.nkb; ++kb)
+                    ptx::tma_load_2d(sB + kb * B_BLOCK, &tmB, res_bar, kb * BLOCK_K, 0);
+            }
+            __syncwarp();
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+            const TileCoord tc = decode_tile(a, tile);
+            const int m0 = tc.mt * BLOCK_M;
+            const int b0 = m0 / a.P;
+            const int h0 = (m0 - b0 * a.P) / a.W;
+            const int nrow = tc.nt * BN + tc.phase * a.N;          // weight row of this tile (per-phase matrices stacked)
+            if constexpr (KIND == K_GENERAL) {
+                const int row0 = m0 / a.W;                          // merged (b, h) row for the unshuffle view
+                const int dy0 = a.mode == CONV_UPSAMPLE ? (tc.phase >> 1) - 1 : -a.pad;
+                const int dx0 = a.mode == CONV_UPSAMPLE ? (tc.phase & 1) - 1 : -a.pad;
+                int kcol = 0;
+                for (int ky = 0; ky < a.kh; ++ky) {
+                    for (int kx = 0; kx < a.kw; ++kx) {
+                        for (int chunk = 0; chunk < chunks; ++chunk) {
+                            ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                            if (ptx::elect_one()) {
+                                ptx::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+                                const bool second = chunk >= a.chunks0;
+                                const CUtensorMap* tm = second ? &tmA1 : &tmA0;
+                                const int c0 = (second ? chunk - a.chunks0 : chunk) * BLOCK_K;
+                                uint8_t* dstA = sA + stage * C::A_STAGE_BYTES;
+                                if (a.mode == CONV_UNSHUFFLE)
+                                    ptx::tma_load_5d(dstA, tm, &full_bar[stage], c0, kx, 0, ky, row0);
+                                else
+                                    ptx::tma_load_4d(dstA, tm, &full_bar[stage], c0, dx0 + kx, h0 + dy0 + ky, b0);
+                                ptx::tma_load_2d(sB + stage * C::B_STAGE_BYTES, &tmB, &full_bar[stage], kcol, nrow);
+                            }
+                            __syncwarp();
+                            kcol += BLOCK_K;
+                            if (++stage == stages) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                }
+            } else {
+                for (int chunk = 0; chunk < chunks; ++chunk) {
                     const bool second = chunk >= a.chunks0;
                     const CUtensorMap* tm = second ? &tmA1 : &tmA0;
                     const int c0 = (second ? chunk - a.chunks0 : chunk) * BLOCK_K;
-                    uint8_t* dstA = sA + stage * A_STAGE_BYTES;
-                    if (a.mode == CONV_TAPS) {
-                        const int dy = tap / a.kw - a.pad;
-                        const int dx = tap - (tap / a.kw) * a.kw - a.pad;
-                        ptx::tma_load_4d(dstA, tm, &full_bar[stage], c0, dx, h0 + dy, b0);
-                    } else {
-                        // tap = p1 * 2 + p2
-                        ptx::tma_load_5d(dstA, tm, &full_bar[stage], c0, tap & 1, 0, tap >> 1, row0);
+                    for (int dxi = 0; dxi < 3; ++dxi) {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        if (ptx::elect_one()) {
+                            constexpr uint32_t wbytes = KIND == K_SLAB ? 3 * B_BLOCK : 0;
+                            ptx::mbar_arrive_expect_tx(&full_bar[stage], a.slab_bytes + wbytes);
+                            ptx::tma_load_4d(sA + stage * C::A_STAGE_BYTES, tm, &full_bar[stage], c0, dxi - 1, h0 - 1, b0);
+                            if constexpr (KIND == K_SLAB) {
+#pragma unroll
+                                for (int dyi = 0; dyi < 3; ++dyi)
+                                    ptx::tma_load_2d(sB + stage * C::B_STAGE_BYTES + dyi * B_BLOCK, &tmB, &full_bar[stage],
+                                                     ((dyi * 3 + dxi) * chunks + chunk) * BLOCK_K, nrow);
+                            }
+                        }
+                        __syncwarp();
+                        if (++stage == stages) { stage = 0; phase ^= 1u; }
                     }
-                    ptx::tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, n0);
-                    if (++chunk == chunks) { chunk = 0; ++tap; }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int iter = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
-                const int as = iter & 1;
-                const uint32_t aphase = (iter >> 1) & 1u;
-                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1u);
-                ptx::tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * BN;
+        // ------------------------------------------------------------------ MMA issuer (warp-uniform, one lane issues)
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BN);
+        const uint64_t descA0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sA));
+        const uint64_t descB0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sB));
+        if constexpr (KIND == K_SLAB_RES) {
+            ptx::mbar_wait(res_bar, 0);
+            ptx::tc_fence_after();
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++iter) {
+            const int as = iter & 1;
+            const uint32_t aphase = (iter >> 1) & 1u;
+            ptx::mbar_wait(&tempty_bar[as], aphase ^ 1u);
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * BN;
+            if constexpr (KIND == K_GENERAL) {
                 for (int kb = 0; kb < a.nkb; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
-                    const uint64_t da = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sA + stage * A_STAGE_BYTES));
-                    const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sB + stage * Cfg::B_STAGE_BYTES));
+                    if (ptx::elect_one()) {
+                        const uint64_t da = descA0 + static_cast<uint64_t>((stage * C::A_STAGE_BYTES) >> 4);
+                        const uint64_t db = descB0 + static_cast<uint64_t>((stage * C::B_STAGE_BYTES) >> 4);
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 16; ++k) {
-                        // advance 16 bf16 = 32 bytes along K inside the swizzle span: +2 in the >>4 address field
-                        ptx::umma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BLOCK_K / 16; ++k)   // +32 bytes along K inside the swizzle span: +2 in the >>4 field
+                            ptx::umma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        ptx::umma_commit(&empty_bar[stage]);
+                        if (kb == a.nkb - 1) ptx::umma_commit(&tfull_bar[as]);
                     }
-                    ptx::umma_commit(&empty_bar[stage]);
-                    if (kb == a.nkb - 1) ptx::umma_commit(&tfull_bar[as]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    __syncwarp();
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                }
+            } else {
+                const int nst = chunks * 3;
+                const uint32_t dy_step = a.slab_dy_bytes >> 4;
+                int chunk = 0, dxi = 0;
+                for (int st = 0; st < nst; ++st) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    if (ptx::elect_one()) {
+                        const uint64_t da = descA0 + static_cast<uint64_t>((stage * C::A_STAGE_BYTES) >> 4);
+#pragma unroll
+                        for (int dyi = 0; dyi < 3; ++dyi) {
+                            uint64_t db;
+                            if constexpr (KIND == K_SLAB)
+                                db = descB0 + static_cast<uint64_t>((stage * C::B_STAGE_BYTES + dyi * B_BLOCK) >> 4);
+                            else
+                                db = descB0 + static_cast<uint64_t>((((dyi * 3 + dxi) * chunks + chunk) * B_BLOCK) >> 4);
+                            const uint64_t dad = da + static_cast<uint64_t>(dyi * dy_step);
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k)
+                                ptx::umma_bf16(tmem_d, dad + 2u * k, db + 2u * k, idesc, (st | dyi | k) != 0 ? 1u : 0u);
+                        }
+                        ptx::umma_commit(&empty_bar[stage]);
+                        if (st == nst - 1) ptx::umma_commit(&tfull_bar[as]);
+                    }
+                    __syncwarp();
+                    if (++dxi == 3) { dxi = 0; ++chunk; }
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -177,14 +331,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;            // accumulator row == pixel within the tile
         const ConvEpilogue& e = a.epi;
-        uint8_t* my_stage = sEpi + q * (2 * EPI_BUF_BYTES);
+        uint8_t* my_stage = sEpi + q * (C::EPI_BUFS * EPI_BUF_BYTES);
         int buf = 0;
         int iter = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
-            const int mt = tile / a.num_n_tiles;
-            const int nt = tile - mt * a.num_n_tiles;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++iter) {
+            const TileCoord tc = decode_tile(a, tile);
+            const int mt = tc.mt;
             const int m = mt * BLOCK_M + r;
-            const int n0 = nt * BN;
+            const int n0 = tc.nt * BN;
             const bool valid = m < a.M;
             const int as = iter & 1;
             const uint32_t aphase = (iter >> 1) & 1u;
@@ -278,61 +432,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     finish(f0, n0 + c);
                     finish(f1, n0 + c + 32);
                     if (e.gn_part != nullptr) {
-                        // GroupNorm partials of this warp's 32 rows x 64 columns (rows are all valid: M % 32 == 0).
-                        const int lg = 31 - __clz(a.N >> 6);            // log2(pieces of 8 columns per group)
-                        float ps[8];
+                        // GroupNorm partials of this warp's 32 rows: (sum, M2) of every 8-channel piece of the 64 columns
+                        // (rows are all valid: M % 32 == 0).  Per-row sums / sums of squares, one 16-value transpose-reduce.
+                        float sq[16];
 #pragma unroll
                         for (int p8 = 0; p8 < 8; ++p8) {
-                            float t = 0.f;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) t += (p8 < 4) ? f0[8 * p8 + j] : f1[8 * (p8 - 4) + j];
-#pragma unroll
-                            for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-                            ps[p8] = t;
-                        }
-                        const float inv_cnt = 1.0f / (32.0f * static_cast<float>(a.N >> 3));
-                        float gsum[8], pmean[8];
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            float t = 0.f;
-#pragma unroll
-                            for (int p8 = 0; p8 < 8; ++p8) t += ((p8 >> lg) == k) ? ps[p8] : 0.f;
-                            gsum[k] = t;
-                        }
-#pragma unroll
-                        for (int p8 = 0; p8 < 8; ++p8) {
-                            float t = 0.f;
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) t = ((p8 >> lg) == k) ? gsum[k] * inv_cnt : t;
-                            pmean[p8] = t;
-                        }
-#pragma unroll
-                        for (int p8 = 0; p8 < 8; ++p8) {
-                            float t = 0.f;
+                            float s = 0.f, ss = 0.f;
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                const float dlt = ((p8 < 4) ? f0[8 * p8 + j] : f1[8 * (p8 - 4) + j]) - pmean[p8];
-                                t = fmaf(dlt, dlt, t);
+                                const float x = (p8 < 4) ? f0[8 * p8 + j] : f1[8 * (p8 - 4) + j];
+                                s += x;
+                                ss = fmaf(x, x, ss);
                             }
-#pragma unroll
-                            for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-                            ps[p8] = t;
+                            sq[2 * p8] = s;
+                            sq[2 * p8 + 1] = ss;
                         }
-                        if (lane == 0 && valid) {
-                            const int ngroups = 8 >> lg;                         // groups inside this 64-column chunk
-                            const int g0 = (n0 + c) / (a.N >> 3);                // first global group of the chunk
-                            float2* dst = e.gn_part + (static_cast<size_t>(mt) * 4 + q) * 8 + g0;
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                float m2 = 0.f;
-#pragma unroll
-                                for (int p8 = 0; p8 < 8; ++p8) m2 += ((p8 >> lg) == k) ? ps[p8] : 0.f;
-                                if (k < ngroups) dst[k] = make_float2(gsum[k], m2);
-                            }
+                        const float mine = transpose_reduce16(sq, lane);           // lane L: value (L >> 1)
+                        const float other = __shfl_down_sync(0xffffffffu, mine, 2);
+                        if ((lane & 3) == 0) {                                      // lane 4p: sum and sum of squares of piece p
+                            const float m2 = fmaxf(other - mine * mine * (1.0f / 256.0f), 0.f);
+                            e.gn_part[(static_cast<size_t>(mt) * 4 + q) * (a.N >> 3) + ((n0 + c) >> 3) + (lane >> 2)] =
+                                make_float2(mine, m2);
                         }
                     }
-                    // staging buffer free?  (at most one older store of this warp may still be reading the OTHER buffer)
-                    if (lane == 0) ptx::bulk_wait_read<1>();
+                    // staging buffer free?  (with two buffers one older store of this warp may still be reading the OTHER one)
+                    if (lane == 0) {
+                        if constexpr (C::EPI_BUFS == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
+                    }
                     __syncwarp();
                     uint8_t* stage_row = my_stage + buf * EPI_BUF_BYTES + lane * 128;
                     const int sw = lane & 7;
@@ -354,10 +480,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     ptx::fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        ptx::tma_store_2d(&tmD, my_stage + buf * EPI_BUF_BYTES, n0 + c, mt * BLOCK_M + q * 32);
+                        const int mrow = mt * BLOCK_M + q * 32;
+                        if (a.mode == CONV_UPSAMPLE) {
+                            // low-res pixel block -> output phase (pa, pb) through the [N, 2, W/2, 2, B*H/2] view
+                            const int rowl = mrow / a.Wl_box;              // merged (b, low-res row)
+                            const int wl = a.rows_box > 1 ? 0 : mrow - rowl * a.Wl_box;
+                            ptx::tma_store_5d(&tmD, my_stage + buf * EPI_BUF_BYTES, n0 + c, tc.phase & 1, wl, tc.phase >> 1, rowl);
+                        } else {
+                            ptx::tma_store_2d(&tmD, my_stage + buf * EPI_BUF_BYTES, n0 + c, mrow);
+                        }
                         ptx::bulk_commit();
                     }
-                    buf ^= 1;
+                    if constexpr (C::EPI_BUFS == 2) buf ^= 1;
                 }
             }
         }
@@ -367,7 +501,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 0) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (warp == 0) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -406,15 +540,18 @@ int encode_map(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dim
     return 0;
 }
 
-int encode_activation_map(CUtensorMap* tm, const ConvSrc& s, const ConvGemmDesc& d, char* err, int errlen) {
+// Hs x Ws: spatial size of the SOURCE tensor the taps walk over (== output size except for CONV_UPSAMPLE: low-res).
+int encode_activation_map(CUtensorMap* tm, const ConvSrc& s, const ConvGemmDesc& d, int Hs, int Ws, int slab_rows,
+                          char* err, int errlen) {
     const cuuint64_t C = s.C;
-    if (d.mode == CONV_TAPS) {
-        const int P = d.H * d.W;
-        const int rows = P >= BLOCK_M ? BLOCK_M / d.W : d.H;
+    if (d.mode != CONV_UNSHUFFLE) {
+        const int P = Hs * Ws;
+        int rows = P >= BLOCK_M ? BLOCK_M / Ws : Hs;
         const int imgs = P >= BLOCK_M ? 1 : BLOCK_M / P;
-        cuuint64_t dims[4] = {C, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
-        cuuint64_t str[3] = {C * 2, C * 2 * d.W, C * 2 * d.W * d.H};
-        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)d.W, (cuuint32_t)rows, (cuuint32_t)imgs};
+        if (slab_rows > 0) rows = slab_rows;
+        cuuint64_t dims[4] = {C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)d.B};
+        cuuint64_t str[3] = {C * 2, C * 2 * Ws, C * 2 * Ws * Hs};
+        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)Ws, (cuuint32_t)rows, (cuuint32_t)imgs};
         return encode_map(tm, s.ptr, 4, dims, str, box, err, errlen);
     }
     // input is [B, 2H, 2W, C]; view as [C, p2, W, p1, B*H]
@@ -424,35 +561,56 @@ int encode_activation_map(CUtensorMap* tm, const ConvSrc& s, const ConvGemmDesc&
     return encode_map(tm, s.ptr, 5, dims, str, box, err, errlen);
 }
 
-template <int BN>
-cudaError_t launch_bn(const ConvGemmLaunch& l, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             TileCfg<BN>::SMEM_BYTES);
+template <int BN, int KIND>
+cudaError_t launch_cfg(const ConvGemmLaunch& l, cudaStream_t s) {
+    static int attr_bytes = 0;
+    if (l.smem_bytes > attr_bytes) {
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             l.smem_bytes);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_bytes = l.smem_bytes;
     }
     KArgs k;
-    k.M = l.M; k.N = l.N; k.num_m_tiles = l.num_m_tiles; k.num_n_tiles = l.num_n_tiles; k.nkb = l.nkb;
-    k.chunks0 = l.chunks0; k.chunks1 = l.chunks1; k.mode = l.mode; k.W = l.W; k.P = l.P; k.kw = l.kw; k.pad = l.pad;
-    k.epi = l.epi; k.out = l.out; k.ldo = l.ldo;
-    conv_gemm_kernel<BN><<<l.grid, NUM_THREADS, TileCfg<BN>::SMEM_BYTES, s>>>(l.tmA0, l.tmA1, l.tmB, l.tmD, k);
+    k.M = l.M; k.N = l.N; k.num_m_tiles = l.num_m_tiles; k.num_n_tiles = l.num_n_tiles; k.num_tiles = l.num_tiles;
+    k.nkb = l.nkb; k.chunks0 = l.chunks0; k.chunks1 = l.chunks1; k.mode = l.mode; k.W = l.W; k.P = l.P;
+    k.kh = l.kh; k.kw = l.kw; k.pad = l.pad; k.stages = l.stages; k.Wl_box = l.Wl_box; k.rows_box = l.rows_box;
+    k.slab_bytes = l.slab_bytes; k.slab_dy_bytes = l.slab_dy_bytes; k.res_b_bytes = l.res_b_bytes;
+    k.epi = l.epi;
+    conv_gemm_kernel<BN, KIND><<<l.grid, NUM_THREADS, l.smem_bytes, s>>>(l.tmA0, l.tmA1, l.tmB, l.tmD, k);
     return cudaGetLastError();
+}
+
+template <int BN>
+void size_cfg(ConvGemmLaunch* l) {
+    switch (l->kind) {
+        case K_SLAB: l->stages = Cfg<BN, K_SLAB>::stages(0); l->smem_bytes = Cfg<BN, K_SLAB>::smem_bytes(l->stages, 0); break;
+        case K_SLAB_RES:
+            l->stages = Cfg<BN, K_SLAB_RES>::stages(l->res_b_bytes);
+            l->smem_bytes = Cfg<BN, K_SLAB_RES>::smem_bytes(l->stages, l->res_b_bytes);
+            break;
+        default: l->stages = Cfg<BN, K_GENERAL>::stages(0); l->smem_bytes = Cfg<BN, K_GENERAL>::smem_bytes(l->stages, 0); break;
+    }
 }
 
 }  // namespace
 
 int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, char* err, int errlen) {
     memset(out, 0, sizeof(*out));
-    const int P = d.H * d.W;
+    const bool up = d.mode == CONV_UPSAMPLE;
+    // the spatial grid the GEMM rows enumerate: output pixels, or (CONV_UPSAMPLE) low-resolution input pixels per phase
+    const int Hs = up ? d.H / 2 : d.H, Ws = up ? d.W / 2 : d.W;
+    const int P = Hs * Ws;
     if (d.src0.ptr == nullptr || d.src0.C % BLOCK_K != 0 || (d.src1.ptr != nullptr && d.src1.C % BLOCK_K != 0)) {
         snprintf(err, errlen, "conv_gemm: input channels must be multiples of %d (got %d/%d)", BLOCK_K, d.src0.C,
                  d.src1.ptr ? d.src1.C : 0);
         return 1;
     }
-    if (d.W > BLOCK_M || BLOCK_M % d.W != 0 || (P < BLOCK_M && BLOCK_M % P != 0) || (P >= BLOCK_M && P % BLOCK_M != 0)) {
-        snprintf(err, errlen, "conv_gemm: unsupported spatial size %dx%d for a %d-pixel tile", d.H, d.W, BLOCK_M);
+    if (up && ((d.H | d.W) & 1)) {
+        snprintf(err, errlen, "conv_gemm: upsample output size %dx%d must be even", d.H, d.W);
+        return 1;
+    }
+    if (Ws > BLOCK_M || BLOCK_M % Ws != 0 || (P < BLOCK_M && BLOCK_M % P != 0) || (P >= BLOCK_M && P % BLOCK_M != 0)) {
+        snprintf(err, errlen, "conv_gemm: unsupported spatial size %dx%d for a %d-pixel tile", Hs, Ws, BLOCK_M);
         return 1;
     }
     if (d.mode == CONV_TAPS && d.ksize != 1 && d.ksize != 3) {
@@ -469,40 +627,67 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
         return 1;
     }
     const int M = d.B * P;
-    out->bn = bn;
     out->M = M;
     out->N = d.N;
     out->num_m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
-    out->num_n_tiles = d.N / bn;
+    const int phases = up ? 4 : 1;
     // Few tiles relative to the machine: prefer a narrower N tile so more SMs get work.
-    while (bn > 64 && out->num_m_tiles * out->num_n_tiles < num_sms && d.N % (bn / 2) == 0) {
-        bn /= 2;
-        out->bn = bn;
-        out->num_n_tiles = d.N / bn;
-    }
+    while (bn > 64 && out->num_m_tiles * (d.N / bn) * phases < num_sms && d.N % (bn / 2) == 0) bn /= 2;
     out->chunks0 = d.src0.C / BLOCK_K;
     out->chunks1 = d.src1.ptr ? d.src1.C / BLOCK_K : 0;
+    const int chunks = out->chunks0 + out->chunks1;
     const int taps = d.mode == CONV_TAPS ? d.ksize * d.ksize : 4;
-    out->nkb = taps * (out->chunks0 + out->chunks1);
+    out->nkb = taps * chunks;
+    // slab path: 3x3 taps over whole image rows, N <= 128 (a 256-wide weight stage would leave one pipeline stage)
+    out->kind = K_GENERAL;
+    if (d.mode == CONV_TAPS && d.ksize == 3 && P >= BLOCK_M && Ws >= 16 && d.N <= 128) {
+        if (bn > 128) bn = 128;
+        out->kind = K_SLAB;
+        if (bn == 64 && d.N == 64 && out->nkb * 64 * BLOCK_K * 2 <= 144 * 1024) {
+            out->kind = K_SLAB_RES;
+            out->res_b_bytes = static_cast<uint32_t>(out->nkb) * 64 * BLOCK_K * 2;
+        }
+    }
+    out->bn = bn;
+    out->num_n_tiles = d.N / bn;
+    out->num_tiles = out->num_m_tiles * out->num_n_tiles * phases;
     out->mode = d.mode;
-    out->W = d.W;
+    out->W = Ws;
     out->P = P;
-    out->kw = d.mode == CONV_TAPS ? d.ksize : 2;
+    out->kh = d.mode == CONV_TAPS ? d.ksize : 2;
+    out->kw = out->kh;
     out->pad = d.mode == CONV_TAPS ? d.ksize / 2 : 0;
     out->epi = d.epi;
     out->out = d.out;
     out->ldo = d.N;
-    const int tiles = out->num_m_tiles * out->num_n_tiles;
-    out->grid = tiles < num_sms ? tiles : num_sms;
+    out->grid = out->num_tiles < num_sms ? out->num_tiles : num_sms;
+    int slab_rows = 0;
+    if (out->kind != K_GENERAL) {
+        slab_rows = BLOCK_M / Ws + 2;
+        out->slab_bytes = static_cast<uint32_t>(slab_rows) * Ws * BLOCK_K * 2;
+        out->slab_dy_bytes = static_cast<uint32_t>(Ws) * BLOCK_K * 2;
+        if (out->slab_bytes > SLAB_CAP_BYTES) {
+            snprintf(err, errlen, "conv_gemm: slab of %u bytes exceeds the stage capacity", out->slab_bytes);
+            return 1;
+        }
+    }
+    if (up && (d.epi.res != nullptr || d.epi.film != nullptr || d.epi.gn_part != nullptr || d.epi.out_f32 != nullptr)) {
+        snprintf(err, errlen, "conv_gemm: the upsample conv supports the bias epilogue only");
+        return 1;
+    }
+    if (d.epi.gn_part != nullptr && (M % 32 != 0 || bn < 64)) {
+        snprintf(err, errlen, "conv_gemm: GroupNorm partials need M %% 32 == 0 and a bf16 output tile");
+        return 1;
+    }
 
-    if (encode_activation_map(&out->tmA0, d.src0, d, err, errlen)) return 1;
+    if (encode_activation_map(&out->tmA0, d.src0, d, Hs, Ws, slab_rows, err, errlen)) return 1;
     if (d.src1.ptr) {
-        if (encode_activation_map(&out->tmA1, d.src1, d, err, errlen)) return 1;
+        if (encode_activation_map(&out->tmA1, d.src1, d, Hs, Ws, slab_rows, err, errlen)) return 1;
     } else {
         out->tmA1 = out->tmA0;
     }
     const cuuint64_t Ktot = (cuuint64_t)out->nkb * BLOCK_K;
-    cuuint64_t wd[2] = {Ktot, (cuuint64_t)d.N};
+    cuuint64_t wd[2] = {Ktot, (cuuint64_t)d.N * phases};
     cuuint64_t ws[1] = {Ktot * 2};
     cuuint32_t wb[2] = {BLOCK_K, (cuuint32_t)bn};
     if (encode_map(&out->tmB, d.weight, 2, wd, ws, wb, err, errlen)) return 1;
@@ -511,32 +696,60 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
             snprintf(err, errlen, "conv_gemm: bf16 output needs an N tile >= 64 and an output buffer");
             return 1;
         }
-        cuuint64_t od[2] = {(cuuint64_t)d.N, (cuuint64_t)M};
-        cuuint64_t os[1] = {(cuuint64_t)d.N * 2};
-        cuuint32_t ob[2] = {64, 32};
-        if (encode_map(&out->tmD, d.out, 2, od, os, ob, err, errlen)) return 1;
+        if (up) {
+            // output [B, H, W, N] viewed as [N, pb, W/2, pa, B*H/2]; a warp stores 32 consecutive low-res pixels of one phase
+            const cuuint64_t N2 = (cuuint64_t)d.N * 2;
+            out->Wl_box = Ws;
+            out->rows_box = Ws >= 32 ? 1 : 32 / Ws;
+            cuuint64_t od[5] = {(cuuint64_t)d.N, 2, (cuuint64_t)Ws, 2, (cuuint64_t)d.B * Hs};
+            cuuint64_t os[4] = {N2, 2 * N2, (cuuint64_t)d.W * N2, 2 * (cuuint64_t)d.W * N2};
+            cuuint32_t ob[5] = {64, 1, (cuuint32_t)(Ws >= 32 ? 32 : Ws), 1, (cuuint32_t)out->rows_box};
+            if (encode_map(&out->tmD, d.out, 5, od, os, ob, err, errlen)) return 1;
+        } else {
+            cuuint64_t od[2] = {(cuuint64_t)d.N, (cuuint64_t)M};
+            cuuint64_t os[1] = {(cuuint64_t)d.N * 2};
+            cuuint32_t ob[2] = {64, 32};
+            if (encode_map(&out->tmD, d.out, 2, od, os, ob, err, errlen)) return 1;
+        }
     } else {
-        if (bn >= 64) {
-            snprintf(err, errlen, "conv_gemm: the fp32 head path is built for N <= 48 (padded to 16-column tiles)");
+        if (bn >= 64 || up) {
+            snprintf(err, errlen, "conv_gemm: the fp32 head path is built for N <= 48 (padded to 16-column tiles), no upsample");
             return 1;
         }
         out->tmD = out->tmB;   // unused by the fp32 head path
     }
     switch (bn) {
-        case 256: out->smem_bytes = TileCfg<256>::SMEM_BYTES; break;
-        case 128: out->smem_bytes = TileCfg<128>::SMEM_BYTES; break;
-        case 64: out->smem_bytes = TileCfg<64>::SMEM_BYTES; break;
-        default: out->smem_bytes = TileCfg<16>::SMEM_BYTES; break;
+        case 256: size_cfg<256>(out); break;
+        case 128: size_cfg<128>(out); break;
+        case 64: size_cfg<64>(out); break;
+        default: size_cfg<16>(out); break;
+    }
+    if (out->stages < 2) {
+        snprintf(err, errlen, "conv_gemm: only %d pipeline stage(s) fit in shared memory", out->stages);
+        return 1;
     }
     return 0;
 }
 
 cudaError_t conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t s) {
-    switch (l.bn) {
-        case 256: return launch_bn<256>(l, s);
-        case 128: return launch_bn<128>(l, s);
-        case 64: return launch_bn<64>(l, s);
-        case 16: return launch_bn<16>(l, s);
+    switch (l.kind) {
+        case K_GENERAL:
+            switch (l.bn) {
+                case 256: return launch_cfg<256, K_GENERAL>(l, s);
+                case 128: return launch_cfg<128, K_GENERAL>(l, s);
+                case 64: return launch_cfg<64, K_GENERAL>(l, s);
+                case 16: return launch_cfg<16, K_GENERAL>(l, s);
+                default: return cudaErrorInvalidValue;
+            }
+        case K_SLAB:
+            switch (l.bn) {
+                case 128: return launch_cfg<128, K_SLAB>(l, s);
+                case 64: return launch_cfg<64, K_SLAB>(l, s);
+                case 16: return launch_cfg<16, K_SLAB>(l, s);
+                default: return cudaErrorInvalidValue;
+            }
+        case K_SLAB_RES:
+            return l.bn == 64 ? launch_cfg<64, K_SLAB_RES>(l, s) : cudaErrorInvalidValue;
         default: return cudaErrorInvalidValue;
     }
 }

@@ -25,6 +25,7 @@ struct ConvSrc {
 enum ConvMode : int {
     CONV_TAPS = 0,       // kh x kw taps, stride 1, "same" zero padding (kh==kw in {1,3})
     CONV_UNSHUFFLE = 1,  // 'b c (h p1) (w p2) -> b (c p1 p2) h w' followed by a 1x1 conv
+    CONV_UPSAMPLE = 2,   // nearest x2 upsample followed by a 3x3 "same" conv, as four 2x2 phase convs over the low-res input
 };
 
 struct ConvEpilogue {
@@ -42,17 +43,19 @@ struct ConvEpilogue {
     int ldr = 0;
     float* out_f32 = nullptr;         // if set: write fp32 [M, n_valid] instead of bf16
     int n_valid = 0;
-    // GroupNorm(8) statistics of THIS conv's output, from the fp32 accumulators (+bias): one (sum, M2) pair per
-    // (32-row warp block, group), M2 = sum of squared deviations from the block's own mean (merged stably later).
-    float2* gn_part = nullptr;        // [M / 32][8]
+    // GroupNorm statistics of THIS conv's output, from the fp32 accumulators (+bias): one (sum, M2) pair per
+    // (32-row warp block, 8-channel piece), M2 = sum of squared deviations from the piece-block's own mean (merged
+    // stably, in a fixed order, by groupnorm_apply_kernel).
+    float2* gn_part = nullptr;        // [M / 32][N / 8]
 };
 
 struct ConvGemmDesc {
     ConvSrc src0, src1;       // src1.ptr == nullptr when there is no channel concat
-    int B, H, W;              // OUTPUT spatial size (== input size for CONV_TAPS; input is 2H x 2W for UNSHUFFLE)
+    int B, H, W;              // OUTPUT spatial size (== input size for CONV_TAPS; input is 2H x 2W for UNSHUFFLE,
+                              // H/2 x W/2 for UPSAMPLE)
     int ksize;                // 1 or 3 (CONV_TAPS); ignored for UNSHUFFLE
     ConvMode mode;
-    const bf16* weight;       // [Npad, Ktot] K-major; K order = (tap, concat channel)
+    const bf16* weight;       // [Npad, Ktot] K-major; K order = (tap, concat channel); UPSAMPLE: 4 stacked phase matrices
     int N;                    // rows of `weight` (multiple of the chosen N tile)
     bf16* out;                // [B*H*W, N]
     ConvEpilogue epi;
@@ -62,10 +65,13 @@ struct ConvGemmDesc {
 struct ConvGemmLaunch {
     CUtensorMap tmA0, tmA1, tmB, tmD;
     int bn;             // N tile (16, 64, 128 or 256)
+    int kind;           // 0 general, 1 slab (3x3, one A box per (chunk, dx)), 2 slab + shared-memory resident weights
     int grid;
     int smem_bytes;
     // kernel scalar arguments
-    int M, N, num_m_tiles, num_n_tiles, nkb, chunks0, chunks1, mode, W, P, kw, pad;
+    int M, N, num_m_tiles, num_n_tiles, num_tiles, nkb, chunks0, chunks1, mode, W, P, kh, kw, pad, stages;
+    int Wl_box, rows_box;
+    uint32_t slab_bytes, slab_dy_bytes, res_b_bytes;
     ConvEpilogue epi;
     bf16* out;
     int ldo;
@@ -82,7 +88,7 @@ struct GroupNormArgs {
     const bf16* x;        // [B, P, C]
     bf16* y;              // [B, P, C]
     int B, P, C;          // P = H*W pixels
-    const float2* part;   // [B * P / 32][8] (sum, M2) partials written by the producing conv (or groupnorm_stats_run)
+    const float2* part;   // [B * P / 32][C / 8] (sum, M2) partials written by the producing conv (or groupnorm_stats_run)
     const float* gamma;   // [C]
     const float* beta;    // [C]
     float eps;
@@ -189,6 +195,9 @@ cudaError_t prep_conv_weight_run(const float* w, bf16* out, int Cout, int Cin, i
                                  int Npad, cudaStream_t s);
 // Downsample 1x1 weight [Cout, 4*C] with K order (c, p1, p2) -> (p1, p2, c)
 cudaError_t prep_unshuffle_weight_run(const float* w, bf16* out, int Cout, int C, cudaStream_t s);
+// Upsample's 3x3 weight [Cout, Cin, 3, 3] -> four phase matrices [4][Cout][(u, v, cin)] of the equivalent 2x2 convs
+// over the low-resolution input (taps that land on the same low-res pixel are summed in fp32)
+cudaError_t prep_upsample_weight_run(const float* w, bf16* out, int Cout, int Cin, cudaStream_t s);
 
 // y[r, ldy*r + off + j] = bias[j] + sum_k act(x[r, k]) * W[j, k];  act: 0 none, 1 SiLU (on input), out_act: 0 none, 1 GELU(erf)
 cudaError_t linear_rows_run(const float* x, int ldx, const float* W, const float* bias, float* y, int ldy, int off,

@@ -5,8 +5,8 @@
 //              ResnetBlock     :185-197 (the "+ res_conv(x)" is the optional residual operand here)
 //              SR3 ResnetBlock /root/reference/src/hicdiff_sr3.py:246-251 (additive noise embedding = postadd)
 //   The statistics come for free from the producing conv: its epilogue (conv_gemm.cu) reduces the fp32 accumulators of
-//   every 32-row warp block to a (sum, M2-about-the-block-mean) pair per group with warp shuffles and writes them to a
-//   small [M/32][8] buffer (no atomics).  This kernel merges an image's partials with Chan's formula (stable, fixed
+//   every 32-row warp block to a (sum, M2-about-the-block-mean) pair per 8-channel piece with warp shuffles and writes
+//   them to a small [M/32][C/8] buffer (no atomics).  This kernel merges an image's partials with Chan's formula (stable, fixed
 //   order, so deterministic) and then streams the activation once: read, normalise, modulate, SiLU, (+residual), write.
 //   (A first version owned one image per thread-block cluster with DSMEM reductions; ncu showed it latency-bound on
 //   cluster syncs and co-scheduling -- see profiles/r01_notes.md.)
@@ -53,29 +53,28 @@ groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int
         r[k] = rin != nullptr ? __ldg(rin + tid + k * GN_THREADS) : make_uint4(0, 0, 0, 0);
     }
 
-    {   // warp g merges group g
+    {   // warp g merges group g: nwb warp blocks x (C / 64) eight-channel pieces, 256 elements behind each partial
         const int nwb = a.P / 32;                                        // warp blocks of this image
-        const float2* pp = a.part + (static_cast<size_t>(b) * nwb) * GN_GROUPS + warp;
-        const float cnt = 32.0f * static_cast<float>(cpg);               // elements behind one partial
-        float2 mine[4];
+        const int ppg = a.C / 64;                                        // pieces per group
+        const int ppr = a.C / 8;                                         // pieces per partial row
+        const int nent = nwb * ppg;                                      // <= 128 on every level of the UNet
+        const float2* pp = a.part + (static_cast<size_t>(b) * nwb) * ppr + warp * ppg;
+        const float cnt = 256.0f;
         float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {                                    // nwb <= 128: at most 4 partials per lane
-            const int idx = lane + 32 * i;
-            mine[i] = idx < nwb ? __ldg(pp + static_cast<size_t>(idx) * GN_GROUPS) : make_float2(0.f, 0.f);
-            s += mine[i].x;
+        for (int idx = lane; idx < nent; idx += 32) {
+            const int blk = idx / ppg;
+            s += __ldg(pp + static_cast<size_t>(blk) * ppr + (idx - blk * ppg)).x;
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
         const float total = static_cast<float>(a.P) * static_cast<float>(cpg);
         const float mean = s / total;
         float m2 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (lane + 32 * i < nwb) {
-                const float dm = mine[i].x / cnt - mean;
-                m2 += mine[i].y + cnt * dm * dm;
-            }
+        for (int idx = lane; idx < nent; idx += 32) {                   // second sweep hits L1/L2 (<= 16 KiB per image)
+            const int blk = idx / ppg;
+            const float2 e = __ldg(pp + static_cast<size_t>(blk) * ppr + (idx - blk * ppg));
+            const float dm = e.x / cnt - mean;
+            m2 += e.y + cnt * dm * dm;
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, off);
@@ -154,28 +153,35 @@ groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int
     }
 }
 
-// Stand-alone partial producer (same layout as the conv epilogue's): one warp per 32-pixel block, lanes = pixels.
+// Stand-alone partial producer (same layout as the conv epilogue's): one warp per 32-pixel block, lanes = pixels,
+// one (sum, M2) pair per 8-channel piece.
 __global__ void __launch_bounds__(256)
 groupnorm_stats_kernel(const bf16* __restrict__ x, float2* __restrict__ part, int nblocks, int C) {
     const int wb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wb >= nblocks) return;
-    const int cpg = C / GN_GROUPS;
+    const int pieces = C / 8;
     const bf16* row = x + (static_cast<size_t>(wb) * 32 + lane) * C;
-    for (int g = 0; g < GN_GROUPS; ++g) {
+    for (int p = 0; p < pieces; ++p) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(row + p * 8));
+        float v[8];
+        float2 t;
+        t = ptx::unpack_bf16x2(u.x); v[0] = t.x; v[1] = t.y;
+        t = ptx::unpack_bf16x2(u.y); v[2] = t.x; v[3] = t.y;
+        t = ptx::unpack_bf16x2(u.z); v[4] = t.x; v[5] = t.y;
+        t = ptx::unpack_bf16x2(u.w); v[6] = t.x; v[7] = t.y;
         float s = 0.f;
-        for (int c = 0; c < cpg; ++c) s += __bfloat162float(row[g * cpg + c]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[j];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        const float mean = s / (32.0f * cpg);
+        const float mean = s * (1.0f / 256.0f);
         float m2 = 0.f;
-        for (int c = 0; c < cpg; ++c) {
-            const float d = __bfloat162float(row[g * cpg + c]) - mean;
-            m2 = fmaf(d, d, m2);
-        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m2 = fmaf(v[j] - mean, v[j] - mean, m2);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, off);
-        if (lane == 0) part[static_cast<size_t>(wb) * GN_GROUPS + g] = make_float2(s, m2);
+        if (lane == 0) part[static_cast<size_t>(wb) * pieces + p] = make_float2(s, m2);
     }
 }
 
@@ -290,7 +296,7 @@ cudaError_t groupnorm_film_silu_run(const GroupNormArgs& a, cudaStream_t s) {
     if (a.C % 64 != 0 || a.C > 512 || GN_THREADS % (a.C / 8) != 0 || a.P % 32 != 0 || a.part == nullptr)
         return cudaErrorInvalidValue;
     const size_t img_chunks = static_cast<size_t>(a.P) * a.C / 8;
-    if (img_chunks % GN_SLAB_CHUNKS != 0 || a.P / 32 > 128) return cudaErrorInvalidValue;   // images are 32 KiB .. 2 MiB here
+    if (img_chunks % GN_SLAB_CHUNKS != 0) return cudaErrorInvalidValue;   // images are 32 KiB .. 2 MiB here
     // each CTA walks `iters` consecutive 16 KiB pieces (amortises the statistics prologue) while keeping >= ~4 waves
     int iters = 4;
     while (iters > 1 && ((img_chunks / GN_SLAB_CHUNKS) % iters != 0 ||

@@ -133,7 +133,7 @@ struct Exec {
     float* film_rows = nullptr;  // [B, film_ld]
     int* iota = nullptr;     // [B]
     float* ctx = nullptr;    // linear-attention scratch [B,4,32,32]
-    float2* gn_part = nullptr;  // GroupNorm partial statistics [B*4096/32][8], rewritten by every GN-feeding conv
+    float2* gn_part = nullptr;  // GroupNorm partial statistics [B*P/32][C/8], rewritten by every GN-feeding conv
     std::vector<Op> ops_rows, ops_table;
     cudaGraphExec_t g_eps = nullptr, g_step = nullptr;
     std::map<std::string, DebugEntry> dbg;
@@ -262,8 +262,8 @@ struct Builder {
     // conv on the tcgen05 path
     Act conv(const std::string& wkey, const std::string& bkey, const Act& x0, const Act* x1, int Cout, int ksize,
              ConvMode mode, ConvEpilogue epi, int n_rows = 0, bool gn_stats = false) {
-        const int Ho = mode == CONV_UNSHUFFLE ? x0.H / 2 : x0.H;
-        const int Wo = mode == CONV_UNSHUFFLE ? x0.W / 2 : x0.W;
+        const int Ho = mode == CONV_UNSHUFFLE ? x0.H / 2 : (mode == CONV_UPSAMPLE ? x0.H * 2 : x0.H);
+        const int Wo = mode == CONV_UNSHUFFLE ? x0.W / 2 : (mode == CONV_UPSAMPLE ? x0.W * 2 : x0.W);
         const int N = n_rows ? n_rows : Cout;
         Act y;
         if (epi.out_f32 == nullptr) y = alloc_act(Ho, Wo, N); else { y.H = Ho; y.W = Wo; y.C = N; }
@@ -286,8 +286,10 @@ struct Builder {
             op.kernel = "conv_gemm";
             const double M = static_cast<double>(B) * Ho * Wo;
             const double K = static_cast<double>(l.nkb) * 64;
+            // FLOPs the kernel EXECUTES (the upsample fold runs 4 of the reference's 9 taps per output pixel)
             op.flops = 2.0 * M * Cout * K;
-            op.bytes = 2.0 * (M * (x0.C + (x1 ? x1->C : 0)) * (mode == CONV_UNSHUFFLE ? 4 : 1) + static_cast<double>(N) * K) +
+            const double in_scale = mode == CONV_UNSHUFFLE ? 4.0 : (mode == CONV_UPSAMPLE ? 0.25 : 1.0);
+            op.bytes = 2.0 * (M * (x0.C + (x1 ? x1->C : 0)) * in_scale + static_cast<double>(N) * K * (mode == CONV_UPSAMPLE ? 4 : 1)) +
                        (epi.out_f32 ? 4.0 * M * epi.n_valid : 2.0 * M * N) + (epi.res ? 2.0 * M * N : 0.0);
             ops->push_back(op);
         }
@@ -480,9 +482,10 @@ struct Builder {
             Act s2 = hs.back(); hs.pop_back();
             Act b = resblock(p + ".1", a, &s2, dout);
             free_act(a); free_act(s2);
-            Act cst = linattn(p + ".2", b, !last);     // the attention's closing LayerNorm also does Upsample's x2
+            Act cst = linattn(p + ".2", b, false);
             free_act(b);
-            if (!last) x = conv(p + ".3.1.weight", p + ".3.1.bias", cst, nullptr, din, 3, CONV_TAPS, ConvEpilogue());
+            // Upsample: the nearest x2 is folded into the conv (four 2x2 phase convs over the low-res tensor)
+            if (!last) x = conv(p + ".3.1.weight", p + ".3.1.bias", cst, nullptr, din, 3, CONV_UPSAMPLE, ConvEpilogue());
             else x = conv(p + ".3.weight", p + ".3.bias", cst, nullptr, din, 3, CONV_TAPS, ConvEpilogue());
             free_act(cst);
             note(p + ".3", x);
@@ -619,7 +622,7 @@ int get_exec(hd_plan* P, int B, cudaStream_t s, Exec** out) {
     EX_TRY(cudaMalloc(&ex->film_rows, static_cast<size_t>(B) * P->film_ld * 4));
     EX_TRY(cudaMalloc(&ex->iota, B * 4));
     EX_TRY(cudaMalloc(&ex->ctx, static_cast<size_t>(B) * 4 * 32 * 32 * 4));
-    EX_TRY(cudaMalloc(&ex->gn_part, static_cast<size_t>(B) * (tile / 32) * 8 * sizeof(float2)));
+    EX_TRY(cudaMalloc(&ex->gn_part, static_cast<size_t>(B) * (tile / 32) * 64 * sizeof(float2)));   // [M/32][C/8], C <= 512
     EX_TRY(cudaMemsetAsync(ex->x, 0, B * tile * 4, s));
     EX_TRY(cudaMemsetAsync(ex->cond, 0, B * tile * 4, s));
     EX_TRY(cudaMemsetAsync(ex->time, 0, B * 4, s));
@@ -849,7 +852,15 @@ int hd_plan_finalize(hd_plan* P, void* stream) {
         wq_bytes += bytes;
         P->wq[key] = q;
         const bool is_down = !P->hicedrn && key.compare(0, 6, "downs.") == 0 && ends_with(key, ".3.1.weight");
-        if (is_down) {
+        const bool is_up = !P->hicedrn && key.compare(0, 4, "ups.") == 0 && ends_with(key, ".3.1.weight");
+        if (is_up) {
+            if (k != 3) return fail("Upsample weight '%s' has an unexpected shape", key.c_str());
+            cudaFree(q);
+            const size_t ub = static_cast<size_t>(4) * Cout * 4 * Cin * 2;   // four phase matrices [Cout, 4*Cin]
+            CUDA_TRY(cudaMalloc(&q, ub));
+            P->wq[key] = q;
+            CUDA_TRY(prep_upsample_weight_run(w.d, q, Cout, Cin, s));
+        } else if (is_down) {
             if (k != 1 || Cin % 4 != 0) return fail("Downsample weight '%s' has an unexpected shape", key.c_str());
             CUDA_TRY(prep_unshuffle_weight_run(w.d, q, Cout, Cin / 4, s));
         } else {
@@ -993,11 +1004,13 @@ int hd_op_conv2d(const uint16_t* x0, int32_t C0, const uint16_t* x1, int32_t C1,
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int Cin = C0 + (x1 ? C1 : 0);
-    const int taps = mode == CONV_UNSHUFFLE ? 4 : ksize * ksize;
+    const int taps = mode == CONV_UNSHUFFLE ? 4 : (mode == CONV_UPSAMPLE ? 16 : ksize * ksize);
+    if (mode == CONV_UPSAMPLE && (ksize != 3 || x1 != nullptr)) return fail("hd_op_conv2d: upsample mode is a 3x3 conv of one source");
     bf16* q = nullptr;
     CUDA_TRY(cudaMalloc(&q, static_cast<size_t>(Cout) * Cin * taps * 2));
     cudaError_t e = mode == CONV_UNSHUFFLE ? prep_unshuffle_weight_run(w, q, Cout, Cin, s)
-                                           : prep_conv_weight_run(w, q, Cout, Cin, ksize, standardize, 1e-5f, Cout, s);
+                    : mode == CONV_UPSAMPLE ? prep_upsample_weight_run(w, q, Cout, Cin, s)
+                                            : prep_conv_weight_run(w, q, Cout, Cin, ksize, standardize, 1e-5f, Cout, s);
     if (e != cudaSuccess) { cudaFree(q); return fail("weight prep failed: %s", cudaGetErrorString(e)); }
     ConvGemmDesc d;
     d.src0 = ConvSrc{reinterpret_cast<const bf16*>(x0), C0};
@@ -1037,7 +1050,7 @@ int hd_op_groupnorm_silu(const uint16_t* x, uint16_t* y, const float* gamma, con
     }
     if (res) g.res = reinterpret_cast<const bf16*>(res);
     float2* part = nullptr;
-    CUDA_TRY(cudaMalloc(&part, static_cast<size_t>(B) * (P / 32 + 1) * 8 * sizeof(float2)));
+    CUDA_TRY(cudaMalloc(&part, static_cast<size_t>(B) * (P / 32 + 1) * (C / 8) * sizeof(float2)));
     g.part = part;
     cudaError_t e = groupnorm_stats_run(g.x, part, B, P, C, s);
     if (e == cudaSuccess) e = groupnorm_film_silu_run(g, s);

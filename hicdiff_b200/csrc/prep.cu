@@ -79,6 +79,34 @@ prep_unshuffle_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out
     }
 }
 
+// Upsample = nearest x2 followed by a 3x3 conv (/root/reference/src/hicdiff_condition.py:72-76).  Output pixel
+// (2i + a, 2j + b) only ever sees the low-res pixels (i + a - 1 + u, j + b - 1 + v), u, v in {0, 1}: original tap ky
+// lands on u = (a + ky + 1) / 2 - a  (a = 0: ky 0 -> u 0, ky 1,2 -> u 1;  a = 1: ky 0,1 -> u 0, ky 2 -> u 1).
+// out[phase = a*2 + b][co][(u*2 + v) * Cin + ci] = sum of the original taps that collapse onto (u, v), in fp32.
+__global__ void __launch_bounds__(256)
+prep_upsample_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin) {
+    const int co = blockIdx.x;
+    const int phase = blockIdx.y;
+    const int a = phase >> 1, b = phase & 1;
+    const int K = 4 * Cin;
+    bf16* orow = out + (static_cast<size_t>(phase) * Cout + co) * K;
+    const float* wrow = w + static_cast<size_t>(co) * Cin * 9;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        const int tap = i / Cin;
+        const int ci = i - tap * Cin;
+        const int u = tap >> 1, v = tap & 1;
+        float acc = 0.f;
+        for (int ky = 0; ky < 3; ++ky) {
+            if ((a + ky + 1) / 2 - a != u) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                if ((b + kx + 1) / 2 - b != v) continue;
+                acc += wrow[ci * 9 + ky * 3 + kx];
+            }
+        }
+        orow[i] = __float2bfloat16(acc);
+    }
+}
+
 __global__ void __launch_bounds__(128)
 posenc_rows_kernel(const float* __restrict__ t, float* __restrict__ y, int rows, int dim, int mode) {
     const int r = blockIdx.x;
@@ -133,6 +161,11 @@ cudaError_t prep_conv_weight_run(const float* w, bf16* out, int Cout, int Cin, i
 
 cudaError_t prep_unshuffle_weight_run(const float* w, bf16* out, int Cout, int C, cudaStream_t s) {
     prep_unshuffle_weight_kernel<<<Cout, 256, 0, s>>>(w, out, Cout, C);
+    return cudaGetLastError();
+}
+
+cudaError_t prep_upsample_weight_run(const float* w, bf16* out, int Cout, int Cin, cudaStream_t s) {
+    prep_upsample_weight_kernel<<<dim3(Cout, 4), 256, 0, s>>>(w, out, Cout, Cin);
     return cudaGetLastError();
 }
 

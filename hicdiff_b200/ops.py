@@ -29,9 +29,10 @@ def _f32c(t):
     return t.detach().to(torch.float32).contiguous()
 
 
-def conv2d_nhwc(x0, w, bias=None, x1=None, res=None, ksize=None, standardize=False, unshuffle=False):
+def conv2d_nhwc(x0, w, bias=None, x1=None, res=None, ksize=None, standardize=False, unshuffle=False, upsample=False):
     """Implicit-GEMM conv. x0/x1: [B,H,W,C] bf16 (x1 = second operand of a channel concat); w: fp32
-    [Cout, Cin, k, k] in the reference layout.  `unshuffle=True` is Downsample (pixel-unshuffle + 1x1)."""
+    [Cout, Cin, k, k] in the reference layout.  `unshuffle=True` is Downsample (pixel-unshuffle + 1x1),
+    `upsample=True` is Upsample (nearest x2 + 3x3, folded into four 2x2 phase convs over the low-res input)."""
     lib = _lib.load()
     _need_cuda(x0, w)
     x0, x1, res = _bf16c(x0), _bf16c(x1), _bf16c(res)
@@ -40,11 +41,12 @@ def conv2d_nhwc(x0, w, bias=None, x1=None, res=None, ksize=None, standardize=Fal
     C1 = x1.shape[-1] if x1 is not None else 0
     Cout = w.shape[0]
     k = int(w.shape[-1]) if ksize is None else ksize
-    Ho, Wo = (H // 2, W // 2) if unshuffle else (H, W)
+    Ho, Wo = (H // 2, W // 2) if unshuffle else ((2 * H, 2 * W) if upsample else (H, W))
     out = torch.empty(B, Ho, Wo, Cout, device=x0.device, dtype=torch.bfloat16)
     _lib.check(
         lib.hd_op_conv2d(_lib.ptr(x0), C0, _lib.ptr(x1), C1, _lib.ptr(w), _lib.ptr(bias), _lib.ptr(res), _lib.ptr(out),
-                         B, Ho, Wo, Cout, k, 1 if unshuffle else 0, 1 if standardize else 0, _lib.stream_ptr()),
+                         B, Ho, Wo, Cout, k, 1 if unshuffle else (2 if upsample else 0), 1 if standardize else 0,
+                         _lib.stream_ptr()),
         "hd_op_conv2d",
     )
     return out

@@ -86,6 +86,23 @@ def test_conv_gemm(B, H, C0, C1, Cout, k, std):
     _check(out, ref, f"conv {C0}+{C1}->{Cout} k{k} @{H}")
 
 
+@pytest.mark.parametrize("B,Hl,C,Cout", [(2, 32, 128, 64), (2, 16, 256, 128), (2, 8, 512, 256), (3, 8, 512, 256)])
+def test_upsample_conv(B, Hl, C, Cout):
+    """Upsample = nn.Upsample(scale_factor=2, mode='nearest') + Conv2d(3, padding=1) (hicdiff_condition.py:72-76), run as
+    four 2x2 phase convs over the low-res input.  The folded weights are sums of up to four taps rounded to bf16 once,
+    so the reference convolves with the fp64 weights and the tolerance carries one extra bf16 weight rounding."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(300 + Hl + B)
+    x = _rand_nhwc(B, Hl, Hl, C, g)
+    w = (torch.randn(Cout, C, 3, 3, generator=g) / math.sqrt(C * 9)).to(DEV)
+    bias = (torch.randn(Cout, generator=g) * 0.1).to(DEV)
+    out = ops.conv2d_nhwc(x, w, bias, upsample=True)
+    torch.cuda.synchronize()
+    up = F.interpolate(_nchw64(x), scale_factor=2, mode="nearest")
+    ref = F.conv2d(up, w.to(torch.float64), bias.to(torch.float64), padding=1)
+    _check(out, ref, f"upsample conv {C}->{Cout} @{Hl}->{2 * Hl}", rel_rms=6e-3)
+
+
 def test_conv_gemm_residual_epilogue():
     ops = _ops()
     g = torch.Generator().manual_seed(7)
