@@ -51,6 +51,7 @@ SIGNATURES = {
     "hd_op_groupnorm_silu": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "hd_op_channel_layernorm": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "hd_op_linear_attention": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
+    "hd_op_linattn_block": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, C.POINTER(C.c_float), _vp]),
     "hd_op_full_attention": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
     "hd_op_stem_conv": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "hd_op_philox_normal": (C.c_int, [_vp, _i64, _u64, _u64, _vp]),

@@ -521,8 +521,10 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-int encode_map(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-               const cuuint32_t* box, char* err, int errlen) {
+}  // namespace
+
+int encode_tmap_bf16(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                     const cuuint32_t* box, char* err, int errlen) {
     EncodeTiledFn fn = get_encode_fn();
     if (fn == nullptr) {
         snprintf(err, errlen, "cuTensorMapEncodeTiled entry point not available");
@@ -538,6 +540,13 @@ int encode_map(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dim
         return 1;
     }
     return 0;
+}
+
+namespace {
+
+inline int encode_map(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box, char* err, int errlen) {
+    return encode_tmap_bf16(tm, ptr, rank, dims, strides_bytes, box, err, errlen);
 }
 
 // Hs x Ws: spatial size of the SOURCE tensor the taps walk over (== output size except for CONV_UPSAMPLE: low-res).

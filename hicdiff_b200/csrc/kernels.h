@@ -81,6 +81,10 @@ struct ConvGemmLaunch {
 int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, char* err, int errlen);
 cudaError_t conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t s);
 
+// bf16 tiled tensor map with 128-byte swizzle (driver entry point resolved at run time; no libcuda link dependency)
+int encode_tmap_bf16(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                     const cuuint32_t* box, char* err, int errlen);
+
 // ---------------------------------------------------------------------------------------------
 // norm.cu -- GroupNorm(8)+FiLM+SiLU (cluster/DSMEM two-pass), channel LayerNorm
 // ---------------------------------------------------------------------------------------------
@@ -129,6 +133,33 @@ struct LinAttnArgs {
     int B, n;
 };
 cudaError_t linear_attention_run(const LinAttnArgs& a, cudaStream_t s);
+
+// linattn_fused.cu -- the whole Residual(PreNorm(LinearAttention)) block in three launches (C <= 128, n >= 128)
+struct LinAttnFusedDesc {
+    const bf16* x;          // [B, n, C] block input (also the residual)
+    bf16* y;                // [B, n, C] block output
+    int B, n, C;
+    const bf16* wqkv;       // [384, C] to_qkv weight with the PreNorm gain folded in (linattn_prep_run)
+    const float* rowsum;    // [384] row sums of wqkv (LayerNorm mean correction)
+    const float* kshift;    // [128] softmax_n shift per k channel
+    const float* wo;        // [C, 128] to_out.0 weight (reference layout, fp32)
+    const float* bo;        // [C]
+    const float* g2;        // [C] to_out.1 gain
+    float* ctx_part;        // scratch [B * max_parts][128][32]
+    float* s_part;          // scratch [B * max_parts][128]
+    bf16* mb;               // scratch [B][C][128]
+    int max_parts;
+    float eps;
+};
+struct LinAttnFusedLaunch {
+    LinAttnFusedDesc d;
+    CUtensorMap tmX, tmW, tmM, tmY;
+    int parts, tiles_per_unit, num_tiles, out_grid;
+};
+cudaError_t linattn_prep_run(const float* wqkv, const float* g1, bf16* out, float* rowsum, float* kshift,
+                             int* max_bound_bits, int C, cudaStream_t s);
+int linattn_fused_prepare(const LinAttnFusedDesc& d, int num_sms, LinAttnFusedLaunch* out, char* err, int errlen);
+cudaError_t linattn_fused_run(const LinAttnFusedLaunch& l, cudaStream_t s);
 
 struct FullAttnArgs {
     const bf16* qkv;   // [B, n, 384], n <= 64

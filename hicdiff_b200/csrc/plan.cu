@@ -39,6 +39,9 @@ int fail(const char* fmt, ...) {
         if (e__ != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(e__));    \
     } while (0)
 
+constexpr int LA_MAX_PARTS = 8;
+constexpr float LA_MAX_BOUND = 100.0f;   // beyond this the analytic softmax shift could underflow: use the unfused kernels
+
 struct WeightT {
     float* d = nullptr;
     std::vector<int64_t> shape;
@@ -134,6 +137,9 @@ struct Exec {
     int* iota = nullptr;     // [B]
     float* ctx = nullptr;    // linear-attention scratch [B,4,32,32]
     float2* gn_part = nullptr;  // GroupNorm partial statistics [B*P/32][C/8], rewritten by every GN-feeding conv
+    float* la_ctx = nullptr;    // fused linear attention: partial contexts [B*8][128][32]
+    float* la_s = nullptr;      //                          partial softmax denominators [B*8][128]
+    bf16* la_mb = nullptr;      //                          per-image to_out * ctx matrices [B][128][128]
     std::vector<Op> ops_rows, ops_table;
     cudaGraphExec_t g_eps = nullptr, g_step = nullptr;
     std::map<std::string, DebugEntry> dbg;
@@ -143,6 +149,15 @@ struct Exec {
 
 }  // namespace
 
+struct LinAttnPrep {          // gain-folded to_qkv weights of one LinearAttention block (linattn_fused.cu)
+    bf16* wqkv = nullptr;     // [384, C]
+    float* rowsum = nullptr;  // [384]
+    float* kshift = nullptr;  // [128]
+    int* bound_bits = nullptr;
+    float bound = 0.f;        // max_d sqrt(C) * ||Wk'_d||_2, read back at finalize
+    int C = 0;
+};
+
 struct hd_plan {
     hd_config cfg;
     int device = 0;
@@ -150,6 +165,7 @@ struct hd_plan {
     std::map<std::string, WeightT> w;
     std::map<std::string, bf16*> wq;      // GEMM-layout bf16 weights
     std::map<std::string, float*> padded; // zero-padded fp32 vectors (bias of padded-N convs)
+    std::map<std::string, LinAttnPrep> lattn;  // Residual prefix -> fused linear-attention weights
     std::vector<FilmSlot> film;
     std::map<std::string, int> film_index;  // block prefix -> slot
     int film_ld = 0;
@@ -364,6 +380,31 @@ struct Builder {
 
     // Residual(PreNorm(dim, LinearAttention(dim)))  (hicdiff_condition.py:199-227,319)
     Act linattn(const std::string& p, const Act& x, bool up2x) {
+        auto lp = P->lattn.find(p);
+        if (!up2x && lp != P->lattn.end() && lp->second.bound <= LA_MAX_BOUND && lp->second.C == x.C &&
+            x.H * x.W >= 128 && (x.H * x.W) % 128 == 0) {
+            // whole Residual(PreNorm(LinearAttention)) block in three launches; qkv never reaches HBM
+            Act y = alloc_act(x.H, x.W, x.C);
+            LinAttnFusedDesc d;
+            d.x = x.p; d.y = y.p; d.B = B; d.n = x.H * x.W; d.C = x.C;
+            d.wqkv = lp->second.wqkv; d.rowsum = lp->second.rowsum; d.kshift = lp->second.kshift;
+            d.wo = wf(p + ".fn.fn.to_out.0.weight"); d.bo = wf(p + ".fn.fn.to_out.0.bias"); d.g2 = wf(p + ".fn.fn.to_out.1.g");
+            d.ctx_part = dry ? nullptr : ex->la_ctx; d.s_part = dry ? nullptr : ex->la_s; d.mb = dry ? nullptr : ex->la_mb;
+            d.max_parts = LA_MAX_PARTS; d.eps = 1e-5f;
+            if (ok && !dry) {
+                LinAttnFusedLaunch l;
+                char e[256];
+                if (linattn_fused_prepare(d, P->num_sms, &l, e, sizeof(e))) { bad(p + ": " + e); return y; }
+                Op op{[l](cudaStream_t s) { return linattn_fused_run(l, s); }, p + ".linattn_fused"};
+                op.kernel = "linattn_fused";
+                const double M = static_cast<double>(B) * d.n;
+                op.flops = 2.0 * M * x.C * 384 + 2.0 * M * 128 * 128 + 2.0 * M * 128 * x.C;   // projections, context, mixed output
+                op.bytes = 2.0 * M * x.C * 3;                                                 // x twice, y once
+                ops->push_back(op);
+            }
+            note(p, y);
+            return y;
+        }
         Act xn = layernorm(x, p + ".fn.norm.g", nullptr, false);
         Act qkv = conv(p + ".fn.fn.to_qkv.weight", "", xn, nullptr, 384, 1, CONV_TAPS, ConvEpilogue());
         free_act(xn);
@@ -558,7 +599,7 @@ void free_exec(Exec* ex) {
     if (ex->g_step) cudaGraphExecDestroy(ex->g_step);
     cudaFree(ex->arena); cudaFree(ex->x); cudaFree(ex->cond); cudaFree(ex->eps); cudaFree(ex->time);
     cudaFree(ex->posenc); cudaFree(ex->temb0); cudaFree(ex->temb); cudaFree(ex->film_rows); cudaFree(ex->iota);
-    cudaFree(ex->ctx); cudaFree(ex->gn_part);
+    cudaFree(ex->ctx); cudaFree(ex->gn_part); cudaFree(ex->la_ctx); cudaFree(ex->la_s); cudaFree(ex->la_mb);
 }
 
 int run_ops(const std::vector<Op>& ops, cudaStream_t s) {
@@ -623,6 +664,11 @@ int get_exec(hd_plan* P, int B, cudaStream_t s, Exec** out) {
     EX_TRY(cudaMalloc(&ex->iota, B * 4));
     EX_TRY(cudaMalloc(&ex->ctx, static_cast<size_t>(B) * 4 * 32 * 32 * 4));
     EX_TRY(cudaMalloc(&ex->gn_part, static_cast<size_t>(B) * (tile / 32) * 64 * sizeof(float2)));   // [M/32][C/8], C <= 512
+    if (!P->lattn.empty()) {
+        EX_TRY(cudaMalloc(&ex->la_ctx, static_cast<size_t>(B) * LA_MAX_PARTS * 128 * 32 * 4));
+        EX_TRY(cudaMalloc(&ex->la_s, static_cast<size_t>(B) * LA_MAX_PARTS * 128 * 4));
+        EX_TRY(cudaMalloc(&ex->la_mb, static_cast<size_t>(B) * 128 * 128 * 2));
+    }
     EX_TRY(cudaMemsetAsync(ex->x, 0, B * tile * 4, s));
     EX_TRY(cudaMemsetAsync(ex->cond, 0, B * tile * 4, s));
     EX_TRY(cudaMemsetAsync(ex->time, 0, B * 4, s));
@@ -880,6 +926,35 @@ int hd_plan_finalize(hd_plan* P, void* stream) {
         }
     }
 
+    // ---- fused linear-attention blocks: fold the PreNorm gain into to_qkv, row sums, softmax shifts
+    for (auto& kv : P->lattn) { cudaFree(kv.second.wqkv); cudaFree(kv.second.rowsum); cudaFree(kv.second.kshift); cudaFree(kv.second.bound_bits); }
+    P->lattn.clear();
+    if (!P->hicedrn) {
+        const char* suf = ".fn.fn.to_qkv.weight";
+        for (auto& kv : P->w) {
+            const std::string& key = kv.first;
+            if (!ends_with(key, suf) || key.compare(0, 8, "mid_attn") == 0) continue;
+            const std::string pre = key.substr(0, key.size() - strlen(suf));
+            const int C = static_cast<int>(kv.second.shape[1]);
+            const WeightT* g1 = find_w(P, pre + ".fn.norm.g");
+            if ((C != 64 && C != 128) || kv.second.shape[0] != 384 || !g1) continue;
+            LinAttnPrep lp;
+            lp.C = C;
+            CUDA_TRY(cudaMalloc(&lp.wqkv, static_cast<size_t>(384) * C * 2));
+            CUDA_TRY(cudaMalloc(&lp.rowsum, 384 * 4));
+            CUDA_TRY(cudaMalloc(&lp.kshift, 128 * 4));
+            CUDA_TRY(cudaMalloc(&lp.bound_bits, 4));
+            CUDA_TRY(linattn_prep_run(kv.second.d, g1->d, lp.wqkv, lp.rowsum, lp.kshift, lp.bound_bits, C, s));
+            P->lattn[pre] = lp;
+        }
+        CUDA_TRY(cudaStreamSynchronize(s));
+        for (auto& kv : P->lattn) {
+            int bits = 0;
+            CUDA_TRY(cudaMemcpy(&bits, kv.second.bound_bits, 4, cudaMemcpyDeviceToHost));
+            memcpy(&kv.second.bound, &bits, 4);
+        }
+    }
+
     // ---- control blocks + [T, film_ld] table
     if (!P->ctl) { CUDA_TRY(cudaMalloc(&P->ctl, sizeof(SampleCtl))); CUDA_TRY(cudaMemsetAsync(P->ctl, 0, sizeof(SampleCtl), s)); }
     if (!P->ctl_one) { CUDA_TRY(cudaMalloc(&P->ctl_one, sizeof(SampleCtl))); CUDA_TRY(cudaMemsetAsync(P->ctl_one, 0, sizeof(SampleCtl), s)); }
@@ -911,6 +986,7 @@ void hd_plan_destroy(hd_plan* P) {
     for (auto& kv : P->w) cudaFree(kv.second.d);
     for (auto& kv : P->wq) cudaFree(kv.second);
     for (auto& kv : P->padded) cudaFree(kv.second);
+    for (auto& kv : P->lattn) { cudaFree(kv.second.wqkv); cudaFree(kv.second.rowsum); cudaFree(kv.second.kshift); cudaFree(kv.second.bound_bits); }
     cudaFree(P->coef); cudaFree(P->time_values); cudaFree(P->film_table); cudaFree(P->ctl); cudaFree(P->ctl_one);
     if (P->cap_stream) cudaStreamDestroy(P->cap_stream);
     delete P;
@@ -1086,6 +1162,52 @@ int hd_op_linear_attention(const uint16_t* qkv, uint16_t* out, int32_t B, int32_
     return 0;
 }
 
+int hd_op_linattn_block(const uint16_t* x, const float* g1, const float* wqkv, const float* wo, const float* bo,
+                        const float* g2, uint16_t* y, int32_t B, int32_t n, int32_t C, float* bound_out, void* stream) {
+    if (!x || !g1 || !wqkv || !wo || !bo || !g2 || !y) return fail("hd_op_linattn_block: null argument");
+    if (C != 64 && C != 128) return fail("hd_op_linattn_block: C must be 64 or 128 (got %d)", C);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    bf16 *wq = nullptr, *mb = nullptr;
+    float *rowsum = nullptr, *kshift = nullptr, *ctx = nullptr, *sp = nullptr;
+    int* bits = nullptr;
+    auto cleanup = [&]() { cudaFree(wq); cudaFree(mb); cudaFree(rowsum); cudaFree(kshift); cudaFree(ctx); cudaFree(sp); cudaFree(bits); };
+#define OP_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess) { cleanup(); return fail("%s failed: %s", #expr, cudaGetErrorString(e__)); } \
+    } while (0)
+    OP_TRY(cudaMalloc(&wq, static_cast<size_t>(384) * C * 2));
+    OP_TRY(cudaMalloc(&rowsum, 384 * 4));
+    OP_TRY(cudaMalloc(&kshift, 128 * 4));
+    OP_TRY(cudaMalloc(&bits, 4));
+    OP_TRY(cudaMalloc(&ctx, static_cast<size_t>(B) * LA_MAX_PARTS * 128 * 32 * 4));
+    OP_TRY(cudaMalloc(&sp, static_cast<size_t>(B) * LA_MAX_PARTS * 128 * 4));
+    OP_TRY(cudaMalloc(&mb, static_cast<size_t>(B) * C * 128 * 2));
+    OP_TRY(linattn_prep_run(wqkv, g1, wq, rowsum, kshift, bits, C, s));
+    OP_TRY(cudaStreamSynchronize(s));
+    int hb = 0;
+    OP_TRY(cudaMemcpy(&hb, bits, 4, cudaMemcpyDeviceToHost));
+    float bound;
+    memcpy(&bound, &hb, 4);
+    if (bound_out) *bound_out = bound;
+    if (bound > LA_MAX_BOUND) { cleanup(); return fail("hd_op_linattn_block: softmax bound %.1f exceeds %.1f (the plan uses the unfused kernels)", bound, LA_MAX_BOUND); }
+    LinAttnFusedDesc d;
+    d.x = reinterpret_cast<const bf16*>(x); d.y = reinterpret_cast<bf16*>(y); d.B = B; d.n = n; d.C = C;
+    d.wqkv = wq; d.rowsum = rowsum; d.kshift = kshift; d.wo = wo; d.bo = bo; d.g2 = g2;
+    d.ctx_part = ctx; d.s_part = sp; d.mb = mb; d.max_parts = LA_MAX_PARTS; d.eps = 1e-5f;
+    LinAttnFusedLaunch l;
+    char msg[256];
+    if (linattn_fused_prepare(d, sms, &l, msg, sizeof(msg))) { cleanup(); return fail("%s", msg); }
+    OP_TRY(linattn_fused_run(l, s));
+    OP_TRY(cudaStreamSynchronize(s));
+#undef OP_TRY
+    cleanup();
+    return 0;
+}
+
 int hd_op_full_attention(const uint16_t* qkv, uint16_t* out, int32_t B, int32_t n, void* stream) {
     if (!qkv || !out) return fail("hd_op_full_attention: null argument");
     FullAttnArgs a;
@@ -1161,7 +1283,7 @@ int hd_plan_launches_per_step(hd_plan* P, int32_t B, int32_t* eps_launches, int3
     // linear attention is two kernels behind one op
     auto count = [](const std::vector<Op>& ops) {
         int n = 0;
-        for (const Op& o : ops) n += ends_with(o.tag, ".linattn") ? 2 : 1;
+        for (const Op& o : ops) n += ends_with(o.tag, ".linattn") ? 2 : (ends_with(o.tag, ".linattn_fused") ? 3 : 1);
         return n;
     };
     if (eps_launches) *eps_launches = count(it->second->ops_rows);

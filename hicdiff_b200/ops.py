@@ -93,6 +93,24 @@ def linear_attention_nhwc(qkv):
     return out
 
 
+def linattn_block_nhwc(x, g1, wqkv, wo, bo, g2):
+    """Fused Residual(PreNorm(LinearAttention)): x [B,H,W,C] bf16 (C in {64,128}, H*W >= 128); g1/g2 [C] LayerNorm gains,
+    wqkv [384,C(,1,1)], wo [C,128(,1,1)], bo [C].  Returns (y [B,H,W,C] bf16, analytic softmax bound)."""
+    import ctypes
+
+    lib = _lib.load()
+    _need_cuda(x)
+    x = _bf16c(x)
+    B, H, W, C = x.shape
+    g1, wqkv, wo, bo, g2 = (_f32c(t.reshape(t.shape[0], -1) if t.dim() > 1 else t) for t in (g1, wqkv, wo, bo, g2))
+    y = torch.empty_like(x)
+    bound = ctypes.c_float(0.0)
+    _lib.check(lib.hd_op_linattn_block(_lib.ptr(x), _lib.ptr(g1.reshape(-1)), _lib.ptr(wqkv), _lib.ptr(wo), _lib.ptr(bo),
+                                       _lib.ptr(g2.reshape(-1)), _lib.ptr(y), B, H * W, C, ctypes.byref(bound),
+                                       _lib.stream_ptr()), "hd_op_linattn_block")
+    return y, bound.value
+
+
 def full_attention_nhwc(qkv):
     lib = _lib.load()
     _need_cuda(qkv)

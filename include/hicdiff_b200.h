@@ -129,6 +129,11 @@ HD_API int hd_op_groupnorm_silu(const uint16_t* x, uint16_t* y, const float* gam
 HD_API int hd_op_channel_layernorm(const uint16_t* x, uint16_t* y, const float* g, const uint16_t* res, int32_t B, int32_t H,
                             int32_t W, int32_t C, int32_t upsample2x, void* stream);
 HD_API int hd_op_linear_attention(const uint16_t* qkv, uint16_t* out, int32_t B, int32_t n, void* stream);
+/* Whole Residual(PreNorm(LinearAttention)) block (hicdiff_condition.py:64-70,99-118,199-227) as the fused three-launch
+ * path the plan uses for C in {64, 128}, n >= 128: g1 [C] PreNorm gain, wqkv [384, C], wo [C, 128], bo [C], g2 [C].
+ * bound_out (host, optional) receives the analytic softmax bound; fails if it exceeds the fused path's limit. */
+HD_API int hd_op_linattn_block(const uint16_t* x, const float* g1, const float* wqkv, const float* wo, const float* bo,
+                        const float* g2, uint16_t* y, int32_t B, int32_t n, int32_t C, float* bound_out, void* stream);
 HD_API int hd_op_full_attention(const uint16_t* qkv, uint16_t* out, int32_t B, int32_t n, void* stream);
 HD_API int hd_op_stem_conv(const float* x0, const float* x1, const float* w, const float* bias, uint16_t* y, int32_t B,
                     int32_t Cout, int32_t Cin, int32_t ksize, void* stream);

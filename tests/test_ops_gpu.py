@@ -196,6 +196,55 @@ def test_linear_attention(B, H):
     _check(out, o, f"linear attention n={H * H}", rel_rms=6e-3, max_rel=3e-2)
 
 
+def _linattn_block_ref(x_nchw, g1, wqkv, wo, bo, g2):
+    """fp64 Residual(PreNorm(LinearAttention)) exactly as hicdiff_condition.py:64-70,99-118,199-227."""
+    def ln(t, g):
+        var = t.var(dim=1, unbiased=False, keepdim=True)
+        mean = t.mean(dim=1, keepdim=True)
+        return (t - mean) * (var + 1e-5).rsqrt() * g.reshape(1, -1, 1, 1)
+
+    b, c, h, w = x_nchw.shape
+    qkv = F.conv2d(ln(x_nchw, g1), wqkv.reshape(384, c, 1, 1)).chunk(3, dim=1)
+    q, k, v = (t.reshape(b, 4, 32, h * w) for t in qkv)
+    q = q.softmax(dim=-2) * 32 ** -0.5
+    k = k.softmax(dim=-1)
+    v = v / (h * w)
+    ctx = torch.einsum("bhdn,bhen->bhde", k, v)
+    out = torch.einsum("bhde,bhdn->bhen", ctx, q).reshape(b, 128, h, w)
+    out = F.conv2d(out, wo.reshape(c, 128, 1, 1), bo)
+    return ln(out, g2) + x_nchw
+
+
+@pytest.mark.parametrize("B,H,C,kscale", [(2, 64, 64, 1.0), (3, 32, 64, 1.0), (2, 32, 128, 1.0), (5, 16, 128, 1.0),
+                                          (2, 32, 64, 8.0), (300, 16, 64, 1.0)])
+def test_linattn_block_fused(B, H, C, kscale):
+    """The fused three-launch block vs the fp64 reference on the same bf16 input.  Error sources: bf16 rounding of the
+    gain-folded weights, of exp(k - shift), of the softmaxed q, of the mixed to_out matrix, and of the output (the
+    unfused chain rounds five intermediate tensors instead).  kscale = 8 pushes the analytic k bound past 40 so the
+    softmax shift is exercised."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(77 + B + H + C)
+    x = (_rand_nhwc(B, H, H, C, g, scale=1.3).float() + 0.2).to(torch.bfloat16)
+    g1 = (1 + 0.1 * torch.randn(C, generator=g)).to(DEV)
+    g2 = (1 + 0.1 * torch.randn(C, generator=g)).to(DEV)
+    wqkv = (torch.randn(384, C, generator=g) / math.sqrt(C))
+    wqkv[128:256] *= kscale
+    wqkv = wqkv.to(DEV)
+    wo = (torch.randn(C, 128, generator=g) / math.sqrt(128)).to(DEV)
+    bo = (0.1 * torch.randn(C, generator=g)).to(DEV)
+    y, bound = ops.linattn_block_nhwc(x, g1, wqkv, wo, bo, g2)
+    torch.cuda.synchronize()
+    assert (bound > 40.0) == (kscale > 1.0), f"bound {bound}"
+    xr = _nchw64(x)
+    ref = _linattn_block_ref(xr, g1.double(), wqkv.double(), wo.double(), bo.double(), g2.double())
+    _check(y, ref, f"linattn block C={C} n={H * H}", rel_rms=8e-3, max_rel=4e-2)
+    # the attention branch alone (output minus the residual), where all the approximation lives
+    br = _nchw64(y) - xr
+    br_ref = ref - xr
+    rel = ((br - br_ref).pow(2).mean().sqrt() / br_ref.pow(2).mean().sqrt()).item()
+    assert rel <= 3e-2, f"attention branch rel-RMS {rel:.3e}"
+
+
 def test_full_attention():
     ops = _ops()
     g = torch.Generator().manual_seed(33)
