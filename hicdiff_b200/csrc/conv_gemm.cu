@@ -146,7 +146,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     constexpr uint32_t B_BLOCK = C::B_BLOCK_BYTES;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
     const int stages = a.stages;
     uint8_t* sA = smem;
     uint8_t* sB = smem + stages * C::A_STAGE_BYTES;                       // per-stage weights, or the resident matrix

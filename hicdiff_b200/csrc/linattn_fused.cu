@@ -136,7 +136,7 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     using Cf = KvCfg<C>;
     constexpr int SPANS = Cf::SPANS;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
     uint8_t* sWk = smem;
     uint8_t* sWv = sWk + Cf::W_BYTES;
     uint8_t* sX = sWv + Cf::W_BYTES;                 // 2 stages
@@ -260,7 +260,8 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             s_shift[te] = a.kshift[te];
         }
         named_bar_sync(1, 256);
-        const float sk_r = s_sk[r], sv_r = s_sv[r], shift_r = s_shift[r];
+        constexpr float LOG2E = 1.4426950408889634f;
+        const float sk_r = s_sk[r] * LOG2E, sv_r = s_sv[r], shift_r = s_shift[r] * LOG2E;   // exp(k) = exp2(k * log2 e)
         const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         float ssum = 0.f;
         for (int t = 0; t < T; ++t) {
@@ -271,7 +272,7 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             if (te < 128) {
                 float mean, rstd;
                 row_stats<C>(sX + st * Cf::X_BYTES, te, a.eps, mean, rstd);
-                s_mu[te] = mean;
+                s_mu[te] = rstd * mean;          // W LN(x) = rstd * (W'x) - (rstd * mean) * rowsum(W')
                 s_rstd[te] = rstd;
             }
             named_bar_sync(1, 256);
@@ -296,9 +297,9 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
                     for (int e2 = 0; e2 < 4; ++e2) {
                         const int j = jj * 8 + e2 * 2;
-                        const float k0 = rs[j] * (__uint_as_float(v[j]) - mu[j] * sk_r) - shift_r;
-                        const float k1 = rs[j + 1] * (__uint_as_float(v[j + 1]) - mu[j + 1] * sk_r) - shift_r;
-                        const __nv_bfloat162 pb = __floats2bfloat162_rn(__expf(k0), __expf(k1));
+                        const float k0 = fmaf(rs[j] * LOG2E, __uint_as_float(v[j]), -fmaf(mu[j], sk_r, shift_r));
+                        const float k1 = fmaf(rs[j + 1] * LOG2E, __uint_as_float(v[j + 1]), -fmaf(mu[j + 1], sk_r, shift_r));
+                        const __nv_bfloat162 pb = __floats2bfloat162_rn(ptx::ex2(k0), ptx::ex2(k1));
                         const float2 pf = __bfloat1622float2(pb);
                         ssum += pf.x + pf.y;                     // the denominator sums the SAME rounded p the MMA consumes
                         pk[e2] = *reinterpret_cast<const uint32_t*>(&pb);
@@ -313,8 +314,8 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
                     for (int e2 = 0; e2 < 4; ++e2) {
                         const int j = jj * 8 + e2 * 2;
-                        const float v0 = rs[j] * (__uint_as_float(v[j]) - mu[j] * sv_r);
-                        const float v1 = rs[j + 1] * (__uint_as_float(v[j + 1]) - mu[j + 1] * sv_r);
+                        const float v0 = fmaf(rs[j], __uint_as_float(v[j]), -mu[j] * sv_r);
+                        const float v1 = fmaf(rs[j + 1], __uint_as_float(v[j + 1]), -mu[j + 1] * sv_r);
                         pk[e2] = ptx::pack_bf16x2(v0, v1);
                     }
                     *reinterpret_cast<uint4*>(sV + hcol * SPAN_BYTES + sw_off(r, c32 * 4 + jj)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -354,19 +355,39 @@ linattn_mix_kernel(const float* __restrict__ ctx_part, const float* __restrict__
     const int t = threadIdx.x;          // hd = h*32 + d
     const int h = t >> 5;
     float S = 0.f;
-    for (int p = 0; p < parts; ++p) S += s_part[(static_cast<size_t>(b) * parts + p) * HD + t];
+    float4 acc4[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < parts; ++p) {
+        const size_t row = (static_cast<size_t>(b) * parts + p) * HD + t;
+        S += __ldg(s_part + row);
+        const float4* src = reinterpret_cast<const float4*>(ctx_part + row * 32);
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(src + j);        // eight independent 16-byte loads in flight
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc4[j].x += v[j].x; acc4[j].y += v[j].y; acc4[j].z += v[j].z; acc4[j].w += v[j].w; }
+    }
     const float norm = inv_n_scale / S;
-    for (int e = 0; e < 32; ++e) {
-        float c = 0.f;
-        for (int p = 0; p < parts; ++p) c += ctx_part[((static_cast<size_t>(b) * parts + p) * HD + t) * 32 + e];
-        s_ctx[t][e] = c * norm;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        s_ctx[t][4 * j] = acc4[j].x * norm; s_ctx[t][4 * j + 1] = acc4[j].y * norm;
+        s_ctx[t][4 * j + 2] = acc4[j].z * norm; s_ctx[t][4 * j + 3] = acc4[j].w * norm;
     }
     __syncthreads();
-    for (int co = 0; co < C; ++co) {
-        const float* w = wo + static_cast<size_t>(co) * HD + h * 32;
+    float c[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) c[e] = s_ctx[t][e];
+    const int per = C / gridDim.y;      // output channels of this block
+    for (int co = blockIdx.y * per; co < (blockIdx.y + 1) * per; ++co) {
+        const float4* w = reinterpret_cast<const float4*>(wo + static_cast<size_t>(co) * HD + h * 32);
         float acc = 0.f;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) acc = fmaf(__ldg(w + e), s_ctx[t][e], acc);
+        for (int e = 0; e < 8; ++e) {
+            const float4 w4 = __ldg(w + e);
+            acc = fmaf(w4.x, c[4 * e], acc); acc = fmaf(w4.y, c[4 * e + 1], acc);
+            acc = fmaf(w4.z, c[4 * e + 2], acc); acc = fmaf(w4.w, c[4 * e + 3], acc);
+        }
         mb[(static_cast<size_t>(b) * C + co) * HD + t] = __float2bfloat16(acc);
     }
 }
@@ -402,7 +423,7 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     using Cf = OutCfg<C>;
     constexpr int SPANS = Cf::SPANS;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
     uint8_t* sWq = smem;
     uint8_t* sX = sWq + Cf::WQ_BYTES;
     uint8_t* sMb = sX + Cf::X_BYTES;
@@ -686,7 +707,7 @@ static cudaError_t run_c(const LinAttnFusedLaunch& l, cudaStream_t s) {
     linattn_kv_kernel<C><<<d.B * l.parts, KV_THREADS, KvCfg<C>::SMEM_BYTES, s>>>(l.tmX, l.tmW, ka);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    linattn_mix_kernel<<<d.B, 128, 0, s>>>(d.ctx_part, d.s_part, d.wo, d.mb, l.parts, C,
+    linattn_mix_kernel<<<dim3(d.B, 4), 128, 0, s>>>(d.ctx_part, d.s_part, d.wo, d.mb, l.parts, C,
                                            0.17677669529663687f / static_cast<float>(d.n));   // 32^-0.5 / n
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
