@@ -48,6 +48,7 @@ SIGNATURES = {
     "hd_tile_extract": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp]),
     "hd_tile_scatter": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
     "hd_op_conv2d": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "hd_op_conv_gn": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "hd_op_groupnorm_silu": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "hd_op_channel_layernorm": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "hd_op_linear_attention": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),

@@ -40,16 +40,16 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                           // 64 bf16 = one 128-byte swizzle span
 constexpr uint32_t A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
 constexpr uint32_t SLAB_CAP_BYTES = 32 * 1024;        // (R + 2) * W pixels * 128 B: 32 / 24 / 20 KiB at W = 64 / 32 / 16
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;                       // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int MAX_STAGES = 8;
-constexpr int EPI_WARPS = 4;
-constexpr uint32_t EPI_BUF_BYTES = 32 * 128;          // 32 rows x 64 bf16, 128B-swizzled TMA-store box
+constexpr int EPI_WARPS = 8;
+constexpr uint32_t EPI_BUF_BYTES = 32 * 64;           // 32 rows x 32 bf16, 64B-swizzled TMA-store box
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int BAR_BYTES = 256;
 
 enum Kind : int { K_GENERAL = 0, K_SLAB = 1, K_SLAB_RES = 2 };
 
-template <int BN, int KIND>
+template <int BN, int KIND, bool GNF = false>
 struct Cfg {
     static constexpr uint32_t B_BLOCK_BYTES = BN * BLOCK_K * 2;                   // one (N tile, K block) of weights
     static constexpr uint32_t A_STAGE_BYTES = KIND == K_GENERAL ? A_TILE_BYTES : SLAB_CAP_BYTES;
@@ -57,15 +57,20 @@ struct Cfg {
     static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int EPI_BUFS = BN <= 64 ? 1 : 2;                             // staging buffers per epilogue warp
     static constexpr uint32_t EPI_BYTES = EPI_WARPS * EPI_BUFS * EPI_BUF_BYTES;
-    static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
-                                          : (2 * BN <= 256) ? 256 : 512;
+    // accumulator ring in TMEM: 2 stages, or 4 when the epilogue also applies GroupNorm (its second phase trails by one
+    // tile while it waits for the image's statistics)
+    static constexpr int ACC_STAGES = GNF ? 4 : 2;
+    static constexpr uint32_t ACC_COLS = ACC_STAGES * BN;
+    static constexpr uint32_t TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
+    static constexpr uint32_t GN_AUX_BYTES = GNF ? (128 + 2 * 3 * BN * 4) : 0;    // (mean, rstd)[2][8] + (mul, add, post)[2][BN]
+    static constexpr int AUX_BYTES = BAR_BYTES + static_cast<int>(GN_AUX_BYTES);
     static int stages(uint32_t res_b_bytes) {
-        const int avail = SMEM_LIMIT - 1024 - BAR_BYTES - static_cast<int>(EPI_BYTES) - static_cast<int>(res_b_bytes);
+        const int avail = SMEM_LIMIT - 1024 - AUX_BYTES - static_cast<int>(EPI_BYTES) - static_cast<int>(res_b_bytes);
         int s = avail / static_cast<int>(STAGE_BYTES);
         return s > MAX_STAGES ? MAX_STAGES : s;
     }
     static int smem_bytes(int stages, uint32_t res_b_bytes) {
-        return stages * STAGE_BYTES + res_b_bytes + EPI_BYTES + 1024 /*align*/ + BAR_BYTES;
+        return stages * STAGE_BYTES + res_b_bytes + EPI_BYTES + 1024 /*align*/ + AUX_BYTES;
     }
 };
 
@@ -138,12 +143,73 @@ __device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
     return v[0];
 }
 
-template <int BN, int KIND>
+// Arrival counter protocol of the GroupNorm-fused epilogue.  Producer: partial stores, __syncwarp, then ONE release
+// reduction (orders the warp's prior stores at L2 without the SC fence + L1 invalidate of __threadfence()).  Consumer: a
+// relaxed (strong, L2) poll -- the data it guards is only ever read with ld.global.cg, i.e. from L2, the coherence
+// point, and only after the poll has returned, so no L1 invalidation is needed on the acquire side either.
+__device__ __forceinline__ void red_release_add(int* p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 ld_cg_f2(const float2* p) {     // L2-only load: data written by other SMs in this launch
+    float2 v;
+    asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// x * sigmoid(x) = h + h * tanh(h), h = x / 2: one MUFU op (tanh.approx, rel. error ~2^-11, below the bf16 output rounding)
+__device__ __forceinline__ float silu_tanh(float v) {
+    const float h = 0.5f * v;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+
+// Warp-wide sums of 8 per-lane values with 9 shuffles: afterwards lane L holds the total of value (L >> 2).
+__device__ __forceinline__ float transpose_reduce8(float (&v)[8], int lane) {
+    constexpr unsigned FULL = 0xffffffffu;
+    {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float keep = up ? v[i + 4] : v[i];
+            const float send = up ? v[i] : v[i + 4];
+            v[i] = keep + __shfl_xor_sync(FULL, send, 16);
+        }
+    }
+    {
+        const bool up = (lane & 8) != 0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float keep = up ? v[i + 2] : v[i];
+            const float send = up ? v[i] : v[i + 2];
+            v[i] = keep + __shfl_xor_sync(FULL, send, 8);
+        }
+    }
+    {
+        const bool up = (lane & 4) != 0;
+        const float keep = up ? v[1] : v[0];
+        const float send = up ? v[0] : v[1];
+        v[0] = keep + __shfl_xor_sync(FULL, send, 4);
+    }
+    v[0] += __shfl_xor_sync(FULL, v[0], 2);
+    v[0] += __shfl_xor_sync(FULL, v[0], 1);
+    return v[0];
+}
+
+template <int BN, int KIND, bool GNF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD, const KArgs a) {
-    using C = Cfg<BN, KIND>;
+    using C = Cfg<BN, KIND, GNF>;
     constexpr uint32_t B_BLOCK = C::B_BLOCK_BYTES;
+    constexpr int ACC = C::ACC_STAGES;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
@@ -154,9 +220,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpi + C::EPI_BYTES);
     uint64_t* empty_bar = full_bar + MAX_STAGES;
     uint64_t* tfull_bar = empty_bar + MAX_STAGES;
-    uint64_t* tempty_bar = tfull_bar + 2;
-    uint64_t* res_bar = tempty_bar + 2;
+    uint64_t* tempty_bar = tfull_bar + 4;
+    uint64_t* res_bar = tempty_bar + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
+    float* s_gn = reinterpret_cast<float*>(sEpi + C::EPI_BYTES + BAR_BYTES);   // GNF: [2][16] (mean[8], rstd[8])
+    float* s_ma = s_gn + 32;                                                   // GNF: [2][3 * BN] (mul, add, post)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -176,9 +244,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             ptx::mbar_init(&full_bar[i], 1);
             ptx::mbar_init(&empty_bar[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < ACC; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 128);
+            ptx::mbar_init(&tempty_bar[i], 256);
         }
         ptx::mbar_init(res_bar, 1);
         ptx::fence_mbar_init();
@@ -272,8 +340,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         uint32_t phase = 0;
         int iter = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++iter) {
-            const int as = iter & 1;
-            const uint32_t aphase = (iter >> 1) & 1u;
+            const int as = iter % ACC;
+            const uint32_t aphase = (iter / ACC) & 1u;
             ptx::mbar_wait(&tempty_bar[as], aphase ^ 1u);
             ptx::tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * BN;
@@ -324,177 +392,356 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (4 warps)
-        // Each warp owns 32 accumulator rows (its TMEM lane quarter).  bf16 output goes through a per-warp, 128B-swizzled
-        // staging buffer and leaves as TMA tensor stores of 32 x 64 boxes (full-line writes, rows past M are clipped
-        // by the TMA unit); the fp32 head path (N padded to 16, one valid column) stores directly.
-        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        // ------------------------------------------------------------------ epilogue (8 warps)
+        // Warp (q, hc): TMEM lane quarter q = warp % 4 (32 accumulator rows), column half hc of every 64-column chunk.
+        // Two warps per scheduler keep the long dependent chains of the epilogue overlapped (with 4 warps ncu showed the
+        // kernel epilogue-bound: one warp per scheduler issues ~1 instruction per 4-5 cycles).  bf16 output goes through a
+        // per-warp, 64B-swizzled staging buffer and leaves as TMA tensor stores of 32 rows x 32 columns (rows past M
+        // are clipped by the TMA unit); the fp32 head path (N padded to 16, one valid column) stores directly.
+        const int q = warp & 3;
+        const int hc = (warp - 2) >> 2;
         const int r = q * 32 + lane;            // accumulator row == pixel within the tile
         const ConvEpilogue& e = a.epi;
-        uint8_t* my_stage = sEpi + q * (C::EPI_BUFS * EPI_BUF_BYTES);
+        uint8_t* my_stage = sEpi + (hc * 4 + q) * (C::EPI_BUFS * EPI_BUF_BYTES);
+        const int swz = (lane >> 1) & 3;        // 64B swizzle: 16-byte chunk j of row `lane` lives at chunk j ^ swz
         int buf = 0;
-        int iter = 0;
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++iter) {
-            const TileCoord tc = decode_tile(a, tile);
-            const int mt = tc.mt;
-            const int m = mt * BLOCK_M + r;
-            const int n0 = tc.nt * BN;
-            const bool valid = m < a.M;
-            const int as = iter & 1;
-            const uint32_t aphase = (iter >> 1) & 1u;
 
-            const float* frow = nullptr;
-            if (e.film != nullptr) {
-                const int b = valid ? m / a.P : 0;
-                const int row = e.film_row[b * e.film_row_stride];
-                frow = e.film + static_cast<size_t>(row) * e.film_ld + e.film_off;
+        // pack 32 fp32 -> bf16, stage, TMA-store as the 32 x 32 box at (column ncol, row block of this warp)
+        auto stage_and_store = [&](const float (&f)[32], int ncol, const TileCoord& tc) {
+            if (lane == 0) {
+                if constexpr (C::EPI_BUFS == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
             }
-            const int shift_off = e.film_has_scale ? a.N : 0;
-
-            ptx::mbar_wait(&tfull_bar[as], aphase);
-            ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-
-            auto finish = [&](float (&f)[32], int n) {      // bias / FiLM / SiLU / scale / residual on 32 columns
-                if (e.bias != nullptr) {
+            __syncwarp();
+            uint8_t* stage_row = my_stage + buf * EPI_BUF_BYTES + lane * 64;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + n + j));
-                        f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
-                    }
+            for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                o.x = ptx::pack_bf16x2(f[8 * j], f[8 * j + 1]);
+                o.y = ptx::pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                o.z = ptx::pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+                o.w = ptx::pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                *reinterpret_cast<uint4*>(stage_row + ((j ^ swz) << 4)) = o;
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                const int mrow = tc.mt * BLOCK_M + q * 32;
+                if (a.mode == CONV_UPSAMPLE) {
+                    // low-res pixel block -> output phase (pa, pb) through the [N, 2, W/2, 2, B*H/2] view
+                    const int rowl = mrow / a.Wl_box;              // merged (b, low-res row)
+                    const int wl = a.rows_box > 1 ? 0 : mrow - rowl * a.Wl_box;
+                    ptx::tma_store_5d(&tmD, my_stage + buf * EPI_BUF_BYTES, ncol, tc.phase & 1, wl, tc.phase >> 1, rowl);
+                } else {
+                    ptx::tma_store_2d(&tmD, my_stage + buf * EPI_BUF_BYTES, ncol, mrow);
                 }
-                if (frow != nullptr) {
-                    if (e.film_has_scale) {
+                ptx::bulk_commit();
+            }
+            if constexpr (C::EPI_BUFS == 2) buf ^= 1;
+        };
+        // (sum, M2) of the four 8-channel pieces of this warp's 32 columns over its 32 rows -> gn_part
+        auto write_partials = [&](const float (&f)[32], int ncol, int mt) {
+            float sq[8];
+#pragma unroll
+            for (int p8 = 0; p8 < 4; ++p8) {
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    s1 += f[8 * p8 + j];
+                    s2 = fmaf(f[8 * p8 + j], f[8 * p8 + j], s2);
+                }
+                sq[2 * p8] = s1;
+                sq[2 * p8 + 1] = s2;
+            }
+            const float mine = transpose_reduce8(sq, lane);                   // lane L: value (L >> 2)
+            const float other = __shfl_down_sync(0xffffffffu, mine, 4);
+            if ((lane & 7) == 0) {                                            // lane 8p: sum and sum of squares of piece p
+                const float m2 = fmaxf(other - mine * mine * (1.0f / 256.0f), 0.f);
+                e.gn_part[(static_cast<size_t>(mt) * 4 + q) * (a.N >> 3) + (ncol >> 3) + (lane >> 3)] = make_float2(mine, m2);
+            }
+        };
+
+        if constexpr (GNF) {
+            // ---- GroupNorm-fused epilogue (slab kinds, P >= 128, N <= 128): the conv's output leaves the SM already
+            // normalised.  Phase A of tile i (as soon as its accumulator is complete): per-piece (sum, M2) partials from
+            // the fp32 accumulators + bias -> global, then one release-increment of the image's arrival counter per warp.
+            // Phase B trails by one tile: wait until every warp block of the image has arrived (all CTAs of this persistent
+            // grid are co-resident and run phase A before any wait on it, so the wait cannot deadlock), merge the image's
+            // partials in a fixed order (Chan), fold bias / gamma / beta / FiLM into one multiply-add per column, re-read
+            // the accumulator from TMEM, SiLU, (+ SR3 post-add) (+ residual), TMA store.
+            const int te = ((warp - 2) << 5) + lane;        // 0..255
+            const int cpg = a.N >> 3;                       // channels per group
+            const int ppg = a.N >> 6;                       // 8-channel pieces per group
+            const int ppr = a.N >> 3;                       // pieces per partial row
+            const int nwb = a.P >> 5;                       // warp blocks per image
+            const int target = nwb * a.num_n_tiles * 2;     // two half-width warps per (warp block, N tile)
+            const float inv_total = 1.0f / (static_cast<float>(a.P) * static_cast<float>(cpg));
+            int prev_tile = -1, prev_iter = 0;
+            for (int iter = 0;; ++iter) {
+                const int tile = blockIdx.x + iter * gridDim.x;
+                const bool have = tile < a.num_tiles;
+                if (have) {
+                    // ------------------------------------------------ phase A: statistics of tile `iter`
+                    const TileCoord tc = decode_tile(a, tile);
+                    const int n0 = tc.nt * BN;
+                    const int as = iter % ACC;
+                    ptx::mbar_wait(&tfull_bar[as], (iter / ACC) & 1u);
+                    ptx::tc_fence_after();
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + hc * 32;
+#pragma unroll 1
+                    for (int c = 0; c < BN; c += 64) {
+                        uint32_t v[32];
+                        ptx::tmem_ld32(taddr + c, v);
+                        ptx::tmem_ld_wait();
+                        const int ncol = n0 + c + hc * 32;
+                        float f[32];
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 sc = __ldg(reinterpret_cast<const float4*>(frow + n + j));
-                            f[j] *= (sc.x + 1.0f); f[j + 1] *= (sc.y + 1.0f);
-                            f[j + 2] *= (sc.z + 1.0f); f[j + 3] *= (sc.w + 1.0f);
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + ncol + j));
+                            f[j] = __uint_as_float(v[j]) + bb.x; f[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
+                            f[j + 2] = __uint_as_float(v[j + 2]) + bb.z; f[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
                         }
+                        write_partials(f, ncol, tc.mt);
                     }
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 sh = __ldg(reinterpret_cast<const float4*>(frow + shift_off + n + j));
-                        f[j] += sh.x; f[j + 1] += sh.y; f[j + 2] += sh.z; f[j + 3] += sh.w;
-                    }
+                    __syncwarp();
+                    if (lane == 0) red_release_add(e.gn_counter + (tc.mt * BLOCK_M + q * 32) / a.P, 1);
                 }
-                if (e.silu) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
-                }
-                if (e.out_scale != 1.0f) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] *= e.out_scale;
-                }
-                if (e.res != nullptr && valid) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(e.res + static_cast<size_t>(m) * e.ldr + n);
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        const uint4 rr = __ldg(rp + j / 8);
-                        float2 t;
-                        t = ptx::unpack_bf16x2(rr.x); f[j] += t.x; f[j + 1] += t.y;
-                        t = ptx::unpack_bf16x2(rr.y); f[j + 2] += t.x; f[j + 3] += t.y;
-                        t = ptx::unpack_bf16x2(rr.z); f[j + 4] += t.x; f[j + 5] += t.y;
-                        t = ptx::unpack_bf16x2(rr.w); f[j + 6] += t.x; f[j + 7] += t.y;
-                    }
-                }
-            };
-
-            if constexpr (BN < 64) {
-                // fp32 head (tail conv of HiCEDRN): 16 accumulator columns, n_valid of them real
-                uint32_t v[16];
-                ptx::tmem_ld16(taddr, v);
-                ptx::tmem_ld_wait();
-                ptx::tc_fence_before();
-                ptx::mbar_arrive(&tempty_bar[as]);
-                if (valid && e.out_f32 != nullptr) {
-                    for (int j = 0; j < 16; ++j)
-                        if (n0 + j < e.n_valid) {
-                            float val = __uint_as_float(v[j]) + (e.bias != nullptr ? __ldg(e.bias + n0 + j) : 0.f);
-                            if (e.res != nullptr) val += __bfloat162float(e.res[static_cast<size_t>(m) * e.ldr + n0 + j]);
-                            e.out_f32[static_cast<size_t>(m) * e.n_valid + n0 + j] = val;
-                        }
-                }
-            } else {
-#pragma unroll 1
-                for (int c = 0; c < BN; c += 64) {
-                    uint32_t v0[32], v1[32];
-                    ptx::tmem_ld32(taddr + c, v0);
-                    ptx::tmem_ld32(taddr + c + 32, v1);
-                    ptx::tmem_ld_wait();
-                    if (c + 64 == BN) {          // accumulator fully drained: hand the TMEM stage back to the MMA warp
-                        ptx::tc_fence_before();
-                        ptx::mbar_arrive(&tempty_bar[as]);
-                    }
-                    float f0[32], f1[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) { f0[j] = __uint_as_float(v0[j]); f1[j] = __uint_as_float(v1[j]); }
-                    finish(f0, n0 + c);
-                    finish(f1, n0 + c + 32);
-                    if (e.gn_part != nullptr) {
-                        // GroupNorm partials of this warp's 32 rows: (sum, M2) of every 8-channel piece of the 64 columns
-                        // (rows are all valid: M % 32 == 0).  Per-row sums / sums of squares, one 16-value transpose-reduce.
-                        float sq[16];
-#pragma unroll
-                        for (int p8 = 0; p8 < 8; ++p8) {
-                            float s = 0.f, ss = 0.f;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float x = (p8 < 4) ? f0[8 * p8 + j] : f1[8 * (p8 - 4) + j];
-                                s += x;
-                                ss = fmaf(x, x, ss);
+                if (prev_tile >= 0) {
+                    // ------------------------------------------------ phase B: normalise + store tile `prev_iter`
+                    const TileCoord tc = decode_tile(a, prev_tile);
+                    const int mt = tc.mt;
+                    const int n0 = tc.nt * BN;
+                    const int m = mt * BLOCK_M + r;
+                    const int b = (mt * BLOCK_M) / a.P;                 // P >= 128: the whole tile lies in one image
+                    const int as = prev_iter % ACC;
+                    const int gb = prev_iter & 1;
+                    // column constants do not depend on the statistics: issue their loads first so the latency hides
+                    // behind the arrival wait below
+                    float cgam = 0.f, cbet = 0.f, cbias = 0.f, csc = 1.0f, csh = 0.f, cpost = 0.f;
+                    if (te < BN) {
+                        const int c = n0 + te;
+                        cgam = __ldg(e.gn_gamma + c);
+                        cbet = __ldg(e.gn_beta + c);
+                        cbias = __ldg(e.bias + c);
+                        if (e.film != nullptr) {
+                            const int row = e.film_row[b * e.film_row_stride];
+                            const float* frow = e.film + static_cast<size_t>(row) * e.film_ld + e.film_off;
+                            if (e.film_has_scale) {
+                                csc = __ldg(frow + c) + 1.0f;
+                                csh = __ldg(frow + a.N + c);
+                            } else {
+                                cpost = __ldg(frow + c);                       // SR3: additive noise embedding after the activation
                             }
-                            sq[2 * p8] = s;
-                            sq[2 * p8 + 1] = ss;
-                        }
-                        const float mine = transpose_reduce16(sq, lane);           // lane L: value (L >> 1)
-                        const float other = __shfl_down_sync(0xffffffffu, mine, 2);
-                        if ((lane & 3) == 0) {                                      // lane 4p: sum and sum of squares of piece p
-                            const float m2 = fmaxf(other - mine * mine * (1.0f / 256.0f), 0.f);
-                            e.gn_part[(static_cast<size_t>(mt) * 4 + q) * (a.N >> 3) + ((n0 + c) >> 3) + (lane >> 2)] =
-                                make_float2(mine, m2);
                         }
                     }
-                    // staging buffer free?  (with two buffers one older store of this warp may still be reading the OTHER one)
                     if (lane == 0) {
-                        if constexpr (C::EPI_BUFS == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
+                        const int* cnt = e.gn_counter + b;
+                        unsigned long long t0 = 0;
+                        unsigned spins = 0;
+                        while (ld_relaxed_gpu(cnt) < target) {
+                            if ((++spins & 0xffu) == 0) {
+                                unsigned long long t1;
+                                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                                if (t0 == 0) t0 = t1;
+                                if (t1 - t0 > 2000000000ull) __trap();   // a protocol bug must surface as an error, not a hang
+                            }
+                        }
                     }
                     __syncwarp();
-                    uint8_t* stage_row = my_stage + buf * EPI_BUF_BYTES + lane * 128;
-                    const int sw = lane & 7;
+                    // epilogue warp w merges group w of image b: all its partials in ONE batch of loads (<= 8 per lane),
+                    // then fixed-order shuffle reductions -> bit-identical statistics in every CTA
+                    {
+                        constexpr int MAXE = 8;                              // nent <= 256 (conv_gemm_can_fuse_gn)
+                        const int g = warp - 2;
+                        const int nent = nwb * ppg;
+                        const float2* pp = e.gn_part + (static_cast<size_t>(b) * nwb) * ppr + g * ppg;
+                        float2 ent[MAXE];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 o;
-                        o.x = ptx::pack_bf16x2(f0[8 * j], f0[8 * j + 1]);
-                        o.y = ptx::pack_bf16x2(f0[8 * j + 2], f0[8 * j + 3]);
-                        o.z = ptx::pack_bf16x2(f0[8 * j + 4], f0[8 * j + 5]);
-                        o.w = ptx::pack_bf16x2(f0[8 * j + 6], f0[8 * j + 7]);
-                        *reinterpret_cast<uint4*>(stage_row + ((j ^ sw) << 4)) = o;
-                        uint4 p;
-                        p.x = ptx::pack_bf16x2(f1[8 * j], f1[8 * j + 1]);
-                        p.y = ptx::pack_bf16x2(f1[8 * j + 2], f1[8 * j + 3]);
-                        p.z = ptx::pack_bf16x2(f1[8 * j + 4], f1[8 * j + 5]);
-                        p.w = ptx::pack_bf16x2(f1[8 * j + 6], f1[8 * j + 7]);
-                        *reinterpret_cast<uint4*>(stage_row + (((j + 4) ^ sw) << 4)) = p;
-                    }
-                    ptx::fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        const int mrow = mt * BLOCK_M + q * 32;
-                        if (a.mode == CONV_UPSAMPLE) {
-                            // low-res pixel block -> output phase (pa, pb) through the [N, 2, W/2, 2, B*H/2] view
-                            const int rowl = mrow / a.Wl_box;              // merged (b, low-res row)
-                            const int wl = a.rows_box > 1 ? 0 : mrow - rowl * a.Wl_box;
-                            ptx::tma_store_5d(&tmD, my_stage + buf * EPI_BUF_BYTES, n0 + c, tc.phase & 1, wl, tc.phase >> 1, rowl);
-                        } else {
-                            ptx::tma_store_2d(&tmD, my_stage + buf * EPI_BUF_BYTES, n0 + c, mrow);
+                        for (int i = 0; i < MAXE; ++i) {
+                            const int idx = lane + 32 * i;
+                            const int blk = idx / ppg;
+                            ent[i] = idx < nent ? ld_cg_f2(pp + static_cast<size_t>(blk) * ppr + (idx - blk * ppg)) : make_float2(0.f, 0.f);
                         }
-                        ptx::bulk_commit();
+                        float s1 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < MAXE; ++i) s1 += ent[i].x;
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+                        const float mean = s1 * inv_total;
+                        float m2 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < MAXE; ++i) {
+                            if (lane + 32 * i < nent) {
+                                const float dm = ent[i].x * (1.0f / 256.0f) - mean;
+                                m2 += ent[i].y + 256.0f * dm * dm;
+                            }
+                        }
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, off);
+                        if (lane == 0) {
+                            s_gn[gb * 16 + g] = mean;
+                            s_gn[gb * 16 + 8 + g] = rsqrtf(m2 * inv_total + e.gn_eps);
+                        }
                     }
-                    if constexpr (C::EPI_BUFS == 2) buf ^= 1;
+                    named_bar_sync(2, 256);
+                    if (te < BN) {
+                        const int g = (n0 + te) / cpg;
+                        float mul = cgam * s_gn[gb * 16 + 8 + g];
+                        float add = cbet - s_gn[gb * 16 + g] * mul;
+                        add = fmaf(cbias, mul, add);                         // (acc + bias) * mul + add
+                        if (e.film != nullptr && e.film_has_scale) {
+                            mul *= csc;
+                            add = fmaf(add, csc, csh);
+                        }
+                        s_ma[gb * 3 * BN + te] = mul;
+                        s_ma[gb * 3 * BN + BN + te] = add;
+                        s_ma[gb * 3 * BN + 2 * BN + te] = cpost;
+                    }
+                    named_bar_sync(2, 256);
+                    const float* smul = s_ma + gb * 3 * BN + hc * 32;
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + hc * 32;
+#pragma unroll 1
+                    for (int c = 0; c < BN; c += 64) {
+                        uint32_t v[32];
+                        ptx::tmem_ld32(taddr + c, v);
+                        ptx::tmem_ld_wait();
+                        if (c + 64 == BN) {          // accumulator fully drained: hand the TMEM stage back to the MMA warp
+                            ptx::tc_fence_before();
+                            ptx::mbar_arrive(&tempty_bar[as]);
+                        }
+                        float f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 m0 = *reinterpret_cast<const float4*>(smul + c + j);
+                            const float4 a0 = *reinterpret_cast<const float4*>(smul + BN + c + j);
+                            const float4 p0 = *reinterpret_cast<const float4*>(smul + 2 * BN + c + j);
+                            f[j] = silu_tanh(fmaf(__uint_as_float(v[j]), m0.x, a0.x)) + p0.x;
+                            f[j + 1] = silu_tanh(fmaf(__uint_as_float(v[j + 1]), m0.y, a0.y)) + p0.y;
+                            f[j + 2] = silu_tanh(fmaf(__uint_as_float(v[j + 2]), m0.z, a0.z)) + p0.z;
+                            f[j + 3] = silu_tanh(fmaf(__uint_as_float(v[j + 3]), m0.w, a0.w)) + p0.w;
+                        }
+                        const int ncol = n0 + c + hc * 32;
+                        if (e.res != nullptr) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(e.res + static_cast<size_t>(m) * e.ldr + ncol);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                const uint4 ra = __ldg(rp + j / 8);
+                                float2 t;
+                                t = ptx::unpack_bf16x2(ra.x); f[j] += t.x; f[j + 1] += t.y;
+                                t = ptx::unpack_bf16x2(ra.y); f[j + 2] += t.x; f[j + 3] += t.y;
+                                t = ptx::unpack_bf16x2(ra.z); f[j + 4] += t.x; f[j + 5] += t.y;
+                                t = ptx::unpack_bf16x2(ra.w); f[j + 6] += t.x; f[j + 7] += t.y;
+                            }
+                        }
+                        stage_and_store(f, ncol, tc);
+                    }
+                }
+                if (!have) break;
+                prev_tile = tile;
+                prev_iter = iter;
+            }
+        } else {
+            int iter = 0;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++iter) {
+                const TileCoord tc = decode_tile(a, tile);
+                const int mt = tc.mt;
+                const int m = mt * BLOCK_M + r;
+                const int n0 = tc.nt * BN;
+                const bool valid = m < a.M;
+                const int as = iter % ACC;
+                const uint32_t aphase = (iter / ACC) & 1u;
+
+                const float* frow = nullptr;
+                if (e.film != nullptr) {
+                    const int b = valid ? m / a.P : 0;
+                    const int row = e.film_row[b * e.film_row_stride];
+                    frow = e.film + static_cast<size_t>(row) * e.film_ld + e.film_off;
+                }
+                const int shift_off = e.film_has_scale ? a.N : 0;
+
+                ptx::mbar_wait(&tfull_bar[as], aphase);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+
+                if constexpr (BN < 64) {
+                    // fp32 head (tail conv of HiCEDRN): 16 accumulator columns, n_valid of them real; column half 0 does the work
+                    uint32_t v[16];
+                    if (hc == 0) {
+                        ptx::tmem_ld16(taddr, v);
+                        ptx::tmem_ld_wait();
+                    }
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(&tempty_bar[as]);
+                    if (hc == 0 && valid && e.out_f32 != nullptr) {
+                        for (int j = 0; j < 16; ++j)
+                            if (n0 + j < e.n_valid) {
+                                float val = __uint_as_float(v[j]) + (e.bias != nullptr ? __ldg(e.bias + n0 + j) : 0.f);
+                                if (e.res != nullptr) val += __bfloat162float(e.res[static_cast<size_t>(m) * e.ldr + n0 + j]);
+                                e.out_f32[static_cast<size_t>(m) * e.n_valid + n0 + j] = val;
+                            }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int c = 0; c < BN; c += 64) {
+                        const int ncol = n0 + c + hc * 32;
+                        uint32_t v[32];
+                        ptx::tmem_ld32(taddr + c + hc * 32, v);
+                        ptx::tmem_ld_wait();
+                        if (c + 64 == BN) {          // accumulator fully drained: hand the TMEM stage back to the MMA warp
+                            ptx::tc_fence_before();
+                            ptx::mbar_arrive(&tempty_bar[as]);
+                        }
+                        float f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                        // bias / FiLM / SiLU / scale / residual on this warp's 32 columns
+                        if (e.bias != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + ncol + j));
+                                f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
+                            }
+                        }
+                        if (frow != nullptr) {
+                            if (e.film_has_scale) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4) {
+                                    const float4 sc = __ldg(reinterpret_cast<const float4*>(frow + ncol + j));
+                                    f[j] *= (sc.x + 1.0f); f[j + 1] *= (sc.y + 1.0f);
+                                    f[j + 2] *= (sc.z + 1.0f); f[j + 3] *= (sc.w + 1.0f);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 sh = __ldg(reinterpret_cast<const float4*>(frow + shift_off + ncol + j));
+                                f[j] += sh.x; f[j + 1] += sh.y; f[j + 2] += sh.z; f[j + 3] += sh.w;
+                            }
+                        }
+                        if (e.silu) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+                        }
+                        if (e.out_scale != 1.0f) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] *= e.out_scale;
+                        }
+                        if (e.res != nullptr && valid) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(e.res + static_cast<size_t>(m) * e.ldr + ncol);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                const uint4 rr = __ldg(rp + j / 8);
+                                float2 t;
+                                t = ptx::unpack_bf16x2(rr.x); f[j] += t.x; f[j + 1] += t.y;
+                                t = ptx::unpack_bf16x2(rr.y); f[j + 2] += t.x; f[j + 3] += t.y;
+                                t = ptx::unpack_bf16x2(rr.z); f[j + 4] += t.x; f[j + 5] += t.y;
+                                t = ptx::unpack_bf16x2(rr.w); f[j + 6] += t.x; f[j + 7] += t.y;
+                            }
+                        }
+                        if (e.gn_part != nullptr) write_partials(f, ncol, mt);   // rows are all valid: M % 32 == 0
+                        stage_and_store(f, ncol, tc);
+                    }
                 }
             }
-        }
+        }   // !GNF
         if (lane == 0) ptx::bulk_wait_all();    // all tensor stores of this warp have landed before the CTA retires
         __syncwarp();
     }
@@ -524,7 +771,7 @@ EncodeTiledFn get_encode_fn() {
 }  // namespace
 
 int encode_tmap_bf16(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                     const cuuint32_t* box, char* err, int errlen) {
+                     const cuuint32_t* box, char* err, int errlen, int swizzle_bytes) {
     EncodeTiledFn fn = get_encode_fn();
     if (fn == nullptr) {
         snprintf(err, errlen, "cuTensorMapEncodeTiled entry point not available");
@@ -532,7 +779,8 @@ int encode_tmap_bf16(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_
     }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         snprintf(err, errlen, "cuTensorMapEncodeTiled failed (CUresult %d, rank %d, dims %llu/%llu/%llu)", (int)r, rank,
@@ -545,8 +793,8 @@ int encode_tmap_bf16(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_
 namespace {
 
 inline int encode_map(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                      const cuuint32_t* box, char* err, int errlen) {
-    return encode_tmap_bf16(tm, ptr, rank, dims, strides_bytes, box, err, errlen);
+                      const cuuint32_t* box, char* err, int errlen, int swizzle_bytes = 128) {
+    return encode_tmap_bf16(tm, ptr, rank, dims, strides_bytes, box, err, errlen, swizzle_bytes);
 }
 
 // Hs x Ws: spatial size of the SOURCE tensor the taps walk over (== output size except for CONV_UPSAMPLE: low-res).
@@ -570,11 +818,11 @@ int encode_activation_map(CUtensorMap* tm, const ConvSrc& s, const ConvGemmDesc&
     return encode_map(tm, s.ptr, 5, dims, str, box, err, errlen);
 }
 
-template <int BN, int KIND>
+template <int BN, int KIND, bool GNF = false>
 cudaError_t launch_cfg(const ConvGemmLaunch& l, cudaStream_t s) {
     static int attr_bytes = 0;
     if (l.smem_bytes > attr_bytes) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, KIND, GNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              l.smem_bytes);
         if (e != cudaSuccess) return e;
         attr_bytes = l.smem_bytes;
@@ -585,23 +833,32 @@ cudaError_t launch_cfg(const ConvGemmLaunch& l, cudaStream_t s) {
     k.kh = l.kh; k.kw = l.kw; k.pad = l.pad; k.stages = l.stages; k.Wl_box = l.Wl_box; k.rows_box = l.rows_box;
     k.slab_bytes = l.slab_bytes; k.slab_dy_bytes = l.slab_dy_bytes; k.res_b_bytes = l.res_b_bytes;
     k.epi = l.epi;
-    conv_gemm_kernel<BN, KIND><<<l.grid, NUM_THREADS, l.smem_bytes, s>>>(l.tmA0, l.tmA1, l.tmB, l.tmD, k);
+    conv_gemm_kernel<BN, KIND, GNF><<<l.grid, NUM_THREADS, l.smem_bytes, s>>>(l.tmA0, l.tmA1, l.tmB, l.tmD, k);
     return cudaGetLastError();
+}
+
+template <int BN, int KIND, bool GNF>
+void size_one(ConvGemmLaunch* l) {
+    l->stages = Cfg<BN, KIND, GNF>::stages(l->res_b_bytes);
+    l->smem_bytes = Cfg<BN, KIND, GNF>::smem_bytes(l->stages, l->res_b_bytes);
 }
 
 template <int BN>
 void size_cfg(ConvGemmLaunch* l) {
     switch (l->kind) {
-        case K_SLAB: l->stages = Cfg<BN, K_SLAB>::stages(0); l->smem_bytes = Cfg<BN, K_SLAB>::smem_bytes(l->stages, 0); break;
-        case K_SLAB_RES:
-            l->stages = Cfg<BN, K_SLAB_RES>::stages(l->res_b_bytes);
-            l->smem_bytes = Cfg<BN, K_SLAB_RES>::smem_bytes(l->stages, l->res_b_bytes);
-            break;
-        default: l->stages = Cfg<BN, K_GENERAL>::stages(0); l->smem_bytes = Cfg<BN, K_GENERAL>::smem_bytes(l->stages, 0); break;
+        case K_SLAB: if (l->gnf) size_one<BN, K_SLAB, true>(l); else size_one<BN, K_SLAB, false>(l); break;
+        case K_SLAB_RES: if (l->gnf) size_one<BN, K_SLAB_RES, true>(l); else size_one<BN, K_SLAB_RES, false>(l); break;
+        default: size_one<BN, K_GENERAL, false>(l); break;
     }
 }
 
 }  // namespace
+
+bool conv_gemm_can_fuse_gn(int B, int H, int W, int N, int ksize, ConvMode mode) {
+    const int P = H * W;
+    return B > 0 && mode == CONV_TAPS && ksize == 3 && P >= BLOCK_M && P % BLOCK_M == 0 && W >= 16 && BLOCK_M % W == 0 &&
+           (N == 64 || N == 128) && (P / 32) * (N / 64) <= 256;   // <= 256 partials per (image, group): one batch per lane
+}
 
 int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, char* err, int errlen) {
     memset(out, 0, sizeof(*out));
@@ -684,6 +941,12 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
         snprintf(err, errlen, "conv_gemm: the upsample conv supports the bias epilogue only");
         return 1;
     }
+    out->gnf = d.epi.gn_gamma != nullptr ? 1 : 0;
+    if (out->gnf && (out->kind == K_GENERAL || !conv_gemm_can_fuse_gn(d.B, d.H, d.W, d.N, d.ksize, d.mode) || d.epi.gn_part == nullptr ||
+                     d.epi.gn_counter == nullptr || d.epi.gn_beta == nullptr || d.epi.bias == nullptr)) {
+        snprintf(err, errlen, "conv_gemm: this conv cannot run the GroupNorm-fused epilogue");
+        return 1;
+    }
     if (d.epi.gn_part != nullptr && (M % 32 != 0 || bn < 64)) {
         snprintf(err, errlen, "conv_gemm: GroupNorm partials need M %% 32 == 0 and a bf16 output tile");
         return 1;
@@ -712,13 +975,13 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
             out->rows_box = Ws >= 32 ? 1 : 32 / Ws;
             cuuint64_t od[5] = {(cuuint64_t)d.N, 2, (cuuint64_t)Ws, 2, (cuuint64_t)d.B * Hs};
             cuuint64_t os[4] = {N2, 2 * N2, (cuuint64_t)d.W * N2, 2 * (cuuint64_t)d.W * N2};
-            cuuint32_t ob[5] = {64, 1, (cuuint32_t)(Ws >= 32 ? 32 : Ws), 1, (cuuint32_t)out->rows_box};
-            if (encode_map(&out->tmD, d.out, 5, od, os, ob, err, errlen)) return 1;
+            cuuint32_t ob[5] = {32, 1, (cuuint32_t)(Ws >= 32 ? 32 : Ws), 1, (cuuint32_t)out->rows_box};
+            if (encode_map(&out->tmD, d.out, 5, od, os, ob, err, errlen, 64)) return 1;
         } else {
             cuuint64_t od[2] = {(cuuint64_t)d.N, (cuuint64_t)M};
             cuuint64_t os[1] = {(cuuint64_t)d.N * 2};
-            cuuint32_t ob[2] = {64, 32};
-            if (encode_map(&out->tmD, d.out, 2, od, os, ob, err, errlen)) return 1;
+            cuuint32_t ob[2] = {32, 32};     // one epilogue warp: 32 rows x 32 columns, 64-byte rows, 64B swizzle
+            if (encode_map(&out->tmD, d.out, 2, od, os, ob, err, errlen, 64)) return 1;
         }
     } else {
         if (bn >= 64 || up) {
@@ -744,7 +1007,7 @@ cudaError_t conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t s) {
     switch (l.kind) {
         case K_GENERAL:
             switch (l.bn) {
-                case 256: return launch_cfg<256, K_GENERAL>(l, s);
+                case 256: return l.gnf ? cudaErrorInvalidValue : launch_cfg<256, K_GENERAL>(l, s);
                 case 128: return launch_cfg<128, K_GENERAL>(l, s);
                 case 64: return launch_cfg<64, K_GENERAL>(l, s);
                 case 16: return launch_cfg<16, K_GENERAL>(l, s);
@@ -752,13 +1015,14 @@ cudaError_t conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t s) {
             }
         case K_SLAB:
             switch (l.bn) {
-                case 128: return launch_cfg<128, K_SLAB>(l, s);
-                case 64: return launch_cfg<64, K_SLAB>(l, s);
-                case 16: return launch_cfg<16, K_SLAB>(l, s);
+                case 128: return l.gnf ? launch_cfg<128, K_SLAB, true>(l, s) : launch_cfg<128, K_SLAB>(l, s);
+                case 64: return l.gnf ? launch_cfg<64, K_SLAB, true>(l, s) : launch_cfg<64, K_SLAB>(l, s);
+                case 16: return l.gnf ? cudaErrorInvalidValue : launch_cfg<16, K_SLAB>(l, s);
                 default: return cudaErrorInvalidValue;
             }
         case K_SLAB_RES:
-            return l.bn == 64 ? launch_cfg<64, K_SLAB_RES>(l, s) : cudaErrorInvalidValue;
+            if (l.bn != 64) return cudaErrorInvalidValue;
+            return l.gnf ? launch_cfg<64, K_SLAB_RES, true>(l, s) : launch_cfg<64, K_SLAB_RES>(l, s);
         default: return cudaErrorInvalidValue;
     }
 }

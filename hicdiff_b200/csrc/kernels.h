@@ -47,6 +47,13 @@ struct ConvEpilogue {
     // (32-row warp block, 8-channel piece), M2 = sum of squared deviations from the piece-block's own mean (merged
     // stably, in a fixed order, by groupnorm_apply_kernel).
     float2* gn_part = nullptr;        // [M / 32][N / 8]
+    // Fused GroupNorm(8) apply (conv_gemm_can_fuse_gn): when gn_gamma is set the epilogue itself waits for the image's
+    // statistics and writes silu(GN(acc + bias) * (scale + 1) + shift) [+ post-add] [+ res]; `film` then modulates the
+    // NORMALISED value (film_has_scale = 0: the row is an SR3 additive embedding applied after the activation).
+    const float* gn_gamma = nullptr;  // [N]
+    const float* gn_beta = nullptr;   // [N]
+    float gn_eps = 1e-5f;
+    int* gn_counter = nullptr;        // [B] per-image arrival counters, zero when the kernel starts
 };
 
 struct ConvGemmDesc {
@@ -65,6 +72,7 @@ struct ConvGemmDesc {
 struct ConvGemmLaunch {
     CUtensorMap tmA0, tmA1, tmB, tmD;
     int bn;             // N tile (16, 64, 128 or 256)
+    int gnf;            // 1: GroupNorm-fused epilogue
     int kind;           // 0 general, 1 slab (3x3, one A box per (chunk, dx)), 2 slab + shared-memory resident weights
     int grid;
     int smem_bytes;
@@ -77,13 +85,15 @@ struct ConvGemmLaunch {
     int ldo;
 };
 
+// True when a 3x3 conv of this shape runs on the slab path, whose epilogue can apply the following GroupNorm itself.
+bool conv_gemm_can_fuse_gn(int B, int H, int W, int N, int ksize, ConvMode mode);
 // Returns 0 on success; on failure fills `err` (size errlen).
 int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, char* err, int errlen);
 cudaError_t conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t s);
 
 // bf16 tiled tensor map with 128-byte swizzle (driver entry point resolved at run time; no libcuda link dependency)
 int encode_tmap_bf16(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                     const cuuint32_t* box, char* err, int errlen);
+                     const cuuint32_t* box, char* err, int errlen, int swizzle_bytes = 128);
 
 // ---------------------------------------------------------------------------------------------
 // norm.cu -- GroupNorm(8)+FiLM+SiLU (cluster/DSMEM two-pass), channel LayerNorm

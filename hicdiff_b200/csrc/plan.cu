@@ -137,6 +137,7 @@ struct Exec {
     int* iota = nullptr;     // [B]
     float* ctx = nullptr;    // linear-attention scratch [B,4,32,32]
     float2* gn_part = nullptr;  // GroupNorm partial statistics [B*P/32][C/8], rewritten by every GN-feeding conv
+    int* gn_cnt = nullptr;      // per-image arrival counters of the GroupNorm-fused conv epilogue [B]
     float* la_ctx = nullptr;    // fused linear attention: partial contexts [B*8][128][32]
     float* la_s = nullptr;      //                          partial softmax denominators [B*8][128]
     bf16* la_mb = nullptr;      //                          per-image to_out * ctx matrices [B][128][128]
@@ -299,6 +300,14 @@ struct Builder {
             char e[256];
             if (conv_gemm_prepare(d, P->num_sms, &l, e, sizeof(e))) { bad(std::string(wkey) + ": " + e); return y; }
             Op op{[l](cudaStream_t s) { return conv_gemm_run(l, s); }, wkey};
+            if (epi.gn_gamma != nullptr) {   // the fused GroupNorm epilogue counts warp-block arrivals per image from zero
+                int* cnt = epi.gn_counter;
+                const size_t cbytes = static_cast<size_t>(B) * 4;
+                op.fn = [l, cnt, cbytes](cudaStream_t s) {
+                    cudaError_t e = cudaMemsetAsync(cnt, 0, cbytes, s);
+                    return e != cudaSuccess ? e : conv_gemm_run(l, s);
+                };
+            }
             op.kernel = "conv_gemm";
             const double M = static_cast<double>(B) * Ho * Wo;
             const double K = static_cast<double>(l.nkb) * 64;
@@ -350,16 +359,39 @@ struct Builder {
         return y;
     }
 
+    // Block (hicdiff_condition.py:155-171): conv -> GroupNorm -> [FiLM] -> SiLU [-> + SR3 embedding] [-> + residual].  One
+    // launch when the conv runs on the slab path (its epilogue then applies the norm itself), else conv + streaming GN.
+    Act conv_norm(const std::string& p, const Act& x0, const Act* x1, int Cout, int film_off, int postadd_off, const Act* res) {
+        // Measured on B200 (profiles/r01_notes.md): the fused epilogue's per-tile dependency chain (arrival counter, partial
+        // merge, second TMEM pass) costs more than the streaming GroupNorm pass it removes (7.3 vs 6.4 ms per step), so the
+        // plan keeps conv + groupnorm_apply unless cfg.reserved[0] bit 0 asks for the fused form (kept for the parity tests).
+        if ((P->cfg.reserved[0] & 1) && !P->cfg.debug_keep && conv_gemm_can_fuse_gn(B, x0.H, x0.W, Cout, 3, CONV_TAPS)) {
+            ConvEpilogue e;
+            e.gn_gamma = wf(p + ".norm.weight");
+            e.gn_beta = wf(p + ".norm.bias");
+            e.gn_eps = 1e-5f;
+            e.gn_counter = dry ? nullptr : ex->gn_cnt;
+            if (film_off >= 0 || postadd_off >= 0) {
+                e.film = film.base; e.film_row = film.row; e.film_row_stride = film.row_stride; e.film_ld = P->film_ld;
+                e.film_off = film_off >= 0 ? film_off : postadd_off;
+                e.film_has_scale = film_off >= 0 ? 1 : 0;
+            }
+            if (res) { e.res = res->p; e.ldr = Cout; }
+            return conv(p + ".proj.weight", p + ".proj.bias", x0, x1, Cout, 3, CONV_TAPS, e, 0, true);
+        }
+        Act h = conv(p + ".proj.weight", p + ".proj.bias", x0, x1, Cout, 3, CONV_TAPS, ConvEpilogue(), 0, true);
+        note(p + ".proj", h);
+        groupnorm(h, p + ".norm", film_off, postadd_off, res);
+        return h;
+    }
+
     // ResnetBlock (hicdiff_condition.py:173-197 / hicdiff_sr3.py:235-251)
     Act resblock(const std::string& p, const Act& x0, const Act* x1, int Cout) {
         const int Cin = x0.C + (x1 ? x1->C : 0);
-        Act h = conv(p + ".block1.proj.weight", p + ".block1.proj.bias", x0, x1, Cout, 3, CONV_TAPS, ConvEpilogue(), 0, true);
-        note(p + ".block1.proj", h);
         const int slot = P->film_index.count(p) ? P->film_index[p] : -1;
         if (slot < 0) bad("no time-embedding slot for block " + p);
         const int off = slot >= 0 ? P->film[slot].off : 0;
-        if (P->sr3) groupnorm(h, p + ".block1.norm", -1, off, nullptr);
-        else groupnorm(h, p + ".block1.norm", off, -1, nullptr);
+        Act h = conv_norm(p + ".block1", x0, x1, Cout, P->sr3 ? -1 : off, P->sr3 ? off : -1, nullptr);
         note(p + ".block1", h);
         // res_conv first: block2's conv must be the last writer of the shared partial-statistics buffer before its norm
         Act r;
@@ -370,9 +402,8 @@ struct Builder {
         } else {
             r = x0;
         }
-        Act h2 = conv(p + ".block2.proj.weight", p + ".block2.proj.bias", h, nullptr, Cout, 3, CONV_TAPS, ConvEpilogue(), 0, true);
+        Act h2 = conv_norm(p + ".block2", h, nullptr, Cout, -1, -1, &r);
         free_act(h);
-        groupnorm(h2, p + ".block2.norm", -1, -1, &r);
         if (own_r) free_act(r);
         note(p, h2);
         return h2;
@@ -599,7 +630,7 @@ void free_exec(Exec* ex) {
     if (ex->g_step) cudaGraphExecDestroy(ex->g_step);
     cudaFree(ex->arena); cudaFree(ex->x); cudaFree(ex->cond); cudaFree(ex->eps); cudaFree(ex->time);
     cudaFree(ex->posenc); cudaFree(ex->temb0); cudaFree(ex->temb); cudaFree(ex->film_rows); cudaFree(ex->iota);
-    cudaFree(ex->ctx); cudaFree(ex->gn_part); cudaFree(ex->la_ctx); cudaFree(ex->la_s); cudaFree(ex->la_mb);
+    cudaFree(ex->ctx); cudaFree(ex->gn_part); cudaFree(ex->la_ctx); cudaFree(ex->la_s); cudaFree(ex->la_mb); cudaFree(ex->gn_cnt);
 }
 
 int run_ops(const std::vector<Op>& ops, cudaStream_t s) {
@@ -664,6 +695,7 @@ int get_exec(hd_plan* P, int B, cudaStream_t s, Exec** out) {
     EX_TRY(cudaMalloc(&ex->iota, B * 4));
     EX_TRY(cudaMalloc(&ex->ctx, static_cast<size_t>(B) * 4 * 32 * 32 * 4));
     EX_TRY(cudaMalloc(&ex->gn_part, static_cast<size_t>(B) * (tile / 32) * 64 * sizeof(float2)));   // [M/32][C/8], C <= 512
+    EX_TRY(cudaMalloc(&ex->gn_cnt, static_cast<size_t>(B) * 4));
     if (!P->lattn.empty()) {
         EX_TRY(cudaMalloc(&ex->la_ctx, static_cast<size_t>(B) * LA_MAX_PARTS * 128 * 32 * 4));
         EX_TRY(cudaMalloc(&ex->la_s, static_cast<size_t>(B) * LA_MAX_PARTS * 128 * 4));
@@ -1103,6 +1135,59 @@ int hd_op_conv2d(const uint16_t* x0, int32_t C0, const uint16_t* x1, int32_t C1,
     cudaFree(q);
     if (e != cudaSuccess) return fail("conv launch failed: %s", cudaGetErrorString(e));
     if (e2 != cudaSuccess) return fail("conv kernel failed: %s", cudaGetErrorString(e2));
+    return 0;
+}
+
+int hd_op_conv_gn(const uint16_t* x0, int32_t C0, const uint16_t* x1, int32_t C1, const float* w, const float* bias,
+                  const float* gamma, const float* beta, const float* scale, const float* shift, const uint16_t* res,
+                  uint16_t* out, int32_t B, int32_t H, int32_t W, int32_t Cout, int32_t standardize, void* stream) {
+    if (!x0 || !w || !bias || !gamma || !beta || !out) return fail("hd_op_conv_gn: null argument");
+    if ((scale == nullptr) != (shift == nullptr)) return fail("hd_op_conv_gn: scale and shift must come together");
+    if (!conv_gemm_can_fuse_gn(B, H, W, Cout, 3, CONV_TAPS)) return fail("hd_op_conv_gn: shape %dx%d -> %d channels is not on the fused path", H, W, Cout);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int Cin = C0 + (x1 ? C1 : 0);
+    bf16* q = nullptr;
+    float* row = nullptr;
+    int* zero = nullptr;
+    int* cnt = nullptr;
+    float2* part = nullptr;
+    auto cleanup = [&]() { cudaFree(q); cudaFree(row); cudaFree(zero); cudaFree(cnt); cudaFree(part); };
+#define OP_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess) { cleanup(); return fail("%s failed: %s", #expr, cudaGetErrorString(e__)); } \
+    } while (0)
+    OP_TRY(cudaMalloc(&q, static_cast<size_t>(Cout) * Cin * 9 * 2));
+    OP_TRY(cudaMalloc(&cnt, static_cast<size_t>(B) * 4));
+    OP_TRY(cudaMalloc(&zero, 4));
+    OP_TRY(cudaMalloc(&part, static_cast<size_t>(B) * (H * W / 32) * (Cout / 8) * sizeof(float2)));
+    OP_TRY(cudaMemsetAsync(cnt, 0, static_cast<size_t>(B) * 4, s));
+    OP_TRY(cudaMemsetAsync(zero, 0, 4, s));
+    OP_TRY(prep_conv_weight_run(w, q, Cout, Cin, 3, standardize, 1e-5f, Cout, s));
+    ConvGemmDesc d;
+    d.src0 = ConvSrc{reinterpret_cast<const bf16*>(x0), C0};
+    d.src1 = ConvSrc{reinterpret_cast<const bf16*>(x1), x1 ? C1 : 0};
+    d.B = B; d.H = H; d.W = W; d.ksize = 3; d.mode = CONV_TAPS;
+    d.weight = q; d.N = Cout; d.out = reinterpret_cast<bf16*>(out);
+    d.epi.bias = bias; d.epi.gn_gamma = gamma; d.epi.gn_beta = beta; d.epi.gn_eps = 1e-5f; d.epi.gn_counter = cnt; d.epi.gn_part = part;
+    if (scale) {
+        OP_TRY(cudaMalloc(&row, 2 * Cout * 4));
+        OP_TRY(cudaMemcpyAsync(row, scale, Cout * 4, cudaMemcpyDeviceToDevice, s));
+        OP_TRY(cudaMemcpyAsync(row + Cout, shift, Cout * 4, cudaMemcpyDeviceToDevice, s));
+        d.epi.film = row; d.epi.film_row = zero; d.epi.film_row_stride = 0; d.epi.film_ld = 2 * Cout; d.epi.film_off = 0;
+        d.epi.film_has_scale = 1;
+    }
+    if (res) { d.epi.res = reinterpret_cast<const bf16*>(res); d.epi.ldr = Cout; }
+    ConvGemmLaunch l;
+    char msg[256];
+    if (conv_gemm_prepare(d, sms, &l, msg, sizeof(msg))) { cleanup(); return fail("%s", msg); }
+    OP_TRY(conv_gemm_run(l, s));
+    OP_TRY(cudaStreamSynchronize(s));
+#undef OP_TRY
+    cleanup();
     return 0;
 }
 

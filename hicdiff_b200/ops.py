@@ -52,6 +52,22 @@ def conv2d_nhwc(x0, w, bias=None, x1=None, res=None, ksize=None, standardize=Fal
     return out
 
 
+def conv_gn_nhwc(x0, w, bias, gamma, beta, x1=None, scale=None, shift=None, res=None, standardize=True):
+    """Block = WeightStandardizedConv2d(3x3) -> GroupNorm(8) -> [x*(scale+1)+shift] -> SiLU [-> + res] in one launch."""
+    lib = _lib.load()
+    _need_cuda(x0, w)
+    x0, x1, res = _bf16c(x0), _bf16c(x1), _bf16c(res)
+    w, bias, gamma, beta, scale, shift = (_f32c(t) for t in (w, bias, gamma, beta, scale, shift))
+    B, H, W, C0 = x0.shape
+    C1 = x1.shape[-1] if x1 is not None else 0
+    Cout = w.shape[0]
+    out = torch.empty(B, H, W, Cout, device=x0.device, dtype=torch.bfloat16)
+    _lib.check(lib.hd_op_conv_gn(_lib.ptr(x0), C0, _lib.ptr(x1), C1, _lib.ptr(w), _lib.ptr(bias), _lib.ptr(gamma), _lib.ptr(beta),
+                                 _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(res), _lib.ptr(out), B, H, W, Cout,
+                                 1 if standardize else 0, _lib.stream_ptr()), "hd_op_conv_gn")
+    return out
+
+
 def groupnorm_silu_nhwc(x, gamma, beta, scale=None, shift=None, res=None):
     lib = _lib.load()
     _need_cuda(x)

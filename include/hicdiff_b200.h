@@ -124,6 +124,11 @@ HD_API int hd_tile_scatter(const float* tiles, float* mat, int64_t n, int32_t pi
 HD_API int hd_op_conv2d(const uint16_t* x0, int32_t C0, const uint16_t* x1, int32_t C1, const float* w, const float* bias,
                  const uint16_t* res, uint16_t* out, int32_t B, int32_t H, int32_t W, int32_t Cout, int32_t ksize,
                  int32_t mode, int32_t standardize, void* stream);
+/* Block (hicdiff_condition.py:155-171) as ONE launch: 3x3 conv whose epilogue applies GroupNorm(8) + FiLM + SiLU (+ res).
+ * Only shapes on the slab path (H*W >= 128, W >= 16, Cout in {64, 128}); scale/shift/res optional. */
+HD_API int hd_op_conv_gn(const uint16_t* x0, int32_t C0, const uint16_t* x1, int32_t C1, const float* w, const float* bias,
+                  const float* gamma, const float* beta, const float* scale, const float* shift, const uint16_t* res,
+                  uint16_t* out, int32_t B, int32_t H, int32_t W, int32_t Cout, int32_t standardize, void* stream);
 HD_API int hd_op_groupnorm_silu(const uint16_t* x, uint16_t* y, const float* gamma, const float* beta, const float* scale,
                          const float* shift, const uint16_t* res, int32_t B, int32_t P, int32_t C, void* stream);
 HD_API int hd_op_channel_layernorm(const uint16_t* x, uint16_t* y, const float* g, const uint16_t* res, int32_t B, int32_t H,

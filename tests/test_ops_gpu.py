@@ -152,6 +152,42 @@ def test_groupnorm_film_silu(B, H, C, film, res):
     _check(out, ref, f"groupnorm C{C} @{H}")
 
 
+@pytest.mark.parametrize("B,H,C0,C1,Cout,film,res", [
+    (3, 64, 64, 0, 64, True, False),      # block1 at level 0 (weights resident in smem)
+    (2, 64, 64, 64, 64, True, False),     # concat 128 -> 64 (K = 1152, resident)
+    (2, 64, 64, 0, 64, False, True),      # block2: no FiLM, + residual
+    (5, 32, 128, 64, 128, True, False),   # 192 -> 128, streaming weights, 128-wide tile
+    (2, 32, 128, 0, 128, False, True),
+    (3, 16, 128, 0, 128, True, True),
+    (160, 16, 128, 0, 128, False, True),  # more tiles than SMs: several phase-B rounds per CTA
+])
+def test_conv_groupnorm_fused(B, H, C0, C1, Cout, film, res):
+    """conv -> GroupNorm(8) -> FiLM -> SiLU (+res) in ONE launch vs fp64 torch on the same bf16 inputs."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(900 + B + H + C0 + C1 + Cout)
+    x0 = _rand_nhwc(B, H, H, C0, g)
+    x1 = _rand_nhwc(B, H, H, C1, g) if C1 else None
+    Cin = C0 + C1
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)).to(DEV)
+    bias = (torch.randn(Cout, generator=g) * 0.3).to(DEV)
+    gamma = (1 + 0.2 * torch.randn(Cout, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(Cout, generator=g)).to(DEV)
+    scale = (0.3 * torch.randn(Cout, generator=g)).to(DEV) if film else None
+    shift = (0.3 * torch.randn(Cout, generator=g)).to(DEV) if film else None
+    r = _rand_nhwc(B, H, H, Cout, g) if res else None
+    out = ops.conv_gn_nhwc(x0, w, bias, gamma, beta, x1=x1, scale=scale, shift=shift, res=r, standardize=True)
+    torch.cuda.synchronize()
+    xin = _nchw64(x0) if x1 is None else torch.cat((_nchw64(x0), _nchw64(x1)), dim=1)
+    y = F.conv2d(xin, _bf16_round(_ws(w).float()), bias.to(torch.float64), padding=1)
+    y = F.group_norm(y, 8, gamma.to(torch.float64), beta.to(torch.float64), eps=1e-5)
+    if film:
+        y = y * (scale.to(torch.float64).view(1, -1, 1, 1) + 1) + shift.to(torch.float64).view(1, -1, 1, 1)
+    y = F.silu(y)
+    if res:
+        y = y + _nchw64(r)
+    _check(out, y, f"fused conv+GN {Cin}->{Cout} @{H}")
+
+
 def test_groupnorm_rejects_unsupported_channel_counts():
     """Channel counts the kernel is not built for must fail loudly, never silently compute something else."""
     ops = _ops()
