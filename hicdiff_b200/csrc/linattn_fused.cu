@@ -405,16 +405,16 @@ template <int C>
 struct OutCfg {
     static constexpr int SPANS = C / 64;
     static constexpr uint32_t WQ_BYTES = SPANS * SPAN_BYTES;
-    static constexpr uint32_t X_BYTES = SPANS * SPAN_BYTES;
+    static constexpr uint32_t X_BYTES = SPANS * SPAN_BYTES;      // one of two input stages; also the output staging (in place)
     static constexpr uint32_t MB_SPAN = C * 128;                 // one 64-wide K span of Mb [C rows]
     static constexpr uint32_t MB_BYTES = 2 * MB_SPAN;
     static constexpr uint32_t A2_BYTES = 2 * SPAN_BYTES;
-    static constexpr uint32_t OUT_BYTES = 4 * SPANS * 4096;      // per epilogue warp and span: 32 rows x 128 B
     static constexpr uint32_t SMALL_BYTES = 512 + 2 * 4 * C + 128;
-    static constexpr int SMEM_BYTES = WQ_BYTES + X_BYTES + MB_BYTES + A2_BYTES + OUT_BYTES + SMALL_BYTES + 1024;
+    static constexpr int SMEM_BYTES = WQ_BYTES + 2 * X_BYTES + MB_BYTES + A2_BYTES + SMALL_BYTES + 1024;
     static constexpr int CTAS_PER_SM = C == 64 ? 2 : 1;
+    static constexpr int X_EMPTY_ARRIVALS = C == 64 ? 4 : 8;     // storing warps per tile
 };
-constexpr int OUT_THREADS = 192;         // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue (thread = pixel row)
+constexpr int OUT_THREADS = 320;         // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue: (TMEM lane quarter, half of the work)
 
 template <int C>
 __global__ void __launch_bounds__(OUT_THREADS, OutCfg<C>::CTAS_PER_SM)
@@ -425,21 +425,21 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
     uint8_t* sWq = smem;
-    uint8_t* sX = sWq + Cf::WQ_BYTES;
-    uint8_t* sMb = sX + Cf::X_BYTES;
+    uint8_t* sX = sWq + Cf::WQ_BYTES;                // 2 stages
+    uint8_t* sMb = sX + 2 * Cf::X_BYTES;
     uint8_t* sA2 = sMb + Cf::MB_BYTES;
-    uint8_t* sOut = sA2 + Cf::A2_BYTES;
-    float* s_sq = reinterpret_cast<float*>(sOut + Cf::OUT_BYTES);
+    float* s_sq = reinterpret_cast<float*>(sA2 + Cf::A2_BYTES);
     float* s_bo = s_sq + 128;
     float* s_g2 = s_bo + C;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_g2 + C);
     uint64_t* wq_bar = bars;
-    uint64_t* in_full = bars + 1;
-    uint64_t* in_empty = bars + 2;
-    uint64_t* q_full = bars + 3;
-    uint64_t* a2_full = bars + 4;
-    uint64_t* y_full = bars + 5;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    uint64_t* x_full = bars + 1;                     // [2]
+    uint64_t* x_empty = bars + 3;                    // [2]
+    uint64_t* mb_full = bars + 5;
+    uint64_t* q_full = bars + 6;
+    uint64_t* a2_full = bars + 7;
+    uint64_t* y_full = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -450,10 +450,10 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         ptx::tmem_relinquish();
     } else if (warp == 1 && lane == 0) {
         ptx::mbar_init(wq_bar, 1);
-        ptx::mbar_init(in_full, 1);
-        ptx::mbar_init(in_empty, 128);
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&x_full[i], 1); ptx::mbar_init(&x_empty[i], Cf::X_EMPTY_ARRIVALS); }
+        ptx::mbar_init(mb_full, 1);
         ptx::mbar_init(q_full, 1);
-        ptx::mbar_init(a2_full, 128);
+        ptx::mbar_init(a2_full, 256);
         ptx::mbar_init(y_full, 1);
         ptx::fence_mbar_init();
     }
@@ -462,23 +462,35 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     constexpr uint32_t COL_Q = 0, COL_Y = 128;
+    const int ntile = a.num_tiles > static_cast<int>(blockIdx.x) ? (a.num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;   // tiles of this CTA
 
     if (warp == 0) {
+        auto load_x = [&](int it) {      // tile `it` of this CTA into stage it & 1 (the stage's previous store has drained)
+            const int st = it & 1;
+            ptx::mbar_wait(&x_empty[st], ((it >> 1) & 1u) ^ 1u);
+            if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(&x_full[st], Cf::X_BYTES);
+                const int tile = blockIdx.x + it * gridDim.x;
+                for (int sp = 0; sp < SPANS; ++sp)
+                    ptx::tma_load_2d(sX + st * Cf::X_BYTES + sp * SPAN_BYTES, &tmX, &x_full[st], sp * 64, tile * TILE);
+            }
+            __syncwarp();
+        };
         if (ptx::elect_one()) {
             ptx::mbar_arrive_expect_tx(wq_bar, Cf::WQ_BYTES);
             for (int sp = 0; sp < SPANS; ++sp) ptx::tma_load_2d(sWq + sp * SPAN_BYTES, &tmW, wq_bar, sp * 64, 0);
         }
         __syncwarp();
-        int it = 0;
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-            ptx::mbar_wait(in_empty, (it & 1u) ^ 1u);
+        if (ntile > 0) load_x(0);
+        for (int it = 0; it < ntile; ++it) {
+            if (it > 0) ptx::mbar_wait(y_full, (it - 1) & 1u);       // MMA2 of the previous tile has consumed Mb
             if (ptx::elect_one()) {
-                ptx::mbar_arrive_expect_tx(in_full, Cf::X_BYTES + Cf::MB_BYTES);
-                for (int sp = 0; sp < SPANS; ++sp) ptx::tma_load_2d(sX + sp * SPAN_BYTES, &tmX, in_full, sp * 64, tile * TILE);
-                const int b = tile / a.tiles_per_img;
-                for (int sp = 0; sp < 2; ++sp) ptx::tma_load_2d(sMb + sp * Cf::MB_SPAN, &tmM, in_full, sp * 64, b * C);
+                ptx::mbar_arrive_expect_tx(mb_full, Cf::MB_BYTES);
+                const int b = (blockIdx.x + it * gridDim.x) / a.tiles_per_img;
+                for (int sp = 0; sp < 2; ++sp) ptx::tma_load_2d(sMb + sp * Cf::MB_SPAN, &tmM, mb_full, sp * 64, b * C);
             }
             __syncwarp();
+            if (it + 1 < ntile) load_x(it + 1);                       // prefetch the next tile behind this one's compute
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc_q = ptx::make_idesc_bf16(128, 128);
@@ -488,22 +500,24 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const uint64_t dA2 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sA2));
         const uint64_t dMb = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sMb));
         ptx::mbar_wait(wq_bar, 0);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-            ptx::mbar_wait(in_full, it & 1u);
+        for (int it = 0; it < ntile; ++it) {
+            const int st = it & 1;
+            ptx::mbar_wait(&x_full[st], (it >> 1) & 1u);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
+                const uint64_t xoff = static_cast<uint64_t>((st * Cf::X_BYTES) >> 4);
 #pragma unroll
                 for (int sp = 0; sp < SPANS; ++sp)
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t off = static_cast<uint64_t>((sp * SPAN_BYTES) >> 4) + 2u * k;
-                        ptx::umma_bf16(tmem_base + COL_Q, dX + off, dWq + off, idesc_q, (sp | k) != 0 ? 1u : 0u);
+                        ptx::umma_bf16(tmem_base + COL_Q, dX + xoff + off, dWq + off, idesc_q, (sp | k) != 0 ? 1u : 0u);
                     }
                 ptx::umma_commit(q_full);
             }
             __syncwarp();
             ptx::mbar_wait(a2_full, it & 1u);
+            ptx::mbar_wait(mb_full, it & 1u);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
 #pragma unroll
@@ -519,23 +533,28 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             __syncwarp();
         }
     } else {
+        // epilogue warp (q, hf): pixel row r = q*32 + lane of the tile; hf picks two of the four heads (softmax) and half
+        // of the output channels (LayerNorm); both halves recompute the cheap per-row statistics instead of exchanging them
         const int q = warp & 3;
-        const int te = (warp - 2) * 32 + lane;
-        const int r = q * 32 + lane;                    // pixel row of the tile == TMEM lane
-        s_sq[te] = a.rowsum[te];
+        const int hf = (warp - 2) >> 2;
+        const int te = (warp - 2) * 32 + lane;          // 0..255
+        const int r = q * 32 + lane;
+        if (te < 128) s_sq[te] = a.rowsum[te];
         if (te < C) { s_bo[te] = a.bo[te]; s_g2[te] = a.g2[te]; }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        uint8_t* my_out = sOut + q * (SPANS * 4096);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-            ptx::mbar_wait(in_full, it & 1u);           // x tile visible to this thread
+        for (int it = 0; it < ntile; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int st = it & 1;
+            uint8_t* xs = sX + st * Cf::X_BYTES;
+            ptx::mbar_wait(&x_full[st], (it >> 1) & 1u);
             float mean, rstd;
-            row_stats<C>(sX, r, a.eps, mean, rstd);
+            row_stats<C>(xs, r, a.eps, mean, rstd);
             ptx::mbar_wait(q_full, it & 1u);
             ptx::tc_fence_after();
 #pragma unroll 1
-            for (int h = 0; h < 4; ++h) {
+            for (int hh = 0; hh < 2; ++hh) {
+                const int h = 2 * hf + hh;
                 uint32_t v[32];
                 ptx::tmem_ld32(tlane + COL_Q + h * 32, v);
                 ptx::tmem_ld_wait();
@@ -550,10 +569,10 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     f[j + 3] = rstd * (__uint_as_float(v[j + 3]) - mean * s4.w);
                     mx = fmaxf(fmaxf(fmaxf(mx, f[j]), fmaxf(f[j + 1], f[j + 2])), f[j + 3]);
                 }
-                float s = 0.f;
+                float ssum = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { f[j] = __expf(f[j] - mx); s += f[j]; }
-                const float inv = 1.0f / s;
+                for (int j = 0; j < 32; ++j) { f[j] = ptx::ex2((f[j] - mx) * 1.4426950408889634f); ssum += f[j]; }
+                const float inv = 1.0f / ssum;
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     uint4 o;
@@ -561,7 +580,7 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     o.y = ptx::pack_bf16x2(f[jj * 8 + 2] * inv, f[jj * 8 + 3] * inv);
                     o.z = ptx::pack_bf16x2(f[jj * 8 + 4] * inv, f[jj * 8 + 5] * inv);
                     o.w = ptx::pack_bf16x2(f[jj * 8 + 6] * inv, f[jj * 8 + 7] * inv);
-                    *reinterpret_cast<uint4*>(sA2 + (h >> 1) * SPAN_BYTES + sw_off(r, (h & 1) * 4 + jj)) = o;
+                    *reinterpret_cast<uint4*>(sA2 + hf * SPAN_BYTES + sw_off(r, hh * 4 + jj)) = o;   // span = h >> 1 = hf
                 }
             }
             ptx::tc_fence_before();
@@ -570,7 +589,7 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 
             ptx::mbar_wait(y_full, it & 1u);
             ptx::tc_fence_after();
-            // LayerNorm over the C output channels of this pixel: three cheap passes over the TMEM row
+            // LayerNorm over the C output channels of this pixel: statistics from two cheap passes over the whole TMEM row
             float sum = 0.f;
 #pragma unroll 1
             for (int c32 = 0; c32 < C / 32; ++c32) {
@@ -594,10 +613,11 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 }
             }
             const float yrstd = rsqrtf(ss * (1.0f / C) + a.eps);
-            if (lane == 0) ptx::bulk_wait_read<0>();     // previous tile's stores have read the staging buffers
-            __syncwarp();
+            // this warp's half of the channels: normalise, + x, and write the result IN PLACE over the x tile (same row, same
+            // swizzled chunk), which then doubles as the TMA-store staging buffer
 #pragma unroll 1
-            for (int c32 = 0; c32 < C / 32; ++c32) {
+            for (int cc = 0; cc < C / 64; ++cc) {
+                const int c32 = hf * (C / 64) + cc;
                 uint32_t v[32];
                 ptx::tmem_ld32(tlane + COL_Y + c32 * 32, v);
                 ptx::tmem_ld_wait();
@@ -605,8 +625,9 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     const int ch = (c32 & 1) * 4 + jj;                       // 16-byte chunk inside the span
+                    uint4* px = reinterpret_cast<uint4*>(xs + sp * SPAN_BYTES + sw_off(r, ch));
                     float xr[8];
-                    unpack8(*reinterpret_cast<const uint4*>(sX + sp * SPAN_BYTES + sw_off(r, ch)), xr);
+                    unpack8(*px, xr);
                     float o[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -618,17 +639,28 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     u.y = ptx::pack_bf16x2(o[2], o[3]);
                     u.z = ptx::pack_bf16x2(o[4], o[5]);
                     u.w = ptx::pack_bf16x2(o[6], o[7]);
-                    *reinterpret_cast<uint4*>(my_out + sp * 4096 + sw_off(lane, ch)) = u;
+                    *px = u;
                 }
             }
             ptx::tc_fence_before();
             ptx::fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                for (int sp = 0; sp < SPANS; ++sp) ptx::tma_store_2d(&tmY, my_out + sp * 4096, sp * 64, tile * TILE + q * 32);
-                ptx::bulk_commit();
+            if constexpr (C == 64) {
+                named_bar_sync(2 + q, 64);               // both halves of this row block are in place
+                if (hf == 0 && lane == 0) {
+                    ptx::tma_store_2d(&tmY, xs + (q * 32) * 128, 0, tile * TILE + q * 32);
+                    ptx::bulk_commit();
+                    ptx::bulk_wait_read<0>();             // the store has read the stage: it may be refilled
+                    ptx::mbar_arrive(&x_empty[st]);
+                }
+            } else {
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::tma_store_2d(&tmY, xs + hf * SPAN_BYTES + (q * 32) * 128, hf * 64, tile * TILE + q * 32);
+                    ptx::bulk_commit();
+                    ptx::bulk_wait_read<0>();
+                    ptx::mbar_arrive(&x_empty[st]);
+                }
             }
-            ptx::mbar_arrive(in_empty);                  // x, Mb, A2 and both accumulators are free for the next tile
         }
         if (lane == 0) ptx::bulk_wait_all();
         __syncwarp();

@@ -60,21 +60,43 @@ groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int
         const int nent = nwb * ppg;                                      // <= 128 on every level of the UNet
         const float2* pp = a.part + (static_cast<size_t>(b) * nwb) * ppr + warp * ppg;
         const float cnt = 256.0f;
-        float s = 0.f;
-        for (int idx = lane; idx < nent; idx += 32) {
-            const int blk = idx / ppg;
-            s += __ldg(pp + static_cast<size_t>(blk) * ppr + (idx - blk * ppg)).x;
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
         const float total = static_cast<float>(a.P) * static_cast<float>(cpg);
-        const float mean = s / total;
-        float m2 = 0.f;
-        for (int idx = lane; idx < nent; idx += 32) {                   // second sweep hits L1/L2 (<= 16 KiB per image)
-            const int blk = idx / ppg;
-            const float2 e = __ldg(pp + static_cast<size_t>(blk) * ppr + (idx - blk * ppg));
-            const float dm = e.x / cnt - mean;
-            m2 += e.y + cnt * dm * dm;
+        float mean, m2 = 0.f;
+        if (nent <= 128) {                                              // one batch of <= 4 independent loads per lane
+            float2 mine[4];
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = lane + 32 * i;
+                const int blk = idx / ppg;
+                mine[i] = idx < nent ? __ldg(pp + static_cast<size_t>(blk) * ppr + (idx - blk * ppg)) : make_float2(0.f, 0.f);
+                s += mine[i].x;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            mean = s / total;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (lane + 32 * i < nent) {
+                    const float dm = mine[i].x / cnt - mean;
+                    m2 += mine[i].y + cnt * dm * dm;
+                }
+            }
+        } else {
+            float s = 0.f;
+            for (int idx = lane; idx < nent; idx += 32) {
+                const int blk = idx / ppg;
+                s += __ldg(pp + static_cast<size_t>(blk) * ppr + (idx - blk * ppg)).x;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            mean = s / total;
+            for (int idx = lane; idx < nent; idx += 32) {               // second sweep hits L1/L2
+                const int blk = idx / ppg;
+                const float2 e = __ldg(pp + static_cast<size_t>(blk) * ppr + (idx - blk * ppg));
+                const float dm = e.x / cnt - mean;
+                m2 += e.y + cnt * dm * dm;
+            }
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, off);

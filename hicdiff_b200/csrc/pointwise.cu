@@ -115,6 +115,125 @@ stem_conv_kernel(const StemConvArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------ stem conv, tensor-core form
+// The same convolution as an implicit GEMM on the warp-level tensor-core path (mma.sync m16n8k16, bf16 x bf16 -> fp32):
+// M = 256 pixels of a CTA (4 rows x 64), N = 64 output channels per pass, K = Cin*k*k padded to a multiple of 16 (98 ->
+// 112 for the UNet's 7x7, 18 -> 32 for HiCEDRN's 3x3).  K is far too thin for a tcgen05 tile (one 128 x 64 x 112 tile
+// would keep the tensor pipe busy for ~220 cycles), and the kernel is bound by writing the [B, 64, 64, Cout] output;
+// the direct fp32 form above ran at 26 TFLOP/s on the CUDA cores and took 250 us, 12x the output's HBM time.
+// A fragments are gathered from the bf16 input window in shared memory through a k -> (ci, ky, kx) offset table.
+constexpr int STEM2_THREADS = 512;       // 16 warps: warp = (output row of the 4-row group, 16-pixel segment)
+constexpr int STEM2_PITCH = 72;          // bf16 per staged input row: 64 + 2*3 halo, padded
+constexpr int STEM2_OUT_PITCH = 72;      // bf16 per staged output pixel: 64 + 8 (conflict-free fragment writes)
+constexpr int STEM2_CTA_ROWS = 16;       // image rows per CTA: weights are staged once for four 4-row groups
+
+__global__ void __launch_bounds__(STEM2_THREADS, 2)
+stem_conv_mma_kernel(const StemConvArgs a, const int KP) {
+    extern __shared__ __align__(16) unsigned char stem2_smem[];
+    const int k = a.ksize;
+    const int pad = k / 2;
+    const int kk = k * k;
+    const int K = a.Cin * kk;
+    const int in_rows = STEM_ROWS + 2 * pad;
+    const int WP = KP + 8;                                   // weight row pitch (bf16): breaks the 32-bank period
+    const int x_elems = (a.Cin * in_rows * STEM2_PITCH + 7) & ~7;
+    bf16* s_x = reinterpret_cast<bf16*>(stem2_smem);          // [Cin][in_rows][PITCH], column c holds pixel c - pad
+    int* s_koff = reinterpret_cast<int*>(s_x + x_elems);      // [KP]
+    bf16* s_w = reinterpret_cast<bf16*>(s_koff + KP);         // [64][WP]
+    bf16* s_out = s_w + 64 * WP;                              // [16 warps][16 px][OUT_PITCH]
+    const int cta_groups = a.H / STEM2_CTA_ROWS;
+    const int b = blockIdx.x / cta_groups;
+    const int hbase = (blockIdx.x - b * cta_groups) * STEM2_CTA_ROWS;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int row = warp >> 2;                                // output row inside the 4-row group
+    const int px0 = (warp & 3) * 16;
+    const int ksteps = KP / 16;
+
+    for (int i = tid; i < KP; i += STEM2_THREADS) {
+        int off = 0;                                          // padded k: any valid location (its weight is zero)
+        if (i < K) {
+            const int ci = i / kk;
+            const int tap = i - ci * kk;
+            const int ky = tap / k;
+            off = (ci * in_rows + ky) * STEM2_PITCH + (tap - ky * k);
+        }
+        s_koff[i] = off;
+    }
+    bf16* my_out = s_out + warp * 16 * STEM2_OUT_PITCH;
+    for (int nb = 0; nb < a.Cout; nb += 64) {
+        __syncthreads();                                      // previous block's weights fully consumed
+        for (int n = warp; n < 64; n += STEM2_THREADS / 32) {
+            const float* wsrc = a.w + static_cast<size_t>(nb + n) * K;
+            for (int kq = lane; kq < KP; kq += 32) s_w[n * WP + kq] = __float2bfloat16(kq < K ? __ldg(wsrc + kq) : 0.f);
+        }
+        for (int grp = 0; grp < STEM2_CTA_ROWS / STEM_ROWS; ++grp) {
+            const int h0 = hbase + grp * STEM_ROWS;
+            __syncthreads();                                  // weights staged / previous group's window consumed
+            for (int i = tid; i < a.Cin * in_rows * STEM2_PITCH; i += STEM2_THREADS) {
+                const int ci = i / (in_rows * STEM2_PITCH);
+                const int rem = i - ci * in_rows * STEM2_PITCH;
+                const int ry = rem / STEM2_PITCH;
+                const int xx = rem - ry * STEM2_PITCH - pad;
+                const int yy = h0 + ry - pad;
+                const float* plane = ci == 0 ? a.x0 : a.x1;
+                float v = 0.f;
+                if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) v = __ldg(plane + (static_cast<size_t>(b) * a.H + yy) * a.W + xx);
+                s_x[i] = __float2bfloat16(v);
+            }
+            __syncthreads();
+            float acc[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[nt][r] = 0.f;
+            const bf16* lo = s_x + row * STEM2_PITCH + px0 + g;
+            const bf16* hi = lo + 8;
+#pragma unroll
+            for (int ks = 0; ks < 7; ++ks) {
+                if (ks < ksteps) {
+                    const int k0 = ks * 16 + 2 * t;
+                    const int o0 = s_koff[k0], o1 = s_koff[k0 + 1], o2 = s_koff[k0 + 8], o3 = s_koff[k0 + 9];
+                    const __nv_bfloat162 a0 = __halves2bfloat162(lo[o0], lo[o1]);
+                    const __nv_bfloat162 a1 = __halves2bfloat162(hi[o0], hi[o1]);
+                    const __nv_bfloat162 a2 = __halves2bfloat162(lo[o2], lo[o3]);
+                    const __nv_bfloat162 a3 = __halves2bfloat162(hi[o2], hi[o3]);
+                    uint32_t af[4];
+                    af[0] = *reinterpret_cast<const uint32_t*>(&a0);
+                    af[1] = *reinterpret_cast<const uint32_t*>(&a1);
+                    af[2] = *reinterpret_cast<const uint32_t*>(&a2);
+                    af[3] = *reinterpret_cast<const uint32_t*>(&a3);
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt) {
+                        const bf16* wr = s_w + (nt * 8 + g) * WP + ks * 16 + 2 * t;
+                        ptx::mma_bf16_16816(acc[nt], af, *reinterpret_cast<const uint32_t*>(wr), *reinterpret_cast<const uint32_t*>(wr + 8));
+                    }
+                }
+            }
+            // + bias -> bf16 -> per-warp staging -> coalesced 16-byte stores (16 consecutive pixels of one image row)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float2 bb = __ldg(reinterpret_cast<const float2*>(a.bias + nb + nt * 8 + 2 * t));
+                *reinterpret_cast<uint32_t*>(my_out + g * STEM2_OUT_PITCH + nt * 8 + 2 * t) =
+                    ptx::pack_bf16x2(acc[nt][0] + bb.x, acc[nt][1] + bb.y);
+                *reinterpret_cast<uint32_t*>(my_out + (g + 8) * STEM2_OUT_PITCH + nt * 8 + 2 * t) =
+                    ptx::pack_bf16x2(acc[nt][2] + bb.x, acc[nt][3] + bb.y);
+            }
+            __syncwarp();
+            bf16* ybase = a.y + ((static_cast<size_t>(b) * a.H + h0 + row) * a.W + px0) * a.Cout;
+#pragma unroll
+            for (int i = lane; i < 16 * 8; i += 32) {
+                const int pr = i >> 3, ch = i & 7;
+                *reinterpret_cast<uint4*>(ybase + static_cast<size_t>(pr) * a.Cout + nb + ch * 8) =
+                    *reinterpret_cast<const uint4*>(my_out + pr * STEM2_OUT_PITCH + ch * 8);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ 1x1 head
 __global__ void __launch_bounds__(256)
 head_conv1x1_kernel(const HeadConvArgs a) {
@@ -233,19 +352,21 @@ __global__ void step_advance_kernel(SampleCtl* ctl, int delta) { ctl->step += de
 }  // namespace
 
 cudaError_t stem_conv_run(const StemConvArgs& a, cudaStream_t s) {
-    if (a.W != STEM_W || a.H % STEM_ROWS != 0 || a.Cout % (4 * STEM_CO) != 0 || a.Cin < 1 || a.Cin > 2 ||
-        (a.ksize != 3 && a.ksize != 7))
+    if (a.W != STEM_W || a.H % STEM2_CTA_ROWS != 0 || a.Cout % 64 != 0 || a.Cin < 1 || a.Cin > 2 || (a.ksize != 3 && a.ksize != 7))
         return cudaErrorInvalidValue;
     const int pad = a.ksize / 2;
-    const int taps = a.Cin * a.ksize * a.ksize;
-    const size_t smem = (static_cast<size_t>(taps) * a.Cout + static_cast<size_t>(a.Cin) * (STEM_ROWS + 2 * pad) * STEM_PITCH) * 4;
+    const int K = a.Cin * a.ksize * a.ksize;
+    const int KP = (K + 15) & ~15;                       // <= 112: seven m16n8k16 steps
+    const int x_elems = (a.Cin * (STEM_ROWS + 2 * pad) * STEM2_PITCH + 7) & ~7;
+    const size_t smem = static_cast<size_t>(x_elems) * 2 + static_cast<size_t>(KP) * 4 + static_cast<size_t>(64) * (KP + 8) * 2 +
+                        static_cast<size_t>(STEM2_THREADS / 32) * 16 * STEM2_OUT_PITCH * 2;
     static size_t max_set = 0;
     if (smem > 48 * 1024 && smem > max_set) {
-        cudaError_t e = cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(stem_conv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         max_set = smem;
     }
-    stem_conv_kernel<<<a.B * (a.H / STEM_ROWS), STEM_THREADS, smem, s>>>(a);
+    stem_conv_mma_kernel<<<a.B * (a.H / STEM2_CTA_ROWS), STEM2_THREADS, smem, s>>>(a, KP);
     return cudaGetLastError();
 }
 
