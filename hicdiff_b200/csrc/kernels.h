@@ -163,7 +163,7 @@ struct LinAttnFusedDesc {
 };
 struct LinAttnFusedLaunch {
     LinAttnFusedDesc d;
-    CUtensorMap tmX, tmW, tmM, tmY;
+    CUtensorMap tmX, tmXk, tmW, tmM, tmY;
     int parts, tiles_per_unit, num_tiles, out_grid;
 };
 cudaError_t linattn_prep_run(const float* wqkv, const float* g1, bf16* out, float* rowsum, float* kshift,

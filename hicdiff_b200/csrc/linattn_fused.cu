@@ -49,7 +49,7 @@ __device__ __forceinline__ void unpack8(const uint4 u, float (&v)[8]) {
 }
 
 // mean / rstd over the C channels of row r of a [128 x C] swizzled x tile (two passes over shared memory)
-template <int C>
+template <int C, uint32_t SPAN_STRIDE = SPAN_BYTES>
 __device__ __forceinline__ void row_stats(const uint8_t* sx, int r, float eps, float& mean, float& rstd) {
     float s = 0.f;
 #pragma unroll
@@ -57,7 +57,7 @@ __device__ __forceinline__ void row_stats(const uint8_t* sx, int r, float eps, f
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             float v[8];
-            unpack8(*reinterpret_cast<const uint4*>(sx + sp * SPAN_BYTES + sw_off(r, c)), v);
+            unpack8(*reinterpret_cast<const uint4*>(sx + sp * SPAN_STRIDE + sw_off(r, c)), v);
 #pragma unroll
             for (int j = 0; j < 8; ++j) s += v[j];
         }
@@ -68,7 +68,7 @@ __device__ __forceinline__ void row_stats(const uint8_t* sx, int r, float eps, f
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             float v[8];
-            unpack8(*reinterpret_cast<const uint4*>(sx + sp * SPAN_BYTES + sw_off(r, c)), v);
+            unpack8(*reinterpret_cast<const uint4*>(sx + sp * SPAN_STRIDE + sw_off(r, c)), v);
 #pragma unroll
             for (int j = 0; j < 8; ++j) ss = fmaf(v[j] - mean, v[j] - mean, ss);
         }
@@ -119,19 +119,24 @@ struct KvArgs {
     float eps;
 };
 
+constexpr int KV_PX = 64;                // pixels per kv tile: K^T / V^T accumulators are 64 columns each, so the CTA needs
+                                         // 256 TMEM columns and two CTAs share an SM (their serial MMA <-> epilogue chains
+                                         // interleave; one 128-pixel CTA per SM left the tensor pipe and the SFUs idle half the time)
 template <int C>
 struct KvCfg {
     static constexpr int SPANS = C / 64;
-    static constexpr uint32_t W_BYTES = SPANS * SPAN_BYTES;       // one of Wk' / Wv'
-    static constexpr uint32_t X_BYTES = SPANS * SPAN_BYTES;
-    static constexpr uint32_t PV_BYTES = 2 * SPAN_BYTES;          // [128 rows][128 px]
-    static constexpr uint32_t SMALL_BYTES = 7 * 512 + 128;
+    static constexpr uint32_t W_BYTES = SPANS * SPAN_BYTES;          // one of Wk' / Wv' [128 rows][C]
+    static constexpr uint32_t XSPAN_BYTES = KV_PX * 128;             // one 64-channel span of a 64-pixel x tile
+    static constexpr uint32_t X_BYTES = SPANS * XSPAN_BYTES;
+    static constexpr uint32_t PV_BYTES = SPAN_BYTES;                 // [128 rows][64 px]
+    static constexpr uint32_t SMALL_BYTES = 2 * 256 + 5 * 512 + 128;
     static constexpr int SMEM_BYTES = 2 * W_BYTES + 2 * X_BYTES + 2 * PV_BYTES + SMALL_BYTES + 1024;
+    static constexpr int CTAS_PER_SM = C == 64 ? 2 : 1;
 };
-constexpr int KV_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int KV_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue: (TMEM lane quarter, 32-pixel half)
 
 template <int C>
-__global__ void __launch_bounds__(KV_THREADS, 1)
+__global__ void __launch_bounds__(KV_THREADS, KvCfg<C>::CTAS_PER_SM)
 linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const KvArgs a) {
     using Cf = KvCfg<C>;
     constexpr int SPANS = Cf::SPANS;
@@ -142,9 +147,9 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint8_t* sX = sWv + Cf::W_BYTES;                 // 2 stages
     uint8_t* sP = sX + 2 * Cf::X_BYTES;
     uint8_t* sV = sP + Cf::PV_BYTES;
-    float* s_mu = reinterpret_cast<float*>(sV + Cf::PV_BYTES);
-    float* s_rstd = s_mu + 128;
-    float* s_sk = s_rstd + 128;
+    float* s_mu = reinterpret_cast<float*>(sV + Cf::PV_BYTES);   // [64] rstd * mean per pixel
+    float* s_rstd = s_mu + KV_PX;                    // [64]
+    float* s_sk = s_rstd + KV_PX;                    // [128]
     float* s_sv = s_sk + 128;
     float* s_shift = s_sv + 128;
     float* s_S = s_shift + 128;                      // [2][128]
@@ -162,7 +167,7 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     if (warp == 0) {
         if (lane == 0) { ptx::prefetch_tmap(&tmX); ptx::prefetch_tmap(&tmW); }
         __syncwarp();
-        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_alloc(tmem_slot, 256);
         ptx::tmem_relinquish();
     } else if (warp == 1 && lane == 0) {
         ptx::mbar_init(w_bar, 1);
@@ -176,13 +181,13 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t COL_K = 0, COL_V = 128, COL_CTX = 256;
+    constexpr uint32_t COL_K = 0, COL_V = 64, COL_CTX = 128;
 
     const int unit = blockIdx.x;
     const int b = unit / a.parts;
     const int part = unit - b * a.parts;
-    const int T = a.tiles_per_unit;
-    const int m0 = b * a.n + part * T * TILE;
+    const int T = a.tiles_per_unit;                  // 64-pixel tiles of this unit
+    const int m0 = b * a.n + part * T * KV_PX;
 
     if (warp == 0) {
         if (ptx::elect_one()) {
@@ -199,12 +204,13 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             if (ptx::elect_one()) {
                 ptx::mbar_arrive_expect_tx(&x_full[st], Cf::X_BYTES);
                 for (int sp = 0; sp < SPANS; ++sp)
-                    ptx::tma_load_2d(sX + st * Cf::X_BYTES + sp * SPAN_BYTES, &tmX, &x_full[st], sp * 64, m0 + t * TILE);
+                    ptx::tma_load_2d(sX + st * Cf::X_BYTES + sp * Cf::XSPAN_BYTES, &tmX, &x_full[st], sp * 64, m0 + t * KV_PX);
             }
             __syncwarp();
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 128);
+        constexpr uint32_t idesc_kv = ptx::make_idesc_bf16(128, KV_PX);     // K^T / V^T: M = 128 (d | e), N = 64 pixels
+        constexpr uint32_t idesc_ctx = ptx::make_idesc_bf16(128, 128);      // ctx: M = 128 d, N = 128 e, K = 64 pixels
         const uint64_t dWk = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sWk));
         const uint64_t dWv = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sWv));
         const uint64_t dX = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sX));
@@ -216,14 +222,10 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             if (t > 0) ptx::mbar_wait(pv_ready, (t - 1) & 1u);     // epilogue t-1: D_K / D_V drained, P / V written
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
-                if (t > 0) {                                        // ctx[d, e] += P V^T over the 128 pixels of tile t-1
+                if (t > 0) {                                        // ctx[d, e] += P V^T over the 64 pixels of tile t-1
 #pragma unroll
-                    for (int sp = 0; sp < 2; ++sp)
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t off = static_cast<uint64_t>((sp * SPAN_BYTES) >> 4) + 2u * k;
-                            ptx::umma_bf16(tmem_base + COL_CTX, dP + off, dV + off, idesc, (t > 1 || (sp | k) != 0) ? 1u : 0u);
-                        }
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_bf16(tmem_base + COL_CTX, dP + 2u * k, dV + 2u * k, idesc_ctx, (t > 1 || k != 0) ? 1u : 0u);
                 }
                 if (t < T) {                                        // K^T = Wk' x^T, V^T = Wv' x^T of tile t
                     const uint64_t xoff = static_cast<uint64_t>(((t & 1) * Cf::X_BYTES) >> 4);
@@ -231,15 +233,17 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     for (int sp = 0; sp < SPANS; ++sp)
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const uint64_t off = static_cast<uint64_t>((sp * SPAN_BYTES) >> 4) + 2u * k;
-                            ptx::umma_bf16(tmem_base + COL_K, dWk + off, dX + xoff + off, idesc, (sp | k) != 0 ? 1u : 0u);
+                            const uint64_t offw = static_cast<uint64_t>((sp * SPAN_BYTES) >> 4) + 2u * k;
+                            const uint64_t offx = static_cast<uint64_t>((sp * Cf::XSPAN_BYTES) >> 4) + 2u * k;
+                            ptx::umma_bf16(tmem_base + COL_K, dWk + offw, dX + xoff + offx, idesc_kv, (sp | k) != 0 ? 1u : 0u);
                         }
 #pragma unroll
                     for (int sp = 0; sp < SPANS; ++sp)
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const uint64_t off = static_cast<uint64_t>((sp * SPAN_BYTES) >> 4) + 2u * k;
-                            ptx::umma_bf16(tmem_base + COL_V, dWv + off, dX + xoff + off, idesc, (sp | k) != 0 ? 1u : 0u);
+                            const uint64_t offw = static_cast<uint64_t>((sp * SPAN_BYTES) >> 4) + 2u * k;
+                            const uint64_t offx = static_cast<uint64_t>((sp * Cf::XSPAN_BYTES) >> 4) + 2u * k;
+                            ptx::umma_bf16(tmem_base + COL_V, dWv + offw, dX + xoff + offx, idesc_kv, (sp | k) != 0 ? 1u : 0u);
                         }
                     ptx::umma_commit(d_full);
                 } else {
@@ -249,10 +253,10 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             __syncwarp();
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: 8 warps, thread = (row, 64-pixel half)
+        // ------------------------------------------------------------------ epilogue: 8 warps, thread = (row, 32-pixel half)
         const int te = (warp - 2) * 32 + lane;          // 0..255
         const int q = warp & 3;                         // TMEM lane quarter
-        const int hcol = (warp - 2) >> 2;               // which 64 pixels of the tile
+        const int hcol = (warp - 2) >> 2;               // which 32 pixels of the tile
         const int r = q * 32 + lane;                    // d (K^T, ctx) / e (V^T) row
         if (te < 128) {
             s_sk[te] = a.rowsum[HD + te];
@@ -263,63 +267,64 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         constexpr float LOG2E = 1.4426950408889634f;
         const float sk_r = s_sk[r] * LOG2E, sv_r = s_sv[r], shift_r = s_shift[r] * LOG2E;   // exp(k) = exp2(k * log2 e)
         const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const int px0 = hcol * 32;
         float ssum = 0.f;
         for (int t = 0; t < T; ++t) {
             const int st = t & 1;
             ptx::mbar_wait(&x_full[st], (t >> 1) & 1u);          // x tile visible to this thread
-            ptx::mbar_wait(d_full, t & 1u);                       // K^T / V^T of tile t ready (and P / V of tile t-1 consumed)
-            ptx::tc_fence_after();
-            if (te < 128) {
+            if (te < KV_PX) {                                     // per-pixel LayerNorm statistics while the MMAs run
                 float mean, rstd;
-                row_stats<C>(sX + st * Cf::X_BYTES, te, a.eps, mean, rstd);
+                row_stats<C, Cf::XSPAN_BYTES>(sX + st * Cf::X_BYTES, te, a.eps, mean, rstd);
                 s_mu[te] = rstd * mean;          // W LN(x) = rstd * (W'x) - (rstd * mean) * rowsum(W')
                 s_rstd[te] = rstd;
             }
+            ptx::mbar_wait(d_full, t & 1u);                       // K^T / V^T of tile t ready (and P / V of tile t-1 consumed)
+            ptx::tc_fence_after();
             named_bar_sync(1, 256);
             if (te == 0) ptx::mbar_arrive(&x_empty[st]);          // MMAs done (d_full) and statistics read: stage free
-#pragma unroll 1
-            for (int c32 = 0; c32 < 2; ++c32) {
-                const int px0 = hcol * 64 + c32 * 32;
-                float mu[32], rs[32];
+            uint32_t v[32];
+            ptx::tmem_ld32(tlane + COL_K + px0, v);
+            ptx::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 m4 = *reinterpret_cast<const float4*>(s_mu + px0 + j);
-                    const float4 r4 = *reinterpret_cast<const float4*>(s_rstd + px0 + j);
-                    mu[j] = m4.x; mu[j + 1] = m4.y; mu[j + 2] = m4.z; mu[j + 3] = m4.w;
-                    rs[j] = r4.x; rs[j + 1] = r4.y; rs[j + 2] = r4.z; rs[j + 3] = r4.w;
+            for (int jj = 0; jj < 4; ++jj) {
+                const float4 ma = *reinterpret_cast<const float4*>(s_mu + px0 + jj * 8);
+                const float4 mb = *reinterpret_cast<const float4*>(s_mu + px0 + jj * 8 + 4);
+                const float4 ra = *reinterpret_cast<const float4*>(s_rstd + px0 + jj * 8);
+                const float4 rb = *reinterpret_cast<const float4*>(s_rstd + px0 + jj * 8 + 4);
+                const float mu[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+                const float rs[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                uint32_t pk[4];
+#pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2) {
+                    const int j = e2 * 2;
+                    const float p0 = ptx::ex2(fmaf(rs[j] * LOG2E, __uint_as_float(v[jj * 8 + j]), -fmaf(mu[j], sk_r, shift_r)));
+                    const float p1 = ptx::ex2(fmaf(rs[j + 1] * LOG2E, __uint_as_float(v[jj * 8 + j + 1]), -fmaf(mu[j + 1], sk_r, shift_r)));
+                    const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+                    const float2 pf = __bfloat1622float2(pb);
+                    ssum += pf.x + pf.y;                     // the denominator sums the SAME rounded p the MMA consumes
+                    pk[e2] = *reinterpret_cast<const uint32_t*>(&pb);
                 }
-                uint32_t v[32];
-                ptx::tmem_ld32(tlane + COL_K + px0, v);
-                ptx::tmem_ld_wait();
+                *reinterpret_cast<uint4*>(sP + sw_off(r, hcol * 4 + jj)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            ptx::tmem_ld32(tlane + COL_V + px0, v);
+            ptx::tmem_ld_wait();
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    uint32_t pk[4];
+            for (int jj = 0; jj < 4; ++jj) {
+                const float4 ma = *reinterpret_cast<const float4*>(s_mu + px0 + jj * 8);
+                const float4 mb = *reinterpret_cast<const float4*>(s_mu + px0 + jj * 8 + 4);
+                const float4 ra = *reinterpret_cast<const float4*>(s_rstd + px0 + jj * 8);
+                const float4 rb = *reinterpret_cast<const float4*>(s_rstd + px0 + jj * 8 + 4);
+                const float mu[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+                const float rs[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                uint32_t pk[4];
 #pragma unroll
-                    for (int e2 = 0; e2 < 4; ++e2) {
-                        const int j = jj * 8 + e2 * 2;
-                        const float k0 = fmaf(rs[j] * LOG2E, __uint_as_float(v[j]), -fmaf(mu[j], sk_r, shift_r));
-                        const float k1 = fmaf(rs[j + 1] * LOG2E, __uint_as_float(v[j + 1]), -fmaf(mu[j + 1], sk_r, shift_r));
-                        const __nv_bfloat162 pb = __floats2bfloat162_rn(ptx::ex2(k0), ptx::ex2(k1));
-                        const float2 pf = __bfloat1622float2(pb);
-                        ssum += pf.x + pf.y;                     // the denominator sums the SAME rounded p the MMA consumes
-                        pk[e2] = *reinterpret_cast<const uint32_t*>(&pb);
-                    }
-                    *reinterpret_cast<uint4*>(sP + hcol * SPAN_BYTES + sw_off(r, c32 * 4 + jj)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                for (int e2 = 0; e2 < 4; ++e2) {
+                    const int j = e2 * 2;
+                    const float v0 = fmaf(rs[j], __uint_as_float(v[jj * 8 + j]), -mu[j] * sv_r);
+                    const float v1 = fmaf(rs[j + 1], __uint_as_float(v[jj * 8 + j + 1]), -mu[j + 1] * sv_r);
+                    pk[e2] = ptx::pack_bf16x2(v0, v1);
                 }
-                ptx::tmem_ld32(tlane + COL_V + px0, v);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    uint32_t pk[4];
-#pragma unroll
-                    for (int e2 = 0; e2 < 4; ++e2) {
-                        const int j = jj * 8 + e2 * 2;
-                        const float v0 = fmaf(rs[j], __uint_as_float(v[j]), -mu[j] * sv_r);
-                        const float v1 = fmaf(rs[j + 1], __uint_as_float(v[j + 1]), -mu[j + 1] * sv_r);
-                        pk[e2] = ptx::pack_bf16x2(v0, v1);
-                    }
-                    *reinterpret_cast<uint4*>(sV + hcol * SPAN_BYTES + sw_off(r, c32 * 4 + jj)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                }
+                *reinterpret_cast<uint4*>(sV + sw_off(r, hcol * 4 + jj)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
             ptx::tc_fence_before();
             ptx::fence_proxy_async_smem();
@@ -343,7 +348,7 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 0) ptx::tmem_dealloc(tmem_base, 512);
+    if (warp == 0) ptx::tmem_dealloc(tmem_base, 256);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel 2: mix
@@ -354,20 +359,33 @@ linattn_mix_kernel(const float* __restrict__ ctx_part, const float* __restrict__
     const int b = blockIdx.x;
     const int t = threadIdx.x;          // hd = h*32 + d
     const int h = t >> 5;
+    // all partial loads of this thread (<= 8 parts x (S + eight 16-byte ctx chunks)) are issued before any is consumed
     float S = 0.f;
     float4 acc4[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = 0; p < parts; ++p) {
-        const size_t row = (static_cast<size_t>(b) * parts + p) * HD + t;
-        S += __ldg(s_part + row);
-        const float4* src = reinterpret_cast<const float4*>(ctx_part + row * 32);
-        float4 v[8];
+    float sp[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __ldg(src + j);        // eight independent 16-byte loads in flight
+    for (int p = 0; p < 8; ++p) sp[p] = p < parts ? __ldg(s_part + (static_cast<size_t>(b) * parts + p) * HD + t) : 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { acc4[j].x += v[j].x; acc4[j].y += v[j].y; acc4[j].z += v[j].z; acc4[j].w += v[j].w; }
+    for (int p0 = 0; p0 < 8; p0 += 2) {
+        float4 v[2][8];
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {
+            const int p = p0 + pp;
+            const float4* src = reinterpret_cast<const float4*>(ctx_part + ((static_cast<size_t>(b) * parts + (p < parts ? p : 0)) * HD + t) * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[pp][j] = p < parts ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc4[j].x += v[pp][j].x; acc4[j].y += v[pp][j].y; acc4[j].z += v[pp][j].z; acc4[j].w += v[pp][j].w;
+            }
     }
+#pragma unroll
+    for (int p = 0; p < 8; ++p) S += sp[p];
     const float norm = inv_n_scale / S;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -704,6 +722,8 @@ int linattn_fused_prepare(const LinAttnFusedDesc& d, int num_sms, LinAttnFusedLa
         cuuint64_t str[1] = {(cuuint64_t)d.C * 2};
         cuuint32_t box[2] = {64, TILE};
         if (encode_tmap_bf16(&out->tmX, d.x, 2, dims, str, box, err, errlen)) return 1;
+        cuuint32_t boxk[2] = {64, KV_PX};
+        if (encode_tmap_bf16(&out->tmXk, d.x, 2, dims, str, boxk, err, errlen)) return 1;
         cuuint32_t boxy[2] = {64, 32};
         if (encode_tmap_bf16(&out->tmY, d.y, 2, dims, str, boxy, err, errlen)) return 1;
     }
@@ -734,9 +754,9 @@ static cudaError_t run_c(const LinAttnFusedLaunch& l, cudaStream_t s) {
     }
     const LinAttnFusedDesc& d = l.d;
     KvArgs ka;
-    ka.n = d.n; ka.tiles_per_unit = l.tiles_per_unit; ka.parts = l.parts; ka.rowsum = d.rowsum; ka.kshift = d.kshift;
+    ka.n = d.n; ka.tiles_per_unit = l.tiles_per_unit * (TILE / KV_PX); ka.parts = l.parts; ka.rowsum = d.rowsum; ka.kshift = d.kshift;
     ka.ctx_part = d.ctx_part; ka.s_part = d.s_part; ka.eps = d.eps;
-    linattn_kv_kernel<C><<<d.B * l.parts, KV_THREADS, KvCfg<C>::SMEM_BYTES, s>>>(l.tmX, l.tmW, ka);
+    linattn_kv_kernel<C><<<d.B * l.parts, KV_THREADS, KvCfg<C>::SMEM_BYTES, s>>>(l.tmXk, l.tmW, ka);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     linattn_mix_kernel<<<dim3(d.B, 4), 128, 0, s>>>(d.ctx_part, d.s_part, d.wo, d.mb, l.parts, C,
