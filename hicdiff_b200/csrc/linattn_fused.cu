@@ -356,9 +356,15 @@ __global__ void __launch_bounds__(128)
 linattn_mix_kernel(const float* __restrict__ ctx_part, const float* __restrict__ s_part, const float* __restrict__ wo,
                    bf16* __restrict__ mb, int parts, int C, float inv_n_scale) {
     __shared__ float s_ctx[HD][33];
+    __shared__ __align__(16) float s_wo[32 * HD];   // this block's rows of Wo (C / 4 <= 32 output channels)
     const int b = blockIdx.x;
     const int t = threadIdx.x;          // hd = h*32 + d
     const int h = t >> 5;
+    const int per = C / gridDim.y;      // output channels of this block
+    {   // coalesced copy of Wo[blockIdx.y * per .. +per][128]; its latency overlaps the partial loads below
+        const float4* src = reinterpret_cast<const float4*>(wo + static_cast<size_t>(blockIdx.y) * per * HD);
+        for (int i = t; i < per * HD / 4; i += 128) reinterpret_cast<float4*>(s_wo)[i] = __ldg(src + i);
+    }
     // all partial loads of this thread (<= 8 parts x (S + eight 16-byte ctx chunks)) are issued before any is consumed
     float S = 0.f;
     float4 acc4[8];
@@ -396,13 +402,13 @@ linattn_mix_kernel(const float* __restrict__ ctx_part, const float* __restrict__
     float c[32];
 #pragma unroll
     for (int e = 0; e < 32; ++e) c[e] = s_ctx[t][e];
-    const int per = C / gridDim.y;      // output channels of this block
-    for (int co = blockIdx.y * per; co < (blockIdx.y + 1) * per; ++co) {
-        const float4* w = reinterpret_cast<const float4*>(wo + static_cast<size_t>(co) * HD + h * 32);
+    for (int cl = 0; cl < per; ++cl) {
+        const int co = blockIdx.y * per + cl;
+        const float4* w = reinterpret_cast<const float4*>(s_wo + cl * HD + h * 32);   // broadcast reads
         float acc = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const float4 w4 = __ldg(w + e);
+            const float4 w4 = w[e];
             acc = fmaf(w4.x, c[4 * e], acc); acc = fmaf(w4.y, c[4 * e + 1], acc);
             acc = fmaf(w4.z, c[4 * e + 2], acc); acc = fmaf(w4.w, c[4 * e + 3], acc);
         }

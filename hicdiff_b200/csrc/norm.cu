@@ -28,129 +28,132 @@ constexpr int GN_SLAB_CHUNKS = GN_THREADS * GN_CHUNKS_PER_THREAD;        // 16 K
 // x * sigmoid(x) with one ex2 and one approximate reciprocal (rel. error ~2^-22, far below the bf16 output rounding)
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
-// Streaming apply: every CTA first merges the image's per-warp-block partials (Chan's parallel variance formula, fixed
-// order -> all CTAs of an image derive bit-identical statistics), then normalises / modulates / activates its slab.
-__global__ void __launch_bounds__(GN_THREADS, 3)
-groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int iters) {
+// Streaming apply, persistent form: each CTA owns a contiguous run of 16 KiB slabs (so it crosses at most a few image
+// boundaries), merges an image's per-warp-block partials when it enters the image (Chan's parallel variance formula, fixed
+// order -> every CTA derives bit-identical statistics), and keeps the next slab's loads in flight while it normalises /
+// modulates / activates the current one.  (The one-CTA-per-64-KiB version paid the statistics prologue and a partial
+// last wave on every launch: 3.9 TB/s at batch 256.)
+__global__ void __launch_bounds__(GN_THREADS, 2)
+groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int total_slabs, const int slabs_per_cta) {
     __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
-    const int b = blockIdx.x / slabs_per_img;
-    const int slab = blockIdx.x - b * slabs_per_img;
+    const int s0 = blockIdx.x * slabs_per_cta;
+    const int s1 = min(s0 + slabs_per_cta, total_slabs);
+    if (s0 >= s1) return;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int chunks_per_pixel = a.C / 8;
     const int cpg = a.C / GN_GROUPS;
-
-    const size_t base_chunk = (static_cast<size_t>(b) * a.P) * chunks_per_pixel +
-                              static_cast<size_t>(slab) * iters * GN_SLAB_CHUNKS;
-    const uint4* xin = reinterpret_cast<const uint4*>(a.x) + base_chunk;
-    const uint4* rin = a.res != nullptr ? reinterpret_cast<const uint4*>(a.res) + base_chunk : nullptr;
-    uint4* yout = reinterpret_cast<uint4*>(a.y) + base_chunk;
-    // first slab's loads go out before the statistics prologue (independent of it)
-    uint4 u[GN_CHUNKS_PER_THREAD], r[GN_CHUNKS_PER_THREAD];
-#pragma unroll
-    for (int k = 0; k < GN_CHUNKS_PER_THREAD; ++k) {
-        u[k] = __ldg(xin + tid + k * GN_THREADS);
-        r[k] = rin != nullptr ? __ldg(rin + tid + k * GN_THREADS) : make_uint4(0, 0, 0, 0);
-    }
-
-    {   // warp g merges group g: nwb warp blocks x (C / 64) eight-channel pieces, 256 elements behind each partial
-        const int nwb = a.P / 32;                                        // warp blocks of this image
-        const int ppg = a.C / 64;                                        // pieces per group
-        const int ppr = a.C / 8;                                         // pieces per partial row
-        const int nent = nwb * ppg;                                      // <= 128 on every level of the UNet
-        const float2* pp = a.part + (static_cast<size_t>(b) * nwb) * ppr + warp * ppg;
-        const float cnt = 256.0f;
-        const float total = static_cast<float>(a.P) * static_cast<float>(cpg);
-        float mean, m2 = 0.f;
-        if (nent <= 128) {                                              // one batch of <= 4 independent loads per lane
-            float2 mine[4];
-            float s = 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int idx = lane + 32 * i;
-                const int blk = idx / ppg;
-                mine[i] = idx < nent ? __ldg(pp + static_cast<size_t>(blk) * ppr + (idx - blk * ppg)) : make_float2(0.f, 0.f);
-                s += mine[i].x;
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            mean = s / total;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (lane + 32 * i < nent) {
-                    const float dm = mine[i].x / cnt - mean;
-                    m2 += mine[i].y + cnt * dm * dm;
-                }
-            }
-        } else {
-            float s = 0.f;
-            for (int idx = lane; idx < nent; idx += 32) {
-                const int blk = idx / ppg;
-                s += __ldg(pp + static_cast<size_t>(blk) * ppr + (idx - blk * ppg)).x;
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            mean = s / total;
-            for (int idx = lane; idx < nent; idx += 32) {               // second sweep hits L1/L2
-                const int blk = idx / ppg;
-                const float2 e = __ldg(pp + static_cast<size_t>(blk) * ppr + (idx - blk * ppg));
-                const float dm = e.x / cnt - mean;
-                m2 += e.y + cnt * dm * dm;
-            }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, off);
-        if (lane == 0) {
-            s_mean[warp] = mean;
-            s_rstd[warp] = rsqrtf(m2 / total + a.eps);
-        }
-    }
-    __syncthreads();
-
+    const uint4* xin = reinterpret_cast<const uint4*>(a.x);
+    const uint4* rin = a.res != nullptr ? reinterpret_cast<const uint4*>(a.res) : nullptr;
+    uint4* yout = reinterpret_cast<uint4*>(a.y);
     const int my_cp = tid % chunks_per_pixel;                // fixed per thread: GN_THREADS % chunks_per_pixel == 0
     const int my_c = my_cp * 8;
     const int my_g = my_c / cpg;
-    const float mean = s_mean[my_g], rstd = s_rstd[my_g];
-    float mul[8], add[8], post[8];
-    {
-        const float* frow = nullptr;
-        const float* prow = nullptr;
-        if (a.film != nullptr || a.postadd != nullptr) {
-            const int row = a.film_row[b * a.film_row_stride];
-            if (a.film != nullptr) frow = a.film + static_cast<size_t>(row) * a.film_ld + a.film_off;
-            if (a.postadd != nullptr) prow = a.postadd + static_cast<size_t>(row) * a.film_ld + a.postadd_off;
-        }
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + my_c));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(a.gamma + my_c + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.beta + my_c));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.beta + my_c + 4));
-        const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float bet[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = my_c + j;
-            float gm = gam[j] * rstd;
-            float bt = bet[j] - mean * gm;
-            if (frow != nullptr) {
-                const float sc = __ldg(frow + c) + 1.0f;
-                const float sh = __ldg(frow + a.C + c);
-                gm *= sc;
-                bt = bt * sc + sh;
-            }
-            mul[j] = gm;
-            add[j] = bt;
-            post[j] = prow != nullptr ? __ldg(prow + c) : 0.f;
-        }
-    }
 
-    for (int it = 0; it < iters; ++it) {
-        if (it > 0) {
+    uint4 u[GN_CHUNKS_PER_THREAD], r[GN_CHUNKS_PER_THREAD];
+    auto load_slab = [&](int s, uint4 (&uu)[GN_CHUNKS_PER_THREAD], uint4 (&rr)[GN_CHUNKS_PER_THREAD]) {
+        const size_t base = static_cast<size_t>(s) * GN_SLAB_CHUNKS + tid;
 #pragma unroll
-            for (int k = 0; k < GN_CHUNKS_PER_THREAD; ++k) {
-                u[k] = __ldg(xin + it * GN_SLAB_CHUNKS + tid + k * GN_THREADS);
-                r[k] = rin != nullptr ? __ldg(rin + it * GN_SLAB_CHUNKS + tid + k * GN_THREADS) : make_uint4(0, 0, 0, 0);
+        for (int k = 0; k < GN_CHUNKS_PER_THREAD; ++k) {
+            uu[k] = __ldg(xin + base + k * GN_THREADS);
+            rr[k] = rin != nullptr ? __ldg(rin + base + k * GN_THREADS) : make_uint4(0, 0, 0, 0);
+        }
+    };
+    load_slab(s0, u, r);                                     // in flight before the first statistics merge
+
+    float mul[8], add[8], post[8];
+    int cur_img = -1;
+    for (int s = s0; s < s1; ++s) {
+        const int b = s / slabs_per_img;
+        if (b != cur_img) {
+            cur_img = b;
+            __syncthreads();                                 // everyone is done with the previous image's statistics
+            {   // warp g merges group g: nwb warp blocks x (C / 64) eight-channel pieces, 256 elements behind each partial
+                const int nwb = a.P / 32;                    // warp blocks of this image
+                const int ppg = a.C / 64;                    // pieces per group
+                const int ppr = a.C / 8;                     // pieces per partial row
+                const int nent = nwb * ppg;                  // <= 128 on every level of the UNet
+                const float2* pp = a.part + (static_cast<size_t>(b) * nwb) * ppr + warp * ppg;
+                const float cnt = 256.0f;
+                const float total = static_cast<float>(a.P) * static_cast<float>(cpg);
+                float mean, m2 = 0.f;
+                if (nent <= 128) {                           // one batch of <= 4 independent loads per lane
+                    float2 mine[4];
+                    float sm = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int idx = lane + 32 * i;
+                        const int blk = idx / ppg;
+                        mine[i] = idx < nent ? __ldg(pp + static_cast<size_t>(blk) * ppr + (idx - blk * ppg)) : make_float2(0.f, 0.f);
+                        sm += mine[i].x;
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, off);
+                    mean = sm / total;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (lane + 32 * i < nent) {
+                            const float dm = mine[i].x / cnt - mean;
+                            m2 += mine[i].y + cnt * dm * dm;
+                        }
+                    }
+                } else {
+                    float sm = 0.f;
+                    for (int idx = lane; idx < nent; idx += 32) {
+                        const int blk = idx / ppg;
+                        sm += __ldg(pp + static_cast<size_t>(blk) * ppr + (idx - blk * ppg)).x;
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, off);
+                    mean = sm / total;
+                    for (int idx = lane; idx < nent; idx += 32) {   // second sweep hits L1/L2
+                        const int blk = idx / ppg;
+                        const float2 e = __ldg(pp + static_cast<size_t>(blk) * ppr + (idx - blk * ppg));
+                        const float dm = e.x / cnt - mean;
+                        m2 += e.y + cnt * dm * dm;
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, off);
+                if (lane == 0) {
+                    s_mean[warp] = mean;
+                    s_rstd[warp] = rsqrtf(m2 / total + a.eps);
+                }
+            }
+            __syncthreads();
+            const float mean = s_mean[my_g], rstd = s_rstd[my_g];
+            const float* frow = nullptr;
+            const float* prow = nullptr;
+            if (a.film != nullptr || a.postadd != nullptr) {
+                const int row = a.film_row[b * a.film_row_stride];
+                if (a.film != nullptr) frow = a.film + static_cast<size_t>(row) * a.film_ld + a.film_off;
+                if (a.postadd != nullptr) prow = a.postadd + static_cast<size_t>(row) * a.film_ld + a.postadd_off;
+            }
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + my_c));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(a.gamma + my_c + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.beta + my_c));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.beta + my_c + 4));
+            const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bet[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = my_c + j;
+                float gm = gam[j] * rstd;
+                float bt = bet[j] - mean * gm;
+                if (frow != nullptr) {
+                    const float sc = __ldg(frow + c) + 1.0f;
+                    const float sh = __ldg(frow + a.C + c);
+                    gm *= sc;
+                    bt = bt * sc + sh;
+                }
+                mul[j] = gm;
+                add[j] = bt;
+                post[j] = prow != nullptr ? __ldg(prow + c) : 0.f;
             }
         }
+        uint4 un[GN_CHUNKS_PER_THREAD], rn[GN_CHUNKS_PER_THREAD];
+        if (s + 1 < s1) load_slab(s + 1, un, rn);            // next slab in flight while this one is processed
+        const size_t obase = static_cast<size_t>(s) * GN_SLAB_CHUNKS + tid;
 #pragma unroll
         for (int k = 0; k < GN_CHUNKS_PER_THREAD; ++k) {
             float v[8];
@@ -170,7 +173,11 @@ groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int
             o.y = ptx::pack_bf16x2(v[2], v[3]);
             o.z = ptx::pack_bf16x2(v[4], v[5]);
             o.w = ptx::pack_bf16x2(v[6], v[7]);
-            yout[it * GN_SLAB_CHUNKS + tid + k * GN_THREADS] = o;
+            yout[obase + k * GN_THREADS] = o;
+        }
+        if (s + 1 < s1) {
+#pragma unroll
+            for (int k = 0; k < GN_CHUNKS_PER_THREAD; ++k) { u[k] = un[k]; r[k] = rn[k]; }
         }
     }
 }
@@ -319,13 +326,19 @@ cudaError_t groupnorm_film_silu_run(const GroupNormArgs& a, cudaStream_t s) {
         return cudaErrorInvalidValue;
     const size_t img_chunks = static_cast<size_t>(a.P) * a.C / 8;
     if (img_chunks % GN_SLAB_CHUNKS != 0) return cudaErrorInvalidValue;   // images are 32 KiB .. 2 MiB here
-    // each CTA walks `iters` consecutive 16 KiB pieces (amortises the statistics prologue) while keeping >= ~4 waves
-    int iters = 4;
-    while (iters > 1 && ((img_chunks / GN_SLAB_CHUNKS) % iters != 0 ||
-                         static_cast<size_t>(a.B) * (img_chunks / GN_SLAB_CHUNKS) / iters < 2048))
-        iters /= 2;
-    const int slabs = static_cast<int>(img_chunks / GN_SLAB_CHUNKS / iters);
-    groupnorm_apply_kernel<<<a.B * slabs, GN_THREADS, 0, s>>>(a, slabs, iters);
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            num_sms = 148;
+    }
+    const int slabs_per_img = static_cast<int>(img_chunks / GN_SLAB_CHUNKS);
+    const int total = a.B * slabs_per_img;
+    int grid = 2 * num_sms;                              // two resident CTAs per SM, one contiguous run of slabs each
+    if (grid > total) grid = total;
+    const int per_cta = (total + grid - 1) / grid;
+    grid = (total + per_cta - 1) / per_cta;
+    groupnorm_apply_kernel<<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
     return cudaGetLastError();
 }
 
