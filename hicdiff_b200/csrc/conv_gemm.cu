@@ -27,6 +27,7 @@
 //     store).  Producer and issuer loops are warp-uniform with one elected lane issuing (ncu showed the earlier
 //     `if (lane == 0)` form issue-bound: ~650 cycles of scalar code per K block, profiles/r01_conv_gemm_ncu.md).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -47,12 +48,13 @@ constexpr uint32_t EPI_BUF_BYTES = 32 * 64;           // 32 rows x 32 bf16, 64B-
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int BAR_BYTES = 256;
 
-enum Kind : int { K_GENERAL = 0, K_SLAB = 1, K_SLAB_RES = 2 };
+enum Kind : int { K_GENERAL = 0, K_SLAB = 1, K_SLAB_RES = 2, K_PAD = 3 };
+constexpr uint32_t PAD_SLAB_CAP_BYTES = 42 * 1024;     // (rows + 2) * (W + 2) pixels * 128 B: 42240 B at W = 64, 30464 B at W = 32
 
 template <int BN, int KIND, bool GNF = false>
 struct Cfg {
     static constexpr uint32_t B_BLOCK_BYTES = BN * BLOCK_K * 2;                   // one (N tile, K block) of weights
-    static constexpr uint32_t A_STAGE_BYTES = KIND == K_GENERAL ? A_TILE_BYTES : SLAB_CAP_BYTES;
+    static constexpr uint32_t A_STAGE_BYTES = KIND == K_GENERAL ? A_TILE_BYTES : (KIND == K_PAD ? PAD_SLAB_CAP_BYTES : SLAB_CAP_BYTES);
     static constexpr uint32_t B_STAGE_BYTES = KIND == K_GENERAL ? B_BLOCK_BYTES : (KIND == K_SLAB ? 3 * B_BLOCK_BYTES : 0);
     static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int EPI_BUFS = BN <= 64 ? 1 : 2;                             // staging buffers per epilogue warp
@@ -79,7 +81,8 @@ struct KArgs {
     int Wl_box, rows_box;          // CONV_UPSAMPLE store box: low-res pixels per row / rows per 32-pixel warp block
     uint32_t slab_bytes;           // bytes of one slab TMA box
     uint32_t slab_dy_bytes;        // W * 128: A-descriptor advance per dy tap
-    uint32_t res_b_bytes;          // resident weight bytes (K_SLAB_RES)
+    uint32_t res_b_bytes;          // resident weight bytes (K_SLAB_RES, K_PAD)
+    int PW, tiles_per_img, H;      // K_PAD: padded row pitch W + 2, 128-position tiles per image, image height
     ConvEpilogue epi;
 };
 
@@ -211,7 +214,8 @@ __device__ __forceinline__ float transpose_reduce8(float (&v)[8], int lane) {
 template <int BN, int KIND, bool GNF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD, const KArgs a) {
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+                 const __grid_constant__ CUtensorMap tmD31, const __grid_constant__ CUtensorMap tmD30, const KArgs a) {
     using C = Cfg<BN, KIND, GNF>;
     constexpr uint32_t B_BLOCK = C::B_BLOCK_BYTES;
     constexpr int ACC = C::ACC_STAGES;
@@ -219,9 +223,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
     const int stages = a.stages;
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + stages * C::A_STAGE_BYTES;                       // per-stage weights, or the resident matrix
-    uint8_t* sEpi = sB + (KIND == K_SLAB_RES ? a.res_b_bytes : stages * C::B_STAGE_BYTES);   // all sizes are KiB multiples
+    uint8_t* sA = KIND == K_PAD ? smem + a.res_b_bytes : smem;
+    uint8_t* sB = KIND == K_PAD ? smem : smem + stages * C::A_STAGE_BYTES;    // per-stage weights, or the resident matrix
+    uint8_t* sEpi = smem + stages * C::A_STAGE_BYTES +
+                    ((KIND == K_SLAB_RES || KIND == K_PAD) ? a.res_b_bytes : stages * C::B_STAGE_BYTES);   // all sizes are KiB multiples
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpi + C::EPI_BYTES);
     uint64_t* empty_bar = full_bar + MAX_STAGES;
     uint64_t* tfull_bar = empty_bar + MAX_STAGES;
@@ -265,7 +270,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (warp-uniform, one lane issues)
-        if constexpr (KIND == K_SLAB_RES) {
+        if constexpr (KIND == K_SLAB_RES || KIND == K_PAD) {
             if (ptx::elect_one()) {
                 ptx::mbar_arrive_expect_tx(res_bar, a.res_b_bytes);
                 for (int kb = 0; kb < a.nkb; ++kb)
@@ -281,7 +286,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int b0 = m0 / a.P;
             const int h0 = (m0 - b0 * a.P) / a.W;
             const int nrow = tc.nt * BN + tc.phase * a.N;          // weight row of this tile (per-phase matrices stacked)
-            if constexpr (KIND == K_GENERAL) {
+            if constexpr (KIND == K_PAD) {
+                // one slab {64 ch, W + 2, rows + 2} per 64-channel chunk serves all nine taps: the box starts at column -1, so
+                // the zero halo columns are part of the shared-memory row pitch and a tap is a pure row offset
+                const int b = tc.mt / a.tiles_per_img;
+                const int y0 = ((tc.mt - b * a.tiles_per_img) * BLOCK_M) / a.PW;
+                for (int chunk = 0; chunk < chunks; ++chunk) {
+                    const bool second = chunk >= a.chunks0;
+                    const CUtensorMap* tm = second ? &tmA1 : &tmA0;
+                    const int c0 = (second ? chunk - a.chunks0 : chunk) * BLOCK_K;
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_arrive_expect_tx(&full_bar[stage], a.slab_bytes);
+                        ptx::tma_load_4d(sA + stage * C::A_STAGE_BYTES, tm, &full_bar[stage], c0, -1, y0 - 1, b);
+                    }
+                    __syncwarp();
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                }
+            } else if constexpr (KIND == K_GENERAL) {
                 const int row0 = m0 / a.W;                          // merged (b, h) row for the unshuffle view
                 const int dy0 = a.mode == CONV_UPSAMPLE ? (tc.phase >> 1) - 1 : -a.pad;
                 const int dx0 = a.mode == CONV_UPSAMPLE ? (tc.phase & 1) - 1 : -a.pad;
@@ -337,7 +359,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BN);
         const uint64_t descA0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sA));
         const uint64_t descB0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sB));
-        if constexpr (KIND == K_SLAB_RES) {
+        if constexpr (KIND == K_SLAB_RES || KIND == K_PAD) {
             ptx::mbar_wait(res_bar, 0);
             ptx::tc_fence_after();
         }
@@ -350,7 +372,37 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             ptx::mbar_wait(&tempty_bar[as], aphase ^ 1u);
             ptx::tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * BN;
-            if constexpr (KIND == K_GENERAL) {
+            if constexpr (KIND == K_PAD) {
+                const TileCoord tc = decode_tile(a, tile);
+                const int p0 = (tc.mt % a.tiles_per_img) * BLOCK_M;
+                const int o0 = p0 - (p0 / a.PW) * a.PW;             // padded column of the tile's first position
+                const uint32_t sA_u32 = ptx::smem_u32(sA);
+                for (int chunk = 0; chunk < chunks; ++chunk) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    if (ptx::elect_one()) {
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            // A row of GEMM row i is slab pixel (1 + dy) * PW + o0 + dx + i: the start is NOT a multiple of the
+                            // 8-row swizzle atom.  Measured on B200: the tensor core derives the 128B-swizzle phase from the
+                            // absolute shared-memory address bits (like the TMA unit that wrote the slab), so a plain
+                            // 128-byte-granular start address is correct and the descriptor's base-offset field must stay 0
+                            // (setting it to (addr >> 7) & 7 double-applies the phase: tests/test_ops_gpu.py::test_conv_gemm).
+                            const int row = (tap / 3) * a.PW + o0 + (tap % 3) - 1;
+                            const uint32_t addr = sA_u32 + stage * C::A_STAGE_BYTES + row * 128;
+                            const uint64_t da = ptx::make_kmajor_sw128_desc(addr);
+                            const uint64_t db = descB0 + static_cast<uint64_t>(((tap * chunks + chunk) * B_BLOCK) >> 4);
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k)
+                                ptx::umma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, (chunk | tap | k) != 0 ? 1u : 0u);
+                        }
+                        ptx::umma_commit(&empty_bar[stage]);
+                        if (chunk == chunks - 1) ptx::umma_commit(&tfull_bar[as]);
+                    }
+                    __syncwarp();
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                }
+            } else if constexpr (KIND == K_GENERAL) {
                 for (int kb = 0; kb < a.nkb; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
@@ -644,6 +696,98 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 prev_tile = tile;
                 prev_iter = iter;
             }
+        } else if constexpr (KIND == K_PAD) {
+            // ---- padded-slab epilogue: GEMM row i of tile mt is PADDED position p0 + i of image b (row pitch W + 2); the
+            // positions that fall on a halo column (or past the image) carry garbage and are masked out of the statistics
+            // and clipped from the output by the TMA unit (negative / >= W column coordinates are simply not written).
+            int iter = 0;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++iter) {
+                const TileCoord tc = decode_tile(a, tile);
+                const int mt = tc.mt;
+                const int b = mt / a.tiles_per_img;
+                const int p0 = (mt - b * a.tiles_per_img) * BLOCK_M;
+                const int y0 = p0 / a.PW;
+                const int o0 = p0 - y0 * a.PW;
+                const int pos = o0 + r;
+                const int yy = pos / a.PW;
+                const int xp = pos - yy * a.PW;
+                const bool valid = xp >= 1 && xp <= a.W && (y0 + yy) < a.H;
+                const int as = iter % ACC;
+                ptx::mbar_wait(&tfull_bar[as], (iter / ACC) & 1u);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + hc * 32;
+                const int ncol = hc * 32;                       // BN == N == 64: one N tile
+                uint32_t v[32];
+                ptx::tmem_ld32(taddr, v);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&tempty_bar[as]);
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + ncol + j));
+                    f[j] = __uint_as_float(v[j]) + bb.x; f[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
+                    f[j + 2] = __uint_as_float(v[j + 2]) + bb.z; f[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
+                }
+                if (e.gn_part != nullptr) {
+                    // (sum, M2) of each 8-channel piece over the VALID rows of this warp block; the consumer recomputes the
+                    // valid-row count from the geometry (groupnorm_apply_kernel, padded partial layout)
+                    const int nv = __popc(__ballot_sync(0xffffffffu, valid));
+                    float sq[8];
+#pragma unroll
+                    for (int p8 = 0; p8 < 4; ++p8) {
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float x = valid ? f[8 * p8 + j] : 0.f;
+                            s1 += x;
+                            s2 = fmaf(x, x, s2);
+                        }
+                        sq[2 * p8] = s1;
+                        sq[2 * p8 + 1] = s2;
+                    }
+                    const float mine = transpose_reduce8(sq, lane);
+                    const float other = __shfl_down_sync(0xffffffffu, mine, 4);
+                    if ((lane & 7) == 0) {
+                        const float cnt = 8.0f * static_cast<float>(nv);
+                        const float m2 = nv > 0 ? fmaxf(other - mine * mine / cnt, 0.f) : 0.f;
+                        e.gn_part[(static_cast<size_t>(mt) * 4 + q) * (a.N >> 3) + (ncol >> 3) + (lane >> 3)] = make_float2(mine, m2);
+                    }
+                }
+                // stage (64B swizzle) and store.  TMA stores reject negative coordinates, so the valid rows are COMPACTED in the
+                // staging buffer: they are consecutive pixels of the dense [B*H*W, N] output (a halo pair sits exactly where
+                // one image row ends and the next begins), and the 32 - nv halo rows are dropped by using the tensor map whose
+                // box has nv rows (nv is 32, 31 or 30; 0 for a block past the end of the image).
+                const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+                const int nvr = __popc(vmask);
+                const int srow = __popc(vmask & ((1u << lane) - 1u));           // compacted staging row of this lane
+                if (lane == 0) ptx::bulk_wait_read<0>();
+                __syncwarp();
+                if (valid) {
+                    uint8_t* stage_row = my_stage + srow * 64;
+                    const int sw2 = (srow >> 1) & 3;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 o;
+                        o.x = ptx::pack_bf16x2(f[8 * j], f[8 * j + 1]);
+                        o.y = ptx::pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                        o.z = ptx::pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+                        o.w = ptx::pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                        *reinterpret_cast<uint4*>(stage_row + ((j ^ sw2) << 4)) = o;
+                    }
+                }
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                // dense pixel index of the first valid row (broadcast from the first valid lane)
+                const int mpix = (b * a.H + y0 + yy) * a.W + (xp - 1);
+                const int first = nvr > 0 ? __ffs(vmask) - 1 : 0;
+                const int m_first = __shfl_sync(0xffffffffu, mpix, first);
+                if (lane == 0 && nvr > 0) {
+                    const CUtensorMap* tm = nvr == 32 ? &tmD : (nvr == 31 ? &tmD31 : &tmD30);
+                    ptx::tma_store_2d(tm, my_stage, ncol, m_first);
+                    ptx::bulk_commit();
+                }
+            }
         } else {
             int iter = 0;
             for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++iter) {
@@ -804,7 +948,7 @@ inline int encode_map(CUtensorMap* tm, const void* ptr, int rank, const cuuint64
 
 // Hs x Ws: spatial size of the SOURCE tensor the taps walk over (== output size except for CONV_UPSAMPLE: low-res).
 int encode_activation_map(CUtensorMap* tm, const ConvSrc& s, const ConvGemmDesc& d, int Hs, int Ws, int slab_rows,
-                          char* err, int errlen) {
+                          char* err, int errlen, int box_w = 0) {
     const cuuint64_t C = s.C;
     if (d.mode != CONV_UNSHUFFLE) {
         const int P = Hs * Ws;
@@ -813,7 +957,7 @@ int encode_activation_map(CUtensorMap* tm, const ConvSrc& s, const ConvGemmDesc&
         if (slab_rows > 0) rows = slab_rows;
         cuuint64_t dims[4] = {C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)d.B};
         cuuint64_t str[3] = {C * 2, C * 2 * Ws, C * 2 * Ws * Hs};
-        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)Ws, (cuuint32_t)rows, (cuuint32_t)imgs};
+        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)(box_w > 0 ? box_w : Ws), (cuuint32_t)rows, (cuuint32_t)imgs};
         return encode_map(tm, s.ptr, 4, dims, str, box, err, errlen);
     }
     // input is [B, 2H, 2W, C]; view as [C, p2, W, p1, B*H]
@@ -837,8 +981,9 @@ cudaError_t launch_cfg(const ConvGemmLaunch& l, cudaStream_t s) {
     k.nkb = l.nkb; k.chunks0 = l.chunks0; k.chunks1 = l.chunks1; k.mode = l.mode; k.W = l.W; k.P = l.P;
     k.kh = l.kh; k.kw = l.kw; k.pad = l.pad; k.stages = l.stages; k.Wl_box = l.Wl_box; k.rows_box = l.rows_box;
     k.slab_bytes = l.slab_bytes; k.slab_dy_bytes = l.slab_dy_bytes; k.res_b_bytes = l.res_b_bytes;
+    k.PW = l.PW; k.tiles_per_img = l.tiles_per_img; k.H = l.Hh;
     k.epi = l.epi;
-    conv_gemm_kernel<BN, KIND, GNF><<<l.grid, NUM_THREADS, l.smem_bytes, s>>>(l.tmA0, l.tmA1, l.tmB, l.tmD, k);
+    conv_gemm_kernel<BN, KIND, GNF><<<l.grid, NUM_THREADS, l.smem_bytes, s>>>(l.tmA0, l.tmA1, l.tmB, l.tmD, l.tmD31, l.tmD30, k);
     return cudaGetLastError();
 }
 
@@ -853,6 +998,7 @@ void size_cfg(ConvGemmLaunch* l) {
     switch (l->kind) {
         case K_SLAB: if (l->gnf) size_one<BN, K_SLAB, true>(l); else size_one<BN, K_SLAB, false>(l); break;
         case K_SLAB_RES: if (l->gnf) size_one<BN, K_SLAB_RES, true>(l); else size_one<BN, K_SLAB_RES, false>(l); break;
+        case K_PAD: size_one<BN, K_PAD, false>(l); break;
         default: size_one<BN, K_GENERAL, false>(l); break;
     }
 }
@@ -907,6 +1053,8 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
     out->chunks0 = d.src0.C / BLOCK_K;
     out->chunks1 = d.src1.ptr ? d.src1.C / BLOCK_K : 0;
     const int chunks = out->chunks0 + out->chunks1;
+    int pad_slab_rows = 0;
+    uint32_t pad_slab_bytes = 0;
     const int taps = d.mode == CONV_TAPS ? d.ksize * d.ksize : 4;
     out->nkb = taps * chunks;
     // slab path: 3x3 taps over whole image rows, N <= 128 (a 256-wide weight stage would leave one pipeline stage)
@@ -917,6 +1065,31 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
         if (bn == 64 && d.N == 64 && out->nkb * 64 * BLOCK_K * 2 <= 144 * 1024) {
             out->kind = K_SLAB_RES;
             out->res_b_bytes = static_cast<uint32_t>(out->nkb) * 64 * BLOCK_K * 2;
+            // padded-slab form: ONE box {64 ch, W + 2, rows + 2} per chunk serves all nine taps (3x less L2 -> SM traffic);
+            // needs the bias(+statistics)-only epilogue and W in {32, 64}
+            // Measured (profiles/r01_notes.md): these N = 64 convs are bound by the tensor core's shared-memory OPERAND
+            // bandwidth (~64 B/clk: 64 clk for the 128-row A slice + N/2 for B per K = 16 step), not by L2 -> SM traffic, so
+            // the padded form buys no time on B200; it stays opt-in (ConvGemmDesc::pad_mode, HD_CONV_PAD overrides).
+            static const int pad_env = [] { const char* v = getenv("HD_CONV_PAD"); return v ? atoi(v) : -1; }();
+            const int pad_mode = pad_env >= 0 ? pad_env : d.pad_mode;
+            const bool plain = d.epi.res == nullptr && d.epi.film == nullptr && !d.epi.silu && d.epi.out_scale == 1.0f &&
+                               d.epi.out_f32 == nullptr && d.epi.gn_gamma == nullptr && d.epi.bias != nullptr;
+            if (pad_mode > 0 && plain && (Ws == 64 || Ws == 32) && (Hs * (Ws + 2)) % 32 == 0) {
+                const int PW = Ws + 2;
+                const int span_rows = (PW - 1 + BLOCK_M - 1) / PW + 1;            // image rows a 128-position tile can touch
+                const uint32_t sbytes = static_cast<uint32_t>(span_rows + 2) * PW * BLOCK_K * 2;
+                const int avail = SMEM_LIMIT - 1024 - BAR_BYTES - 16384 - static_cast<int>(out->res_b_bytes);
+                const int nst = avail / static_cast<int>(PAD_SLAB_CAP_BYTES);
+                if (sbytes <= PAD_SLAB_CAP_BYTES && (nst >= 2 || (pad_mode > 1 && nst >= 1))) {
+                    out->kind = K_PAD;
+                    out->PW = PW;
+                    out->Hh = Hs;
+                    out->tiles_per_img = (Hs * PW + BLOCK_M - 1) / BLOCK_M;
+                    out->num_m_tiles = d.B * out->tiles_per_img;
+                    pad_slab_rows = span_rows + 2;
+                    pad_slab_bytes = sbytes;
+                }
+            }
         }
     }
     out->bn = bn;
@@ -933,7 +1106,10 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
     out->ldo = d.N;
     out->grid = out->num_tiles < num_sms ? out->num_tiles : num_sms;
     int slab_rows = 0;
-    if (out->kind != K_GENERAL) {
+    if (out->kind == K_PAD) {
+        slab_rows = pad_slab_rows;
+        out->slab_bytes = pad_slab_bytes;
+    } else if (out->kind != K_GENERAL) {
         slab_rows = BLOCK_M / Ws + 2;
         out->slab_bytes = static_cast<uint32_t>(slab_rows) * Ws * BLOCK_K * 2;
         out->slab_dy_bytes = static_cast<uint32_t>(Ws) * BLOCK_K * 2;
@@ -952,14 +1128,15 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
         snprintf(err, errlen, "conv_gemm: this conv cannot run the GroupNorm-fused epilogue");
         return 1;
     }
-    if (d.epi.gn_part != nullptr && (M % 32 != 0 || bn < 64)) {
+    if (d.epi.gn_part != nullptr && out->kind != K_PAD && (M % 32 != 0 || bn < 64)) {
         snprintf(err, errlen, "conv_gemm: GroupNorm partials need M %% 32 == 0 and a bf16 output tile");
         return 1;
     }
 
-    if (encode_activation_map(&out->tmA0, d.src0, d, Hs, Ws, slab_rows, err, errlen)) return 1;
+    const int box_w = out->kind == K_PAD ? out->PW : 0;
+    if (encode_activation_map(&out->tmA0, d.src0, d, Hs, Ws, slab_rows, err, errlen, box_w)) return 1;
     if (d.src1.ptr) {
-        if (encode_activation_map(&out->tmA1, d.src1, d, Hs, Ws, slab_rows, err, errlen)) return 1;
+        if (encode_activation_map(&out->tmA1, d.src1, d, Hs, Ws, slab_rows, err, errlen, box_w)) return 1;
     } else {
         out->tmA1 = out->tmA0;
     }
@@ -973,7 +1150,17 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
             snprintf(err, errlen, "conv_gemm: bf16 output needs an N tile >= 64 and an output buffer");
             return 1;
         }
-        if (up) {
+        if (out->kind == K_PAD) {
+            // dense [N, M] output; a warp block stores its 32, 31 or 30 valid (non-halo) rows: one tensor map per box height
+            cuuint64_t od[2] = {(cuuint64_t)d.N, (cuuint64_t)M};
+            cuuint64_t os[1] = {(cuuint64_t)d.N * 2};
+            cuuint32_t ob[2] = {32, 32};
+            if (encode_map(&out->tmD, d.out, 2, od, os, ob, err, errlen, 64)) return 1;
+            ob[1] = 31;
+            if (encode_map(&out->tmD31, d.out, 2, od, os, ob, err, errlen, 64)) return 1;
+            ob[1] = 30;
+            if (encode_map(&out->tmD30, d.out, 2, od, os, ob, err, errlen, 64)) return 1;
+        } else if (up) {
             // output [B, H, W, N] viewed as [N, pb, W/2, pa, B*H/2]; a warp stores 32 consecutive low-res pixels of one phase
             const cuuint64_t N2 = (cuuint64_t)d.N * 2;
             out->Wl_box = Ws;
@@ -1001,7 +1188,7 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
         case 64: size_cfg<64>(out); break;
         default: size_cfg<16>(out); break;
     }
-    if (out->stages < 2) {
+    if (out->stages < (out->kind == K_PAD ? 1 : 2)) {
         snprintf(err, errlen, "conv_gemm: only %d pipeline stage(s) fit in shared memory", out->stages);
         return 1;
     }
@@ -1025,6 +1212,8 @@ cudaError_t conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t s) {
                 case 16: return l.gnf ? cudaErrorInvalidValue : launch_cfg<16, K_SLAB>(l, s);
                 default: return cudaErrorInvalidValue;
             }
+        case K_PAD:
+            return (l.bn == 64 && !l.gnf) ? launch_cfg<64, K_PAD>(l, s) : cudaErrorInvalidValue;
         case K_SLAB_RES:
             if (l.bn != 64) return cudaErrorInvalidValue;
             return l.gnf ? launch_cfg<64, K_SLAB_RES, true>(l, s) : launch_cfg<64, K_SLAB_RES>(l, s);

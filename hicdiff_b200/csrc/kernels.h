@@ -66,19 +66,22 @@ struct ConvGemmDesc {
     int N;                    // rows of `weight` (multiple of the chosen N tile)
     bf16* out;                // [B*H*W, N]
     ConvEpilogue epi;
+    int pad_mode = 0;         // 3x3, N == 64: 1 = padded-slab form where >= 2 stages fit, 2 = wherever it fits, 0 = never
 };
 
 // Opaque prepared launch (tensor maps encoded once, replayed inside CUDA graphs).
 struct ConvGemmLaunch {
-    CUtensorMap tmA0, tmA1, tmB, tmD;
+    CUtensorMap tmA0, tmA1, tmB, tmD, tmD31, tmD30;   // tmD31 / tmD30: padded-slab kind, 31- / 30-row output boxes
     int bn;             // N tile (16, 64, 128 or 256)
     int gnf;            // 1: GroupNorm-fused epilogue
-    int kind;           // 0 general, 1 slab (3x3, one A box per (chunk, dx)), 2 slab + shared-memory resident weights
+    int kind;           // 0 general, 1 slab (3x3, one A box per (chunk, dx)), 2 slab + shared-memory resident weights,
+                        // 3 padded slab (one A box per chunk serves all nine taps; GroupNorm partials use the padded layout)
     int grid;
     int smem_bytes;
     // kernel scalar arguments
     int M, N, num_m_tiles, num_n_tiles, num_tiles, nkb, chunks0, chunks1, mode, W, P, kh, kw, pad, stages;
     int Wl_box, rows_box;
+    int PW, tiles_per_img, Hh;   // padded-slab kind: row pitch W + 2, 128-position tiles per image, image height
     uint32_t slab_bytes, slab_dy_bytes, res_b_bytes;
     ConvEpilogue epi;
     bf16* out;
@@ -103,6 +106,8 @@ struct GroupNormArgs {
     bf16* y;              // [B, P, C]
     int B, P, C;          // P = H*W pixels
     const float2* part;   // [B * P / 32][C / 8] (sum, M2) partials written by the producing conv (or groupnorm_stats_run)
+    int part_tpi = 0;     // > 0: partials come from a padded-slab conv: part_tpi * 4 warp blocks per image, block k covers
+    int part_W = 0;       //      padded positions [32k, 32k + 32) of a (W + 2)-pitch image (halo columns carry no data)
     const float* gamma;   // [C]
     const float* beta;    // [C]
     float eps;

@@ -75,20 +75,33 @@ groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int
         if (b != cur_img) {
             cur_img = b;
             __syncthreads();                                 // everyone is done with the previous image's statistics
-            {   // warp g merges group g: nwb warp blocks x (C / 64) eight-channel pieces, 256 elements behind each partial
-                const int nwb = a.P / 32;                    // warp blocks of this image
+            {   // warp g merges group g: nwb warp blocks x (C / 64) eight-channel pieces; 256 elements stand behind each
+                // partial of the dense layout, 8 * (valid rows of the block) behind one written by a padded-slab conv
+                const int nwb = a.part_tpi > 0 ? a.part_tpi * 4 : a.P / 32;   // warp blocks of this image
                 const int ppg = a.C / 64;                    // pieces per group
                 const int ppr = a.C / 8;                     // pieces per partial row
-                const int nent = nwb * ppg;                  // <= 128 on every level of the UNet
+                const int nent = nwb * ppg;
                 const float2* pp = a.part + (static_cast<size_t>(b) * nwb) * ppr + warp * ppg;
-                const float cnt = 256.0f;
                 const float total = static_cast<float>(a.P) * static_cast<float>(cpg);
+                const int PW = a.part_W + 2;
+                const int HPW = a.part_W > 0 ? (a.P / a.part_W) * PW : 0;
+                auto block_count = [&](int blk) -> float {
+                    if (a.part_tpi == 0) return 256.0f;
+                    auto valid_below = [&](int n) {          // valid (non-halo, in-image) padded positions below n
+                        n = n < HPW ? n : HPW;
+                        const int rows = n / PW;
+                        int rem = n - rows * PW - 1;
+                        rem = rem < 0 ? 0 : (rem > a.part_W ? a.part_W : rem);
+                        return rows * a.part_W + rem;
+                    };
+                    return 8.0f * static_cast<float>(valid_below(32 * blk + 32) - valid_below(32 * blk));
+                };
                 float mean, m2 = 0.f;
-                if (nent <= 128) {                           // one batch of <= 4 independent loads per lane
-                    float2 mine[4];
+                if (nent <= 160) {                           // one batch of <= 5 independent loads per lane
+                    float2 mine[5];
                     float sm = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < 5; ++i) {
                         const int idx = lane + 32 * i;
                         const int blk = idx / ppg;
                         mine[i] = idx < nent ? __ldg(pp + static_cast<size_t>(blk) * ppr + (idx - blk * ppg)) : make_float2(0.f, 0.f);
@@ -98,10 +111,14 @@ groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int
                     for (int off = 16; off > 0; off >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, off);
                     mean = sm / total;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (lane + 32 * i < nent) {
-                            const float dm = mine[i].x / cnt - mean;
-                            m2 += mine[i].y + cnt * dm * dm;
+                    for (int i = 0; i < 5; ++i) {
+                        const int idx = lane + 32 * i;
+                        if (idx < nent) {
+                            const float cnt = block_count(idx / ppg);
+                            if (cnt > 0.f) {
+                                const float dm = mine[i].x / cnt - mean;
+                                m2 += mine[i].y + cnt * dm * dm;
+                            }
                         }
                     }
                 } else {
@@ -116,8 +133,11 @@ groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int
                     for (int idx = lane; idx < nent; idx += 32) {   // second sweep hits L1/L2
                         const int blk = idx / ppg;
                         const float2 e = __ldg(pp + static_cast<size_t>(blk) * ppr + (idx - blk * ppg));
-                        const float dm = e.x / cnt - mean;
-                        m2 += e.y + cnt * dm * dm;
+                        const float cnt = block_count(blk);
+                        if (cnt > 0.f) {
+                            const float dm = e.x / cnt - mean;
+                            m2 += e.y + cnt * dm * dm;
+                        }
                     }
                 }
 #pragma unroll

@@ -243,6 +243,7 @@ struct Builder {
     FilmRef film;
     std::string err;
     bool ok = true;
+    int last_part_tpi = 0, last_part_W = 0;   // partial-statistics layout of the last conv that produced GroupNorm partials
 
     Act alloc_act(int H, int W, int C) {
         Act a;
@@ -291,6 +292,7 @@ struct Builder {
         d.src1 = ConvSrc{x1 ? x1->p : nullptr, x1 ? x1->C : 0};
         d.B = B; d.H = Ho; d.W = Wo; d.ksize = ksize; d.mode = mode;
         d.weight = wq(wkey);
+        d.pad_mode = (P->cfg.reserved[0] >> 1) & 3;
         d.N = N;
         d.out = y.p;
         d.epi = epi;
@@ -299,6 +301,7 @@ struct Builder {
             ConvGemmLaunch l;
             char e[256];
             if (conv_gemm_prepare(d, P->num_sms, &l, e, sizeof(e))) { bad(std::string(wkey) + ": " + e); return y; }
+            if (gn_stats) { last_part_tpi = l.kind == 3 ? l.tiles_per_img : 0; last_part_W = l.kind == 3 ? Wo : 0; }
             Op op{[l](cudaStream_t s) { return conv_gemm_run(l, s); }, wkey};
             if (epi.gn_gamma != nullptr) {   // the fused GroupNorm epilogue counts warp-block arrivals per image from zero
                 int* cnt = epi.gn_counter;
@@ -331,6 +334,7 @@ struct Builder {
         g.x = x.p; g.y = x.p;   // in place: each CTA stages its own slab in smem before writing it back
         g.B = B; g.P = x.H * x.W; g.C = x.C;
         g.part = dry ? nullptr : ex->gn_part;
+        g.part_tpi = last_part_tpi; g.part_W = last_part_W;
         g.gamma = wf(prefix + ".weight");
         g.beta = wf(prefix + ".bias");
         g.eps = 1e-5f;
@@ -1118,13 +1122,14 @@ int hd_op_conv2d(const uint16_t* x0, int32_t C0, const uint16_t* x1, int32_t C1,
     CUDA_TRY(cudaMalloc(&q, static_cast<size_t>(Cout) * Cin * taps * 2));
     cudaError_t e = mode == CONV_UNSHUFFLE ? prep_unshuffle_weight_run(w, q, Cout, Cin, s)
                     : mode == CONV_UPSAMPLE ? prep_upsample_weight_run(w, q, Cout, Cin, s)
-                                            : prep_conv_weight_run(w, q, Cout, Cin, ksize, standardize, 1e-5f, Cout, s);
+                                            : prep_conv_weight_run(w, q, Cout, Cin, ksize, standardize & 1, 1e-5f, Cout, s);
     if (e != cudaSuccess) { cudaFree(q); return fail("weight prep failed: %s", cudaGetErrorString(e)); }
     ConvGemmDesc d;
     d.src0 = ConvSrc{reinterpret_cast<const bf16*>(x0), C0};
     d.src1 = ConvSrc{reinterpret_cast<const bf16*>(x1), x1 ? C1 : 0};
     d.B = B; d.H = H; d.W = W; d.ksize = ksize; d.mode = static_cast<ConvMode>(mode);
     d.weight = q; d.N = Cout; d.out = reinterpret_cast<bf16*>(out);
+    d.pad_mode = (standardize >> 1) & 3;   // bits 1-2 of `standardize`: opt into the padded-slab conv form (parity tests)
     d.epi.bias = bias;
     if (res) { d.epi.res = reinterpret_cast<const bf16*>(res); d.epi.ldr = Cout; }
     ConvGemmLaunch l;

@@ -66,6 +66,9 @@ CONV_CASES = [
     (2, 32, 128, 0, 64, 1, False),      # to_out
     (2, 16, 256, 128, 256, 1, False),   # res_conv on a concat
     (2, 64, 256, 0, 256, 3, False),     # HiCEDRN body conv
+    (3, 32, 64, 0, 64, 3, True),        # level-1 64 -> 64: padded-slab path with 34-pixel row pitch, 9 tiles per image
+    (2, 32, 64, 64, 64, 3, True),
+    (5, 64, 64, 0, 64, 3, False),       # odd batch on the padded-slab path (33 tiles per image)
 ]
 
 
@@ -101,6 +104,27 @@ def test_upsample_conv(B, Hl, C, Cout):
     up = F.interpolate(_nchw64(x), scale_factor=2, mode="nearest")
     ref = F.conv2d(up, w.to(torch.float64), bias.to(torch.float64), padding=1)
     _check(out, ref, f"upsample conv {C}->{Cout} @{Hl}->{2 * Hl}", rel_rms=6e-3)
+
+
+@pytest.mark.parametrize("B,H,C0,C1", [(2, 64, 64, 0), (5, 64, 64, 0), (1, 64, 64, 64), (3, 32, 64, 0), (2, 32, 64, 64)])
+def test_conv_gemm_padded_slab(B, H, C0, C1):
+    """Opt-in padded-slab form of the 3x3, Cout = 64 conv: one TMA box {64 ch, W + 2, rows + 2} per chunk, the nine taps are
+    row offsets into it (A descriptors start at arbitrary 128-byte rows: the tensor core takes the swizzle phase from the
+    absolute smem address), halo positions are masked / compacted away in the epilogue."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(4242 + B + H + C1)
+    x0 = _rand_nhwc(B, H, H, C0, g)
+    x1 = _rand_nhwc(B, H, H, C1, g) if C1 else None
+    Cin = C0 + C1
+    w = (torch.randn(64, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)).to(DEV)
+    bias = (torch.randn(64, generator=g) * 0.1).to(DEV)
+    out = ops.conv2d_nhwc(x0, w, bias, x1=x1, standardize=True, pad_mode=2)
+    torch.cuda.synchronize()
+    xin = _nchw64(x0) if x1 is None else torch.cat((_nchw64(x0), _nchw64(x1)), dim=1)
+    ref = F.conv2d(xin, _bf16_round(_ws(w).float()), bias.to(torch.float64), padding=1)
+    _check(out, ref, f"padded-slab conv {Cin}->64 @{H}")
+    same = ops.conv2d_nhwc(x0, w, bias, x1=x1, standardize=True, pad_mode=0)
+    assert (out.float() - same.float()).abs().max().item() <= 2e-2 * ref.abs().max().item()
 
 
 def test_conv_gemm_residual_epilogue():
