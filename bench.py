@@ -293,10 +293,22 @@ def run_b200_arm(args, rank, world):
     total_ms = sum(f["ms"] for f in fam.values())
     conv = fam.get("conv_gemm", dict(ms=1.0, flops=0.0, bytes=0.0, launches=0))
     conv_tflops = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
+    # DRAM traffic of the same kernel family for one step, from the committed ncu launch list of this workload / batch
+    traffic, traffic_note = None, "no ncu capture committed for this workload / batch"
+    tpath = ROOT / "profiles" / "conv_traffic.json"
+    if tpath.exists():
+        t = json.loads(tpath.read_text()).get(name)
+        if t and t.get("batch") == B:
+            traffic = t["families"]["conv_gemm"]["dram_bytes"]
+            traffic_note = t["source"]
     roofline = {
         "bound": "tensor", "kernel": "conv_gemm_kernel (all launches of one step)", "achieved": conv_tflops,
         "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": conv_tflops / peaks["bf16_sustained"],
-        "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+        "traffic": traffic, "traffic_unit": "DRAM bytes per step (all conv_gemm launches)", "traffic_source": traffic_note,
+        "algorithmic_bytes": conv["bytes"],
+        "flops_counted": "executed by the kernel (2*M*N*K per launch; the folded Upsample convs execute 4 of the reference's "
+                         "9 taps, so this is BELOW the reference-algorithmic figure; whole_step uses the reference FLOPs)",
+        "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
         "launches_per_step": conv["launches"], "share_of_step_time": conv["ms"] / total_ms if total_ms else None,
         "whole_step": {"achieved": step_tflops, "frac": step_tflops / peaks["bf16_sustained"],
                        "flops_per_tile_step": FLOPS_PER_TILE_STEP[name]},

@@ -18,7 +18,7 @@ if [ -z "$NO_NCU" ]; then
 CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --profile-reps 1"
 echo "=== ncu launch list"
 $CMD > gpurun_out/ncu_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c ${LCOUNT:-450} --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 tail -2 gpurun_out/ncu_launch.log
 echo "=== ncu --set full (conv_gemm)"
 $CMD > gpurun_out/ncu_plain.log 2>&1 &&

@@ -7,24 +7,34 @@ from collections import OrderedDict
 
 path = sys.argv[1]
 skip = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-rows = []
 with open(path) as f:
     lines = [l for l in f if l.startswith('"')]
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 1e3, "ms": 1e6, "nsecond": 1.0, "usecond": 1e3, "msecond": 1e6}
+per_id = OrderedDict()
 for r in csv.DictReader(lines):
-    if r.get("Metric Name") != "gpu__time_duration.sum":
+    name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("unnamed>::", "").replace("hd::<", "")
+    e = per_id.setdefault(int(r["ID"]), {"name": name, "ns": 0.0, "rd": 0.0, "wr": 0.0})
+    try:
+        val = float(r["Metric Value"].replace(",", "")) * UNIT.get(r.get("Metric Unit", ""), 1.0)
+    except ValueError:
         continue
-    name = r["Kernel Name"]
-    name = re.sub(r"\(.*", "", name).replace("unnamed>::", "").replace("hd::<", "")
-    rows.append((int(r["ID"]), name, float(r["Metric Value"]), r["Grid Size"], r["Block Size"]))
-rows = rows[skip:]
+    m = r.get("Metric Name")
+    if m == "gpu__time_duration.sum":
+        e["ns"] = val
+    elif m == "dram__bytes_read.sum":
+        e["rd"] = val
+    elif m == "dram__bytes_write.sum":
+        e["wr"] = val
+rows = list(per_id.values())[skip:]
 agg = OrderedDict()
-for _, n, ns, *_ in rows:
-    a = agg.setdefault(n, [0, 0.0])
+for e in rows:
+    a = agg.setdefault(e["name"], [0, 0.0, 0.0])
     a[0] += 1
-    a[1] += ns
+    a[1] += e["ns"]
+    a[2] += e["rd"] + e["wr"]
 tot = sum(v[1] for v in agg.values())
 print(f"source: {path} (first {skip} launches skipped); {len(rows)} launches, {tot / 1e6:.3f} ms total device time\n")
-print("| kernel | launches | total ms | share | avg us |")
-print("|---|---:|---:|---:|---:|")
-for n, (c, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    print(f"| `{n}` | {c} | {ns / 1e6:.3f} | {100 * ns / tot:.1f}% | {ns / c / 1e3:.1f} |")
+print("| kernel | launches | total ms | share | avg us | DRAM MB (rd+wr) total |")
+print("|---|---:|---:|---:|---:|---:|")
+for n, (c, ns, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print(f"| `{n}` | {c} | {ns / 1e6:.3f} | {100 * ns / tot:.1f}% | {ns / c / 1e3:.1f} | {by / 1e6:.1f} |")
