@@ -229,6 +229,23 @@ struct PosteriorArgs {
 };
 cudaError_t posterior_step_run(const PosteriorArgs& a, cudaStream_t s);
 
+// One DDRM step for the denoising operator (all singular values 1): mode 0 "noisier than y", 1 "less noisy than y",
+// 2 "sigma_next == sigma_0"; c0..c2 are the mode's coefficients (see ddrm_step_kernel).
+struct DdrmArgs {
+    float* x;               // [n] in: x_t, out: x_{t_next}
+    const float* eps;       // [n]
+    const float* y;         // [n] observation y_0
+    const float* noise;     // [n] z of this step, or nullptr -> Philox(seed, tile, step_id)
+    float* x0_out;          // optional: x0_t
+    int mode;
+    float sqrt_at, sqrt_1m_at, sqrt_at_next, c0, c1, c2, sigma_0;
+    long long n;
+    int tile_elems;
+    unsigned long long seed, tile_offset;
+    unsigned int step_id;
+};
+cudaError_t ddrm_step_run(const DdrmArgs& a, cudaStream_t s);
+
 cudaError_t philox_normal_run(float* out, long long n, unsigned long long seed, unsigned long long tile_offset,
                               int tile_elems, unsigned long long stream_id, cudaStream_t s);
 cudaError_t step_advance_run(SampleCtl* ctl, int delta, cudaStream_t s);

@@ -1085,6 +1085,20 @@ int hd_sample(hd_plan* P, const float* cond, const float* noise, float* out, flo
     return 0;
 }
 
+int hd_ddrm_step(float* x, const float* eps, const float* y, const float* noise, float* x0_out, int32_t mode, float sqrt_at,
+                 float sqrt_1m_at, float sqrt_at_next, float c0, float c1, float c2, float sigma_0, int64_t n, uint64_t seed,
+                 uint64_t tile_offset, uint32_t step_id, void* stream) {
+    if (!x || !eps || !y) return fail("hd_ddrm_step: null argument");
+    if (mode < 0 || mode > 2) return fail("hd_ddrm_step: mode must be 0 (before), 1 (after) or 2 (equal), got %d", mode);
+    if (n <= 0 || n % 4096 != 0) return fail("hd_ddrm_step: n = %lld is not a whole number of 64x64 tiles", static_cast<long long>(n));
+    DdrmArgs a;
+    a.x = x; a.eps = eps; a.y = y; a.noise = noise; a.x0_out = x0_out; a.mode = mode;
+    a.sqrt_at = sqrt_at; a.sqrt_1m_at = sqrt_1m_at; a.sqrt_at_next = sqrt_at_next; a.c0 = c0; a.c1 = c1; a.c2 = c2; a.sigma_0 = sigma_0;
+    a.n = n; a.tile_elems = 4096; a.seed = seed; a.tile_offset = tile_offset; a.step_id = step_id;
+    CUDA_TRY(ddrm_step_run(a, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
 int64_t hd_tile_count(int64_t n, int32_t piece, int32_t band_blocks) {
     if (n < 0 || piece <= 0 || band_blocks < 0) return -1;
     return tile_count(static_cast<int>(n), piece, band_blocks);

@@ -349,6 +349,43 @@ posterior_step_kernel(const PosteriorArgs a) {
 
 __global__ void step_advance_kernel(SampleCtl* ctl, int delta) { ctl->step += delta; }
 
+// ------------------------------------------------------------------------------------------ DDRM step (denoising operator)
+// efficient_generalized_steps (/root/reference/src/functions/denoising.py:49-104) for H = Denoising (svd_replacement.py:148-168:
+// U = V = I, every singular value is 1), so the three masked cases of :88-97 collapse to ONE case per step, chosen on the host
+// by comparing sigma_next with sigma_0.  Same operation order as the reference (separately rounded multiplies / adds).
+__global__ void __launch_bounds__(256)
+ddrm_step_kernel(const DdrmArgs a) {
+    const long long i4 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= a.n) return;
+    const float4 x = *reinterpret_cast<const float4*>(a.x + i4);
+    const float4 e = *reinterpret_cast<const float4*>(a.eps + i4);
+    const float4 y = *reinterpret_cast<const float4*>(a.y + i4);
+    float4 z;
+    if (a.noise != nullptr) {
+        z = __ldg(reinterpret_cast<const float4*>(a.noise + i4));
+    } else {
+        const unsigned long long tile = a.tile_offset + static_cast<unsigned long long>(i4 / a.tile_elems);
+        z = philox_normal4(a.seed, tile, static_cast<uint32_t>((i4 % a.tile_elems) >> 2), a.step_id + 1u);
+    }
+    const float xs[4] = {x.x, x.y, x.z, x.w}, es[4] = {e.x, e.y, e.z, e.w}, ys[4] = {y.x, y.y, y.z, y.w}, zs[4] = {z.x, z.y, z.z, z.w};
+    float o[4], x0s[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float x0 = __fdiv_rn(__fsub_rn(xs[j], __fmul_rn(es[j], a.sqrt_1m_at)), a.sqrt_at);                 // :68
+        float v;
+        if (a.mode == 0)        // noisier than y (:96-97): y*etaB + (1-etaB)*x0 + sqrt(sigma_next^2 - sigma_0^2 etaB^2) * z
+            v = __fadd_rn(__fadd_rn(__fmul_rn(ys[j], a.c0), __fmul_rn(a.c1, x0)), __fmul_rn(a.c2, zs[j]));
+        else if (a.mode == 1)   // less noisy than y (:92-93): x0 + sigma_tilde_A * ((y - x0) / sigma_0) + std_A * z
+            v = __fadd_rn(__fadd_rn(x0, __fmul_rn(a.c0, __fdiv_rn(__fsub_rn(ys[j], x0), a.sigma_0))), __fmul_rn(a.c1, zs[j]));
+        else                    // sigma_next == sigma_0 (:89): x0 + sigma_tilde_C * eps + std_C * z
+            v = __fadd_rn(__fadd_rn(x0, __fmul_rn(a.c0, es[j])), __fmul_rn(a.c1, zs[j]));
+        o[j] = __fmul_rn(a.sqrt_at_next, v);                                                                       // :101
+        x0s[j] = x0;
+    }
+    *reinterpret_cast<float4*>(a.x + i4) = make_float4(o[0], o[1], o[2], o[3]);
+    if (a.x0_out != nullptr) *reinterpret_cast<float4*>(a.x0_out + i4) = make_float4(x0s[0], x0s[1], x0s[2], x0s[3]);
+}
+
 }  // namespace
 
 cudaError_t stem_conv_run(const StemConvArgs& a, cudaStream_t s) {
@@ -367,6 +404,13 @@ cudaError_t stem_conv_run(const StemConvArgs& a, cudaStream_t s) {
         max_set = smem;
     }
     stem_conv_mma_kernel<<<a.B * (a.H / STEM2_CTA_ROWS), STEM2_THREADS, smem, s>>>(a, KP);
+    return cudaGetLastError();
+}
+
+cudaError_t ddrm_step_run(const DdrmArgs& a, cudaStream_t s) {
+    if (a.n % 4 != 0 || a.mode < 0 || a.mode > 2) return cudaErrorInvalidValue;
+    const int grid = static_cast<int>((a.n / 4 + 255) / 256);
+    ddrm_step_kernel<<<grid, 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -103,6 +103,17 @@ HD_API int hd_ddpm_step(hd_plan* plan, float* x, const float* eps, const float* 
 HD_API int hd_sample(hd_plan* plan, const float* cond, const float* noise, float* out, float* trace, int32_t B,
               uint64_t seed, uint64_t tile_offset, int32_t t_start, int32_t t_end, void* stream);
 
+/* One step of the DDRM sampler for the denoising operator (every singular value 1), given eps = model(x_t, t): replaces the
+ * body of the loop of efficient_generalized_steps (src/functions/denoising.py:49-104; H = Denoising,
+ * src/functions/svd_replacement.py:148-168).  With all singular values equal the three masked cases collapse to one per
+ * step, chosen by the caller: mode 0 (sigma_next > sigma_0): c0 = etaB, c1 = 1 - etaB, c2 = sqrt(sigma_next^2 - sigma_0^2 etaB^2);
+ * mode 1 (sigma_next < sigma_0): c0 = sqrt(sigma_next^2 - (sigma_next etaA)^2), c1 = sigma_next etaA; mode 2 (equal):
+ * c0 = sqrt(sigma_next^2 - (sigma_next etaC)^2), c1 = sigma_next etaC.  x is updated in place to x_{t_next}; x0_out (optional)
+ * receives x0_t; noise is this step's z or NULL for Philox(seed, tile_offset + tile, step_id).  n = elements (B*4096). */
+HD_API int hd_ddrm_step(float* x, const float* eps, const float* y, const float* noise, float* x0_out, int32_t mode, float sqrt_at,
+                 float sqrt_1m_at, float sqrt_at_next, float c0, float c1, float c2, float sigma_0, int64_t n, uint64_t seed,
+                 uint64_t tile_offset, uint32_t step_id, void* stream);
+
 /* -------------------------------------------------------------------------------------------------------------
  * Tiling.  hd_tile_extract replaces splitPieces (processdata/PrepareData_linear.py:25-46): zero-pad the n x n
  * matrix to a multiple of `piece`, enumerate block rows i and block columns j >= i with (j - i) <= band_blocks

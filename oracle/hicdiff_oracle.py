@@ -353,6 +353,55 @@ def p_losses(eps_fn, buf: SD, noisy, clean, t, noise, *, loss_type="l2", self_co
 
 
 # --------------------------------------------------------------------------------------------------------------
+# DDRM sampler for the denoising operator     src/functions/denoising.py:6-111, svd_replacement.py:148-168
+# --------------------------------------------------------------------------------------------------------------
+
+
+def ddrm_compute_alpha(beta, t):  # :6-9
+    beta = torch.cat([torch.zeros(1).to(beta.device), beta], dim=0)
+    return (1 - beta).cumprod(dim=0).index_select(0, t + 1).view(-1, 1, 1, 1)
+
+
+def ddrm_denoising_steps(eps_fn, betas, x, seq, y_0, sigma_0, etaB, etaA, etaC, noise):
+    """efficient_generalized_steps with H = Denoising (U = V = I, singulars == 1): the masked updates of :88-97 cover all
+    elements, one case per step.  `noise[k]` is the z the reference USES at step k (its third draw when sigma_next > sigma_0,
+    its second otherwise).  Returns (xs, x0_preds) like the reference."""
+    seq = list(seq)
+    n = x.size(0)
+    y = y_0.reshape(n, -1)
+    la = ddrm_compute_alpha(betas, (torch.ones(n) * seq[-1]).long())
+    largest_sigmas = (1 - la).sqrt() / la.sqrt()
+    big = bool(largest_sigmas[0, 0, 0, 0] > sigma_0)                                        # :22
+    inv = torch.full((1, y.shape[1]), float(sigma_0) if big else 0.0)                        # :25-27 (sigma_0 / 1)
+    init_y = (y if big else torch.zeros_like(y)).view(*x.size())                             # :31-33
+    remaining_s = (largest_sigmas.view(-1, 1) ** 2 - inv ** 2).view(*x.shape).clamp_min(0.0).sqrt()   # :34-35
+    x = (init_y + remaining_s * x) / largest_sigmas                                          # :36-40
+    seq_next = [-1] + seq[:-1]
+    xs, x0_preds = [x], []
+    for k, (i, j) in enumerate(zip(reversed(seq), reversed(seq_next))):
+        t = torch.ones(n) * i
+        at = ddrm_compute_alpha(betas, (torch.ones(n) * i).long())
+        at_next = ddrm_compute_alpha(betas, (torch.ones(n) * j).long())
+        xt = xs[-1]
+        et = eps_fn(xt, t)
+        x0_t = (xt - et * (1 - at).sqrt()) / at.sqrt()                                       # :68
+        sigma_next = (1 - at_next).sqrt()[0, 0, 0, 0] / at_next.sqrt()[0, 0, 0, 0]           # :72
+        v0, e0, z = x0_t.reshape(n, -1), et.reshape(n, -1), noise[k].reshape(n, -1)
+        if bool(sigma_next > sigma_0):                                                       # :96-97
+            d = torch.sqrt(sigma_next ** 2 - sigma_0 ** 2 / torch.ones(()) ** 2 * (etaB ** 2))
+            nxt = y * etaB + (1 - etaB) * v0 + d * z
+        elif bool(sigma_next < sigma_0):                                                     # :92-93
+            std = sigma_next * etaA
+            nxt = v0 + torch.sqrt(sigma_next ** 2 - std ** 2) * ((y - v0) / sigma_0) + std * z
+        else:                                                                                # :89
+            std = sigma_next * etaC
+            nxt = v0 + torch.sqrt(sigma_next ** 2 - std ** 2) * e0 + std * z
+        xs.append((at_next.sqrt()[0, 0, 0, 0] * nxt).view(*x.shape))                         # :100-101
+        x0_preds.append(x0_t)
+    return xs, x0_preds
+
+
+# --------------------------------------------------------------------------------------------------------------
 # Tiling                                                   processdata/PrepareData_linear.py:25-46
 # --------------------------------------------------------------------------------------------------------------
 
