@@ -51,9 +51,10 @@ constexpr int BAR_BYTES = 256;
 enum Kind : int { K_GENERAL = 0, K_SLAB = 1, K_SLAB_RES = 2, K_PAD = 3 };
 constexpr uint32_t PAD_SLAB_CAP_BYTES = 42 * 1024;     // (rows + 2) * (W + 2) pixels * 128 B: 42240 B at W = 64, 30464 B at W = 32
 
-template <int BN, int KIND, bool GNF = false>
+template <int BN, int KIND, bool GNF = false, int CG = 1>
 struct Cfg {
-    static constexpr uint32_t B_BLOCK_BYTES = BN * BLOCK_K * 2;                   // one (N tile, K block) of weights
+    // one (N tile, K block) of weights; a CTA pair (CG == 2, tcgen05 cta_group::2) splits the N rows between its two CTAs
+    static constexpr uint32_t B_BLOCK_BYTES = (BN / CG) * BLOCK_K * 2;
     static constexpr uint32_t A_STAGE_BYTES = KIND == K_GENERAL ? A_TILE_BYTES : (KIND == K_PAD ? PAD_SLAB_CAP_BYTES : SLAB_CAP_BYTES);
     static constexpr uint32_t B_STAGE_BYTES = KIND == K_GENERAL ? B_BLOCK_BYTES : (KIND == K_SLAB ? 3 * B_BLOCK_BYTES : 0);
     static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -83,6 +84,7 @@ struct KArgs {
     uint32_t slab_dy_bytes;        // W * 128: A-descriptor advance per dy tap
     uint32_t res_b_bytes;          // resident weight bytes (K_SLAB_RES, K_PAD)
     int PW, tiles_per_img, H;      // K_PAD: padded row pitch W + 2, 128-position tiles per image, image height
+    int m_tiles_real;              // number of real 128-row M tiles (a CTA pair may own one phantom tile at the end)
     ConvEpilogue epi;
 };
 
@@ -211,14 +213,23 @@ __device__ __forceinline__ float transpose_reduce8(float (&v)[8], int lane) {
     return v[0];
 }
 
-template <int BN, int KIND, bool GNF>
+template <int BN, int KIND, bool GNF, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
                  const __grid_constant__ CUtensorMap tmD31, const __grid_constant__ CUtensorMap tmD30, const KArgs a) {
-    using C = Cfg<BN, KIND, GNF>;
+    using C = Cfg<BN, KIND, GNF, CG>;
     constexpr uint32_t B_BLOCK = C::B_BLOCK_BYTES;
     constexpr int ACC = C::ACC_STAGES;
+    // CG == 2: two CTAs (a cluster) compute one 256-row tile pair with tcgen05 cta_group::2 -- each supplies its own 128 rows
+    // of A and HALF of the N rows of B, so the per-SM shared-memory operand traffic of a K = 16 step drops from
+    // 4096 + 32 N to 4096 + 16 N bytes (the measured limiter of the 1-CTA form).  The leader (rank 0) issues every MMA; TMA
+    // completions of both CTAs land on the leader's barriers; commits are multicast to both.
+    constexpr bool TWO = CG == 2;
+    static_assert(!TWO || (!GNF && KIND != K_PAD && BN >= 64), "cta_group::2 is built for the plain general / slab kinds");
+    const uint32_t rank = TWO ? ptx::cluster_ctarank() : 0u;
+    const int tile0 = TWO ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int tile_stride = TWO ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
@@ -247,45 +258,80 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             ptx::prefetch_tmap(&tmD);
         }
         __syncwarp();
-        ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
-        ptx::tmem_relinquish();
+        if constexpr (TWO) { ptx::tmem_alloc_cg2(tmem_slot, C::TMEM_COLS); ptx::tmem_relinquish_cg2(); }
+        else { ptx::tmem_alloc(tmem_slot, C::TMEM_COLS); ptx::tmem_relinquish(); }
     } else if (warp == 1 && lane == 0) {
         for (int i = 0; i < MAX_STAGES; ++i) {
-            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&full_bar[i], CG);          // CG == 2: the leader's expect_tx arrival + the peer's remote arrival
             ptx::mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < ACC; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 256);
+            ptx::mbar_init(&tempty_bar[i], 256 * CG);  // the leader's barrier collects the epilogue threads of both CTAs
         }
-        ptx::mbar_init(res_bar, 1);
+        ptx::mbar_init(res_bar, CG);
         ptx::fence_mbar_init();
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (TWO) ptx::cluster_sync_all(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const int chunks = a.chunks0 + a.chunks1;
 
+    // Stage hand-off helpers (called by the elected producer lane).  CG == 2: both CTAs' loads complete on the LEADER's barrier.
+    auto arm = [&](uint64_t* bar, uint32_t bytes) -> uint32_t {
+        if constexpr (TWO) {
+            const uint32_t lb = ptx::mapa(ptx::smem_u32(bar), 0);
+            if (rank == 0) ptx::mbar_arrive_expect_tx(bar, 2 * bytes); else ptx::mbar_arrive_cluster(lb);
+            return lb;
+        } else {
+            ptx::mbar_arrive_expect_tx(bar, bytes);
+            return 0;
+        }
+    };
+    auto ld2 = [&](void* dst, const CUtensorMap* tm, uint64_t* bar, uint32_t lb, int c0, int c1) {
+        if constexpr (TWO) ptx::tma_load_2d_cg2(dst, tm, lb, c0, c1); else ptx::tma_load_2d(dst, tm, bar, c0, c1);
+    };
+    auto ld4 = [&](void* dst, const CUtensorMap* tm, uint64_t* bar, uint32_t lb, int c0, int c1, int c2, int c3) {
+        if constexpr (TWO) ptx::tma_load_4d_cg2(dst, tm, lb, c0, c1, c2, c3); else ptx::tma_load_4d(dst, tm, bar, c0, c1, c2, c3);
+    };
+    auto ld5 = [&](void* dst, const CUtensorMap* tm, uint64_t* bar, uint32_t lb, int c0, int c1, int c2, int c3, int c4) {
+        if constexpr (TWO) ptx::tma_load_5d_cg2(dst, tm, lb, c0, c1, c2, c3, c4); else ptx::tma_load_5d(dst, tm, bar, c0, c1, c2, c3, c4);
+    };
+    auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+        if constexpr (TWO) ptx::umma_bf16_cg2(d, da, db, idesc, acc); else ptx::umma_bf16(d, da, db, idesc, acc);
+    };
+    auto commit = [&](uint64_t* bar) {
+        if constexpr (TWO) ptx::umma_commit_cg2(bar, 3); else ptx::umma_commit(bar);
+    };
+    auto release_acc = [&](uint64_t* bar) {      // epilogue thread: this accumulator stage is drained
+        if constexpr (TWO) {
+            if (rank == 0) ptx::mbar_arrive(bar); else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(bar), 0));
+        } else {
+            ptx::mbar_arrive(bar);
+        }
+    };
+    const int brow_off = static_cast<int>(rank) * (BN / CG);    // this CTA's slice of the N rows of every weight block
+
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (warp-uniform, one lane issues)
         if constexpr (KIND == K_SLAB_RES || KIND == K_PAD) {
             if (ptx::elect_one()) {
-                ptx::mbar_arrive_expect_tx(res_bar, a.res_b_bytes);
+                const uint32_t lb = arm(res_bar, a.res_b_bytes);
                 for (int kb = 0; kb < a.nkb; ++kb)
-                    ptx::tma_load_2d(sB + kb * B_BLOCK, &tmB, res_bar, kb * BLOCK_K, 0);
+                    ld2(sB + kb * B_BLOCK, &tmB, res_bar, lb, kb * BLOCK_K, brow_off);
             }
             __syncwarp();
         }
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < a.num_tiles; tile += tile_stride) {
             const TileCoord tc = decode_tile(a, tile);
-            const int m0 = tc.mt * BLOCK_M;
+            const int m0 = (TWO ? 2 * tc.mt + static_cast<int>(rank) : tc.mt) * BLOCK_M;   // a pair covers M tiles 2*mt, 2*mt + 1
             const int b0 = m0 / a.P;
             const int h0 = (m0 - b0 * a.P) / a.W;
-            const int nrow = tc.nt * BN + tc.phase * a.N;          // weight row of this tile (per-phase matrices stacked)
+            const int nrow = tc.nt * BN + tc.phase * a.N + brow_off;   // weight row of this tile (per-phase matrices stacked)
             if constexpr (KIND == K_PAD) {
                 // one slab {64 ch, W + 2, rows + 2} per 64-channel chunk serves all nine taps: the box starts at column -1, so
                 // the zero halo columns are part of the shared-memory row pitch and a tap is a pure row offset
@@ -313,16 +359,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         for (int chunk = 0; chunk < chunks; ++chunk) {
                             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
                             if (ptx::elect_one()) {
-                                ptx::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+                                const uint32_t lb = arm(&full_bar[stage], C::STAGE_BYTES);
                                 const bool second = chunk >= a.chunks0;
                                 const CUtensorMap* tm = second ? &tmA1 : &tmA0;
                                 const int c0 = (second ? chunk - a.chunks0 : chunk) * BLOCK_K;
                                 uint8_t* dstA = sA + stage * C::A_STAGE_BYTES;
                                 if (a.mode == CONV_UNSHUFFLE)
-                                    ptx::tma_load_5d(dstA, tm, &full_bar[stage], c0, kx, 0, ky, row0);
+                                    ld5(dstA, tm, &full_bar[stage], lb, c0, kx, 0, ky, row0);
                                 else
-                                    ptx::tma_load_4d(dstA, tm, &full_bar[stage], c0, dx0 + kx, h0 + dy0 + ky, b0);
-                                ptx::tma_load_2d(sB + stage * C::B_STAGE_BYTES, &tmB, &full_bar[stage], kcol, nrow);
+                                    ld4(dstA, tm, &full_bar[stage], lb, c0, dx0 + kx, h0 + dy0 + ky, b0);
+                                ld2(sB + stage * C::B_STAGE_BYTES, &tmB, &full_bar[stage], lb, kcol, nrow);
                             }
                             __syncwarp();
                             kcol += BLOCK_K;
@@ -339,13 +385,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
                         if (ptx::elect_one()) {
                             constexpr uint32_t wbytes = KIND == K_SLAB ? 3 * B_BLOCK : 0;
-                            ptx::mbar_arrive_expect_tx(&full_bar[stage], a.slab_bytes + wbytes);
-                            ptx::tma_load_4d(sA + stage * C::A_STAGE_BYTES, tm, &full_bar[stage], c0, dxi - 1, h0 - 1, b0);
+                            const uint32_t lb = arm(&full_bar[stage], a.slab_bytes + wbytes);
+                            ld4(sA + stage * C::A_STAGE_BYTES, tm, &full_bar[stage], lb, c0, dxi - 1, h0 - 1, b0);
                             if constexpr (KIND == K_SLAB) {
 #pragma unroll
                                 for (int dyi = 0; dyi < 3; ++dyi)
-                                    ptx::tma_load_2d(sB + stage * C::B_STAGE_BYTES + dyi * B_BLOCK, &tmB, &full_bar[stage],
-                                                     ((dyi * 3 + dxi) * chunks + chunk) * BLOCK_K, nrow);
+                                    ld2(sB + stage * C::B_STAGE_BYTES + dyi * B_BLOCK, &tmB, &full_bar[stage], lb,
+                                        ((dyi * 3 + dxi) * chunks + chunk) * BLOCK_K, nrow);
                             }
                         }
                         __syncwarp();
@@ -354,9 +400,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 && rank == 0) {
         // ------------------------------------------------------------------ MMA issuer (warp-uniform, one lane issues)
-        constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BN);
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M * CG, BN);
         const uint64_t descA0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sA));
         const uint64_t descB0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sB));
         if constexpr (KIND == K_SLAB_RES || KIND == K_PAD) {
@@ -366,7 +412,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         int stage = 0;
         uint32_t phase = 0;
         int iter = 0;
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++iter) {
+        for (int tile = tile0; tile < a.num_tiles; tile += tile_stride, ++iter) {
             const int as = iter % ACC;
             const uint32_t aphase = (iter / ACC) & 1u;
             ptx::mbar_wait(&tempty_bar[as], aphase ^ 1u);
@@ -411,9 +457,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         const uint64_t db = descB0 + static_cast<uint64_t>((stage * C::B_STAGE_BYTES) >> 4);
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / 16; ++k)   // +32 bytes along K inside the swizzle span: +2 in the >>4 field
-                            ptx::umma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                        ptx::umma_commit(&empty_bar[stage]);
-                        if (kb == a.nkb - 1) ptx::umma_commit(&tfull_bar[as]);
+                            mma(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        commit(&empty_bar[stage]);
+                        if (kb == a.nkb - 1) commit(&tfull_bar[as]);
                     }
                     __syncwarp();
                     if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -437,10 +483,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             const uint64_t dad = da + static_cast<uint64_t>(dyi * dy_step);
 #pragma unroll
                             for (int k = 0; k < BLOCK_K / 16; ++k)
-                                ptx::umma_bf16(tmem_d, dad + 2u * k, db + 2u * k, idesc, (st | dyi | k) != 0 ? 1u : 0u);
+                                mma(tmem_d, dad + 2u * k, db + 2u * k, idesc, (st | dyi | k) != 0 ? 1u : 0u);
                         }
-                        ptx::umma_commit(&empty_bar[stage]);
-                        if (st == nst - 1) ptx::umma_commit(&tfull_bar[as]);
+                        commit(&empty_bar[stage]);
+                        if (st == nst - 1) commit(&tfull_bar[as]);
                     }
                     __syncwarp();
                     if (++dxi == 3) { dxi = 0; ++chunk; }
@@ -448,7 +494,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 }
             }
         }
-    } else {
+    } else if (warp >= 2) {
         // ------------------------------------------------------------------ epilogue (8 warps)
         // Warp (q, hc): TMEM lane quarter q = warp % 4 (32 accumulator rows), column half hc of every 64-column chunk.
         // Two warps per scheduler keep the long dependent chains of the epilogue overlapped (with 4 warps ncu showed the
@@ -534,7 +580,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const float inv_total = 1.0f / (static_cast<float>(a.P) * static_cast<float>(cpg));
             int prev_tile = -1, prev_iter = 0;
             for (int iter = 0;; ++iter) {
-                const int tile = blockIdx.x + iter * gridDim.x;
+                const int tile = tile0 + iter * tile_stride;
                 const bool have = tile < a.num_tiles;
                 if (have) {
                     // ------------------------------------------------ phase A: statistics of tile `iter`
@@ -701,7 +747,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             // positions that fall on a halo column (or past the image) carry garbage and are masked out of the statistics
             // and clipped from the output by the TMA unit (negative / >= W column coordinates are simply not written).
             int iter = 0;
-            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++iter) {
+            for (int tile = tile0; tile < a.num_tiles; tile += tile_stride, ++iter) {
                 const TileCoord tc = decode_tile(a, tile);
                 const int mt = tc.mt;
                 const int b = mt / a.tiles_per_img;
@@ -790,8 +836,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
         } else {
             int iter = 0;
-            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++iter) {
-                const TileCoord tc = decode_tile(a, tile);
+            for (int tile = tile0; tile < a.num_tiles; tile += tile_stride, ++iter) {
+                TileCoord tc = decode_tile(a, tile);
+                if constexpr (TWO) tc.mt = 2 * tc.mt + static_cast<int>(rank);      // this CTA's M tile of the pair
                 const int mt = tc.mt;
                 const int m = mt * BLOCK_M + r;
                 const int n0 = tc.nt * BN;
@@ -819,7 +866,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         ptx::tmem_ld_wait();
                     }
                     ptx::tc_fence_before();
-                    ptx::mbar_arrive(&tempty_bar[as]);
+                    release_acc(&tempty_bar[as]);
                     if (hc == 0 && valid && e.out_f32 != nullptr) {
                         for (int j = 0; j < 16; ++j)
                             if (n0 + j < e.n_valid) {
@@ -837,7 +884,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         ptx::tmem_ld_wait();
                         if (c + 64 == BN) {          // accumulator fully drained: hand the TMEM stage back to the MMA warp
                             ptx::tc_fence_before();
-                            ptx::mbar_arrive(&tempty_bar[as]);
+                            release_acc(&tempty_bar[as]);
                         }
                         float f[32];
 #pragma unroll
@@ -885,7 +932,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                 t = ptx::unpack_bf16x2(rr.w); f[j + 6] += t.x; f[j + 7] += t.y;
                             }
                         }
-                        if (e.gn_part != nullptr) write_partials(f, ncol, mt);   // rows are all valid: M % 32 == 0
+                        if (e.gn_part != nullptr && mt < a.m_tiles_real) write_partials(f, ncol, mt);   // rows are all valid: M % 32 == 0
                         stage_and_store(f, ncol, tc);
                     }
                 }
@@ -896,8 +943,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 0) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (TWO) ptx::cluster_sync_all(); else __syncthreads();   // the peer's smem / TMEM stay alive until the leader's MMAs retired
+    if (warp == 0) {
+        if constexpr (TWO) ptx::tmem_dealloc_cg2(tmem_base, C::TMEM_COLS); else ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -967,11 +1016,11 @@ int encode_activation_map(CUtensorMap* tm, const ConvSrc& s, const ConvGemmDesc&
     return encode_map(tm, s.ptr, 5, dims, str, box, err, errlen);
 }
 
-template <int BN, int KIND, bool GNF = false>
+template <int BN, int KIND, bool GNF = false, int CG = 1>
 cudaError_t launch_cfg(const ConvGemmLaunch& l, cudaStream_t s) {
     static int attr_bytes = 0;
     if (l.smem_bytes > attr_bytes) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, KIND, GNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, KIND, GNF, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              l.smem_bytes);
         if (e != cudaSuccess) return e;
         attr_bytes = l.smem_bytes;
@@ -981,20 +1030,46 @@ cudaError_t launch_cfg(const ConvGemmLaunch& l, cudaStream_t s) {
     k.nkb = l.nkb; k.chunks0 = l.chunks0; k.chunks1 = l.chunks1; k.mode = l.mode; k.W = l.W; k.P = l.P;
     k.kh = l.kh; k.kw = l.kw; k.pad = l.pad; k.stages = l.stages; k.Wl_box = l.Wl_box; k.rows_box = l.rows_box;
     k.slab_bytes = l.slab_bytes; k.slab_dy_bytes = l.slab_dy_bytes; k.res_b_bytes = l.res_b_bytes;
-    k.PW = l.PW; k.tiles_per_img = l.tiles_per_img; k.H = l.Hh;
+    k.PW = l.PW; k.tiles_per_img = l.tiles_per_img; k.H = l.Hh; k.m_tiles_real = l.m_tiles_real;
     k.epi = l.epi;
-    conv_gemm_kernel<BN, KIND, GNF><<<l.grid, NUM_THREADS, l.smem_bytes, s>>>(l.tmA0, l.tmA1, l.tmB, l.tmD, l.tmD31, l.tmD30, k);
-    return cudaGetLastError();
+    if constexpr (CG == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(l.grid);
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = l.smem_bytes;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, KIND, GNF, CG>, l.tmA0, l.tmA1, l.tmB, l.tmD, l.tmD31, l.tmD30, k);
+    } else {
+        conv_gemm_kernel<BN, KIND, GNF, CG><<<l.grid, NUM_THREADS, l.smem_bytes, s>>>(l.tmA0, l.tmA1, l.tmB, l.tmD, l.tmD31, l.tmD30, k);
+        return cudaGetLastError();
+    }
 }
 
-template <int BN, int KIND, bool GNF>
+template <int BN, int KIND, bool GNF, int CG = 1>
 void size_one(ConvGemmLaunch* l) {
-    l->stages = Cfg<BN, KIND, GNF>::stages(l->res_b_bytes);
-    l->smem_bytes = Cfg<BN, KIND, GNF>::smem_bytes(l->stages, l->res_b_bytes);
+    l->stages = Cfg<BN, KIND, GNF, CG>::stages(l->res_b_bytes);
+    l->smem_bytes = Cfg<BN, KIND, GNF, CG>::smem_bytes(l->stages, l->res_b_bytes);
 }
 
 template <int BN>
 void size_cfg(ConvGemmLaunch* l) {
+    if constexpr (BN >= 64) {
+        if (l->cg == 2) {
+            switch (l->kind) {
+                case K_SLAB: if constexpr (BN <= 128) size_one<BN, K_SLAB, false, 2>(l); break;
+                case K_SLAB_RES: if constexpr (BN == 64) size_one<BN, K_SLAB_RES, false, 2>(l); break;
+                default: size_one<BN, K_GENERAL, false, 2>(l); break;
+            }
+            return;
+        }
+    }
     switch (l->kind) {
         case K_SLAB: if (l->gnf) size_one<BN, K_SLAB, true>(l); else size_one<BN, K_SLAB, false>(l); break;
         case K_SLAB_RES: if (l->gnf) size_one<BN, K_SLAB_RES, true>(l); else size_one<BN, K_SLAB_RES, false>(l); break;
@@ -1094,6 +1169,21 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
     }
     out->bn = bn;
     out->num_n_tiles = d.N / bn;
+    out->m_tiles_real = out->num_m_tiles;
+    // CTA pairs (tcgen05 cta_group::2): two CTAs share one weight tile, each fetches half of its rows.  Opt-in: correct
+    // (test_conv_gemm_cta_pairs) but measured 1.4-2x SLOWER than the 1-CTA form on this pool's B200s -- the peer's half of B
+    // reaches the tensor core at only ~19 B/clk (profiles/r01_notes.md); to be resolved before it becomes the default.
+    out->cg = 1;
+    {
+        static const int cg_env = [] { const char* v = getenv("HD_CONV_CG2"); return v ? atoi(v) : -1; }();
+        const int want = cg_env >= 0 ? cg_env : d.cg2_mode;
+        const bool plain_kind = out->kind != K_PAD && d.epi.gn_gamma == nullptr && d.epi.out_f32 == nullptr && bn >= 64;
+        if (want > 0 && plain_kind && out->num_m_tiles >= 2 && num_sms >= 2) {
+            out->cg = 2;
+            if (out->kind == K_SLAB_RES) out->res_b_bytes /= 2;
+            out->num_m_tiles = (out->num_m_tiles + 1) / 2;          // M-tile PAIRS from here on
+        }
+    }
     out->num_tiles = out->num_m_tiles * out->num_n_tiles * phases;
     out->mode = d.mode;
     out->W = Ws;
@@ -1105,6 +1195,10 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
     out->out = d.out;
     out->ldo = d.N;
     out->grid = out->num_tiles < num_sms ? out->num_tiles : num_sms;
+    if (out->cg == 2) {
+        const int pairs = num_sms / 2;
+        out->grid = 2 * (out->num_tiles < pairs ? out->num_tiles : pairs);
+    }
     int slab_rows = 0;
     if (out->kind == K_PAD) {
         slab_rows = pad_slab_rows;
@@ -1143,7 +1237,7 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
     const cuuint64_t Ktot = (cuuint64_t)out->nkb * BLOCK_K;
     cuuint64_t wd[2] = {Ktot, (cuuint64_t)d.N * phases};
     cuuint64_t ws[1] = {Ktot * 2};
-    cuuint32_t wb[2] = {BLOCK_K, (cuuint32_t)bn};
+    cuuint32_t wb[2] = {BLOCK_K, (cuuint32_t)(bn / out->cg)};
     if (encode_map(&out->tmB, d.weight, 2, wd, ws, wb, err, errlen)) return 1;
     if (d.epi.out_f32 == nullptr) {
         if (bn < 64 || d.out == nullptr) {
@@ -1196,6 +1290,26 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
 }
 
 cudaError_t conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t s) {
+    if (l.cg == 2) {
+        switch (l.kind) {
+            case K_GENERAL:
+                switch (l.bn) {
+                    case 256: return launch_cfg<256, K_GENERAL, false, 2>(l, s);
+                    case 128: return launch_cfg<128, K_GENERAL, false, 2>(l, s);
+                    case 64: return launch_cfg<64, K_GENERAL, false, 2>(l, s);
+                    default: return cudaErrorInvalidValue;
+                }
+            case K_SLAB:
+                switch (l.bn) {
+                    case 128: return launch_cfg<128, K_SLAB, false, 2>(l, s);
+                    case 64: return launch_cfg<64, K_SLAB, false, 2>(l, s);
+                    default: return cudaErrorInvalidValue;
+                }
+            case K_SLAB_RES:
+                return l.bn == 64 ? launch_cfg<64, K_SLAB_RES, false, 2>(l, s) : cudaErrorInvalidValue;
+            default: return cudaErrorInvalidValue;
+        }
+    }
     switch (l.kind) {
         case K_GENERAL:
             switch (l.bn) {

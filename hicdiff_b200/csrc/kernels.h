@@ -66,6 +66,7 @@ struct ConvGemmDesc {
     int N;                    // rows of `weight` (multiple of the chosen N tile)
     bf16* out;                // [B*H*W, N]
     ConvEpilogue epi;
+    int cg2_mode = 0;         // 1: run on CTA pairs (tcgen05 cta_group::2) where the kind supports it
     int pad_mode = 0;         // 3x3, N == 64: 1 = padded-slab form where >= 2 stages fit, 2 = wherever it fits, 0 = never
 };
 
@@ -74,6 +75,8 @@ struct ConvGemmLaunch {
     CUtensorMap tmA0, tmA1, tmB, tmD, tmD31, tmD30;   // tmD31 / tmD30: padded-slab kind, 31- / 30-row output boxes
     int bn;             // N tile (16, 64, 128 or 256)
     int gnf;            // 1: GroupNorm-fused epilogue
+    int cg;             // 1, or 2: CTA pairs (clusters of two, tcgen05 cta_group::2); num_m_tiles then counts tile PAIRS
+    int m_tiles_real;   // real 128-row M tiles
     int kind;           // 0 general, 1 slab (3x3, one A box per (chunk, dx)), 2 slab + shared-memory resident weights,
                         // 3 padded slab (one A box per chunk serves all nine taps; GroupNorm partials use the padded layout)
     int grid;

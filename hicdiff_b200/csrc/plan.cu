@@ -293,6 +293,7 @@ struct Builder {
         d.B = B; d.H = Ho; d.W = Wo; d.ksize = ksize; d.mode = mode;
         d.weight = wq(wkey);
         d.pad_mode = (P->cfg.reserved[0] >> 1) & 3;
+        d.cg2_mode = (P->cfg.reserved[0] >> 3) & 1;
         d.N = N;
         d.out = y.p;
         d.epi = epi;
@@ -1144,6 +1145,7 @@ int hd_op_conv2d(const uint16_t* x0, int32_t C0, const uint16_t* x1, int32_t C1,
     d.B = B; d.H = H; d.W = W; d.ksize = ksize; d.mode = static_cast<ConvMode>(mode);
     d.weight = q; d.N = Cout; d.out = reinterpret_cast<bf16*>(out);
     d.pad_mode = (standardize >> 1) & 3;   // bits 1-2 of `standardize`: opt into the padded-slab conv form (parity tests)
+    d.cg2_mode = (standardize >> 3) & 1;   // bit 3: run on CTA pairs (tcgen05 cta_group::2)
     d.epi.bias = bias;
     if (res) { d.epi.res = reinterpret_cast<const bf16*>(res); d.epi.ldr = Cout; }
     ConvGemmLaunch l;

@@ -127,6 +127,26 @@ def test_conv_gemm_padded_slab(B, H, C0, C1):
     assert (out.float() - same.float()).abs().max().item() <= 2e-2 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("B,H,C0,C1,Cout,k", [(2, 64, 64, 0, 64, 3), (3, 32, 128, 64, 128, 3), (3, 8, 512, 256, 512, 3), (2, 16, 256, 0, 256, 3),
+                                               (2, 64, 64, 0, 384, 1), (1, 8, 256, 0, 512, 3)])
+def test_conv_gemm_cta_pairs(B, H, C0, C1, Cout, k):
+    """Opt-in CTA-pair form (cluster of 2, tcgen05.mma.cta_group::2): M = 256 tile pairs, each CTA loads its 128 rows of A and
+    half of the weight rows, TMA completions land on the leader's barriers, commits are multicast.  Includes an odd number of
+    M tiles (phantom tile in the last pair) and the resident / slab / general kinds."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(777 + B + H + C0 + Cout)
+    x0 = _rand_nhwc(B, H, H, C0, g)
+    x1 = _rand_nhwc(B, H, H, C1, g) if C1 else None
+    Cin = C0 + C1
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)).to(DEV)
+    bias = (torch.randn(Cout, generator=g) * 0.1).to(DEV)
+    out = ops.conv2d_nhwc(x0, w, bias, x1=x1, cta_pairs=True)
+    torch.cuda.synchronize()
+    xin = _nchw64(x0) if x1 is None else torch.cat((_nchw64(x0), _nchw64(x1)), dim=1)
+    ref = F.conv2d(xin, _bf16_round(w), bias.to(torch.float64), padding=k // 2)
+    _check(out, ref, f"cta-pair conv {Cin}->{Cout} k{k} @{H}")
+
+
 def test_conv_gemm_residual_epilogue():
     ops = _ops()
     g = torch.Generator().manual_seed(7)
