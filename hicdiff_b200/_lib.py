@@ -46,6 +46,7 @@ SIGNATURES = {
     "hd_sample": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _u64, _u64, _i32, _i32, _vp]),
     "hd_ddrm_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                C.c_float, _i64, _u64, _u64, C.c_uint32, _vp]),
+    "hd_ssim_mse_tiles": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "hd_tile_count": (_i64, [_i64, _i32, _i32]),
     "hd_tile_extract": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp]),
     "hd_tile_scatter": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),

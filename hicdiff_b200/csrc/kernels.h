@@ -278,4 +278,10 @@ cudaError_t tile_extract_run(const float* mat, int n, float* tiles, int piece, i
 cudaError_t tile_scatter_run(const float* tiles, float* mat, int n, int piece, int band_blocks, cudaStream_t s);
 int tile_count(int n, int piece, int band_blocks);
 
+// ---------------------------------------------------------------------------------------------
+// metrics.cu -- per-tile SSIM (reference window, zero padding) and MSE of 64x64 tiles
+// ---------------------------------------------------------------------------------------------
+cudaError_t ssim_mse_tiles_run(const float* a, const float* b, const float* window, float* ssim_out, float* mse_out, int B,
+                               int rescale, cudaStream_t s);
+
 }  // namespace hd

@@ -40,6 +40,7 @@ __device__ __forceinline__ float silu_f(float v) {
 // order -> every CTA derives bit-identical statistics), and keeps the next slab's loads in flight while it normalises /
 // modulates / activates the current one.  (The one-CTA-per-64-KiB version paid the statistics prologue and a partial
 // last wave on every launch: 3.9 TB/s at batch 256.)
+template <bool HAS_RES, bool HAS_POST>   // compile out the residual stream and the SR3 post-add where a launch has none (issue-bound kernel)
 __global__ void __launch_bounds__(GN_THREADS, 2)
 groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int total_slabs, const int slabs_per_cta) {
     __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
@@ -51,7 +52,7 @@ groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int
     const int chunks_per_pixel = a.C / 8;
     const int cpg = a.C / GN_GROUPS;
     const uint4* xin = reinterpret_cast<const uint4*>(a.x);
-    const uint4* rin = a.res != nullptr ? reinterpret_cast<const uint4*>(a.res) : nullptr;
+    const uint4* rin = HAS_RES ? reinterpret_cast<const uint4*>(a.res) : nullptr;
     uint4* yout = reinterpret_cast<uint4*>(a.y);
     const int my_cp = tid % chunks_per_pixel;                // fixed per thread: GN_THREADS % chunks_per_pixel == 0
     const int my_c = my_cp * 8;
@@ -63,7 +64,7 @@ groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int
 #pragma unroll
         for (int k = 0; k < GN_CHUNKS_PER_THREAD; ++k) {
             uu[k] = __ldg(xin + base + k * GN_THREADS);
-            rr[k] = rin != nullptr ? __ldg(rin + base + k * GN_THREADS) : make_uint4(0, 0, 0, 0);
+            if constexpr (HAS_RES) rr[k] = __ldg(rin + base + k * GN_THREADS);
         }
     };
     load_slab(s0, u, r);                                     // in flight before the first statistics merge
@@ -190,11 +191,16 @@ groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int
             t = ptx::unpack_bf16x2(u[k].z); v[4] = t.x; v[5] = t.y;
             t = ptx::unpack_bf16x2(u[k].w); v[6] = t.x; v[7] = t.y;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = silu_f(fmaf(v[j], mul[j], add[j])) + post[j];
-            t = ptx::unpack_bf16x2(r[k].x); v[0] += t.x; v[1] += t.y;
-            t = ptx::unpack_bf16x2(r[k].y); v[2] += t.x; v[3] += t.y;
-            t = ptx::unpack_bf16x2(r[k].z); v[4] += t.x; v[5] += t.y;
-            t = ptx::unpack_bf16x2(r[k].w); v[6] += t.x; v[7] += t.y;
+            for (int j = 0; j < 8; ++j) {
+                v[j] = silu_f(fmaf(v[j], mul[j], add[j]));
+                if constexpr (HAS_POST) v[j] += post[j];
+            }
+            if constexpr (HAS_RES) {
+                t = ptx::unpack_bf16x2(r[k].x); v[0] += t.x; v[1] += t.y;
+                t = ptx::unpack_bf16x2(r[k].y); v[2] += t.x; v[3] += t.y;
+                t = ptx::unpack_bf16x2(r[k].z); v[4] += t.x; v[5] += t.y;
+                t = ptx::unpack_bf16x2(r[k].w); v[6] += t.x; v[7] += t.y;
+            }
             uint4 o;
             o.x = ptx::pack_bf16x2(v[0], v[1]);
             o.y = ptx::pack_bf16x2(v[2], v[3]);
@@ -204,7 +210,10 @@ groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int
         }
         if (s + 1 < s1) {
 #pragma unroll
-            for (int k = 0; k < GN_CHUNKS_PER_THREAD; ++k) { u[k] = un[k]; r[k] = rn[k]; }
+            for (int k = 0; k < GN_CHUNKS_PER_THREAD; ++k) {
+                u[k] = un[k];
+                if constexpr (HAS_RES) r[k] = rn[k];
+            }
         }
     }
 }
@@ -365,7 +374,11 @@ cudaError_t groupnorm_film_silu_run(const GroupNormArgs& a, cudaStream_t s) {
     if (grid > total) grid = total;
     const int per_cta = (total + grid - 1) / grid;
     grid = (total + per_cta - 1) / per_cta;
-    groupnorm_apply_kernel<<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
+    const bool res = a.res != nullptr, post = a.postadd != nullptr;
+    if (res && post) groupnorm_apply_kernel<true, true><<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
+    else if (res) groupnorm_apply_kernel<true, false><<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
+    else if (post) groupnorm_apply_kernel<false, true><<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
+    else groupnorm_apply_kernel<false, false><<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
     return cudaGetLastError();
 }
 

@@ -1100,6 +1100,15 @@ int hd_ddrm_step(float* x, const float* eps, const float* y, const float* noise,
     return 0;
 }
 
+int hd_ssim_mse_tiles(const float* a, const float* b, const float* window121, float* ssim_out, float* mse_out, int32_t B,
+                      int32_t rescale, void* stream) {
+    if (B < 0) return fail("hd_ssim_mse_tiles: negative tile count");
+    if (B == 0) return 0;
+    if (!a || !b || !window121 || !ssim_out || !mse_out) return fail("hd_ssim_mse_tiles: null argument");
+    CUDA_TRY(ssim_mse_tiles_run(a, b, window121, ssim_out, mse_out, B, rescale, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
 int64_t hd_tile_count(int64_t n, int32_t piece, int32_t band_blocks) {
     if (n < 0 || piece <= 0 || band_blocks < 0) return -1;
     return tile_count(static_cast<int>(n), piece, band_blocks);

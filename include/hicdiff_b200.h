@@ -114,6 +114,13 @@ HD_API int hd_ddrm_step(float* x, const float* eps, const float* y, const float*
                  float sqrt_1m_at, float sqrt_at_next, float c0, float c1, float c2, float sigma_0, int64_t n, uint64_t seed,
                  uint64_t tile_offset, uint32_t step_id, void* stream);
 
+/* Per-tile SSIM and MSE of fp32 [B,1,64,64] tiles: _ssim of src/Utils/loss/SSIM.py:17-36 with the caller's 11x11 window
+ * (create_window :10-14, 121 floats on the device) and zero "same" padding; rescale = 1 first applies
+ * inverse_data_transform('rescaled') (src/datasets/__init__.py:214-223).  ssim_out / mse_out: fp32 [B] on the device; the
+ * reference's scalar SSIM is their mean, its PSNR 10 log10(1 / mean(mse_out)). */
+HD_API int hd_ssim_mse_tiles(const float* a, const float* b, const float* window121, float* ssim_out, float* mse_out, int32_t B,
+                      int32_t rescale, void* stream);
+
 /* -------------------------------------------------------------------------------------------------------------
  * Tiling.  hd_tile_extract replaces splitPieces (processdata/PrepareData_linear.py:25-46): zero-pad the n x n
  * matrix to a multiple of `piece`, enumerate block rows i and block columns j >= i with (j - i) <= band_blocks
