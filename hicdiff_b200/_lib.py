@@ -47,6 +47,16 @@ SIGNATURES = {
     "hd_ddrm_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                C.c_float, _i64, _u64, _u64, C.c_uint32, _vp]),
     "hd_ssim_mse_tiles": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "hd_trainer_create": (C.c_int, [C.POINTER(hd_config), _i32, C.POINTER(_vp)]),
+    "hd_trainer_bind": (C.c_int, [_vp, C.c_char_p, _vp, _vp, C.POINTER(_i64), _i32]),
+    "hd_trainer_finalize": (C.c_int, [_vp, _vp]),
+    "hd_trainer_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "hd_trainer_num_launches": (C.c_int, [_vp]),
+    "hd_trainer_profile": (C.c_int, [_vp, _i32, C.c_char_p, _i64, _vp]),
+    "hd_trainer_device_bytes": (_i64, [_vp]),
+    "hd_trainer_destroy": (None, [_vp]),
+    "hd_op_conv3x3_wgrad": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
+    "hd_op_conv3x3_dgrad": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "hd_tile_count": (_i64, [_i64, _i32, _i32]),
     "hd_tile_extract": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp]),
     "hd_tile_scatter": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),

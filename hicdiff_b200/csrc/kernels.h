@@ -265,7 +265,7 @@ cudaError_t prep_unshuffle_weight_run(const float* w, bf16* out, int Cout, int C
 // over the low-resolution input (taps that land on the same low-res pixel are summed in fp32)
 cudaError_t prep_upsample_weight_run(const float* w, bf16* out, int Cout, int Cin, cudaStream_t s);
 
-// y[r, ldy*r + off + j] = bias[j] + sum_k act(x[r, k]) * W[j, k];  act: 0 none, 1 SiLU (on input), out_act: 0 none, 1 GELU(erf)
+// y[r, ldy*r + off + j] = bias[j] + sum_k act(x[r, k]) * W[j, k];  in_act: 0 none, 1 SiLU, 2 GELU(erf) (on the input), out_act: 0 none, 1 GELU(erf)
 cudaError_t linear_rows_run(const float* x, int ldx, const float* W, const float* bias, float* y, int ldy, int off,
                             int rows, int in_f, int out_f, int in_act, int out_act, cudaStream_t s);
 // mode 0: SinusoidalPosEmb(dim) of integer timesteps t[r] (as float); mode 1: SR3 PositionalEncoding of level[r]
@@ -283,5 +283,48 @@ int tile_count(int n, int piece, int band_blocks);
 // ---------------------------------------------------------------------------------------------
 cudaError_t ssim_mse_tiles_run(const float* a, const float* b, const float* window, float* ssim_out, float* mse_out, int B,
                                int rescale, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// wgrad.cu / train_kernels.cu -- the HiCEDRN training step (backward of conv / FiLM / SiLU / time MLPs, loss)
+// ---------------------------------------------------------------------------------------------
+struct WgradLaunch {
+    CUtensorMap tmG, tmX[3];   // planar [B, C, H, W] bf16 copies of dY and of the conv input pre-shifted by dx = -1, 0, +1
+    int kb_total, H, nsplit;
+    float* part;            // [nsplit][9][256][256] fp32
+};
+int wgrad_prepare(const bf16* g_planar, const bf16* x_planar3, int B, int H, int W, int C, int nsplit, float* part,
+                  WgradLaunch* out, char* err, int errlen);
+cudaError_t wgrad_run(const WgradLaunch& l, cudaStream_t s);
+// dW [256, 256, 3, 3] (+)= scale * sum over the K splits
+cudaError_t wgrad_reduce_run(const float* part, int nsplit, float scale, int accumulate, float* dw, cudaStream_t s);
+size_t wgrad_part_bytes(int nsplit);
+
+cudaError_t prep_dgrad_weight_run(const float* w, bf16* out, int Cout, int Cin, cudaStream_t s);
+cudaError_t flip_tail_weight_run(const float* w, float* out, int C, cudaStream_t s);
+cudaError_t film_silu_fwd_run(const bf16* a, bf16* sout, const float* film, int ld, int off, int B, int P, int C, cudaStream_t s);
+int film_bwd_part_floats(int B, int C);
+// da (may alias ds) = ds * SiLU'(a * (scale + 1) + shift) * (scale + 1); dfilm[b, off + c] = d scale, [off + C + c] = d shift
+cudaError_t film_silu_bwd_run(const bf16* ds, const bf16* a, bf16* da, const float* film, float* dfilm, int ld, int off, int B,
+                              int P, int C, float* part, cudaStream_t s);
+cudaError_t edrn_bias_grad_run(const float* film, const float* dfilm, int ld, int off, int B, const float* colsum_g, float g_scale,
+                               float* dbias, int C, cudaStream_t s);
+int colsum_parts(long long M);
+// out[c] (+)= scale * sum_m x[m, c]
+cudaError_t colsum_run(const bf16* x, long long M, int C, float* part, float scale, int accumulate, float* out, cudaStream_t s);
+cudaError_t sum_parts_run(const float* part, int nparts, int n, float scale, int accumulate, float* out, cudaStream_t s);
+// shifts == 3: three copies out[sh][B][C][P], copy sh holds the image shifted by dx = sh - 1 along x (zero fill); W must be 64
+cudaError_t nhwc_to_planar_run(const bf16* in, bf16* out, int B, int P, int C, int shifts, cudaStream_t s);
+cudaError_t add_bf16_run(const bf16* a, const bf16* b, bf16* y, long long n, cudaStream_t s);
+// dw[(c * nk + k) * 9 + tap] = sum_{b,y,x} G[b,y,x,c] * u_k[b, y + sgn*(ky-1), x + sgn*(kx-1)];  part: [B * 8][nk][9][256]
+cudaError_t thin_wgrad_run(const bf16* G, const float* u0, const float* u1, int sgn, int B, float* part, float* dw, cudaStream_t s);
+int loss_parts();
+cudaError_t loss_grad_run(const float* eps, const float* target, const float* w, int loss_type, int B, int tile_elems, float* d_eps,
+                          float* part, float* loss, cudaStream_t s);
+cudaError_t sum_f32_run(const float* x, long long n, float* part, float* out, cudaStream_t s);
+cudaError_t linear_bwd_weight_run(const float* dY, int ldy, int off, const float* X, int ldx, int rows, int in_f, int out_f,
+                                  int in_act, float* dW, float* db, cudaStream_t s);
+cudaError_t linear_bwd_input_run(const float* dY, int ldy, int off, const float* W, int rows, int in_f, int out_f, int accumulate,
+                                 float* dX, int ldx, cudaStream_t s);
+cudaError_t act_grad_run(float* d, const float* x, long long n, int act, cudaStream_t s);
 
 }  // namespace hd

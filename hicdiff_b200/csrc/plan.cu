@@ -782,6 +782,10 @@ int set_ctl(SampleCtl* dev, int step, int single, const float* noise, uint64_t s
 
 }  // namespace
 
+namespace hd {
+int set_error(const char* msg) { g_err = msg ? msg : ""; return 1; }   // trainer.cu reports through the same hd_last_error()
+}
+
 // ================================================================================================= C ABI
 extern "C" {
 

@@ -141,6 +141,7 @@ linear_rows_kernel(const float* __restrict__ x, int ldx, const float* __restrict
     for (int k = lane; k < in_f; k += 32) {
         float xv = xr[k];
         if (in_act == 1) xv = xv / (1.0f + expf(-xv));
+        else if (in_act == 2) xv = 0.5f * xv * (1.0f + erff(xv * 0.70710678118654752440f));
         acc = fmaf(xv, wr[k], acc);
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);

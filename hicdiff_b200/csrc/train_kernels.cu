@@ -1,0 +1,481 @@
+// Bandwidth-bound kernels of the HiCEDRN training step (train.py:109-136 trains hicedrn_Diff through
+// GaussianDiffusion.p_losses, hicdiff_condition.py:715-746).  The convolutions run on conv_gemm.cu (forward and dgrad) and
+// wgrad.cu; everything around them is here:
+//
+//   prep_dgrad_weight   [Cout, Cin, 3, 3] fp32 -> [Cin, (tap', cout)] bf16 with tap' = 8 - tap: the data gradient of a 3x3
+//                       "same" conv is the same implicit GEMM over the flipped, transposed filter
+//   film_silu_fwd       s = SiLU(a * (scale + 1) + shift)                  hicedrn_Diff.py:175-178,201-203
+//   film_silu_bwd       da = ds * SiLU'(h) * (scale + 1), per-(sample, channel) sums for d scale / d shift
+//   colsum              per-channel sums over all pixels (bias gradients)
+//   nhwc_to_planar      [B, P, C] -> [B, C, P] (the K-major operand layout of wgrad.cu)
+//   thin_wgrad          weight gradient of the 1- or 2-plane head conv / the 1-channel tail conv
+//   loss_grad           weighted l1 / l2 loss and its gradient             hicdiff_condition.py:706-713,741-746
+//   linear_bwd_*        the time-embedding MLPs (a few rows; fp32)         hicedrn_Diff.py:232-246,189-200
+// All reductions are two-pass with a fixed order (no atomics): gradients are bit-reproducible run to run.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace hd {
+namespace {
+
+__device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + __expf(-v)); }
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+    float2 t;
+    t = ptx::unpack_bf16x2(u.x); v[0] = t.x; v[1] = t.y;
+    t = ptx::unpack_bf16x2(u.y); v[2] = t.x; v[3] = t.y;
+    t = ptx::unpack_bf16x2(u.z); v[4] = t.x; v[5] = t.y;
+    t = ptx::unpack_bf16x2(u.w); v[6] = t.x; v[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+    uint4 o;
+    o.x = ptx::pack_bf16x2(v[0], v[1]);
+    o.y = ptx::pack_bf16x2(v[2], v[3]);
+    o.z = ptx::pack_bf16x2(v[4], v[5]);
+    o.w = ptx::pack_bf16x2(v[6], v[7]);
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+__global__ void __launch_bounds__(256)
+prep_dgrad_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin) {
+    const int ci = blockIdx.x;
+    bf16* orow = out + static_cast<size_t>(ci) * 9 * Cout;
+    for (int i = threadIdx.x; i < 9 * Cout; i += blockDim.x) {
+        const int tapp = i / Cout, co = i - tapp * Cout;
+        orow[i] = __float2bfloat16(w[(static_cast<size_t>(co) * Cin + ci) * 9 + (8 - tapp)]);
+    }
+}
+
+// tail conv [1, C, 3, 3] -> the [C, 1, 3, 3] filter whose forward conv over d_eps is the tail's data gradient
+__global__ void flip_tail_weight_kernel(const float* __restrict__ w, float* __restrict__ out, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < C * 9) {
+        const int c = i / 9, t = i - c * 9;
+        out[i] = w[c * 9 + (8 - t)];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ FiLM + SiLU
+__global__ void __launch_bounds__(256)
+film_silu_fwd_kernel(const uint4* __restrict__ a, uint4* __restrict__ s, const float* __restrict__ film, int ld, int off,
+                     int P, int C, long long total_chunks) {
+    const int cpp = C / 8;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total_chunks; i += gridDim.x * 256ll) {
+        const int cc = static_cast<int>(i % cpp);
+        const long long pix = i / cpp;
+        const int b = static_cast<int>(pix / P);
+        const float* row = film + static_cast<size_t>(b) * ld + off + cc * 8;
+        float v[8];
+        unpack8(__ldg(a + i), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float h = fmaf(v[j], __ldg(row + j) + 1.0f, __ldg(row + C + j));
+            v[j] = h * sigmoid_f(h);
+        }
+        s[i] = pack8(v);
+    }
+}
+
+constexpr int FB_CHUNKS = 16;   // pixel chunks per image in the backward reduction (P = 4096 -> 256 pixels per CTA)
+
+// grid (FB_CHUNKS, B), C == 256: thread = (8-channel chunk cc = tid % 32, pixel lane pl = tid / 32)
+__global__ void __launch_bounds__(256)
+film_silu_bwd_kernel(const uint4* __restrict__ ds, const uint4* __restrict__ a, uint4* __restrict__ da,
+                     const float* __restrict__ film, int ld, int off, int P, float* __restrict__ part) {
+    constexpr int C = 256, CPP = C / 8;
+    __shared__ float s_red[8][2 * C];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int cc = threadIdx.x & 31, pl = threadIdx.x >> 5;
+    const int ppc = P / FB_CHUNKS;
+    const float* row = film + static_cast<size_t>(b) * ld + off + cc * 8;
+    float sc1[8], sh[8], acc_sc[8], acc_sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc1[j] = __ldg(row + j) + 1.0f; sh[j] = __ldg(row + C + j); acc_sc[j] = 0.f; acc_sh[j] = 0.f; }
+    const size_t base = (static_cast<size_t>(b) * P + static_cast<size_t>(chunk) * ppc) * CPP + cc;
+    for (int p = pl; p < ppc; p += 8) {
+        const size_t i = base + static_cast<size_t>(p) * CPP;
+        float g[8], av[8];
+        unpack8(__ldg(ds + i), g);
+        unpack8(__ldg(a + i), av);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float h = fmaf(av[j], sc1[j], sh[j]);
+            const float sg = sigmoid_f(h);
+            const float dh = g[j] * (sg * (1.0f + h * (1.0f - sg)));
+            acc_sc[j] = fmaf(dh, av[j], acc_sc[j]);
+            acc_sh[j] += dh;
+            g[j] = dh * sc1[j];
+        }
+        da[i] = pack8(g);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s_red[pl][cc * 8 + j] = acc_sc[j]; s_red[pl][C + cc * 8 + j] = acc_sh[j]; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += 256) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += s_red[k][i];
+        part[(static_cast<size_t>(b) * FB_CHUNKS + chunk) * 2 * C + i] = t;
+    }
+}
+
+// dfilm[b, off + i] = sum over the chunks (i < 2C: d scale then d shift); grid B, 2C threads
+__global__ void film_grad_finish_kernel(const float* __restrict__ part, float* __restrict__ dfilm, int ld, int off, int C) {
+    const int b = blockIdx.x, i = threadIdx.x;
+    float t = 0.f;
+    for (int k = 0; k < FB_CHUNKS; ++k) t += part[(static_cast<size_t>(b) * FB_CHUNKS + k) * 2 * C + i];
+    dfilm[static_cast<size_t>(b) * ld + off + i] = t;
+}
+
+// the shared conv's bias gradient: its first use contributes sum_b (scale + 1) * dshift (da = dh * (scale + 1)), its second
+// 0.1 * colsum(g)
+__global__ void edrn_bias_grad_kernel(const float* __restrict__ film, const float* __restrict__ dfilm, int ld, int off, int B,
+                                      const float* __restrict__ colsum_g, float g_scale, float* __restrict__ dbias, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float t = 0.f;
+    for (int b = 0; b < B; ++b)
+        t = fmaf(film[static_cast<size_t>(b) * ld + off + c] + 1.0f, dfilm[static_cast<size_t>(b) * ld + off + C + c], t);
+    dbias[c] = t + g_scale * colsum_g[c];
+}
+
+// ------------------------------------------------------------------------------------------------ column sums
+// x [M, C] bf16, C/8 divides 256.  Block k sums rows [k * rpb, (k + 1) * rpb) -> part[k][C]
+__global__ void __launch_bounds__(256)
+colsum_part_kernel(const uint4* __restrict__ x, float* __restrict__ part, long long M, int C, int rpb) {
+    extern __shared__ float cs_red[];   // [lanes][C]
+    const int cpp = C / 8;
+    const int lanes = 256 / cpp;
+    const int cc = threadIdx.x % cpp, pl = threadIdx.x / cpp;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const long long r0 = static_cast<long long>(blockIdx.x) * rpb;
+    const long long r1 = r0 + rpb < M ? r0 + rpb : M;
+    for (long long r = r0 + pl; r < r1; r += lanes) {
+        float v[8];
+        unpack8(__ldg(x + r * cpp + cc), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs_red[pl * C + cc * 8 + j] = acc[j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += 256) {
+        float t = 0.f;
+        for (int k = 0; k < lanes; ++k) t += cs_red[k * C + i];
+        part[static_cast<size_t>(blockIdx.x) * C + i] = t;
+    }
+}
+
+// out[i] = scale * sum_k part[k][i] (+ out[i] when accumulate); n columns
+__global__ void sum_parts_kernel(const float* __restrict__ part, int nparts, int n, float scale, int accumulate,
+                                 float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float t = 0.f;
+    for (int k = 0; k < nparts; ++k) t += part[static_cast<size_t>(k) * n + i];
+    out[i] = accumulate ? fmaf(scale, t, out[i]) : scale * t;
+}
+
+// ------------------------------------------------------------------------------------------------ layout
+// [B, P, C] -> [B, C, P], 64 x 64 tiles through shared memory; grid (P/64, C/64, B).  A tile is one 64-pixel image row, so
+// shifts == 3 can also emit the row shifted by dx = -1 / 0 / +1 pixels with zero fill (copy stride B * C * P elements).
+__global__ void __launch_bounds__(256)
+nhwc_to_planar_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int P, int C, int shifts, size_t copy_stride) {
+    __shared__ bf16 t[64][72];
+    const int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64, b = blockIdx.z;
+    const bf16* src = in + (static_cast<size_t>(b) * P + p0) * C + c0;
+    for (int i = threadIdx.x; i < 512; i += 256) {
+        const int p = i >> 3, ch = i & 7;
+        *reinterpret_cast<uint4*>(&t[p][ch * 8]) = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(p) * C + ch * 8));
+    }
+    __syncthreads();
+    for (int sh = 0; sh < shifts; ++sh) {
+        const int dx = shifts == 3 ? sh - 1 : 0;
+        bf16* dst = out + sh * copy_stride + (static_cast<size_t>(b) * C + c0) * P + p0;
+        for (int i = threadIdx.x; i < 512; i += 256) {
+            const int c = i & 63, pc = i >> 6;
+            __align__(16) bf16 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int px = pc * 8 + j + dx;
+                v[j] = (px >= 0 && px < 64) ? t[px][c] : __float2bfloat16(0.f);
+            }
+            *reinterpret_cast<uint4*>(dst + static_cast<size_t>(c) * P + pc * 8) = *reinterpret_cast<const uint4*>(v);
+        }
+    }
+}
+
+// y = a + b (bf16, 16-byte chunks)
+__global__ void __launch_bounds__(256)
+add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ y, long long chunks) {
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < chunks; i += gridDim.x * 256ll) {
+        float x[8], z[8];
+        unpack8(__ldg(a + i), x);
+        unpack8(__ldg(b + i), z);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += z[j];
+        y[i] = pack8(x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ thin wgrad
+// part[(b * 8 + rg)][k][tap][c] = sum over the 8 rows of row group rg of G[b, y, x, c] * u_k[b, y + sgn*(ky-1), x + sgn*(kx-1)]
+// G [B, 64, 64, 256] bf16, u_k fp32 planes [B, 64, 64]; grid (8, B), 256 threads = channels.
+__global__ void __launch_bounds__(256)
+thin_wgrad_kernel(const bf16* __restrict__ G, const float* __restrict__ u0, const float* __restrict__ u1, int sgn,
+                  float* __restrict__ part) {
+    constexpr int C = 256, W = 64, H = 64, ROWS = 8, PITCH = 66;
+    __shared__ float s_u[2][ROWS + 2][PITCH];
+    const int rg = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
+    const int nk = u1 != nullptr ? 2 : 1;
+    const int y0 = rg * ROWS;
+    for (int i = threadIdx.x; i < nk * (ROWS + 2) * PITCH; i += 256) {
+        const int k = i / ((ROWS + 2) * PITCH);
+        const int rem = i - k * (ROWS + 2) * PITCH;
+        const int yy = rem / PITCH + y0 - 1, xx = rem % PITCH - 1;
+        const float* u = k == 0 ? u0 : u1;
+        s_u[k][rem / PITCH][rem % PITCH] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(u + (static_cast<size_t>(b) * H + yy) * W + xx) : 0.f;
+    }
+    __syncthreads();
+    float acc[2][9];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[k][t] = 0.f;
+    const bf16* g = G + ((static_cast<size_t>(b) * H + y0) * W) * C + c;
+    for (int yl = 0; yl < ROWS; ++yl) {
+        for (int x = 0; x < W; ++x) {
+            const float gv = __bfloat162float(g[(static_cast<size_t>(yl) * W + x) * C]);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (k < nk) {
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const int dy = sgn * (t / 3 - 1), dx = sgn * (t % 3 - 1);
+                        acc[k][t] = fmaf(gv, s_u[k][yl + 1 + dy][x + 1 + dx], acc[k][t]);
+                    }
+                }
+            }
+        }
+    }
+    float* o = part + (static_cast<size_t>(b) * 8 + rg) * nk * 9 * C;
+    for (int k = 0; k < nk; ++k)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) o[(k * 9 + t) * C + c] = acc[k][t];
+}
+
+// dW[(c * nk + k) * 9 + tap] = sum_parts part[.][k][tap][c]
+__global__ void thin_wgrad_finish_kernel(const float* __restrict__ part, int nparts, int nk, float* __restrict__ dw) {
+    constexpr int C = 256;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;    // index into [k][tap][c]
+    if (i >= nk * 9 * C) return;
+    float t = 0.f;
+    for (int p = 0; p < nparts; ++p) t += part[static_cast<size_t>(p) * nk * 9 * C + i];
+    const int c = i % C, kt = i / C, k = kt / 9, tap = kt - k * 9;
+    dw[(c * nk + k) * 9 + tap] = t;
+}
+
+// ------------------------------------------------------------------------------------------------ loss
+// loss_type 0: l1, 1: l2.  part[blk] = sum over the block's elements of |d|^p * w[b]; d_eps = dL/d eps for L = mean(...)
+__global__ void __launch_bounds__(256)
+loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ target, const float* __restrict__ w, int loss_type,
+                 long long n, int tile_elems, float* __restrict__ d_eps, float* __restrict__ part) {
+    __shared__ float s_red[8];
+    const float inv_n = 1.0f / static_cast<float>(n);
+    float acc = 0.f;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) {
+        const float wb = __ldg(w + i / tile_elems);
+        const float d = eps[i] - target[i];
+        if (loss_type == 1) {
+            acc = fmaf(d * d, wb, acc);
+            d_eps[i] = 2.0f * d * wb * inv_n;
+        } else {
+            acc = fmaf(fabsf(d), wb, acc);
+            d_eps[i] = (d > 0.f ? 1.0f : (d < 0.f ? -1.0f : 0.f)) * wb * inv_n;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int k = 0; k < 8; ++k) t += s_red[k];
+        part[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sum_f32_part_kernel(const float* __restrict__ x, long long n, float* __restrict__ part) {
+    __shared__ float s_red[8];
+    float acc = 0.f;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) acc += x[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int k = 0; k < 8; ++k) t += s_red[k];
+        part[blockIdx.x] = t;
+    }
+}
+
+__global__ void sum_scalar_kernel(const float* __restrict__ part, int nparts, float scale, float* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < nparts; ++k) t += part[k];
+        out[0] = static_cast<float>(t * scale);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ small linears
+__device__ __forceinline__ float act_f(float v, int act) {
+    if (act == 1) return v * sigmoid_f(v);
+    if (act == 2) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+    return v;
+}
+__device__ __forceinline__ float act_grad_f(float v, int act) {
+    if (act == 1) { const float s = 1.0f / (1.0f + expf(-v)); return s * (1.0f + v * (1.0f - s)); }
+    if (act == 2) return 0.5f * (1.0f + erff(v * 0.70710678118654752440f)) + v * 0.3989422804014327f * expf(-0.5f * v * v);
+    return 1.0f;
+}
+
+// dW[j, k] = sum_r dY[r, off + j] * act(X[r, k]);  db[j] = sum_r dY[r, off + j].  grid (ceil(in_f / 256), out_f)
+__global__ void __launch_bounds__(256)
+linear_bwd_weight_kernel(const float* __restrict__ dY, int ldy, int off, const float* __restrict__ X, int ldx, int rows,
+                         int in_f, int in_act, float* __restrict__ dW, float* __restrict__ db) {
+    const int j = blockIdx.y;
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    float acc = 0.f, accb = 0.f;
+    for (int r = 0; r < rows; ++r) {
+        const float g = __ldg(dY + static_cast<size_t>(r) * ldy + off + j);
+        accb += g;
+        if (k < in_f) acc = fmaf(g, act_f(__ldg(X + static_cast<size_t>(r) * ldx + k), in_act), acc);
+    }
+    if (k < in_f) dW[static_cast<size_t>(j) * in_f + k] = acc;
+    if (k == 0 && db != nullptr) db[j] = accb;
+}
+
+// dX[r, k] (+)= sum_j dY[r, off + j] * W[j, k].  grid (ceil(in_f / 256), rows)
+__global__ void __launch_bounds__(256)
+linear_bwd_input_kernel(const float* __restrict__ dY, int ldy, int off, const float* __restrict__ W, int out_f, int in_f,
+                        int accumulate, float* __restrict__ dX, int ldx) {
+    const int r = blockIdx.y;
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= in_f) return;
+    float acc = 0.f;
+    for (int j = 0; j < out_f; ++j) acc = fmaf(__ldg(dY + static_cast<size_t>(r) * ldy + off + j), __ldg(W + static_cast<size_t>(j) * in_f + k), acc);
+    float* o = dX + static_cast<size_t>(r) * ldx + k;
+    *o = accumulate ? *o + acc : acc;
+}
+
+// d[i] *= act'(x[i])
+__global__ void act_grad_kernel(float* __restrict__ d, const float* __restrict__ x, long long n, int act) {
+    const long long i = blockIdx.x * 256ll + threadIdx.x;
+    if (i < n) d[i] *= act_grad_f(x[i], act);
+}
+
+}  // namespace
+
+// ================================================================================================ launchers
+cudaError_t prep_dgrad_weight_run(const float* w, bf16* out, int Cout, int Cin, cudaStream_t s) {
+    prep_dgrad_weight_kernel<<<Cin, 256, 0, s>>>(w, out, Cout, Cin);
+    return cudaGetLastError();
+}
+cudaError_t flip_tail_weight_run(const float* w, float* out, int C, cudaStream_t s) {
+    flip_tail_weight_kernel<<<(C * 9 + 255) / 256, 256, 0, s>>>(w, out, C);
+    return cudaGetLastError();
+}
+cudaError_t film_silu_fwd_run(const bf16* a, bf16* sout, const float* film, int ld, int off, int B, int P, int C, cudaStream_t s) {
+    const long long chunks = static_cast<long long>(B) * P * C / 8;
+    const int grid = static_cast<int>(chunks / 256 < 148 * 16 ? (chunks + 255) / 256 : 148 * 16);
+    film_silu_fwd_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<uint4*>(sout), film, ld, off, P, C, chunks);
+    return cudaGetLastError();
+}
+int film_bwd_part_floats(int B, int C) { return B * FB_CHUNKS * 2 * C; }
+cudaError_t film_silu_bwd_run(const bf16* ds, const bf16* a, bf16* da, const float* film, float* dfilm, int ld, int off, int B,
+                              int P, int C, float* part, cudaStream_t s) {
+    if (C != 256 || P % (FB_CHUNKS * 8) != 0) return cudaErrorInvalidValue;
+    film_silu_bwd_kernel<<<dim3(FB_CHUNKS, B), 256, 0, s>>>(reinterpret_cast<const uint4*>(ds), reinterpret_cast<const uint4*>(a),
+                                                           reinterpret_cast<uint4*>(da), film, ld, off, P, part);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    film_grad_finish_kernel<<<B, 2 * C, 0, s>>>(part, dfilm, ld, off, C);
+    return cudaGetLastError();
+}
+cudaError_t edrn_bias_grad_run(const float* film, const float* dfilm, int ld, int off, int B, const float* colsum_g, float g_scale,
+                               float* dbias, int C, cudaStream_t s) {
+    edrn_bias_grad_kernel<<<(C + 255) / 256, 256, 0, s>>>(film, dfilm, ld, off, B, colsum_g, g_scale, dbias, C);
+    return cudaGetLastError();
+}
+int colsum_parts(long long M) { return static_cast<int>(M / 256 < 592 ? (M + 255) / 256 : 592); }
+cudaError_t colsum_run(const bf16* x, long long M, int C, float* part, float scale, int accumulate, float* out, cudaStream_t s) {
+    if (C % 8 != 0 || 256 % (C / 8) != 0) return cudaErrorInvalidValue;
+    const int nparts = colsum_parts(M);
+    const int rpb = static_cast<int>((M + nparts - 1) / nparts);
+    const int lanes = 256 / (C / 8);
+    colsum_part_kernel<<<nparts, 256, lanes * C * sizeof(float), s>>>(reinterpret_cast<const uint4*>(x), part, M, C, rpb);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    sum_parts_kernel<<<(C + 255) / 256, 256, 0, s>>>(part, nparts, C, scale, accumulate, out);
+    return cudaGetLastError();
+}
+cudaError_t sum_parts_run(const float* part, int nparts, int n, float scale, int accumulate, float* out, cudaStream_t s) {
+    sum_parts_kernel<<<(n + 255) / 256, 256, 0, s>>>(part, nparts, n, scale, accumulate, out);
+    return cudaGetLastError();
+}
+cudaError_t nhwc_to_planar_run(const bf16* in, bf16* out, int B, int P, int C, int shifts, cudaStream_t s) {
+    if (P % 64 != 0 || C % 64 != 0 || (shifts != 1 && shifts != 3)) return cudaErrorInvalidValue;
+    nhwc_to_planar_kernel<<<dim3(P / 64, C / 64, B), 256, 0, s>>>(in, out, P, C, shifts, static_cast<size_t>(B) * C * P);
+    return cudaGetLastError();
+}
+cudaError_t add_bf16_run(const bf16* a, const bf16* b, bf16* y, long long n, cudaStream_t s) {
+    const long long chunks = n / 8;
+    const int grid = static_cast<int>(chunks / 256 < 148 * 16 ? (chunks + 255) / 256 : 148 * 16);
+    add_bf16_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b), reinterpret_cast<uint4*>(y), chunks);
+    return cudaGetLastError();
+}
+cudaError_t thin_wgrad_run(const bf16* G, const float* u0, const float* u1, int sgn, int B, float* part, float* dw, cudaStream_t s) {
+    const int nk = u1 != nullptr ? 2 : 1;
+    thin_wgrad_kernel<<<dim3(8, B), 256, 0, s>>>(G, u0, u1, sgn, part);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    thin_wgrad_finish_kernel<<<(nk * 9 * 256 + 255) / 256, 256, 0, s>>>(part, B * 8, nk, dw);
+    return cudaGetLastError();
+}
+int loss_parts() { return 592; }
+cudaError_t loss_grad_run(const float* eps, const float* target, const float* w, int loss_type, int B, int tile_elems, float* d_eps,
+                          float* part, float* loss, cudaStream_t s) {
+    const long long n = static_cast<long long>(B) * tile_elems;
+    loss_grad_kernel<<<loss_parts(), 256, 0, s>>>(eps, target, w, loss_type, n, tile_elems, d_eps, part);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    sum_scalar_kernel<<<1, 32, 0, s>>>(part, loss_parts(), 1.0f / static_cast<float>(n), loss);
+    return cudaGetLastError();
+}
+// out[0] = sum x[0..n); part: loss_parts() floats
+cudaError_t sum_f32_run(const float* x, long long n, float* part, float* out, cudaStream_t s) {
+    sum_f32_part_kernel<<<loss_parts(), 256, 0, s>>>(x, n, part);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    sum_scalar_kernel<<<1, 32, 0, s>>>(part, loss_parts(), 1.0f, out);
+    return cudaGetLastError();
+}
+cudaError_t linear_bwd_weight_run(const float* dY, int ldy, int off, const float* X, int ldx, int rows, int in_f, int out_f,
+                                  int in_act, float* dW, float* db, cudaStream_t s) {
+    linear_bwd_weight_kernel<<<dim3((in_f + 255) / 256, out_f), 256, 0, s>>>(dY, ldy, off, X, ldx, rows, in_f, in_act, dW, db);
+    return cudaGetLastError();
+}
+cudaError_t linear_bwd_input_run(const float* dY, int ldy, int off, const float* W, int rows, int in_f, int out_f, int accumulate,
+                                 float* dX, int ldx, cudaStream_t s) {
+    linear_bwd_input_kernel<<<dim3((in_f + 255) / 256, rows), 256, 0, s>>>(dY, ldy, off, W, out_f, in_f, accumulate, dX, ldx);
+    return cudaGetLastError();
+}
+cudaError_t act_grad_run(float* d, const float* x, long long n, int act, cudaStream_t s) {
+    act_grad_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(d, x, n, act);
+    return cudaGetLastError();
+}
+
+}  // namespace hd

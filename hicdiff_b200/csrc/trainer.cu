@@ -1,0 +1,539 @@
+// hd_trainer: one training step (forward, loss, backward) of GaussianDiffusion.p_losses over the hicedrn_Diff eps-net, the
+// model the reference's train.py trains (train.py:84-107 builds hicedrn_Diff + GaussianDiffusion(loss_type='l2'),
+// :109-136 runs loss = diffusion(x); loss.backward(); optimizer.step()).  Reference math:
+//   forward   hicedrn_Diff.forward              /root/reference/src/model/hicedrn_Diff.py:267-289 (ResnetBlock :194-208)
+//   loss      p_losses                          /root/reference/src/hicdiff_condition.py:715-746 (loss_fn :706-713)
+//   backward  torch.autograd over the above     (no reference source: the chain rule of the forward, restated in
+//                                                oracle/hicdiff_oracle.py::hicedrn_loss_and_grads with torch.autograd)
+// Parameters are bound by pointer (the caller's fp32 tensors are read in place every step, so a stock torch optimizer
+// keeps working) and gradients are written into caller-provided fp32 buffers.  Activations are bf16 NHWC; the convs run on
+// tcgen05 (conv_gemm.cu forward and data gradient, wgrad.cu weight gradient); statistics-free glue is in train_kernels.cu.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/hicdiff_b200.h"
+#include "kernels.h"
+
+using namespace hd;
+
+namespace hd {
+int set_error(const char* msg);   // plan.cu: fills the thread-local message behind hd_last_error()
+}
+
+namespace {
+
+int tfail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    return hd::set_error(buf);
+}
+
+#define T_TRY(expr)                                                                              \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess) return tfail("%s failed: %s", #expr, cudaGetErrorString(e__));   \
+    } while (0)
+
+struct TParam {
+    const float* w = nullptr;
+    float* g = nullptr;
+    std::vector<int64_t> shape;
+    size_t numel = 0;
+};
+
+struct TOp {
+    std::function<cudaError_t(cudaStream_t)> fn;
+    std::string tag;
+    const char* kernel = "";
+    double flops = 0;
+};
+
+constexpr int F = 256;          // n_feat
+constexpr int S = 64;           // tile edge
+constexpr int P = S * S;
+constexpr int TIME_DIM = 1024;
+constexpr int WG_SPLITS = 16;   // 9 taps x 16 K splits = 144 CTAs
+
+}  // namespace
+
+struct hd_trainer {
+    hd_config cfg;
+    int device = 0, num_sms = 148, B = 0, nb = 0;
+    bool finalized = false;
+    std::map<std::string, TParam> p;
+    std::vector<void*> allocs;
+    size_t bytes = 0;
+    std::vector<TOp> ops;
+    float *x = nullptr, *cond = nullptr, *time = nullptr, *target = nullptr, *weight = nullptr, *eps = nullptr, *d_eps = nullptr,
+          *loss = nullptr;
+    int* loss_type = nullptr;
+    int loss_kind = 1;
+};
+
+namespace {
+
+template <typename T>
+int dalloc(hd_trainer* t, T** out, size_t bytes, bool zero = false) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes ? bytes : 16);
+    if (e != cudaSuccess) return tfail("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    if (zero) cudaMemset(q, 0, bytes ? bytes : 16);
+    t->allocs.push_back(q);
+    t->bytes += bytes;
+    *out = static_cast<T*>(q);
+    return 0;
+}
+
+const TParam* find_p(const hd_trainer* t, const std::string& k, std::initializer_list<int64_t> shape) {
+    auto it = t->p.find(k);
+    if (it == t->p.end()) { tfail("parameter '%s' was not bound", k.c_str()); return nullptr; }
+    if (it->second.shape != std::vector<int64_t>(shape)) { tfail("parameter '%s' has an unexpected shape", k.c_str()); return nullptr; }
+    return &it->second;
+}
+
+struct TB {   // builder state
+    hd_trainer* t;
+    bool ok = true;
+    void push(const char* kernel, const std::string& tag, std::function<cudaError_t(cudaStream_t)> fn, double flops = 0) {
+        TOp o;
+        o.fn = std::move(fn); o.tag = tag; o.kernel = kernel; o.flops = flops;
+        t->ops.push_back(std::move(o));
+    }
+    // 3x3 256 -> N conv over [B, 64, 64, 256] on conv_gemm
+    bool conv(const std::string& tag, const bf16* in, const bf16* wq, int N, bf16* out, ConvEpilogue epi) {
+        ConvGemmDesc d;
+        d.src0 = ConvSrc{in, F};
+        d.src1 = ConvSrc{nullptr, 0};
+        d.B = t->B; d.H = S; d.W = S; d.ksize = 3; d.mode = CONV_TAPS;
+        d.weight = wq; d.N = N; d.out = out; d.epi = epi;
+        ConvGemmLaunch l;
+        char e[256];
+        if (conv_gemm_prepare(d, t->num_sms, &l, e, sizeof(e))) { tfail("%s: %s", tag.c_str(), e); return ok = false; }
+        push("conv_gemm", tag, [l](cudaStream_t s) { return conv_gemm_run(l, s); }, 2.0 * t->B * P * (N < F ? 1 : N) * 9.0 * F);
+        return true;
+    }
+};
+
+int build(hd_trainer* t) {
+    const int B = t->B, nb = t->nb;
+    const int cin = t->cfg.self_condition ? 2 : 1;
+    const int ld = nb * 2 * F;
+    const size_t act_elems = static_cast<size_t>(B) * P * F;
+    const long long M = static_cast<long long>(B) * P;
+    TB b{t};
+
+    // ---------------------------------------------------------------- parameters
+    const TParam *head_w = find_p(t, "head.weight", {F, cin, 3, 3}), *head_b = find_p(t, "head.bias", {F});
+    const TParam *w1 = find_p(t, "time_mlp.1.weight", {TIME_DIM, F}), *b1 = find_p(t, "time_mlp.1.bias", {TIME_DIM});
+    const TParam *w3 = find_p(t, "time_mlp.3.weight", {TIME_DIM, TIME_DIM}), *b3 = find_p(t, "time_mlp.3.bias", {TIME_DIM});
+    const TParam *bt_w = find_p(t, "body_tail.weight", {F, F, 3, 3}), *bt_b = find_p(t, "body_tail.bias", {F});
+    const TParam *tail_w = find_p(t, "tail.weight", {1, F, 3, 3}), *tail_b = find_p(t, "tail.bias", {1});
+    if (!head_w || !head_b || !w1 || !b1 || !w3 || !b3 || !bt_w || !bt_b || !tail_w || !tail_b) return 1;
+    std::vector<const TParam*> cw(nb), cb(nb), mw(nb), mb(nb);
+    for (int i = 0; i < nb; ++i) {
+        const std::string pre = "body." + std::to_string(i);
+        cw[i] = find_p(t, pre + ".conv.proj.weight", {F, F, 3, 3});
+        cb[i] = find_p(t, pre + ".conv.proj.bias", {F});
+        mw[i] = find_p(t, pre + ".mlp.1.weight", {2 * F, TIME_DIM});
+        mb[i] = find_p(t, pre + ".mlp.1.bias", {2 * F});
+        if (!cw[i] || !cb[i] || !mw[i] || !mb[i]) return 1;
+    }
+
+    // ---------------------------------------------------------------- buffers
+    if (dalloc(t, &t->x, M * 4, true) || dalloc(t, &t->cond, M * 4, true) || dalloc(t, &t->target, M * 4, true) ||
+        dalloc(t, &t->eps, M * 4) || dalloc(t, &t->d_eps, M * 4) || dalloc(t, &t->time, B * 4, true) ||
+        dalloc(t, &t->weight, B * 4, true) || dalloc(t, &t->loss, 16, true))
+        return 1;
+    std::vector<bf16*> wqf(nb + 1), wqd(nb + 1);   // forward / data-gradient GEMM layouts; index nb = body_tail
+    for (int i = 0; i <= nb; ++i)
+        if (dalloc(t, &wqf[i], static_cast<size_t>(F) * 9 * F * 2) || dalloc(t, &wqd[i], static_cast<size_t>(F) * 9 * F * 2)) return 1;
+    bf16* wq_tail = nullptr;
+    float *tail_bias16 = nullptr, *tail_flip = nullptr, *zero_bias = nullptr;
+    if (dalloc(t, &wq_tail, static_cast<size_t>(16) * 9 * F * 2) || dalloc(t, &tail_bias16, 16 * 4, true) ||
+        dalloc(t, &tail_flip, F * 9 * 4) || dalloc(t, &zero_bias, F * 4, true))
+        return 1;
+    float *posenc = nullptr, *z1 = nullptr, *temb = nullptr, *film = nullptr, *dfilm = nullptr, *d_act = nullptr, *d_g1 = nullptr;
+    if (dalloc(t, &posenc, static_cast<size_t>(B) * F * 4) || dalloc(t, &z1, static_cast<size_t>(B) * TIME_DIM * 4) ||
+        dalloc(t, &temb, static_cast<size_t>(B) * TIME_DIM * 4) || dalloc(t, &film, static_cast<size_t>(B) * ld * 4) ||
+        dalloc(t, &dfilm, static_cast<size_t>(B) * ld * 4, true) || dalloc(t, &d_act, static_cast<size_t>(B) * TIME_DIM * 4) ||
+        dalloc(t, &d_g1, static_cast<size_t>(B) * TIME_DIM * 4))
+        return 1;
+    std::vector<bf16*> X(nb + 1), A(nb), Sx(nb);
+    for (int i = 0; i <= nb; ++i) if (dalloc(t, &X[i], act_elems * 2)) return 1;
+    for (int i = 0; i < nb; ++i) if (dalloc(t, &A[i], act_elems * 2) || dalloc(t, &Sx[i], act_elems * 2)) return 1;
+    bf16 *BT = nullptr, *DBT = nullptr, *GX[2] = {nullptr, nullptr}, *DS = nullptr, *Tg = nullptr, *Tx = nullptr;
+    if (dalloc(t, &BT, act_elems * 2) || dalloc(t, &DBT, act_elems * 2) || dalloc(t, &GX[0], act_elems * 2) ||
+        dalloc(t, &GX[1], act_elems * 2) || dalloc(t, &DS, act_elems * 2) || dalloc(t, &Tg, act_elems * 2) ||
+        dalloc(t, &Tx, act_elems * 2 * 3))
+        return 1;
+    float *ws1 = nullptr, *ws2 = nullptr, *film_part = nullptr, *cs_part = nullptr, *cs_g = nullptr, *thin_part = nullptr,
+          *loss_part = nullptr;
+    if (dalloc(t, &ws1, wgrad_part_bytes(WG_SPLITS)) || dalloc(t, &ws2, wgrad_part_bytes(WG_SPLITS)) ||
+        dalloc(t, &film_part, static_cast<size_t>(film_bwd_part_floats(B, F)) * 4) ||
+        dalloc(t, &cs_part, static_cast<size_t>(colsum_parts(M)) * F * 4) || dalloc(t, &cs_g, F * 4) ||
+        dalloc(t, &thin_part, static_cast<size_t>(B) * 8 * 2 * 9 * F * 4) || dalloc(t, &loss_part, static_cast<size_t>(loss_parts()) * 4))
+        return 1;
+    WgradLaunch wl1, wl2;
+    {
+        char e[256];
+        if (wgrad_prepare(Tg, Tx, B, S, S, F, WG_SPLITS, ws1, &wl1, e, sizeof(e))) return tfail("%s", e);
+        if (wgrad_prepare(Tg, Tx, B, S, S, F, WG_SPLITS, ws2, &wl2, e, sizeof(e))) return tfail("%s", e);
+    }
+    const double conv_flops = 2.0 * M * F * 9.0 * F;
+
+    // ---------------------------------------------------------------- per-step weight preparation (parameters move every step)
+    for (int i = 0; i <= nb; ++i) {
+        const float* w = i < nb ? cw[i]->w : bt_w->w;
+        bf16 *qf = wqf[i], *qd = wqd[i];
+        b.push("prep", "prep.conv." + std::to_string(i), [=](cudaStream_t s) {
+            cudaError_t e = prep_conv_weight_run(w, qf, F, F, 3, 0, 1e-5f, F, s);
+            return e != cudaSuccess ? e : prep_dgrad_weight_run(w, qd, F, F, s);
+        });
+    }
+    {
+        const float *w = tail_w->w, *bias = tail_b->w;
+        b.push("prep", "prep.tail", [=](cudaStream_t s) {
+            cudaError_t e = prep_conv_weight_run(w, wq_tail, 1, F, 3, 0, 1e-5f, 16, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(tail_bias16, bias, 4, cudaMemcpyDeviceToDevice, s);
+            return e != cudaSuccess ? e : flip_tail_weight_run(w, tail_flip, F, s);
+        });
+    }
+
+    // ---------------------------------------------------------------- forward: time embedding -> FiLM rows
+    {
+        float* tv = t->time;
+        b.push("time", "posenc", [=](cudaStream_t s) { return posenc_rows_run(tv, posenc, B, F, 0, s); });
+        const float *w1d = w1->w, *b1d = b1->w, *w3d = w3->w, *b3d = b3->w;
+        b.push("time", "time_mlp.1", [=](cudaStream_t s) { return linear_rows_run(posenc, F, w1d, b1d, z1, TIME_DIM, 0, B, F, TIME_DIM, 0, 0, s); });
+        b.push("time", "gelu+time_mlp.3", [=](cudaStream_t s) { return linear_rows_run(z1, TIME_DIM, w3d, b3d, temb, TIME_DIM, 0, B, TIME_DIM, TIME_DIM, 2, 0, s); });
+        for (int i = 0; i < nb; ++i) {
+            const float *w = mw[i]->w, *bias = mb[i]->w;
+            const int off = i * 2 * F;
+            b.push("time", "body." + std::to_string(i) + ".mlp", [=](cudaStream_t s) {
+                return linear_rows_run(temb, TIME_DIM, w, bias, film, ld, off, B, TIME_DIM, 2 * F, 1, 0, s);
+            });
+        }
+    }
+    // ---------------------------------------------------------------- forward: eps-net
+    {
+        StemConvArgs a;
+        a.x0 = t->cfg.self_condition ? t->cond : t->x;
+        a.x1 = t->cfg.self_condition ? t->x : nullptr;
+        a.w = head_w->w; a.bias = head_b->w; a.y = X[0];
+        a.B = B; a.H = S; a.W = S; a.Cout = F; a.Cin = cin; a.ksize = 3;
+        b.push("stem_conv", "head", [a](cudaStream_t s) { return stem_conv_run(a, s); });
+    }
+    for (int i = 0; i < nb; ++i) {
+        const std::string pre = "body." + std::to_string(i);
+        ConvEpilogue e1;
+        e1.bias = cb[i]->w;
+        if (!b.conv(pre + ".conv#1", X[i], wqf[i], F, A[i], e1)) return 1;
+        const bf16* ai = A[i];
+        bf16* si = Sx[i];
+        const int off = i * 2 * F;
+        b.push("film_silu_fwd", pre + ".film_silu", [=](cudaStream_t s) { return film_silu_fwd_run(ai, si, film, ld, off, B, P, F, s); });
+        ConvEpilogue e2;
+        e2.bias = cb[i]->w; e2.out_scale = 0.1f; e2.res = X[i]; e2.ldr = F;
+        if (!b.conv(pre + ".conv#2", Sx[i], wqf[i], F, X[i + 1], e2)) return 1;
+    }
+    {
+        ConvEpilogue et;
+        et.bias = bt_b->w; et.res = X[0]; et.ldr = F;
+        if (!b.conv("body_tail", X[nb], wqf[nb], F, BT, et)) return 1;
+        ConvEpilogue eo;
+        eo.bias = tail_bias16; eo.out_f32 = t->eps; eo.n_valid = 1;
+        if (!b.conv("tail", BT, wq_tail, 16, nullptr, eo)) return 1;
+    }
+    // ---------------------------------------------------------------- loss and d loss / d eps
+    {
+        hd_trainer* tt = t;
+        b.push("loss", "loss", [=](cudaStream_t s) {
+            return loss_grad_run(tt->eps, tt->target, tt->weight, tt->loss_kind, B, P, tt->d_eps, loss_part, tt->loss, s);
+        });
+    }
+    // ---------------------------------------------------------------- backward: tail (256 -> 1)
+    {
+        const float* de = t->d_eps;
+        float *gw = tail_w->g, *gb = tail_b->g;
+        b.push("thin_wgrad", "tail.wgrad", [=](cudaStream_t s) { return thin_wgrad_run(BT, de, nullptr, -1, B, thin_part, gw, s); });
+        b.push("reduce", "tail.bias_grad", [=](cudaStream_t s) {
+            return sum_f32_run(de, M, loss_part, gb, s);
+        });
+        StemConvArgs a;
+        a.x0 = de; a.x1 = nullptr; a.w = tail_flip; a.bias = zero_bias; a.y = DBT;
+        a.B = B; a.H = S; a.W = S; a.Cout = F; a.Cin = 1; a.ksize = 3;
+        b.push("stem_conv", "tail.dgrad", [a](cudaStream_t s) { return stem_conv_run(a, s); });
+    }
+    // ---------------------------------------------------------------- backward: body_tail
+    {
+        float *gw = bt_w->g, *gb = bt_b->g;
+        b.push("colsum", "body_tail.bias_grad", [=](cudaStream_t s) { return colsum_run(DBT, M, F, cs_part, 1.0f, 0, gb, s); });
+        const bf16* xin = X[nb];
+        b.push("transpose", "body_tail.planar", [=](cudaStream_t s) {
+            cudaError_t e = nhwc_to_planar_run(DBT, Tg, B, P, F, 1, s);
+            return e != cudaSuccess ? e : nhwc_to_planar_run(xin, Tx, B, P, F, 3, s);
+        });
+        b.push("wgrad", "body_tail.wgrad", [=](cudaStream_t s) { return wgrad_run(wl1, s); }, conv_flops);
+        b.push("reduce", "body_tail.wgrad_reduce", [=](cudaStream_t s) { return wgrad_reduce_run(ws1, WG_SPLITS, 1.0f, 0, gw, s); });
+        if (!b.conv("body_tail.dgrad", DBT, wqd[nb], F, GX[0], ConvEpilogue())) return 1;
+    }
+    // ---------------------------------------------------------------- backward: residual blocks
+    int cur = 0;
+    for (int i = nb - 1; i >= 0; --i) {
+        const std::string pre = "body." + std::to_string(i);
+        const bf16* g = GX[cur];
+        bf16* gnext = GX[cur ^ 1];
+        const bf16 *si = Sx[i], *ai = A[i], *xi = X[i];
+        const int off = i * 2 * F;
+        float *gw = cw[i]->g, *gb = cb[i]->g;
+        b.push("colsum", pre + ".colsum_g", [=](cudaStream_t s) { return colsum_run(g, M, F, cs_part, 1.0f, 0, cs_g, s); });
+        b.push("transpose", pre + ".planar#2", [=](cudaStream_t s) {
+            cudaError_t e = nhwc_to_planar_run(g, Tg, B, P, F, 1, s);
+            return e != cudaSuccess ? e : nhwc_to_planar_run(si, Tx, B, P, F, 3, s);
+        });
+        b.push("wgrad", pre + ".wgrad#2", [=](cudaStream_t s) { return wgrad_run(wl2, s); }, conv_flops);
+        ConvEpilogue e2;
+        e2.out_scale = 0.1f;
+        if (!b.conv(pre + ".dgrad#2", g, wqd[i], F, DS, e2)) return 1;
+        b.push("film_silu_bwd", pre + ".film_silu_bwd", [=](cudaStream_t s) {
+            return film_silu_bwd_run(DS, ai, DS, film, dfilm, ld, off, B, P, F, film_part, s);
+        });
+        b.push("reduce", pre + ".bias_grad", [=](cudaStream_t s) { return edrn_bias_grad_run(film, dfilm, ld, off, B, cs_g, 0.1f, gb, F, s); });
+        b.push("transpose", pre + ".planar#1", [=](cudaStream_t s) {
+            cudaError_t e = nhwc_to_planar_run(DS, Tg, B, P, F, 1, s);
+            return e != cudaSuccess ? e : nhwc_to_planar_run(xi, Tx, B, P, F, 3, s);
+        });
+        b.push("wgrad", pre + ".wgrad#1", [=](cudaStream_t s) { return wgrad_run(wl1, s); }, conv_flops);
+        b.push("reduce", pre + ".wgrad_reduce", [=](cudaStream_t s) {
+            cudaError_t e = wgrad_reduce_run(ws1, WG_SPLITS, 1.0f, 0, gw, s);
+            return e != cudaSuccess ? e : wgrad_reduce_run(ws2, WG_SPLITS, 0.1f, 1, gw, s);
+        });
+        ConvEpilogue e1;
+        e1.res = g; e1.ldr = F;
+        if (!b.conv(pre + ".dgrad#1", DS, wqd[i], F, gnext, e1)) return 1;
+        cur ^= 1;
+    }
+    // ---------------------------------------------------------------- backward: head (r = head output feeds block 0 AND body_tail's skip)
+    {
+        const bf16* g = GX[cur];
+        bf16* g0 = GX[cur ^ 1];
+        float *gw = head_w->g, *gb = head_b->g;
+        const float* u0 = t->cfg.self_condition ? t->cond : t->x;
+        const float* u1 = t->cfg.self_condition ? t->x : nullptr;
+        b.push("pointwise", "head.grad_sum", [=](cudaStream_t s) { return add_bf16_run(g, DBT, g0, static_cast<long long>(act_elems), s); });
+        b.push("colsum", "head.bias_grad", [=](cudaStream_t s) { return colsum_run(g0, M, F, cs_part, 1.0f, 0, gb, s); });
+        b.push("thin_wgrad", "head.wgrad", [=](cudaStream_t s) { return thin_wgrad_run(g0, u0, u1, +1, B, thin_part, gw, s); });
+    }
+    // ---------------------------------------------------------------- backward: time-embedding MLPs
+    for (int i = 0; i < nb; ++i) {
+        const float* w = mw[i]->w;
+        float *gw = mw[i]->g, *gb = mb[i]->g;
+        const int off = i * 2 * F;
+        const int acc = i > 0 ? 1 : 0;
+        b.push("time_bwd", "body." + std::to_string(i) + ".mlp.bwd", [=](cudaStream_t s) {
+            cudaError_t e = linear_bwd_weight_run(dfilm, ld, off, temb, TIME_DIM, B, TIME_DIM, 2 * F, 1, gw, gb, s);
+            return e != cudaSuccess ? e : linear_bwd_input_run(dfilm, ld, off, w, B, TIME_DIM, 2 * F, acc, d_act, TIME_DIM, s);
+        });
+    }
+    {
+        float *gw3 = w3->g, *gb3 = b3->g, *gw1 = w1->g, *gb1 = b1->g;
+        const float* w3d = w3->w;
+        b.push("time_bwd", "time_mlp.bwd", [=](cudaStream_t s) {
+            cudaError_t e = act_grad_run(d_act, temb, static_cast<long long>(B) * TIME_DIM, 1, s);                     // through SiLU(temb)
+            if (e == cudaSuccess) e = linear_bwd_weight_run(d_act, TIME_DIM, 0, z1, TIME_DIM, B, TIME_DIM, TIME_DIM, 2, gw3, gb3, s);
+            if (e == cudaSuccess) e = linear_bwd_input_run(d_act, TIME_DIM, 0, w3d, B, TIME_DIM, TIME_DIM, 0, d_g1, TIME_DIM, s);
+            if (e == cudaSuccess) e = act_grad_run(d_g1, z1, static_cast<long long>(B) * TIME_DIM, 2, s);              // through GELU(z1)
+            if (e == cudaSuccess) e = linear_bwd_weight_run(d_g1, TIME_DIM, 0, posenc, F, B, F, TIME_DIM, 0, gw1, gb1, s);
+            return e;
+        });
+    }
+    return b.ok ? 0 : 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hd_trainer_create(const hd_config* cfg, int32_t batch, hd_trainer** out) {
+    if (!cfg || !out) return tfail("hd_trainer_create: null argument");
+    if (cfg->abi_version != HD_ABI_VERSION) return tfail("ABI version mismatch: header %d, library %d", cfg->abi_version, HD_ABI_VERSION);
+    if (cfg->variant != HD_HICEDRN)
+        return tfail("hd_trainer is built for hicedrn_Diff (variant %d), the model train.py trains; variant %d has no backward yet", HD_HICEDRN, cfg->variant);
+    if (cfg->image_size != 64) return tfail("image_size must be 64");
+    if (cfg->num_blocks < 1) return tfail("HiCEDRN needs num_blocks >= 1");
+    if (batch < 1) return tfail("batch must be positive (got %d)", batch);
+    int dev = 0, cc_major = 0, sms = 0;
+    T_TRY(cudaGetDevice(&dev));
+    T_TRY(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    T_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (cc_major != 10) return tfail("hicdiff_b200 needs an sm_100a GPU (compute capability 10.x); device %d is %d.x", dev, cc_major);
+    hd_trainer* t = new hd_trainer();
+    t->cfg = *cfg;
+    t->device = dev;
+    t->num_sms = sms;
+    t->B = batch;
+    t->nb = cfg->num_blocks;
+    *out = t;
+    return 0;
+}
+
+int hd_trainer_bind(hd_trainer* t, const char* key, const float* param, float* grad, const int64_t* shape, int32_t ndim) {
+    if (!t || !key || !param || !grad || (ndim > 0 && !shape)) return tfail("hd_trainer_bind: null argument");
+    if (t->finalized) return tfail("hd_trainer_bind: the trainer is already finalized");
+    TParam p;
+    p.w = param; p.g = grad; p.numel = 1;
+    for (int i = 0; i < ndim; ++i) { p.shape.push_back(shape[i]); p.numel *= static_cast<size_t>(shape[i]); }
+    t->p[key] = p;
+    return 0;
+}
+
+int hd_trainer_finalize(hd_trainer* t, void* stream) {
+    if (!t) return tfail("hd_trainer_finalize: null trainer");
+    if (t->finalized) return 0;
+    T_TRY(cudaSetDevice(t->device));
+    if (build(t)) return 1;
+    T_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    t->finalized = true;
+    return 0;
+}
+
+int hd_trainer_step(hd_trainer* t, const float* x_t, const float* cond, const float* time, const float* target,
+                    const float* weight, int32_t loss_type, float* eps_out, float* loss_out, void* stream) {
+    if (!t || !x_t || !time || !target || !weight || !loss_out) return tfail("hd_trainer_step: null argument");
+    if (!t->finalized) return tfail("hd_trainer_finalize has not been called");
+    if (t->cfg.self_condition && !cond) return tfail("hd_trainer_step: the net is self-conditioned, cond must not be NULL");
+    if (loss_type != 0 && loss_type != 1) return tfail("loss_type must be 0 (l1) or 1 (l2)");
+    T_TRY(cudaSetDevice(t->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t tb = static_cast<size_t>(t->B) * P * 4;
+    T_TRY(cudaMemcpyAsync(t->x, x_t, tb, cudaMemcpyDeviceToDevice, s));
+    if (cond) T_TRY(cudaMemcpyAsync(t->cond, cond, tb, cudaMemcpyDeviceToDevice, s));
+    T_TRY(cudaMemcpyAsync(t->target, target, tb, cudaMemcpyDeviceToDevice, s));
+    T_TRY(cudaMemcpyAsync(t->time, time, t->B * 4, cudaMemcpyDeviceToDevice, s));
+    T_TRY(cudaMemcpyAsync(t->weight, weight, t->B * 4, cudaMemcpyDeviceToDevice, s));
+    t->loss_kind = loss_type;
+    for (const TOp& op : t->ops) {
+        cudaError_t e = op.fn(s);
+        if (e != cudaSuccess) return tfail("launch of '%s' failed: %s", op.tag.c_str(), cudaGetErrorString(e));
+    }
+    if (eps_out) T_TRY(cudaMemcpyAsync(eps_out, t->eps, tb, cudaMemcpyDeviceToDevice, s));
+    T_TRY(cudaMemcpyAsync(loss_out, t->loss, 4, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+int hd_trainer_num_launches(hd_trainer* t) { return t ? static_cast<int>(t->ops.size()) : 0; }
+
+int hd_trainer_profile(hd_trainer* t, int32_t reps, char* buf, int64_t buflen, void* stream) {
+    if (!t || !buf || buflen <= 0 || reps <= 0) return tfail("hd_trainer_profile: bad argument");
+    if (!t->finalized) return tfail("hd_trainer_finalize has not been called");
+    T_TRY(cudaSetDevice(t->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaEvent_t e0, e1;
+    T_TRY(cudaEventCreate(&e0));
+    T_TRY(cudaEventCreate(&e1));
+    std::map<std::string, std::pair<double, double>> fam;   // kernel family -> (ms, flops)
+    std::map<std::string, int> cnt;
+    for (const TOp& op : t->ops) {
+        cudaError_t e = op.fn(s);
+        if (e == cudaSuccess) e = cudaEventRecord(e0, s);
+        for (int r = 0; r < reps && e == cudaSuccess; ++r) e = op.fn(s);
+        if (e == cudaSuccess) e = cudaEventRecord(e1, s);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e != cudaSuccess) {
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+            return tfail("profiling '%s' failed: %s", op.tag.c_str(), cudaGetErrorString(e));
+        }
+        fam[op.kernel].first += ms / reps;
+        fam[op.kernel].second += op.flops;
+        cnt[op.kernel] += 1;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    std::string out = "{";
+    bool first = true;
+    for (auto& kv : fam) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s\"%s\":{\"ms\":%.6f,\"flops\":%.6e,\"ops\":%d}", first ? "" : ",", kv.first.c_str(),
+                 kv.second.first, kv.second.second, cnt[kv.first]);
+        out += line;
+        first = false;
+    }
+    out += "}";
+    if (static_cast<int64_t>(out.size()) + 1 > buflen) return tfail("hd_trainer_profile: buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return 0;
+}
+
+int64_t hd_trainer_device_bytes(hd_trainer* t) { return t ? static_cast<int64_t>(t->bytes) : 0; }
+
+void hd_trainer_destroy(hd_trainer* t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    for (void* q : t->allocs) cudaFree(q);
+    delete t;
+}
+
+// ---- single-operator entry points of the training path (parity tests pin each kernel against torch.autograd on the CPU)
+int hd_op_conv3x3_wgrad(const uint16_t* x, const uint16_t* dy, float* dw, int32_t B, void* stream) {
+    if (!x || !dy || !dw || B < 1) return tfail("hd_op_conv3x3_wgrad: bad argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t elems = static_cast<size_t>(B) * P * F;
+    bf16 *tg = nullptr, *tx = nullptr;
+    float* ws = nullptr;
+    T_TRY(cudaMalloc(&tg, elems * 2));
+    T_TRY(cudaMalloc(&tx, elems * 2 * 3));
+    T_TRY(cudaMalloc(&ws, wgrad_part_bytes(WG_SPLITS)));
+    WgradLaunch wl;
+    char e[256];
+    int rc = wgrad_prepare(tg, tx, B, S, S, F, WG_SPLITS, ws, &wl, e, sizeof(e));
+    cudaError_t ce = cudaSuccess;
+    const char* stage = "transpose";
+    if (!rc) ce = nhwc_to_planar_run(reinterpret_cast<const bf16*>(dy), tg, B, P, F, 1, s);
+    if (!rc && ce == cudaSuccess) ce = nhwc_to_planar_run(reinterpret_cast<const bf16*>(x), tx, B, P, F, 3, s);
+    if (!rc && ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    if (!rc && ce == cudaSuccess) { stage = "wgrad_kernel"; ce = wgrad_run(wl, s); }
+    if (!rc && ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    if (!rc && ce == cudaSuccess) { stage = "reduce"; ce = wgrad_reduce_run(ws, WG_SPLITS, 1.0f, 0, dw, s); }
+    if (!rc && ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    cudaFree(tg); cudaFree(tx); cudaFree(ws);
+    if (rc) return tfail("%s", e);
+    if (ce != cudaSuccess) return tfail("hd_op_conv3x3_wgrad failed in %s: %s", stage, cudaGetErrorString(ce));
+    return 0;
+}
+
+int hd_op_conv3x3_dgrad(const uint16_t* dy, const float* w, uint16_t* dx, int32_t B, void* stream) {
+    if (!dy || !w || !dx || B < 1) return tfail("hd_op_conv3x3_dgrad: bad argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    bf16* wq = nullptr;
+    T_TRY(cudaMalloc(&wq, static_cast<size_t>(F) * 9 * F * 2));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    ConvGemmDesc d;
+    d.src0 = ConvSrc{reinterpret_cast<const bf16*>(dy), F};
+    d.src1 = ConvSrc{nullptr, 0};
+    d.B = B; d.H = S; d.W = S; d.ksize = 3; d.mode = CONV_TAPS;
+    d.weight = wq; d.N = F; d.out = reinterpret_cast<bf16*>(dx);
+    ConvGemmLaunch l;
+    char e[256];
+    int rc = conv_gemm_prepare(d, sms, &l, e, sizeof(e));
+    cudaError_t ce = cudaSuccess;
+    if (!rc) ce = prep_dgrad_weight_run(w, wq, F, F, s);
+    if (!rc && ce == cudaSuccess) ce = conv_gemm_run(l, s);
+    if (!rc && ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    cudaFree(wq);
+    if (rc) return tfail("%s", e);
+    if (ce != cudaSuccess) return tfail("hd_op_conv3x3_dgrad failed: %s", cudaGetErrorString(ce));
+    return 0;
+}
+
+}  // extern "C"

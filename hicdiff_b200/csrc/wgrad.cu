@@ -1,0 +1,215 @@
+// Weight gradient of a 256 -> 256 3x3 "same" convolution on tcgen05 (HiCEDRN training):
+//
+//     dW[co, ci, ky, kx] = sum_{b, y, x} dY[b, y, x, co] * X[b, y + ky - 1, x + kx - 1, ci]
+//
+// i.e. nine GEMMs (one per tap) with M = Cout, N = Cin and K = B * H * W pixels.  Both operands are read from PLANAR copies
+// ([B, C, H, W] bf16, made by nhwc_to_planar_kernel) so that a K block -- one image row of 64 pixels -- is a K-major,
+// 128-byte-swizzled TMA box {64 px, 1 row, 256 channels}: exactly the operand layout conv_gemm.cu uses.  The tap's dy shift
+// is a TMA row coordinate (rows outside the image are skipped: they only meet the conv's zero padding); its dx shift cannot
+// be one -- a TMA box must start on a 16-byte boundary of the innermost dimension and one pixel is 2 bytes (measured: an
+// illegal-instruction fault) -- so nhwc_to_planar_kernel writes THREE planar copies of X, pre-shifted by dx = -1, 0, +1
+// with zero fill, and tap (dy, dx) reads copy dx.
+//
+// One CTA = one (tap, K split): both 128-row halves of dY^T and the whole X^T box per stage (64 KiB, 3 stages), two
+// M = 128 x N = 256 fp32 accumulators = all 512 TMEM columns, 8 MMAs per stage.  Warp 0 produces (TMA), warp 1 issues, warps
+// 2-5 drain the accumulators into a [split][tap][co][ci] fp32 workspace that wgrad_reduce_kernel sums in a fixed order
+// (deterministic; no atomics) into the reference's [Cout, Cin, 3, 3] layout.
+#include "kernels.h"
+#include "ptx.cuh"
+
+#include <cstdio>
+
+namespace hd {
+namespace {
+
+constexpr int WG_C = 256;
+constexpr int WG_THREADS = 192;
+constexpr int WG_STAGES = 3;
+constexpr uint32_t WG_A_BYTES = WG_C * 64 * 2;   // dY^T: 256 rows (co) x 64 px
+constexpr uint32_t WG_B_BYTES = WG_C * 64 * 2;   // X^T : 256 rows (ci) x 64 px
+constexpr uint32_t WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+
+struct WgradKArgs {
+    int kb_total;     // B * H K blocks (image rows)
+    int nsplit;
+    int H;
+    float* part;      // [nsplit][9][256][256]
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
+             const __grid_constant__ CUtensorMap tmX2, const WgradKArgs a) {
+    extern __shared__ uint8_t wg_smem_raw[];
+    uint8_t* smem = wg_smem_raw + ((1024u - (ptx::smem_u32(wg_smem_raw) & 1023u)) & 1023u);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + WG_STAGES;
+    uint64_t* tfull_bar = empty_bar + WG_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tap = blockIdx.x % 9, split = blockIdx.x / 9;
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    const CUtensorMap* tmX = dx < 0 ? &tmX0 : (dx == 0 ? &tmX1 : &tmX2);   // the copy of X pre-shifted by dx
+    const int kb0 = static_cast<int>(static_cast<long long>(a.kb_total) * split / a.nsplit);
+    const int kb1 = static_cast<int>(static_cast<long long>(a.kb_total) * (split + 1) / a.nsplit);
+
+    if (warp == 0) {
+        if (lane == 0) { ptx::prefetch_tmap(&tmG); ptx::prefetch_tmap(tmX); }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    } else if (warp == 1 && lane == 0) {
+        for (int i = 0; i < WG_STAGES; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+        ptx::mbar_init(tfull_bar, 1);
+        ptx::fence_mbar_init();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- TMA producer
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            const int b = kb / a.H, y = kb - b * a.H;
+            if (y + dy < 0 || y + dy >= a.H) continue;        // the shifted row lies in the zero padding
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+            if (ptx::elect_one()) {
+                uint8_t* sA = smem + stage * WG_STAGE_BYTES;
+                ptx::mbar_arrive_expect_tx(&full_bar[stage], WG_STAGE_BYTES);
+                ptx::tma_load_4d(sA, &tmG, &full_bar[stage], 0, y, 0, b);
+                ptx::tma_load_4d(sA + WG_A_BYTES, tmX, &full_bar[stage], 0, y + dy, 0, b);
+            }
+            __syncwarp();
+            if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(128, WG_C);
+        const uint64_t desc0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem));
+        int stage = 0;
+        uint32_t phase = 0;
+        bool first = true;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            const int y = kb % a.H;
+            if (y + dy < 0 || y + dy >= a.H) continue;
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint64_t da = desc0 + static_cast<uint64_t>((stage * WG_STAGE_BYTES) >> 4);
+                const uint64_t db = da + static_cast<uint64_t>(WG_A_BYTES >> 4);
+#pragma unroll
+                for (int mh = 0; mh < 2; ++mh) {
+                    const uint64_t dam = da + static_cast<uint64_t>((mh * (WG_A_BYTES / 2)) >> 4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_bf16(tmem_base + mh * WG_C, dam + 2u * k, db + 2u * k, idesc, (first && k == 0) ? 0u : 1u);
+                }
+                ptx::umma_commit(&empty_bar[stage]);
+            }
+            __syncwarp();
+            first = false;
+            if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (ptx::elect_one()) ptx::umma_commit(tfull_bar);
+        __syncwarp();
+    } else {
+        // ---------------------------------------------------------------- epilogue: TMEM -> fp32 workspace
+        const int q = warp & 3;                       // TMEM lane quarter this warp may read
+        bool any = false;
+        for (int kb = kb0; kb < kb1; ++kb) { const int y = kb % a.H; if (y + dy >= 0 && y + dy < a.H) { any = true; break; } }
+        ptx::mbar_wait(tfull_bar, 0);
+        ptx::tc_fence_after();
+        float* out = a.part + (static_cast<size_t>(split) * 9 + tap) * WG_C * WG_C;
+#pragma unroll 1
+        for (int mh = 0; mh < 2; ++mh) {
+            float* orow = out + static_cast<size_t>(mh * 128 + q * 32 + lane) * WG_C;
+#pragma unroll 1
+            for (int c = 0; c < WG_C; c += 32) {
+                uint32_t v[32];
+                if (any) {
+                    ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mh * WG_C + c, v);
+                    ptx::tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0u;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<uint4*>(orow + c + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+        }
+        ptx::tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// dW[(co * 256 + ci) * 9 + tap] (+)= scale * sum_split part[split][tap][co][ci]
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, float scale, int accumulate, float* __restrict__ dw) {
+    __shared__ float s_t[9][257];
+    const int i0 = blockIdx.x * 256;                 // 256 consecutive (co, ci) pairs
+    for (int tap = 0; tap < 9; ++tap) {
+        float t = 0.f;
+        for (int sp = 0; sp < nsplit; ++sp)
+            t += __ldg(part + (static_cast<size_t>(sp) * 9 + tap) * WG_C * WG_C + i0 + threadIdx.x);
+        s_t[tap][threadIdx.x] = t * scale;
+    }
+    __syncthreads();
+    float* o = dw + static_cast<size_t>(i0) * 9;
+    for (int j = threadIdx.x; j < 256 * 9; j += 256) {
+        const float v = s_t[j % 9][j / 9];
+        o[j] = accumulate ? o[j] + v : v;
+    }
+}
+
+}  // namespace
+
+int wgrad_prepare(const bf16* g_planar, const bf16* x_planar3, int B, int H, int W, int C, int nsplit, float* part,
+                  WgradLaunch* out, char* err, int errlen) {
+    if (C != WG_C || W != 64) {
+        snprintf(err, errlen, "wgrad: built for 256 channels and 64-pixel rows (got C = %d, W = %d)", C, W);
+        return 1;
+    }
+    if (nsplit < 1 || static_cast<long long>(B) * H / nsplit < 4) {
+        snprintf(err, errlen, "wgrad: %d K splits leave fewer than 4 image rows per CTA", nsplit);
+        return 1;
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)W * 2, (cuuint64_t)W * H * 2, (cuuint64_t)W * H * C * 2};
+    cuuint32_t box[4] = {64, 1, (cuuint32_t)WG_C, 1};
+    if (encode_tmap_bf16(&out->tmG, g_planar, 4, dims, str, box, err, errlen)) return 1;
+    for (int i = 0; i < 3; ++i)
+        if (encode_tmap_bf16(&out->tmX[i], x_planar3 + static_cast<size_t>(i) * B * C * H * W, 4, dims, str, box, err, errlen)) return 1;
+    out->kb_total = B * H;
+    out->H = H;
+    out->nsplit = nsplit;
+    out->part = part;
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+    if (e != cudaSuccess) { snprintf(err, errlen, "wgrad: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return 1; }
+    return 0;
+}
+
+cudaError_t wgrad_run(const WgradLaunch& l, cudaStream_t s) {
+    WgradKArgs a;
+    a.kb_total = l.kb_total; a.nsplit = l.nsplit; a.H = l.H; a.part = l.part;
+
+    wgrad_kernel<<<9 * l.nsplit, WG_THREADS, WG_SMEM, s>>>(l.tmG, l.tmX[0], l.tmX[1], l.tmX[2], a);
+    return cudaGetLastError();
+}
+
+cudaError_t wgrad_reduce_run(const float* part, int nsplit, float scale, int accumulate, float* dw, cudaStream_t s) {
+    wgrad_reduce_kernel<<<WG_C * WG_C / 256, 256, 0, s>>>(part, nsplit, scale, accumulate, dw);
+    return cudaGetLastError();
+}
+
+size_t wgrad_part_bytes(int nsplit) { return static_cast<size_t>(nsplit) * 9 * WG_C * WG_C * sizeof(float); }
+
+}  // namespace hd

@@ -60,8 +60,9 @@ class _LossNeedsBackward(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):  # pragma: no cover - exercised only on GPU
         raise NotImplementedError(
-            "hicdiff_b200: the eps-net backward (dgrad/wgrad kernels) is not built yet -- SURVEY.md 8(f) N2. "
-            "The forward loss value is exact; train with the reference until N2 lands."
+            "hicdiff_b200: the backward of this eps-net (Unet / SR3 variants) is not built yet -- SURVEY.md 8(f) N2. "
+            "hicedrn_Diff, the model train.py trains, has a full backward (hicdiff_b200/train.py); for the others the "
+            "forward loss value is exact and training stays with the reference."
         )
 
 
@@ -247,7 +248,7 @@ class _GaussianDiffusionBase(nn.Module):
     def super_resolution(self, x_in, continous=False, noise=None):
         return self.p_sample_loop(x_in, continous, noise=noise)
 
-    # ------------------------------------------------------------------ training objective (forward value only)
+    # ------------------------------------------------------------------ training objective
     def q_sample(self, x_start, t, noise=None):
         noise = torch.randn_like(x_start) if noise is None else noise
         return _gather(self.sqrt_alphas_cumprod, t, x_start) * x_start + \
@@ -267,6 +268,18 @@ class _GaussianDiffusionBase(nn.Module):
             return _LossNeedsBackward.apply(loss, *params)
         return loss
 
+    def _wants_grad(self) -> bool:
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters())
+
+    def _trained_loss(self, x, t, cond, noise):
+        """Forward + loss + backward in one device call when the eps-net has a backward (hicedrn_Diff); else None."""
+        from . import train as _train
+
+        if not (self._wants_grad() and _train.supports_training(self.model)):
+            return None
+        weight = self.p2_loss_weight.gather(-1, t)
+        return _train.training_loss(self.model, x, t.to(torch.float32), cond, noise, weight, self.loss_type)
+
     def p_losses(self, x_in, t=None, noise=None):
         noisy, clean = x_in
         b, c, h, w = clean.shape
@@ -275,6 +288,9 @@ class _GaussianDiffusionBase(nn.Module):
             t = torch.randint(0, self.num_timesteps, (b,), device=clean.device).long()
         noise = torch.randn_like(clean) if noise is None else noise
         x = self.q_sample(clean, t, noise)
+        trained = self._trained_loss(x, t, noisy if self.self_condition else None, noise)
+        if trained is not None:
+            return trained
         with torch.no_grad():
             out = self.model(x, t, noisy if self.self_condition else None)
         loss = self.loss_fn(out, noise, reduction="none").reshape(b, -1)  # 'b ... -> b (...)' keeps all elements
@@ -309,6 +325,9 @@ class GaussianDiffusionUncond(_GaussianDiffusionBase):
         b = x_start.shape[0]
         noise = torch.randn_like(x_start) if noise is None else noise
         x = self.q_sample(x_start, t, noise)
+        trained = self._trained_loss(x, t, None, noise)
+        if trained is not None:
+            return trained
         with torch.no_grad():
             out = self.model(x, t, None)
         loss = self.loss_fn(out, noise, reduction="none").reshape(b, -1)  # 'b ... -> b (...)' keeps all elements

@@ -189,3 +189,29 @@ def tile_scatter(tiles, n, piece=64, band_blocks=4):
     mat = torch.zeros(n, n, device=tiles.device, dtype=torch.float32)
     _lib.check(lib.hd_tile_scatter(_lib.ptr(tiles), _lib.ptr(mat), n, piece, band_blocks, _lib.stream_ptr()), "hd_tile_scatter")
     return mat
+
+
+def conv3x3_wgrad_nhwc(x, dy):
+    """d/dW of conv2d(x, W, padding=1) for a 256 -> 256 3x3 conv over 64x64 tiles: x, dy [B,64,64,256] bf16 -> fp32
+    [256,256,3,3] (planar transposes + tcgen05 wgrad kernel + fixed-order split reduction)."""
+    lib = _lib.load()
+    _need_cuda(x, dy)
+    x, dy = _bf16c(x), _bf16c(dy)
+    if x.shape != dy.shape or tuple(x.shape[1:]) != (64, 64, 256):
+        raise ValueError(f"expected two [B,64,64,256] tensors, got {tuple(x.shape)} / {tuple(dy.shape)}")
+    dw = torch.empty(256, 256, 3, 3, device=x.device, dtype=torch.float32)
+    _lib.check(lib.hd_op_conv3x3_wgrad(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(dw), x.shape[0], _lib.stream_ptr()), "hd_op_conv3x3_wgrad")
+    return dw
+
+
+def conv3x3_dgrad_nhwc(dy, w):
+    """d/dx of conv2d(x, W, padding=1): dy [B,64,64,256] bf16, W fp32 [256,256,3,3] -> dx [B,64,64,256] bf16 (the forward
+    implicit-GEMM kernel over the flipped, transposed filter)."""
+    lib = _lib.load()
+    _need_cuda(dy, w)
+    dy, w = _bf16c(dy), _f32c(w)
+    if tuple(dy.shape[1:]) != (64, 64, 256) or tuple(w.shape) != (256, 256, 3, 3):
+        raise ValueError("expected dy [B,64,64,256] and w [256,256,3,3]")
+    dx = torch.empty_like(dy)
+    _lib.check(lib.hd_op_conv3x3_dgrad(_lib.ptr(dy), _lib.ptr(w), _lib.ptr(dx), dy.shape[0], _lib.stream_ptr()), "hd_op_conv3x3_dgrad")
+    return dx

@@ -1,0 +1,153 @@
+"""Training step on the sm_100a trainer (`hd_trainer_*`, include/hicdiff_b200.h).
+
+The reference trains hicedrn_Diff through `loss = diffusion(x); loss.backward(); optimizer.step()` (train.py:109-136).
+Here `GaussianDiffusion.p_losses` hands the whole forward + loss + backward of the eps-net to libhicdiff_b200.so in ONE call
+and returns a scalar whose autograd node delivers the parameter gradients, so the loop above -- including a stock
+`torch.optim.Adam(diffusion.parameters())` -- runs unchanged.  Parameters are bound by pointer: the optimizer's in-place
+updates are seen by the next step without any re-upload.  There is no ATen fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+
+
+class Trainer:
+    """One `hd_trainer` for a parameter-holder net (nets.hicedrn_Diff) at a fixed batch size."""
+
+    def __init__(self, net: torch.nn.Module, batch: int):
+        lib = _lib.load()
+        cfgd = net._plan_config()
+        if cfgd["variant"] != _lib.HD_HICEDRN:
+            raise NotImplementedError(
+                "hicdiff_b200: the training backward is built for hicedrn_Diff (the model train.py trains); "
+                "Unet / SR3 backward is SURVEY.md 8(f) N2, not built yet")
+        params = dict(net.named_parameters())
+        dev = next(iter(params.values())).device
+        if dev.type != "cuda":
+            raise RuntimeError("hicdiff_b200 trains on sm_100a GPUs only: move the module to a CUDA device (no CPU fallback)")
+        for k, p in params.items():
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError(f"parameter {k} must be contiguous fp32 (got {p.dtype})")
+        self.net = net
+        self.batch = int(batch)
+        self.device = dev
+        self._ptrs = {k: p.data_ptr() for k, p in params.items()}
+        total = sum(p.numel() for p in params.values())
+        self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grads: Dict[str, torch.Tensor] = {}
+        off = 0
+        for k, p in params.items():
+            self.grads[k] = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        cfg = _lib.hd_config()
+        cfg.abi_version = _lib.HD_ABI_VERSION
+        cfg.variant = cfgd["variant"]
+        cfg.self_condition = cfgd["self_condition"]
+        cfg.image_size = 64
+        cfg.timesteps = 1
+        cfg.num_blocks = cfgd["num_blocks"]
+        h = C.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(lib.hd_trainer_create(C.byref(cfg), self.batch, C.byref(h)), "hd_trainer_create")
+            self._handle: Optional[int] = h.value
+            for k, p in params.items():
+                shape = (C.c_int64 * max(p.dim(), 1))(*p.shape)
+                _lib.check(lib.hd_trainer_bind(self._handle, k.encode(), p.data_ptr(), self.grads[k].data_ptr(), shape, p.dim()),
+                           f"hd_trainer_bind({k})")
+            _lib.check(lib.hd_trainer_finalize(self._handle, _lib.stream_ptr()), "hd_trainer_finalize")
+
+    def matches(self, net, batch: int) -> bool:
+        if self._handle is None or batch != self.batch:
+            return False
+        ps = dict(net.named_parameters())
+        return ps.keys() == self._ptrs.keys() and all(p.data_ptr() == self._ptrs[k] for k, p in ps.items())
+
+    def destroy(self):
+        if self._handle is not None:
+            _lib.load().hd_trainer_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    def _tiles(self, t, name):
+        if t.shape != (self.batch, 1, 64, 64):
+            raise ValueError(f"{name} must be [{self.batch}, 1, 64, 64] (got {tuple(t.shape)})")
+        if t.device != self.device:
+            raise RuntimeError(f"{name} is on {t.device}, the module is on {self.device}")
+        return t.detach().to(torch.float32).contiguous()
+
+    def step(self, x_t, cond, time, target, weight, loss_type: str, want_eps: bool = False):
+        """Forward + loss + backward.  Returns (loss [] fp32 device tensor, eps or None); gradients land in `self.grads`."""
+        lib = _lib.load()
+        x_t = self._tiles(x_t, "x_t")
+        target = self._tiles(target, "target")
+        cond = self._tiles(cond, "cond") if cond is not None else None
+        tv = time.detach().reshape(-1).to(device=self.device, dtype=torch.float32).contiguous()
+        wv = weight.detach().reshape(-1).to(device=self.device, dtype=torch.float32).contiguous()
+        if tv.numel() != self.batch or wv.numel() != self.batch:
+            raise ValueError("time and weight must have one entry per sample")
+        kind = {"l1": 0, "l2": 1}[loss_type]
+        loss = torch.empty((), device=self.device, dtype=torch.float32)
+        eps = torch.empty_like(x_t) if want_eps else None
+        with torch.cuda.device(self.device):
+            _lib.check(lib.hd_trainer_step(self._handle, x_t.data_ptr(), _lib.ptr(cond), tv.data_ptr(), target.data_ptr(),
+                                           wv.data_ptr(), kind, _lib.ptr(eps), loss.data_ptr(), _lib.stream_ptr()),
+                       "hd_trainer_step")
+        return loss, eps
+
+    def profile(self, reps: int = 3) -> dict:
+        buf = C.create_string_buffer(1 << 16)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().hd_trainer_profile(self._handle, reps, buf, len(buf), _lib.stream_ptr()), "hd_trainer_profile")
+        return json.loads(buf.value.decode())
+
+    def device_bytes(self) -> int:
+        return int(_lib.load().hd_trainer_device_bytes(self._handle))
+
+    def num_launch_groups(self) -> int:
+        return int(_lib.load().hd_trainer_num_launches(self._handle))
+
+
+class _TrainStep(torch.autograd.Function):
+    """loss = trainer.step(...) as an autograd node over the net's parameters (the backward already ran on the device)."""
+
+    @staticmethod
+    def forward(ctx, trainer, x_t, cond, time, target, weight, loss_type, *params):
+        loss, _ = trainer.step(x_t, cond, time, target, weight, loss_type)
+        ctx.trainer = trainer
+        ctx.names = list(trainer.grads.keys())
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        tr = ctx.trainer
+        grads = tuple(gout * tr.grads[k] for k in ctx.names)   # fresh tensors: the trainer's buffers are rewritten every step
+        return (None,) * 7 + grads
+
+
+def supports_training(net) -> bool:
+    cfg = getattr(net, "_plan_config", None)
+    return cfg is not None and cfg()["variant"] == _lib.HD_HICEDRN
+
+
+def training_loss(net, x_t, time, cond, target, weight, loss_type: str):
+    """Scalar loss with a grad_fn over `net.parameters()` (named_parameters order)."""
+    batch = x_t.shape[0]
+    tr = getattr(net, "_trainer", None)
+    if tr is None or not tr.matches(net, batch):
+        if tr is not None:
+            tr.destroy()
+        tr = Trainer(net, batch)
+        object.__setattr__(net, "_trainer", tr)
+    params = [p for _, p in net.named_parameters()]
+    return _TrainStep.apply(tr, x_t, cond, time, target, weight, loss_type, *params)

@@ -122,6 +122,37 @@ HD_API int hd_ssim_mse_tiles(const float* a, const float* b, const float* window
                       int32_t rescale, void* stream);
 
 /* -------------------------------------------------------------------------------------------------------------
+ * Training step.  Replaces, for hicedrn_Diff -- the model train.py trains (train.py:84-107) -- the
+ * forward + loss + loss.backward() of one iteration (train.py:120-129): eps = model(x_t, t, cond)
+ * (src/model/hicedrn_Diff.py:267-289), loss = mean(|eps - target|^p * weight[b]) (p_losses, hicdiff_condition.py:741-746,
+ * loss_fn :706-713; weight = p2_loss_weight[t]), and d loss / d parameter for every parameter of the net.
+ *   hd_trainer_create    cfg.variant must be HD_HICEDRN; `batch` tiles per step (fixed per trainer)
+ *   hd_trainer_bind      once per state_dict entry (key without the `model.` prefix): `param` is READ IN PLACE at every
+ *                        step (so any optimizer may update it between steps), `grad` (same shape, fp32) is OVERWRITTEN by
+ *                        every step; both are device pointers the caller keeps alive
+ *   hd_trainer_step      x_t = q_sample(x_start, t, noise) (:698-704), cond (NULL iff self_condition == 0), time fp32 [B],
+ *                        target fp32 [B,1,64,64] (the noise), weight fp32 [B]; loss_type 0 = l1, 1 = l2.
+ *                        eps_out (optional) fp32 [B,1,64,64]; loss_out: device fp32 scalar.
+ * Gradients are deterministic (fixed-order two-pass reductions, no atomics).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct hd_trainer hd_trainer;
+HD_API int hd_trainer_create(const hd_config* cfg, int32_t batch, hd_trainer** out);
+HD_API int hd_trainer_bind(hd_trainer* trainer, const char* key, const float* param, float* grad, const int64_t* shape,
+                    int32_t ndim);
+HD_API int hd_trainer_finalize(hd_trainer* trainer, void* stream);
+HD_API int hd_trainer_step(hd_trainer* trainer, const float* x_t, const float* cond, const float* time, const float* target,
+                    const float* weight, int32_t loss_type, float* eps_out, float* loss_out, void* stream);
+/* Launch groups of one step / per-kernel-family timing of one step as JSON {"family": {"ms", "flops", "ops"}} / bytes held */
+HD_API int hd_trainer_num_launches(hd_trainer* trainer);
+HD_API int hd_trainer_profile(hd_trainer* trainer, int32_t reps, char* buf, int64_t buflen, void* stream);
+HD_API int64_t hd_trainer_device_bytes(hd_trainer* trainer);
+HD_API void hd_trainer_destroy(hd_trainer* trainer);
+/* The two conv gradients as single operators (256 -> 256, 3x3 "same", 64x64 tiles; activations bf16 NHWC as uint16):
+ * dw fp32 [256,256,3,3] = d/dW of conv2d(x, W) given dy; dx = d/dx given dy and W (fp32, reference layout).  Synchronise. */
+HD_API int hd_op_conv3x3_wgrad(const uint16_t* x, const uint16_t* dy, float* dw, int32_t B, void* stream);
+HD_API int hd_op_conv3x3_dgrad(const uint16_t* dy, const float* w, uint16_t* dx, int32_t B, void* stream);
+
+/* -------------------------------------------------------------------------------------------------------------
  * Tiling.  hd_tile_extract replaces splitPieces (processdata/PrepareData_linear.py:25-46): zero-pad the n x n
  * matrix to a multiple of `piece`, enumerate block rows i and block columns j >= i with (j - i) <= band_blocks
  * (= 4 * int(40000 / res)), row-major.  hd_tile_scatter is its exact inverse (the reference has none): tile k is

@@ -352,6 +352,17 @@ def p_losses(eps_fn, buf: SD, noisy, clean, t, noise, *, loss_type="l2", self_co
     return loss.mean()
 
 
+def p_losses_and_grads(sd: SD, buf: SD, noisy, clean, t, noise, *, loss_type="l2", self_condition=True, num_blocks=32):
+    """One training iteration's loss and d loss / d parameter for the hicedrn_Diff eps-net: what `loss = diffusion(x);
+    loss.backward()` leaves in `.grad` (train.py:127-128) -- torch.autograd over the restated forward (the reference has no
+    hand-written backward to cite).  Returns (loss, {state_dict key: grad})."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if torch.is_floating_point(v)}
+    loss = p_losses(lambda x, tt, c: hicedrn_forward(leaves, x, tt, c, self_condition=self_condition, num_blocks=num_blocks),
+                    buf, noisy, clean, t, noise, loss_type=loss_type, self_condition=self_condition)
+    grads = torch.autograd.grad(loss, list(leaves.values()))
+    return loss.detach(), dict(zip(leaves.keys(), grads))
+
+
 # --------------------------------------------------------------------------------------------------------------
 # DDRM sampler for the denoising operator     src/functions/denoising.py:6-111, svd_replacement.py:148-168
 # --------------------------------------------------------------------------------------------------------------

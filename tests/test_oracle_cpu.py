@@ -135,3 +135,33 @@ def test_oracle_against_live_reference_unet_cond():
     t = torch.tensor([123])
     with torch.no_grad():
         assert torch.equal(ref(x, t, c), O.unet_forward(ref.state_dict(), x, t, c, self_condition=True))
+
+
+@pytest.mark.parametrize("name", ["cond_l2", "uncond_l1"])
+def test_oracle_training_gradients_reproduce_reference_golden(name):
+    """p_losses_and_grads against the per-parameter summaries of the reference's own loss.backward()
+    (oracle/make_golden_train.py asserted bit-equality of the FULL gradients when it wrote the fixture)."""
+    import json
+
+    gold = json.loads((helpers.GOLD / "hicedrn_train.json").read_text())
+    c = gold["cases"][name]
+    from hicdiff_b200.model.hicedrn_Diff import hicedrn_Diff
+
+    torch.manual_seed(gold["weight_seed"])
+    net = hicedrn_Diff(number_resnet=c["blocks"], self_condition=c["self_condition"])
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    clean, noisy = O.synthetic_tiles(c["B"], seed=gold["tile_seed"])
+    t = torch.tensor(c["t"], dtype=torch.long)
+    noise = torch.randn(c["B"], 1, 64, 64, generator=torch.Generator().manual_seed(gold["noise_seed"]))
+    buf = O.diffusion_buffers(c["schedule"], c["T"])
+    loss, grads = O.p_losses_and_grads(sd, buf, noisy, clean, t, noise, loss_type=c["loss_type"],
+                                       self_condition=c["self_condition"], num_blocks=c["blocks"])
+    assert abs(float(loss) - c["loss"]) <= 1e-6 * max(1.0, abs(c["loss"]))
+    assert set(grads) == set(c["grads"])
+    for k, s in c["grads"].items():
+        g = grads[k].reshape(-1)
+        got = g[torch.tensor(s["idx"])].double()
+        want = torch.tensor(s["val"], dtype=torch.float64)
+        scale = max(s["norm"] / max(g.numel(), 1) ** 0.5, 1e-12)      # RMS of the tensor: thread-count-dependent fp32 order only
+        assert float((got - want).abs().max()) <= 1e-3 * scale + 1e-9, k
+        assert abs(float(g.double().norm()) - s["norm"]) <= 1e-4 * s["norm"] + 1e-12, k
