@@ -288,12 +288,12 @@ cudaError_t ssim_mse_tiles_run(const float* a, const float* b, const float* wind
 // wgrad.cu / train_kernels.cu -- the HiCEDRN training step (backward of conv / FiLM / SiLU / time MLPs, loss)
 // ---------------------------------------------------------------------------------------------
 struct WgradLaunch {
-    CUtensorMap tmG, tmX[3];   // planar [B, C, H, W] bf16 copies of dY and of the conv input pre-shifted by dx = -1, 0, +1
+    CUtensorMap tmG, tmX;   // 5-D views {64 ch, W, H, B, C / 64} of the NHWC dY and conv input
     int kb_total, H, nsplit;
     float* part;            // [nsplit][9][256][256] fp32
 };
-int wgrad_prepare(const bf16* g_planar, const bf16* x_planar3, int B, int H, int W, int C, int nsplit, float* part,
-                  WgradLaunch* out, char* err, int errlen);
+int wgrad_prepare(const bf16* g, const bf16* x, int B, int H, int W, int C, int nsplit, float* part, WgradLaunch* out, char* err,
+                  int errlen);
 cudaError_t wgrad_run(const WgradLaunch& l, cudaStream_t s);
 // dW [256, 256, 3, 3] (+)= scale * sum over the K splits
 cudaError_t wgrad_reduce_run(const float* part, int nsplit, float scale, int accumulate, float* dw, cudaStream_t s);
@@ -312,8 +312,6 @@ int colsum_parts(long long M);
 // out[c] (+)= scale * sum_m x[m, c]
 cudaError_t colsum_run(const bf16* x, long long M, int C, float* part, float scale, int accumulate, float* out, cudaStream_t s);
 cudaError_t sum_parts_run(const float* part, int nparts, int n, float scale, int accumulate, float* out, cudaStream_t s);
-// shifts == 3: three copies out[sh][B][C][P], copy sh holds the image shifted by dx = sh - 1 along x (zero fill); W must be 64
-cudaError_t nhwc_to_planar_run(const bf16* in, bf16* out, int B, int P, int C, int shifts, cudaStream_t s);
 cudaError_t add_bf16_run(const bf16* a, const bf16* b, bf16* y, long long n, cudaStream_t s);
 // dw[(c * nk + k) * 9 + tap] = sum_{b,y,x} G[b,y,x,c] * u_k[b, y + sgn*(ky-1), x + sgn*(kx-1)];  part: [B * 8][nk][9][256]
 cudaError_t thin_wgrad_run(const bf16* G, const float* u0, const float* u1, int sgn, int B, float* part, float* dw, cudaStream_t s);

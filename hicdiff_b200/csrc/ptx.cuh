@@ -295,10 +295,27 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
+// MN-major, 128-byte-swizzled operand: the contiguous dimension is M (or N), 64 elements = 128 B per K row, atoms of 8 K rows
+// = 1024 B.  Canonical form ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units (CuTe mma_traits_sm100.hpp: make_umma_desc):
+// LBO = byte stride between 64-element groups along M/N, SBO = byte stride between groups of 8 K rows.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4);
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
 // kind::f16 instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, both K-major,
 // N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+// same with both operands MN-major (a_major bit 15, b_major bit 16)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(uint32_t m, uint32_t n) {
+    return make_idesc_bf16(m, n) | (1u << 15) | (1u << 16);
 }
 
 // ---------------------------------------------------------------- warp-level MMA (small per-head contractions)

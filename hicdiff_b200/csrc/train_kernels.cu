@@ -7,7 +7,6 @@
 //   film_silu_fwd       s = SiLU(a * (scale + 1) + shift)                  hicedrn_Diff.py:175-178,201-203
 //   film_silu_bwd       da = ds * SiLU'(h) * (scale + 1), per-(sample, channel) sums for d scale / d shift
 //   colsum              per-channel sums over all pixels (bias gradients)
-//   nhwc_to_planar      [B, P, C] -> [B, C, P] (the K-major operand layout of wgrad.cu)
 //   thin_wgrad          weight gradient of the 1- or 2-plane head conv / the 1-channel tail conv
 //   loss_grad           weighted l1 / l2 loss and its gradient             hicdiff_condition.py:706-713,741-746
 //   linear_bwd_*        the time-embedding MLPs (a few rows; fp32)         hicedrn_Diff.py:232-246,189-200
@@ -180,34 +179,6 @@ __global__ void sum_parts_kernel(const float* __restrict__ part, int nparts, int
 }
 
 // ------------------------------------------------------------------------------------------------ layout
-// [B, P, C] -> [B, C, P], 64 x 64 tiles through shared memory; grid (P/64, C/64, B).  A tile is one 64-pixel image row, so
-// shifts == 3 can also emit the row shifted by dx = -1 / 0 / +1 pixels with zero fill (copy stride B * C * P elements).
-__global__ void __launch_bounds__(256)
-nhwc_to_planar_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int P, int C, int shifts, size_t copy_stride) {
-    __shared__ bf16 t[64][72];
-    const int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64, b = blockIdx.z;
-    const bf16* src = in + (static_cast<size_t>(b) * P + p0) * C + c0;
-    for (int i = threadIdx.x; i < 512; i += 256) {
-        const int p = i >> 3, ch = i & 7;
-        *reinterpret_cast<uint4*>(&t[p][ch * 8]) = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(p) * C + ch * 8));
-    }
-    __syncthreads();
-    for (int sh = 0; sh < shifts; ++sh) {
-        const int dx = shifts == 3 ? sh - 1 : 0;
-        bf16* dst = out + sh * copy_stride + (static_cast<size_t>(b) * C + c0) * P + p0;
-        for (int i = threadIdx.x; i < 512; i += 256) {
-            const int c = i & 63, pc = i >> 6;
-            __align__(16) bf16 v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int px = pc * 8 + j + dx;
-                v[j] = (px >= 0 && px < 64) ? t[px][c] : __float2bfloat16(0.f);
-            }
-            *reinterpret_cast<uint4*>(dst + static_cast<size_t>(c) * P + pc * 8) = *reinterpret_cast<const uint4*>(v);
-        }
-    }
-}
-
 // y = a + b (bf16, 16-byte chunks)
 __global__ void __launch_bounds__(256)
 add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ y, long long chunks) {
@@ -424,11 +395,6 @@ cudaError_t colsum_run(const bf16* x, long long M, int C, float* part, float sca
 }
 cudaError_t sum_parts_run(const float* part, int nparts, int n, float scale, int accumulate, float* out, cudaStream_t s) {
     sum_parts_kernel<<<(n + 255) / 256, 256, 0, s>>>(part, nparts, n, scale, accumulate, out);
-    return cudaGetLastError();
-}
-cudaError_t nhwc_to_planar_run(const bf16* in, bf16* out, int B, int P, int C, int shifts, cudaStream_t s) {
-    if (P % 64 != 0 || C % 64 != 0 || (shifts != 1 && shifts != 3)) return cudaErrorInvalidValue;
-    nhwc_to_planar_kernel<<<dim3(P / 64, C / 64, B), 256, 0, s>>>(in, out, P, C, shifts, static_cast<size_t>(B) * C * P);
     return cudaGetLastError();
 }
 cudaError_t add_bf16_run(const bf16* a, const bf16* b, bf16* y, long long n, cudaStream_t s) {

@@ -169,10 +169,9 @@ int build(hd_trainer* t) {
     std::vector<bf16*> X(nb + 1), A(nb), Sx(nb);
     for (int i = 0; i <= nb; ++i) if (dalloc(t, &X[i], act_elems * 2)) return 1;
     for (int i = 0; i < nb; ++i) if (dalloc(t, &A[i], act_elems * 2) || dalloc(t, &Sx[i], act_elems * 2)) return 1;
-    bf16 *BT = nullptr, *DBT = nullptr, *GX[2] = {nullptr, nullptr}, *DS = nullptr, *Tg = nullptr, *Tx = nullptr;
+    bf16 *BT = nullptr, *DBT = nullptr, *GX[2] = {nullptr, nullptr}, *DS = nullptr;
     if (dalloc(t, &BT, act_elems * 2) || dalloc(t, &DBT, act_elems * 2) || dalloc(t, &GX[0], act_elems * 2) ||
-        dalloc(t, &GX[1], act_elems * 2) || dalloc(t, &DS, act_elems * 2) || dalloc(t, &Tg, act_elems * 2) ||
-        dalloc(t, &Tx, act_elems * 2 * 3))
+        dalloc(t, &GX[1], act_elems * 2) || dalloc(t, &DS, act_elems * 2))
         return 1;
     float *ws1 = nullptr, *ws2 = nullptr, *film_part = nullptr, *cs_part = nullptr, *cs_g = nullptr, *thin_part = nullptr,
           *loss_part = nullptr;
@@ -181,13 +180,14 @@ int build(hd_trainer* t) {
         dalloc(t, &cs_part, static_cast<size_t>(colsum_parts(M)) * F * 4) || dalloc(t, &cs_g, F * 4) ||
         dalloc(t, &thin_part, static_cast<size_t>(B) * 8 * 2 * 9 * F * 4) || dalloc(t, &loss_part, static_cast<size_t>(loss_parts()) * 4))
         return 1;
-    WgradLaunch wl1, wl2;
-    {
+    // weight gradient of one conv use: dW partials of conv(xin) given its output gradient g, into workspace ws
+    auto wgrad = [&](const std::string& tag, const bf16* g, const bf16* xin, float* ws) -> bool {
+        WgradLaunch wl;
         char e[256];
-        if (wgrad_prepare(Tg, Tx, B, S, S, F, WG_SPLITS, ws1, &wl1, e, sizeof(e))) return tfail("%s", e);
-        if (wgrad_prepare(Tg, Tx, B, S, S, F, WG_SPLITS, ws2, &wl2, e, sizeof(e))) return tfail("%s", e);
-    }
-    const double conv_flops = 2.0 * M * F * 9.0 * F;
+        if (wgrad_prepare(g, xin, B, S, S, F, WG_SPLITS, ws, &wl, e, sizeof(e))) { tfail("%s: %s", tag.c_str(), e); return false; }
+        b.push("wgrad", tag, [wl](cudaStream_t s) { return wgrad_run(wl, s); }, 2.0 * M * F * 9.0 * F);
+        return true;
+    };
 
     // ---------------------------------------------------------------- per-step weight preparation (parameters move every step)
     for (int i = 0; i <= nb; ++i) {
@@ -276,12 +276,7 @@ int build(hd_trainer* t) {
     {
         float *gw = bt_w->g, *gb = bt_b->g;
         b.push("colsum", "body_tail.bias_grad", [=](cudaStream_t s) { return colsum_run(DBT, M, F, cs_part, 1.0f, 0, gb, s); });
-        const bf16* xin = X[nb];
-        b.push("transpose", "body_tail.planar", [=](cudaStream_t s) {
-            cudaError_t e = nhwc_to_planar_run(DBT, Tg, B, P, F, 1, s);
-            return e != cudaSuccess ? e : nhwc_to_planar_run(xin, Tx, B, P, F, 3, s);
-        });
-        b.push("wgrad", "body_tail.wgrad", [=](cudaStream_t s) { return wgrad_run(wl1, s); }, conv_flops);
+        if (!wgrad("body_tail.wgrad", DBT, X[nb], ws1)) return 1;
         b.push("reduce", "body_tail.wgrad_reduce", [=](cudaStream_t s) { return wgrad_reduce_run(ws1, WG_SPLITS, 1.0f, 0, gw, s); });
         if (!b.conv("body_tail.dgrad", DBT, wqd[nb], F, GX[0], ConvEpilogue())) return 1;
     }
@@ -295,11 +290,7 @@ int build(hd_trainer* t) {
         const int off = i * 2 * F;
         float *gw = cw[i]->g, *gb = cb[i]->g;
         b.push("colsum", pre + ".colsum_g", [=](cudaStream_t s) { return colsum_run(g, M, F, cs_part, 1.0f, 0, cs_g, s); });
-        b.push("transpose", pre + ".planar#2", [=](cudaStream_t s) {
-            cudaError_t e = nhwc_to_planar_run(g, Tg, B, P, F, 1, s);
-            return e != cudaSuccess ? e : nhwc_to_planar_run(si, Tx, B, P, F, 3, s);
-        });
-        b.push("wgrad", pre + ".wgrad#2", [=](cudaStream_t s) { return wgrad_run(wl2, s); }, conv_flops);
+        if (!wgrad(pre + ".wgrad#2", g, si, ws2)) return 1;
         ConvEpilogue e2;
         e2.out_scale = 0.1f;
         if (!b.conv(pre + ".dgrad#2", g, wqd[i], F, DS, e2)) return 1;
@@ -307,11 +298,7 @@ int build(hd_trainer* t) {
             return film_silu_bwd_run(DS, ai, DS, film, dfilm, ld, off, B, P, F, film_part, s);
         });
         b.push("reduce", pre + ".bias_grad", [=](cudaStream_t s) { return edrn_bias_grad_run(film, dfilm, ld, off, B, cs_g, 0.1f, gb, F, s); });
-        b.push("transpose", pre + ".planar#1", [=](cudaStream_t s) {
-            cudaError_t e = nhwc_to_planar_run(DS, Tg, B, P, F, 1, s);
-            return e != cudaSuccess ? e : nhwc_to_planar_run(xi, Tx, B, P, F, 3, s);
-        });
-        b.push("wgrad", pre + ".wgrad#1", [=](cudaStream_t s) { return wgrad_run(wl1, s); }, conv_flops);
+        if (!wgrad(pre + ".wgrad#1", DS, xi, ws1)) return 1;
         b.push("reduce", pre + ".wgrad_reduce", [=](cudaStream_t s) {
             cudaError_t e = wgrad_reduce_run(ws1, WG_SPLITS, 1.0f, 0, gw, s);
             return e != cudaSuccess ? e : wgrad_reduce_run(ws2, WG_SPLITS, 0.1f, 1, gw, s);
@@ -486,27 +473,18 @@ void hd_trainer_destroy(hd_trainer* t) {
 int hd_op_conv3x3_wgrad(const uint16_t* x, const uint16_t* dy, float* dw, int32_t B, void* stream) {
     if (!x || !dy || !dw || B < 1) return tfail("hd_op_conv3x3_wgrad: bad argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const size_t elems = static_cast<size_t>(B) * P * F;
-    bf16 *tg = nullptr, *tx = nullptr;
     float* ws = nullptr;
-    T_TRY(cudaMalloc(&tg, elems * 2));
-    T_TRY(cudaMalloc(&tx, elems * 2 * 3));
     T_TRY(cudaMalloc(&ws, wgrad_part_bytes(WG_SPLITS)));
     WgradLaunch wl;
     char e[256];
-    int rc = wgrad_prepare(tg, tx, B, S, S, F, WG_SPLITS, ws, &wl, e, sizeof(e));
+    int rc = wgrad_prepare(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), B, S, S, F, WG_SPLITS, ws, &wl, e, sizeof(e));
     cudaError_t ce = cudaSuccess;
-    const char* stage = "transpose";
-    if (!rc) ce = nhwc_to_planar_run(reinterpret_cast<const bf16*>(dy), tg, B, P, F, 1, s);
-    if (!rc && ce == cudaSuccess) ce = nhwc_to_planar_run(reinterpret_cast<const bf16*>(x), tx, B, P, F, 3, s);
+    if (!rc) ce = wgrad_run(wl, s);
+    if (!rc && ce == cudaSuccess) ce = wgrad_reduce_run(ws, WG_SPLITS, 1.0f, 0, dw, s);
     if (!rc && ce == cudaSuccess) ce = cudaStreamSynchronize(s);
-    if (!rc && ce == cudaSuccess) { stage = "wgrad_kernel"; ce = wgrad_run(wl, s); }
-    if (!rc && ce == cudaSuccess) ce = cudaStreamSynchronize(s);
-    if (!rc && ce == cudaSuccess) { stage = "reduce"; ce = wgrad_reduce_run(ws, WG_SPLITS, 1.0f, 0, dw, s); }
-    if (!rc && ce == cudaSuccess) ce = cudaStreamSynchronize(s);
-    cudaFree(tg); cudaFree(tx); cudaFree(ws);
+    cudaFree(ws);
     if (rc) return tfail("%s", e);
-    if (ce != cudaSuccess) return tfail("hd_op_conv3x3_wgrad failed in %s: %s", stage, cudaGetErrorString(ce));
+    if (ce != cudaSuccess) return tfail("hd_op_conv3x3_wgrad failed: %s", cudaGetErrorString(ce));
     return 0;
 }
 

@@ -2,18 +2,19 @@
 //
 //     dW[co, ci, ky, kx] = sum_{b, y, x} dY[b, y, x, co] * X[b, y + ky - 1, x + kx - 1, ci]
 //
-// i.e. nine GEMMs (one per tap) with M = Cout, N = Cin and K = B * H * W pixels.  Both operands are read from PLANAR copies
-// ([B, C, H, W] bf16, made by nhwc_to_planar_kernel) so that a K block -- one image row of 64 pixels -- is a K-major,
-// 128-byte-swizzled TMA box {64 px, 1 row, 256 channels}: exactly the operand layout conv_gemm.cu uses.  The tap's dy shift
-// is a TMA row coordinate (rows outside the image are skipped: they only meet the conv's zero padding); its dx shift cannot
-// be one -- a TMA box must start on a 16-byte boundary of the innermost dimension and one pixel is 2 bytes (measured: an
-// illegal-instruction fault) -- so nhwc_to_planar_kernel writes THREE planar copies of X, pre-shifted by dx = -1, 0, +1
-// with zero fill, and tap (dy, dx) reads copy dx.
+// i.e. nine GEMMs (one per tap) with M = Cout, N = Cin and K = B * H * W pixels.  Both operands are read straight from the
+// NHWC bf16 activations as MN-MAJOR tiles: a K block is one image row of 64 pixels, and one 5-D TMA box
+// {64 ch, 64 px, 1 row, 1 img, 4 chunks} lands in shared memory as [chunk][px][64 ch] -- K rows (pixels) of 128 B, 8-pixel
+// swizzle atoms 1 KiB apart (SBO), 64-channel groups 8 KiB apart (LBO): the canonical MN-major SWIZZLE_128B operand of
+// tcgen05.mma (a_major = b_major = 1 in the instruction descriptor).  The tap's (dy, dx) shift is a TMA coordinate offset
+// of the H / W dimensions whose out-of-range pixels the TMA unit zero-fills (the conv's zero padding).  (A first version
+// read planar [B, C, H, W] copies as K-major tiles; there dx falls on the innermost dimension, where a TMA box must start
+// on a 16-byte boundary -- an illegal-instruction fault -- and the transposes cost more than the GEMM.)
 //
-// One CTA = one (tap, K split): both 128-row halves of dY^T and the whole X^T box per stage (64 KiB, 3 stages), two
-// M = 128 x N = 256 fp32 accumulators = all 512 TMEM columns, 8 MMAs per stage.  Warp 0 produces (TMA), warp 1 issues, warps
-// 2-5 drain the accumulators into a [split][tap][co][ci] fp32 workspace that wgrad_reduce_kernel sums in a fixed order
-// (deterministic; no atomics) into the reference's [Cout, Cin, 3, 3] layout.
+// One CTA = one (tap, K split): the whole dY row tile (both 128-channel halves) and the whole X row tile per stage (64 KiB,
+// 3 stages), two M = 128 x N = 256 fp32 accumulators = all 512 TMEM columns, 8 MMAs per stage.  Warp 0 produces (TMA), warp 1
+// issues, warps 2-5 drain the accumulators into a [split][tap][co][ci] fp32 workspace that wgrad_reduce_kernel sums in a
+// fixed order (deterministic; no atomics) into the reference's [Cout, Cin, 3, 3] layout.
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -25,8 +26,8 @@ namespace {
 constexpr int WG_C = 256;
 constexpr int WG_THREADS = 192;
 constexpr int WG_STAGES = 3;
-constexpr uint32_t WG_A_BYTES = WG_C * 64 * 2;   // dY^T: 256 rows (co) x 64 px
-constexpr uint32_t WG_B_BYTES = WG_C * 64 * 2;   // X^T : 256 rows (ci) x 64 px
+constexpr uint32_t WG_A_BYTES = WG_C * 64 * 2;   // dY row tile: [4 chunks][64 px][64 co]
+constexpr uint32_t WG_B_BYTES = WG_C * 64 * 2;   // X  row tile: [4 chunks][64 px][64 ci]
 constexpr uint32_t WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;
 constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
 
@@ -38,8 +39,7 @@ struct WgradKArgs {
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
-wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
-             const __grid_constant__ CUtensorMap tmX2, const WgradKArgs a) {
+wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const WgradKArgs a) {
     extern __shared__ uint8_t wg_smem_raw[];
     uint8_t* smem = wg_smem_raw + ((1024u - (ptx::smem_u32(wg_smem_raw) & 1023u)) & 1023u);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
@@ -50,12 +50,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tap = blockIdx.x % 9, split = blockIdx.x / 9;
     const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-    const CUtensorMap* tmX = dx < 0 ? &tmX0 : (dx == 0 ? &tmX1 : &tmX2);   // the copy of X pre-shifted by dx
     const int kb0 = static_cast<int>(static_cast<long long>(a.kb_total) * split / a.nsplit);
     const int kb1 = static_cast<int>(static_cast<long long>(a.kb_total) * (split + 1) / a.nsplit);
 
     if (warp == 0) {
-        if (lane == 0) { ptx::prefetch_tmap(&tmG); ptx::prefetch_tmap(tmX); }
+        if (lane == 0) { ptx::prefetch_tmap(&tmG); ptx::prefetch_tmap(&tmX); }
         __syncwarp();
         ptx::tmem_alloc(tmem_slot, 512);
         ptx::tmem_relinquish();
@@ -80,16 +79,17 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
             if (ptx::elect_one()) {
                 uint8_t* sA = smem + stage * WG_STAGE_BYTES;
                 ptx::mbar_arrive_expect_tx(&full_bar[stage], WG_STAGE_BYTES);
-                ptx::tma_load_4d(sA, &tmG, &full_bar[stage], 0, y, 0, b);
-                ptx::tma_load_4d(sA + WG_A_BYTES, tmX, &full_bar[stage], 0, y + dy, 0, b);
+                ptx::tma_load_5d(sA, &tmG, &full_bar[stage], 0, 0, y, b, 0);
+                ptx::tma_load_5d(sA + WG_A_BYTES, &tmX, &full_bar[stage], 0, dx, y + dy, b, 0);
             }
             __syncwarp();
             if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
         }
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
-        constexpr uint32_t idesc = ptx::make_idesc_bf16(128, WG_C);
-        const uint64_t desc0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem));
+        constexpr uint32_t idesc = ptx::make_idesc_bf16_mn(128, WG_C);
+        constexpr uint32_t K16_STEP = 2048u >> 4;   // 16 pixels = two 1 KiB swizzle atoms
+        const uint64_t desc0 = ptx::make_mnmajor_sw128_desc(ptx::smem_u32(smem), 64 * 128, 1024);
         int stage = 0;
         uint32_t phase = 0;
         bool first = true;
@@ -106,7 +106,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
                     const uint64_t dam = da + static_cast<uint64_t>((mh * (WG_A_BYTES / 2)) >> 4);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        ptx::umma_bf16(tmem_base + mh * WG_C, dam + 2u * k, db + 2u * k, idesc, (first && k == 0) ? 0u : 1u);
+                        ptx::umma_bf16(tmem_base + mh * WG_C, dam + K16_STEP * k, db + K16_STEP * k, idesc, (first && k == 0) ? 0u : 1u);
                 }
                 ptx::umma_commit(&empty_bar[stage]);
             }
@@ -172,8 +172,8 @@ wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, float scale, int
 
 }  // namespace
 
-int wgrad_prepare(const bf16* g_planar, const bf16* x_planar3, int B, int H, int W, int C, int nsplit, float* part,
-                  WgradLaunch* out, char* err, int errlen) {
+int wgrad_prepare(const bf16* g, const bf16* x, int B, int H, int W, int C, int nsplit, float* part, WgradLaunch* out, char* err,
+                       int errlen) {
     if (C != WG_C || W != 64) {
         snprintf(err, errlen, "wgrad: built for 256 channels and 64-pixel rows (got C = %d, W = %d)", C, W);
         return 1;
@@ -182,12 +182,12 @@ int wgrad_prepare(const bf16* g_planar, const bf16* x_planar3, int B, int H, int
         snprintf(err, errlen, "wgrad: %d K splits leave fewer than 4 image rows per CTA", nsplit);
         return 1;
     }
-    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
-    cuuint64_t str[3] = {(cuuint64_t)W * 2, (cuuint64_t)W * H * 2, (cuuint64_t)W * H * C * 2};
-    cuuint32_t box[4] = {64, 1, (cuuint32_t)WG_C, 1};
-    if (encode_tmap_bf16(&out->tmG, g_planar, 4, dims, str, box, err, errlen)) return 1;
-    for (int i = 0; i < 3; ++i)
-        if (encode_tmap_bf16(&out->tmX[i], x_planar3 + static_cast<size_t>(i) * B * C * H * W, 4, dims, str, box, err, errlen)) return 1;
+    // [B, H, W, C] viewed as {64 ch, W, H, B, C / 64 chunks}
+    cuuint64_t dims[5] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)C / 64};
+    cuuint64_t str[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, 128};
+    cuuint32_t box[5] = {64, 64, 1, 1, (cuuint32_t)C / 64};
+    if (encode_tmap_bf16(&out->tmG, g, 5, dims, str, box, err, errlen)) return 1;
+    if (encode_tmap_bf16(&out->tmX, x, 5, dims, str, box, err, errlen)) return 1;
     out->kb_total = B * H;
     out->H = H;
     out->nsplit = nsplit;
@@ -201,7 +201,7 @@ cudaError_t wgrad_run(const WgradLaunch& l, cudaStream_t s) {
     WgradKArgs a;
     a.kb_total = l.kb_total; a.nsplit = l.nsplit; a.H = l.H; a.part = l.part;
 
-    wgrad_kernel<<<9 * l.nsplit, WG_THREADS, WG_SMEM, s>>>(l.tmG, l.tmX[0], l.tmX[1], l.tmX[2], a);
+    wgrad_kernel<<<9 * l.nsplit, WG_THREADS, WG_SMEM, s>>>(l.tmG, l.tmX, a);
     return cudaGetLastError();
 }
 

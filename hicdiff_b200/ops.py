@@ -193,7 +193,7 @@ def tile_scatter(tiles, n, piece=64, band_blocks=4):
 
 def conv3x3_wgrad_nhwc(x, dy):
     """d/dW of conv2d(x, W, padding=1) for a 256 -> 256 3x3 conv over 64x64 tiles: x, dy [B,64,64,256] bf16 -> fp32
-    [256,256,3,3] (planar transposes + tcgen05 wgrad kernel + fixed-order split reduction)."""
+    [256,256,3,3] (tcgen05 wgrad kernel over MN-major NHWC tiles + fixed-order split reduction)."""
     lib = _lib.load()
     _need_cuda(x, dy)
     x, dy = _bf16c(x), _bf16c(dy)

@@ -118,12 +118,33 @@ class Trainer:
         return int(_lib.load().hd_trainer_num_launches(self._handle))
 
 
+def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """DDP's gradient exchange for BASELINE config 5: ONE all-reduce over the trainer's flat fp32 gradient buffer (NCCL over
+    NVLink on GPUs; any backend works), averaged over the ranks.  No-op without an initialised process group."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return flat
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(dist.get_world_size(group))
+    return flat
+
+
+def enable_gradient_allreduce(net, group=None, enabled: bool = True) -> None:
+    """Data-parallel replicas (one process per GPU, torch.distributed initialised by the caller): average the gradients
+    across ranks inside every training step, as DistributedDataParallel would."""
+    object.__setattr__(net, "_grad_allreduce", (group,) if enabled else None)
+
+
 class _TrainStep(torch.autograd.Function):
     """loss = trainer.step(...) as an autograd node over the net's parameters (the backward already ran on the device)."""
 
     @staticmethod
     def forward(ctx, trainer, x_t, cond, time, target, weight, loss_type, *params):
         loss, _ = trainer.step(x_t, cond, time, target, weight, loss_type)
+        ar = getattr(trainer.net, "_grad_allreduce", None)
+        if ar is not None:
+            allreduce_mean_(trainer.flat_grad, ar[0])
         ctx.trainer = trainer
         ctx.names = list(trainer.grads.keys())
         return loss
