@@ -323,6 +323,7 @@ cudaError_t linear_bwd_weight_run(const float* dY, int ldy, int off, const float
                                   int in_act, float* dW, float* db, cudaStream_t s);
 cudaError_t linear_bwd_input_run(const float* dY, int ldy, int off, const float* W, int rows, int in_f, int out_f, int accumulate,
                                  float* dX, int ldx, cudaStream_t s);
+cudaError_t act_apply_run(const float* x, float* y, long long n, int act, cudaStream_t s);   // act: 1 SiLU, 2 GELU(erf)
 cudaError_t act_grad_run(float* d, const float* x, long long n, int act, cudaStream_t s);
 
 }  // namespace hd

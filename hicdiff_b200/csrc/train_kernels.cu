@@ -17,7 +17,13 @@
 namespace hd {
 namespace {
 
-__device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + __expf(-v)); }
+// sigmoid(v) = 0.5 * tanh(0.5 v) + 0.5 with one MUFU op (tanh.approx, abs. error ~2^-11: below the bf16 rounding of every
+// tensor these kernels write); the exact-division form made the FiLM kernels issue-bound instead of HBM-bound
+__device__ __forceinline__ float sigmoid_f(float v) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
+    return fmaf(0.5f, t, 0.5f);
+}
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
     float2 t;
@@ -56,32 +62,43 @@ __global__ void flip_tail_weight_kernel(const float* __restrict__ w, float* __re
 }
 
 // ------------------------------------------------------------------------------------------------ FiLM + SiLU
+constexpr int FB_CHUNKS = 16;   // pixel chunks per image (P = 4096 -> 256 pixels per CTA)
+
+// grid (FB_CHUNKS, B), C == 256: thread = (8-channel chunk cc = tid % 32, pixel lane pl = tid / 32); the thread's scale / shift
+// stay in registers and loads are issued four pixels ahead of their use
 __global__ void __launch_bounds__(256)
-film_silu_fwd_kernel(const uint4* __restrict__ a, uint4* __restrict__ s, const float* __restrict__ film, int ld, int off,
-                     int P, int C, long long total_chunks) {
-    const int cpp = C / 8;
-    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total_chunks; i += gridDim.x * 256ll) {
-        const int cc = static_cast<int>(i % cpp);
-        const long long pix = i / cpp;
-        const int b = static_cast<int>(pix / P);
-        const float* row = film + static_cast<size_t>(b) * ld + off + cc * 8;
-        float v[8];
-        unpack8(__ldg(a + i), v);
+film_silu_fwd_kernel(const uint4* __restrict__ a, uint4* __restrict__ s, const float* __restrict__ film, int ld, int off, int P) {
+    constexpr int C = 256, CPP = C / 8;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int cc = threadIdx.x & 31, pl = threadIdx.x >> 5;
+    const int ppc = P / FB_CHUNKS;
+    const float* row = film + static_cast<size_t>(b) * ld + off + cc * 8;
+    float sc1[8], sh[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float h = fmaf(v[j], __ldg(row + j) + 1.0f, __ldg(row + C + j));
-            v[j] = h * sigmoid_f(h);
+    for (int j = 0; j < 8; ++j) { sc1[j] = __ldg(row + j) + 1.0f; sh[j] = __ldg(row + C + j); }
+    const size_t base = (static_cast<size_t>(b) * P + static_cast<size_t>(chunk) * ppc) * CPP + cc;
+    for (int p = pl; p < ppc; p += 32) {
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = __ldg(a + base + static_cast<size_t>(p + 8 * k) * CPP);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float v[8];
+            unpack8(u[k], v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float h = fmaf(v[j], sc1[j], sh[j]);
+                v[j] = h * sigmoid_f(h);
+            }
+            s[base + static_cast<size_t>(p + 8 * k) * CPP] = pack8(v);
         }
-        s[i] = pack8(v);
     }
 }
 
-constexpr int FB_CHUNKS = 16;   // pixel chunks per image in the backward reduction (P = 4096 -> 256 pixels per CTA)
-
-// grid (FB_CHUNKS, B), C == 256: thread = (8-channel chunk cc = tid % 32, pixel lane pl = tid / 32)
+// same thread layout; ds and da may be the same buffer (each element is read before it is written by the same thread)
 __global__ void __launch_bounds__(256)
-film_silu_bwd_kernel(const uint4* __restrict__ ds, const uint4* __restrict__ a, uint4* __restrict__ da,
-                     const float* __restrict__ film, int ld, int off, int P, float* __restrict__ part) {
+film_silu_bwd_kernel(const uint4* ds, const uint4* __restrict__ a, uint4* da, const float* __restrict__ film, int ld, int off, int P,
+                     float* __restrict__ part) {
     constexpr int C = 256, CPP = C / 8;
     __shared__ float s_red[8][2 * C];
     const int b = blockIdx.y, chunk = blockIdx.x;
@@ -92,21 +109,30 @@ film_silu_bwd_kernel(const uint4* __restrict__ ds, const uint4* __restrict__ a, 
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sc1[j] = __ldg(row + j) + 1.0f; sh[j] = __ldg(row + C + j); acc_sc[j] = 0.f; acc_sh[j] = 0.f; }
     const size_t base = (static_cast<size_t>(b) * P + static_cast<size_t>(chunk) * ppc) * CPP + cc;
-    for (int p = pl; p < ppc; p += 8) {
-        const size_t i = base + static_cast<size_t>(p) * CPP;
-        float g[8], av[8];
-        unpack8(__ldg(ds + i), g);
-        unpack8(__ldg(a + i), av);
+    for (int p = pl; p < ppc; p += 32) {
+        uint4 ug[4], ua[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float h = fmaf(av[j], sc1[j], sh[j]);
-            const float sg = sigmoid_f(h);
-            const float dh = g[j] * (sg * (1.0f + h * (1.0f - sg)));
-            acc_sc[j] = fmaf(dh, av[j], acc_sc[j]);
-            acc_sh[j] += dh;
-            g[j] = dh * sc1[j];
+        for (int k = 0; k < 4; ++k) {
+            const size_t i = base + static_cast<size_t>(p + 8 * k) * CPP;
+            ug[k] = ds[i];
+            ua[k] = __ldg(a + i);
         }
-        da[i] = pack8(g);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float g[8], av[8];
+            unpack8(ug[k], g);
+            unpack8(ua[k], av);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float h = fmaf(av[j], sc1[j], sh[j]);
+                const float sg = sigmoid_f(h);
+                const float dh = g[j] * (sg * (1.0f + h * (1.0f - sg)));
+                acc_sc[j] = fmaf(dh, av[j], acc_sc[j]);
+                acc_sh[j] += dh;
+                g[j] = dh * sc1[j];
+            }
+            da[base + static_cast<size_t>(p + 8 * k) * CPP] = pack8(g);
+        }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s_red[pl][cc * 8 + j] = acc_sc[j]; s_red[pl][C + cc * 8 + j] = acc_sh[j]; }
@@ -152,7 +178,20 @@ colsum_part_kernel(const uint4* __restrict__ x, float* __restrict__ part, long l
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     const long long r0 = static_cast<long long>(blockIdx.x) * rpb;
     const long long r1 = r0 + rpb < M ? r0 + rpb : M;
-    for (long long r = r0 + pl; r < r1; r += lanes) {
+    long long r = r0 + pl;
+    for (; r + 3 * lanes < r1; r += 4 * lanes) {     // four rows in flight
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = __ldg(x + (r + k * lanes) * cpp + cc);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float v[8];
+            unpack8(u[k], v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += v[j];
+        }
+    }
+    for (; r < r1; r += lanes) {
         float v[8];
         unpack8(__ldg(x + r * cpp + cc), v);
 #pragma unroll
@@ -168,17 +207,27 @@ colsum_part_kernel(const uint4* __restrict__ x, float* __restrict__ part, long l
     }
 }
 
-// out[i] = scale * sum_k part[k][i] (+ out[i] when accumulate); n columns
-__global__ void sum_parts_kernel(const float* __restrict__ part, int nparts, int n, float scale, int accumulate,
-                                 float* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// out[i] = scale * sum_k part[k][i] (+ out[i] when accumulate); n columns.  32 columns per block, 8 threads per column each
+// summing a contiguous slice of the partials, combined in a fixed order (a single thread per column was latency-bound).
+__global__ void __launch_bounds__(256)
+sum_parts_kernel(const float* __restrict__ part, int nparts, int n, float scale, int accumulate, float* __restrict__ out) {
+    __shared__ float s_p[8][32];
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31), sl = threadIdx.x >> 5;
+    const int per = (nparts + 7) / 8;
+    const int k0 = sl * per, k1 = min(nparts, k0 + per);
     float t = 0.f;
-    for (int k = 0; k < nparts; ++k) t += part[static_cast<size_t>(k) * n + i];
-    out[i] = accumulate ? fmaf(scale, t, out[i]) : scale * t;
+    if (col < n)
+        for (int k = k0; k < k1; ++k) t += part[static_cast<size_t>(k) * n + col];
+    s_p[sl][threadIdx.x & 31] = t;
+    __syncthreads();
+    if (sl == 0 && col < n) {
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v += s_p[k][threadIdx.x];
+        out[col] = accumulate ? fmaf(scale, v, out[col]) : scale * v;
+    }
 }
 
-// ------------------------------------------------------------------------------------------------ layout
 // y = a + b (bf16, 16-byte chunks)
 __global__ void __launch_bounds__(256)
 add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ y, long long chunks) {
@@ -303,7 +352,7 @@ __global__ void sum_scalar_kernel(const float* __restrict__ part, int nparts, fl
 
 // ------------------------------------------------------------------------------------------------ small linears
 __device__ __forceinline__ float act_f(float v, int act) {
-    if (act == 1) return v * sigmoid_f(v);
+    if (act == 1) return v / (1.0f + expf(-v));
     if (act == 2) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
     return v;
 }
@@ -313,20 +362,36 @@ __device__ __forceinline__ float act_grad_f(float v, int act) {
     return 1.0f;
 }
 
-// dW[j, k] = sum_r dY[r, off + j] * act(X[r, k]);  db[j] = sum_r dY[r, off + j].  grid (ceil(in_f / 256), out_f)
+// dW[j, k] = sum_r dY[r, off + j] * act(X[r, k]);  db[j] = sum_r dY[r, off + j].  grid (ceil(in_f / 256), out_f / 8): a thread
+// owns column k for 8 output features, so each X element is loaded once per 8 (not once per 1) features
+constexpr int LBW_J = 8;
 __global__ void __launch_bounds__(256)
 linear_bwd_weight_kernel(const float* __restrict__ dY, int ldy, int off, const float* __restrict__ X, int ldx, int rows,
                          int in_f, int in_act, float* __restrict__ dW, float* __restrict__ db) {
-    const int j = blockIdx.y;
+    const int j0 = blockIdx.y * LBW_J;
     const int k = blockIdx.x * 256 + threadIdx.x;
-    float acc = 0.f, accb = 0.f;
+    float acc[LBW_J], accb[LBW_J];
+#pragma unroll
+    for (int j = 0; j < LBW_J; ++j) { acc[j] = 0.f; accb[j] = 0.f; }
+#pragma unroll 4
     for (int r = 0; r < rows; ++r) {
-        const float g = __ldg(dY + static_cast<size_t>(r) * ldy + off + j);
-        accb += g;
-        if (k < in_f) acc = fmaf(g, act_f(__ldg(X + static_cast<size_t>(r) * ldx + k), in_act), acc);
+        const float xv = k < in_f ? act_f(__ldg(X + static_cast<size_t>(r) * ldx + k), in_act) : 0.f;
+        const float* g = dY + static_cast<size_t>(r) * ldy + off + j0;
+#pragma unroll
+        for (int j = 0; j < LBW_J; ++j) {
+            const float gv = __ldg(g + j);
+            accb[j] += gv;
+            acc[j] = fmaf(gv, xv, acc[j]);
+        }
     }
-    if (k < in_f) dW[static_cast<size_t>(j) * in_f + k] = acc;
-    if (k == 0 && db != nullptr) db[j] = accb;
+    if (k < in_f) {
+#pragma unroll
+        for (int j = 0; j < LBW_J; ++j) dW[static_cast<size_t>(j0 + j) * in_f + k] = acc[j];
+    }
+    if (k == 0 && db != nullptr) {
+#pragma unroll
+        for (int j = 0; j < LBW_J; ++j) db[j0 + j] = accb[j];
+    }
 }
 
 // dX[r, k] (+)= sum_j dY[r, off + j] * W[j, k].  grid (ceil(in_f / 256), rows)
@@ -337,9 +402,16 @@ linear_bwd_input_kernel(const float* __restrict__ dY, int ldy, int off, const fl
     const int k = blockIdx.x * 256 + threadIdx.x;
     if (k >= in_f) return;
     float acc = 0.f;
+#pragma unroll 16
     for (int j = 0; j < out_f; ++j) acc = fmaf(__ldg(dY + static_cast<size_t>(r) * ldy + off + j), __ldg(W + static_cast<size_t>(j) * in_f + k), acc);
     float* o = dX + static_cast<size_t>(r) * ldx + k;
     *o = accumulate ? *o + acc : acc;
+}
+
+// y[i] = act(x[i])
+__global__ void act_apply_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int act) {
+    const long long i = blockIdx.x * 256ll + threadIdx.x;
+    if (i < n) y[i] = act_f(x[i], act);
 }
 
 // d[i] *= act'(x[i])
@@ -360,15 +432,14 @@ cudaError_t flip_tail_weight_run(const float* w, float* out, int C, cudaStream_t
     return cudaGetLastError();
 }
 cudaError_t film_silu_fwd_run(const bf16* a, bf16* sout, const float* film, int ld, int off, int B, int P, int C, cudaStream_t s) {
-    const long long chunks = static_cast<long long>(B) * P * C / 8;
-    const int grid = static_cast<int>(chunks / 256 < 148 * 16 ? (chunks + 255) / 256 : 148 * 16);
-    film_silu_fwd_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<uint4*>(sout), film, ld, off, P, C, chunks);
+    if (C != 256 || P % (FB_CHUNKS * 32) != 0) return cudaErrorInvalidValue;
+    film_silu_fwd_kernel<<<dim3(FB_CHUNKS, B), 256, 0, s>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<uint4*>(sout), film, ld, off, P);
     return cudaGetLastError();
 }
 int film_bwd_part_floats(int B, int C) { return B * FB_CHUNKS * 2 * C; }
 cudaError_t film_silu_bwd_run(const bf16* ds, const bf16* a, bf16* da, const float* film, float* dfilm, int ld, int off, int B,
                               int P, int C, float* part, cudaStream_t s) {
-    if (C != 256 || P % (FB_CHUNKS * 8) != 0) return cudaErrorInvalidValue;
+    if (C != 256 || P % (FB_CHUNKS * 32) != 0) return cudaErrorInvalidValue;
     film_silu_bwd_kernel<<<dim3(FB_CHUNKS, B), 256, 0, s>>>(reinterpret_cast<const uint4*>(ds), reinterpret_cast<const uint4*>(a),
                                                            reinterpret_cast<uint4*>(da), film, ld, off, P, part);
     cudaError_t e = cudaGetLastError();
@@ -390,11 +461,11 @@ cudaError_t colsum_run(const bf16* x, long long M, int C, float* part, float sca
     colsum_part_kernel<<<nparts, 256, lanes * C * sizeof(float), s>>>(reinterpret_cast<const uint4*>(x), part, M, C, rpb);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    sum_parts_kernel<<<(C + 255) / 256, 256, 0, s>>>(part, nparts, C, scale, accumulate, out);
+    sum_parts_kernel<<<(C + 31) / 32, 256, 0, s>>>(part, nparts, C, scale, accumulate, out);
     return cudaGetLastError();
 }
 cudaError_t sum_parts_run(const float* part, int nparts, int n, float scale, int accumulate, float* out, cudaStream_t s) {
-    sum_parts_kernel<<<(n + 255) / 256, 256, 0, s>>>(part, nparts, n, scale, accumulate, out);
+    sum_parts_kernel<<<(n + 31) / 32, 256, 0, s>>>(part, nparts, n, scale, accumulate, out);
     return cudaGetLastError();
 }
 cudaError_t add_bf16_run(const bf16* a, const bf16* b, bf16* y, long long n, cudaStream_t s) {
@@ -431,12 +502,17 @@ cudaError_t sum_f32_run(const float* x, long long n, float* part, float* out, cu
 }
 cudaError_t linear_bwd_weight_run(const float* dY, int ldy, int off, const float* X, int ldx, int rows, int in_f, int out_f,
                                   int in_act, float* dW, float* db, cudaStream_t s) {
-    linear_bwd_weight_kernel<<<dim3((in_f + 255) / 256, out_f), 256, 0, s>>>(dY, ldy, off, X, ldx, rows, in_f, in_act, dW, db);
+    if (out_f % LBW_J != 0) return cudaErrorInvalidValue;
+    linear_bwd_weight_kernel<<<dim3((in_f + 255) / 256, out_f / LBW_J), 256, 0, s>>>(dY, ldy, off, X, ldx, rows, in_f, in_act, dW, db);
     return cudaGetLastError();
 }
 cudaError_t linear_bwd_input_run(const float* dY, int ldy, int off, const float* W, int rows, int in_f, int out_f, int accumulate,
                                  float* dX, int ldx, cudaStream_t s) {
     linear_bwd_input_kernel<<<dim3((in_f + 255) / 256, rows), 256, 0, s>>>(dY, ldy, off, W, out_f, in_f, accumulate, dX, ldx);
+    return cudaGetLastError();
+}
+cudaError_t act_apply_run(const float* x, float* y, long long n, int act, cudaStream_t s) {
+    act_apply_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(x, y, n, act);
     return cudaGetLastError();
 }
 cudaError_t act_grad_run(float* d, const float* x, long long n, int act, cudaStream_t s) {

@@ -160,9 +160,10 @@ int build(hd_trainer* t) {
     if (dalloc(t, &wq_tail, static_cast<size_t>(16) * 9 * F * 2) || dalloc(t, &tail_bias16, 16 * 4, true) ||
         dalloc(t, &tail_flip, F * 9 * 4) || dalloc(t, &zero_bias, F * 4, true))
         return 1;
-    float *posenc = nullptr, *z1 = nullptr, *temb = nullptr, *film = nullptr, *dfilm = nullptr, *d_act = nullptr, *d_g1 = nullptr;
+    float *posenc = nullptr, *z1 = nullptr, *g1 = nullptr, *temb = nullptr, *stemb = nullptr, *film = nullptr, *dfilm = nullptr, *d_act = nullptr, *d_g1 = nullptr;
     if (dalloc(t, &posenc, static_cast<size_t>(B) * F * 4) || dalloc(t, &z1, static_cast<size_t>(B) * TIME_DIM * 4) ||
-        dalloc(t, &temb, static_cast<size_t>(B) * TIME_DIM * 4) || dalloc(t, &film, static_cast<size_t>(B) * ld * 4) ||
+        dalloc(t, &temb, static_cast<size_t>(B) * TIME_DIM * 4) || dalloc(t, &g1, static_cast<size_t>(B) * TIME_DIM * 4) ||
+        dalloc(t, &stemb, static_cast<size_t>(B) * TIME_DIM * 4) || dalloc(t, &film, static_cast<size_t>(B) * ld * 4) ||
         dalloc(t, &dfilm, static_cast<size_t>(B) * ld * 4, true) || dalloc(t, &d_act, static_cast<size_t>(B) * TIME_DIM * 4) ||
         dalloc(t, &d_g1, static_cast<size_t>(B) * TIME_DIM * 4))
         return 1;
@@ -213,12 +214,18 @@ int build(hd_trainer* t) {
         b.push("time", "posenc", [=](cudaStream_t s) { return posenc_rows_run(tv, posenc, B, F, 0, s); });
         const float *w1d = w1->w, *b1d = b1->w, *w3d = w3->w, *b3d = b3->w;
         b.push("time", "time_mlp.1", [=](cudaStream_t s) { return linear_rows_run(posenc, F, w1d, b1d, z1, TIME_DIM, 0, B, F, TIME_DIM, 0, 0, s); });
-        b.push("time", "gelu+time_mlp.3", [=](cudaStream_t s) { return linear_rows_run(z1, TIME_DIM, w3d, b3d, temb, TIME_DIM, 0, B, TIME_DIM, TIME_DIM, 2, 0, s); });
+        // activations are applied ONCE into their own buffers (g1 = GELU(z1), stemb = SiLU(temb)): the linears and their
+        // backward would otherwise re-evaluate them once per output feature
+        b.push("time", "gelu+time_mlp.3+silu", [=](cudaStream_t s) {
+            cudaError_t e = act_apply_run(z1, g1, static_cast<long long>(B) * TIME_DIM, 2, s);
+            if (e == cudaSuccess) e = linear_rows_run(g1, TIME_DIM, w3d, b3d, temb, TIME_DIM, 0, B, TIME_DIM, TIME_DIM, 0, 0, s);
+            return e != cudaSuccess ? e : act_apply_run(temb, stemb, static_cast<long long>(B) * TIME_DIM, 1, s);
+        });
         for (int i = 0; i < nb; ++i) {
             const float *w = mw[i]->w, *bias = mb[i]->w;
             const int off = i * 2 * F;
             b.push("time", "body." + std::to_string(i) + ".mlp", [=](cudaStream_t s) {
-                return linear_rows_run(temb, TIME_DIM, w, bias, film, ld, off, B, TIME_DIM, 2 * F, 1, 0, s);
+                return linear_rows_run(stemb, TIME_DIM, w, bias, film, ld, off, B, TIME_DIM, 2 * F, 0, 0, s);
             });
         }
     }
@@ -326,7 +333,7 @@ int build(hd_trainer* t) {
         const int off = i * 2 * F;
         const int acc = i > 0 ? 1 : 0;
         b.push("time_bwd", "body." + std::to_string(i) + ".mlp.bwd", [=](cudaStream_t s) {
-            cudaError_t e = linear_bwd_weight_run(dfilm, ld, off, temb, TIME_DIM, B, TIME_DIM, 2 * F, 1, gw, gb, s);
+            cudaError_t e = linear_bwd_weight_run(dfilm, ld, off, stemb, TIME_DIM, B, TIME_DIM, 2 * F, 0, gw, gb, s);
             return e != cudaSuccess ? e : linear_bwd_input_run(dfilm, ld, off, w, B, TIME_DIM, 2 * F, acc, d_act, TIME_DIM, s);
         });
     }
@@ -335,7 +342,7 @@ int build(hd_trainer* t) {
         const float* w3d = w3->w;
         b.push("time_bwd", "time_mlp.bwd", [=](cudaStream_t s) {
             cudaError_t e = act_grad_run(d_act, temb, static_cast<long long>(B) * TIME_DIM, 1, s);                     // through SiLU(temb)
-            if (e == cudaSuccess) e = linear_bwd_weight_run(d_act, TIME_DIM, 0, z1, TIME_DIM, B, TIME_DIM, TIME_DIM, 2, gw3, gb3, s);
+            if (e == cudaSuccess) e = linear_bwd_weight_run(d_act, TIME_DIM, 0, g1, TIME_DIM, B, TIME_DIM, TIME_DIM, 0, gw3, gb3, s);
             if (e == cudaSuccess) e = linear_bwd_input_run(d_act, TIME_DIM, 0, w3d, B, TIME_DIM, TIME_DIM, 0, d_g1, TIME_DIM, s);
             if (e == cudaSuccess) e = act_grad_run(d_g1, z1, static_cast<long long>(B) * TIME_DIM, 2, s);              // through GELU(z1)
             if (e == cudaSuccess) e = linear_bwd_weight_run(d_g1, TIME_DIM, 0, posenc, F, B, F, TIME_DIM, 0, gw1, gb1, s);
