@@ -57,6 +57,11 @@ SIGNATURES = {
     "hd_trainer_destroy": (None, [_vp]),
     "hd_op_conv3x3_wgrad": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "hd_op_conv3x3_dgrad": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
+    "hd_coo_to_dense": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "hd_remove_empty_bins": (C.c_int, [_vp, _i64, _vp, _vp, C.POINTER(_i64), _vp]),
+    "hd_select_ranks": (C.c_int, [_vp, _i64, C.POINTER(_i64), _i32, C.POINTER(C.c_float), _vp]),
+    "hd_normalize_contacts": (C.c_int, [_vp, _i64, C.c_float, _vp]),
+    "hd_add_noise": (C.c_int, [_vp, _vp, C.c_float, _i64, _vp, _vp]),
     "hd_tile_count": (_i64, [_i64, _i32, _i32]),
     "hd_tile_extract": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp]),
     "hd_tile_scatter": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),

@@ -326,4 +326,18 @@ cudaError_t linear_bwd_input_run(const float* dY, int ldy, int off, const float*
 cudaError_t act_apply_run(const float* x, float* y, long long n, int act, cudaStream_t s);   // act: 1 SiLU, 2 GELU(erf)
 cudaError_t act_grad_run(float* d, const float* x, long long n, int act, cudaStream_t s);
 
+// ---------------------------------------------------------------------------------------------
+// dataprep.cu -- contact triples -> dense matrix, empty-bin removal, exact percentile, normalisation, noise injection
+// ---------------------------------------------------------------------------------------------
+size_t coo_scratch_bytes(long long n);
+// synchronises; *bad_host != 0 when a triple fell outside [smallbin, smallbin + n)
+cudaError_t coo_to_dense_run(const long long* rows, const long long* cols, const float* vals, long long nnz, long long smallbin,
+                             long long n, float* mat, void* scratch, int* bad_host, cudaStream_t s);
+cudaError_t keep_map_run(const float* mat, long long n, long long* map, long long* n_kept_dev, cudaStream_t s);
+cudaError_t compact_run(const float* mat, long long n, const long long* map, long long m, float* out, cudaStream_t s);
+size_t select_scratch_bytes();
+cudaError_t select_rank_run(const float* x, long long n, unsigned long long rank, float* out, void* scratch, cudaStream_t s);
+cudaError_t normalize_contacts_run(float* x, long long n, float per, cudaStream_t s);
+cudaError_t axpy_noise_run(const float* x, const float* z, float sigma, long long n, float* y, cudaStream_t s);
+
 }  // namespace hd

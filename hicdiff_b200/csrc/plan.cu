@@ -1113,6 +1113,74 @@ int hd_ssim_mse_tiles(const float* a, const float* b, const float* window121, fl
     return 0;
 }
 
+// ---- data preparation (dataprep.cu)
+int hd_coo_to_dense(const int64_t* rows, const int64_t* cols, const float* vals, int64_t nnz, int64_t smallbin, int64_t n,
+                    float* mat, void* stream) {
+    if (n < 0 || nnz < 0) return fail("hd_coo_to_dense: negative size");
+    if (n == 0) return 0;
+    if (!mat || (nnz > 0 && (!rows || !cols || !vals))) return fail("hd_coo_to_dense: null argument");
+    if (nnz > 2147483647LL) return fail("hd_coo_to_dense: more than 2^31 - 1 triples");
+    void* scratch = nullptr;
+    CUDA_TRY(cudaMalloc(&scratch, coo_scratch_bytes(n)));
+    int bad = 0;
+    cudaError_t e = coo_to_dense_run(reinterpret_cast<const long long*>(rows), reinterpret_cast<const long long*>(cols), vals, nnz,
+                                     smallbin, n, mat, scratch, &bad, static_cast<cudaStream_t>(stream));
+    cudaFree(scratch);
+    if (e != cudaSuccess) return fail("hd_coo_to_dense failed: %s", cudaGetErrorString(e));
+    if (bad) return fail("hd_coo_to_dense: a (row, col) pair lies outside [smallbin, smallbin + n)");
+    return 0;
+}
+
+int hd_remove_empty_bins(const float* mat, int64_t n, float* out, int64_t* kept_idx, int64_t* n_kept_host, void* stream) {
+    if (n < 0 || !n_kept_host) return fail("hd_remove_empty_bins: bad argument");
+    *n_kept_host = 0;
+    if (n == 0) return 0;
+    if (!mat || !out || !kept_idx) return fail("hd_remove_empty_bins: null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    long long* cnt = nullptr;
+    CUDA_TRY(cudaMalloc(&cnt, 8));
+    cudaError_t e = keep_map_run(mat, n, reinterpret_cast<long long*>(kept_idx), cnt, s);
+    long long m = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&m, cnt, 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = compact_run(mat, n, reinterpret_cast<const long long*>(kept_idx), m, out, s);
+    cudaFree(cnt);
+    if (e != cudaSuccess) return fail("hd_remove_empty_bins failed: %s", cudaGetErrorString(e));
+    *n_kept_host = m;
+    return 0;
+}
+
+int hd_select_ranks(const float* x, int64_t n, const int64_t* ranks_host, int32_t nranks, float* out_host, void* stream) {
+    if (!x || !ranks_host || !out_host || n <= 0 || nranks <= 0) return fail("hd_select_ranks: bad argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    void* scratch = nullptr;
+    float* out = nullptr;
+    CUDA_TRY(cudaMalloc(&scratch, select_scratch_bytes()));
+    CUDA_TRY(cudaMalloc(&out, static_cast<size_t>(nranks) * 4));
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < nranks && e == cudaSuccess; ++i) {
+        if (ranks_host[i] < 0 || ranks_host[i] >= n) { cudaFree(scratch); cudaFree(out); return fail("hd_select_ranks: rank %lld outside [0, %lld)", (long long)ranks_host[i], (long long)n); }
+        e = select_rank_run(x, n, static_cast<unsigned long long>(ranks_host[i]), out + i, scratch, s);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, out, static_cast<size_t>(nranks) * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(scratch); cudaFree(out);
+    if (e != cudaSuccess) return fail("hd_select_ranks failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int hd_normalize_contacts(float* x, int64_t n, float per, void* stream) {
+    if (n < 0 || (n > 0 && !x)) return fail("hd_normalize_contacts: bad argument");
+    CUDA_TRY(normalize_contacts_run(x, n, per, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int hd_add_noise(const float* x, const float* noise, float sigma, int64_t n, float* out, void* stream) {
+    if (n < 0 || (n > 0 && (!x || !noise || !out))) return fail("hd_add_noise: bad argument");
+    CUDA_TRY(axpy_noise_run(x, noise, sigma, n, out, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
 int64_t hd_tile_count(int64_t n, int32_t piece, int32_t band_blocks) {
     if (n < 0 || piece <= 0 || band_blocks < 0) return -1;
     return tile_count(static_cast<int>(n), piece, band_blocks);

@@ -153,6 +153,26 @@ HD_API int hd_op_conv3x3_wgrad(const uint16_t* x, const uint16_t* dy, float* dw,
 HD_API int hd_op_conv3x3_dgrad(const uint16_t* dy, const float* w, uint16_t* dx, int32_t B, void* stream);
 
 /* -------------------------------------------------------------------------------------------------------------
+ * Data preparation: loadBothConstraints (processdata/PrepareData_linear.py:48-103) and the noise
+ * injection of split_numpy (:183-213) on the device.  All results are bit-exact (indexing, integer histograms, IEEE fp32).
+ *   hd_coo_to_dense        the loop :67-72: mat[r - smallbin, c - smallbin] = mat[c - smallbin, r - smallbin] = v for every triple,
+ *                          LATER triples overwriting earlier ones; rows / cols int64 bin indices, vals fp32, mat fp32 [n, n]
+ *                          (fully overwritten).  Synchronises.
+ *   hd_remove_empty_bins   :77-85: delete the rows and columns whose diagonal entry is 0 or NaN; out fp32 [m, m] (capacity
+ *                          n * n), kept_idx int64 [n] (first m valid), *n_kept_host = m.  Synchronises.
+ *   hd_select_ranks        exact order statistics (0-based ranks, ascending) of x[0..n) -- the two neighbours np.percentile
+ *                          (:88) interpolates between; ranks / results are HOST arrays.  Synchronises.
+ *   hd_normalize_contacts  :90-92 in place: x = 2 * (clip(x, 0, per) / per) - 1
+ *   hd_add_noise           :203-204 for the 'deno' operator: out = x + sigma * noise (noise: caller's N(0,1) draws)
+ * ------------------------------------------------------------------------------------------------------------- */
+HD_API int hd_coo_to_dense(const int64_t* rows, const int64_t* cols, const float* vals, int64_t nnz, int64_t smallbin, int64_t n,
+                    float* mat, void* stream);
+HD_API int hd_remove_empty_bins(const float* mat, int64_t n, float* out, int64_t* kept_idx, int64_t* n_kept_host, void* stream);
+HD_API int hd_select_ranks(const float* x, int64_t n, const int64_t* ranks_host, int32_t nranks, float* out_host, void* stream);
+HD_API int hd_normalize_contacts(float* x, int64_t n, float per, void* stream);
+HD_API int hd_add_noise(const float* x, const float* noise, float sigma, int64_t n, float* out, void* stream);
+
+/* -------------------------------------------------------------------------------------------------------------
  * Tiling.  hd_tile_extract replaces splitPieces (processdata/PrepareData_linear.py:25-46): zero-pad the n x n
  * matrix to a multiple of `piece`, enumerate block rows i and block columns j >= i with (j - i) <= band_blocks
  * (= 4 * int(40000 / res)), row-major.  hd_tile_scatter is its exact inverse (the reference has none): tile k is

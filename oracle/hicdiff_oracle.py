@@ -468,6 +468,70 @@ def reassemble(tiles: np.ndarray, n: int, piece: int = 64, res: int = 40000) -> 
 from hicdiff_b200.synthetic import synthetic_noise, synthetic_tiles  # noqa: E402,F401
 
 # --------------------------------------------------------------------------------------------------------------
+# Data preparation                                        processdata/PrepareData_linear.py:48-103,183-213
+# --------------------------------------------------------------------------------------------------------------
+
+
+def synthetic_contacts(n_bins: int, res: int = 40000, seed: int = 0, offset_bins: int = 3, empty_every: int = 17,
+                       duplicates: int = 50):
+    """Seeded (pos1, pos2, value) triples in the text-dump format loadBothConstraints reads (:49-50): genomic positions in
+    bp, band-limited symmetric contacts with a decaying count profile, some bins left without a diagonal entry (they get
+    removed, :77-85) and a few duplicated cells (later lines overwrite earlier ones, :67-72)."""
+    rng = np.random.default_rng(seed)
+    rows, cols, vals = [], [], []
+    for i in range(n_bins):
+        if empty_every and i % empty_every == empty_every - 1:
+            continue
+        for j in range(i, min(n_bins, i + 40)):
+            if j != i and (empty_every and j % empty_every == empty_every - 1):
+                continue
+            if j != i and rng.random() < 0.35:
+                continue
+            rows.append(i)
+            cols.append(j)
+            vals.append(float(np.float32(rng.gamma(2.0, 30.0 / (1 + (j - i))))))
+    rows, cols, vals = np.array(rows), np.array(cols), np.array(vals)
+    pick = rng.integers(0, len(rows), duplicates)
+    rows = np.concatenate([rows, rows[pick]])
+    cols = np.concatenate([cols, cols[pick]])
+    vals = np.concatenate([vals, vals[pick] * 0.5 + 1.0])
+    perm = rng.permutation(len(rows))
+    rows, cols, vals = rows[perm], cols[perm], vals[perm]
+    pos = np.stack([(rows + offset_bins) * res + rng.integers(0, res, len(rows)) * 0,      # bin starts, like `cooler dump`
+                    (cols + offset_bins) * res, vals], axis=1)
+    return pos.astype(np.float64)
+
+
+def load_constraints(triples_a: np.ndarray, triples_b: np.ndarray, res: int) -> np.ndarray:
+    """loadBothConstraints :48-103 on already-loaded `np.loadtxt` arrays: returns the normalised matrix `mata`."""
+    rowsa = (triples_a[:, 0] / res).astype(int)
+    colsa = (triples_a[:, 1] / res).astype(int)
+    valsa = triples_a[:, 2]
+    rowsb = (triples_b[:, 0] / res).astype(int)
+    colsb = (triples_b[:, 1] / res).astype(int)
+    bigbin = np.max((np.max((rowsa, colsa)), np.max((rowsb, colsb))))
+    smallbin = np.min((np.min((rowsa, colsa)), np.min((rowsb, colsb))))
+    mata = np.zeros((bigbin - smallbin + 1, bigbin - smallbin + 1), dtype="float32")
+    for ra, ca, ia in zip(rowsa, colsa, valsa):  # :67-70
+        mata[ra - smallbin, ca - smallbin] = ia
+        mata[ca - smallbin, ra - smallbin] = ia
+    diaga = np.diag(mata)
+    removeidx = np.unique(np.concatenate((np.argwhere(diaga == 0)[:, 0], np.argwhere(np.isnan(diaga))[:, 0])))  # :80
+    mata = np.delete(mata, removeidx, axis=0)
+    mata = np.delete(mata, removeidx, axis=1)
+    per_a = np.percentile(mata, 99.0)  # :88
+    mata = np.clip(mata, 0, per_a)
+    mata = mata / per_a
+    mata = 2 * mata - 1.0
+    return mata
+
+
+def add_noise(tiles: torch.Tensor, sigma_0: float, noise: torch.Tensor) -> torch.Tensor:
+    """split_numpy :199-204 for deg == 'deno' (H and H_pinv are the identity, svd_replacement.py:148-168)."""
+    return tiles + sigma_0 * noise
+
+
+# --------------------------------------------------------------------------------------------------------------
 # Quality metrics used for the 1e-3 SSIM/PSNR bar            src/Utils/loss/SSIM.py:6-74,
 # src/datasets/__init__.py:214-223 (inverse_data_transform 'rescaled'), pretrain/train_unet_Diff_cond_n.py:125-133
 # --------------------------------------------------------------------------------------------------------------

@@ -165,3 +165,22 @@ def test_oracle_training_gradients_reproduce_reference_golden(name):
         scale = max(s["norm"] / max(g.numel(), 1) ** 0.5, 1e-12)      # RMS of the tensor: thread-count-dependent fp32 order only
         assert float((got - want).abs().max()) <= 1e-3 * scale + 1e-9, k
         assert abs(float(g.double().norm()) - s["norm"]) <= 1e-4 * s["norm"] + 1e-12, k
+
+
+def test_oracle_data_preparation_reproduces_reference_golden():
+    """load_constraints against the checksums of the reference's own loadBothConstraints (oracle/make_golden_prepare.py).
+    The percentile rule travels with the numpy version (float32 index arithmetic in numpy >= 2), so the checksum is only
+    comparable under the numpy major version that wrote it."""
+    import json
+
+    gold = json.loads((helpers.GOLD / "prepare.json").read_text())
+    if gold["numpy"].split(".")[0] != np.__version__.split(".")[0]:
+        pytest.skip("fixture written under a different numpy major version")
+    for c in gold["cases"]:
+        a = O.synthetic_contacts(c["n_bins"], c["res"], c["seed"])
+        b = O.synthetic_contacts(c["n_bins"] + 2, c["res"], c["seed"] + 100)
+        b[:, 2] = np.round(b[:, 2])
+        m = O.load_constraints(a, b, c["res"])
+        assert list(m.shape) == c["shape"] and m.dtype == np.float32
+        assert hashlib.sha256(np.ascontiguousarray(m).tobytes()).hexdigest() == c["sha256"]
+        assert m.min() == -1.0 and m.max() == 1.0 and np.array_equal(m, m.T)
