@@ -301,13 +301,15 @@ size_t wgrad_part_bytes(int nsplit);
 
 cudaError_t prep_dgrad_weight_run(const float* w, bf16* out, int Cout, int Cin, cudaStream_t s);
 cudaError_t flip_tail_weight_run(const float* w, float* out, int C, cudaStream_t s);
-cudaError_t film_silu_fwd_run(const bf16* a, bf16* sout, const float* film, int ld, int off, int B, int P, int C, cudaStream_t s);
+// has_scale = 1: row = [scale(C) | shift(C)] (hicedrn_Diff); 0: row = [shift(C)] only (SR3 FeatureWiseAffine)
+cudaError_t film_silu_fwd_run(const bf16* a, bf16* sout, const float* film, int ld, int off, int B, int P, int C, int has_scale,
+                              cudaStream_t s);
 int film_bwd_part_floats(int B, int C);
 // da (may alias ds) = ds * SiLU'(a * (scale + 1) + shift) * (scale + 1); dfilm[b, off + c] = d scale, [off + C + c] = d shift
 cudaError_t film_silu_bwd_run(const bf16* ds, const bf16* a, bf16* da, const float* film, float* dfilm, int ld, int off, int B,
-                              int P, int C, float* part, cudaStream_t s);
+                              int P, int C, float* part, int has_scale, cudaStream_t s);
 cudaError_t edrn_bias_grad_run(const float* film, const float* dfilm, int ld, int off, int B, const float* colsum_g, float g_scale,
-                               float* dbias, int C, cudaStream_t s);
+                               float* dbias, int C, int has_scale, cudaStream_t s);
 int colsum_parts(long long M);
 // out[c] (+)= scale * sum_m x[m, c]
 cudaError_t colsum_run(const bf16* x, long long M, int C, float* part, float scale, int accumulate, float* out, cudaStream_t s);

@@ -67,15 +67,16 @@ constexpr int FB_CHUNKS = 16;   // pixel chunks per image (P = 4096 -> 256 pixel
 // grid (FB_CHUNKS, B), C == 256: thread = (8-channel chunk cc = tid % 32, pixel lane pl = tid / 32); the thread's scale / shift
 // stay in registers and loads are issued four pixels ahead of their use
 __global__ void __launch_bounds__(256)
-film_silu_fwd_kernel(const uint4* __restrict__ a, uint4* __restrict__ s, const float* __restrict__ film, int ld, int off, int P) {
+film_silu_fwd_kernel(const uint4* __restrict__ a, uint4* __restrict__ s, const float* __restrict__ film, int ld, int off, int P,
+                     int has_scale) {
     constexpr int C = 256, CPP = C / 8;
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int cc = threadIdx.x & 31, pl = threadIdx.x >> 5;
     const int ppc = P / FB_CHUNKS;
     const float* row = film + static_cast<size_t>(b) * ld + off + cc * 8;
-    float sc1[8], sh[8];
+    float sc1[8], sh[8];   // has_scale == 0 (SR3 FeatureWiseAffine): the row holds the additive term only
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { sc1[j] = __ldg(row + j) + 1.0f; sh[j] = __ldg(row + C + j); }
+    for (int j = 0; j < 8; ++j) { sc1[j] = has_scale ? __ldg(row + j) + 1.0f : 1.0f; sh[j] = __ldg(row + (has_scale ? C : 0) + j); }
     const size_t base = (static_cast<size_t>(b) * P + static_cast<size_t>(chunk) * ppc) * CPP + cc;
     for (int p = pl; p < ppc; p += 32) {
         uint4 u[4];
@@ -98,7 +99,7 @@ film_silu_fwd_kernel(const uint4* __restrict__ a, uint4* __restrict__ s, const f
 // same thread layout; ds and da may be the same buffer (each element is read before it is written by the same thread)
 __global__ void __launch_bounds__(256)
 film_silu_bwd_kernel(const uint4* ds, const uint4* __restrict__ a, uint4* da, const float* __restrict__ film, int ld, int off, int P,
-                     float* __restrict__ part) {
+                     float* __restrict__ part, int has_scale) {
     constexpr int C = 256, CPP = C / 8;
     __shared__ float s_red[8][2 * C];
     const int b = blockIdx.y, chunk = blockIdx.x;
@@ -107,7 +108,11 @@ film_silu_bwd_kernel(const uint4* ds, const uint4* __restrict__ a, uint4* da, co
     const float* row = film + static_cast<size_t>(b) * ld + off + cc * 8;
     float sc1[8], sh[8], acc_sc[8], acc_sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { sc1[j] = __ldg(row + j) + 1.0f; sh[j] = __ldg(row + C + j); acc_sc[j] = 0.f; acc_sh[j] = 0.f; }
+    for (int j = 0; j < 8; ++j) {
+        sc1[j] = has_scale ? __ldg(row + j) + 1.0f : 1.0f;
+        sh[j] = __ldg(row + (has_scale ? C : 0) + j);
+        acc_sc[j] = 0.f; acc_sh[j] = 0.f;
+    }
     const size_t base = (static_cast<size_t>(b) * P + static_cast<size_t>(chunk) * ppc) * CPP + cc;
     for (int p = pl; p < ppc; p += 32) {
         uint4 ug[4], ua[4];
@@ -145,23 +150,26 @@ film_silu_bwd_kernel(const uint4* ds, const uint4* __restrict__ a, uint4* da, co
     }
 }
 
-// dfilm[b, off + i] = sum over the chunks (i < 2C: d scale then d shift); grid B, 2C threads
-__global__ void film_grad_finish_kernel(const float* __restrict__ part, float* __restrict__ dfilm, int ld, int off, int C) {
+// dfilm[b, off + i] = sum over the chunks (i < 2C: d scale then d shift; has_scale == 0: d shift only, i < C); grid B, 2C threads
+__global__ void film_grad_finish_kernel(const float* __restrict__ part, float* __restrict__ dfilm, int ld, int off, int C, int has_scale) {
     const int b = blockIdx.x, i = threadIdx.x;
+    if (!has_scale && i < C) return;
     float t = 0.f;
     for (int k = 0; k < FB_CHUNKS; ++k) t += part[(static_cast<size_t>(b) * FB_CHUNKS + k) * 2 * C + i];
-    dfilm[static_cast<size_t>(b) * ld + off + i] = t;
+    dfilm[static_cast<size_t>(b) * ld + off + (has_scale ? i : i - C)] = t;
 }
 
 // the shared conv's bias gradient: its first use contributes sum_b (scale + 1) * dshift (da = dh * (scale + 1)), its second
 // 0.1 * colsum(g)
 __global__ void edrn_bias_grad_kernel(const float* __restrict__ film, const float* __restrict__ dfilm, int ld, int off, int B,
-                                      const float* __restrict__ colsum_g, float g_scale, float* __restrict__ dbias, int C) {
+                                      const float* __restrict__ colsum_g, float g_scale, float* __restrict__ dbias, int C, int has_scale) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float t = 0.f;
-    for (int b = 0; b < B; ++b)
-        t = fmaf(film[static_cast<size_t>(b) * ld + off + c] + 1.0f, dfilm[static_cast<size_t>(b) * ld + off + C + c], t);
+    for (int b = 0; b < B; ++b) {
+        if (has_scale) t = fmaf(film[static_cast<size_t>(b) * ld + off + c] + 1.0f, dfilm[static_cast<size_t>(b) * ld + off + C + c], t);
+        else t += dfilm[static_cast<size_t>(b) * ld + off + c];
+    }
     dbias[c] = t + g_scale * colsum_g[c];
 }
 
@@ -431,25 +439,26 @@ cudaError_t flip_tail_weight_run(const float* w, float* out, int C, cudaStream_t
     flip_tail_weight_kernel<<<(C * 9 + 255) / 256, 256, 0, s>>>(w, out, C);
     return cudaGetLastError();
 }
-cudaError_t film_silu_fwd_run(const bf16* a, bf16* sout, const float* film, int ld, int off, int B, int P, int C, cudaStream_t s) {
+cudaError_t film_silu_fwd_run(const bf16* a, bf16* sout, const float* film, int ld, int off, int B, int P, int C, int has_scale,
+                              cudaStream_t s) {
     if (C != 256 || P % (FB_CHUNKS * 32) != 0) return cudaErrorInvalidValue;
-    film_silu_fwd_kernel<<<dim3(FB_CHUNKS, B), 256, 0, s>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<uint4*>(sout), film, ld, off, P);
+    film_silu_fwd_kernel<<<dim3(FB_CHUNKS, B), 256, 0, s>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<uint4*>(sout), film, ld, off, P, has_scale);
     return cudaGetLastError();
 }
 int film_bwd_part_floats(int B, int C) { return B * FB_CHUNKS * 2 * C; }
 cudaError_t film_silu_bwd_run(const bf16* ds, const bf16* a, bf16* da, const float* film, float* dfilm, int ld, int off, int B,
-                              int P, int C, float* part, cudaStream_t s) {
+                              int P, int C, float* part, int has_scale, cudaStream_t s) {
     if (C != 256 || P % (FB_CHUNKS * 32) != 0) return cudaErrorInvalidValue;
     film_silu_bwd_kernel<<<dim3(FB_CHUNKS, B), 256, 0, s>>>(reinterpret_cast<const uint4*>(ds), reinterpret_cast<const uint4*>(a),
-                                                           reinterpret_cast<uint4*>(da), film, ld, off, P, part);
+                                                           reinterpret_cast<uint4*>(da), film, ld, off, P, part, has_scale);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    film_grad_finish_kernel<<<B, 2 * C, 0, s>>>(part, dfilm, ld, off, C);
+    film_grad_finish_kernel<<<B, 2 * C, 0, s>>>(part, dfilm, ld, off, C, has_scale);
     return cudaGetLastError();
 }
 cudaError_t edrn_bias_grad_run(const float* film, const float* dfilm, int ld, int off, int B, const float* colsum_g, float g_scale,
-                               float* dbias, int C, cudaStream_t s) {
-    edrn_bias_grad_kernel<<<(C + 255) / 256, 256, 0, s>>>(film, dfilm, ld, off, B, colsum_g, g_scale, dbias, C);
+                               float* dbias, int C, int has_scale, cudaStream_t s) {
+    edrn_bias_grad_kernel<<<(C + 255) / 256, 256, 0, s>>>(film, dfilm, ld, off, B, colsum_g, g_scale, dbias, C, has_scale);
     return cudaGetLastError();
 }
 int colsum_parts(long long M) { return static_cast<int>(M / 256 < 592 ? (M + 255) / 256 : 592); }

@@ -125,7 +125,10 @@ struct TB {   // builder state
 int build(hd_trainer* t) {
     const int B = t->B, nb = t->nb;
     const int cin = t->cfg.self_condition ? 2 : 1;
-    const int ld = nb * 2 * F;
+    const bool sr3 = t->cfg.variant == HD_HICEDRN_SR3;   // FeatureWiseAffine: h = conv(x) + Linear(t) (no scale, no SiLU on t)
+    const int fw = sr3 ? F : 2 * F;                       // FiLM row width per block
+    const int hs = sr3 ? 0 : 1;
+    const int ld = nb * fw;
     const size_t act_elems = static_cast<size_t>(B) * P * F;
     const long long M = static_cast<long long>(B) * P;
     TB b{t};
@@ -142,8 +145,8 @@ int build(hd_trainer* t) {
         const std::string pre = "body." + std::to_string(i);
         cw[i] = find_p(t, pre + ".conv.proj.weight", {F, F, 3, 3});
         cb[i] = find_p(t, pre + ".conv.proj.bias", {F});
-        mw[i] = find_p(t, pre + ".mlp.1.weight", {2 * F, TIME_DIM});
-        mb[i] = find_p(t, pre + ".mlp.1.bias", {2 * F});
+        mw[i] = find_p(t, pre + (sr3 ? ".noise_func.noise_func.0.weight" : ".mlp.1.weight"), {fw, TIME_DIM});
+        mb[i] = find_p(t, pre + (sr3 ? ".noise_func.noise_func.0.bias" : ".mlp.1.bias"), {fw});
         if (!cw[i] || !cb[i] || !mw[i] || !mb[i]) return 1;
     }
 
@@ -211,7 +214,7 @@ int build(hd_trainer* t) {
     // ---------------------------------------------------------------- forward: time embedding -> FiLM rows
     {
         float* tv = t->time;
-        b.push("time", "posenc", [=](cudaStream_t s) { return posenc_rows_run(tv, posenc, B, F, 0, s); });
+        b.push("time", "posenc", [=](cudaStream_t s) { return posenc_rows_run(tv, posenc, B, F, sr3 ? 1 : 0, s); });
         const float *w1d = w1->w, *b1d = b1->w, *w3d = w3->w, *b3d = b3->w;
         b.push("time", "time_mlp.1", [=](cudaStream_t s) { return linear_rows_run(posenc, F, w1d, b1d, z1, TIME_DIM, 0, B, F, TIME_DIM, 0, 0, s); });
         // activations are applied ONCE into their own buffers (g1 = GELU(z1), stemb = SiLU(temb)): the linears and their
@@ -223,9 +226,10 @@ int build(hd_trainer* t) {
         });
         for (int i = 0; i < nb; ++i) {
             const float *w = mw[i]->w, *bias = mb[i]->w;
-            const int off = i * 2 * F;
+            const int off = i * fw;
+            const float* tin = sr3 ? temb : stemb;
             b.push("time", "body." + std::to_string(i) + ".mlp", [=](cudaStream_t s) {
-                return linear_rows_run(stemb, TIME_DIM, w, bias, film, ld, off, B, TIME_DIM, 2 * F, 0, 0, s);
+                return linear_rows_run(tin, TIME_DIM, w, bias, film, ld, off, B, TIME_DIM, fw, 0, 0, s);
             });
         }
     }
@@ -245,8 +249,8 @@ int build(hd_trainer* t) {
         if (!b.conv(pre + ".conv#1", X[i], wqf[i], F, A[i], e1)) return 1;
         const bf16* ai = A[i];
         bf16* si = Sx[i];
-        const int off = i * 2 * F;
-        b.push("film_silu_fwd", pre + ".film_silu", [=](cudaStream_t s) { return film_silu_fwd_run(ai, si, film, ld, off, B, P, F, s); });
+        const int off = i * fw;
+        b.push("film_silu_fwd", pre + ".film_silu", [=](cudaStream_t s) { return film_silu_fwd_run(ai, si, film, ld, off, B, P, F, hs, s); });
         ConvEpilogue e2;
         e2.bias = cb[i]->w; e2.out_scale = 0.1f; e2.res = X[i]; e2.ldr = F;
         if (!b.conv(pre + ".conv#2", Sx[i], wqf[i], F, X[i + 1], e2)) return 1;
@@ -294,7 +298,7 @@ int build(hd_trainer* t) {
         const bf16* g = GX[cur];
         bf16* gnext = GX[cur ^ 1];
         const bf16 *si = Sx[i], *ai = A[i], *xi = X[i];
-        const int off = i * 2 * F;
+        const int off = i * fw;
         float *gw = cw[i]->g, *gb = cb[i]->g;
         b.push("colsum", pre + ".colsum_g", [=](cudaStream_t s) { return colsum_run(g, M, F, cs_part, 1.0f, 0, cs_g, s); });
         if (!wgrad(pre + ".wgrad#2", g, si, ws2)) return 1;
@@ -302,9 +306,9 @@ int build(hd_trainer* t) {
         e2.out_scale = 0.1f;
         if (!b.conv(pre + ".dgrad#2", g, wqd[i], F, DS, e2)) return 1;
         b.push("film_silu_bwd", pre + ".film_silu_bwd", [=](cudaStream_t s) {
-            return film_silu_bwd_run(DS, ai, DS, film, dfilm, ld, off, B, P, F, film_part, s);
+            return film_silu_bwd_run(DS, ai, DS, film, dfilm, ld, off, B, P, F, film_part, hs, s);
         });
-        b.push("reduce", pre + ".bias_grad", [=](cudaStream_t s) { return edrn_bias_grad_run(film, dfilm, ld, off, B, cs_g, 0.1f, gb, F, s); });
+        b.push("reduce", pre + ".bias_grad", [=](cudaStream_t s) { return edrn_bias_grad_run(film, dfilm, ld, off, B, cs_g, 0.1f, gb, F, hs, s); });
         if (!wgrad(pre + ".wgrad#1", DS, xi, ws1)) return 1;
         b.push("reduce", pre + ".wgrad_reduce", [=](cudaStream_t s) {
             cudaError_t e = wgrad_reduce_run(ws1, WG_SPLITS, 1.0f, 0, gw, s);
@@ -330,18 +334,19 @@ int build(hd_trainer* t) {
     for (int i = 0; i < nb; ++i) {
         const float* w = mw[i]->w;
         float *gw = mw[i]->g, *gb = mb[i]->g;
-        const int off = i * 2 * F;
+        const int off = i * fw;
         const int acc = i > 0 ? 1 : 0;
+        const float* tin = sr3 ? temb : stemb;
         b.push("time_bwd", "body." + std::to_string(i) + ".mlp.bwd", [=](cudaStream_t s) {
-            cudaError_t e = linear_bwd_weight_run(dfilm, ld, off, stemb, TIME_DIM, B, TIME_DIM, 2 * F, 0, gw, gb, s);
-            return e != cudaSuccess ? e : linear_bwd_input_run(dfilm, ld, off, w, B, TIME_DIM, 2 * F, acc, d_act, TIME_DIM, s);
+            cudaError_t e = linear_bwd_weight_run(dfilm, ld, off, tin, TIME_DIM, B, TIME_DIM, fw, 0, gw, gb, s);
+            return e != cudaSuccess ? e : linear_bwd_input_run(dfilm, ld, off, w, B, TIME_DIM, fw, acc, d_act, TIME_DIM, s);
         });
     }
     {
         float *gw3 = w3->g, *gb3 = b3->g, *gw1 = w1->g, *gb1 = b1->g;
         const float* w3d = w3->w;
         b.push("time_bwd", "time_mlp.bwd", [=](cudaStream_t s) {
-            cudaError_t e = act_grad_run(d_act, temb, static_cast<long long>(B) * TIME_DIM, 1, s);                     // through SiLU(temb)
+            cudaError_t e = sr3 ? cudaSuccess : act_grad_run(d_act, temb, static_cast<long long>(B) * TIME_DIM, 1, s);   // through SiLU(temb)
             if (e == cudaSuccess) e = linear_bwd_weight_run(d_act, TIME_DIM, 0, g1, TIME_DIM, B, TIME_DIM, TIME_DIM, 0, gw3, gb3, s);
             if (e == cudaSuccess) e = linear_bwd_input_run(d_act, TIME_DIM, 0, w3d, B, TIME_DIM, TIME_DIM, 0, d_g1, TIME_DIM, s);
             if (e == cudaSuccess) e = act_grad_run(d_g1, z1, static_cast<long long>(B) * TIME_DIM, 2, s);              // through GELU(z1)
@@ -359,8 +364,9 @@ extern "C" {
 int hd_trainer_create(const hd_config* cfg, int32_t batch, hd_trainer** out) {
     if (!cfg || !out) return tfail("hd_trainer_create: null argument");
     if (cfg->abi_version != HD_ABI_VERSION) return tfail("ABI version mismatch: header %d, library %d", cfg->abi_version, HD_ABI_VERSION);
-    if (cfg->variant != HD_HICEDRN)
-        return tfail("hd_trainer is built for hicedrn_Diff (variant %d), the model train.py trains; variant %d has no backward yet", HD_HICEDRN, cfg->variant);
+    if (cfg->variant != HD_HICEDRN && cfg->variant != HD_HICEDRN_SR3)
+        return tfail("hd_trainer is built for the hicedrn_Diff eps-nets (variants %d, %d), the models train.py / pretrain/train_hicedrn_*.py train; variant %d has no backward yet",
+                     HD_HICEDRN, HD_HICEDRN_SR3, cfg->variant);
     if (cfg->image_size != 64) return tfail("image_size must be 64");
     if (cfg->num_blocks < 1) return tfail("HiCEDRN needs num_blocks >= 1");
     if (batch < 1) return tfail("batch must be positive (got %d)", batch);

@@ -349,7 +349,7 @@ class GaussianDiffusionSR3(_GaussianDiffusionBase):
         noise = torch.randn_like(x_start) if noise is None else noise
         return continuous_sqrt_alpha_cumprod * x_start + (1 - continuous_sqrt_alpha_cumprod ** 2).sqrt() * noise
 
-    def p_losses(self, x_in, noise=None, level=None):  # hicdiff_sr3.py:750-792 (numpy global RNG, no p2 weight)
+    def p_losses(self, x_in, t=None, noise=None, level=None):  # hicdiff_sr3.py:750-792 (numpy global RNG, no p2 weight; `t` is ignored there too)
         noisy, clean = x_in
         b, c, h, w = clean.shape
         assert h == self.image_size and w == self.image_size, f"height and width of image must be {self.image_size}"
@@ -360,6 +360,11 @@ class GaussianDiffusionSR3(_GaussianDiffusionBase):
         level = level.view(b, -1)
         noise = torch.randn_like(clean) if noise is None else noise
         x = self.q_sample(clean, level.view(-1, 1, 1, 1), noise)
+        from . import train as _train
+
+        if self._wants_grad() and _train.supports_training(self.model):      # hicedrn_sr3_Diff: forward + loss + backward on the device
+            return _train.training_loss(self.model, x, level.reshape(-1), noisy if self.self_condition else None, noise,
+                                        torch.ones(b, device=clean.device), self.loss_type)
         with torch.no_grad():
             out = self.model(x, level, noisy if self.self_condition else None)
         return self._finish_loss(self.loss_fn(out, noise, reduction="none").mean())

@@ -23,10 +23,10 @@ class Trainer:
     def __init__(self, net: torch.nn.Module, batch: int):
         lib = _lib.load()
         cfgd = net._plan_config()
-        if cfgd["variant"] != _lib.HD_HICEDRN:
+        if cfgd["variant"] not in (_lib.HD_HICEDRN, _lib.HD_HICEDRN_SR3):
             raise NotImplementedError(
-                "hicdiff_b200: the training backward is built for hicedrn_Diff (the model train.py trains); "
-                "Unet / SR3 backward is SURVEY.md 8(f) N2, not built yet")
+                "hicdiff_b200: the training backward is built for the hicedrn_Diff eps-nets (train.py, "
+                "pretrain/train_hicedrn_*.py); the Unet backward is SURVEY.md 8(f) N2, not built yet")
         params = dict(net.named_parameters())
         dev = next(iter(params.values())).device
         if dev.type != "cuda":
@@ -158,7 +158,7 @@ class _TrainStep(torch.autograd.Function):
 
 def supports_training(net) -> bool:
     cfg = getattr(net, "_plan_config", None)
-    return cfg is not None and cfg()["variant"] == _lib.HD_HICEDRN
+    return cfg is not None and cfg()["variant"] in (_lib.HD_HICEDRN, _lib.HD_HICEDRN_SR3)
 
 
 def training_loss(net, x_t, time, cond, target, weight, loss_type: str):

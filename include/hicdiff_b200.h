@@ -126,7 +126,8 @@ HD_API int hd_ssim_mse_tiles(const float* a, const float* b, const float* window
  * forward + loss + loss.backward() of one iteration (train.py:120-129): eps = model(x_t, t, cond)
  * (src/model/hicedrn_Diff.py:267-289), loss = mean(|eps - target|^p * weight[b]) (p_losses, hicdiff_condition.py:741-746,
  * loss_fn :706-713; weight = p2_loss_weight[t]), and d loss / d parameter for every parameter of the net.
- *   hd_trainer_create    cfg.variant must be HD_HICEDRN; `batch` tiles per step (fixed per trainer)
+ *   hd_trainer_create    cfg.variant must be HD_HICEDRN or HD_HICEDRN_SR3 (src/model/hicedrn_sr3_Diff.py: additive noise-level
+ *                        embedding, `time` = the continuous noise level); `batch` tiles per step (fixed per trainer)
  *   hd_trainer_bind      once per state_dict entry (key without the `model.` prefix): `param` is READ IN PLACE at every
  *                        step (so any optimizer may update it between steps), `grad` (same shape, fp32) is OVERWRITTEN by
  *                        every step; both are device pointers the caller keeps alive

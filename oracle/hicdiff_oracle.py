@@ -352,6 +352,24 @@ def p_losses(eps_fn, buf: SD, noisy, clean, t, noise, *, loss_type="l2", self_co
     return loss.mean()
 
 
+def sr3_p_losses(eps_fn, noisy, clean, level, noise, *, loss_type="l2", self_condition=True):
+    """SR3 p_losses (src/hicdiff_sr3.py:750-792) with the noise level and the noise supplied (the reference draws them from
+    numpy's global RNG :760-770): x = level * x0 + sqrt(1 - level^2) * noise; plain mean loss, no p2 weight."""
+    lv = level.view(-1, 1, 1, 1)
+    x = lv * clean + (1 - lv ** 2).sqrt() * noise          # q_sample :735-739
+    out = eps_fn(x, level.view(clean.shape[0], -1), noisy if self_condition else None)
+    return (F.mse_loss(out, noise, reduction="none") if loss_type == "l2" else F.l1_loss(out, noise, reduction="none")).mean()
+
+
+def sr3_p_losses_and_grads(sd: SD, noisy, clean, level, noise, *, loss_type="l2", self_condition=True, num_blocks=32):
+    """Loss and parameter gradients of one SR3 training iteration over hicedrn_sr3_Diff (pretrain/train_hicedrn_Diff_sr3.py)."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if torch.is_floating_point(v)}
+    loss = sr3_p_losses(lambda x, lv, c: hicedrn_forward(leaves, x, lv, c, self_condition=self_condition, sr3=True, num_blocks=num_blocks),
+                        noisy, clean, level, noise, loss_type=loss_type, self_condition=self_condition)
+    grads = torch.autograd.grad(loss, list(leaves.values()))
+    return loss.detach(), dict(zip(leaves.keys(), grads))
+
+
 def p_losses_and_grads(sd: SD, buf: SD, noisy, clean, t, noise, *, loss_type="l2", self_condition=True, num_blocks=32):
     """One training iteration's loss and d loss / d parameter for the hicedrn_Diff eps-net: what `loss = diffusion(x);
     loss.backward()` leaves in `.grad` (train.py:127-128) -- torch.autograd over the restated forward (the reference has no

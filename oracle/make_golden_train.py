@@ -69,9 +69,36 @@ def main():
         assert ref_grads.keys() == o_grads.keys()
         for k in ref_grads:
             assert torch.equal(ref_grads[k], o_grads[k]), f"{c['name']}: oracle grad of {k} differs from the reference"
-        out["cases"][c["name"]] = {**{k: v for k, v in c.items() if k != "name"}, "loss": float(loss),
+        out["cases"][c["name"]] = {**{k: v for k, v in c.items() if k != "name"}, "loss": float(loss.detach()),
                                    "grads": {k: summary(g) for k, g in ref_grads.items()}}
         print(f"{c['name']}: oracle == reference bit-for-bit (loss {float(loss):.6f}, {len(ref_grads)} gradients)")
+    # ---- SR3 flavour over hicedrn_sr3_Diff (pretrain/train_hicedrn_Diff_sr3.py): numpy's global RNG picks t and the level
+    from src import hicdiff_sr3 as R_s
+    from src.model.hicedrn_sr3_Diff import hicedrn_Diff as hicedrn_sr3
+
+    c = dict(flavour="sr3", self_condition=True, loss_type="l2", schedule="linear", B=2, blocks=2, T=1000, np_seed=5)
+    torch.manual_seed(0)
+    net = hicedrn_sr3(number_resnet=c["blocks"], self_condition=True)
+    diff = R_s.GaussianDiffusion(net, image_size=64, timesteps=c["T"], loss_type=c["loss_type"], beta_schedule=c["schedule"], auto_normalize=False)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    clean, noisy = O.synthetic_tiles(c["B"], seed=1234)
+    noise = torch.randn(c["B"], 1, 64, 64, generator=torch.Generator().manual_seed(99))
+    import numpy as np
+    np.random.seed(c["np_seed"])
+    loss = diff.p_losses([noisy, clean], noise=noise.clone())
+    loss.backward()
+    np.random.seed(c["np_seed"])                                   # replay the two draws of p_losses :754-762
+    t = np.random.randint(1, c["T"] + 1)
+    lv_table = O.sr3_noise_levels(c["schedule"], c["T"])
+    level = torch.FloatTensor(np.random.uniform(lv_table[t - 1], lv_table[t], size=c["B"]))
+    ref_grads = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+    o_loss, o_grads = O.sr3_p_losses_and_grads(sd, noisy, clean, level, noise, loss_type=c["loss_type"], self_condition=True, num_blocks=c["blocks"])
+    assert torch.equal(o_loss, loss.detach()), (float(o_loss), float(loss))
+    for k in ref_grads:
+        assert torch.equal(ref_grads[k], o_grads[k]), f"sr3: oracle grad of {k} differs from the reference"
+    out["cases"]["sr3_l2"] = {**c, "t": int(t), "level": [float(v) for v in level], "loss": float(loss.detach()),
+                              "grads": {k: summary(g) for k, g in ref_grads.items()}}
+    print(f"sr3_l2: oracle == reference bit-for-bit (t = {t}, loss {float(loss.detach()):.6f}, {len(ref_grads)} gradients)")
     path = ROOT / "tests" / "golden" / "hicedrn_train.json"
     path.write_text(json.dumps(out, indent=1))
     print("wrote", path)

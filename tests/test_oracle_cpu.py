@@ -137,7 +137,7 @@ def test_oracle_against_live_reference_unet_cond():
         assert torch.equal(ref(x, t, c), O.unet_forward(ref.state_dict(), x, t, c, self_condition=True))
 
 
-@pytest.mark.parametrize("name", ["cond_l2", "uncond_l1"])
+@pytest.mark.parametrize("name", ["cond_l2", "uncond_l1", "sr3_l2"])
 def test_oracle_training_gradients_reproduce_reference_golden(name):
     """p_losses_and_grads against the per-parameter summaries of the reference's own loss.backward()
     (oracle/make_golden_train.py asserted bit-equality of the FULL gradients when it wrote the fixture)."""
@@ -147,15 +147,22 @@ def test_oracle_training_gradients_reproduce_reference_golden(name):
     c = gold["cases"][name]
     from hicdiff_b200.model.hicedrn_Diff import hicedrn_Diff
 
+    from hicdiff_b200.model.hicedrn_sr3_Diff import hicedrn_Diff as hicedrn_sr3
+
     torch.manual_seed(gold["weight_seed"])
-    net = hicedrn_Diff(number_resnet=c["blocks"], self_condition=c["self_condition"])
+    sr3 = c["flavour"] == "sr3"
+    net = (hicedrn_sr3 if sr3 else hicedrn_Diff)(number_resnet=c["blocks"], self_condition=c["self_condition"])
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     clean, noisy = O.synthetic_tiles(c["B"], seed=gold["tile_seed"])
-    t = torch.tensor(c["t"], dtype=torch.long)
     noise = torch.randn(c["B"], 1, 64, 64, generator=torch.Generator().manual_seed(gold["noise_seed"]))
-    buf = O.diffusion_buffers(c["schedule"], c["T"])
-    loss, grads = O.p_losses_and_grads(sd, buf, noisy, clean, t, noise, loss_type=c["loss_type"],
-                                       self_condition=c["self_condition"], num_blocks=c["blocks"])
+    if sr3:
+        loss, grads = O.sr3_p_losses_and_grads(sd, noisy, clean, torch.tensor(c["level"], dtype=torch.float32), noise,
+                                               loss_type=c["loss_type"], self_condition=True, num_blocks=c["blocks"])
+    else:
+        t = torch.tensor(c["t"], dtype=torch.long)
+        buf = O.diffusion_buffers(c["schedule"], c["T"])
+        loss, grads = O.p_losses_and_grads(sd, buf, noisy, clean, t, noise, loss_type=c["loss_type"],
+                                           self_condition=c["self_condition"], num_blocks=c["blocks"])
     assert abs(float(loss) - c["loss"]) <= 1e-6 * max(1.0, abs(c["loss"]))
     assert set(grads) == set(c["grads"])
     for k, s in c["grads"].items():

@@ -77,7 +77,7 @@ def test_loss_backward_matches_oracle(name):
         loss = diff.p_losses(clean.to(DEV), t.to(DEV), noise=noise.to(DEV))
     assert loss.requires_grad
     loss.backward()                                                                  # train.py:128
-    assert abs(float(loss) - float(o_loss)) <= 5e-3 * abs(float(o_loss)), (float(loss), float(o_loss))
+    assert abs(float(loss.detach()) - float(o_loss)) <= 5e-3 * abs(float(o_loss)), (float(loss.detach()), float(o_loss))
     worst = {}
     for k, p in net.named_parameters():
         assert p.grad is not None, k
@@ -85,8 +85,43 @@ def test_loss_backward_matches_oracle(name):
         worst[k] = _rel(p.grad, o_grads[k])
     bad = {k: v for k, v in worst.items() if v > 3e-2}
     assert not bad, f"{name}: gradient rel-RMS above 3e-2: {bad}"
-    print(f"{name}: loss {float(loss):.6f} (oracle {float(o_loss):.6f}); worst grad rel-RMS {max(worst.values()):.3e} "
+    print(f"{name}: loss {float(loss.detach()):.6f} (oracle {float(o_loss):.6f}); worst grad rel-RMS {max(worst.values()):.3e} "
           f"({max(worst, key=worst.get)})")
+
+
+def test_sr3_loss_backward_matches_oracle():
+    """pretrain/train_hicedrn_Diff_sr3.py: hicedrn_sr3_Diff (additive noise-level embedding) under the SR3 GaussianDiffusion."""
+    from hicdiff_b200.hicdiff_sr3 import GaussianDiffusion
+    from hicdiff_b200.model.hicedrn_sr3_Diff import hicedrn_Diff as hicedrn_sr3
+
+    c = GOLD["cases"]["sr3_l2"]
+    torch.manual_seed(GOLD["weight_seed"])
+    net = hicedrn_sr3(number_resnet=c["blocks"], self_condition=True)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    clean, noisy = O.synthetic_tiles(c["B"], seed=GOLD["tile_seed"])
+    noise = torch.randn(c["B"], 1, 64, 64, generator=torch.Generator().manual_seed(GOLD["noise_seed"]))
+    level = torch.tensor(c["level"], dtype=torch.float32)
+    o_loss, o_grads = O.sr3_p_losses_and_grads(sd, noisy, clean, level, noise, loss_type=c["loss_type"], self_condition=True,
+                                               num_blocks=c["blocks"])
+    assert abs(float(o_loss) - c["loss"]) <= 1e-6 * max(1.0, abs(c["loss"]))
+    diff = GaussianDiffusion(net, image_size=64, timesteps=c["T"], loss_type=c["loss_type"], beta_schedule=c["schedule"],
+                             auto_normalize=False).to(DEV)
+    diff.train()
+    loss = diff.p_losses([noisy.to(DEV), clean.to(DEV)], noise=noise.to(DEV), level=level.to(DEV))
+    loss.backward()
+    assert abs(float(loss.detach()) - float(o_loss)) <= 5e-3 * abs(float(o_loss)), (float(loss.detach()), float(o_loss))
+    worst = {k: _rel(p.grad, o_grads[k]) for k, p in net.named_parameters()}
+    bad = {k: v for k, v in worst.items() if v > 3e-2}
+    assert not bad, f"sr3: gradient rel-RMS above 3e-2: {bad}"
+    # the reference's own call: numpy's global RNG picks t and the level (hicdiff_sr3.py:754-762)
+    import numpy as np
+
+    np.random.seed(c["np_seed"])
+    net.zero_grad()
+    l2 = diff([noisy.to(DEV), clean.to(DEV)], noise=noise.to(DEV))
+    l2.backward()
+    assert abs(float(l2.detach()) - float(loss.detach())) <= 1e-6                  # same seed -> same t / level -> same step
+    print(f"sr3_l2: loss {float(loss.detach()):.6f} (oracle {float(o_loss):.6f}); worst grad rel-RMS {max(worst.values()):.3e}")
 
 
 def test_train_loop_runs_unchanged_and_is_deterministic():
