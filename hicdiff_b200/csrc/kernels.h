@@ -295,6 +295,19 @@ struct WgradLaunch {
 int wgrad_prepare(const bf16* g, const bf16* x, int B, int H, int W, int C, int nsplit, float* part, WgradLaunch* out, char* err,
                   int errlen);
 cudaError_t wgrad_run(const WgradLaunch& l, cudaStream_t s);
+// general form: dY [B,H,W,Cout], X [B,H,W,Cin] NHWC bf16 (Cout, Cin multiples of 64; W in {8,16,32,64}; ksize 1 or 3)
+struct WgradGenLaunch {
+    CUtensorMap tmG, tmX;
+    int B, H, W, rows_kb, Cout, Cin, Nt, taps, mtiles, ntiles, nsplit, kb_total;
+    float* part;            // [nsplit][taps][Cout][Cin] fp32, wgrad_general_part_bytes(); set by the caller after prepare
+};
+int wgrad_general_prepare(const bf16* g, const bf16* x, int B, int H, int W, int Cout, int Cin, int ksize, int num_sms,
+                          WgradGenLaunch* out, char* err, int errlen);
+size_t wgrad_general_part_bytes(const WgradGenLaunch& l);
+cudaError_t wgrad_general_run(const WgradGenLaunch& l, cudaStream_t s);
+// dw [Cout, cin_total, k, k] columns [ci0, ci0 + Cin) (+)= scale * sum over the K splits (the slice of a channel concat)
+cudaError_t wgrad_general_reduce_run(const WgradGenLaunch& l, int cin_total, int ci0, float scale, int accumulate, float* dw,
+                                     cudaStream_t s);
 // dW [256, 256, 3, 3] (+)= scale * sum over the K splits
 cudaError_t wgrad_reduce_run(const float* part, int nsplit, float scale, int accumulate, float* dw, cudaStream_t s);
 size_t wgrad_part_bytes(int nsplit);

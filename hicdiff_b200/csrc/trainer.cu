@@ -501,6 +501,29 @@ int hd_op_conv3x3_wgrad(const uint16_t* x, const uint16_t* dy, float* dw, int32_
     return 0;
 }
 
+int hd_op_conv_wgrad(const uint16_t* x, const uint16_t* dy, float* dw, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                     int32_t ksize, int32_t cin_total, int32_t ci0, void* stream) {
+    if (!x || !dy || !dw || B < 1) return tfail("hd_op_conv_wgrad: bad argument");
+    if (ci0 < 0 || ci0 + Cin > cin_total) return tfail("hd_op_conv_wgrad: channel slice [%d, %d) outside [0, %d)", ci0, ci0 + Cin, cin_total);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    WgradGenLaunch wl;
+    char e[256];
+    if (wgrad_general_prepare(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), B, H, W, Cout, Cin, ksize, sms, &wl, e, sizeof(e)))
+        return tfail("%s", e);
+    float* ws = nullptr;
+    T_TRY(cudaMalloc(&ws, wgrad_general_part_bytes(wl)));
+    wl.part = ws;
+    cudaError_t ce = wgrad_general_run(wl, s);
+    if (ce == cudaSuccess) ce = wgrad_general_reduce_run(wl, cin_total, ci0, 1.0f, 0, dw, s);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    cudaFree(ws);
+    if (ce != cudaSuccess) return tfail("hd_op_conv_wgrad failed: %s", cudaGetErrorString(ce));
+    return 0;
+}
+
 int hd_op_conv3x3_dgrad(const uint16_t* dy, const float* w, uint16_t* dx, int32_t B, void* stream) {
     if (!dy || !w || !dx || B < 1) return tfail("hd_op_conv3x3_dgrad: bad argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -170,6 +170,142 @@ wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, float scale, int
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// General form (the Unet's convs): any Cout / Cin that are multiples of 64, 1x1 or 3x3, image width 8 .. 64.  One CTA =
+// one (tap, 128-channel Cout tile, <= 256-channel Cin tile, K split) with ONE accumulator; a K block is 64 pixels = 64 / W
+// image rows (box {64 ch, W, 64 / W rows, 1 img, chunks}); Cout = 64 rides as half of a 128-row tile whose upper chunk the
+// TMA unit zero-fills (the chunk coordinate is out of range).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int WGG_STAGES = 4;
+constexpr uint32_t WGG_CHUNK = 64 * 128;            // one 64-channel chunk of a 64-pixel K block
+constexpr uint32_t WGG_A_BYTES = 2 * WGG_CHUNK;
+constexpr uint32_t WGG_STAGE_MAX = WGG_A_BYTES + 4 * WGG_CHUNK;
+constexpr int WGG_SMEM = WGG_STAGES * WGG_STAGE_MAX + 1024 + 256;
+
+struct WgradGenKArgs {
+    int B, H, W, rows_kb;        // rows_kb = 64 / W image rows per K block
+    int Cout, Cin, Nt;           // Nt = Cin tile (64, 128 or 256)
+    int taps, mtiles, ntiles, nsplit;
+    int kb_total;                // B * H / rows_kb
+    float* part;                 // [nsplit][taps][Cout][Cin]
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_general_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const WgradGenKArgs a) {
+    extern __shared__ uint8_t wg_smem_raw[];
+    uint8_t* smem = wg_smem_raw + ((1024u - (ptx::smem_u32(wg_smem_raw) & 1023u)) & 1023u);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WGG_STAGES * WGG_STAGE_MAX);
+    uint64_t* empty_bar = full_bar + WGG_STAGES;
+    uint64_t* tfull_bar = empty_bar + WGG_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int id = blockIdx.x;
+    const int tap = id % a.taps; id /= a.taps;
+    const int mt = id % a.mtiles; id /= a.mtiles;
+    const int nt = id % a.ntiles; id /= a.ntiles;
+    const int split = id;
+    const int dy = a.taps == 9 ? tap / 3 - 1 : 0, dx = a.taps == 9 ? tap % 3 - 1 : 0;
+    const int kb0 = static_cast<int>(static_cast<long long>(a.kb_total) * split / a.nsplit);
+    const int kb1 = static_cast<int>(static_cast<long long>(a.kb_total) * (split + 1) / a.nsplit);
+    const uint32_t stage_bytes = WGG_A_BYTES + (a.Nt / 64) * WGG_CHUNK;
+    const int kb_per_img = a.H / a.rows_kb;
+    const uint32_t tmem_cols = a.Nt < 32 ? 32u : static_cast<uint32_t>(a.Nt);
+
+    if (warp == 0) {
+        if (lane == 0) { ptx::prefetch_tmap(&tmG); ptx::prefetch_tmap(&tmX); }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, tmem_cols);
+        ptx::tmem_relinquish();
+    } else if (warp == 1 && lane == 0) {
+        for (int i = 0; i < WGG_STAGES; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+        ptx::mbar_init(tfull_bar, 1);
+        ptx::fence_mbar_init();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            const int b = kb / kb_per_img, y0 = (kb - b * kb_per_img) * a.rows_kb;
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+            if (ptx::elect_one()) {
+                uint8_t* sA = smem + stage * WGG_STAGE_MAX;
+                ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+                ptx::tma_load_5d(sA, &tmG, &full_bar[stage], 0, 0, y0, b, mt * 2);
+                ptx::tma_load_5d(sA + WGG_A_BYTES, &tmX, &full_bar[stage], 0, dx, y0 + dy, b, nt * (a.Nt / 64));
+            }
+            __syncwarp();
+            if (++stage == WGG_STAGES) { stage = 0; phase ^= 1u; }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = ptx::make_idesc_bf16_mn(128, static_cast<uint32_t>(a.Nt));
+        constexpr uint32_t K16_STEP = 2048u >> 4;
+        const uint64_t desc0 = ptx::make_mnmajor_sw128_desc(ptx::smem_u32(smem), WGG_CHUNK, 1024);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint64_t da = desc0 + static_cast<uint64_t>((stage * WGG_STAGE_MAX) >> 4);
+                const uint64_t db = da + static_cast<uint64_t>(WGG_A_BYTES >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    ptx::umma_bf16(tmem_base, da + K16_STEP * k, db + K16_STEP * k, idesc, (kb == kb0 && k == 0) ? 0u : 1u);
+                ptx::umma_commit(&empty_bar[stage]);
+            }
+            __syncwarp();
+            if (++stage == WGG_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (ptx::elect_one()) ptx::umma_commit(tfull_bar);
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        ptx::mbar_wait(tfull_bar, 0);
+        ptx::tc_fence_after();
+        const int co = mt * 128 + q * 32 + lane;
+        float* orow = a.part + ((static_cast<size_t>(split) * a.taps + tap) * a.Cout + co) * a.Cin + nt * a.Nt;
+#pragma unroll 1
+        for (int c = 0; c < a.Nt; c += 32) {
+            uint32_t v[32];
+            ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, v);
+            ptx::tmem_ld_wait();
+            if (co < a.Cout) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<uint4*>(orow + c + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+        }
+        ptx::tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// dw[(co * cin_total + ci0 + ci) * taps + tap] (+)= scale * sum_split part[split][tap][co][ci]; one thread per (co, ci)
+__global__ void __launch_bounds__(256)
+wgrad_general_reduce_kernel(const float* __restrict__ part, int nsplit, int taps, int Cout, int Cin, int cin_total, int ci0,
+                            float scale, int accumulate, float* __restrict__ dw) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= Cout * Cin) return;
+    const int co = i / Cin, ci = i - co * Cin;
+    const size_t plane = static_cast<size_t>(Cout) * Cin;
+    float* o = dw + (static_cast<size_t>(co) * cin_total + ci0 + ci) * taps;
+    for (int tap = 0; tap < taps; ++tap) {
+        float t = 0.f;
+        for (int sp = 0; sp < nsplit; ++sp) t += __ldg(part + (static_cast<size_t>(sp) * taps + tap) * plane + i);
+        o[tap] = accumulate ? fmaf(scale, t, o[tap]) : scale * t;
+    }
+}
+
 }  // namespace
 
 int wgrad_prepare(const bf16* g, const bf16* x, int B, int H, int W, int C, int nsplit, float* part, WgradLaunch* out, char* err,
@@ -202,6 +338,59 @@ cudaError_t wgrad_run(const WgradLaunch& l, cudaStream_t s) {
     a.kb_total = l.kb_total; a.nsplit = l.nsplit; a.H = l.H; a.part = l.part;
 
     wgrad_kernel<<<9 * l.nsplit, WG_THREADS, WG_SMEM, s>>>(l.tmG, l.tmX, a);
+    return cudaGetLastError();
+}
+
+int wgrad_general_prepare(const bf16* g, const bf16* x, int B, int H, int W, int Cout, int Cin, int ksize, int num_sms,
+                          WgradGenLaunch* out, char* err, int errlen) {
+    if ((ksize != 1 && ksize != 3) || Cout % 64 != 0 || Cin % 64 != 0 || Cout < 64 || Cin < 64 ||
+        (W != 8 && W != 16 && W != 32 && W != 64) || H % (64 / W) != 0) {
+        snprintf(err, errlen, "wgrad: unsupported shape (B %d, H %d, W %d, Cout %d, Cin %d, k %d)", B, H, W, Cout, Cin, ksize);
+        return 1;
+    }
+    const int rows = 64 / W;
+    const int Nt = Cin % 256 == 0 ? 256 : (Cin % 128 == 0 ? 128 : 64);
+    cuuint64_t gd[5] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)Cout / 64};
+    cuuint64_t gs[4] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2, 128};
+    cuuint32_t gb[5] = {64, (cuuint32_t)W, (cuuint32_t)rows, 1, 2};
+    if (encode_tmap_bf16(&out->tmG, g, 5, gd, gs, gb, err, errlen)) return 1;
+    cuuint64_t xd[5] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)Cin / 64};
+    cuuint64_t xs[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2, 128};
+    cuuint32_t xb[5] = {64, (cuuint32_t)W, (cuuint32_t)rows, 1, (cuuint32_t)Nt / 64};
+    if (encode_tmap_bf16(&out->tmX, x, 5, xd, xs, xb, err, errlen)) return 1;
+    out->B = B; out->H = H; out->W = W; out->rows_kb = rows; out->Cout = Cout; out->Cin = Cin; out->Nt = Nt;
+    out->taps = ksize * ksize;
+    out->mtiles = (Cout + 127) / 128;
+    out->ntiles = Cin / Nt;
+    out->kb_total = B * H / rows;
+    const int units = out->taps * out->mtiles * out->ntiles;
+    int ns = (2 * num_sms + units - 1) / units;             // about two waves of CTAs
+    if (ns > out->kb_total / 2) ns = out->kb_total / 2;
+    if (ns < 1) ns = 1;
+    if (ns > 32) ns = 32;
+    out->nsplit = ns;
+    out->part = nullptr;
+    cudaError_t e = cudaFuncSetAttribute(wgrad_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WGG_SMEM);
+    if (e != cudaSuccess) { snprintf(err, errlen, "wgrad: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return 1; }
+    return 0;
+}
+
+size_t wgrad_general_part_bytes(const WgradGenLaunch& l) {
+    return static_cast<size_t>(l.nsplit) * l.taps * l.Cout * l.Cin * sizeof(float);
+}
+
+cudaError_t wgrad_general_run(const WgradGenLaunch& l, cudaStream_t s) {
+    WgradGenKArgs a;
+    a.B = l.B; a.H = l.H; a.W = l.W; a.rows_kb = l.rows_kb; a.Cout = l.Cout; a.Cin = l.Cin; a.Nt = l.Nt; a.taps = l.taps;
+    a.mtiles = l.mtiles; a.ntiles = l.ntiles; a.nsplit = l.nsplit; a.kb_total = l.kb_total; a.part = l.part;
+    wgrad_general_kernel<<<l.taps * l.mtiles * l.ntiles * l.nsplit, WG_THREADS, WGG_SMEM, s>>>(l.tmG, l.tmX, a);
+    return cudaGetLastError();
+}
+
+cudaError_t wgrad_general_reduce_run(const WgradGenLaunch& l, int cin_total, int ci0, float scale, int accumulate, float* dw,
+                                     cudaStream_t s) {
+    const int n = l.Cout * l.Cin;
+    wgrad_general_reduce_kernel<<<(n + 255) / 256, 256, 0, s>>>(l.part, l.nsplit, l.taps, l.Cout, l.Cin, cin_total, ci0, scale, accumulate, dw);
     return cudaGetLastError();
 }
 

@@ -215,3 +215,19 @@ def conv3x3_dgrad_nhwc(dy, w):
     dx = torch.empty_like(dy)
     _lib.check(lib.hd_op_conv3x3_dgrad(_lib.ptr(dy), _lib.ptr(w), _lib.ptr(dx), dy.shape[0], _lib.stream_ptr()), "hd_op_conv3x3_dgrad")
     return dx
+
+
+def conv_wgrad_nhwc(x, dy, ksize, dw=None, cin_total=None, ci0=0):
+    """General conv weight gradient: x [B,H,W,Cin], dy [B,H,W,Cout] bf16 -> dw fp32 [Cout, cin_total, k, k] (columns
+    [ci0, ci0 + Cin) are written; pass `dw` to fill the slices of a channel concat one operand at a time)."""
+    lib = _lib.load()
+    _need_cuda(x, dy)
+    x, dy = _bf16c(x), _bf16c(dy)
+    B, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    cin_total = Cin if cin_total is None else cin_total
+    if dw is None:
+        dw = torch.zeros(Cout, cin_total, ksize, ksize, device=x.device, dtype=torch.float32)
+    _lib.check(lib.hd_op_conv_wgrad(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(dw), B, H, W, Cin, Cout, ksize, cin_total, ci0,
+                                    _lib.stream_ptr()), "hd_op_conv_wgrad")
+    return dw

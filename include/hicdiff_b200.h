@@ -151,6 +151,11 @@ HD_API void hd_trainer_destroy(hd_trainer* trainer);
 /* The two conv gradients as single operators (256 -> 256, 3x3 "same", 64x64 tiles; activations bf16 NHWC as uint16):
  * dw fp32 [256,256,3,3] = d/dW of conv2d(x, W) given dy; dx = d/dx given dy and W (fp32, reference layout).  Synchronise. */
 HD_API int hd_op_conv3x3_wgrad(const uint16_t* x, const uint16_t* dy, float* dw, int32_t B, void* stream);
+/* General conv weight gradient (the Unet's shapes): x [B,H,W,Cin], dy [B,H,W,Cout] bf16 NHWC, Cin / Cout multiples of 64, W in
+ * {8,16,32,64}, ksize 1 or 3 ("same").  Writes columns [ci0, ci0 + Cin) of dw fp32 [Cout, cin_total, k, k] -- the slice that
+ * belongs to one operand of a channel concat (cin_total = Cin, ci0 = 0 for a plain conv).  Synchronises. */
+HD_API int hd_op_conv_wgrad(const uint16_t* x, const uint16_t* dy, float* dw, int32_t B, int32_t H, int32_t W, int32_t Cin,
+                     int32_t Cout, int32_t ksize, int32_t cin_total, int32_t ci0, void* stream);
 HD_API int hd_op_conv3x3_dgrad(const uint16_t* dy, const float* w, uint16_t* dx, int32_t B, void* stream);
 
 /* -------------------------------------------------------------------------------------------------------------

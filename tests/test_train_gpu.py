@@ -174,3 +174,44 @@ def test_eval_and_unsupported_paths():
     loss = d2.p_losses([noisy.to(DEV), clean.to(DEV)], t=torch.tensor([1, 5], device=DEV), noise=noise.to(DEV))
     with pytest.raises(NotImplementedError):
         loss.backward()
+
+
+WGRAD_CASES = [
+    # B, H, Cin, Cout, k      (the Unet's levels: 64x64 .. 8x8, 1x1 and 3x3, Cout = 64 rides on a zero-filled 128-row tile)
+    (2, 64, 64, 64, 3), (2, 64, 128, 64, 3), (2, 32, 128, 128, 3), (3, 16, 256, 256, 3), (4, 8, 512, 512, 3),
+    (2, 8, 256, 512, 3), (2, 64, 64, 384, 1), (2, 32, 128, 64, 1), (3, 16, 256, 128, 1), (2, 8, 512, 256, 1),
+]
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout,k", WGRAD_CASES)
+def test_general_conv_wgrad(B, H, Cin, Cout, k):
+    from hicdiff_b200 import ops
+
+    g = torch.Generator().manual_seed(B * 1000 + H + Cin + Cout + k)
+    x = torch.randn(B, H, H, Cin, generator=g).to(torch.bfloat16)
+    dy = (torch.randn(B, H, H, Cout, generator=g) * 0.1).to(torch.bfloat16)
+    wr = torch.zeros(Cout, Cin, k, k, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(x.permute(0, 3, 1, 2).double(), wr, padding=k // 2)
+    (gw,) = torch.autograd.grad(y, [wr], dy.permute(0, 3, 1, 2).double())
+    dw = ops.conv_wgrad_nhwc(x.to(DEV), dy.to(DEV), k)
+    assert torch.isfinite(dw).all()
+    assert _rel(dw, gw) <= 4e-3, _rel(dw, gw)
+    for t in range(k * k):
+        assert _rel(dw[:, :, t // k, t % k], gw[:, :, t // k, t % k]) <= 4e-3, t
+
+
+def test_general_conv_wgrad_concat_slices():
+    """torch.cat((x, skip), 1) feeding a conv: the weight gradient is filled one operand at a time."""
+    from hicdiff_b200 import ops
+
+    g = torch.Generator().manual_seed(11)
+    B, H, C0, C1, Cout = 2, 32, 128, 64, 128
+    x0 = torch.randn(B, H, H, C0, generator=g).to(torch.bfloat16)
+    x1 = torch.randn(B, H, H, C1, generator=g).to(torch.bfloat16)
+    dy = (torch.randn(B, H, H, Cout, generator=g) * 0.1).to(torch.bfloat16)
+    wr = torch.zeros(Cout, C0 + C1, 3, 3, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(torch.cat((x0, x1), -1).permute(0, 3, 1, 2).double(), wr, padding=1)
+    (gw,) = torch.autograd.grad(y, [wr], dy.permute(0, 3, 1, 2).double())
+    dw = ops.conv_wgrad_nhwc(x0.to(DEV), dy.to(DEV), 3, cin_total=C0 + C1, ci0=0)
+    dw = ops.conv_wgrad_nhwc(x1.to(DEV), dy.to(DEV), 3, dw=dw, cin_total=C0 + C1, ci0=C0)
+    assert _rel(dw, gw) <= 4e-3, _rel(dw, gw)
