@@ -342,6 +342,33 @@ cudaError_t act_apply_run(const float* x, float* y, long long n, int act, cudaSt
 cudaError_t act_grad_run(float* d, const float* x, long long n, int act, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------
+// norm_bwd.cu -- backward of GroupNorm(8)+FiLM+SiLU, channel LayerNorm, weight standardisation (Unet training blocks)
+// ---------------------------------------------------------------------------------------------
+struct GroupNormBwdArgs {
+    const bf16* y;        // [B, P, C] the GroupNorm INPUT (conv output)
+    const bf16* ds;       // [B, P, C] gradient w.r.t. the block output SiLU(...)
+    bf16* dy;             // [B, P, C] gradient w.r.t. y (may alias ds)
+    int B, P, C;
+    const float* gamma;   // [C]
+    const float* beta;    // [C]
+    float eps;
+    const float* scale = nullptr;   // [B, C] FiLM scale (nullptr: no FiLM, e.g. block2)
+    const float* shift = nullptr;   // [B, C]
+    float* dgamma;        // [C]
+    float* dbeta;         // [C]
+    float* dscale = nullptr;        // [B, C] (optional)
+    float* dshift = nullptr;        // [B, C]
+};
+size_t gn_bwd_scratch_floats(int B, int P, int C);
+cudaError_t groupnorm_silu_bwd_run(const GroupNormBwdArgs& a, float* scratch, cudaStream_t s);
+int ln_bwd_blocks(long long M);
+// z = LayerNorm_C(x) * gain: dx (may NOT alias x), dgain [C]; part: ln_bwd_blocks(M) * C floats
+cudaError_t channel_layernorm_bwd_run(const bf16* x, const bf16* dz, const float* gain, long long M, int C, float eps, bf16* dx,
+                                      float* dgain, float* part, cudaStream_t s);
+// dw [Cout, K] from the gradient w.r.t. the standardised weight (dw may alias dwt)
+cudaError_t weight_standardize_bwd_run(const float* w, const float* dwt, int Cout, int K, float eps, float* dw, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
 // dataprep.cu -- contact triples -> dense matrix, empty-bin removal, exact percentile, normalisation, noise injection
 // ---------------------------------------------------------------------------------------------
 size_t coo_scratch_bytes(long long n);

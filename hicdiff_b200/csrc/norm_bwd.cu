@@ -1,0 +1,359 @@
+// Backward of the Unet's normalisation layers (building blocks of the Unet training step):
+//
+//   Block           s = SiLU( GN_8(y) * (scale + 1) + shift ),  GN_8(y) = (y - mu_g) * r_g * gamma + beta
+//                   /root/reference/src/hicdiff_condition.py:155-171 (nn.GroupNorm(8, C), eps 1e-5, biased variance)
+//   LayerNorm       z = (x - mu) * rsqrt(var + eps) * g over the channel dimension of every pixel      :99-108
+//   WeightStandardizedConv2d   w~ = (w - mu_o) * rsqrt(var_o + eps) per output channel                :84-97
+//
+// GroupNorm backward, with dh = ds * SiLU'(h), xhat = (y - mu) * r and per (sample, channel) U = sum_p dh, V = sum_p dh xhat:
+//   d shift = U,  d scale = gamma V + beta U,  d beta = sum_b (scale + 1) U,  d gamma = sum_b (scale + 1) V,
+//   dy = r * ( dh (scale + 1) gamma  -  m1  -  xhat m2 ),  m1 = mean_g[(scale + 1) gamma U] , m2 = mean_g[(scale + 1) gamma V]
+// (means over the group's channels and all pixels).  Three streaming passes (statistics, (U, V), dy); every reduction is
+// two-stage in a fixed order -> bit-reproducible.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace hd {
+namespace {
+
+constexpr int G = 8;   // groups
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+    float2 t;
+    t = ptx::unpack_bf16x2(u.x); v[0] = t.x; v[1] = t.y;
+    t = ptx::unpack_bf16x2(u.y); v[2] = t.x; v[3] = t.y;
+    t = ptx::unpack_bf16x2(u.z); v[4] = t.x; v[5] = t.y;
+    t = ptx::unpack_bf16x2(u.w); v[6] = t.x; v[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+    uint4 o;
+    o.x = ptx::pack_bf16x2(v[0], v[1]); o.y = ptx::pack_bf16x2(v[2], v[3]);
+    o.z = ptx::pack_bf16x2(v[4], v[5]); o.w = ptx::pack_bf16x2(v[6], v[7]);
+    return o;
+}
+__device__ __forceinline__ float block_sum(float v, float* s_red) {   // 256 threads; result valid in every thread
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += s_red[k];
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------- statistics
+// grid (G, B): mean and rstd of group g of sample b (two passes over the group's P * cpg elements: mean, then variance)
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const uint4* __restrict__ y, int P, int C, float eps, float2* __restrict__ stats) {
+    __shared__ float s_red[8];
+    const int g = blockIdx.x, b = blockIdx.y;
+    const int cpp = C / 8, gch = cpp / G;                       // 16-byte chunks per pixel / per group (cpg = 8 * gch channels)
+    const uint4* base = y + static_cast<size_t>(b) * P * cpp + g * gch;
+    const int n_chunks = P * gch;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n_chunks; i += 256) {
+        float v[8];
+        unpack8(__ldg(base + static_cast<size_t>(i / gch) * cpp + i % gch), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += v[j];
+    }
+    const float n = static_cast<float>(n_chunks) * 8.0f;
+    const float mean = block_sum(acc, s_red) / n;
+    acc = 0.f;
+    for (int i = threadIdx.x; i < n_chunks; i += 256) {
+        float v[8];
+        unpack8(__ldg(base + static_cast<size_t>(i / gch) * cpp + i % gch), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; acc = fmaf(d, d, acc); }
+    }
+    const float var = block_sum(acc, s_red) / n;
+    if (threadIdx.x == 0) stats[b * G + g] = make_float2(mean, rsqrtf(var + eps));
+}
+
+__device__ __forceinline__ float silu_grad(float h) {
+    const float sg = 1.0f / (1.0f + __expf(-h));
+    return sg * (1.0f + h * (1.0f - sg));
+}
+
+constexpr int GB_CHUNKS_MAX = 16;
+
+// ---------------------------------------------------------------------------------------------- pass 1: (U, V) partials
+// grid (nchunk, B); thread = (8-channel chunk cc, pixel lane pl), lanes = 256 / (C / 8)
+__global__ void __launch_bounds__(256)
+gn_bwd_sums_kernel(const uint4* __restrict__ y, const uint4* __restrict__ ds, const float2* __restrict__ stats,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ scale,
+                   const float* __restrict__ shift, int P, int C, int nchunk, float* __restrict__ part) {
+    extern __shared__ float gs_red[];   // [lanes][2 * C]
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int cpp = C / 8, lanes = 256 / cpp;
+    const int cc = threadIdx.x % cpp, pl = threadIdx.x / cpp;
+    const int ppc = P / nchunk;
+    const float2 st = stats[b * G + (cc * 8) / (C / G)];
+    float ga[8], be[8], sc1[8], sh[8], U[8], V[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = cc * 8 + j;
+        ga[j] = gamma[c]; be[j] = beta[c];
+        sc1[j] = scale ? scale[static_cast<size_t>(b) * C + c] + 1.0f : 1.0f;
+        sh[j] = shift ? shift[static_cast<size_t>(b) * C + c] : 0.0f;
+        U[j] = 0.f; V[j] = 0.f;
+    }
+    const size_t base = (static_cast<size_t>(b) * P + static_cast<size_t>(chunk) * ppc) * cpp + cc;
+    for (int p = pl; p < ppc; p += lanes) {
+        float yv[8], g[8];
+        unpack8(__ldg(y + base + static_cast<size_t>(p) * cpp), yv);
+        unpack8(__ldg(ds + base + static_cast<size_t>(p) * cpp), g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float xh = (yv[j] - st.x) * st.y;
+            const float h = fmaf(fmaf(xh, ga[j], be[j]), sc1[j], sh[j]);
+            const float dh = g[j] * silu_grad(h);
+            U[j] += dh;
+            V[j] = fmaf(dh, xh, V[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { gs_red[pl * 2 * C + cc * 8 + j] = U[j]; gs_red[pl * 2 * C + C + cc * 8 + j] = V[j]; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += 256) {
+        float t = 0.f;
+        for (int k = 0; k < lanes; ++k) t += gs_red[k * 2 * C + i];
+        part[(static_cast<size_t>(b) * nchunk + chunk) * 2 * C + i] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- per-sample coefficients
+// grid B, 2 * 256 threads max -> one thread per channel (C <= 512): UV[b][2][C], group means m[b][G][2], d scale / d shift
+__global__ void __launch_bounds__(512)
+gn_bwd_coef_kernel(const float* __restrict__ part, int nchunk, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const float* __restrict__ scale, int P, int C, float* __restrict__ UV, float* __restrict__ gm,
+                   float* __restrict__ dscale, float* __restrict__ dshift) {
+    __shared__ float s_a[512], s_b[512];
+    const int b = blockIdx.x, c = threadIdx.x;
+    float U = 0.f, V = 0.f;
+    if (c < C) {
+        for (int k = 0; k < nchunk; ++k) {
+            U += part[(static_cast<size_t>(b) * nchunk + k) * 2 * C + c];
+            V += part[(static_cast<size_t>(b) * nchunk + k) * 2 * C + C + c];
+        }
+        UV[(static_cast<size_t>(b) * 2) * C + c] = U;
+        UV[(static_cast<size_t>(b) * 2 + 1) * C + c] = V;
+        if (dshift) dshift[static_cast<size_t>(b) * C + c] = U;
+        if (dscale) dscale[static_cast<size_t>(b) * C + c] = fmaf(gamma[c], V, beta[c] * U);
+        const float k1 = (scale ? scale[static_cast<size_t>(b) * C + c] + 1.0f : 1.0f) * gamma[c];
+        s_a[c] = k1 * U;
+        s_b[c] = k1 * V;
+    }
+    __syncthreads();
+    if (c < G) {
+        const int cpg = C / G;
+        float a = 0.f, v = 0.f;
+        for (int j = 0; j < cpg; ++j) { a += s_a[c * cpg + j]; v += s_b[c * cpg + j]; }
+        const float inv = 1.0f / (static_cast<float>(cpg) * static_cast<float>(P));
+        gm[(b * G + c) * 2] = a * inv;
+        gm[(b * G + c) * 2 + 1] = v * inv;
+    }
+}
+
+// d gamma[c] = sum_b (scale + 1) V, d beta[c] = sum_b (scale + 1) U  (accumulate: += for a layer used more than once)
+__global__ void gn_bwd_affine_kernel(const float* __restrict__ UV, const float* __restrict__ scale, int B, int C,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float dg = 0.f, db = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const float s1 = scale ? scale[static_cast<size_t>(b) * C + c] + 1.0f : 1.0f;
+        db = fmaf(s1, UV[(static_cast<size_t>(b) * 2) * C + c], db);
+        dg = fmaf(s1, UV[(static_cast<size_t>(b) * 2 + 1) * C + c], dg);
+    }
+    dgamma[c] = dg;
+    dbeta[c] = db;
+}
+
+// ---------------------------------------------------------------------------------------------- pass 2: dy
+__global__ void __launch_bounds__(256)
+gn_bwd_dx_kernel(const uint4* __restrict__ y, const uint4* ds, const float2* __restrict__ stats, const float* __restrict__ gm,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ scale,
+                 const float* __restrict__ shift, int P, int C, int nchunk, uint4* dy) {
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int cpp = C / 8, lanes = 256 / cpp;
+    const int cc = threadIdx.x % cpp, pl = threadIdx.x / cpp;
+    const int ppc = P / nchunk;
+    const int g = (cc * 8) / (C / G);
+    const float2 st = stats[b * G + g];
+    const float m1 = gm[(b * G + g) * 2], m2 = gm[(b * G + g) * 2 + 1];
+    float ga[8], be[8], sc1[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = cc * 8 + j;
+        ga[j] = gamma[c]; be[j] = beta[c];
+        sc1[j] = scale ? scale[static_cast<size_t>(b) * C + c] + 1.0f : 1.0f;
+        sh[j] = shift ? shift[static_cast<size_t>(b) * C + c] : 0.0f;
+    }
+    const size_t base = (static_cast<size_t>(b) * P + static_cast<size_t>(chunk) * ppc) * cpp + cc;
+    for (int p = pl; p < ppc; p += lanes) {
+        const size_t i = base + static_cast<size_t>(p) * cpp;
+        float yv[8], gr[8];
+        unpack8(__ldg(y + i), yv);
+        unpack8(ds[i], gr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float xh = (yv[j] - st.x) * st.y;
+            const float h = fmaf(fmaf(xh, ga[j], be[j]), sc1[j], sh[j]);
+            const float dh = gr[j] * silu_grad(h);
+            gr[j] = st.y * (dh * sc1[j] * ga[j] - m1 - xh * m2);
+        }
+        dy[i] = pack8(gr);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- channel LayerNorm backward
+// z = xhat * g, xhat = (x - mu) * r over the C channels of a pixel.  One warp per pixel:
+//   dx = r * (dz g - mean_c(dz g) - xhat mean_c(dz g xhat));  dg partial sums per block -> part[blk][C]
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dz, const float* __restrict__ gain, long long M, int C,
+              float eps, bf16* __restrict__ dx, float* __restrict__ part) {
+    extern __shared__ float ln_dg[];   // [8 warps][C]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = C / 32;            // channels per lane (2 .. 16)
+    float dg[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dg[j] = 0.f;
+    for (long long m = static_cast<long long>(blockIdx.x) * 8 + warp; m < M; m += static_cast<long long>(gridDim.x) * 8) {
+        float xv[16], gv[16];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (j < per) {
+                const int c = j * 32 + lane;
+                xv[j] = __bfloat162float(x[m * C + c]);
+                gv[j] = __bfloat162float(dz[m * C + c]);
+                s += xv[j];
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s / C;
+        float vs = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if (j < per) { const float d = xv[j] - mean; vs = fmaf(d, d, vs); }
+        for (int o = 16; o > 0; o >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, o);
+        const float r = rsqrtf(vs / C + eps);
+        float a = 0.f, bsum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (j < per) {
+                const int c = j * 32 + lane;
+                const float xh = (xv[j] - mean) * r;
+                const float t = gv[j] * gain[c];
+                dg[j] = fmaf(gv[j], xh, dg[j]);
+                a += t;
+                bsum = fmaf(t, xh, bsum);
+                xv[j] = xh;
+                gv[j] = t;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); bsum += __shfl_xor_sync(0xffffffffu, bsum, o); }
+        a /= C; bsum /= C;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (j < per) dx[m * C + j * 32 + lane] = __float2bfloat16(r * (gv[j] - a - xv[j] * bsum));
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) if (j < per) ln_dg[warp * C + j * 32 + lane] = dg[j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += ln_dg[k * C + c];
+        part[static_cast<size_t>(blockIdx.x) * C + c] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- weight standardisation backward
+// grid Cout: dw = rstd * (dwt - mean(dwt) - what * mean(dwt * what)), what = (w - mean) * rstd over K = Cin * k * k
+__global__ void __launch_bounds__(256)
+ws_bwd_kernel(const float* __restrict__ w, const float* dwt, int K, float eps, float* dw) {
+    __shared__ float s_red[8];
+    const float* wr = w + static_cast<size_t>(blockIdx.x) * K;
+    const float* gr = dwt + static_cast<size_t>(blockIdx.x) * K;
+    float* orow = dw + static_cast<size_t>(blockIdx.x) * K;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < K; i += 256) s += wr[i];
+    const float mean = block_sum(s, s_red) / K;
+    float v = 0.f;
+    for (int i = threadIdx.x; i < K; i += 256) { const float d = wr[i] - mean; v = fmaf(d, d, v); }
+    const float rstd = rsqrtf(block_sum(v, s_red) / K + eps);
+    float a = 0.f, bsum = 0.f;
+    for (int i = threadIdx.x; i < K; i += 256) {
+        const float g = gr[i];
+        a += g;
+        bsum = fmaf(g, (wr[i] - mean) * rstd, bsum);
+    }
+    a = block_sum(a, s_red) / K;
+    bsum = block_sum(bsum, s_red) / K;
+    for (int i = threadIdx.x; i < K; i += 256) orow[i] = rstd * (gr[i] - a - (wr[i] - mean) * rstd * bsum);
+}
+
+__global__ void sum_rows_kernel(const float* __restrict__ part, int nparts, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float t = 0.f;
+    for (int k = 0; k < nparts; ++k) t += part[static_cast<size_t>(k) * n + i];
+    out[i] = t;
+}
+
+int gn_chunks(int P, int C) {
+    const int lanes = 256 / (C / 8);
+    int nchunk = GB_CHUNKS_MAX;
+    while (nchunk > 1 && (P % nchunk != 0 || (P / nchunk) < lanes)) nchunk >>= 1;
+    return nchunk;
+}
+
+}  // namespace
+
+size_t gn_bwd_scratch_floats(int B, int P, int C) {
+    return static_cast<size_t>(B) * G * 2 /*stats*/ + static_cast<size_t>(B) * gn_chunks(P, C) * 2 * C /*part*/ +
+           static_cast<size_t>(B) * 2 * C /*UV*/ + static_cast<size_t>(B) * G * 2 /*gm*/ + 64;
+}
+
+cudaError_t groupnorm_silu_bwd_run(const GroupNormBwdArgs& a, float* scratch, cudaStream_t s) {
+    const int B = a.B, P = a.P, C = a.C;
+    if (C % 64 != 0 || C > 512 || 256 % (C / 8) != 0) return cudaErrorInvalidValue;
+    const int nchunk = gn_chunks(P, C);
+    const int lanes = 256 / (C / 8);
+    float2* stats = reinterpret_cast<float2*>(scratch);
+    float* part = scratch + static_cast<size_t>(B) * G * 2;
+    float* UV = part + static_cast<size_t>(B) * nchunk * 2 * C;
+    float* gm = UV + static_cast<size_t>(B) * 2 * C;
+    const uint4* y = reinterpret_cast<const uint4*>(a.y);
+    const uint4* ds = reinterpret_cast<const uint4*>(a.ds);
+    gn_stats_kernel<<<dim3(G, B), 256, 0, s>>>(y, P, C, a.eps, stats);
+    gn_bwd_sums_kernel<<<dim3(nchunk, B), 256, static_cast<size_t>(lanes) * 2 * C * sizeof(float), s>>>(
+        y, ds, stats, a.gamma, a.beta, a.scale, a.shift, P, C, nchunk, part);
+    gn_bwd_coef_kernel<<<B, 512, 0, s>>>(part, nchunk, a.gamma, a.beta, a.scale, P, C, UV, gm, a.dscale, a.dshift);
+    gn_bwd_affine_kernel<<<(C + 255) / 256, 256, 0, s>>>(UV, a.scale, B, C, a.dgamma, a.dbeta);
+    gn_bwd_dx_kernel<<<dim3(nchunk, B), 256, 0, s>>>(y, ds, stats, gm, a.gamma, a.beta, a.scale, a.shift, P, C, nchunk,
+                                                      reinterpret_cast<uint4*>(a.dy));
+    return cudaGetLastError();
+}
+
+int ln_bwd_blocks(long long M) { return static_cast<int>(M / 8 < 592 ? (M + 7) / 8 : 592); }
+
+cudaError_t channel_layernorm_bwd_run(const bf16* x, const bf16* dz, const float* gain, long long M, int C, float eps, bf16* dx,
+                                      float* dgain, float* part, cudaStream_t s) {
+    if (C % 32 != 0 || C > 512) return cudaErrorInvalidValue;
+    const int blocks = ln_bwd_blocks(M);
+    ln_bwd_kernel<<<blocks, 256, static_cast<size_t>(8) * C * sizeof(float), s>>>(x, dz, gain, M, C, eps, dx, part);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    sum_rows_kernel<<<(C + 255) / 256, 256, 0, s>>>(part, blocks, C, dgain);
+    return cudaGetLastError();
+}
+
+cudaError_t weight_standardize_bwd_run(const float* w, const float* dwt, int Cout, int K, float eps, float* dw, cudaStream_t s) {
+    ws_bwd_kernel<<<Cout, 256, 0, s>>>(w, dwt, K, eps, dw);
+    return cudaGetLastError();
+}
+
+}  // namespace hd

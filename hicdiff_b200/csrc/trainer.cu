@@ -501,6 +501,45 @@ int hd_op_conv3x3_wgrad(const uint16_t* x, const uint16_t* dy, float* dw, int32_
     return 0;
 }
 
+int hd_op_groupnorm_silu_bwd(const uint16_t* y, const uint16_t* ds, const float* gamma, const float* beta, const float* scale,
+                             const float* shift, uint16_t* dy, float* dgamma, float* dbeta, float* dscale, float* dshift, int32_t B,
+                             int32_t P, int32_t C, void* stream) {
+    if (!y || !ds || !gamma || !beta || !dy || !dgamma || !dbeta || B < 1) return tfail("hd_op_groupnorm_silu_bwd: bad argument");
+    if ((scale == nullptr) != (shift == nullptr)) return tfail("hd_op_groupnorm_silu_bwd: scale and shift come together");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float* scratch = nullptr;
+    T_TRY(cudaMalloc(&scratch, gn_bwd_scratch_floats(B, P, C) * sizeof(float)));
+    GroupNormBwdArgs a;
+    a.y = reinterpret_cast<const bf16*>(y); a.ds = reinterpret_cast<const bf16*>(ds); a.dy = reinterpret_cast<bf16*>(dy);
+    a.B = B; a.P = P; a.C = C; a.gamma = gamma; a.beta = beta; a.eps = 1e-5f; a.scale = scale; a.shift = shift;
+    a.dgamma = dgamma; a.dbeta = dbeta; a.dscale = dscale; a.dshift = dshift;
+    cudaError_t ce = groupnorm_silu_bwd_run(a, scratch, s);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    cudaFree(scratch);
+    if (ce != cudaSuccess) return tfail("hd_op_groupnorm_silu_bwd failed: %s", cudaGetErrorString(ce));
+    return 0;
+}
+
+int hd_op_channel_layernorm_bwd(const uint16_t* x, const uint16_t* dz, const float* g, uint16_t* dx, float* dg, int64_t M, int32_t C,
+                                void* stream) {
+    if (!x || !dz || !g || !dx || !dg || M < 1) return tfail("hd_op_channel_layernorm_bwd: bad argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float* part = nullptr;
+    T_TRY(cudaMalloc(&part, static_cast<size_t>(ln_bwd_blocks(M)) * C * sizeof(float)));
+    cudaError_t ce = channel_layernorm_bwd_run(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dz), g, M, C, 1e-5f,
+                                               reinterpret_cast<bf16*>(dx), dg, part, s);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    cudaFree(part);
+    if (ce != cudaSuccess) return tfail("hd_op_channel_layernorm_bwd failed: %s", cudaGetErrorString(ce));
+    return 0;
+}
+
+int hd_op_weight_standardize_bwd(const float* w, const float* dwt, float* dw, int32_t Cout, int32_t K, void* stream) {
+    if (!w || !dwt || !dw || Cout < 1 || K < 1) return tfail("hd_op_weight_standardize_bwd: bad argument");
+    T_TRY(weight_standardize_bwd_run(w, dwt, Cout, K, 1e-5f, dw, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
 int hd_op_conv_wgrad(const uint16_t* x, const uint16_t* dy, float* dw, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
                      int32_t ksize, int32_t cin_total, int32_t ci0, void* stream) {
     if (!x || !dy || !dw || B < 1) return tfail("hd_op_conv_wgrad: bad argument");

@@ -231,3 +231,45 @@ def conv_wgrad_nhwc(x, dy, ksize, dw=None, cin_total=None, ci0=0):
     _lib.check(lib.hd_op_conv_wgrad(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(dw), B, H, W, Cin, Cout, ksize, cin_total, ci0,
                                     _lib.stream_ptr()), "hd_op_conv_wgrad")
     return dw
+
+
+def groupnorm_silu_bwd_nhwc(y, ds, gamma, beta, scale=None, shift=None):
+    """Backward of SiLU(GroupNorm_8(y) * (scale + 1) + shift): y, ds [B,H,W,C] bf16 -> (dy bf16, dgamma, dbeta, dscale, dshift)."""
+    lib = _lib.load()
+    _need_cuda(y, ds)
+    y, ds = _bf16c(y), _bf16c(ds)
+    B, H, W, C = y.shape
+    gamma, beta, scale, shift = _f32c(gamma), _f32c(beta), _f32c(scale), _f32c(shift)
+    dy = torch.empty_like(y)
+    dgamma = torch.empty(C, device=y.device, dtype=torch.float32)
+    dbeta = torch.empty_like(dgamma)
+    dscale = torch.empty(B, C, device=y.device, dtype=torch.float32) if scale is not None else None
+    dshift = torch.empty_like(dscale) if scale is not None else None
+    _lib.check(lib.hd_op_groupnorm_silu_bwd(_lib.ptr(y), _lib.ptr(ds), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(scale), _lib.ptr(shift),
+                                            _lib.ptr(dy), _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.ptr(dscale), _lib.ptr(dshift),
+                                            B, H * W, C, _lib.stream_ptr()), "hd_op_groupnorm_silu_bwd")
+    return dy, dgamma, dbeta, dscale, dshift
+
+
+def channel_layernorm_bwd_nhwc(x, dz, g):
+    """Backward of the channel LayerNorm: x, dz [..., C] bf16, g [C] -> (dx bf16, dg fp32 [C])."""
+    lib = _lib.load()
+    _need_cuda(x, dz)
+    x, dz, g = _bf16c(x), _bf16c(dz), _f32c(g).reshape(-1)
+    C = x.shape[-1]
+    dx = torch.empty_like(x)
+    dg = torch.empty(C, device=x.device, dtype=torch.float32)
+    _lib.check(lib.hd_op_channel_layernorm_bwd(_lib.ptr(x), _lib.ptr(dz), _lib.ptr(g), _lib.ptr(dx), _lib.ptr(dg), x.numel() // C, C,
+                                               _lib.stream_ptr()), "hd_op_channel_layernorm_bwd")
+    return dx, dg
+
+
+def weight_standardize_bwd(w, dwt):
+    """Gradient w.r.t. the raw weight from the gradient w.r.t. WeightStandardizedConv2d's standardised weight."""
+    lib = _lib.load()
+    _need_cuda(w, dwt)
+    w, dwt = _f32c(w), _f32c(dwt)
+    dw = torch.empty_like(w)
+    _lib.check(lib.hd_op_weight_standardize_bwd(_lib.ptr(w), _lib.ptr(dwt), _lib.ptr(dw), w.shape[0], w[0].numel(), _lib.stream_ptr()),
+               "hd_op_weight_standardize_bwd")
+    return dw

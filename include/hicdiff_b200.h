@@ -156,6 +156,19 @@ HD_API int hd_op_conv3x3_wgrad(const uint16_t* x, const uint16_t* dy, float* dw,
  * belongs to one operand of a channel concat (cin_total = Cin, ci0 = 0 for a plain conv).  Synchronises. */
 HD_API int hd_op_conv_wgrad(const uint16_t* x, const uint16_t* dy, float* dw, int32_t B, int32_t H, int32_t W, int32_t Cin,
                      int32_t Cout, int32_t ksize, int32_t cin_total, int32_t ci0, void* stream);
+/* Backward of Block's tail (hicdiff_condition.py:159-171): s = SiLU(GroupNorm_8(y) * (scale + 1) + shift).  y, ds, dy bf16
+ * [B,P,C] (dy may alias ds); gamma / beta [C]; scale / shift [B,C] or both NULL (block2); outputs dgamma / dbeta [C] and,
+ * when FiLM is present, dscale / dshift [B,C].  eps = 1e-5.  Synchronises. */
+HD_API int hd_op_groupnorm_silu_bwd(const uint16_t* y, const uint16_t* ds, const float* gamma, const float* beta, const float* scale,
+                             const float* shift, uint16_t* dy, float* dgamma, float* dbeta, float* dscale, float* dshift,
+                             int32_t B, int32_t P, int32_t C, void* stream);
+/* Backward of the channel LayerNorm (hicdiff_condition.py:99-108): z = (x - mean_c) * rsqrt(var_c + 1e-5) * g; x, dz, dx bf16
+ * [M,C] (dx must not alias x), dg fp32 [C].  Synchronises. */
+HD_API int hd_op_channel_layernorm_bwd(const uint16_t* x, const uint16_t* dz, const float* g, uint16_t* dx, float* dg, int64_t M,
+                                int32_t C, void* stream);
+/* Backward of WeightStandardizedConv2d's weight transform (:89-95): dw [Cout,K] from the gradient w.r.t. the standardised
+ * weight (dw may alias dwt); K = Cin * k * k. */
+HD_API int hd_op_weight_standardize_bwd(const float* w, const float* dwt, float* dw, int32_t Cout, int32_t K, void* stream);
 HD_API int hd_op_conv3x3_dgrad(const uint16_t* dy, const float* w, uint16_t* dx, int32_t B, void* stream);
 
 /* -------------------------------------------------------------------------------------------------------------

@@ -215,3 +215,64 @@ def test_general_conv_wgrad_concat_slices():
     dw = ops.conv_wgrad_nhwc(x0.to(DEV), dy.to(DEV), 3, cin_total=C0 + C1, ci0=0)
     dw = ops.conv_wgrad_nhwc(x1.to(DEV), dy.to(DEV), 3, dw=dw, cin_total=C0 + C1, ci0=C0)
     assert _rel(dw, gw) <= 4e-3, _rel(dw, gw)
+
+
+# ------------------------------------------------------------------------------------------------ Unet backward building blocks
+@pytest.mark.parametrize("B,H,C,film", [(2, 64, 64, True), (2, 32, 128, True), (3, 16, 256, False), (2, 8, 512, True), (1, 64, 64, False)])
+def test_groupnorm_film_silu_backward(B, H, C, film):
+    """Block's tail (hicdiff_condition.py:159-171) against torch.autograd in float64 on the same bf16-rounded inputs."""
+    from hicdiff_b200 import ops
+
+    g = torch.Generator().manual_seed(B + H + C)
+    y = (torch.randn(B, H, H, C, generator=g) * 1.5 + 0.3).to(torch.bfloat16)
+    ds = (torch.randn(B, H, H, C, generator=g) * 0.1).to(torch.bfloat16)
+    gamma = torch.randn(C, generator=g) * 0.5 + 1.0
+    beta = torch.randn(C, generator=g) * 0.2
+    scale = torch.randn(B, C, generator=g) * 0.3 if film else None
+    shift = torch.randn(B, C, generator=g) * 0.3 if film else None
+    leaves = [y.permute(0, 3, 1, 2).double().requires_grad_(True), gamma.double().requires_grad_(True), beta.double().requires_grad_(True)]
+    n = F.group_norm(leaves[0], 8, leaves[1], leaves[2], eps=1e-5)
+    if film:
+        leaves += [scale.double().requires_grad_(True), shift.double().requires_grad_(True)]
+        n = n * (leaves[3][:, :, None, None] + 1) + leaves[4][:, :, None, None]
+    s = F.silu(n)
+    grads = torch.autograd.grad(s, leaves, ds.permute(0, 3, 1, 2).double())
+    dy, dgamma, dbeta, dscale, dshift = ops.groupnorm_silu_bwd_nhwc(
+        y.to(DEV), ds.to(DEV), gamma.to(DEV), beta.to(DEV), scale.to(DEV) if film else None, shift.to(DEV) if film else None)
+    assert _rel(dy.permute(0, 3, 1, 2), grads[0]) <= 6e-3, _rel(dy.permute(0, 3, 1, 2), grads[0])     # bf16 output rounding
+    assert _rel(dgamma, grads[1]) <= 1e-4 and _rel(dbeta, grads[2]) <= 1e-4
+    if film:
+        assert _rel(dscale, grads[3]) <= 1e-4 and _rel(dshift, grads[4]) <= 1e-4
+
+
+@pytest.mark.parametrize("M,C", [(4096 * 2, 64), (1024 * 3, 128), (256 * 2, 256), (64 * 5, 512)])
+def test_channel_layernorm_backward(M, C):
+    from hicdiff_b200 import ops
+
+    g = torch.Generator().manual_seed(M + C)
+    x = (torch.randn(M, C, generator=g) * 2 + 0.5).to(torch.bfloat16)
+    dz = (torch.randn(M, C, generator=g) * 0.1).to(torch.bfloat16)
+    gain = torch.randn(C, generator=g) * 0.3 + 1.0
+    xr, gr = x.double().requires_grad_(True), gain.double().requires_grad_(True)
+    var = xr.var(dim=1, unbiased=False, keepdim=True)
+    z = (xr - xr.mean(dim=1, keepdim=True)) * (var + 1e-5).rsqrt() * gr          # LayerNorm.forward :104-108
+    gx, gg = torch.autograd.grad(z, [xr, gr], dz.double())
+    dx, dg = ops.channel_layernorm_bwd_nhwc(x.to(DEV), dz.to(DEV), gain.to(DEV))
+    assert _rel(dx, gx) <= 6e-3, _rel(dx, gx)
+    assert _rel(dg, gg) <= 1e-4, _rel(dg, gg)
+
+
+@pytest.mark.parametrize("Cout,Cin,k", [(64, 64, 3), (128, 192, 3), (512, 768, 3)])
+def test_weight_standardize_backward(Cout, Cin, k):
+    from hicdiff_b200 import ops
+
+    g = torch.Generator().manual_seed(Cout + Cin)
+    w = torch.randn(Cout, Cin, k, k, generator=g) * 0.05
+    dwt = torch.randn(Cout, Cin, k, k, generator=g)
+    wr = w.double().requires_grad_(True)
+    mean = wr.mean(dim=(1, 2, 3), keepdim=True)
+    var = wr.var(dim=(1, 2, 3), unbiased=False, keepdim=True)
+    wt = (wr - mean) * (var + 1e-5).rsqrt()                                     # WeightStandardizedConv2d.forward :89-95
+    (gw,) = torch.autograd.grad(wt, [wr], dwt.double())
+    dw = ops.weight_standardize_bwd(w.to(DEV), dwt.to(DEV))
+    assert _rel(dw, gw) <= 1e-4, _rel(dw, gw)
