@@ -60,6 +60,7 @@ SIGNATURES = {
     "hd_op_groupnorm_silu_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "hd_op_channel_layernorm_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "hd_op_weight_standardize_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "hd_op_attention_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "hd_op_conv3x3_dgrad": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "hd_coo_to_dense": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "hd_remove_empty_bins": (C.c_int, [_vp, _i64, _vp, _vp, C.POINTER(_i64), _vp]),

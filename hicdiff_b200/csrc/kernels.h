@@ -368,6 +368,11 @@ cudaError_t channel_layernorm_bwd_run(const bf16* x, const bf16* dz, const float
 // dw [Cout, K] from the gradient w.r.t. the standardised weight (dw may alias dwt)
 cudaError_t weight_standardize_bwd_run(const float* w, const float* dwt, int Cout, int K, float eps, float* dw, cudaStream_t s);
 
+// attention_bwd.cu -- backward of the linear-attention core and of the 8x8 softmax attention; qkv / dqkv [B, n, 384], dout [B, n, 128]
+size_t linattn_bwd_scratch_floats(int B);
+cudaError_t linear_attention_bwd_run(const bf16* qkv, const bf16* dout, bf16* dqkv, int B, int n, float* scratch, cudaStream_t s);
+cudaError_t full_attention_bwd_run(const bf16* qkv, const bf16* dout, bf16* dqkv, int B, int n, cudaStream_t s);
+
 // ---------------------------------------------------------------------------------------------
 // dataprep.cu -- contact triples -> dense matrix, empty-bin removal, exact percentile, normalisation, noise injection
 // ---------------------------------------------------------------------------------------------

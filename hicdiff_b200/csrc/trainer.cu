@@ -540,6 +540,25 @@ int hd_op_weight_standardize_bwd(const float* w, const float* dwt, float* dw, in
     return 0;
 }
 
+int hd_op_attention_bwd(const uint16_t* qkv, const uint16_t* dout, uint16_t* dqkv, int32_t B, int32_t n, int32_t linear, void* stream) {
+    if (!qkv || !dout || !dqkv || B < 1 || n < 1) return tfail("hd_op_attention_bwd: bad argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t ce;
+    if (linear) {
+        float* scratch = nullptr;
+        T_TRY(cudaMalloc(&scratch, linattn_bwd_scratch_floats(B) * sizeof(float)));
+        ce = linear_attention_bwd_run(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(dout), reinterpret_cast<bf16*>(dqkv), B, n, scratch, s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        cudaFree(scratch);
+    } else {
+        if (n != 64) return tfail("hd_op_attention_bwd: the softmax attention runs at 8x8 only (n = 64), got n = %d", n);
+        ce = full_attention_bwd_run(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(dout), reinterpret_cast<bf16*>(dqkv), B, n, s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    }
+    if (ce != cudaSuccess) return tfail("hd_op_attention_bwd failed: %s", cudaGetErrorString(ce));
+    return 0;
+}
+
 int hd_op_conv_wgrad(const uint16_t* x, const uint16_t* dy, float* dw, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
                      int32_t ksize, int32_t cin_total, int32_t ci0, void* stream) {
     if (!x || !dy || !dw || B < 1) return tfail("hd_op_conv_wgrad: bad argument");

@@ -273,3 +273,15 @@ def weight_standardize_bwd(w, dwt):
     _lib.check(lib.hd_op_weight_standardize_bwd(_lib.ptr(w), _lib.ptr(dwt), _lib.ptr(dw), w.shape[0], w[0].numel(), _lib.stream_ptr()),
                "hd_op_weight_standardize_bwd")
     return dw
+
+
+def attention_bwd(qkv, dout, linear=True):
+    """Backward of LinearAttention's core (linear=True) or of the 8x8 softmax attention: qkv [B,n,384], dout [B,n,128] bf16."""
+    lib = _lib.load()
+    _need_cuda(qkv, dout)
+    qkv, dout = _bf16c(qkv), _bf16c(dout)
+    B, n = qkv.shape[0], qkv.shape[1]
+    dqkv = torch.empty_like(qkv)
+    _lib.check(lib.hd_op_attention_bwd(_lib.ptr(qkv), _lib.ptr(dout), _lib.ptr(dqkv), B, n, 1 if linear else 0, _lib.stream_ptr()),
+               "hd_op_attention_bwd")
+    return dqkv

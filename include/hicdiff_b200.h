@@ -169,6 +169,10 @@ HD_API int hd_op_channel_layernorm_bwd(const uint16_t* x, const uint16_t* dz, co
 /* Backward of WeightStandardizedConv2d's weight transform (:89-95): dw [Cout,K] from the gradient w.r.t. the standardised
  * weight (dw may alias dwt); K = Cin * k * k. */
 HD_API int hd_op_weight_standardize_bwd(const float* w, const float* dwt, float* dw, int32_t Cout, int32_t K, void* stream);
+/* Backward of the attention cores given d_out [B,n,128]: linear = 1 LinearAttention (hicdiff_condition.py:212-227),
+ * linear = 0 Attention at 8x8 (:239-251, n = 64).  qkv / dqkv bf16 [B,n,384].  Synchronises. */
+HD_API int hd_op_attention_bwd(const uint16_t* qkv, const uint16_t* dout, uint16_t* dqkv, int32_t B, int32_t n, int32_t linear,
+                        void* stream);
 HD_API int hd_op_conv3x3_dgrad(const uint16_t* dy, const float* w, uint16_t* dx, int32_t B, void* stream);
 
 /* -------------------------------------------------------------------------------------------------------------

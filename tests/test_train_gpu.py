@@ -276,3 +276,36 @@ def test_weight_standardize_backward(Cout, Cin, k):
     (gw,) = torch.autograd.grad(wt, [wr], dwt.double())
     dw = ops.weight_standardize_bwd(w.to(DEV), dwt.to(DEV))
     assert _rel(dw, gw) <= 1e-4, _rel(dw, gw)
+
+
+def _attn_ref(qkv, linear):
+    """qkv [B, n, 384] float64 -> out [B, n, 128]: LinearAttention / Attention cores (hicdiff_condition.py:212-227, 239-251)."""
+    B, n, _ = qkv.shape
+    q, k, v = (t.reshape(B, n, 4, 32).permute(0, 2, 3, 1) for t in qkv.chunk(3, dim=2))      # 'b h d n'
+    scale = 32 ** -0.5
+    if linear:
+        q = q.softmax(dim=-2) * scale
+        k = k.softmax(dim=-1)
+        v = v / n
+        ctx = torch.einsum("bhdn,bhen->bhde", k, v)
+        out = torch.einsum("bhde,bhdn->bhen", ctx, q)                                      # 'b h e n'
+        return out.permute(0, 3, 1, 2).reshape(B, n, 128)
+    sim = torch.einsum("bhdi,bhdj->bhij", q * scale, k)
+    attn = sim.softmax(dim=-1)
+    out = torch.einsum("bhij,bhdj->bhid", attn, v)                                          # 'b h i d'
+    return out.permute(0, 2, 1, 3).reshape(B, n, 128)
+
+
+@pytest.mark.parametrize("B,n,linear", [(2, 4096, True), (3, 1024, True), (2, 256, True), (5, 64, True), (3, 64, False)])
+def test_attention_core_backward(B, n, linear):
+    from hicdiff_b200 import ops
+
+    g = torch.Generator().manual_seed(B * 7 + n)
+    qkv = (torch.randn(B, n, 384, generator=g) * 1.2).to(torch.bfloat16)
+    dout = (torch.randn(B, n, 128, generator=g) * 0.1).to(torch.bfloat16)
+    x = qkv.double().requires_grad_(True)
+    (gq,) = torch.autograd.grad(_attn_ref(x, linear), [x], dout.double())
+    dqkv = ops.attention_bwd(qkv.to(DEV), dout.to(DEV), linear=linear)
+    for name, sl in (("dq", slice(0, 128)), ("dk", slice(128, 256)), ("dv", slice(256, 384))):
+        r = _rel(dqkv[:, :, sl], gq[:, :, sl])
+        assert r <= 6e-3, (name, r)
