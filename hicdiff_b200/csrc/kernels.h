@@ -354,6 +354,7 @@ struct GroupNormBwdArgs {
     float eps;
     const float* scale = nullptr;   // [B, C] FiLM scale (nullptr: no FiLM, e.g. block2)
     const float* shift = nullptr;   // [B, C]
+    int ld = 0;                     // row stride of scale / shift / dscale / dshift (0: C)
     float* dgamma;        // [C]
     float* dbeta;         // [C]
     float* dscale = nullptr;        // [B, C] (optional)
@@ -372,6 +373,18 @@ cudaError_t weight_standardize_bwd_run(const float* w, const float* dwt, int Cou
 size_t linattn_bwd_scratch_floats(int B);
 cudaError_t linear_attention_bwd_run(const bf16* qkv, const bf16* dout, bf16* dqkv, int B, int n, float* scratch, cudaStream_t s);
 cudaError_t full_attention_bwd_run(const bf16* qkv, const bf16* dout, bf16* dqkv, int B, int n, cudaStream_t s);
+
+// unet_train_kernels.cu -- resampling copies, thin convs at the ends of the Unet, standardised dgrad weights
+cudaError_t unshuffle_run(const bf16* in, bf16* out, int B, int H, int W, int C, int inverse, cudaStream_t s);   // H, W: LOW-res size
+cudaError_t upsample2x_run(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t s);               // in [B,H,W,C]
+cudaError_t sumpool2x_run(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t s);                // out [B,H,W,C]
+cudaError_t stem_wgrad_run(const bf16* G, const float* u0, const float* u1, int B, int C, int ksize, float* part, float* dw, cudaStream_t s);
+int head_bwd_parts(long long M);
+cudaError_t head_bwd_run(const bf16* x, const float* d_eps, const float* w, long long M, int C, bf16* dx, float* part, float* dw,
+                         cudaStream_t s);
+cudaError_t ws_stats_run(const float* w, int Cout, int K, float eps, float2* stats, cudaStream_t s);
+// [Cout, Cin, k, k] fp32 -> [Cin, (tap', cout)] bf16, tap' = k*k - 1 - tap; stats != nullptr: standardised with (mean, rstd)[Cout]
+cudaError_t prep_dgrad_weight_general_run(const float* w, const float2* stats, bf16* out, int Cout, int Cin, int ksize, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------
 // dataprep.cu -- contact triples -> dense matrix, empty-bin removal, exact percentile, normalisation, noise injection

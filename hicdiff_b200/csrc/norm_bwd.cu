@@ -83,7 +83,7 @@ constexpr int GB_CHUNKS_MAX = 16;
 __global__ void __launch_bounds__(256)
 gn_bwd_sums_kernel(const uint4* __restrict__ y, const uint4* __restrict__ ds, const float2* __restrict__ stats,
                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ scale,
-                   const float* __restrict__ shift, int P, int C, int nchunk, float* __restrict__ part) {
+                   const float* __restrict__ shift, int ld, int P, int C, int nchunk, float* __restrict__ part) {
     extern __shared__ float gs_red[];   // [lanes][2 * C]
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int cpp = C / 8, lanes = 256 / cpp;
@@ -95,8 +95,8 @@ gn_bwd_sums_kernel(const uint4* __restrict__ y, const uint4* __restrict__ ds, co
     for (int j = 0; j < 8; ++j) {
         const int c = cc * 8 + j;
         ga[j] = gamma[c]; be[j] = beta[c];
-        sc1[j] = scale ? scale[static_cast<size_t>(b) * C + c] + 1.0f : 1.0f;
-        sh[j] = shift ? shift[static_cast<size_t>(b) * C + c] : 0.0f;
+        sc1[j] = scale ? scale[static_cast<size_t>(b) * ld + c] + 1.0f : 1.0f;
+        sh[j] = shift ? shift[static_cast<size_t>(b) * ld + c] : 0.0f;
         U[j] = 0.f; V[j] = 0.f;
     }
     const size_t base = (static_cast<size_t>(b) * P + static_cast<size_t>(chunk) * ppc) * cpp + cc;
@@ -127,7 +127,7 @@ gn_bwd_sums_kernel(const uint4* __restrict__ y, const uint4* __restrict__ ds, co
 // grid B, 2 * 256 threads max -> one thread per channel (C <= 512): UV[b][2][C], group means m[b][G][2], d scale / d shift
 __global__ void __launch_bounds__(512)
 gn_bwd_coef_kernel(const float* __restrict__ part, int nchunk, const float* __restrict__ gamma, const float* __restrict__ beta,
-                   const float* __restrict__ scale, int P, int C, float* __restrict__ UV, float* __restrict__ gm,
+                   const float* __restrict__ scale, int ld, int P, int C, float* __restrict__ UV, float* __restrict__ gm,
                    float* __restrict__ dscale, float* __restrict__ dshift) {
     __shared__ float s_a[512], s_b[512];
     const int b = blockIdx.x, c = threadIdx.x;
@@ -139,9 +139,9 @@ gn_bwd_coef_kernel(const float* __restrict__ part, int nchunk, const float* __re
         }
         UV[(static_cast<size_t>(b) * 2) * C + c] = U;
         UV[(static_cast<size_t>(b) * 2 + 1) * C + c] = V;
-        if (dshift) dshift[static_cast<size_t>(b) * C + c] = U;
-        if (dscale) dscale[static_cast<size_t>(b) * C + c] = fmaf(gamma[c], V, beta[c] * U);
-        const float k1 = (scale ? scale[static_cast<size_t>(b) * C + c] + 1.0f : 1.0f) * gamma[c];
+        if (dshift) dshift[static_cast<size_t>(b) * ld + c] = U;
+        if (dscale) dscale[static_cast<size_t>(b) * ld + c] = fmaf(gamma[c], V, beta[c] * U);
+        const float k1 = (scale ? scale[static_cast<size_t>(b) * ld + c] + 1.0f : 1.0f) * gamma[c];
         s_a[c] = k1 * U;
         s_b[c] = k1 * V;
     }
@@ -157,13 +157,13 @@ gn_bwd_coef_kernel(const float* __restrict__ part, int nchunk, const float* __re
 }
 
 // d gamma[c] = sum_b (scale + 1) V, d beta[c] = sum_b (scale + 1) U  (accumulate: += for a layer used more than once)
-__global__ void gn_bwd_affine_kernel(const float* __restrict__ UV, const float* __restrict__ scale, int B, int C,
+__global__ void gn_bwd_affine_kernel(const float* __restrict__ UV, const float* __restrict__ scale, int ld, int B, int C,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float dg = 0.f, db = 0.f;
     for (int b = 0; b < B; ++b) {
-        const float s1 = scale ? scale[static_cast<size_t>(b) * C + c] + 1.0f : 1.0f;
+        const float s1 = scale ? scale[static_cast<size_t>(b) * ld + c] + 1.0f : 1.0f;
         db = fmaf(s1, UV[(static_cast<size_t>(b) * 2) * C + c], db);
         dg = fmaf(s1, UV[(static_cast<size_t>(b) * 2 + 1) * C + c], dg);
     }
@@ -175,7 +175,7 @@ __global__ void gn_bwd_affine_kernel(const float* __restrict__ UV, const float* 
 __global__ void __launch_bounds__(256)
 gn_bwd_dx_kernel(const uint4* __restrict__ y, const uint4* ds, const float2* __restrict__ stats, const float* __restrict__ gm,
                  const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ scale,
-                 const float* __restrict__ shift, int P, int C, int nchunk, uint4* dy) {
+                 const float* __restrict__ shift, int ld, int P, int C, int nchunk, uint4* dy) {
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int cpp = C / 8, lanes = 256 / cpp;
     const int cc = threadIdx.x % cpp, pl = threadIdx.x / cpp;
@@ -188,8 +188,8 @@ gn_bwd_dx_kernel(const uint4* __restrict__ y, const uint4* ds, const float2* __r
     for (int j = 0; j < 8; ++j) {
         const int c = cc * 8 + j;
         ga[j] = gamma[c]; be[j] = beta[c];
-        sc1[j] = scale ? scale[static_cast<size_t>(b) * C + c] + 1.0f : 1.0f;
-        sh[j] = shift ? shift[static_cast<size_t>(b) * C + c] : 0.0f;
+        sc1[j] = scale ? scale[static_cast<size_t>(b) * ld + c] + 1.0f : 1.0f;
+        sh[j] = shift ? shift[static_cast<size_t>(b) * ld + c] : 0.0f;
     }
     const size_t base = (static_cast<size_t>(b) * P + static_cast<size_t>(chunk) * ppc) * cpp + cc;
     for (int p = pl; p < ppc; p += lanes) {
@@ -322,6 +322,7 @@ cudaError_t groupnorm_silu_bwd_run(const GroupNormBwdArgs& a, float* scratch, cu
     if (C % 64 != 0 || C > 512 || 256 % (C / 8) != 0) return cudaErrorInvalidValue;
     const int nchunk = gn_chunks(P, C);
     const int lanes = 256 / (C / 8);
+    const int ld = a.ld > 0 ? a.ld : C;
     float2* stats = reinterpret_cast<float2*>(scratch);
     float* part = scratch + static_cast<size_t>(B) * G * 2;
     float* UV = part + static_cast<size_t>(B) * nchunk * 2 * C;
@@ -330,10 +331,10 @@ cudaError_t groupnorm_silu_bwd_run(const GroupNormBwdArgs& a, float* scratch, cu
     const uint4* ds = reinterpret_cast<const uint4*>(a.ds);
     gn_stats_kernel<<<dim3(G, B), 256, 0, s>>>(y, P, C, a.eps, stats);
     gn_bwd_sums_kernel<<<dim3(nchunk, B), 256, static_cast<size_t>(lanes) * 2 * C * sizeof(float), s>>>(
-        y, ds, stats, a.gamma, a.beta, a.scale, a.shift, P, C, nchunk, part);
-    gn_bwd_coef_kernel<<<B, 512, 0, s>>>(part, nchunk, a.gamma, a.beta, a.scale, P, C, UV, gm, a.dscale, a.dshift);
-    gn_bwd_affine_kernel<<<(C + 255) / 256, 256, 0, s>>>(UV, a.scale, B, C, a.dgamma, a.dbeta);
-    gn_bwd_dx_kernel<<<dim3(nchunk, B), 256, 0, s>>>(y, ds, stats, gm, a.gamma, a.beta, a.scale, a.shift, P, C, nchunk,
+        y, ds, stats, a.gamma, a.beta, a.scale, a.shift, ld, P, C, nchunk, part);
+    gn_bwd_coef_kernel<<<B, 512, 0, s>>>(part, nchunk, a.gamma, a.beta, a.scale, ld, P, C, UV, gm, a.dscale, a.dshift);
+    gn_bwd_affine_kernel<<<(C + 255) / 256, 256, 0, s>>>(UV, a.scale, ld, B, C, a.dgamma, a.dbeta);
+    gn_bwd_dx_kernel<<<dim3(nchunk, B), 256, 0, s>>>(y, ds, stats, gm, a.gamma, a.beta, a.scale, a.shift, ld, P, C, nchunk,
                                                       reinterpret_cast<uint4*>(a.dy));
     return cudaGetLastError();
 }

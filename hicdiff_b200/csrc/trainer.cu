@@ -8,53 +8,19 @@
 // Parameters are bound by pointer (the caller's fp32 tensors are read in place every step, so a stock torch optimizer
 // keeps working) and gradients are written into caller-provided fp32 buffers.  Activations are bf16 NHWC; the convs run on
 // tcgen05 (conv_gemm.cu forward and data gradient, wgrad.cu weight gradient); statistics-free glue is in train_kernels.cu.
-#include <cstdarg>
-#include <cstdio>
 #include <cstring>
-#include <functional>
-#include <map>
-#include <string>
-#include <vector>
 
-#include "../../include/hicdiff_b200.h"
-#include "kernels.h"
+#include "trainer_internal.h"
 
 using namespace hd;
 
-namespace hd {
-int set_error(const char* msg);   // plan.cu: fills the thread-local message behind hd_last_error()
-}
-
 namespace {
-
-int tfail(const char* fmt, ...) {
-    char buf[1024];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof(buf), fmt, ap);
-    va_end(ap);
-    return hd::set_error(buf);
-}
 
 #define T_TRY(expr)                                                                              \
     do {                                                                                         \
         cudaError_t e__ = (expr);                                                                \
         if (e__ != cudaSuccess) return tfail("%s failed: %s", #expr, cudaGetErrorString(e__));   \
     } while (0)
-
-struct TParam {
-    const float* w = nullptr;
-    float* g = nullptr;
-    std::vector<int64_t> shape;
-    size_t numel = 0;
-};
-
-struct TOp {
-    std::function<cudaError_t(cudaStream_t)> fn;
-    std::string tag;
-    const char* kernel = "";
-    double flops = 0;
-};
 
 constexpr int F = 256;          // n_feat
 constexpr int S = 64;           // tile edge
@@ -64,40 +30,7 @@ constexpr int WG_SPLITS = 16;   // 9 taps x 16 K splits = 144 CTAs
 
 }  // namespace
 
-struct hd_trainer {
-    hd_config cfg;
-    int device = 0, num_sms = 148, B = 0, nb = 0;
-    bool finalized = false;
-    std::map<std::string, TParam> p;
-    std::vector<void*> allocs;
-    size_t bytes = 0;
-    std::vector<TOp> ops;
-    float *x = nullptr, *cond = nullptr, *time = nullptr, *target = nullptr, *weight = nullptr, *eps = nullptr, *d_eps = nullptr,
-          *loss = nullptr;
-    int* loss_type = nullptr;
-    int loss_kind = 1;
-};
-
 namespace {
-
-template <typename T>
-int dalloc(hd_trainer* t, T** out, size_t bytes, bool zero = false) {
-    void* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, bytes ? bytes : 16);
-    if (e != cudaSuccess) return tfail("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
-    if (zero) cudaMemset(q, 0, bytes ? bytes : 16);
-    t->allocs.push_back(q);
-    t->bytes += bytes;
-    *out = static_cast<T*>(q);
-    return 0;
-}
-
-const TParam* find_p(const hd_trainer* t, const std::string& k, std::initializer_list<int64_t> shape) {
-    auto it = t->p.find(k);
-    if (it == t->p.end()) { tfail("parameter '%s' was not bound", k.c_str()); return nullptr; }
-    if (it->second.shape != std::vector<int64_t>(shape)) { tfail("parameter '%s' has an unexpected shape", k.c_str()); return nullptr; }
-    return &it->second;
-}
 
 struct TB {   // builder state
     hd_trainer* t;
@@ -364,11 +297,18 @@ extern "C" {
 int hd_trainer_create(const hd_config* cfg, int32_t batch, hd_trainer** out) {
     if (!cfg || !out) return tfail("hd_trainer_create: null argument");
     if (cfg->abi_version != HD_ABI_VERSION) return tfail("ABI version mismatch: header %d, library %d", cfg->abi_version, HD_ABI_VERSION);
-    if (cfg->variant != HD_HICEDRN && cfg->variant != HD_HICEDRN_SR3)
-        return tfail("hd_trainer is built for the hicedrn_Diff eps-nets (variants %d, %d), the models train.py / pretrain/train_hicedrn_*.py train; variant %d has no backward yet",
-                     HD_HICEDRN, HD_HICEDRN_SR3, cfg->variant);
+    if (cfg->variant != HD_HICEDRN && cfg->variant != HD_HICEDRN_SR3 && cfg->variant != HD_UNET)
+        return tfail("hd_trainer covers hicedrn_Diff, hicedrn_sr3_Diff and the (non-SR3) Unet; variant %d has no backward yet", cfg->variant);
     if (cfg->image_size != 64) return tfail("image_size must be 64");
-    if (cfg->num_blocks < 1) return tfail("HiCEDRN needs num_blocks >= 1");
+    if (cfg->variant == HD_UNET) {
+        if (cfg->dim != 64) return tfail("the Unet training step is built for dim = 64 (got %d)", cfg->dim);
+        if (cfg->num_mults < 1 || cfg->num_mults > 4) return tfail("len(dim_mults) must be 1..4 for 64x64 tiles (got %d)", cfg->num_mults);
+        for (int i = 0; i < cfg->num_mults; ++i)
+            if (cfg->dim_mults[i] != 1 && cfg->dim_mults[i] != 2 && cfg->dim_mults[i] != 4 && cfg->dim_mults[i] != 8)
+                return tfail("dim_mults[%d] = %d: the training kernels cover 64 / 128 / 256 / 512 channels", i, cfg->dim_mults[i]);
+    } else if (cfg->num_blocks < 1) {
+        return tfail("HiCEDRN needs num_blocks >= 1");
+    }
     if (batch < 1) return tfail("batch must be positive (got %d)", batch);
     int dev = 0, cc_major = 0, sms = 0;
     T_TRY(cudaGetDevice(&dev));
@@ -399,7 +339,7 @@ int hd_trainer_finalize(hd_trainer* t, void* stream) {
     if (!t) return tfail("hd_trainer_finalize: null trainer");
     if (t->finalized) return 0;
     T_TRY(cudaSetDevice(t->device));
-    if (build(t)) return 1;
+    if (t->cfg.variant == HD_UNET ? build_unet_trainer(t) : build(t)) return 1;
     T_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     t->finalized = true;
     return 0;

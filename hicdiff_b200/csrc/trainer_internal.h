@@ -1,0 +1,76 @@
+// Shared between trainer.cu (hd_trainer C ABI + the hicedrn_Diff step) and unet_trainer.cu (the Unet step).
+#pragma once
+#include <cstdarg>
+#include <cstdio>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/hicdiff_b200.h"
+#include "kernels.h"
+
+namespace hd {
+int set_error(const char* msg);   // plan.cu: fills the thread-local message behind hd_last_error()
+
+inline int tfail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    return set_error(buf);
+}
+
+struct TParam {
+    const float* w = nullptr;
+    float* g = nullptr;
+    std::vector<int64_t> shape;
+    size_t numel = 0;
+};
+
+struct TOp {
+    std::function<cudaError_t(cudaStream_t)> fn;
+    std::string tag;
+    const char* kernel = "";
+    double flops = 0;
+};
+}  // namespace hd
+
+struct hd_trainer {
+    hd_config cfg;
+    int device = 0, num_sms = 148, B = 0, nb = 0;
+    bool finalized = false;
+    std::map<std::string, hd::TParam> p;
+    std::vector<void*> allocs;
+    size_t bytes = 0;
+    std::vector<hd::TOp> ops;
+    float *x = nullptr, *cond = nullptr, *time = nullptr, *target = nullptr, *weight = nullptr, *eps = nullptr, *d_eps = nullptr,
+          *loss = nullptr;
+    int loss_kind = 1;
+};
+
+namespace hd {
+
+template <typename T>
+int dalloc(hd_trainer* t, T** out, size_t bytes, bool zero = false) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes ? bytes : 16);
+    if (e != cudaSuccess) return tfail("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    if (zero) cudaMemset(q, 0, bytes ? bytes : 16);
+    t->allocs.push_back(q);
+    t->bytes += bytes;
+    *out = static_cast<T*>(q);
+    return 0;
+}
+
+inline const TParam* find_p(const hd_trainer* t, const std::string& k, std::initializer_list<int64_t> shape) {
+    auto it = t->p.find(k);
+    if (it == t->p.end()) { tfail("parameter '%s' was not bound", k.c_str()); return nullptr; }
+    if (it->second.shape != std::vector<int64_t>(shape)) { tfail("parameter '%s' has an unexpected shape", k.c_str()); return nullptr; }
+    return &it->second;
+}
+
+int build_unet_trainer(hd_trainer* t);   // unet_trainer.cu
+
+}  // namespace hd

@@ -1,0 +1,226 @@
+// Glue kernels of the Unet training step: the resampling layers as explicit copies, the thin convs at the
+// two ends of the net, and the data-gradient weight layout with the weight standardisation applied.
+//
+//   Downsample  'b c (h p1) (w p2) -> b (c p1 p2) h w' + 1x1 conv     /root/reference/src/hicdiff_condition.py:78-82
+//   Upsample    nearest x2 + 3x3 conv                                 :72-76
+//   init_conv   7x7, Cin = 1 or 2 -> dim                              :278-279
+//   final_conv  1x1, dim -> 1                                         :343
+// (The sampling path folds both resampling layers into the conv's TMA addressing; training materialises the rearranged
+// tensor once so that the conv, its dgrad and its wgrad are the plain kernels.)
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace hd {
+namespace {
+
+// out[b, h, w, c * 4 + p1 * 2 + p2] = in[b, 2h + p1, 2w + p2, c]   (inverse == 1: the scatter back, out is [B, 2H, 2W, C])
+__global__ void __launch_bounds__(256)
+unshuffle_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C, int inverse) {
+    const long long total = static_cast<long long>(B) * H * W * 4 * C;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+        const int c4 = static_cast<int>(i % (4 * C));
+        const long long pix = i / (4 * C);
+        const int w = static_cast<int>(pix % W), h = static_cast<int>((pix / W) % H), b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+        const int c = c4 >> 2, p1 = (c4 >> 1) & 1, p2 = c4 & 1;
+        const long long hi = ((static_cast<long long>(b) * 2 * H + 2 * h + p1) * 2 * W + 2 * w + p2) * C + c;
+        if (inverse) out[hi] = in[i]; else out[i] = in[hi];
+    }
+}
+
+// nearest x2: out[b, y, x, :] = in[b, y / 2, x / 2, :]   (16-byte chunks)
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int cpp) {
+    const long long total = static_cast<long long>(B) * 2 * H * 2 * W * cpp;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+        const int cc = static_cast<int>(i % cpp);
+        const long long pix = i / cpp;
+        const int x = static_cast<int>(pix % (2 * W)), y = static_cast<int>((pix / (2 * W)) % (2 * H));
+        const long long b = pix / (static_cast<long long>(4) * W * H);
+        out[i] = __ldg(in + ((b * H + y / 2) * W + x / 2) * cpp + cc);
+    }
+}
+// its backward: out[b, h, w, :] = sum of the 2x2 block of in [B, 2H, 2W, C]
+__global__ void __launch_bounds__(256)
+sumpool2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int cpp) {
+    const long long total = static_cast<long long>(B) * H * W * cpp;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+        const int cc = static_cast<int>(i % cpp);
+        const long long pix = i / cpp;
+        const int w = static_cast<int>(pix % W), h = static_cast<int>((pix / W) % H);
+        const long long b = pix / (static_cast<long long>(W) * H);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint4 u = __ldg(in + ((b * 2 * H + 2 * h + (q >> 1)) * 2 * W + 2 * w + (q & 1)) * cpp + cc);
+            float2 t;
+            t = ptx::unpack_bf16x2(u.x); acc[0] += t.x; acc[1] += t.y;
+            t = ptx::unpack_bf16x2(u.y); acc[2] += t.x; acc[3] += t.y;
+            t = ptx::unpack_bf16x2(u.z); acc[4] += t.x; acc[5] += t.y;
+            t = ptx::unpack_bf16x2(u.w); acc[6] += t.x; acc[7] += t.y;
+        }
+        uint4 o;
+        o.x = ptx::pack_bf16x2(acc[0], acc[1]); o.y = ptx::pack_bf16x2(acc[2], acc[3]);
+        o.z = ptx::pack_bf16x2(acc[4], acc[5]); o.w = ptx::pack_bf16x2(acc[6], acc[7]);
+        out[i] = o;
+    }
+}
+
+// ---- init_conv weight gradient: part[(b * 8 + rg)][k][tap][c] over 8 image rows; G [B, 64, 64, C] bf16, u_k fp32 planes, k x k taps.
+// grid (8, B, ksize): blockIdx.z = filter row ky; threads = channels (C <= 256)
+__global__ void __launch_bounds__(256)
+stem_wgrad_kernel(const bf16* __restrict__ G, const float* __restrict__ u0, const float* __restrict__ u1, int C, int ksize,
+                  float* __restrict__ part) {
+    constexpr int W = 64, H = 64, ROWS = 8;
+    extern __shared__ float sw_u[];                      // [nk][ROWS][W + ksize - 1] rows y0 + ky - pad .. (only the ky of this block)
+    const int pad = ksize / 2, pitch = W + ksize - 1;
+    const int rg = blockIdx.x, b = blockIdx.y, ky = blockIdx.z, c = threadIdx.x;
+    const int nk = u1 != nullptr ? 2 : 1;
+    const int y0 = rg * ROWS;
+    for (int i = threadIdx.x; i < nk * ROWS * pitch; i += 256) {
+        const int k = i / (ROWS * pitch), rem = i - k * ROWS * pitch;
+        const int yy = y0 + rem / pitch + ky - pad, xx = rem % pitch - pad;
+        const float* u = k == 0 ? u0 : u1;
+        sw_u[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(u + (static_cast<size_t>(b) * H + yy) * W + xx) : 0.f;
+    }
+    __syncthreads();
+    if (c >= C) return;
+    float acc[2][7];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int t = 0; t < 7; ++t) acc[k][t] = 0.f;
+    const bf16* g = G + ((static_cast<size_t>(b) * H + y0) * W) * C + c;
+    for (int yl = 0; yl < ROWS; ++yl)
+        for (int x = 0; x < W; ++x) {
+            const float gv = __bfloat162float(g[(static_cast<size_t>(yl) * W + x) * C]);
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                if (k < nk)
+#pragma unroll
+                    for (int t = 0; t < 7; ++t)
+                        if (t < ksize) acc[k][t] = fmaf(gv, sw_u[(k * ROWS + yl) * pitch + x + t], acc[k][t]);
+        }
+    float* o = part + ((static_cast<size_t>(b) * 8 + rg) * nk * ksize * ksize) * C;
+    for (int k = 0; k < nk; ++k)
+        for (int t = 0; t < ksize; ++t) o[((k * ksize + ky) * ksize + t) * C + c] = acc[k][t];
+}
+// dw[(c * nk + k) * taps + tap] = sum_parts part[.][k][tap][c]
+__global__ void stem_wgrad_finish_kernel(const float* __restrict__ part, int nparts, int nk, int taps, int C, float* __restrict__ dw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nk * taps * C) return;
+    float t = 0.f;
+    for (int p = 0; p < nparts; ++p) t += part[static_cast<size_t>(p) * nk * taps * C + i];
+    const int c = i % C, kt = i / C, k = kt / taps, tap = kt - k * taps;
+    dw[(c * nk + k) * taps + tap] = t;
+}
+
+// ---- final_conv (C -> 1) backward: dx[m, c] = d_eps[m] * w[c];  dw partials part[blk][c] = sum_m d_eps[m] x[m, c]
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ d_eps, const float* __restrict__ w, long long M, int C,
+                bf16* __restrict__ dx, float* __restrict__ part, int rpb) {
+    extern __shared__ float hb_red[];    // [lanes][C]
+    const int lanes = 256 / C;           // C = 64 -> 4 row lanes
+    const int c = threadIdx.x % C, pl = threadIdx.x / C;
+    const float wc = w[c];
+    const long long r0 = static_cast<long long>(blockIdx.x) * rpb, r1 = r0 + rpb < M ? r0 + rpb : M;
+    float acc = 0.f;
+    for (long long m = r0 + pl; m < r1; m += lanes) {
+        const float g = d_eps[m];
+        acc = fmaf(g, __bfloat162float(x[m * C + c]), acc);
+        dx[m * C + c] = __float2bfloat16(g * wc);
+    }
+    hb_red[pl * C + c] = acc;
+    __syncthreads();
+    if (pl == 0) {
+        float t = 0.f;
+        for (int k = 0; k < lanes; ++k) t += hb_red[k * C + c];
+        part[static_cast<size_t>(blockIdx.x) * C + c] = t;
+    }
+}
+
+// ---- per-output-channel (mean, rstd) of a conv weight, then the dgrad layout of the standardised weight
+__global__ void __launch_bounds__(256)
+ws_stats_kernel(const float* __restrict__ w, int K, float eps, float2* __restrict__ stats) {
+    __shared__ float s_red[8];
+    const float* wr = w + static_cast<size_t>(blockIdx.x) * K;
+    auto bsum = [&](float v) {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        float t = 0.f;
+        for (int k = 0; k < 8; ++k) t += s_red[k];
+        return t;
+    };
+    float s = 0.f;
+    for (int i = threadIdx.x; i < K; i += 256) s += wr[i];
+    const float mean = bsum(s) / K;
+    float v = 0.f;
+    for (int i = threadIdx.x; i < K; i += 256) { const float d = wr[i] - mean; v = fmaf(d, d, v); }
+    const float rstd = rsqrtf(bsum(v) / K + eps);
+    if (threadIdx.x == 0) stats[blockIdx.x] = make_float2(mean, rstd);
+}
+// out[ci][(tap', co)] = wt[co][ci][taps - 1 - tap'], wt = (w - mean_co) * rstd_co when stats != nullptr; grid Cin
+__global__ void __launch_bounds__(256)
+prep_dgrad_weight_general_kernel(const float* __restrict__ w, const float2* __restrict__ stats, bf16* __restrict__ out, int Cout, int Cin,
+                                 int taps) {
+    const int ci = blockIdx.x;
+    bf16* orow = out + static_cast<size_t>(ci) * taps * Cout;
+    for (int i = threadIdx.x; i < taps * Cout; i += blockDim.x) {
+        const int tapp = i / Cout, co = i - tapp * Cout;
+        float v = w[(static_cast<size_t>(co) * Cin + ci) * taps + (taps - 1 - tapp)];
+        if (stats != nullptr) { const float2 st = stats[co]; v = (v - st.x) * st.y; }
+        orow[i] = __float2bfloat16(v);
+    }
+}
+
+inline int grid_for(long long n) { return static_cast<int>(n / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16); }
+
+}  // namespace
+
+cudaError_t unshuffle_run(const bf16* in, bf16* out, int B, int H, int W, int C, int inverse, cudaStream_t s) {
+    unshuffle_kernel<<<grid_for(static_cast<long long>(B) * H * W * 4 * C), 256, 0, s>>>(in, out, B, H, W, C, inverse);
+    return cudaGetLastError();
+}
+cudaError_t upsample2x_run(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t s) {
+    upsample2x_kernel<<<grid_for(static_cast<long long>(B) * 4 * H * W * (C / 8)), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), B, H, W, C / 8);
+    return cudaGetLastError();
+}
+cudaError_t sumpool2x_run(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t s) {
+    sumpool2x_kernel<<<grid_for(static_cast<long long>(B) * H * W * (C / 8)), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), B, H, W, C / 8);
+    return cudaGetLastError();
+}
+// G [B, 64, 64, C] (C <= 256); part: B * 8 * nk * k * k * C floats; dw in the reference layout [C, nk, k, k]
+cudaError_t stem_wgrad_run(const bf16* G, const float* u0, const float* u1, int B, int C, int ksize, float* part, float* dw, cudaStream_t s) {
+    if (C > 256 || ksize > 7 || (ksize & 1) == 0) return cudaErrorInvalidValue;
+    const int nk = u1 != nullptr ? 2 : 1;
+    const size_t smem = static_cast<size_t>(nk) * 8 * (64 + ksize - 1) * sizeof(float);
+    stem_wgrad_kernel<<<dim3(8, B, ksize), 256, smem, s>>>(G, u0, u1, C, ksize, part);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int n = nk * ksize * ksize * C;
+    stem_wgrad_finish_kernel<<<(n + 255) / 256, 256, 0, s>>>(part, B * 8, nk, ksize * ksize, C, dw);
+    return cudaGetLastError();
+}
+int head_bwd_parts(long long M) { return static_cast<int>(M / 64 < 592 ? (M + 63) / 64 : 592); }
+// x [M, C] (256 % C == 0), dx [M, C], dw [C] (via part: head_bwd_parts(M) * C floats)
+cudaError_t head_bwd_run(const bf16* x, const float* d_eps, const float* w, long long M, int C, bf16* dx, float* part, float* dw,
+                         cudaStream_t s) {
+    if (C > 256 || 256 % C != 0) return cudaErrorInvalidValue;
+    const int nparts = head_bwd_parts(M);
+    const int rpb = static_cast<int>((M + nparts - 1) / nparts);
+    head_bwd_kernel<<<nparts, 256, 256 * sizeof(float), s>>>(x, d_eps, w, M, C, dx, part, rpb);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return sum_parts_run(part, nparts, C, 1.0f, 0, dw, s);
+}
+cudaError_t ws_stats_run(const float* w, int Cout, int K, float eps, float2* stats, cudaStream_t s) {
+    ws_stats_kernel<<<Cout, 256, 0, s>>>(w, K, eps, stats);
+    return cudaGetLastError();
+}
+cudaError_t prep_dgrad_weight_general_run(const float* w, const float2* stats, bf16* out, int Cout, int Cin, int ksize, cudaStream_t s) {
+    prep_dgrad_weight_general_kernel<<<Cin, 256, 0, s>>>(w, stats, out, Cout, Cin, ksize * ksize);
+    return cudaGetLastError();
+}
+
+}  // namespace hd

@@ -17,16 +17,19 @@ import torch
 from . import _lib
 
 
+_TRAINABLE = (_lib.HD_HICEDRN, _lib.HD_HICEDRN_SR3, _lib.HD_UNET)
+
+
 class Trainer:
     """One `hd_trainer` for a parameter-holder net (nets.hicedrn_Diff) at a fixed batch size."""
 
     def __init__(self, net: torch.nn.Module, batch: int):
         lib = _lib.load()
         cfgd = net._plan_config()
-        if cfgd["variant"] not in (_lib.HD_HICEDRN, _lib.HD_HICEDRN_SR3):
+        if cfgd["variant"] not in _TRAINABLE:
             raise NotImplementedError(
-                "hicdiff_b200: the training backward is built for the hicedrn_Diff eps-nets (train.py, "
-                "pretrain/train_hicedrn_*.py); the Unet backward is SURVEY.md 8(f) N2, not built yet")
+                "hicdiff_b200: the training backward covers hicedrn_Diff, hicedrn_sr3_Diff and the Unet of "
+                "hicdiff.py / hicdiff_condition.py; the SR3 Unet backward is not built yet")
         params = dict(net.named_parameters())
         dev = next(iter(params.values())).device
         if dev.type != "cuda":
@@ -52,6 +55,10 @@ class Trainer:
         cfg.image_size = 64
         cfg.timesteps = 1
         cfg.num_blocks = cfgd["num_blocks"]
+        cfg.dim = cfgd["dim"]
+        cfg.num_mults = len(cfgd["dim_mults"])
+        for i, m in enumerate(cfgd["dim_mults"]):
+            cfg.dim_mults[i] = int(m)
         h = C.c_void_p()
         with torch.cuda.device(dev):
             _lib.check(lib.hd_trainer_create(C.byref(cfg), self.batch, C.byref(h)), "hd_trainer_create")
@@ -158,7 +165,7 @@ class _TrainStep(torch.autograd.Function):
 
 def supports_training(net) -> bool:
     cfg = getattr(net, "_plan_config", None)
-    return cfg is not None and cfg()["variant"] in (_lib.HD_HICEDRN, _lib.HD_HICEDRN_SR3)
+    return cfg is not None and cfg()["variant"] in _TRAINABLE
 
 
 def training_loss(net, x_t, time, cond, target, weight, loss_type: str):

@@ -370,13 +370,16 @@ def sr3_p_losses_and_grads(sd: SD, noisy, clean, level, noise, *, loss_type="l2"
     return loss.detach(), dict(zip(leaves.keys(), grads))
 
 
-def p_losses_and_grads(sd: SD, buf: SD, noisy, clean, t, noise, *, loss_type="l2", self_condition=True, num_blocks=32):
+def p_losses_and_grads(sd: SD, buf: SD, noisy, clean, t, noise, *, loss_type="l2", self_condition=True, num_blocks=32, net="hicedrn"):
     """One training iteration's loss and d loss / d parameter for the hicedrn_Diff eps-net: what `loss = diffusion(x);
     loss.backward()` leaves in `.grad` (train.py:127-128) -- torch.autograd over the restated forward (the reference has no
     hand-written backward to cite).  Returns (loss, {state_dict key: grad})."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if torch.is_floating_point(v)}
-    loss = p_losses(lambda x, tt, c: hicedrn_forward(leaves, x, tt, c, self_condition=self_condition, num_blocks=num_blocks),
-                    buf, noisy, clean, t, noise, loss_type=loss_type, self_condition=self_condition)
+    if net == "unet":
+        eps_fn = lambda x, tt, c: unet_forward(leaves, x, tt, c, self_condition=self_condition)  # noqa: E731
+    else:
+        eps_fn = lambda x, tt, c: hicedrn_forward(leaves, x, tt, c, self_condition=self_condition, num_blocks=num_blocks)  # noqa: E731
+    loss = p_losses(eps_fn, buf, noisy, clean, t, noise, loss_type=loss_type, self_condition=self_condition)
     grads = torch.autograd.grad(loss, list(leaves.values()))
     return loss.detach(), dict(zip(leaves.keys(), grads))
 
