@@ -99,6 +99,35 @@ def main():
     out["cases"]["sr3_l2"] = {**c, "t": int(t), "level": [float(v) for v in level], "loss": float(loss.detach()),
                               "grads": {k: summary(g) for k, g in ref_grads.items()}}
     print(f"sr3_l2: oracle == reference bit-for-bit (t = {t}, loss {float(loss.detach()):.6f}, {len(ref_grads)} gradients)")
+    # ---- the Unet eps-net (pretrain/train_unet_Diff_cond*.py, train_unet_uncond.py)
+    for c in (dict(name="unet_cond_l2", flavour="cond", self_condition=True, loss_type="l2", schedule="sigmoid", B=2, T=1000, t=[17, 803]),
+              dict(name="unet_uncond_l1", flavour="uncond", self_condition=False, loss_type="l1", schedule="linear", B=2, T=1000, t=[17, 803])):
+        R = R_c if c["flavour"] == "cond" else R_u
+        torch.manual_seed(0)
+        net = R.Unet(dim=64, dim_mults=(1, 2, 4, 8), self_condition=c["self_condition"])
+        diff = R.GaussianDiffusion(net, image_size=64, timesteps=c["T"], loss_type=c["loss_type"], beta_schedule=c["schedule"])
+        sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        clean, noisy = O.synthetic_tiles(c["B"], seed=1234)
+        t = torch.tensor(c["t"], dtype=torch.long)
+        noise = torch.randn(c["B"], 1, 64, 64, generator=torch.Generator().manual_seed(99))
+        o_randint, o_randn_like = torch.randint, torch.randn_like
+        torch.randint = lambda *a, **k: t.clone()
+        torch.randn_like = lambda *a, **k: noise.clone()
+        try:
+            loss = diff([noisy, clean]) if c["flavour"] == "cond" else diff(clean)
+            loss.backward()
+        finally:
+            torch.randint, torch.randn_like = o_randint, o_randn_like
+        ref_grads = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+        o_loss, o_grads = O.p_losses_and_grads(sd, O.diffusion_buffers(c["schedule"], c["T"]), noisy, clean, t, noise,
+                                               loss_type=c["loss_type"], self_condition=c["self_condition"], net="unet")
+        assert torch.equal(o_loss, loss.detach()), (float(o_loss), float(loss.detach()))
+        assert ref_grads.keys() == o_grads.keys()
+        for k in ref_grads:
+            assert torch.equal(ref_grads[k], o_grads[k]), f"{c['name']}: oracle grad of {k} differs from the reference"
+        out["cases"][c["name"]] = {**{k: v for k, v in c.items() if k != "name"}, "loss": float(loss.detach()),
+                                   "grads": {k: summary(g) for k, g in ref_grads.items()}}
+        print(f"{c['name']}: oracle == reference bit-for-bit (loss {float(loss.detach()):.6f}, {len(ref_grads)} gradients)")
     path = ROOT / "tests" / "golden" / "hicedrn_train.json"
     path.write_text(json.dumps(out, indent=1))
     print("wrote", path)

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--model", choices=["hicedrn", "unet"], default="hicedrn")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -37,8 +38,14 @@ def main():
     from hicdiff_b200.synthetic import synthetic_tiles
 
     torch.manual_seed(0)
-    net = hicedrn_Diff(number_resnet=a.blocks, self_condition=True)
-    diff = GaussianDiffusion(net, image_size=64, timesteps=1000, loss_type="l2", beta_schedule="linear", auto_normalize=False).cuda()
+    if a.model == "unet":       # BASELINE config 5: conditional Unet p_losses
+        from hicdiff_b200.hicdiff_condition import Unet
+
+        net = Unet(dim=64, dim_mults=(1, 2, 4, 8), self_condition=True)
+        diff = GaussianDiffusion(net, image_size=64, timesteps=1000, loss_type="l2", beta_schedule="sigmoid").cuda()
+    else:
+        net = hicedrn_Diff(number_resnet=a.blocks, self_condition=True)
+        diff = GaussianDiffusion(net, image_size=64, timesteps=1000, loss_type="l2", beta_schedule="linear", auto_normalize=False).cuda()
     diff.train()
     if world > 1:
         T.enable_gradient_allreduce(net)
@@ -71,11 +78,12 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
     if rank == 0:
-        fwd_flops = 314.162e9 * a.blocks / 32.0                         # per tile, scaled to the block count
+        fwd_flops = 14.564e9 if a.model == "unet" else 314.162e9 * a.blocks / 32.0   # per tile
         out = {"metric": "train_tiles_per_sec", "value": a.batch * world / (ms * 1e-3), "unit": "tiles/s", "n_gpus": world,
                "ms_per_step": ms, "steps": a.steps, "warmup": a.warmup, "wall_s": time.time() - t0, "loss": float(loss.detach()),
                "dtype": "bf16 activations / fp32 parameters and gradients", "data": "synthetic",
-               "config": {"workload": f"hicedrn_Diff({a.blocks} blocks, self_condition) p_losses l2 + backward + torch Adam, batch {a.batch}/GPU",
+               "config": {"workload": (f"conditional Unet (dim 64, mults 1/2/4/8) p_losses l2 + backward + torch Adam, batch {a.batch}/GPU" if a.model == "unet" else
+                                       f"hicedrn_Diff({a.blocks} blocks, self_condition) p_losses l2 + backward + torch Adam, batch {a.batch}/GPU"),
                           "allreduce": "one NCCL all-reduce of the flat fp32 gradient buffer per step" if world > 1 else "none"},
                "model_tflops": 3 * fwd_flops * a.batch / (ms * 1e-3) / 1e12,
                "device_bytes": net._trainer.device_bytes(), "launch_groups": net._trainer.num_launch_groups()}

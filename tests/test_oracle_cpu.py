@@ -137,7 +137,7 @@ def test_oracle_against_live_reference_unet_cond():
         assert torch.equal(ref(x, t, c), O.unet_forward(ref.state_dict(), x, t, c, self_condition=True))
 
 
-@pytest.mark.parametrize("name", ["cond_l2", "uncond_l1", "sr3_l2"])
+@pytest.mark.parametrize("name", ["cond_l2", "uncond_l1", "sr3_l2", "unet_cond_l2", "unet_uncond_l1"])
 def test_oracle_training_gradients_reproduce_reference_golden(name):
     """p_losses_and_grads against the per-parameter summaries of the reference's own loss.backward()
     (oracle/make_golden_train.py asserted bit-equality of the FULL gradients when it wrote the fixture)."""
@@ -151,7 +151,13 @@ def test_oracle_training_gradients_reproduce_reference_golden(name):
 
     torch.manual_seed(gold["weight_seed"])
     sr3 = c["flavour"] == "sr3"
-    net = (hicedrn_sr3 if sr3 else hicedrn_Diff)(number_resnet=c["blocks"], self_condition=c["self_condition"])
+    unet = name.startswith("unet")
+    if unet:
+        from hicdiff_b200 import hicdiff, hicdiff_condition
+
+        net = (hicdiff_condition if c["self_condition"] else hicdiff).Unet(dim=64, dim_mults=(1, 2, 4, 8), self_condition=c["self_condition"])
+    else:
+        net = (hicedrn_sr3 if sr3 else hicedrn_Diff)(number_resnet=c["blocks"], self_condition=c["self_condition"])
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     clean, noisy = O.synthetic_tiles(c["B"], seed=gold["tile_seed"])
     noise = torch.randn(c["B"], 1, 64, 64, generator=torch.Generator().manual_seed(gold["noise_seed"]))
@@ -162,7 +168,8 @@ def test_oracle_training_gradients_reproduce_reference_golden(name):
         t = torch.tensor(c["t"], dtype=torch.long)
         buf = O.diffusion_buffers(c["schedule"], c["T"])
         loss, grads = O.p_losses_and_grads(sd, buf, noisy, clean, t, noise, loss_type=c["loss_type"],
-                                           self_condition=c["self_condition"], num_blocks=c["blocks"])
+                                           self_condition=c["self_condition"], num_blocks=c.get("blocks", 0),
+                                           net="unet" if unet else "hicedrn")
     assert abs(float(loss) - c["loss"]) <= 1e-6 * max(1.0, abs(c["loss"]))
     assert set(grads) == set(c["grads"])
     for k, s in c["grads"].items():

@@ -169,9 +169,13 @@ def test_eval_and_unsupported_paths():
     with torch.no_grad():                                                            # validation loop: value only, no trainer
         v = diff.p_losses([noisy.to(DEV), clean.to(DEV)], t=t.to(DEV), noise=noise.to(DEV))
     assert not v.requires_grad and abs(float(v) - c["loss"]) <= 2e-2 * c["loss"]
-    unet = Unet(dim=64, dim_mults=(1, 2, 4, 8), self_condition=True)
-    d2 = GaussianDiffusion(unet, image_size=64, timesteps=10, loss_type="l2").to(DEV)
-    loss = d2.p_losses([noisy.to(DEV), clean.to(DEV)], t=torch.tensor([1, 5], device=DEV), noise=noise.to(DEV))
+    # the SR3 Unet is the one eps-net without a backward yet: the loss value is there, .backward() says so
+    from hicdiff_b200 import hicdiff_sr3
+
+    unet = hicdiff_sr3.Unet(dim=64, dim_mults=(1, 2, 4, 8), self_condition=True, noise_level_emb=True)
+    d2 = hicdiff_sr3.GaussianDiffusion(unet, image_size=64, timesteps=10, loss_type="l2").to(DEV)
+    loss = d2.p_losses([noisy.to(DEV), clean.to(DEV)], noise=noise.to(DEV))
+    assert torch.isfinite(loss.detach())
     with pytest.raises(NotImplementedError):
         loss.backward()
 
@@ -335,6 +339,8 @@ def test_unet_loss_backward_matches_oracle(self_condition, loss_type, schedule):
     net, sd, diff, clean, noisy, t, noise = _unet_case(self_condition, loss_type, schedule)
     buf = O.diffusion_buffers(schedule, 1000)
     o_loss, o_grads = O.p_losses_and_grads(sd, buf, noisy, clean, t, noise, loss_type=loss_type, self_condition=self_condition, net="unet")
+    gold = GOLD["cases"]["unet_cond_l2" if self_condition else "unet_uncond_l1"]          # the reference's own loss.backward()
+    assert abs(float(o_loss) - gold["loss"]) <= 1e-6 * max(1.0, abs(gold["loss"]))
     diff = diff.to(DEV)
     diff.train()
     if self_condition:
@@ -351,3 +357,35 @@ def test_unet_loss_backward_matches_oracle(self_condition, loss_type, schedule):
     print(f"unet(self_condition={self_condition}, {loss_type}): loss {float(loss.detach()):.6f} (oracle {float(o_loss):.6f}); worst grad rel-RMS: {top}")
     bad = {k: v for k, v in worst.items() if v > 5e-2}
     assert not bad, f"gradient rel-RMS above 5e-2: {bad}"
+
+
+def test_unet_train_loop_runs_unchanged():
+    """The loop of pretrain/train_unet_Diff_cond.py: Adam over diffusion.parameters(); same batch / t / noise -> the loss must fall;
+    deterministic gradients; the sampling plan sees the updated weights."""
+    net, sd, diff, clean, noisy, t, noise = _unet_case(True, "l2", "sigmoid")
+    diff = diff.to(DEV)
+    diff.train()
+    opt = torch.optim.Adam(diff.parameters(), lr=1e-4)
+    x = [noisy.to(DEV), clean.to(DEV)]
+    losses = []
+    for it in range(6):
+        loss = diff.p_losses(x, t=t.to(DEV), noise=noise.to(DEV))
+        loss.backward()
+        if it == 0:
+            g0 = {k: p.grad.clone() for k, p in net.named_parameters()}
+        opt.step()
+        opt.zero_grad()
+        losses.append(loss.item())
+    assert all(l == l for l in losses) and losses[-1] < 0.9 * losses[0], losses
+    loss = diff(x)                                                                   # random t / noise, what the scripts call
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+    net2, _, diff2, *_ = _unet_case(True, "l2", "sigmoid")
+    diff2 = diff2.to(DEV)
+    l2 = diff2.p_losses(x, t=t.to(DEV), noise=noise.to(DEV))
+    l2.backward()
+    for k, p in net2.named_parameters():
+        assert torch.equal(p.grad, g0[k]), k
+    with torch.no_grad():
+        eps = net(x[1], t.to(DEV), x[0])
+    assert torch.isfinite(eps).all()
