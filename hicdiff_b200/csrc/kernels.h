@@ -359,6 +359,7 @@ struct GroupNormBwdArgs {
     float* dbeta;         // [C]
     float* dscale = nullptr;        // [B, C] (optional)
     float* dshift = nullptr;        // [B, C]
+    float* dpost = nullptr;         // [B, C] (optional) sum_p ds: gradient of an SR3 embedding added AFTER the activation
 };
 size_t gn_bwd_scratch_floats(int B, int P, int C);
 cudaError_t groupnorm_silu_bwd_run(const GroupNormBwdArgs& a, float* scratch, cudaStream_t s);

@@ -84,20 +84,20 @@ __global__ void __launch_bounds__(256)
 gn_bwd_sums_kernel(const uint4* __restrict__ y, const uint4* __restrict__ ds, const float2* __restrict__ stats,
                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ scale,
                    const float* __restrict__ shift, int ld, int P, int C, int nchunk, float* __restrict__ part) {
-    extern __shared__ float gs_red[];   // [lanes][2 * C]
+    extern __shared__ float gs_red[];   // [lanes][3 * C]: U, V and the plain sum of ds (the SR3 post-activation embedding's gradient)
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int cpp = C / 8, lanes = 256 / cpp;
     const int cc = threadIdx.x % cpp, pl = threadIdx.x / cpp;
     const int ppc = P / nchunk;
     const float2 st = stats[b * G + (cc * 8) / (C / G)];
-    float ga[8], be[8], sc1[8], sh[8], U[8], V[8];
+    float ga[8], be[8], sc1[8], sh[8], U[8], V[8], Ws[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = cc * 8 + j;
         ga[j] = gamma[c]; be[j] = beta[c];
         sc1[j] = scale ? scale[static_cast<size_t>(b) * ld + c] + 1.0f : 1.0f;
         sh[j] = shift ? shift[static_cast<size_t>(b) * ld + c] : 0.0f;
-        U[j] = 0.f; V[j] = 0.f;
+        U[j] = 0.f; V[j] = 0.f; Ws[j] = 0.f;
     }
     const size_t base = (static_cast<size_t>(b) * P + static_cast<size_t>(chunk) * ppc) * cpp + cc;
     for (int p = pl; p < ppc; p += lanes) {
@@ -111,15 +111,18 @@ gn_bwd_sums_kernel(const uint4* __restrict__ y, const uint4* __restrict__ ds, co
             const float dh = g[j] * silu_grad(h);
             U[j] += dh;
             V[j] = fmaf(dh, xh, V[j]);
+            Ws[j] += g[j];
         }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { gs_red[pl * 2 * C + cc * 8 + j] = U[j]; gs_red[pl * 2 * C + C + cc * 8 + j] = V[j]; }
+    for (int j = 0; j < 8; ++j) {
+        gs_red[pl * 3 * C + cc * 8 + j] = U[j]; gs_red[pl * 3 * C + C + cc * 8 + j] = V[j]; gs_red[pl * 3 * C + 2 * C + cc * 8 + j] = Ws[j];
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    for (int i = threadIdx.x; i < 3 * C; i += 256) {
         float t = 0.f;
-        for (int k = 0; k < lanes; ++k) t += gs_red[k * 2 * C + i];
-        part[(static_cast<size_t>(b) * nchunk + chunk) * 2 * C + i] = t;
+        for (int k = 0; k < lanes; ++k) t += gs_red[k * 3 * C + i];
+        part[(static_cast<size_t>(b) * nchunk + chunk) * 3 * C + i] = t;
     }
 }
 
@@ -128,15 +131,17 @@ gn_bwd_sums_kernel(const uint4* __restrict__ y, const uint4* __restrict__ ds, co
 __global__ void __launch_bounds__(512)
 gn_bwd_coef_kernel(const float* __restrict__ part, int nchunk, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ scale, int ld, int P, int C, float* __restrict__ UV, float* __restrict__ gm,
-                   float* __restrict__ dscale, float* __restrict__ dshift) {
+                   float* __restrict__ dscale, float* __restrict__ dshift, float* __restrict__ dpost) {
     __shared__ float s_a[512], s_b[512];
     const int b = blockIdx.x, c = threadIdx.x;
-    float U = 0.f, V = 0.f;
+    float U = 0.f, V = 0.f, Wp = 0.f;
     if (c < C) {
         for (int k = 0; k < nchunk; ++k) {
-            U += part[(static_cast<size_t>(b) * nchunk + k) * 2 * C + c];
-            V += part[(static_cast<size_t>(b) * nchunk + k) * 2 * C + C + c];
+            U += part[(static_cast<size_t>(b) * nchunk + k) * 3 * C + c];
+            V += part[(static_cast<size_t>(b) * nchunk + k) * 3 * C + C + c];
+            Wp += part[(static_cast<size_t>(b) * nchunk + k) * 3 * C + 2 * C + c];
         }
+        if (dpost) dpost[static_cast<size_t>(b) * ld + c] = Wp;
         UV[(static_cast<size_t>(b) * 2) * C + c] = U;
         UV[(static_cast<size_t>(b) * 2 + 1) * C + c] = V;
         if (dshift) dshift[static_cast<size_t>(b) * ld + c] = U;
@@ -313,7 +318,7 @@ int gn_chunks(int P, int C) {
 }  // namespace
 
 size_t gn_bwd_scratch_floats(int B, int P, int C) {
-    return static_cast<size_t>(B) * G * 2 /*stats*/ + static_cast<size_t>(B) * gn_chunks(P, C) * 2 * C /*part*/ +
+    return static_cast<size_t>(B) * G * 2 /*stats*/ + static_cast<size_t>(B) * gn_chunks(P, C) * 3 * C /*part*/ +
            static_cast<size_t>(B) * 2 * C /*UV*/ + static_cast<size_t>(B) * G * 2 /*gm*/ + 64;
 }
 
@@ -325,14 +330,14 @@ cudaError_t groupnorm_silu_bwd_run(const GroupNormBwdArgs& a, float* scratch, cu
     const int ld = a.ld > 0 ? a.ld : C;
     float2* stats = reinterpret_cast<float2*>(scratch);
     float* part = scratch + static_cast<size_t>(B) * G * 2;
-    float* UV = part + static_cast<size_t>(B) * nchunk * 2 * C;
+    float* UV = part + static_cast<size_t>(B) * nchunk * 3 * C;
     float* gm = UV + static_cast<size_t>(B) * 2 * C;
     const uint4* y = reinterpret_cast<const uint4*>(a.y);
     const uint4* ds = reinterpret_cast<const uint4*>(a.ds);
     gn_stats_kernel<<<dim3(G, B), 256, 0, s>>>(y, P, C, a.eps, stats);
-    gn_bwd_sums_kernel<<<dim3(nchunk, B), 256, static_cast<size_t>(lanes) * 2 * C * sizeof(float), s>>>(
+    gn_bwd_sums_kernel<<<dim3(nchunk, B), 256, static_cast<size_t>(lanes) * 3 * C * sizeof(float), s>>>(
         y, ds, stats, a.gamma, a.beta, a.scale, a.shift, ld, P, C, nchunk, part);
-    gn_bwd_coef_kernel<<<B, 512, 0, s>>>(part, nchunk, a.gamma, a.beta, a.scale, ld, P, C, UV, gm, a.dscale, a.dshift);
+    gn_bwd_coef_kernel<<<B, 512, 0, s>>>(part, nchunk, a.gamma, a.beta, a.scale, ld, P, C, UV, gm, a.dscale, a.dshift, a.dpost);
     gn_bwd_affine_kernel<<<(C + 255) / 256, 256, 0, s>>>(UV, a.scale, ld, B, C, a.dgamma, a.dbeta);
     gn_bwd_dx_kernel<<<dim3(nchunk, B), 256, 0, s>>>(y, ds, stats, gm, a.gamma, a.beta, a.scale, a.shift, ld, P, C, nchunk,
                                                       reinterpret_cast<uint4*>(a.dy));

@@ -297,10 +297,9 @@ extern "C" {
 int hd_trainer_create(const hd_config* cfg, int32_t batch, hd_trainer** out) {
     if (!cfg || !out) return tfail("hd_trainer_create: null argument");
     if (cfg->abi_version != HD_ABI_VERSION) return tfail("ABI version mismatch: header %d, library %d", cfg->abi_version, HD_ABI_VERSION);
-    if (cfg->variant != HD_HICEDRN && cfg->variant != HD_HICEDRN_SR3 && cfg->variant != HD_UNET)
-        return tfail("hd_trainer covers hicedrn_Diff, hicedrn_sr3_Diff and the (non-SR3) Unet; variant %d has no backward yet", cfg->variant);
+    if (cfg->variant < HD_UNET || cfg->variant > HD_HICEDRN_SR3) return tfail("unknown variant %d", cfg->variant);
     if (cfg->image_size != 64) return tfail("image_size must be 64");
-    if (cfg->variant == HD_UNET) {
+    if (cfg->variant == HD_UNET || cfg->variant == HD_UNET_SR3) {
         if (cfg->dim != 64) return tfail("the Unet training step is built for dim = 64 (got %d)", cfg->dim);
         if (cfg->num_mults < 1 || cfg->num_mults > 4) return tfail("len(dim_mults) must be 1..4 for 64x64 tiles (got %d)", cfg->num_mults);
         for (int i = 0; i < cfg->num_mults; ++i)
@@ -339,7 +338,7 @@ int hd_trainer_finalize(hd_trainer* t, void* stream) {
     if (!t) return tfail("hd_trainer_finalize: null trainer");
     if (t->finalized) return 0;
     T_TRY(cudaSetDevice(t->device));
-    if (t->cfg.variant == HD_UNET ? build_unet_trainer(t) : build(t)) return 1;
+    if ((t->cfg.variant == HD_UNET || t->cfg.variant == HD_UNET_SR3) ? build_unet_trainer(t) : build(t)) return 1;
     T_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     t->finalized = true;
     return 0;

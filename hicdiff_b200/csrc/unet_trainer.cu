@@ -40,6 +40,7 @@ struct UB {
     hd_trainer* t;
     int B;
     bool ok = true;
+    bool sr3 = false;                 // hicdiff_sr3.Unet: additive noise-level embedding after block1 instead of FiLM
     int ld = 0;                       // FiLM row width
     float *film = nullptr, *dfilm = nullptr;
     int* iota = nullptr;
@@ -183,7 +184,8 @@ struct UB {
         {
             GroupNormArgs a;
             a.x = y1->p; a.y = s1->p; a.B = B; a.P = P; a.C = Cout; a.part = gn_part; a.gamma = g1->w; a.beta = b1->w; a.eps = EPS;
-            a.film = film; a.film_row = iota; a.film_row_stride = 1; a.film_ld = ld; a.film_off = film_off;
+            a.film_row = iota; a.film_row_stride = 1; a.film_ld = ld;
+            if (sr3) { a.postadd = film; a.postadd_off = film_off; } else { a.film = film; a.film_off = film_off; }
             push("groupnorm", p + ".block1.norm", [a](cudaStream_t s) { return groupnorm_film_silu_run(a, s); });
         }
         if (!conv_fwd(p + ".block2.conv", c2, *s1, nullptr, y2->p, ConvEpilogue(), true)) return out;
@@ -210,8 +212,10 @@ struct UB {
             {
                 GroupNormBwdArgs a;
                 a.y = y1->p; a.ds = T2; a.dy = T2; a.B = B; a.P = P; a.C = Cout; a.gamma = g1->w; a.beta = b1->w; a.eps = EPS;
-                a.scale = film + film_off; a.shift = film + film_off + Cout; a.ld = ld;
-                a.dgamma = g1->g; a.dbeta = b1->g; a.dscale = dfilm + film_off; a.dshift = dfilm + film_off + Cout;
+                a.ld = ld;
+                if (sr3) { a.dpost = dfilm + film_off; }
+                else { a.scale = film + film_off; a.shift = film + film_off + Cout; a.dscale = dfilm + film_off; a.dshift = dfilm + film_off + Cout; }
+                a.dgamma = g1->g; a.dbeta = b1->g;
                 float* sc = gn_scratch;
                 push("groupnorm_bwd", p + ".block1.norm.bwd", [a, sc](cudaStream_t s) { return groupnorm_silu_bwd_run(a, sc, s); });
             }
@@ -389,7 +393,9 @@ int build_unet_trainer(hd_trainer* t) {
     std::vector<int> dims{dim};
     for (int i = 0; i < L; ++i) dims.push_back(dim * c.dim_mults[i]);
 
+    const bool sr3 = c.variant == HD_UNET_SR3;
     UB u{t, B};
+    u.sr3 = sr3;
     // ---------------------------------------------------------------- FiLM slots (module order, hd_plan_finalize's layout)
     std::vector<std::pair<std::string, int>> blocks;
     for (int i = 0; i < L; ++i) { blocks.push_back({"downs." + std::to_string(i) + ".0", dims[i]}); blocks.push_back({"downs." + std::to_string(i) + ".1", dims[i]}); }
@@ -399,7 +405,7 @@ int build_unet_trainer(hd_trainer* t) {
     blocks.push_back({"final_res_block", dim});
     std::map<std::string, int> film_off;
     int ld = 0;
-    for (auto& b : blocks) { film_off[b.first] = ld; ld += 2 * b.second; }
+    for (auto& b : blocks) { film_off[b.first] = ld; ld += (sr3 ? 1 : 2) * b.second; }
     u.ld = ld;
 
     // ---------------------------------------------------------------- io + shared scratch
@@ -432,8 +438,9 @@ int build_unet_trainer(hd_trainer* t) {
         return 1;
     std::vector<const TParam*> mw, mb;
     for (auto& b : blocks) {
-        mw.push_back(find_p(t, b.first + ".mlp.1.weight", {2 * b.second, time_dim}));
-        mb.push_back(find_p(t, b.first + ".mlp.1.bias", {2 * b.second}));
+        const int width = (sr3 ? 1 : 2) * b.second;
+        mw.push_back(find_p(t, b.first + (sr3 ? ".noise_func.noise_func.0.weight" : ".mlp.1.weight"), {width, time_dim}));
+        mb.push_back(find_p(t, b.first + (sr3 ? ".noise_func.noise_func.0.bias" : ".mlp.1.bias"), {width}));
         if (!mw.back() || !mb.back()) return 1;
     }
     // weight preparation ops are pushed by convw() as the layers are declared -> declare the whole net FIRST into a side list,
@@ -445,7 +452,7 @@ int build_unet_trainer(hd_trainer* t) {
         float* tv = t->time;
         const float *w1d = w1->w, *b1d = b1->w, *w3d = w3->w, *b3d = b3->w;
         float* film = u.film;
-        u.push("time", "posenc", [=](cudaStream_t s) { return posenc_rows_run(tv, posenc, B, dim, 0, s); });
+        u.push("time", "posenc", [=](cudaStream_t s) { return posenc_rows_run(tv, posenc, B, dim, sr3 ? 1 : 0, s); });
         u.push("time", "time_mlp.1", [=](cudaStream_t s) { return linear_rows_run(posenc, dim, w1d, b1d, z1, time_dim, 0, B, dim, time_dim, 0, 0, s); });
         u.push("time", "gelu+time_mlp.3+silu", [=](cudaStream_t s) {
             cudaError_t e = act_apply_run(z1, g1, static_cast<long long>(B) * time_dim, 2, s);
@@ -454,8 +461,9 @@ int build_unet_trainer(hd_trainer* t) {
         });
         for (size_t i = 0; i < blocks.size(); ++i) {
             const float *w = mw[i]->w, *bias = mb[i]->w;
-            const int off = film_off[blocks[i].first], width = 2 * blocks[i].second;
-            u.push("time", blocks[i].first + ".mlp", [=](cudaStream_t s) { return linear_rows_run(stemb, time_dim, w, bias, film, ld, off, B, time_dim, width, 0, 0, s); });
+            const int off = film_off[blocks[i].first], width = (sr3 ? 1 : 2) * blocks[i].second;
+            const float* tin = sr3 ? temb : stemb;
+            u.push("time", blocks[i].first + ".mlp", [=](cudaStream_t s) { return linear_rows_run(tin, time_dim, w, bias, film, ld, off, B, time_dim, width, 0, 0, s); });
         }
         time_ops.swap(t->ops);
         t->ops.swap(keep);
@@ -557,17 +565,18 @@ int build_unet_trainer(hd_trainer* t) {
         for (size_t i = 0; i < blocks.size(); ++i) {
             const float* w = mw[i]->w;
             float *gw = mw[i]->g, *gb = mb[i]->g;
-            const int off = film_off[blocks[i].first], width = 2 * blocks[i].second;
+            const int off = film_off[blocks[i].first], width = (sr3 ? 1 : 2) * blocks[i].second;
             const int acc = i > 0 ? 1 : 0;
+            const float* tin = sr3 ? temb : stemb;
             u.push("time_bwd", blocks[i].first + ".mlp.bwd", [=](cudaStream_t s) {
-                cudaError_t e = linear_bwd_weight_run(dfilm, ld, off, stemb, time_dim, B, time_dim, width, 0, gw, gb, s);
+                cudaError_t e = linear_bwd_weight_run(dfilm, ld, off, tin, time_dim, B, time_dim, width, 0, gw, gb, s);
                 return e != cudaSuccess ? e : linear_bwd_input_run(dfilm, ld, off, w, B, time_dim, width, acc, d_act, time_dim, s);
             });
         }
         float *gw3 = w3->g, *gb3 = b3->g, *gw1 = w1->g, *gb1 = b1->g;
         const float* w3d = w3->w;
         u.push("time_bwd", "time_mlp.bwd", [=](cudaStream_t s) {
-            cudaError_t e = act_grad_run(d_act, temb, static_cast<long long>(B) * time_dim, 1, s);
+            cudaError_t e = sr3 ? cudaSuccess : act_grad_run(d_act, temb, static_cast<long long>(B) * time_dim, 1, s);
             if (e == cudaSuccess) e = linear_bwd_weight_run(d_act, time_dim, 0, g1, time_dim, B, time_dim, time_dim, 0, gw3, gb3, s);
             if (e == cudaSuccess) e = linear_bwd_input_run(d_act, time_dim, 0, w3d, B, time_dim, time_dim, 0, d_g1, time_dim, s);
             if (e == cudaSuccess) e = act_grad_run(d_g1, z1, static_cast<long long>(B) * time_dim, 2, s);

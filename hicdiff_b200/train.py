@@ -17,7 +17,7 @@ import torch
 from . import _lib
 
 
-_TRAINABLE = (_lib.HD_HICEDRN, _lib.HD_HICEDRN_SR3, _lib.HD_UNET)
+_TRAINABLE = (_lib.HD_HICEDRN, _lib.HD_HICEDRN_SR3, _lib.HD_UNET, _lib.HD_UNET_SR3)
 
 
 class Trainer:
@@ -27,9 +27,7 @@ class Trainer:
         lib = _lib.load()
         cfgd = net._plan_config()
         if cfgd["variant"] not in _TRAINABLE:
-            raise NotImplementedError(
-                "hicdiff_b200: the training backward covers hicedrn_Diff, hicedrn_sr3_Diff and the Unet of "
-                "hicdiff.py / hicdiff_condition.py; the SR3 Unet backward is not built yet")
+            raise NotImplementedError("hicdiff_b200: no training backward for this eps-net variant")
         params = dict(net.named_parameters())
         dev = next(iter(params.values())).device
         if dev.type != "cuda":

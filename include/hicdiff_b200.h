@@ -122,12 +122,12 @@ HD_API int hd_ssim_mse_tiles(const float* a, const float* b, const float* window
                       int32_t rescale, void* stream);
 
 /* -------------------------------------------------------------------------------------------------------------
- * Training step.  Replaces, for hicedrn_Diff -- the model train.py trains (train.py:84-107) -- the
- * forward + loss + loss.backward() of one iteration (train.py:120-129): eps = model(x_t, t, cond)
- * (src/model/hicedrn_Diff.py:267-289), loss = mean(|eps - target|^p * weight[b]) (p_losses, hicdiff_condition.py:741-746,
+ * Training step.  Replaces the forward + loss + loss.backward() of one iteration (train.py:120-129,
+ * pretrain/train_*.py) for every eps-net variant: eps = model(x_t, t, cond) (src/model/hicedrn_Diff.py:267-289,
+ * src/hicdiff_condition.py:345-384, src/hicdiff_sr3.py:410-445), loss = mean(|eps - target|^p * weight[b]) (p_losses, hicdiff_condition.py:741-746,
  * loss_fn :706-713; weight = p2_loss_weight[t]), and d loss / d parameter for every parameter of the net.
- *   hd_trainer_create    cfg.variant must be HD_HICEDRN or HD_HICEDRN_SR3 (src/model/hicedrn_sr3_Diff.py: additive noise-level
- *                        embedding, `time` = the continuous noise level); `batch` tiles per step (fixed per trainer)
+ *   hd_trainer_create    any hd_variant (the SR3 variants take the continuous noise level as `time`; Unet: dim = 64,
+ *                        dim_mults in {1,2,4,8}); `batch` tiles per step (fixed per trainer)
  *   hd_trainer_bind      once per state_dict entry (key without the `model.` prefix): `param` is READ IN PLACE at every
  *                        step (so any optimizer may update it between steps), `grad` (same shape, fp32) is OVERWRITTEN by
  *                        every step; both are device pointers the caller keeps alive

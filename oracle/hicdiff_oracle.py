@@ -361,11 +361,15 @@ def sr3_p_losses(eps_fn, noisy, clean, level, noise, *, loss_type="l2", self_con
     return (F.mse_loss(out, noise, reduction="none") if loss_type == "l2" else F.l1_loss(out, noise, reduction="none")).mean()
 
 
-def sr3_p_losses_and_grads(sd: SD, noisy, clean, level, noise, *, loss_type="l2", self_condition=True, num_blocks=32):
-    """Loss and parameter gradients of one SR3 training iteration over hicedrn_sr3_Diff (pretrain/train_hicedrn_Diff_sr3.py)."""
+def sr3_p_losses_and_grads(sd: SD, noisy, clean, level, noise, *, loss_type="l2", self_condition=True, num_blocks=32, net="hicedrn"):
+    """Loss and parameter gradients of one SR3 training iteration over hicedrn_sr3_Diff (pretrain/train_hicedrn_Diff_sr3.py) or
+    the SR3 Unet (pretrain/train_unet_Diff_sr3.py)."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if torch.is_floating_point(v)}
-    loss = sr3_p_losses(lambda x, lv, c: hicedrn_forward(leaves, x, lv, c, self_condition=self_condition, sr3=True, num_blocks=num_blocks),
-                        noisy, clean, level, noise, loss_type=loss_type, self_condition=self_condition)
+    if net == "unet":
+        eps_fn = lambda x, lv, c: unet_forward(leaves, x, lv, c, self_condition=self_condition, sr3=True)  # noqa: E731
+    else:
+        eps_fn = lambda x, lv, c: hicedrn_forward(leaves, x, lv, c, self_condition=self_condition, sr3=True, num_blocks=num_blocks)  # noqa: E731
+    loss = sr3_p_losses(eps_fn, noisy, clean, level, noise, loss_type=loss_type, self_condition=self_condition)
     grads = torch.autograd.grad(loss, list(leaves.values()))
     return loss.detach(), dict(zip(leaves.keys(), grads))
 

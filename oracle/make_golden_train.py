@@ -99,6 +99,27 @@ def main():
     out["cases"]["sr3_l2"] = {**c, "t": int(t), "level": [float(v) for v in level], "loss": float(loss.detach()),
                               "grads": {k: summary(g) for k, g in ref_grads.items()}}
     print(f"sr3_l2: oracle == reference bit-for-bit (t = {t}, loss {float(loss.detach()):.6f}, {len(ref_grads)} gradients)")
+    # ---- SR3 Unet (pretrain/train_unet_Diff_sr3.py)
+    c = dict(flavour="sr3", self_condition=True, loss_type="l2", schedule="linear", B=2, T=1000, np_seed=6)
+    torch.manual_seed(0)
+    net = R_s.Unet(dim=64, dim_mults=(1, 2, 4, 8), self_condition=True, noise_level_emb=True)
+    diff = R_s.GaussianDiffusion(net, image_size=64, timesteps=c["T"], loss_type=c["loss_type"], beta_schedule=c["schedule"], auto_normalize=False)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    np.random.seed(c["np_seed"])
+    loss = diff.p_losses([noisy, clean], noise=noise.clone())
+    loss.backward()
+    np.random.seed(c["np_seed"])
+    t = np.random.randint(1, c["T"] + 1)
+    level = torch.FloatTensor(np.random.uniform(lv_table[t - 1], lv_table[t], size=c["B"]))
+    ref_grads = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+    o_loss, o_grads = O.sr3_p_losses_and_grads(sd, noisy, clean, level, noise, loss_type=c["loss_type"], self_condition=True, net="unet")
+    assert torch.equal(o_loss, loss.detach()), (float(o_loss), float(loss))
+    for k in ref_grads:
+        assert torch.equal(ref_grads[k], o_grads[k]), f"unet sr3: oracle grad of {k} differs from the reference"
+    out["cases"]["unet_sr3_l2"] = {**c, "t": int(t), "level": [float(v) for v in level], "loss": float(loss.detach()),
+                                   "grads": {k: summary(g) for k, g in ref_grads.items()}}
+    print(f"unet_sr3_l2: oracle == reference bit-for-bit (t = {t}, loss {float(loss.detach()):.6f}, {len(ref_grads)} gradients)")
+
     # ---- the Unet eps-net (pretrain/train_unet_Diff_cond*.py, train_unet_uncond.py)
     for c in (dict(name="unet_cond_l2", flavour="cond", self_condition=True, loss_type="l2", schedule="sigmoid", B=2, T=1000, t=[17, 803]),
               dict(name="unet_uncond_l1", flavour="uncond", self_condition=False, loss_type="l1", schedule="linear", B=2, T=1000, t=[17, 803])):

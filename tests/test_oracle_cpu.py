@@ -137,7 +137,7 @@ def test_oracle_against_live_reference_unet_cond():
         assert torch.equal(ref(x, t, c), O.unet_forward(ref.state_dict(), x, t, c, self_condition=True))
 
 
-@pytest.mark.parametrize("name", ["cond_l2", "uncond_l1", "sr3_l2", "unet_cond_l2", "unet_uncond_l1"])
+@pytest.mark.parametrize("name", ["cond_l2", "uncond_l1", "sr3_l2", "unet_cond_l2", "unet_uncond_l1", "unet_sr3_l2"])
 def test_oracle_training_gradients_reproduce_reference_golden(name):
     """p_losses_and_grads against the per-parameter summaries of the reference's own loss.backward()
     (oracle/make_golden_train.py asserted bit-equality of the FULL gradients when it wrote the fixture)."""
@@ -155,7 +155,12 @@ def test_oracle_training_gradients_reproduce_reference_golden(name):
     if unet:
         from hicdiff_b200 import hicdiff, hicdiff_condition
 
-        net = (hicdiff_condition if c["self_condition"] else hicdiff).Unet(dim=64, dim_mults=(1, 2, 4, 8), self_condition=c["self_condition"])
+        if sr3:
+            from hicdiff_b200 import hicdiff_sr3
+
+            net = hicdiff_sr3.Unet(dim=64, dim_mults=(1, 2, 4, 8), self_condition=True, noise_level_emb=True)
+        else:
+            net = (hicdiff_condition if c["self_condition"] else hicdiff).Unet(dim=64, dim_mults=(1, 2, 4, 8), self_condition=c["self_condition"])
     else:
         net = (hicedrn_sr3 if sr3 else hicedrn_Diff)(number_resnet=c["blocks"], self_condition=c["self_condition"])
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
@@ -163,7 +168,8 @@ def test_oracle_training_gradients_reproduce_reference_golden(name):
     noise = torch.randn(c["B"], 1, 64, 64, generator=torch.Generator().manual_seed(gold["noise_seed"]))
     if sr3:
         loss, grads = O.sr3_p_losses_and_grads(sd, noisy, clean, torch.tensor(c["level"], dtype=torch.float32), noise,
-                                               loss_type=c["loss_type"], self_condition=True, num_blocks=c["blocks"])
+                                               loss_type=c["loss_type"], self_condition=True, num_blocks=c.get("blocks", 0),
+                                               net="unet" if unet else "hicedrn")
     else:
         t = torch.tensor(c["t"], dtype=torch.long)
         buf = O.diffusion_buffers(c["schedule"], c["T"])

@@ -161,23 +161,13 @@ def test_train_loop_runs_unchanged_and_is_deterministic():
     assert torch.isfinite(eps).all()
 
 
-def test_eval_and_unsupported_paths():
-    from hicdiff_b200.hicdiff_condition import GaussianDiffusion, Unet
+def test_eval_path_needs_no_trainer():
 
     c, net, sd, diff, clean, noisy, t, noise = _case("cond_l2")
     diff = diff.to(DEV)
     with torch.no_grad():                                                            # validation loop: value only, no trainer
         v = diff.p_losses([noisy.to(DEV), clean.to(DEV)], t=t.to(DEV), noise=noise.to(DEV))
     assert not v.requires_grad and abs(float(v) - c["loss"]) <= 2e-2 * c["loss"]
-    # the SR3 Unet is the one eps-net without a backward yet: the loss value is there, .backward() says so
-    from hicdiff_b200 import hicdiff_sr3
-
-    unet = hicdiff_sr3.Unet(dim=64, dim_mults=(1, 2, 4, 8), self_condition=True, noise_level_emb=True)
-    d2 = hicdiff_sr3.GaussianDiffusion(unet, image_size=64, timesteps=10, loss_type="l2").to(DEV)
-    loss = d2.p_losses([noisy.to(DEV), clean.to(DEV)], noise=noise.to(DEV))
-    assert torch.isfinite(loss.detach())
-    with pytest.raises(NotImplementedError):
-        loss.backward()
 
 
 WGRAD_CASES = [
@@ -389,3 +379,30 @@ def test_unet_train_loop_runs_unchanged():
     with torch.no_grad():
         eps = net(x[1], t.to(DEV), x[0])
     assert torch.isfinite(eps).all()
+
+
+def test_unet_sr3_loss_backward_matches_oracle():
+    """pretrain/train_unet_Diff_sr3.py: Unet(noise_level_emb=True) under the SR3 GaussianDiffusion (additive noise-level
+    embedding after block1, numpy-RNG level sampling)."""
+    from hicdiff_b200 import hicdiff_sr3
+
+    c = GOLD["cases"]["unet_sr3_l2"]
+    torch.manual_seed(GOLD["weight_seed"])
+    net = hicdiff_sr3.Unet(dim=64, dim_mults=(1, 2, 4, 8), self_condition=True, noise_level_emb=True)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    clean, noisy = O.synthetic_tiles(c["B"], seed=GOLD["tile_seed"])
+    noise = torch.randn(c["B"], 1, 64, 64, generator=torch.Generator().manual_seed(GOLD["noise_seed"]))
+    level = torch.tensor(c["level"], dtype=torch.float32)
+    o_loss, o_grads = O.sr3_p_losses_and_grads(sd, noisy, clean, level, noise, loss_type=c["loss_type"], self_condition=True, net="unet")
+    assert abs(float(o_loss) - c["loss"]) <= 1e-6 * max(1.0, abs(c["loss"]))
+    diff = hicdiff_sr3.GaussianDiffusion(net, image_size=64, timesteps=c["T"], loss_type=c["loss_type"], beta_schedule=c["schedule"],
+                                         auto_normalize=False).to(DEV)
+    diff.train()
+    loss = diff.p_losses([noisy.to(DEV), clean.to(DEV)], noise=noise.to(DEV), level=level.to(DEV))
+    loss.backward()
+    assert abs(float(loss.detach()) - float(o_loss)) <= 5e-3 * abs(float(o_loss)), (float(loss.detach()), float(o_loss))
+    worst = {k: _rel(p.grad, o_grads[k]) for k, p in net.named_parameters()}
+    top = sorted(worst.items(), key=lambda kv: -kv[1])[:4]
+    print(f"unet_sr3: loss {float(loss.detach()):.6f} (oracle {float(o_loss):.6f}); worst grad rel-RMS: {top}")
+    bad = {k: v for k, v in worst.items() if v > 5e-2}
+    assert not bad, f"gradient rel-RMS above 5e-2: {bad}"
