@@ -151,7 +151,7 @@ la_t_kernel(const bf16* __restrict__ qkv, int n, const float* __restrict__ kmax,
 }
 
 // ---- pass 4: the gradients.  grid (chunks, B * HEADS); per pixel one warp
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)     // <= 128 registers: two CTAs per SM (ncu: at 159 registers one CTA / SM left the kernel latency-bound)
 la_grad_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, int n, float scale, const float* __restrict__ kmax,
                const float* __restrict__ ksum, const float* __restrict__ cd, const float* __restrict__ tvec, bf16* __restrict__ dqkv) {
     __shared__ float s_ctx[DH][DH + 1], s_dctx[DH][DH + 1];

@@ -43,37 +43,52 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {   // 256 thr
 }
 
 // ---------------------------------------------------------------------------------------------- statistics
-// grid (G, B): mean and rstd of group g of sample b (two passes over the group's P * cpg elements: mean, then variance)
+// One coalesced pass: grid (nchunk, B), thread = (8-channel chunk cc, pixel lane pl) like the passes below; every thread's eight
+// channels lie in ONE group, so it keeps a (sum, sum of squares) pair; per-group partials per pixel chunk are merged in double
+// precision by gn_stats_finish_kernel (E[x^2] - mean^2 on conv outputs: |mean| ~ std, far from cancellation in fp64).
 __global__ void __launch_bounds__(256)
-gn_stats_kernel(const uint4* __restrict__ y, int P, int C, float eps, float2* __restrict__ stats) {
-    __shared__ float s_red[8];
-    const int g = blockIdx.x, b = blockIdx.y;
-    const int cpp = C / 8, gch = cpp / G;                       // 16-byte chunks per pixel / per group (cpg = 8 * gch channels)
-    const uint4* base = y + static_cast<size_t>(b) * P * cpp + g * gch;
-    const int n_chunks = P * gch;
-    float acc = 0.f;
-    for (int i = threadIdx.x; i < n_chunks; i += 256) {
+gn_stats_part_kernel(const uint4* __restrict__ y, int P, int C, int nchunk, float2* __restrict__ spart) {
+    __shared__ float s_s[256], s_q[256];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int cpp = C / 8, lanes = 256 / cpp;
+    const int cc = threadIdx.x % cpp, pl = threadIdx.x / cpp;
+    const int ppc = P / nchunk;
+    const size_t base = (static_cast<size_t>(b) * P + static_cast<size_t>(chunk) * ppc) * cpp + cc;
+    float s1 = 0.f, s2 = 0.f;
+    for (int p = pl; p < ppc; p += lanes) {
         float v[8];
-        unpack8(__ldg(base + static_cast<size_t>(i / gch) * cpp + i % gch), v);
+        unpack8(__ldg(y + base + static_cast<size_t>(p) * cpp), v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc += v[j];
+        for (int j = 0; j < 8; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
     }
-    const float n = static_cast<float>(n_chunks) * 8.0f;
-    const float mean = block_sum(acc, s_red) / n;
-    acc = 0.f;
-    for (int i = threadIdx.x; i < n_chunks; i += 256) {
-        float v[8];
-        unpack8(__ldg(base + static_cast<size_t>(i / gch) * cpp + i % gch), v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; acc = fmaf(d, d, acc); }
+    s_s[threadIdx.x] = s1;
+    s_q[threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.x < G) {
+        const int g = threadIdx.x, gch = cpp / G;        // chunks cc in [g * gch, (g + 1) * gch) belong to group g
+        float a = 0.f, q = 0.f;
+        for (int l = 0; l < lanes; ++l)
+            for (int k = 0; k < gch; ++k) { a += s_s[l * cpp + g * gch + k]; q += s_q[l * cpp + g * gch + k]; }
+        spart[(static_cast<size_t>(b) * nchunk + chunk) * G + g] = make_float2(a, q);
     }
-    const float var = block_sum(acc, s_red) / n;
-    if (threadIdx.x == 0) stats[b * G + g] = make_float2(mean, rsqrtf(var + eps));
+}
+__global__ void gn_stats_finish_kernel(const float2* __restrict__ spart, int nchunk, int P, int C, float eps, float2* __restrict__ stats) {
+    const int b = blockIdx.x, g = threadIdx.x;
+    if (g >= G) return;
+    double a = 0.0, q = 0.0;
+    for (int k = 0; k < nchunk; ++k) { const float2 v = spart[(static_cast<size_t>(b) * nchunk + k) * G + g]; a += v.x; q += v.y; }
+    const double n = static_cast<double>(P) * (C / G);
+    const double mean = a / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[b * G + g] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
 }
 
-__device__ __forceinline__ float silu_grad(float h) {
-    const float sg = 1.0f / (1.0f + __expf(-h));
-    return sg * (1.0f + h * (1.0f - sg));
+__device__ __forceinline__ float silu_grad(float h) {     // sigmoid through one tanh.approx (see train_kernels.cu): these passes are issue-bound
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * h));
+    const float sg = fmaf(0.5f, t, 0.5f);
+    return sg * fmaf(h, 1.0f - sg, 1.0f);
 }
 
 constexpr int GB_CHUNKS_MAX = 16;
@@ -214,58 +229,76 @@ gn_bwd_dx_kernel(const uint4* __restrict__ y, const uint4* ds, const float2* __r
 }
 
 // ---------------------------------------------------------------------------------------------- channel LayerNorm backward
-// z = xhat * g, xhat = (x - mu) * r over the C channels of a pixel.  One warp per pixel:
+// z = xhat * g, xhat = (x - mu) * r over the C channels of a pixel.  One warp per pixel, PB pixels in flight per warp (their
+// shuffle reductions interleave):
 //   dx = r * (dz g - mean_c(dz g) - xhat mean_c(dz g xhat));  dg partial sums per block -> part[blk][C]
+template <int PER, int PB>      // PER = C / 32 channels per lane
 __global__ void __launch_bounds__(256)
-ln_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dz, const float* __restrict__ gain, long long M, int C,
-              float eps, bf16* __restrict__ dx, float* __restrict__ part) {
+ln_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dz, const float* __restrict__ gain, long long M, float eps,
+              bf16* __restrict__ dx, float* __restrict__ part) {
+    constexpr int C = PER * 32;
     extern __shared__ float ln_dg[];   // [8 warps][C]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int per = C / 32;            // channels per lane (2 .. 16)
-    float dg[16];
+    float dg[PER], gn[PER];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) dg[j] = 0.f;
-    for (long long m = static_cast<long long>(blockIdx.x) * 8 + warp; m < M; m += static_cast<long long>(gridDim.x) * 8) {
-        float xv[16], gv[16];
-        float s = 0.f;
+    for (int j = 0; j < PER; ++j) { dg[j] = 0.f; gn[j] = gain[j * 32 + lane]; }
+    const long long stride = static_cast<long long>(gridDim.x) * 8 * PB;
+    for (long long m0 = (static_cast<long long>(blockIdx.x) * 8 + warp) * PB; m0 < M; m0 += stride) {
+        float xv[PB][PER], gv[PB][PER], s[PB], vs[PB], a[PB], bs[PB], r[PB];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            if (j < per) {
-                const int c = j * 32 + lane;
-                xv[j] = __bfloat162float(x[m * C + c]);
-                gv[j] = __bfloat162float(dz[m * C + c]);
-                s += xv[j];
+        for (int q = 0; q < PB; ++q) {
+            const long long m = m0 + q < M ? m0 + q : M - 1;          // tail: recompute the last pixel, store guarded below
+            s[q] = 0.f;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                xv[q][j] = __bfloat162float(x[m * C + j * 32 + lane]);
+                gv[q][j] = __bfloat162float(dz[m * C + j * 32 + lane]);
+                s[q] += xv[q][j];
             }
         }
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const float mean = s / C;
-        float vs = 0.f;
+        for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) if (j < per) { const float d = xv[j] - mean; vs = fmaf(d, d, vs); }
-        for (int o = 16; o > 0; o >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, o);
-        const float r = rsqrtf(vs / C + eps);
-        float a = 0.f, bsum = 0.f;
+            for (int q = 0; q < PB; ++q) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            if (j < per) {
-                const int c = j * 32 + lane;
-                const float xh = (xv[j] - mean) * r;
-                const float t = gv[j] * gain[c];
-                dg[j] = fmaf(gv[j], xh, dg[j]);
-                a += t;
-                bsum = fmaf(t, xh, bsum);
-                xv[j] = xh;
-                gv[j] = t;
+        for (int q = 0; q < PB; ++q) {
+            s[q] /= C;
+            vs[q] = 0.f;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) { const float d = xv[q][j] - s[q]; vs[q] = fmaf(d, d, vs[q]); }
+        }
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int q = 0; q < PB; ++q) vs[q] += __shfl_xor_sync(0xffffffffu, vs[q], o);
+#pragma unroll
+        for (int q = 0; q < PB; ++q) {
+            r[q] = rsqrtf(vs[q] / C + eps);
+            a[q] = 0.f; bs[q] = 0.f;
+            const bool live = m0 + q < M;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const float xh = (xv[q][j] - s[q]) * r[q];
+                const float t = gv[q][j] * gn[j];
+                if (live) dg[j] = fmaf(gv[q][j], xh, dg[j]);
+                a[q] += t;
+                bs[q] = fmaf(t, xh, bs[q]);
+                xv[q][j] = xh;
+                gv[q][j] = t;
             }
         }
-        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); bsum += __shfl_xor_sync(0xffffffffu, bsum, o); }
-        a /= C; bsum /= C;
+        for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (j < per) dx[m * C + j * 32 + lane] = __float2bfloat16(r * (gv[j] - a - xv[j] * bsum));
+            for (int q = 0; q < PB; ++q) { a[q] += __shfl_xor_sync(0xffffffffu, a[q], o); bs[q] += __shfl_xor_sync(0xffffffffu, bs[q], o); }
+#pragma unroll
+        for (int q = 0; q < PB; ++q) {
+            if (m0 + q < M) {
+                const float am = a[q] / C, bm = bs[q] / C;
+#pragma unroll
+                for (int j = 0; j < PER; ++j) dx[(m0 + q) * C + j * 32 + lane] = __float2bfloat16(r[q] * (gv[q][j] - am - xv[q][j] * bm));
+            }
+        }
     }
 #pragma unroll
-    for (int j = 0; j < 16; ++j) if (j < per) ln_dg[warp * C + j * 32 + lane] = dg[j];
+    for (int j = 0; j < PER; ++j) ln_dg[warp * C + j * 32 + lane] = dg[j];
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += 256) {
         float t = 0.f;
@@ -319,7 +352,7 @@ int gn_chunks(int P, int C) {
 
 size_t gn_bwd_scratch_floats(int B, int P, int C) {
     return static_cast<size_t>(B) * G * 2 /*stats*/ + static_cast<size_t>(B) * gn_chunks(P, C) * 3 * C /*part*/ +
-           static_cast<size_t>(B) * 2 * C /*UV*/ + static_cast<size_t>(B) * G * 2 /*gm*/ + 64;
+           static_cast<size_t>(B) * 2 * C /*UV*/ + static_cast<size_t>(B) * GB_CHUNKS_MAX * G * 2 /*gm, statistics partials*/ + 64;
 }
 
 cudaError_t groupnorm_silu_bwd_run(const GroupNormBwdArgs& a, float* scratch, cudaStream_t s) {
@@ -334,7 +367,8 @@ cudaError_t groupnorm_silu_bwd_run(const GroupNormBwdArgs& a, float* scratch, cu
     float* gm = UV + static_cast<size_t>(B) * 2 * C;
     const uint4* y = reinterpret_cast<const uint4*>(a.y);
     const uint4* ds = reinterpret_cast<const uint4*>(a.ds);
-    gn_stats_kernel<<<dim3(G, B), 256, 0, s>>>(y, P, C, a.eps, stats);
+    gn_stats_part_kernel<<<dim3(nchunk, B), 256, 0, s>>>(y, P, C, nchunk, reinterpret_cast<float2*>(gm));   // gm is free until the coefficient pass
+    gn_stats_finish_kernel<<<B, 32, 0, s>>>(reinterpret_cast<const float2*>(gm), nchunk, P, C, a.eps, stats);
     gn_bwd_sums_kernel<<<dim3(nchunk, B), 256, static_cast<size_t>(lanes) * 3 * C * sizeof(float), s>>>(
         y, ds, stats, a.gamma, a.beta, a.scale, a.shift, ld, P, C, nchunk, part);
     gn_bwd_coef_kernel<<<B, 512, 0, s>>>(part, nchunk, a.gamma, a.beta, a.scale, ld, P, C, UV, gm, a.dscale, a.dshift, a.dpost);
@@ -348,9 +382,15 @@ int ln_bwd_blocks(long long M) { return static_cast<int>(M / 8 < 592 ? (M + 7) /
 
 cudaError_t channel_layernorm_bwd_run(const bf16* x, const bf16* dz, const float* gain, long long M, int C, float eps, bf16* dx,
                                       float* dgain, float* part, cudaStream_t s) {
-    if (C % 32 != 0 || C > 512) return cudaErrorInvalidValue;
     const int blocks = ln_bwd_blocks(M);
-    ln_bwd_kernel<<<blocks, 256, static_cast<size_t>(8) * C * sizeof(float), s>>>(x, dz, gain, M, C, eps, dx, part);
+    const size_t smem = static_cast<size_t>(8) * C * sizeof(float);
+    switch (C) {
+        case 64: ln_bwd_kernel<2, 4><<<blocks, 256, smem, s>>>(x, dz, gain, M, eps, dx, part); break;
+        case 128: ln_bwd_kernel<4, 4><<<blocks, 256, smem, s>>>(x, dz, gain, M, eps, dx, part); break;
+        case 256: ln_bwd_kernel<8, 2><<<blocks, 256, smem, s>>>(x, dz, gain, M, eps, dx, part); break;
+        case 512: ln_bwd_kernel<16, 1><<<blocks, 256, smem, s>>>(x, dz, gain, M, eps, dx, part); break;
+        default: return cudaErrorInvalidValue;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     sum_rows_kernel<<<(C + 255) / 256, 256, 0, s>>>(part, blocks, C, dgain);

@@ -8,6 +8,7 @@
 // Parameters are bound by pointer (the caller's fp32 tensors are read in place every step, so a stock torch optimizer
 // keeps working) and gradients are written into caller-provided fp32 buffers.  Activations are bf16 NHWC; the convs run on
 // tcgen05 (conv_gemm.cu forward and data gradient, wgrad.cu weight gradient); statistics-free glue is in train_kernels.cu.
+#include <algorithm>
 #include <cstring>
 
 #include "trainer_internal.h"
@@ -380,6 +381,7 @@ int hd_trainer_profile(hd_trainer* t, int32_t reps, char* buf, int64_t buflen, v
     T_TRY(cudaEventCreate(&e1));
     std::map<std::string, std::pair<double, double>> fam;   // kernel family -> (ms, flops)
     std::map<std::string, int> cnt;
+    std::vector<std::pair<double, std::string>> slow;        // (ms, tag) of every op, for the "top" list
     for (const TOp& op : t->ops) {
         cudaError_t e = op.fn(s);
         if (e == cudaSuccess) e = cudaEventRecord(e0, s);
@@ -392,6 +394,7 @@ int hd_trainer_profile(hd_trainer* t, int32_t reps, char* buf, int64_t buflen, v
             cudaEventDestroy(e0); cudaEventDestroy(e1);
             return tfail("profiling '%s' failed: %s", op.tag.c_str(), cudaGetErrorString(e));
         }
+        slow.push_back({ms / reps, op.tag});
         fam[op.kernel].first += ms / reps;
         fam[op.kernel].second += op.flops;
         cnt[op.kernel] += 1;
@@ -406,7 +409,14 @@ int hd_trainer_profile(hd_trainer* t, int32_t reps, char* buf, int64_t buflen, v
         out += line;
         first = false;
     }
-    out += "}";
+    std::sort(slow.begin(), slow.end(), [](const std::pair<double, std::string>& a, const std::pair<double, std::string>& b) { return a.first > b.first; });
+    out += ",\"_top\":{";
+    for (size_t i = 0; i < slow.size() && i < 24; ++i) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s\"%s\":{\"ms\":%.6f,\"flops\":0,\"ops\":1}", i ? "," : "", slow[i].second.c_str(), slow[i].first);
+        out += line;
+    }
+    out += "}}";
     if (static_cast<int64_t>(out.size()) + 1 > buflen) return tfail("hd_trainer_profile: buffer too small");
     memcpy(buf, out.c_str(), out.size() + 1);
     return 0;

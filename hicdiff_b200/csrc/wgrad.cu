@@ -365,8 +365,8 @@ int wgrad_general_prepare(const bf16* g, const bf16* x, int B, int H, int W, int
     out->kb_total = B * H / rows;
     const int units = out->taps * out->mtiles * out->ntiles;
     int ns = (2 * num_sms + units - 1) / units;             // about two waves of CTAs
-    if (ns > out->kb_total / 2) ns = out->kb_total / 2;
-    if (ns < 1) ns = 1;
+    if (ns > out->kb_total / 32) ns = out->kb_total / 32;   // >= 32 K blocks per CTA: below that the fp32 partials (written, then re-read
+    if (ns < 1) ns = 1;                                      // by the reduction) cost more than the parallelism buys on the low-resolution levels
     if (ns > 32) ns = 32;
     out->nsplit = ns;
     out->part = nullptr;

@@ -157,8 +157,13 @@ class _TrainStep(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         tr = ctx.trainer
-        grads = tuple(gout * tr.grads[k] for k in ctx.names)   # fresh tensors: the trainer's buffers are rewritten every step
-        return (None,) * 7 + grads
+        flat = gout * tr.flat_grad            # ONE launch; a fresh tensor (the trainer's buffer is rewritten every step)
+        grads, off = [], 0
+        for k in ctx.names:
+            g = tr.grads[k]
+            grads.append(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        return (None,) * 7 + tuple(grads)
 
 
 def supports_training(net) -> bool:

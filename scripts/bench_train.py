@@ -89,6 +89,8 @@ def main():
                "device_bytes": net._trainer.device_bytes(), "launch_groups": net._trainer.num_launch_groups()}
         if a.profile:
             prof = net._trainer.profile(3)
+            top = prof.pop("_top", {})
+            out["slowest_ops_ms"] = {k: round(v["ms"], 4) for k, v in top.items()}
             out["families"] = {k: {"ms": round(v["ms"], 4), "ops": v["ops"], "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1)}
                                for k, v in prof.items()}
             out["families_total_ms"] = round(sum(v["ms"] for v in prof.values()), 3)
