@@ -150,49 +150,105 @@ la_t_kernel(const bf16* __restrict__ qkv, int n, const float* __restrict__ kmax,
     }
 }
 
-// ---- pass 4: the gradients.  grid (chunks, B * HEADS); per pixel one warp
-__global__ void __launch_bounds__(256, 2)     // <= 128 registers: two CTAs per SM (ncu: at 159 registers one CTA / SM left the kernel latency-bound)
+// ---- pass 4: the gradients.  grid (chunks, B * HEADS); ONE THREAD PER PIXEL: its q / k / v / d_out rows (32 values each) live in
+// registers, the 32 x 32 matrices are read from shared memory as 16-byte broadcasts, so there is no cross-lane traffic at all.
+// (The first version -- one warp per pixel, lane = d, 96 shuffles per pixel -- ran at 12 % occupancy on 159 registers and was
+// latency-bound: profiles/r01_train_unet_linattn_bwd_ncu.md.)
+__device__ __forceinline__ void load_row32(const bf16* p, float (&v)[DH]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + i);
+        float2 t;
+        t = ptx::unpack_bf16x2(u.x); v[8 * i] = t.x; v[8 * i + 1] = t.y;
+        t = ptx::unpack_bf16x2(u.y); v[8 * i + 2] = t.x; v[8 * i + 3] = t.y;
+        t = ptx::unpack_bf16x2(u.z); v[8 * i + 4] = t.x; v[8 * i + 5] = t.y;
+        t = ptx::unpack_bf16x2(u.w); v[8 * i + 6] = t.x; v[8 * i + 7] = t.y;
+    }
+}
+__device__ __forceinline__ void store_row32(bf16* p, const float (&v)[DH]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = ptx::pack_bf16x2(v[8 * i], v[8 * i + 1]); u.y = ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+        u.z = ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); u.w = ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+        reinterpret_cast<uint4*>(p)[i] = u;
+    }
+}
+// out[r] = sum_c m[r][c] * x[c], m row-major [32][32] in shared memory (every thread reads the same addresses: broadcasts)
+__device__ __forceinline__ void matvec32(const float* __restrict__ m, const float (&x)[DH], float (&out)[DH]) {
+#pragma unroll
+    for (int r = 0; r < DH; ++r) {
+        const float4* row = reinterpret_cast<const float4*>(m + r * DH);
+        float acc = 0.f;
+#pragma unroll
+        for (int c4 = 0; c4 < DH / 4; ++c4) {
+            const float4 w = row[c4];
+            acc = fmaf(w.x, x[4 * c4], acc); acc = fmaf(w.y, x[4 * c4 + 1], acc);
+            acc = fmaf(w.z, x[4 * c4 + 2], acc); acc = fmaf(w.w, x[4 * c4 + 3], acc);
+        }
+        out[r] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(128)
 la_grad_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, int n, float scale, const float* __restrict__ kmax,
                const float* __restrict__ ksum, const float* __restrict__ cd, const float* __restrict__ tvec, bf16* __restrict__ dqkv) {
-    __shared__ float s_ctx[DH][DH + 1], s_dctx[DH][DH + 1];
+    __shared__ __align__(16) float s_ctx[DH * DH], s_dctx[DH * DH], s_dctxT[DH * DH];
+    __shared__ float s_km[DH], s_kinv[DH], s_t[DH];
     const int bh = blockIdx.y, b = bh / HEADS, h = bh % HEADS;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < DH * DH; i += 256) {
-        s_ctx[i / DH][i % DH] = cd[static_cast<size_t>(bh) * 2 * DH * DH + i];
-        s_dctx[i / DH][i % DH] = cd[(static_cast<size_t>(bh) * 2 + 1) * DH * DH + i];
+    for (int i = threadIdx.x; i < DH * DH; i += blockDim.x) {
+        const float c = cd[static_cast<size_t>(bh) * 2 * DH * DH + i];
+        const float d = cd[(static_cast<size_t>(bh) * 2 + 1) * DH * DH + i];
+        s_ctx[i] = c;                                   // [d][e]
+        s_dctx[i] = d;                                  // [d][e]
+        s_dctxT[(i % DH) * DH + i / DH] = d;            // [e][d]
+    }
+    if (threadIdx.x < DH) {
+        s_km[threadIdx.x] = kmax[bh * DH + threadIdx.x];
+        s_kinv[threadIdx.x] = 1.0f / ksum[bh * DH + threadIdx.x];
+        s_t[threadIdx.x] = tvec[bh * DH + threadIdx.x];
     }
     __syncthreads();
     const int per = (n + gridDim.x - 1) / gridDim.x;
     const int p0 = blockIdx.x * per, p1 = min(n, p0 + per);
-    const bf16* base = qkv + static_cast<size_t>(b) * n * QKV_LD + h * DH + lane;
-    const bf16* dob = dout + static_cast<size_t>(b) * n * OUT_LD + h * DH + lane;
-    bf16* ob = dqkv + static_cast<size_t>(b) * n * QKV_LD + h * DH + lane;
-    const float km = kmax[bh * DH + lane], kinv = 1.0f / ksum[bh * DH + lane];
-    const float tl = tvec[bh * DH + lane];
     const float inv_n = 1.0f / static_cast<float>(n);
-    float crow[DH], drow[DH], dcol[DH];      // ctx[lane][e], dctx[lane][e] (lane = d); dctx[d][lane] (lane = e)
-#pragma unroll
-    for (int e = 0; e < DH; ++e) { crow[e] = s_ctx[lane][e]; drow[e] = s_dctx[lane][e]; dcol[e] = s_dctx[e][lane]; }
-    for (int p = p0 + warp; p < p1; p += 8) {
+    const bf16* base = qkv + static_cast<size_t>(b) * n * QKV_LD + h * DH;
+    const bf16* dob = dout + static_cast<size_t>(b) * n * OUT_LD + h * DH;
+    bf16* ob = dqkv + static_cast<size_t>(b) * n * QKV_LD + h * DH;
+    for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
         const size_t ro = static_cast<size_t>(p) * QKV_LD;
-        const float q = __bfloat162float(base[ro]);
-        const float k = __bfloat162float(base[ro + HEADS * DH]);
-        const float v = __bfloat162float(base[ro + 2 * HEADS * DH]) * inv_n;
-        const float go = __bfloat162float(dob[static_cast<size_t>(p) * OUT_LD]);      // lane = e
-        const float qe = __expf(q - warp_max(q));
-        const float qsm = qe / warp_sum(qe);                    // softmax_d(q), lane = d
-        const float ks = __expf(k - km) * kinv;                 // lane = d
-        float dqs = 0.f, dks = 0.f, dv = 0.f;
+        float x[DH], y[DH], o[DH];
+        // dq = s * softmax_d(q) o (dqs - <dqs, softmax_d(q)>),  dqs[d] = sum_e dout[e] ctx[d][e]
+        load_row32(dob + static_cast<size_t>(p) * OUT_LD, x);       // d_out[e]
+        matvec32(s_ctx, x, o);                                       // dqs[d]
+        load_row32(base + ro, y);                                    // q[d]
+        float m = y[0];
 #pragma unroll
-        for (int e = 0; e < DH; ++e) {
-            dqs = fmaf(__shfl_sync(0xffffffffu, go, e), crow[e], dqs);      // lane = d
-            dks = fmaf(__shfl_sync(0xffffffffu, v, e), drow[e], dks);       // lane = d
-            dv = fmaf(__shfl_sync(0xffffffffu, ks, e), dcol[e], dv);        // lane = e (loop index plays d)
-        }
-        const float dot = warp_sum(dqs * qsm);
-        ob[ro] = __float2bfloat16(scale * qsm * (dqs - dot));
-        ob[ro + HEADS * DH] = __float2bfloat16(ks * (dks - tl));
-        ob[ro + 2 * HEADS * DH] = __float2bfloat16(dv * inv_n);
+        for (int d = 1; d < DH; ++d) m = fmaxf(m, y[d]);
+        float sum = 0.f;
+#pragma unroll
+        for (int d = 0; d < DH; ++d) { y[d] = __expf(y[d] - m); sum += y[d]; }
+        const float inv = 1.0f / sum;
+        float dot = 0.f;
+#pragma unroll
+        for (int d = 0; d < DH; ++d) { y[d] *= inv; dot = fmaf(o[d], y[d], dot); }
+#pragma unroll
+        for (int d = 0; d < DH; ++d) o[d] = scale * y[d] * (o[d] - dot);
+        store_row32(ob + ro, o);
+        // dk = ks o (dks - t),  dks[d] = sum_e vs[e] dctx[d][e]
+        load_row32(base + ro + 2 * HEADS * DH, x);                  // v[e]
+#pragma unroll
+        for (int e = 0; e < DH; ++e) x[e] *= inv_n;
+        matvec32(s_dctx, x, o);                                      // dks[d]
+        load_row32(base + ro + HEADS * DH, y);                       // k[d]
+#pragma unroll
+        for (int d = 0; d < DH; ++d) { y[d] = __expf(y[d] - s_km[d]) * s_kinv[d]; o[d] = y[d] * (o[d] - s_t[d]); }
+        store_row32(ob + ro + HEADS * DH, o);
+        // dv[e] = (1 / n) sum_d ks[d] dctx[d][e]
+        matvec32(s_dctxT, y, o);
+#pragma unroll
+        for (int e = 0; e < DH; ++e) o[e] *= inv_n;
+        store_row32(ob + ro + 2 * HEADS * DH, o);
     }
 }
 
@@ -286,8 +342,8 @@ cudaError_t linear_attention_bwd_run(const bf16* qkv, const bf16* dout, bf16* dq
     la_reduce_kernel<<<bh, 256, 0, s>>>(cpart, 2 * DH * DH, cd);
     la_t_kernel<<<dim3(LAB_SPLIT, bh), 256, 0, s>>>(qkv, n, kmax, ksum, cd, tpart);
     la_reduce_kernel<<<bh, 32, 0, s>>>(tpart, DH, tv);
-    const int chunks = n >= 1024 ? 8 : (n >= 256 ? 4 : 1);
-    la_grad_kernel<<<dim3(chunks, bh), 256, 0, s>>>(qkv, dout, n, scale, kmax, ksum, cd, tv, dqkv);
+    const int chunks = (n + 127) / 128;     // one pixel per thread, 128 threads per CTA
+    la_grad_kernel<<<dim3(chunks, bh), 128, 0, s>>>(qkv, dout, n, scale, kmax, ksum, cd, tv, dqkv);
     return cudaGetLastError();
 }
 
