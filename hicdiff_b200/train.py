@@ -172,13 +172,23 @@ def supports_training(net) -> bool:
 
 
 def training_loss(net, x_t, time, cond, target, weight, loss_type: str):
-    """Scalar loss with a grad_fn over `net.parameters()` (named_parameters order)."""
+    """Scalar loss with a grad_fn over `net.parameters()` (named_parameters order).  One trainer is kept per batch size (an
+    epoch's ragged last batch must not evict the main one); all are rebuilt if the parameters move (`.to()`, new storage)."""
     batch = x_t.shape[0]
-    tr = getattr(net, "_trainer", None)
+    cache = getattr(net, "_trainers", None)
+    if cache is None:
+        cache = {}
+        object.__setattr__(net, "_trainers", cache)
+    tr = cache.get(batch)
     if tr is None or not tr.matches(net, batch):
-        if tr is not None:
-            tr.destroy()
+        if any(not t.matches(net, t.batch) for t in cache.values()):
+            for t in cache.values():
+                t.destroy()
+            cache.clear()
+        while len(cache) >= 2:                       # at most two batch sizes resident (activations are GBs per trainer)
+            cache.pop(next(iter(cache))).destroy()
         tr = Trainer(net, batch)
-        object.__setattr__(net, "_trainer", tr)
+        cache[batch] = tr
+    object.__setattr__(net, "_trainer", tr)      # the most recently used one (benchmarks / introspection)
     params = [p for _, p in net.named_parameters()]
     return _TrainStep.apply(tr, x_t, cond, time, target, weight, loss_type, *params)

@@ -181,3 +181,43 @@ def test_drosophila_like_tile_budget():
 
     lib = _lib.load()
     assert sum(lib.hd_tile_count(n, 64, 4) for n in (588, 632, 703, 802, 34, 588)) == 221
+
+
+def _allreduce_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from hicdiff_b200 import train as T
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        flat = torch.arange(10, dtype=torch.float32) * (rank + 1)          # what a trainer's flat gradient buffer would hold
+        T.allreduce_mean_(flat)
+        q.put((rank, flat.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_mean_world2_gloo():
+    """The data-parallel exchange of the training step (BASELINE config 5): ONE all-reduce of the flat gradient buffer, averaged."""
+    import socket
+    import torch.multiprocessing as mp
+
+    from hicdiff_b200 import train as T
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_allreduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = [i * 1.5 for i in range(10)]                                       # mean of 1x and 2x
+    assert got[0] == want and got[1] == want
+    solo = torch.ones(4)
+    assert T.allreduce_mean_(solo) is solo and solo.tolist() == [1.0] * 4     # no process group: a no-op
