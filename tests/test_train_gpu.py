@@ -406,3 +406,32 @@ def test_unet_sr3_loss_backward_matches_oracle():
     print(f"unet_sr3: loss {float(loss.detach()):.6f} (oracle {float(o_loss):.6f}); worst grad rel-RMS: {top}")
     bad = {k: v for k, v in worst.items() if v > 5e-2}
     assert not bad, f"gradient rel-RMS above 5e-2: {bad}"
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_training_step_ragged_batches(B):
+    """An epoch's last batch is ragged: B = 1 and B = 3 through both trainers (loss and a sample of gradients vs the oracle);
+    trainers for two batch sizes stay resident side by side."""
+    from hicdiff_b200 import hicdiff_condition
+    from hicdiff_b200.model.hicedrn_Diff import hicedrn_Diff
+
+    clean, noisy = O.synthetic_tiles(B, seed=77)
+    t = torch.tensor([5, 400, 999][:B], dtype=torch.long)
+    noise = torch.randn(B, 1, 64, 64, generator=torch.Generator().manual_seed(3))
+    buf = O.diffusion_buffers("linear", 1000)
+    for kind in ("hicedrn", "unet"):
+        torch.manual_seed(1)
+        net = hicedrn_Diff(number_resnet=1, self_condition=True) if kind == "hicedrn" else hicdiff_condition.Unet(dim=64, dim_mults=(1, 2, 4, 8), self_condition=True)
+        sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        o_loss, o_grads = O.p_losses_and_grads(sd, buf, noisy, clean, t, noise, loss_type="l2", self_condition=True, num_blocks=1, net=kind)
+        diff = hicdiff_condition.GaussianDiffusion(net, image_size=64, timesteps=1000, loss_type="l2", beta_schedule="linear").to(DEV)
+        loss = diff.p_losses([noisy.to(DEV), clean.to(DEV)], t=t.to(DEV), noise=noise.to(DEV))
+        loss.backward()
+        assert abs(float(loss.detach()) - float(o_loss)) <= 5e-3 * abs(float(o_loss)), (kind, B, float(loss.detach()), float(o_loss))
+        worst = max(_rel(p.grad, o_grads[k]) for k, p in net.named_parameters())
+        assert worst <= 6e-2, (kind, B, worst)
+        # a second batch size keeps its own trainer; the first one is still there
+        if B == 3:
+            l1 = diff.p_losses([noisy[:1].to(DEV), clean[:1].to(DEV)], t=t[:1].to(DEV), noise=noise[:1].to(DEV))
+            l1.backward()
+            assert sorted(net._trainers) == [1, 3]
