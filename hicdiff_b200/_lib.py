@@ -46,6 +46,8 @@ SIGNATURES = {
     "hd_sample": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _u64, _u64, _i32, _i32, _vp]),
     "hd_ddrm_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                C.c_float, _i64, _u64, _u64, C.c_uint32, _vp]),
+    "hd_ddim_step": (C.c_int, [_vp, _vp, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _i32, _i64, _u64, _u64,
+                               C.c_uint32, _vp]),
     "hd_ssim_mse_tiles": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "hd_trainer_create": (C.c_int, [C.POINTER(hd_config), _i32, C.POINTER(_vp)]),
     "hd_trainer_bind": (C.c_int, [_vp, C.c_char_p, _vp, _vp, C.POINTER(_i64), _i32]),

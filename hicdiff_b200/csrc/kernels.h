@@ -249,6 +249,22 @@ struct DdrmArgs {
 };
 cudaError_t ddrm_step_run(const DdrmArgs& a, cudaStream_t s);
 
+// One DDIM step (ddim_sample, hicdiff.py:623-664): x0 = clamp(sr * x - srm1 * eps, -1, 1); last step: x = x0; else
+// x = x0 * sqrt_a_next + c * eps + sigma * z
+struct DdimArgs {
+    float* x;               // [n] in: x_t, out: x_{t_next}
+    const float* eps;       // [n]
+    const float* noise;     // [n] z of this step, or nullptr -> Philox(seed, tile, step_id)
+    float* x0_out;          // optional clipped x_start
+    float sr, srm1, sqrt_a_next, c, sigma;
+    int last;               // 1: time_next < 0
+    long long n;
+    int tile_elems;
+    unsigned long long seed, tile_offset;
+    unsigned int step_id;
+};
+cudaError_t ddim_step_run(const DdimArgs& a, cudaStream_t s);
+
 cudaError_t philox_normal_run(float* out, long long n, unsigned long long seed, unsigned long long tile_offset,
                               int tile_elems, unsigned long long stream_id, cudaStream_t s);
 cudaError_t step_advance_run(SampleCtl* ctl, int delta, cudaStream_t s);

@@ -1104,6 +1104,17 @@ int hd_ddrm_step(float* x, const float* eps, const float* y, const float* noise,
     return 0;
 }
 
+int hd_ddim_step(float* x, const float* eps, const float* noise, float* x0_out, float sqrt_recip, float sqrt_recipm1, float sqrt_a_next,
+                 float c, float sigma, int32_t last, int64_t n, uint64_t seed, uint64_t tile_offset, uint32_t step_id, void* stream) {
+    if (!x || !eps || n <= 0) return fail("hd_ddim_step: bad argument");
+    DdimArgs a;
+    a.x = x; a.eps = eps; a.noise = noise; a.x0_out = x0_out;
+    a.sr = sqrt_recip; a.srm1 = sqrt_recipm1; a.sqrt_a_next = sqrt_a_next; a.c = c; a.sigma = sigma; a.last = last ? 1 : 0;
+    a.n = n; a.tile_elems = 4096; a.seed = seed; a.tile_offset = tile_offset; a.step_id = step_id;
+    CUDA_TRY(ddim_step_run(a, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
 int hd_ssim_mse_tiles(const float* a, const float* b, const float* window121, float* ssim_out, float* mse_out, int32_t B,
                       int32_t rescale, void* stream) {
     if (B < 0) return fail("hd_ssim_mse_tiles: negative tile count");

@@ -386,7 +386,45 @@ ddrm_step_kernel(const DdrmArgs a) {
     if (a.x0_out != nullptr) *reinterpret_cast<float4*>(a.x0_out + i4) = make_float4(x0s[0], x0s[1], x0s[2], x0s[3]);
 }
 
+// ddim_sample (hicdiff.py:623-664 / hicdiff_condition.py:625-668), same operation order as the reference:
+// x_start = clamp(extract(sqrt_recip) * x - extract(sqrt_recipm1) * eps) (:526-530, clip_x_start); img = x_start * sqrt(alpha_next)
+// + c * pred_noise + sigma * noise (:655-657); the last pair (time_next < 0) returns x_start.
+__global__ void __launch_bounds__(256)
+ddim_step_kernel(const DdimArgs a) {
+    const long long i4 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= a.n) return;
+    const float4 x = *reinterpret_cast<const float4*>(a.x + i4);
+    const float4 e = *reinterpret_cast<const float4*>(a.eps + i4);
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!a.last) {
+        if (a.noise != nullptr) {
+            z = __ldg(reinterpret_cast<const float4*>(a.noise + i4));
+        } else {
+            const unsigned long long tile = a.tile_offset + static_cast<unsigned long long>(i4 / a.tile_elems);
+            z = philox_normal4(a.seed, tile, static_cast<uint32_t>((i4 % a.tile_elems) >> 2), a.step_id + 1u);
+        }
+    }
+    const float xs[4] = {x.x, x.y, x.z, x.w}, es[4] = {e.x, e.y, e.z, e.w}, zs[4] = {z.x, z.y, z.z, z.w};
+    float o[4], x0s[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float x0 = __fsub_rn(__fmul_rn(a.sr, xs[j]), __fmul_rn(a.srm1, es[j]));
+        x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+        x0s[j] = x0;
+        o[j] = a.last ? x0 : __fadd_rn(__fadd_rn(__fmul_rn(x0, a.sqrt_a_next), __fmul_rn(a.c, es[j])), __fmul_rn(a.sigma, zs[j]));
+    }
+    *reinterpret_cast<float4*>(a.x + i4) = make_float4(o[0], o[1], o[2], o[3]);
+    if (a.x0_out != nullptr) *reinterpret_cast<float4*>(a.x0_out + i4) = make_float4(x0s[0], x0s[1], x0s[2], x0s[3]);
+}
+
 }  // namespace
+
+cudaError_t ddim_step_run(const DdimArgs& a, cudaStream_t s) {
+    if (a.n % 4 != 0 || a.tile_elems % 4 != 0) return cudaErrorInvalidValue;
+    const int grid = static_cast<int>((a.n / 4 + 255) / 256);
+    ddim_step_kernel<<<grid, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
 
 cudaError_t stem_conv_run(const StemConvArgs& a, cudaStream_t s) {
     if (a.W != STEM_W || a.H % STEM2_CTA_ROWS != 0 || a.Cout % 64 != 0 || a.Cin < 1 || a.Cin > 2 || (a.ksize != 3 && a.ksize != 7))

@@ -76,7 +76,7 @@ stem_wgrad_kernel(const bf16* __restrict__ G, const float* __restrict__ u0, cons
     const int rg = blockIdx.x, b = blockIdx.y, ky = blockIdx.z, c = threadIdx.x;
     const int nk = u1 != nullptr ? 2 : 1;
     const int y0 = rg * ROWS;
-    for (int i = threadIdx.x; i < nk * ROWS * pitch; i += 256) {
+    for (int i = threadIdx.x; i < nk * ROWS * pitch; i += blockDim.x) {
         const int k = i / (ROWS * pitch), rem = i - k * ROWS * pitch;
         const int yy = y0 + rem / pitch + ky - pad, xx = rem % pitch - pad;
         const float* u = k == 0 ? u0 : u1;
@@ -195,7 +195,7 @@ cudaError_t stem_wgrad_run(const bf16* G, const float* u0, const float* u1, int 
     if (C > 256 || ksize > 7 || (ksize & 1) == 0) return cudaErrorInvalidValue;
     const int nk = u1 != nullptr ? 2 : 1;
     const size_t smem = static_cast<size_t>(nk) * 8 * (64 + ksize - 1) * sizeof(float);
-    stem_wgrad_kernel<<<dim3(8, B, ksize), 256, smem, s>>>(G, u0, u1, C, ksize, part);
+    stem_wgrad_kernel<<<dim3(8, B, ksize), (C + 31) / 32 * 32, smem, s>>>(G, u0, u1, C, ksize, part);   // one thread per channel
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int n = nk * ksize * ksize * C;

@@ -103,9 +103,6 @@ class _GaussianDiffusionBase(nn.Module):
         assert self.sampling_timesteps <= timesteps
         self.is_ddim_sampling = self.sampling_timesteps < timesteps
         self.ddim_sampling_eta = ddim_sampling_eta
-        if self.is_ddim_sampling:
-            raise NotImplementedError("DDIM sampling (sampling_timesteps < timesteps) is not used by any reference "
-                                      "script and is not built")
         post_var = betas * (1.0 - abar_prev) / (1.0 - abar)
         vals = {
             "betas": betas,
@@ -239,10 +236,64 @@ class _GaussianDiffusionBase(nn.Module):
         return self.unnormalize([cond] + list(trace.unbind(0)))  # hicdiff_condition.py:607,617,620
 
     @torch.no_grad()
+    def ddim_sample(self, shape, return_all_timesteps=False, noise=None):
+        """DDIM sampling (hicdiff.py:623-664, hicdiff_condition.py:625-668): `sampling_timesteps` strided steps, one eps-net
+        call + one `hd_ddim_step` each.  `noise`: optional list / tensor of the draws the reference would make (x_T, then one z
+        per step except the last).  Like the reference, this only works for eps-nets without self-conditioning (there the
+        reference feeds its own x_start -- None on the first step -- to torch.cat)."""
+        from . import _lib
+
+        if self.self_condition:
+            raise NotImplementedError("ddim_sample needs self_condition=False (the reference's version cannot run with it either)")
+        if self._flavour == "sr3":
+            raise NotImplementedError("the SR3 flavour has no DDIM sampler in the reference")
+        batch = shape[0]
+        dev = self.betas.device
+        if dev.type != "cuda":
+            raise RuntimeError("hicdiff_b200 runs on sm_100a GPUs only (there is no CPU fallback)")
+        T, S, eta = self.num_timesteps, self.sampling_timesteps, self.ddim_sampling_eta
+        times = list(reversed(torch.linspace(-1, T - 1, steps=S + 1).int().tolist()))
+        pairs = list(zip(times[:-1], times[1:]))
+        draws = iter(noise) if noise is not None else None
+        seed = 0 if noise is not None else self._next_seed(None)
+        if draws is not None:
+            img = next(draws).to(dev, torch.float32).contiguous().clone()
+        else:
+            from .ops import philox_normal
+
+            img = philox_normal(batch, seed, 0, device=dev)
+        imgs = [img.clone()] if return_all_timesteps else None
+        lib = _lib.load()
+        ac = self.alphas_cumprod.detach().cpu()
+        sr, srm1 = self.sqrt_recip_alphas_cumprod.detach().cpu(), self.sqrt_recipm1_alphas_cumprod.detach().cpu()
+        for k, (t, t_next) in enumerate(pairs):
+            eps = self.model(img, torch.full((batch,), t, device=dev, dtype=torch.long), None)
+            last = t_next < 0
+            if last:
+                san = c = sigma = 0.0
+            else:
+                alpha, alpha_next = ac[t], ac[t_next]                          # the reference's fp32 expressions :648-652
+                sg = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+                c = float((1 - alpha_next - sg ** 2).sqrt())
+                san, sigma = float(alpha_next.sqrt()), float(sg)
+            z = None
+            if not last and draws is not None:
+                z = next(draws).to(dev, torch.float32).contiguous()
+            with torch.cuda.device(dev):
+                _lib.check(lib.hd_ddim_step(img.data_ptr(), eps.data_ptr(), _lib.ptr(z), None, float(sr[t]), float(srm1[t]), san, c, sigma,
+                                            1 if last else 0, img.numel(), int(seed), 0, k, _lib.stream_ptr()), "hd_ddim_step")
+            if imgs is not None:
+                imgs.append(img.clone())
+        ret = img if not return_all_timesteps else torch.stack(imgs, dim=1)
+        return self.unnormalize(ret)
+
+    @torch.no_grad()
     def sample(self, x, return_all_timesteps=False, noise=None):
         b = x.shape[0]
-        return self.p_sample_loop((b, self.channels, self.image_size, self.image_size),
-                                  return_all_timesteps=return_all_timesteps, noise=noise)
+        shape = (b, self.channels, self.image_size, self.image_size)
+        if self.is_ddim_sampling:                                   # hicdiff.py:670-673
+            return self.ddim_sample(shape, return_all_timesteps=return_all_timesteps, noise=noise)
+        return self.p_sample_loop(shape, return_all_timesteps=return_all_timesteps, noise=noise)
 
     @torch.no_grad()
     def super_resolution(self, x_in, continous=False, noise=None):

@@ -114,6 +114,14 @@ HD_API int hd_ddrm_step(float* x, const float* eps, const float* y, const float*
                  float sqrt_1m_at, float sqrt_at_next, float c0, float c1, float c2, float sigma_0, int64_t n, uint64_t seed,
                  uint64_t tile_offset, uint32_t step_id, void* stream);
 
+/* One step of DDIM sampling given eps = model(x_t, t): replaces the loop body of ddim_sample (src/hicdiff.py:636-659,
+ * src/hicdiff_condition.py:639-664): x_start = clamp(sqrt_recip * x - sqrt_recipm1 * eps, -1, 1); last != 0 (time_next < 0):
+ * x = x_start; else x = x_start * sqrt_a_next + c * eps + sigma * z.  The five scalars are the caller's fp32 evaluations of the
+ * reference expressions (:648-657).  noise: this step's z or NULL for Philox(seed, tile_offset + tile, step_id); n = B * 4096. */
+HD_API int hd_ddim_step(float* x, const float* eps, const float* noise, float* x0_out, float sqrt_recip, float sqrt_recipm1,
+                 float sqrt_a_next, float c, float sigma, int32_t last, int64_t n, uint64_t seed, uint64_t tile_offset,
+                 uint32_t step_id, void* stream);
+
 /* Per-tile SSIM and MSE of fp32 [B,1,64,64] tiles: _ssim of src/Utils/loss/SSIM.py:17-36 with the caller's 11x11 window
  * (create_window :10-14, 121 floats on the device) and zero "same" padding; rescale = 1 first applies
  * inverse_data_transform('rescaled') (src/datasets/__init__.py:214-223).  ssim_out / mse_out: fp32 [B] on the device; the

@@ -337,6 +337,29 @@ def p_sample_loop(eps_fn, buf: SD, cond, noise: torch.Tensor, *, timesteps: int,
     return (img, trace) if return_all else img
 
 
+def ddim_sample(eps_fn, buf: SD, noise, *, timesteps: int, sampling_timesteps: int, eta: float = 0.0, return_all=False):
+    """ddim_sample src/hicdiff.py:623-664 with the draws supplied: noise[0] = x_T, then one z per step except the last."""
+    times = list(reversed(torch.linspace(-1, timesteps - 1, steps=sampling_timesteps + 1).int().tolist()))
+    draws = iter(noise)
+    img = next(draws).clone()
+    imgs = [img]
+    for time, time_next in zip(times[:-1], times[1:]):
+        t = torch.full((img.shape[0],), time, dtype=torch.long)
+        pred_noise = eps_fn(img, t, None)
+        x_start = _extract(buf["sqrt_recip_alphas_cumprod"], t, img.shape) * img - _extract(buf["sqrt_recipm1_alphas_cumprod"], t, img.shape) * pred_noise
+        x_start = torch.clamp(x_start, min=-1.0, max=1.0)
+        if time_next < 0:
+            img = x_start
+            imgs.append(img)
+            continue
+        alpha, alpha_next = buf["alphas_cumprod"][time], buf["alphas_cumprod"][time_next]
+        sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+        c = (1 - alpha_next - sigma ** 2).sqrt()
+        img = x_start * alpha_next.sqrt() + c * pred_noise + sigma * next(draws)
+        imgs.append(img)
+    return torch.stack(imgs, dim=1) if return_all else img
+
+
 def q_sample(buf: SD, x_start, t, noise):  # :698-704
     return _extract(buf["sqrt_alphas_cumprod"], t, x_start.shape) * x_start + \
         _extract(buf["sqrt_one_minus_alphas_cumprod"], t, x_start.shape) * noise
