@@ -82,8 +82,8 @@ class _GaussianDiffusionBase(nn.Module):
         beta_schedule = self._default_schedule if beta_schedule is None else beta_schedule
         if objective not in {"pred_noise", "pred_x0", "pred_v"}:
             raise AssertionError("objective must be pred_noise, pred_x0 or pred_v")
-        if objective != "pred_noise":
-            raise NotImplementedError("only objective='pred_noise' is used by the reference scripts and built here")
+        if objective != "pred_noise" and self._flavour == "sr3":
+            raise NotImplementedError("objective != 'pred_noise' is built for the conditional / unconditional flavours only")
         if image_size != 64:
             raise NotImplementedError("the sm_100a path is built for the reference's 64x64 tiles (image_size=64)")
 
@@ -150,12 +150,27 @@ class _GaussianDiffusionBase(nn.Module):
             return self.sqrt_alphas_cumprod_prev[1:T + 1].to(torch.float32)
         return torch.arange(T, dtype=torch.float32)
 
+    def _x_start_coefficients(self):
+        """(a, b) with x_start = a[t] * x_t - b[t] * model_output -- the one place the objective enters the reverse step
+        (model_predictions :559-579): pred_noise -> predict_start_from_noise (:526-530), pred_v -> predict_start_from_v
+        (:545-549), pred_x0 -> the output itself (0 * x - (-1) * out, exact in fp32)."""
+        if self.objective == "pred_noise":
+            return self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod
+        cached = getattr(self, "_obj_cols", None)
+        if cached is None or cached[0].device != self.betas.device:
+            if self.objective == "pred_v":
+                cached = (self.sqrt_alphas_cumprod.detach().clone(), self.sqrt_one_minus_alphas_cumprod.detach().clone())
+            else:
+                cached = (torch.zeros_like(self.betas), -torch.ones_like(self.betas))
+            object.__setattr__(self, "_obj_cols", cached)      # plain attributes (stable pointers), not buffers / state_dict entries
+        return cached
+
     def _sync_plan(self):
         plan = self.model.eps_plan
-        sid = (self.sqrt_recip_alphas_cumprod.data_ptr(), self.posterior_mean_coef1.data_ptr(), self.num_timesteps)
+        a, b = self._x_start_coefficients()
+        sid = (a.data_ptr(), self.posterior_mean_coef1.data_ptr(), self.num_timesteps)
         if plan._schedule_id != sid:
-            plan.set_schedule(self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod,
-                              self.posterior_mean_coef1, self.posterior_mean_coef2,
+            plan.set_schedule(a, b, self.posterior_mean_coef1, self.posterior_mean_coef2,
                               self.posterior_log_variance_clipped, self._time_values())
         return plan
 
@@ -183,11 +198,27 @@ class _GaussianDiffusionBase(nn.Module):
 
     @torch.no_grad()
     def model_predictions(self, x, t, x_self_cond=None, clip_x_start=False, t_real=None):
-        eps = self.model(x, t, x_self_cond)
-        x_start = self.predict_start_from_noise(x, t if t_real is None else t_real, eps)
-        if clip_x_start:
-            x_start = x_start.clamp(-1.0, 1.0)
-        return ModelPrediction(eps, x_start)
+        out = self.model(x, t, x_self_cond)
+        tt = t if t_real is None else t_real
+        clip = (lambda v: v.clamp(-1.0, 1.0)) if clip_x_start else (lambda v: v)
+        if self.objective == "pred_noise":
+            return ModelPrediction(out, clip(self.predict_start_from_noise(x, tt, out)))
+        x_start = clip(out if self.objective == "pred_x0" else self.predict_start_from_v(x, tt, out))
+        return ModelPrediction(self.predict_noise_from_start(x, tt, x_start), x_start)
+
+    def predict_noise_from_start(self, x_t, t, x0):  # :532-536
+        return (_gather(self.sqrt_recip_alphas_cumprod, t, x_t) * x_t - x0) / _gather(self.sqrt_recipm1_alphas_cumprod, t, x_t)
+
+    def predict_v(self, x_start, t, noise):  # :538-542
+        return _gather(self.sqrt_alphas_cumprod, t, x_start) * noise - _gather(self.sqrt_one_minus_alphas_cumprod, t, x_start) * x_start
+
+    def predict_start_from_v(self, x_t, t, v):  # :544-548
+        return _gather(self.sqrt_alphas_cumprod, t, x_t) * x_t - _gather(self.sqrt_one_minus_alphas_cumprod, t, x_t) * v
+
+    def _loss_target(self, x_start, t, noise):  # p_losses :731-740
+        if self.objective == "pred_noise":
+            return noise
+        return x_start if self.objective == "pred_x0" else self.predict_v(x_start, t, noise)
 
     @torch.no_grad()
     def p_sample(self, x, t: int, x_self_cond=None, noise=None):
@@ -245,6 +276,8 @@ class _GaussianDiffusionBase(nn.Module):
 
         if self.self_condition:
             raise NotImplementedError("ddim_sample needs self_condition=False (the reference's version cannot run with it either)")
+        if self.objective != "pred_noise":
+            raise NotImplementedError("ddim_sample is built for objective='pred_noise'")
         if self._flavour == "sr3":
             raise NotImplementedError("the SR3 flavour has no DDIM sampler in the reference")
         batch = shape[0]
@@ -339,12 +372,15 @@ class _GaussianDiffusionBase(nn.Module):
             t = torch.randint(0, self.num_timesteps, (b,), device=clean.device).long()
         noise = torch.randn_like(clean) if noise is None else noise
         x = self.q_sample(clean, t, noise)
-        trained = self._trained_loss(x, t, noisy if self.self_condition else None, noise)
+        # reference quirk kept (hicdiff_condition.py:716,733-737): the pred_x0 / pred_v targets are built from `x_start`, which in
+        # the conditional p_losses is the NOISY input of the pair, not the clean tile that was diffused
+        target = self._loss_target(noisy, t, noise)
+        trained = self._trained_loss(x, t, noisy if self.self_condition else None, target)
         if trained is not None:
             return trained
         with torch.no_grad():
             out = self.model(x, t, noisy if self.self_condition else None)
-        loss = self.loss_fn(out, noise, reduction="none").reshape(b, -1)  # 'b ... -> b (...)' keeps all elements
+        loss = self.loss_fn(out, target, reduction="none").reshape(b, -1)  # 'b ... -> b (...)' keeps all elements
         loss = loss * _gather(self.p2_loss_weight, t, loss)
         return self._finish_loss(loss.mean())
 
@@ -376,12 +412,13 @@ class GaussianDiffusionUncond(_GaussianDiffusionBase):
         b = x_start.shape[0]
         noise = torch.randn_like(x_start) if noise is None else noise
         x = self.q_sample(x_start, t, noise)
-        trained = self._trained_loss(x, t, None, noise)
+        target = self._loss_target(x_start, t, noise)
+        trained = self._trained_loss(x, t, None, target)
         if trained is not None:
             return trained
         with torch.no_grad():
             out = self.model(x, t, None)
-        loss = self.loss_fn(out, noise, reduction="none").reshape(b, -1)  # 'b ... -> b (...)' keeps all elements
+        loss = self.loss_fn(out, target, reduction="none").reshape(b, -1)  # 'b ... -> b (...)' keeps all elements
         loss = loss * _gather(self.p2_loss_weight, t, loss)
         return self._finish_loss(loss.mean())
 

@@ -298,7 +298,7 @@ def _extract(a, t, x_shape):  # :388-391
     return out.reshape(t.shape[0], *((1,) * (len(x_shape) - 1)))
 
 
-def p_sample(eps_fn, buf: SD, x, t: int, cond, noise, *, sr3_levels: Optional[torch.Tensor] = None):
+def p_sample(eps_fn, buf: SD, x, t: int, cond, noise, *, sr3_levels: Optional[torch.Tensor] = None, objective: str = "pred_noise"):
     """One reverse step: p_mean_variance :581-589 + p_sample :591-598 (SR3: src/hicdiff_sr3.py:634-652).
 
     eps_fn(x, time, cond) -> eps.  `noise` is the z tensor (ignored at t == 0).  Returns (x_{t-1}, x_start, eps).
@@ -307,8 +307,14 @@ def p_sample(eps_fn, buf: SD, x, t: int, cond, noise, *, sr3_levels: Optional[to
     if sr3_levels is None:
         bt = torch.full((b,), t, dtype=torch.long)
         eps = eps_fn(x, bt, cond)
-        x_start = _extract(buf["sqrt_recip_alphas_cumprod"], bt, x.shape) * x - \
-            _extract(buf["sqrt_recipm1_alphas_cumprod"], bt, x.shape) * eps  # :526-530
+        if objective == "pred_noise":
+            x_start = _extract(buf["sqrt_recip_alphas_cumprod"], bt, x.shape) * x - \
+                _extract(buf["sqrt_recipm1_alphas_cumprod"], bt, x.shape) * eps  # :526-530
+        elif objective == "pred_x0":  # model_predictions :568-571
+            x_start = eps
+        else:  # pred_v: predict_start_from_v :544-548
+            x_start = _extract(buf["sqrt_alphas_cumprod"], bt, x.shape) * x - \
+                _extract(buf["sqrt_one_minus_alphas_cumprod"], bt, x.shape) * eps
         x_start = x_start.clamp(-1.0, 1.0)  # :586
         mean = _extract(buf["posterior_mean_coef1"], bt, x.shape) * x_start + \
             _extract(buf["posterior_mean_coef2"], bt, x.shape) * x  # :550-554
@@ -325,13 +331,13 @@ def p_sample(eps_fn, buf: SD, x, t: int, cond, noise, *, sr3_levels: Optional[to
 
 
 def p_sample_loop(eps_fn, buf: SD, cond, noise: torch.Tensor, *, timesteps: int,
-                  sr3_levels: Optional[torch.Tensor] = None, return_all: bool = False, t_end: int = 0):
+                  sr3_levels: Optional[torch.Tensor] = None, return_all: bool = False, t_end: int = 0, objective: str = "pred_noise"):
     """p_sample_loop :600-623 with INJECTED noise: noise[0] = x_T (:605), noise[i] = z of step t = T - i (:596)."""
     img = noise[0]
     trace = []
     for t in reversed(range(t_end, timesteps)):
         z = noise[timesteps - t] if t > 0 else None
-        img, _, _ = p_sample(eps_fn, buf, img, t, cond, z, sr3_levels=sr3_levels)
+        img, _, _ = p_sample(eps_fn, buf, img, t, cond, z, sr3_levels=sr3_levels, objective=objective)
         if return_all:
             trace.append(img)
     return (img, trace) if return_all else img
@@ -365,11 +371,21 @@ def q_sample(buf: SD, x_start, t, noise):  # :698-704
         _extract(buf["sqrt_one_minus_alphas_cumprod"], t, x_start.shape) * noise
 
 
-def p_losses(eps_fn, buf: SD, noisy, clean, t, noise, *, loss_type="l2", self_condition=True):
+def p_losses(eps_fn, buf: SD, noisy, clean, t, noise, *, loss_type="l2", self_condition=True, objective="pred_noise"):
     """Conditional p_losses :715-746 with t and noise supplied (the reference draws them :719,721)."""
     x = q_sample(buf, clean, t, noise)
     out = eps_fn(x, t, noisy if self_condition else None)
-    loss = F.mse_loss(out, noise, reduction="none") if loss_type == "l2" else F.l1_loss(out, noise, reduction="none")
+    if objective == "pred_noise":
+        target = noise
+    else:
+        # reference quirk (:716,:733-737): the conditional p_losses unpacks `x_start, x_end = x_in`, diffuses x_end (the clean
+        # tile) but builds the pred_x0 / pred_v targets from `x_start` -- the NOISY conditional input
+        ref = noisy if self_condition else clean
+        if objective == "pred_x0":
+            target = ref
+        else:  # predict_v :538-542
+            target = _extract(buf["sqrt_alphas_cumprod"], t, ref.shape) * noise - _extract(buf["sqrt_one_minus_alphas_cumprod"], t, ref.shape) * ref
+    loss = F.mse_loss(out, target, reduction="none") if loss_type == "l2" else F.l1_loss(out, target, reduction="none")
     loss = loss.reshape(loss.shape[0], -1)  # reduce(loss, 'b ... -> b (...)', 'mean') keeps every element :743
     loss = loss * _extract(buf["p2_loss_weight"], t, loss.shape)
     return loss.mean()
@@ -397,7 +413,8 @@ def sr3_p_losses_and_grads(sd: SD, noisy, clean, level, noise, *, loss_type="l2"
     return loss.detach(), dict(zip(leaves.keys(), grads))
 
 
-def p_losses_and_grads(sd: SD, buf: SD, noisy, clean, t, noise, *, loss_type="l2", self_condition=True, num_blocks=32, net="hicedrn"):
+def p_losses_and_grads(sd: SD, buf: SD, noisy, clean, t, noise, *, loss_type="l2", self_condition=True, num_blocks=32, net="hicedrn",
+                       objective="pred_noise"):
     """One training iteration's loss and d loss / d parameter for the hicedrn_Diff eps-net: what `loss = diffusion(x);
     loss.backward()` leaves in `.grad` (train.py:127-128) -- torch.autograd over the restated forward (the reference has no
     hand-written backward to cite).  Returns (loss, {state_dict key: grad})."""
@@ -406,7 +423,7 @@ def p_losses_and_grads(sd: SD, buf: SD, noisy, clean, t, noise, *, loss_type="l2
         eps_fn = lambda x, tt, c: unet_forward(leaves, x, tt, c, self_condition=self_condition)  # noqa: E731
     else:
         eps_fn = lambda x, tt, c: hicedrn_forward(leaves, x, tt, c, self_condition=self_condition, num_blocks=num_blocks)  # noqa: E731
-    loss = p_losses(eps_fn, buf, noisy, clean, t, noise, loss_type=loss_type, self_condition=self_condition)
+    loss = p_losses(eps_fn, buf, noisy, clean, t, noise, loss_type=loss_type, self_condition=self_condition, objective=objective)
     grads = torch.autograd.grad(loss, list(leaves.values()))
     return loss.detach(), dict(zip(leaves.keys(), grads))
 
