@@ -150,19 +150,19 @@ class _TrainStep(torch.autograd.Function):
         ar = getattr(trainer.net, "_grad_allreduce", None)
         if ar is not None:
             allreduce_mean_(trainer.flat_grad, ar[0])
-        ctx.trainer = trainer
-        ctx.names = list(trainer.grads.keys())
+        # snapshot: the trainer's buffer is rewritten by the next step, and a caller may run several forwards before any
+        # backward (e.g. (loss1 + loss2).backward()) -- every loss must keep ITS gradients (one flat copy, ~0.05 ms)
+        ctx.flat = trainer.flat_grad.clone()
+        ctx.shapes = [(k, g.shape, g.numel()) for k, g in trainer.grads.items()]
         return loss
 
     @staticmethod
     def backward(ctx, gout):
-        tr = ctx.trainer
-        flat = gout * tr.flat_grad            # ONE launch; a fresh tensor (the trainer's buffer is rewritten every step)
+        flat = gout * ctx.flat                # ONE launch; a fresh tensor
         grads, off = [], 0
-        for k in ctx.names:
-            g = tr.grads[k]
-            grads.append(flat[off:off + g.numel()].view_as(g))
-            off += g.numel()
+        for _, shape, numel in ctx.shapes:
+            grads.append(flat[off:off + numel].view(shape))
+            off += numel
         return (None,) * 7 + tuple(grads)
 
 

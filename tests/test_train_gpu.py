@@ -435,3 +435,22 @@ def test_training_step_ragged_batches(B):
             l1 = diff.p_losses([noisy[:1].to(DEV), clean[:1].to(DEV)], t=t[:1].to(DEV), noise=noise[:1].to(DEV))
             l1.backward()
             assert sorted(net._trainers) == [1, 3]
+
+
+def test_two_forwards_before_backward_keep_their_own_gradients():
+    """(loss1 + loss2).backward(): each loss node must deliver the gradients of ITS step, not the trainer's latest buffer."""
+    c, net, sd, diff, clean, noisy, t, noise = _case("cond_l2")
+    diff = diff.to(DEV)
+    x = [noisy.to(DEV), clean.to(DEV)]
+    t2 = torch.tensor([500, 2], device=DEV)
+    l1 = diff.p_losses(x, t=t.to(DEV), noise=noise.to(DEV))
+    l2 = diff.p_losses(x, t=t2, noise=noise.to(DEV))
+    (l1 + l2).backward()
+    both = {k: p.grad.clone() for k, p in net.named_parameters()}
+    net.zero_grad()
+    diff.p_losses(x, t=t.to(DEV), noise=noise.to(DEV)).backward()
+    g1 = {k: p.grad.clone() for k, p in net.named_parameters()}
+    net.zero_grad()
+    diff.p_losses(x, t=t2, noise=noise.to(DEV)).backward()
+    for k, p in net.named_parameters():
+        assert torch.equal(both[k], g1[k] + p.grad), k
