@@ -336,8 +336,12 @@ cudaError_t linear_attention_bwd_run(const bf16* qkv, const bf16* dout, bf16* dq
     float* tv = tpart + static_cast<size_t>(bh) * LAB_SPLIT * DH;
     la_kstats_kernel<<<bh, 256, 0, s>>>(qkv, n, kmax, ksum);
     constexpr size_t ctx_smem = static_cast<size_t>(8) * 2 * DH * (DH + 1) * sizeof(float);
-    cudaError_t ae = cudaFuncSetAttribute(la_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx_smem));
-    if (ae != cudaSuccess) return ae;
+    static bool ctx_attr = false;     // once per process (one process per GPU); never inside a stream capture (the first step is eager)
+    if (!ctx_attr) {
+        cudaError_t ae = cudaFuncSetAttribute(la_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx_smem));
+        if (ae != cudaSuccess) return ae;
+        ctx_attr = true;
+    }
     la_ctx_kernel<<<dim3(LAB_SPLIT, bh), 256, ctx_smem, s>>>(qkv, dout, n, scale, kmax, ksum, cpart);
     la_reduce_kernel<<<bh, 256, 0, s>>>(cpart, 2 * DH * DH, cd);
     la_t_kernel<<<dim3(LAB_SPLIT, bh), 256, 0, s>>>(qkv, n, kmax, ksum, cd, tpart);
@@ -350,8 +354,12 @@ cudaError_t linear_attention_bwd_run(const bf16* qkv, const bf16* dout, bf16* dq
 cudaError_t full_attention_bwd_run(const bf16* qkv, const bf16* dout, bf16* dqkv, int B, int n, cudaStream_t s) {
     if (n != FA_N) return cudaErrorInvalidValue;
     constexpr size_t fa_bytes = (static_cast<size_t>(4) * FA_N * (DH + 1) + 2 * FA_N * (FA_N + 1)) * sizeof(float);
-    cudaError_t ae = cudaFuncSetAttribute(full_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fa_bytes));
-    if (ae != cudaSuccess) return ae;
+    static bool fa_attr = false;
+    if (!fa_attr) {
+        cudaError_t ae = cudaFuncSetAttribute(full_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fa_bytes));
+        if (ae != cudaSuccess) return ae;
+        fa_attr = true;
+    }
     full_attention_bwd_kernel<<<B * HEADS, 256, fa_bytes, s>>>(qkv, dout, 0.17677669529663687f, dqkv);
     return cudaGetLastError();
 }

@@ -9,6 +9,7 @@
 // keeps working) and gradients are written into caller-provided fp32 buffers.  Activations are bf16 NHWC; the convs run on
 // tcgen05 (conv_gemm.cu forward and data gradient, wgrad.cu weight gradient); statistics-free glue is in train_kernels.cu.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "trainer_internal.h"
@@ -360,9 +361,34 @@ int hd_trainer_step(hd_trainer* t, const float* x_t, const float* cond, const fl
     T_TRY(cudaMemcpyAsync(t->time, time, t->B * 4, cudaMemcpyDeviceToDevice, s));
     T_TRY(cudaMemcpyAsync(t->weight, weight, t->B * 4, cudaMemcpyDeviceToDevice, s));
     t->loss_kind = loss_type;
-    for (const TOp& op : t->ops) {
-        cudaError_t e = op.fn(s);
-        if (e != cudaSuccess) return tfail("launch of '%s' failed: %s", op.tag.c_str(), cudaGetErrorString(e));
+    static const bool use_graph = [] { const char* v = getenv("HD_TRAIN_GRAPH"); return !(v && v[0] == '0'); }();
+    if (use_graph && t->graph[loss_type] == nullptr && t->eager_steps[loss_type] >= 1) {
+        // capture (nothing executes) on the private stream: the caller's stream may be the legacy default stream
+        if (!t->cap_stream) T_TRY(cudaStreamCreateWithFlags(&t->cap_stream, cudaStreamNonBlocking));
+        T_TRY(cudaStreamBeginCapture(t->cap_stream, cudaStreamCaptureModeThreadLocal));
+        cudaError_t le = cudaSuccess;
+        const char* bad = "";
+        for (const TOp& op : t->ops) {
+            le = op.fn(t->cap_stream);
+            if (le != cudaSuccess) { bad = op.tag.c_str(); break; }
+        }
+        cudaGraph_t g = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(t->cap_stream, &g);
+        if (le == cudaSuccess && ce == cudaSuccess) ce = cudaGraphInstantiate(&t->graph[loss_type], g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (le != cudaSuccess || ce != cudaSuccess) {
+            t->graph[loss_type] = nullptr;
+            return tfail("capturing the training step failed at '%s': %s", bad, cudaGetErrorString(le != cudaSuccess ? le : ce));
+        }
+    }
+    if (use_graph && t->graph[loss_type] != nullptr) {
+        T_TRY(cudaGraphLaunch(t->graph[loss_type], s));
+    } else {
+        for (const TOp& op : t->ops) {
+            cudaError_t e = op.fn(s);
+            if (e != cudaSuccess) return tfail("launch of '%s' failed: %s", op.tag.c_str(), cudaGetErrorString(e));
+        }
+        t->eager_steps[loss_type] += 1;
     }
     if (eps_out) T_TRY(cudaMemcpyAsync(eps_out, t->eps, tb, cudaMemcpyDeviceToDevice, s));
     T_TRY(cudaMemcpyAsync(loss_out, t->loss, 4, cudaMemcpyDeviceToDevice, s));
@@ -427,6 +453,8 @@ int64_t hd_trainer_device_bytes(hd_trainer* t) { return t ? static_cast<int64_t>
 void hd_trainer_destroy(hd_trainer* t) {
     if (!t) return;
     cudaSetDevice(t->device);
+    for (int k = 0; k < 2; ++k) if (t->graph[k]) cudaGraphExecDestroy(t->graph[k]);
+    if (t->cap_stream) cudaStreamDestroy(t->cap_stream);
     for (void* q : t->allocs) cudaFree(q);
     delete t;
 }

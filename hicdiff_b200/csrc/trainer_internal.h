@@ -48,6 +48,11 @@ struct hd_trainer {
     float *x = nullptr, *cond = nullptr, *time = nullptr, *target = nullptr, *weight = nullptr, *eps = nullptr, *d_eps = nullptr,
           *loss = nullptr;
     int loss_kind = 1;
+    // the whole step as a CUDA graph per loss kind: step 1 runs eagerly (validates every launch), step 2 is captured on a
+    // trainer-private stream, later steps replay (HD_TRAIN_GRAPH=0 keeps the eager path)
+    int eager_steps[2] = {0, 0};
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    cudaStream_t cap_stream = nullptr;
 };
 
 namespace hd {
