@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-eager-gpu"])
     ap.add_argument("--workload", default="unet_uncond", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="tiles per GPU (default: the workload's)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -154,6 +154,83 @@ def run_reference_arm(args, rank):
         "cpu_baseline": {"value": tiles_s, "unit": "tiles/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": tiles_s, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_reference_eager_gpu_arm(args, rank):
+    """Extra reported baseline: the reference's algorithm -- the oracle port, i.e. the same ATen call
+    sequence -- executed by PyTorch eager on THIS GPU (cuDNN / cuBLAS), fp32 and under torch.autocast(bf16).  The reference
+    ships no GPU kernels of its own, so this is the practical 'kernel to beat'.  One JSON line; not part of the driver's arms."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import hicdiff_oracle as O
+
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    batch = args.batch or wl["batch"]
+    steps, warmup = min(args.steps, 20), max(3, min(args.warmup, 5))
+    dev = torch.device("cuda:0")
+    net, okw, _ = build_variant(args.workload)
+    sd = {k: t.detach().to(dev) for k, t in net.state_dict().items()}
+    fwd = O.unet_forward if okw["kind"] == "unet" else O.hicedrn_forward
+    eps_fn = lambda x, t, c: fwd(sd, x, t, c, self_condition=okw["self_condition"], sr3=okw["sr3"])  # noqa: E731
+    buf = {k: v.to(dev) for k, v in O.diffusion_buffers(wl["schedule"], T_FULL).items()}
+    levels = O.sr3_noise_levels(wl["schedule"], T_FULL) if okw["sr3"] else None
+    from hicdiff_b200.synthetic import synthetic_tiles
+
+    clean, noisy = synthetic_tiles(batch, seed=1234)
+    cond = noisy.to(dev) if okw["self_condition"] else None
+
+    def time_sampling(autocast):
+        x = torch.randn(batch, 1, 64, 64, device=dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            for i in range(warmup + steps):
+                if i == warmup:
+                    torch.cuda.synchronize()
+                    ev[0].record()
+                z = torch.randn(batch, 1, 64, 64, device=dev)
+                x, _, _ = O.p_sample(eps_fn, buf, x, T_FULL - 1 - i, cond, z, sr3_levels=levels)
+                x = x.float()
+            ev[1].record()
+            torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[1]) / steps
+
+    def time_training(autocast, tb):
+        leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if torch.is_floating_point(v)}
+        f = lambda x, t, c: fwd(leaves, x, t, c, self_condition=okw["self_condition"], sr3=okw["sr3"])  # noqa: E731
+        cl, no = clean[:tb].to(dev), noisy[:tb].to(dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        n = 5
+        for i in range(2 + n):
+            if i == 2:
+                torch.cuda.synchronize()
+                ev[0].record()
+            t = torch.randint(0, T_FULL, (tb,), device=dev)
+            noise = torch.randn_like(cl)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                xt = O.q_sample(buf, cl, t, noise)
+                out = f(xt, levels.to(dev)[t].float().view(tb, 1) if okw["sr3"] else t, no if okw["self_condition"] else None)
+                loss = F.mse_loss(out.float(), noise)
+            torch.autograd.grad(loss, list(leaves.values()))
+        ev[1].record()
+        torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[1]) / n
+
+    ms32, ms16 = time_sampling(False), time_sampling(True)
+    tb = min(64, batch)
+    tr32, tr16 = time_training(False, tb), time_training(True, tb)
+    line = {
+        "impl": "reference-eager-gpu", "metric": "tiles_per_sec_T1000", "value": batch / (ms32 * 1e-3 * T_FULL), "unit": "tiles/s",
+        "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": ms32, "higher_is_better": True, "dtype": "fp32 (cuDNN TF32 default)",
+        "data": "synthetic",
+        "config": {"workload": f"{wl['desc']}, oracle port of the reference under PyTorch eager on this GPU", "tiles_per_gpu": batch},
+        "autocast_bf16": {"value": batch / (ms16 * 1e-3 * T_FULL), "unit": "tiles/s", "ms_per_step": ms16},
+        "train_step": {"batch": tb, "fp32_ms": tr32, "autocast_bf16_ms": tr16, "fp32_tiles_per_s": tb / (tr32 * 1e-3),
+                       "autocast_bf16_tiles_per_s": tb / (tr16 * 1e-3), "note": "forward + loss + autograd backward, no optimizer"},
+        "torch": torch.__version__,
     }
     print(json.dumps(line), flush=True)
 
@@ -390,6 +467,8 @@ def main():
         raise SystemExit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference_arm(args, rank)
+    elif args.impl == "reference-eager-gpu":
+        run_reference_eager_gpu_arm(args, rank)
     else:
         run_b200_arm(args, rank, world)
 

@@ -305,7 +305,7 @@ def p_sample(eps_fn, buf: SD, x, t: int, cond, noise, *, sr3_levels: Optional[to
     """
     b = x.shape[0]
     if sr3_levels is None:
-        bt = torch.full((b,), t, dtype=torch.long)
+        bt = torch.full((b,), t, dtype=torch.long, device=x.device)
         eps = eps_fn(x, bt, cond)
         if objective == "pred_noise":
             x_start = _extract(buf["sqrt_recip_alphas_cumprod"], bt, x.shape) * x - \
@@ -320,7 +320,7 @@ def p_sample(eps_fn, buf: SD, x, t: int, cond, noise, *, sr3_levels: Optional[to
             _extract(buf["posterior_mean_coef2"], bt, x.shape) * x  # :550-554
         logvar = _extract(buf["posterior_log_variance_clipped"], bt, x.shape)
     else:
-        level = torch.FloatTensor([sr3_levels[t + 1]]).repeat(b, 1)  # sr3 :636
+        level = torch.FloatTensor([sr3_levels[t + 1]]).repeat(b, 1).to(x.device)  # sr3 :636
         eps = eps_fn(x, level, cond)
         x_start = buf["sqrt_recip_alphas_cumprod"][t] * x - buf["sqrt_recipm1_alphas_cumprod"][t] * eps
         x_start = x_start.clamp(-1.0, 1.0)
