@@ -59,7 +59,7 @@ SIGNATURES = {
     "hd_trainer_destroy": (None, [_vp]),
     "hd_op_conv3x3_wgrad": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "hd_op_conv_wgrad": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "hd_op_groupnorm_silu_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "hd_op_groupnorm_silu_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "hd_op_channel_layernorm_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "hd_op_weight_standardize_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "hd_op_attention_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),

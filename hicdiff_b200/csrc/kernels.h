@@ -375,6 +375,7 @@ struct GroupNormBwdArgs {
     float* dbeta;         // [C]
     float* dscale = nullptr;        // [B, C] (optional)
     float* dshift = nullptr;        // [B, C]
+    float* dconv_bias = nullptr;    // [C] (optional) sum_{b,p} dy: the bias gradient of the conv that produced y, from the same sums
     float* dpost = nullptr;         // [B, C] (optional) sum_p ds: gradient of an SR3 embedding added AFTER the activation
 };
 size_t gn_bwd_scratch_floats(int B, int P, int C);

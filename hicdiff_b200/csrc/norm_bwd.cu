@@ -99,20 +99,21 @@ __global__ void __launch_bounds__(256)
 gn_bwd_sums_kernel(const uint4* __restrict__ y, const uint4* __restrict__ ds, const float2* __restrict__ stats,
                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ scale,
                    const float* __restrict__ shift, int ld, int P, int C, int nchunk, float* __restrict__ part) {
-    extern __shared__ float gs_red[];   // [lanes][3 * C]: U, V and the plain sum of ds (the SR3 post-activation embedding's gradient)
+    extern __shared__ float gs_red[];   // [lanes][4 * C]: U, V, the plain sum of ds (SR3 post-activation embedding's gradient), sum of y
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int cpp = C / 8, lanes = 256 / cpp;
     const int cc = threadIdx.x % cpp, pl = threadIdx.x / cpp;
     const int ppc = P / nchunk;
     const float2 st = stats[b * G + (cc * 8) / (C / G)];
-    float ga[8], be[8], sc1[8], sh[8], U[8], V[8], Ws[8];
+    float k1[8], k0[8], U[8], V[8], Ws[8], Ys[8];      // h = xhat * k1 + k0, k1 = gamma (scale + 1), k0 = beta (scale + 1) + shift
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = cc * 8 + j;
-        ga[j] = gamma[c]; be[j] = beta[c];
-        sc1[j] = scale ? scale[static_cast<size_t>(b) * ld + c] + 1.0f : 1.0f;
-        sh[j] = shift ? shift[static_cast<size_t>(b) * ld + c] : 0.0f;
-        U[j] = 0.f; V[j] = 0.f; Ws[j] = 0.f;
+        const float sc1 = scale ? scale[static_cast<size_t>(b) * ld + c] + 1.0f : 1.0f;
+        const float sh = shift ? shift[static_cast<size_t>(b) * ld + c] : 0.0f;
+        k1[j] = gamma[c] * sc1;
+        k0[j] = fmaf(beta[c], sc1, sh);
+        U[j] = 0.f; V[j] = 0.f; Ws[j] = 0.f; Ys[j] = 0.f;
     }
     const size_t base = (static_cast<size_t>(b) * P + static_cast<size_t>(chunk) * ppc) * cpp + cc;
     for (int p = pl; p < ppc; p += lanes) {
@@ -122,22 +123,23 @@ gn_bwd_sums_kernel(const uint4* __restrict__ y, const uint4* __restrict__ ds, co
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float xh = (yv[j] - st.x) * st.y;
-            const float h = fmaf(fmaf(xh, ga[j], be[j]), sc1[j], sh[j]);
-            const float dh = g[j] * silu_grad(h);
+            const float dh = g[j] * silu_grad(fmaf(xh, k1[j], k0[j]));
             U[j] += dh;
             V[j] = fmaf(dh, xh, V[j]);
             Ws[j] += g[j];
+            Ys[j] += yv[j];
         }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        gs_red[pl * 3 * C + cc * 8 + j] = U[j]; gs_red[pl * 3 * C + C + cc * 8 + j] = V[j]; gs_red[pl * 3 * C + 2 * C + cc * 8 + j] = Ws[j];
+        float* r = gs_red + pl * 4 * C + cc * 8 + j;
+        r[0] = U[j]; r[C] = V[j]; r[2 * C] = Ws[j]; r[3 * C] = Ys[j];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 3 * C; i += 256) {
+    for (int i = threadIdx.x; i < 4 * C; i += 256) {
         float t = 0.f;
-        for (int k = 0; k < lanes; ++k) t += gs_red[k * 3 * C + i];
-        part[(static_cast<size_t>(b) * nchunk + chunk) * 3 * C + i] = t;
+        for (int k = 0; k < lanes; ++k) t += gs_red[k * 4 * C + i];
+        part[(static_cast<size_t>(b) * nchunk + chunk) * 4 * C + i] = t;
     }
 }
 
@@ -149,16 +151,16 @@ gn_bwd_coef_kernel(const float* __restrict__ part, int nchunk, const float* __re
                    float* __restrict__ dscale, float* __restrict__ dshift, float* __restrict__ dpost) {
     __shared__ float s_a[512], s_b[512];
     const int b = blockIdx.x, c = threadIdx.x;
-    float U = 0.f, V = 0.f, Wp = 0.f;
+    float U = 0.f, V = 0.f, Wp = 0.f, Yp = 0.f;
     if (c < C) {
         for (int k = 0; k < nchunk; ++k) {
-            U += part[(static_cast<size_t>(b) * nchunk + k) * 3 * C + c];
-            V += part[(static_cast<size_t>(b) * nchunk + k) * 3 * C + C + c];
-            Wp += part[(static_cast<size_t>(b) * nchunk + k) * 3 * C + 2 * C + c];
+            const float* pp = part + (static_cast<size_t>(b) * nchunk + k) * 4 * C + c;
+            U += pp[0]; V += pp[C]; Wp += pp[2 * C]; Yp += pp[3 * C];
         }
         if (dpost) dpost[static_cast<size_t>(b) * ld + c] = Wp;
-        UV[(static_cast<size_t>(b) * 2) * C + c] = U;
-        UV[(static_cast<size_t>(b) * 2 + 1) * C + c] = V;
+        UV[(static_cast<size_t>(b) * 3) * C + c] = U;
+        UV[(static_cast<size_t>(b) * 3 + 1) * C + c] = V;
+        UV[(static_cast<size_t>(b) * 3 + 2) * C + c] = Yp;
         if (dshift) dshift[static_cast<size_t>(b) * ld + c] = U;
         if (dscale) dscale[static_cast<size_t>(b) * ld + c] = fmaf(gamma[c], V, beta[c] * U);
         const float k1 = (scale ? scale[static_cast<size_t>(b) * ld + c] + 1.0f : 1.0f) * gamma[c];
@@ -176,19 +178,30 @@ gn_bwd_coef_kernel(const float* __restrict__ part, int nchunk, const float* __re
     }
 }
 
-// d gamma[c] = sum_b (scale + 1) V, d beta[c] = sum_b (scale + 1) U  (accumulate: += for a layer used more than once)
-__global__ void gn_bwd_affine_kernel(const float* __restrict__ UV, const float* __restrict__ scale, int ld, int B, int C,
-                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+// d gamma[c] = sum_b (scale + 1) V, d beta[c] = sum_b (scale + 1) U; optionally the bias gradient of the conv that produced y:
+// sum_{b,p} dy = sum_b r (k1 U - P m1 - m2 sum_p xhat), sum_p xhat = r (sum_p y - P mu)  -- no extra pass over dy
+__global__ void gn_bwd_affine_kernel(const float* __restrict__ UV, const float* __restrict__ scale, int ld, int B, int C, int P,
+                                     const float* __restrict__ gamma, const float2* __restrict__ stats, const float* __restrict__ gm,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dconv_bias) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    float dg = 0.f, db = 0.f;
+    const int g = c / (C / G);
+    float dg = 0.f, db = 0.f, dcb = 0.f;
     for (int b = 0; b < B; ++b) {
         const float s1 = scale ? scale[static_cast<size_t>(b) * ld + c] + 1.0f : 1.0f;
-        db = fmaf(s1, UV[(static_cast<size_t>(b) * 2) * C + c], db);
-        dg = fmaf(s1, UV[(static_cast<size_t>(b) * 2 + 1) * C + c], dg);
+        const float U = UV[(static_cast<size_t>(b) * 3) * C + c], V = UV[(static_cast<size_t>(b) * 3 + 1) * C + c];
+        db = fmaf(s1, U, db);
+        dg = fmaf(s1, V, dg);
+        if (dconv_bias != nullptr) {
+            const float2 st = stats[b * G + g];
+            const float m1 = gm[(b * G + g) * 2], m2 = gm[(b * G + g) * 2 + 1];
+            const float xs = st.y * (UV[(static_cast<size_t>(b) * 3 + 2) * C + c] - static_cast<float>(P) * st.x);
+            dcb += st.y * (gamma[c] * s1 * U - static_cast<float>(P) * m1 - m2 * xs);
+        }
     }
     dgamma[c] = dg;
     dbeta[c] = db;
+    if (dconv_bias != nullptr) dconv_bias[c] = dcb;
 }
 
 // ---------------------------------------------------------------------------------------------- pass 2: dy
@@ -203,13 +216,14 @@ gn_bwd_dx_kernel(const uint4* __restrict__ y, const uint4* ds, const float2* __r
     const int g = (cc * 8) / (C / G);
     const float2 st = stats[b * G + g];
     const float m1 = gm[(b * G + g) * 2], m2 = gm[(b * G + g) * 2 + 1];
-    float ga[8], be[8], sc1[8], sh[8];
+    float k1[8], k0[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = cc * 8 + j;
-        ga[j] = gamma[c]; be[j] = beta[c];
-        sc1[j] = scale ? scale[static_cast<size_t>(b) * ld + c] + 1.0f : 1.0f;
-        sh[j] = shift ? shift[static_cast<size_t>(b) * ld + c] : 0.0f;
+        const float sc1 = scale ? scale[static_cast<size_t>(b) * ld + c] + 1.0f : 1.0f;
+        const float sh = shift ? shift[static_cast<size_t>(b) * ld + c] : 0.0f;
+        k1[j] = gamma[c] * sc1;
+        k0[j] = fmaf(beta[c], sc1, sh);
     }
     const size_t base = (static_cast<size_t>(b) * P + static_cast<size_t>(chunk) * ppc) * cpp + cc;
     for (int p = pl; p < ppc; p += lanes) {
@@ -220,9 +234,8 @@ gn_bwd_dx_kernel(const uint4* __restrict__ y, const uint4* ds, const float2* __r
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float xh = (yv[j] - st.x) * st.y;
-            const float h = fmaf(fmaf(xh, ga[j], be[j]), sc1[j], sh[j]);
-            const float dh = gr[j] * silu_grad(h);
-            gr[j] = st.y * (dh * sc1[j] * ga[j] - m1 - xh * m2);
+            const float dh = gr[j] * silu_grad(fmaf(xh, k1[j], k0[j]));
+            gr[j] = st.y * (dh * k1[j] - m1 - xh * m2);
         }
         dy[i] = pack8(gr);
     }
@@ -351,8 +364,8 @@ int gn_chunks(int P, int C) {
 }  // namespace
 
 size_t gn_bwd_scratch_floats(int B, int P, int C) {
-    return static_cast<size_t>(B) * G * 2 /*stats*/ + static_cast<size_t>(B) * gn_chunks(P, C) * 3 * C /*part*/ +
-           static_cast<size_t>(B) * 2 * C /*UV*/ + static_cast<size_t>(B) * GB_CHUNKS_MAX * G * 2 /*gm, statistics partials*/ + 64;
+    return static_cast<size_t>(B) * G * 2 /*stats*/ + static_cast<size_t>(B) * gn_chunks(P, C) * 4 * C /*part*/ +
+           static_cast<size_t>(B) * 3 * C /*U, V, sum y*/ + static_cast<size_t>(B) * GB_CHUNKS_MAX * G * 2 /*gm, statistics partials*/ + 64;
 }
 
 cudaError_t groupnorm_silu_bwd_run(const GroupNormBwdArgs& a, float* scratch, cudaStream_t s) {
@@ -363,16 +376,16 @@ cudaError_t groupnorm_silu_bwd_run(const GroupNormBwdArgs& a, float* scratch, cu
     const int ld = a.ld > 0 ? a.ld : C;
     float2* stats = reinterpret_cast<float2*>(scratch);
     float* part = scratch + static_cast<size_t>(B) * G * 2;
-    float* UV = part + static_cast<size_t>(B) * nchunk * 3 * C;
-    float* gm = UV + static_cast<size_t>(B) * 2 * C;
+    float* UV = part + static_cast<size_t>(B) * nchunk * 4 * C;
+    float* gm = UV + static_cast<size_t>(B) * 3 * C;
     const uint4* y = reinterpret_cast<const uint4*>(a.y);
     const uint4* ds = reinterpret_cast<const uint4*>(a.ds);
     gn_stats_part_kernel<<<dim3(nchunk, B), 256, 0, s>>>(y, P, C, nchunk, reinterpret_cast<float2*>(gm));   // gm is free until the coefficient pass
     gn_stats_finish_kernel<<<B, 32, 0, s>>>(reinterpret_cast<const float2*>(gm), nchunk, P, C, a.eps, stats);
-    gn_bwd_sums_kernel<<<dim3(nchunk, B), 256, static_cast<size_t>(lanes) * 3 * C * sizeof(float), s>>>(
+    gn_bwd_sums_kernel<<<dim3(nchunk, B), 256, static_cast<size_t>(lanes) * 4 * C * sizeof(float), s>>>(
         y, ds, stats, a.gamma, a.beta, a.scale, a.shift, ld, P, C, nchunk, part);
     gn_bwd_coef_kernel<<<B, 512, 0, s>>>(part, nchunk, a.gamma, a.beta, a.scale, ld, P, C, UV, gm, a.dscale, a.dshift, a.dpost);
-    gn_bwd_affine_kernel<<<(C + 255) / 256, 256, 0, s>>>(UV, a.scale, ld, B, C, a.dgamma, a.dbeta);
+    gn_bwd_affine_kernel<<<(C + 255) / 256, 256, 0, s>>>(UV, a.scale, ld, B, C, P, a.gamma, stats, gm, a.dgamma, a.dbeta, a.dconv_bias);
     gn_bwd_dx_kernel<<<dim3(nchunk, B), 256, 0, s>>>(y, ds, stats, gm, a.gamma, a.beta, a.scale, a.shift, ld, P, C, nchunk,
                                                       reinterpret_cast<uint4*>(a.dy));
     return cudaGetLastError();

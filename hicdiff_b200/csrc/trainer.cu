@@ -479,8 +479,8 @@ int hd_op_conv3x3_wgrad(const uint16_t* x, const uint16_t* dy, float* dw, int32_
 }
 
 int hd_op_groupnorm_silu_bwd(const uint16_t* y, const uint16_t* ds, const float* gamma, const float* beta, const float* scale,
-                             const float* shift, uint16_t* dy, float* dgamma, float* dbeta, float* dscale, float* dshift, int32_t B,
-                             int32_t P, int32_t C, void* stream) {
+                             const float* shift, uint16_t* dy, float* dgamma, float* dbeta, float* dscale, float* dshift,
+                             float* dconv_bias, int32_t B, int32_t P, int32_t C, void* stream) {
     if (!y || !ds || !gamma || !beta || !dy || !dgamma || !dbeta || B < 1) return tfail("hd_op_groupnorm_silu_bwd: bad argument");
     if ((scale == nullptr) != (shift == nullptr)) return tfail("hd_op_groupnorm_silu_bwd: scale and shift come together");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -489,7 +489,7 @@ int hd_op_groupnorm_silu_bwd(const uint16_t* y, const uint16_t* ds, const float*
     GroupNormBwdArgs a;
     a.y = reinterpret_cast<const bf16*>(y); a.ds = reinterpret_cast<const bf16*>(ds); a.dy = reinterpret_cast<bf16*>(dy);
     a.B = B; a.P = P; a.C = C; a.gamma = gamma; a.beta = beta; a.eps = 1e-5f; a.scale = scale; a.shift = shift;
-    a.dgamma = dgamma; a.dbeta = dbeta; a.dscale = dscale; a.dshift = dshift;
+    a.dgamma = dgamma; a.dbeta = dbeta; a.dscale = dscale; a.dshift = dshift; a.dconv_bias = dconv_bias;
     cudaError_t ce = groupnorm_silu_bwd_run(a, scratch, s);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
     cudaFree(scratch);

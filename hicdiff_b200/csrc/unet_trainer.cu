@@ -122,7 +122,7 @@ struct UB {
         return true;
     }
     // weight (+ bias) gradient of conv `c` given dy and its source tensors; finishes with the standardisation backward
-    bool conv_wgrad(const std::string& tag, const ConvW* c, const bf16* dy, int H, const Ten& x0, const Ten* x1) {
+    bool conv_wgrad(const std::string& tag, const ConvW* c, const bf16* dy, int H, const Ten& x0, const Ten* x1, bool bias_done = false) {
         int ci0 = 0;
         const Ten* src[2] = {&x0, x1};
         for (int i = 0; i < 2; ++i) {
@@ -145,7 +145,7 @@ struct UB {
             const int Cout = c->Cout, K = c->Cin * c->k * c->k;
             push("ws_bwd", tag + ".ws", [=](cudaStream_t s) { return weight_standardize_bwd_run(w, gw, Cout, K, EPS, gw, s); });
         }
-        if (c->b) {
+        if (c->b && !bias_done) {      // (the GroupNorm backward already produced the bias gradient of the convs it follows)
             float* gb = c->b->g;
             float* part = cs_part;
             const long long M = rows(H);
@@ -202,11 +202,11 @@ struct UB {
             {
                 GroupNormBwdArgs a;
                 a.y = y2->p; a.ds = g; a.dy = T1; a.B = B; a.P = P; a.C = Cout; a.gamma = g2->w; a.beta = b2->w; a.eps = EPS;
-                a.dgamma = g2->g; a.dbeta = b2->g;
+                a.dgamma = g2->g; a.dbeta = b2->g; a.dconv_bias = c2->b->g;
                 float* sc = gn_scratch;
                 push("groupnorm_bwd", p + ".block2.norm.bwd", [a, sc](cudaStream_t s) { return groupnorm_silu_bwd_run(a, sc, s); });
             }
-            if (!conv_wgrad(p + ".block2.wgrad", c2, T1, H, *s1, nullptr)) return;
+            if (!conv_wgrad(p + ".block2.wgrad", c2, T1, H, *s1, nullptr, true)) return;
             if (!conv_dgrad(p + ".block2.dgrad", c2, T1, H, 0, Cout, T2, nullptr)) return;
             // block1: GroupNorm + FiLM + SiLU (in place on T2), conv1
             {
@@ -215,11 +215,11 @@ struct UB {
                 a.ld = ld;
                 if (sr3) { a.dpost = dfilm + film_off; }
                 else { a.scale = film + film_off; a.shift = film + film_off + Cout; a.dscale = dfilm + film_off; a.dshift = dfilm + film_off + Cout; }
-                a.dgamma = g1->g; a.dbeta = b1->g;
+                a.dgamma = g1->g; a.dbeta = b1->g; a.dconv_bias = c1->b->g;
                 float* sc = gn_scratch;
                 push("groupnorm_bwd", p + ".block1.norm.bwd", [a, sc](cudaStream_t s) { return groupnorm_silu_bwd_run(a, sc, s); });
             }
-            if (!conv_wgrad(p + ".block1.wgrad", c1, T2, H, *xa, xb.get())) return;
+            if (!conv_wgrad(p + ".block1.wgrad", c1, T2, H, *xa, xb.get(), true)) return;
             if (cr && !conv_wgrad(p + ".res_conv.wgrad", cr, g, H, *xa, xb.get())) return;
             // input gradients: conv1 path + residual path (identity or 1x1 conv) [+ what the tensor already holds]
             int ci0 = 0;

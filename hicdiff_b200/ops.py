@@ -233,7 +233,7 @@ def conv_wgrad_nhwc(x, dy, ksize, dw=None, cin_total=None, ci0=0):
     return dw
 
 
-def groupnorm_silu_bwd_nhwc(y, ds, gamma, beta, scale=None, shift=None):
+def groupnorm_silu_bwd_nhwc(y, ds, gamma, beta, scale=None, shift=None, want_conv_bias=False):
     """Backward of SiLU(GroupNorm_8(y) * (scale + 1) + shift): y, ds [B,H,W,C] bf16 -> (dy bf16, dgamma, dbeta, dscale, dshift)."""
     lib = _lib.load()
     _need_cuda(y, ds)
@@ -245,9 +245,12 @@ def groupnorm_silu_bwd_nhwc(y, ds, gamma, beta, scale=None, shift=None):
     dbeta = torch.empty_like(dgamma)
     dscale = torch.empty(B, C, device=y.device, dtype=torch.float32) if scale is not None else None
     dshift = torch.empty_like(dscale) if scale is not None else None
+    dcb = torch.empty_like(dgamma) if want_conv_bias else None
     _lib.check(lib.hd_op_groupnorm_silu_bwd(_lib.ptr(y), _lib.ptr(ds), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(scale), _lib.ptr(shift),
                                             _lib.ptr(dy), _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.ptr(dscale), _lib.ptr(dshift),
-                                            B, H * W, C, _lib.stream_ptr()), "hd_op_groupnorm_silu_bwd")
+                                            _lib.ptr(dcb), B, H * W, C, _lib.stream_ptr()), "hd_op_groupnorm_silu_bwd")
+    if want_conv_bias:
+        return dy, dgamma, dbeta, dscale, dshift, dcb
     return dy, dgamma, dbeta, dscale, dshift
 
 

@@ -166,10 +166,11 @@ HD_API int hd_op_conv_wgrad(const uint16_t* x, const uint16_t* dy, float* dw, in
                      int32_t Cout, int32_t ksize, int32_t cin_total, int32_t ci0, void* stream);
 /* Backward of Block's tail (hicdiff_condition.py:159-171): s = SiLU(GroupNorm_8(y) * (scale + 1) + shift).  y, ds, dy bf16
  * [B,P,C] (dy may alias ds); gamma / beta [C]; scale / shift [B,C] or both NULL (block2); outputs dgamma / dbeta [C] and,
- * when FiLM is present, dscale / dshift [B,C].  eps = 1e-5.  Synchronises. */
+ * when FiLM is present, dscale / dshift [B,C]; dconv_bias [C] (optional) = sum over samples and pixels of dy, i.e. the bias
+ * gradient of the conv that produced y, derived from the same reductions.  eps = 1e-5.  Synchronises. */
 HD_API int hd_op_groupnorm_silu_bwd(const uint16_t* y, const uint16_t* ds, const float* gamma, const float* beta, const float* scale,
                              const float* shift, uint16_t* dy, float* dgamma, float* dbeta, float* dscale, float* dshift,
-                             int32_t B, int32_t P, int32_t C, void* stream);
+                             float* dconv_bias, int32_t B, int32_t P, int32_t C, void* stream);
 /* Backward of the channel LayerNorm (hicdiff_condition.py:99-108): z = (x - mean_c) * rsqrt(var_c + 1e-5) * g; x, dz, dx bf16
  * [M,C] (dx must not alias x), dg fp32 [C].  Synchronises. */
 HD_API int hd_op_channel_layernorm_bwd(const uint16_t* x, const uint16_t* dz, const float* g, uint16_t* dx, float* dg, int64_t M,

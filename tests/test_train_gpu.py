@@ -231,8 +231,14 @@ def test_groupnorm_film_silu_backward(B, H, C, film):
         n = n * (leaves[3][:, :, None, None] + 1) + leaves[4][:, :, None, None]
     s = F.silu(n)
     grads = torch.autograd.grad(s, leaves, ds.permute(0, 3, 1, 2).double())
-    dy, dgamma, dbeta, dscale, dshift = ops.groupnorm_silu_bwd_nhwc(
-        y.to(DEV), ds.to(DEV), gamma.to(DEV), beta.to(DEV), scale.to(DEV) if film else None, shift.to(DEV) if film else None)
+    dy, dgamma, dbeta, dscale, dshift, dcb = ops.groupnorm_silu_bwd_nhwc(
+        y.to(DEV), ds.to(DEV), gamma.to(DEV), beta.to(DEV), scale.to(DEV) if film else None, shift.to(DEV) if film else None,
+        want_conv_bias=True)
+    # the bias gradient of the conv that produced y = sum over (b, pixels) of dy; values are O(1e-3) sums of cancelling terms,
+    # so compare on the scale of |dy| summed in quadrature
+    ref_cb = grads[0].sum(dim=(0, 2, 3))
+    scale_cb = float(grads[0].pow(2).sum(dim=(0, 2, 3)).sqrt().mean())
+    assert float((dcb.cpu().double() - ref_cb).abs().max()) <= 2e-3 * scale_cb + 1e-7, float((dcb.cpu().double() - ref_cb).abs().max())
     assert _rel(dy.permute(0, 3, 1, 2), grads[0]) <= 6e-3, _rel(dy.permute(0, 3, 1, 2), grads[0])     # bf16 output rounding
     assert _rel(dgamma, grads[1]) <= 1e-4 and _rel(dbeta, grads[2]) <= 1e-4
     if film:
