@@ -221,6 +221,35 @@ class _GaussianDiffusionBase(nn.Module):
         return x_start if self.objective == "pred_x0" else self.predict_v(x_start, t, noise)
 
     @torch.no_grad()
+    def p_mean_variance(self, x, t, x_self_cond=None, clip_denoised=True):
+        """(model_mean, posterior_variance, posterior_log_variance, x_start) for a batch of timesteps t [B] (long) -- the
+        reference's helper (hicdiff_condition.py:581-589); the eps-net runs on the device plan, the four results are composed
+        from the schedule buffers like the reference does."""
+        preds = self.model_predictions(x, t, x_self_cond)
+        x_start = preds.pred_x_start
+        if clip_denoised:
+            x_start = x_start.clamp(-1.0, 1.0)
+        mean, var, logvar = self.q_posterior(x_start=x_start, x_t=x, t=t)
+        return mean, var, logvar, x_start
+
+    @torch.no_grad()
+    def interpolate(self, x1, x2, t=None, lam=0.5, noise=None):
+        """hicdiff_condition.py:680-696: diffuse both inputs to step t, mix them, run the reverse chain from t - 1 down to 0
+        without conditioning (so, like the reference's, only for eps-nets built with self_condition=False)."""
+        if self.self_condition:
+            raise NotImplementedError("interpolate is unconditional (self_cond = None in the reference): it needs self_condition=False")
+        assert x1.shape == x2.shape
+        b = x1.shape[0]
+        t = self.num_timesteps - 1 if t is None else int(t)
+        tb = torch.full((b,), t, device=x1.device, dtype=torch.long)
+        img = (1 - lam) * self.q_sample(x1, tb) + lam * self.q_sample(x2, tb)
+        if t == 0:
+            return img
+        plan = self._sync_plan()
+        seed = 0 if noise is not None else self._next_seed(None)
+        return plan.sample(b, cond=None, noise=noise, seed=seed, t_start=t - 1, t_end=0, init=img)
+
+    @torch.no_grad()
     def p_sample(self, x, t: int, x_self_cond=None, noise=None):
         """One reverse step (hicdiff_condition.py:591-598): returns (x_{t-1}, x_start).  `noise` injects z."""
         t = int(t)

@@ -193,3 +193,35 @@ def test_errors_are_loud(nets):
         net(torch.zeros(1, 1, 32, 32).cuda(), torch.zeros(1, dtype=torch.long).cuda(), torch.zeros(1, 1, 32, 32).cuda())
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 1, 64, 64), torch.zeros(1, dtype=torch.long), torch.zeros(1, 1, 64, 64))   # CPU tensors
+
+
+def test_p_mean_variance_and_interpolate_helpers():
+    """The reference's remaining helper methods (hicdiff_condition.py:581-589, 680-696)."""
+    from hicdiff_b200 import hicdiff
+    from oracle import hicdiff_oracle as O
+
+    torch.manual_seed(0)
+    net = hicdiff.Unet(dim=64, dim_mults=(1, 2, 4, 8), self_condition=False)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    T = 40
+    diff = hicdiff.GaussianDiffusion(net, image_size=64, timesteps=T, loss_type="l2", beta_schedule="linear").to("cuda")
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 1, 64, 64, generator=g)
+    t = torch.tensor([3, 30])
+    mean, var, logvar, x0 = diff.p_mean_variance(x.cuda(), t.cuda())
+    buf = O.diffusion_buffers("linear", T)
+    with torch.no_grad():
+        eps = O.unet_forward(sd, x, t, None, self_condition=False)
+    ex = lambda name: buf[name][t].view(-1, 1, 1, 1)  # noqa: E731
+    x0_ref = (ex("sqrt_recip_alphas_cumprod") * x - ex("sqrt_recipm1_alphas_cumprod") * eps).clamp(-1, 1)
+    mean_ref = ex("posterior_mean_coef1") * x0_ref + ex("posterior_mean_coef2") * x
+    assert float((x0.cpu() - x0_ref).pow(2).mean().sqrt()) <= 2e-2 * float(x0_ref.pow(2).mean().sqrt()) + 1e-3
+    assert float((mean.cpu() - mean_ref).pow(2).mean().sqrt()) <= 2e-2 * float(mean_ref.pow(2).mean().sqrt()) + 1e-3
+    assert torch.equal(var.cpu().flatten(), buf["posterior_variance"][t]) and torch.equal(logvar.cpu().flatten(), buf["posterior_log_variance_clipped"][t])
+    # interpolate: q_sample both ends at t, mix, reverse chain t-1 .. 0; reproducible under torch.manual_seed
+    a, b = torch.rand(2, 1, 64, 64, generator=g) * 2 - 1, torch.rand(2, 1, 64, 64, generator=g) * 2 - 1
+    torch.manual_seed(9)
+    r1 = diff.interpolate(a.cuda(), b.cuda(), t=10, lam=0.3)
+    torch.manual_seed(9)
+    r2 = diff.interpolate(a.cuda(), b.cuda(), t=10, lam=0.3)
+    assert r1.shape == (2, 1, 64, 64) and torch.isfinite(r1).all() and torch.equal(r1, r2)
