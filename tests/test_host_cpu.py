@@ -84,6 +84,13 @@ def test_no_cpu_fallback():
         d.super_resolution(x)
     with pytest.raises(RuntimeError, match="only holds parameters"):
         net.downs[0][0](x)
+    # training: loss = diffusion(x) on a CPU module must raise too (the trainer is sm_100a-only), for both trainers
+    from hicdiff_b200.model.hicedrn_Diff import hicedrn_Diff
+
+    for m in (net, hicedrn_Diff(number_resnet=1, self_condition=True)):
+        dd = GaussianDiffusion(m, image_size=64, timesteps=10, loss_type="l2")
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            dd([x, x])
 
 
 def test_product_package_never_imports_the_oracle():

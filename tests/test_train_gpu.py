@@ -460,3 +460,26 @@ def test_two_forwards_before_backward_keep_their_own_gradients():
     diff.p_losses(x, t=t2, noise=noise.to(DEV)).backward()
     for k, p in net.named_parameters():
         assert torch.equal(both[k], g1[k] + p.grad), k
+
+
+def test_p2_loss_weights_reach_the_device_loss():
+    """p2_loss_weight_gamma != 0: the per-sample weights (hicdiff_condition.py:519, :744) scale the loss and every gradient."""
+    from hicdiff_b200 import hicdiff_condition
+    from hicdiff_b200.model.hicedrn_Diff import hicedrn_Diff
+
+    torch.manual_seed(2)
+    net = hicedrn_Diff(number_resnet=1, self_condition=True)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    diff = hicdiff_condition.GaussianDiffusion(net, image_size=64, timesteps=1000, loss_type="l2", beta_schedule="linear",
+                                               p2_loss_weight_gamma=1.0, p2_loss_weight_k=1).to(DEV)
+    clean, noisy = O.synthetic_tiles(3, seed=5)
+    t = torch.tensor([2, 500, 990])
+    noise = torch.randn(3, 1, 64, 64, generator=torch.Generator().manual_seed(8))
+    buf = O.diffusion_buffers("linear", 1000, p2_gamma=1.0, p2_k=1)
+    assert float(buf["p2_loss_weight"][t].max() / buf["p2_loss_weight"][t].min()) > 100           # the weights really differ
+    o_loss, o_grads = O.p_losses_and_grads(sd, buf, noisy, clean, t, noise, loss_type="l2", self_condition=True, num_blocks=1)
+    loss = diff.p_losses([noisy.to(DEV), clean.to(DEV)], t=t.to(DEV), noise=noise.to(DEV))
+    loss.backward()
+    assert abs(float(loss.detach()) - float(o_loss)) <= 5e-3 * abs(float(o_loss))
+    worst = max(_rel(p.grad, o_grads[k]) for k, p in net.named_parameters())
+    assert worst <= 3e-2, worst
