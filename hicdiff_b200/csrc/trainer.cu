@@ -235,8 +235,13 @@ int build(hd_trainer* t) {
         const bf16 *si = Sx[i], *ai = A[i], *xi = X[i];
         const int off = i * fw;
         float *gw = cw[i]->g, *gb = cb[i]->g;
+        // graph schedule: the HBM-bound reductions of a block (column sums of g, bias gradient, split-K reduction of dW) run on
+        // the side stream next to the tensor-bound GEMMs; the block's first GEMM waits for the previous block's side work (it
+        // overwrites ws2, and the next dgrad#1 overwrites g)
         b.push("colsum", pre + ".colsum_g", [=](cudaStream_t s) { return colsum_run(g, M, F, cs_part, 1.0f, 0, cs_g, s); });
+        t->ops.back().side = 1;
         if (!wgrad(pre + ".wgrad#2", g, si, ws2)) return 1;
+        t->ops.back().join = 1;
         ConvEpilogue e2;
         e2.out_scale = 0.1f;
         if (!b.conv(pre + ".dgrad#2", g, wqd[i], F, DS, e2)) return 1;
@@ -244,11 +249,13 @@ int build(hd_trainer* t) {
             return film_silu_bwd_run(DS, ai, DS, film, dfilm, ld, off, B, P, F, film_part, hs, s);
         });
         b.push("reduce", pre + ".bias_grad", [=](cudaStream_t s) { return edrn_bias_grad_run(film, dfilm, ld, off, B, cs_g, 0.1f, gb, F, hs, s); });
+        t->ops.back().side = 1;
         if (!wgrad(pre + ".wgrad#1", DS, xi, ws1)) return 1;
         b.push("reduce", pre + ".wgrad_reduce", [=](cudaStream_t s) {
             cudaError_t e = wgrad_reduce_run(ws1, WG_SPLITS, 1.0f, 0, gw, s);
             return e != cudaSuccess ? e : wgrad_reduce_run(ws2, WG_SPLITS, 0.1f, 1, gw, s);
         });
+        t->ops.back().side = 1;
         ConvEpilogue e1;
         e1.res = g; e1.ldr = F;
         if (!b.conv(pre + ".dgrad#1", DS, wqd[i], F, gnext, e1)) return 1;
@@ -262,6 +269,7 @@ int build(hd_trainer* t) {
         const float* u0 = t->cfg.self_condition ? t->cond : t->x;
         const float* u1 = t->cfg.self_condition ? t->x : nullptr;
         b.push("pointwise", "head.grad_sum", [=](cudaStream_t s) { return add_bf16_run(g, DBT, g0, static_cast<long long>(act_elems), s); });
+        t->ops.back().join = 1;     // the last block's side work shares cs_part / g with what follows
         b.push("colsum", "head.bias_grad", [=](cudaStream_t s) { return colsum_run(g0, M, F, cs_part, 1.0f, 0, gb, s); });
         b.push("thin_wgrad", "head.wgrad", [=](cudaStream_t s) { return thin_wgrad_run(g0, u0, u1, +1, B, thin_part, gw, s); });
     }
@@ -364,14 +372,35 @@ int hd_trainer_step(hd_trainer* t, const float* x_t, const float* cond, const fl
     static const bool use_graph = [] { const char* v = getenv("HD_TRAIN_GRAPH"); return !(v && v[0] == '0'); }();
     if (use_graph && t->graph[loss_type] == nullptr && t->eager_steps[loss_type] >= 1) {
         // capture (nothing executes) on the private stream: the caller's stream may be the legacy default stream
-        if (!t->cap_stream) T_TRY(cudaStreamCreateWithFlags(&t->cap_stream, cudaStreamNonBlocking));
+        if (!t->cap_stream) {
+            T_TRY(cudaStreamCreateWithFlags(&t->cap_stream, cudaStreamNonBlocking));
+            T_TRY(cudaStreamCreateWithFlags(&t->side_stream, cudaStreamNonBlocking));
+            T_TRY(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
+            T_TRY(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
+        }
         T_TRY(cudaStreamBeginCapture(t->cap_stream, cudaStreamCaptureModeThreadLocal));
         cudaError_t le = cudaSuccess;
         const char* bad = "";
+        bool side_dirty = false;
+        auto join_side = [&]() -> cudaError_t {
+            if (!side_dirty) return cudaSuccess;
+            side_dirty = false;
+            cudaError_t e = cudaEventRecord(t->ev_join, t->side_stream);
+            return e != cudaSuccess ? e : cudaStreamWaitEvent(t->cap_stream, t->ev_join, 0);
+        };
         for (const TOp& op : t->ops) {
-            le = op.fn(t->cap_stream);
+            if (op.side) {
+                le = cudaEventRecord(t->ev_fork, t->cap_stream);
+                if (le == cudaSuccess) le = cudaStreamWaitEvent(t->side_stream, t->ev_fork, 0);
+                if (le == cudaSuccess) le = op.fn(t->side_stream);
+                side_dirty = true;
+            } else {
+                if (op.join) le = join_side();
+                if (le == cudaSuccess) le = op.fn(t->cap_stream);
+            }
             if (le != cudaSuccess) { bad = op.tag.c_str(); break; }
         }
+        if (le == cudaSuccess) le = join_side();
         cudaGraph_t g = nullptr;
         cudaError_t ce = cudaStreamEndCapture(t->cap_stream, &g);
         if (le == cudaSuccess && ce == cudaSuccess) ce = cudaGraphInstantiate(&t->graph[loss_type], g, 0);
@@ -455,6 +484,9 @@ void hd_trainer_destroy(hd_trainer* t) {
     cudaSetDevice(t->device);
     for (int k = 0; k < 2; ++k) if (t->graph[k]) cudaGraphExecDestroy(t->graph[k]);
     if (t->cap_stream) cudaStreamDestroy(t->cap_stream);
+    if (t->side_stream) cudaStreamDestroy(t->side_stream);
+    if (t->ev_fork) cudaEventDestroy(t->ev_fork);
+    if (t->ev_join) cudaEventDestroy(t->ev_join);
     for (void* q : t->allocs) cudaFree(q);
     delete t;
 }

@@ -34,6 +34,11 @@ struct TOp {
     std::string tag;
     const char* kernel = "";
     double flops = 0;
+    // graph capture only (the eager path runs everything on the caller's stream, in order): side = 1 launches the op on the
+    // trainer's side stream, forked from the main stream at this point of the list (so it sees everything issued before it);
+    // join = 1 makes a main-stream op wait for all side work issued so far.  Lets HBM-bound reductions overlap the tensor-bound GEMMs.
+    int side = 0;
+    int join = 0;
 };
 }  // namespace hd
 
@@ -52,7 +57,8 @@ struct hd_trainer {
     // trainer-private stream, later steps replay (HD_TRAIN_GRAPH=0 keeps the eager path)
     int eager_steps[2] = {0, 0};
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
-    cudaStream_t cap_stream = nullptr;
+    cudaStream_t cap_stream = nullptr, side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace hd {

@@ -483,3 +483,29 @@ def test_p2_loss_weights_reach_the_device_loss():
     assert abs(float(loss.detach()) - float(o_loss)) <= 5e-3 * abs(float(o_loss))
     worst = max(_rel(p.grad, o_grads[k]) for k, p in net.named_parameters())
     assert worst <= 3e-2, worst
+
+
+@pytest.mark.parametrize("kind", ["hicedrn", "unet"])
+def test_graph_replay_equals_eager_step(kind):
+    """Step 1 runs eagerly, step 2 is captured as a CUDA graph (with the side-stream schedule), step 3 replays it: with the same
+    inputs and untouched weights all three must give bit-identical losses and gradients."""
+    from hicdiff_b200 import hicdiff_condition
+    from hicdiff_b200.model.hicedrn_Diff import hicedrn_Diff
+
+    torch.manual_seed(4)
+    net = hicedrn_Diff(number_resnet=3, self_condition=True) if kind == "hicedrn" else hicdiff_condition.Unet(dim=64, dim_mults=(1, 2, 4, 8), self_condition=True)
+    diff = hicdiff_condition.GaussianDiffusion(net, image_size=64, timesteps=1000, loss_type="l2", beta_schedule="linear").to(DEV)
+    clean, noisy = O.synthetic_tiles(4, seed=21)
+    t = torch.tensor([1, 250, 600, 999], device=DEV)
+    noise = torch.randn(4, 1, 64, 64, generator=torch.Generator().manual_seed(6)).to(DEV)
+    x = [noisy.to(DEV), clean.to(DEV)]
+    runs = []
+    for _ in range(3):
+        net.zero_grad()
+        loss = diff.p_losses(x, t=t, noise=noise)
+        loss.backward()
+        runs.append((loss.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters()}))
+    for later in runs[1:]:
+        assert torch.equal(later[0], runs[0][0])
+        for k in runs[0][1]:
+            assert torch.equal(later[1][k], runs[0][1][k]), k
