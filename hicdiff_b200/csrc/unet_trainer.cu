@@ -50,9 +50,20 @@ struct UB {
     std::vector<std::function<void()>> bwd;              // backward emitters, run in reverse
     std::vector<ConvW*> convs;
 
+    // Graph schedule (see TOp::side / join): weight-gradient work (wgrad + split reduction, standardisation backward, bias column
+    // sums) is a leaf of the backward graph, so it runs on the side stream next to the data-gradient chain; it reads the gradient
+    // temporaries T1 / T2 of its own layer, which the NEXT layer's backward overwrites -> the first main-stream op of every
+    // backward emitter joins.  On the low-resolution levels neither kind of kernel fills the GPU, so the two overlap.
+    bool side_mode = false, pending_join = false;
     void push(const char* kernel, const std::string& tag, std::function<cudaError_t(cudaStream_t)> fn, double flops = 0) {
         TOp o;
         o.fn = std::move(fn); o.tag = tag; o.kernel = kernel; o.flops = flops;
+        if (side_mode) {
+            o.side = 1;
+        } else if (pending_join) {
+            o.join = 1;
+            pending_join = false;
+        }
         t->ops.push_back(std::move(o));
     }
     bool fail(const std::string& m) { if (ok) { ok = false; tfail("%s", m.c_str()); } return false; }
@@ -123,6 +134,7 @@ struct UB {
     }
     // weight (+ bias) gradient of conv `c` given dy and its source tensors; finishes with the standardisation backward
     bool conv_wgrad(const std::string& tag, const ConvW* c, const bf16* dy, int H, const Ten& x0, const Ten* x1, bool bias_done = false) {
+        struct SideScope { UB* u; explicit SideScope(UB* p) : u(p) { u->side_mode = true; } ~SideScope() { u->side_mode = false; } } scope(this);
         int ci0 = 0;
         const Ten* src[2] = {&x0, x1};
         for (int i = 0; i < 2; ++i) {
@@ -543,9 +555,11 @@ int build_unet_trainer(hd_trainer* t) {
         x->gset = true;
     }
     for (auto it = u.bwd.rbegin(); it != u.bwd.rend(); ++it) {
+        u.pending_join = true;
         (*it)();
         if (!u.ok) return 1;
     }
+    u.pending_join = true;      // init_conv's column sums share cs_part with the side stream
     {   // init_conv: weight / bias gradient (its input needs none)
         float* spart = nullptr;
         if (dalloc(t, &spart, static_cast<size_t>(B) * 8 * 2 * 49 * dim * 4)) return 1;
