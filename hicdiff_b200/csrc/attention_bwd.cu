@@ -76,19 +76,34 @@ la_ctx_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, int n
     float ctx[DH], dctx[DH];     // [d] for this lane's e
 #pragma unroll
     for (int d = 0; d < DH; ++d) { ctx[d] = 0.f; dctx[d] = 0.f; }
-    for (int p = p0 + warp; p < p1; p += 8) {
-        const size_t ro = static_cast<size_t>(p) * QKV_LD;
-        const float q = __bfloat162float(base[ro]);
-        const float k = __bfloat162float(base[ro + HEADS * DH]);
-        const float v = __bfloat162float(base[ro + 2 * HEADS * DH]) * inv_n;
-        const float go = __bfloat162float(dob[static_cast<size_t>(p) * OUT_LD]);
-        const float qe = __expf(q - warp_max(q));
-        const float qs = qe / warp_sum(qe) * scale;            // lane = d
-        const float ks = __expf(k - km) * kinv;                // lane = d
+    // ncu (source page): 36 % of the stall samples sit on the first use of the 2-byte loads -- with one pixel per warp in flight
+    // an SM has ~4 KB outstanding, i.e. 0.6 TB/s for the whole GPU, exactly what the kernel reached.  Eight pixels' loads are
+    // issued before any of them is used.
+    constexpr int PF = 8;
+    for (int pb = p0 + warp; pb < p1; pb += 8 * PF) {
+        bf16 qa[PF], ka[PF], va[PF], ga[PF];
 #pragma unroll
-        for (int d = 0; d < DH; ++d) {
-            ctx[d] = fmaf(__shfl_sync(0xffffffffu, ks, d), v, ctx[d]);       // lane = e
-            dctx[d] = fmaf(__shfl_sync(0xffffffffu, qs, d), go, dctx[d]);
+        for (int u = 0; u < PF; ++u) {
+            const int p = min(pb + 8 * u, p1 - 1);
+            const size_t ro = static_cast<size_t>(p) * QKV_LD;
+            qa[u] = base[ro];
+            ka[u] = base[ro + HEADS * DH];
+            va[u] = base[ro + 2 * HEADS * DH];
+            ga[u] = dob[static_cast<size_t>(p) * OUT_LD];
+        }
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            if (pb + 8 * u >= p1) break;
+            const float q = __bfloat162float(qa[u]);
+            const float v = __bfloat162float(va[u]) * inv_n, go = __bfloat162float(ga[u]);
+            const float qe = __expf(q - warp_max(q));
+            const float qs = qe / warp_sum(qe) * scale;            // lane = d
+            const float ks = __expf(__bfloat162float(ka[u]) - km) * kinv;                // lane = d
+#pragma unroll
+            for (int d = 0; d < DH; ++d) {
+                ctx[d] = fmaf(__shfl_sync(0xffffffffu, ks, d), v, ctx[d]);       // lane = e
+                dctx[d] = fmaf(__shfl_sync(0xffffffffu, qs, d), go, dctx[d]);
+            }
         }
     }
 #pragma unroll
@@ -126,19 +141,35 @@ la_t_kernel(const bf16* __restrict__ qkv, int n, const float* __restrict__ kmax,
     const bf16* base = qkv + static_cast<size_t>(b) * n * QKV_LD + h * DH + lane;
     const float km = kmax[bh * DH + lane], kinv = 1.0f / ksum[bh * DH + lane];
     const float inv_n = 1.0f / static_cast<float>(n);
+    // the 32 x 32 matrix goes through shared memory: a direct per-lane row read is 32 strided sectors per instruction, repeated
+    // by every warp of 2048 CTAs -- ~70 us of L2 requests per launch whatever n is (measured at the 8x8 level)
+    __shared__ float s_d[DH][DH + 1];
     const float* dctx = cd + (static_cast<size_t>(bh) * 2 + 1) * DH * DH;
+    for (int i = threadIdx.x; i < DH * DH; i += 256) s_d[i / DH][i % DH] = dctx[i];
+    __syncthreads();
     float row[DH];
 #pragma unroll
-    for (int e = 0; e < DH; ++e) row[e] = dctx[lane * DH + e];
+    for (int e = 0; e < DH; ++e) row[e] = s_d[lane][e];
     float t = 0.f;
-    for (int p = p0 + warp; p < p1; p += 8) {
-        const size_t ro = static_cast<size_t>(p) * QKV_LD;
-        const float ks = __expf(__bfloat162float(base[ro + HEADS * DH]) - km) * kinv;
-        const float v = __bfloat162float(base[ro + 2 * HEADS * DH]) * inv_n;
-        float dks = 0.f;
+    constexpr int PF = 8;                                  // eight pixels' loads in flight per warp (see la_ctx_kernel)
+    for (int pb = p0 + warp; pb < p1; pb += 8 * PF) {
+        bf16 ka[PF], va[PF];
 #pragma unroll
-        for (int e = 0; e < DH; ++e) dks = fmaf(__shfl_sync(0xffffffffu, v, e), row[e], dks);
-        t = fmaf(dks, ks, t);
+        for (int u = 0; u < PF; ++u) {
+            const size_t ro = static_cast<size_t>(min(pb + 8 * u, p1 - 1)) * QKV_LD;
+            ka[u] = base[ro + HEADS * DH];
+            va[u] = base[ro + 2 * HEADS * DH];
+        }
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            if (pb + 8 * u >= p1) break;
+            const float ks = __expf(__bfloat162float(ka[u]) - km) * kinv;
+            const float v = __bfloat162float(va[u]) * inv_n;
+            float dks = 0.f;
+#pragma unroll
+            for (int e = 0; e < DH; ++e) dks = fmaf(__shfl_sync(0xffffffffu, v, e), row[e], dks);
+            t = fmaf(dks, ks, t);
+        }
     }
     s_t[warp][lane] = t;
     __syncthreads();
