@@ -354,6 +354,16 @@ cudaError_t linear_bwd_weight_run(const float* dY, int ldy, int off, const float
                                   int in_act, float* dW, float* db, cudaStream_t s);
 cudaError_t linear_bwd_input_run(const float* dY, int ldy, int off, const float* W, int rows, int in_f, int out_f, int accumulate,
                                  float* dX, int ldx, cudaStream_t s);
+struct LinSlot {            // one per-block time-embedding Linear inside the FiLM row
+    const float* W;         // [width, in_f]
+    float* gW;              // its gradient
+    float* gb;              // bias gradient [width]
+    int off, width;         // column slice of the FiLM row
+};
+cudaError_t linear_bwd_weight_batched_run(const float* dY, int ldy, const float* X, int ldx, int rows, int in_f, const LinSlot* slots,
+                                          int nslots, int max_width, cudaStream_t s);
+cudaError_t linear_bwd_input_batched_run(const float* dY, int ldy, int rows, int in_f, const LinSlot* slots, int nslots, float* part,
+                                         float* dX, cudaStream_t s);
 cudaError_t act_apply_run(const float* x, float* y, long long n, int act, cudaStream_t s);   // act: 1 SiLU, 2 GELU(erf)
 cudaError_t act_grad_run(float* d, const float* x, long long n, int act, cudaStream_t s);
 

@@ -422,6 +422,53 @@ __global__ void act_apply_kernel(const float* __restrict__ x, float* __restrict_
     if (i < n) y[i] = act_f(x[i], act);
 }
 
+// ---- the per-block time-embedding Linears, all slots in ONE launch each (19 / 32 launches of the single-slot kernels were
+// ~36 us of latency apiece: 8 % of the Unet training step)
+__global__ void __launch_bounds__(256)
+linear_bwd_weight_batched_kernel(const float* __restrict__ dY, int ldy, const float* __restrict__ X, int ldx, int rows, int in_f,
+                                 const LinSlot* __restrict__ slots) {
+    const LinSlot sl = slots[blockIdx.z];
+    const int j0 = blockIdx.y * LBW_J;
+    if (j0 >= sl.width) return;
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    float acc[LBW_J], accb[LBW_J];
+#pragma unroll
+    for (int j = 0; j < LBW_J; ++j) { acc[j] = 0.f; accb[j] = 0.f; }
+#pragma unroll 4
+    for (int r = 0; r < rows; ++r) {
+        const float xv = k < in_f ? __ldg(X + static_cast<size_t>(r) * ldx + k) : 0.f;
+        const float* g = dY + static_cast<size_t>(r) * ldy + sl.off + j0;
+#pragma unroll
+        for (int j = 0; j < LBW_J; ++j) {
+            const float gv = __ldg(g + j);
+            accb[j] += gv;
+            acc[j] = fmaf(gv, xv, acc[j]);
+        }
+    }
+    if (k < in_f) {
+#pragma unroll
+        for (int j = 0; j < LBW_J; ++j) sl.gW[static_cast<size_t>(j0 + j) * in_f + k] = acc[j];
+    }
+    if (k == 0) {
+#pragma unroll
+        for (int j = 0; j < LBW_J; ++j) sl.gb[j0 + j] = accb[j];
+    }
+}
+// part[slot][r][k] = sum_j dY[r, off + j] * W_slot[j, k]; grid (ceil(in_f / 256), rows, nslots)
+__global__ void __launch_bounds__(256)
+linear_bwd_input_batched_kernel(const float* __restrict__ dY, int ldy, int rows, int in_f, const LinSlot* __restrict__ slots,
+                                float* __restrict__ part) {
+    const LinSlot sl = slots[blockIdx.z];
+    const int r = blockIdx.y;
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= in_f) return;
+    const float* g = dY + static_cast<size_t>(r) * ldy + sl.off;
+    float acc = 0.f;
+#pragma unroll 16
+    for (int j = 0; j < sl.width; ++j) acc = fmaf(__ldg(g + j), __ldg(sl.W + static_cast<size_t>(j) * in_f + k), acc);
+    part[(static_cast<size_t>(blockIdx.z) * rows + r) * in_f + k] = acc;
+}
+
 // d[i] *= act'(x[i])
 __global__ void act_grad_kernel(float* __restrict__ d, const float* __restrict__ x, long long n, int act) {
     const long long i = blockIdx.x * 256ll + threadIdx.x;
@@ -519,6 +566,21 @@ cudaError_t linear_bwd_input_run(const float* dY, int ldy, int off, const float*
                                  float* dX, int ldx, cudaStream_t s) {
     linear_bwd_input_kernel<<<dim3((in_f + 255) / 256, rows), 256, 0, s>>>(dY, ldy, off, W, out_f, in_f, accumulate, dX, ldx);
     return cudaGetLastError();
+}
+// weight / bias gradients of all slots (X is shared: the activated time embedding); every slot width must be a multiple of 8
+cudaError_t linear_bwd_weight_batched_run(const float* dY, int ldy, const float* X, int ldx, int rows, int in_f, const LinSlot* slots,
+                                          int nslots, int max_width, cudaStream_t s) {
+    if (max_width % LBW_J != 0) return cudaErrorInvalidValue;
+    linear_bwd_weight_batched_kernel<<<dim3((in_f + 255) / 256, max_width / LBW_J, nslots), 256, 0, s>>>(dY, ldy, X, ldx, rows, in_f, slots);
+    return cudaGetLastError();
+}
+// dX[r, k] = sum over the slots (in slot order) of dY_slot W_slot; part: nslots * rows * in_f floats
+cudaError_t linear_bwd_input_batched_run(const float* dY, int ldy, int rows, int in_f, const LinSlot* slots, int nslots, float* part,
+                                         float* dX, cudaStream_t s) {
+    linear_bwd_input_batched_kernel<<<dim3((in_f + 255) / 256, rows, nslots), 256, 0, s>>>(dY, ldy, rows, in_f, slots, part);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return sum_parts_run(part, nslots, rows * in_f, 1.0f, 0, dX, s);
 }
 cudaError_t act_apply_run(const float* x, float* y, long long n, int act, cudaStream_t s) {
     act_apply_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(x, y, n, act);

@@ -274,15 +274,17 @@ int build(hd_trainer* t) {
         b.push("thin_wgrad", "head.wgrad", [=](cudaStream_t s) { return thin_wgrad_run(g0, u0, u1, +1, B, thin_part, gw, s); });
     }
     // ---------------------------------------------------------------- backward: time-embedding MLPs
-    for (int i = 0; i < nb; ++i) {
-        const float* w = mw[i]->w;
-        float *gw = mw[i]->g, *gb = mb[i]->g;
-        const int off = i * fw;
-        const int acc = i > 0 ? 1 : 0;
+    {
+        std::vector<LinSlot> hs_slots(nb);
+        for (int i = 0; i < nb; ++i) hs_slots[i] = LinSlot{mw[i]->w, mw[i]->g, mb[i]->g, i * fw, fw};
+        LinSlot* slots = nullptr;
+        float* lpart = nullptr;
+        if (dalloc(t, &slots, sizeof(LinSlot) * nb) || dalloc(t, &lpart, static_cast<size_t>(nb) * B * TIME_DIM * 4)) return 1;
+        if (cudaMemcpy(slots, hs_slots.data(), sizeof(LinSlot) * nb, cudaMemcpyHostToDevice) != cudaSuccess) return tfail("slot upload failed");
         const float* tin = sr3 ? temb : stemb;
-        b.push("time_bwd", "body." + std::to_string(i) + ".mlp.bwd", [=](cudaStream_t s) {
-            cudaError_t e = linear_bwd_weight_run(dfilm, ld, off, tin, TIME_DIM, B, TIME_DIM, fw, 0, gw, gb, s);
-            return e != cudaSuccess ? e : linear_bwd_input_run(dfilm, ld, off, w, B, TIME_DIM, fw, acc, d_act, TIME_DIM, s);
+        b.push("time_bwd", "body.*.mlp.bwd", [=](cudaStream_t s) {
+            cudaError_t e = linear_bwd_weight_batched_run(dfilm, ld, tin, TIME_DIM, B, TIME_DIM, slots, nb, fw, s);
+            return e != cudaSuccess ? e : linear_bwd_input_batched_run(dfilm, ld, B, TIME_DIM, slots, nb, lpart, d_act, s);
         });
     }
     {

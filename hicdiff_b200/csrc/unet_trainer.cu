@@ -576,15 +576,23 @@ int build_unet_trainer(hd_trainer* t) {
     // ---------------------------------------------------------------- backward: time-embedding MLPs
     {
         float* dfilm = u.dfilm;
-        for (size_t i = 0; i < blocks.size(); ++i) {
-            const float* w = mw[i]->w;
-            float *gw = mw[i]->g, *gb = mb[i]->g;
-            const int off = film_off[blocks[i].first], width = (sr3 ? 1 : 2) * blocks[i].second;
-            const int acc = i > 0 ? 1 : 0;
+        {
+            const int ns = static_cast<int>(blocks.size());
+            std::vector<LinSlot> hs_slots(ns);
+            int max_width = 0;
+            for (int i = 0; i < ns; ++i) {
+                const int width = (sr3 ? 1 : 2) * blocks[i].second;
+                hs_slots[i] = LinSlot{mw[i]->w, mw[i]->g, mb[i]->g, film_off[blocks[i].first], width};
+                max_width = width > max_width ? width : max_width;
+            }
+            LinSlot* slots = nullptr;
+            float* lpart = nullptr;
+            if (dalloc(t, &slots, sizeof(LinSlot) * ns) || dalloc(t, &lpart, static_cast<size_t>(ns) * B * time_dim * 4)) return 1;
+            if (cudaMemcpy(slots, hs_slots.data(), sizeof(LinSlot) * ns, cudaMemcpyHostToDevice) != cudaSuccess) return tfail("slot upload failed");
             const float* tin = sr3 ? temb : stemb;
-            u.push("time_bwd", blocks[i].first + ".mlp.bwd", [=](cudaStream_t s) {
-                cudaError_t e = linear_bwd_weight_run(dfilm, ld, off, tin, time_dim, B, time_dim, width, 0, gw, gb, s);
-                return e != cudaSuccess ? e : linear_bwd_input_run(dfilm, ld, off, w, B, time_dim, width, acc, d_act, time_dim, s);
+            u.push("time_bwd", "*.mlp.bwd", [=](cudaStream_t s) {
+                cudaError_t e = linear_bwd_weight_batched_run(dfilm, ld, tin, time_dim, B, time_dim, slots, ns, max_width, s);
+                return e != cudaSuccess ? e : linear_bwd_input_batched_run(dfilm, ld, B, time_dim, slots, ns, lpart, d_act, s);
             });
         }
         float *gw3 = w3->g, *gb3 = b3->g, *gw1 = w1->g, *gb1 = b1->g;
