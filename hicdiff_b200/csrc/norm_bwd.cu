@@ -153,6 +153,7 @@ gn_bwd_coef_kernel(const float* __restrict__ part, int nchunk, const float* __re
     const int b = blockIdx.x, c = threadIdx.x;
     float U = 0.f, V = 0.f, Wp = 0.f, Yp = 0.f;
     if (c < C) {
+#pragma unroll 4
         for (int k = 0; k < nchunk; ++k) {
             const float* pp = part + (static_cast<size_t>(b) * nchunk + k) * 4 * C + c;
             U += pp[0]; V += pp[C]; Wp += pp[2 * C]; Yp += pp[3 * C];

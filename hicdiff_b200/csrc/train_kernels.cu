@@ -161,16 +161,30 @@ __global__ void film_grad_finish_kernel(const float* __restrict__ part, float* _
 
 // the shared conv's bias gradient: its first use contributes sum_b (scale + 1) * dshift (da = dh * (scale + 1)), its second
 // 0.1 * colsum(g)
-__global__ void edrn_bias_grad_kernel(const float* __restrict__ film, const float* __restrict__ dfilm, int ld, int off, int B,
-                                      const float* __restrict__ colsum_g, float g_scale, float* __restrict__ dbias, int C, int has_scale) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+__global__ void __launch_bounds__(256)
+edrn_bias_grad_kernel(const float* __restrict__ film, const float* __restrict__ dfilm, int ld, int off, int B,
+                      const float* __restrict__ colsum_g, float g_scale, float* __restrict__ dbias, int C, int has_scale) {
+    // 32 channels x 8 sample slices per block (a single thread per channel over all B samples is a chain of dependent loads)
+    __shared__ float s_p[8][32];
+    const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    const int per = (B + 7) / 8;
+    const int b0 = sl * per, b1 = min(B, b0 + per);
     float t = 0.f;
-    for (int b = 0; b < B; ++b) {
-        if (has_scale) t = fmaf(film[static_cast<size_t>(b) * ld + off + c] + 1.0f, dfilm[static_cast<size_t>(b) * ld + off + C + c], t);
-        else t += dfilm[static_cast<size_t>(b) * ld + off + c];
+    if (c < C) {
+        for (int b = b0; b < b1; ++b) {
+            if (has_scale) t = fmaf(film[static_cast<size_t>(b) * ld + off + c] + 1.0f, dfilm[static_cast<size_t>(b) * ld + off + C + c], t);
+            else t += dfilm[static_cast<size_t>(b) * ld + off + c];
+        }
     }
-    dbias[c] = t + g_scale * colsum_g[c];
+    s_p[sl][cl] = t;
+    __syncthreads();
+    if (sl == 0 && c < C) {
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v += s_p[k][cl];
+        dbias[c] = v + g_scale * colsum_g[c];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ column sums
@@ -505,7 +519,7 @@ cudaError_t film_silu_bwd_run(const bf16* ds, const bf16* a, bf16* da, const flo
 }
 cudaError_t edrn_bias_grad_run(const float* film, const float* dfilm, int ld, int off, int B, const float* colsum_g, float g_scale,
                                float* dbias, int C, int has_scale, cudaStream_t s) {
-    edrn_bias_grad_kernel<<<(C + 255) / 256, 256, 0, s>>>(film, dfilm, ld, off, B, colsum_g, g_scale, dbias, C, has_scale);
+    edrn_bias_grad_kernel<<<(C + 31) / 32, 256, 0, s>>>(film, dfilm, ld, off, B, colsum_g, g_scale, dbias, C, has_scale);
     return cudaGetLastError();
 }
 int colsum_parts(long long M) { return static_cast<int>(M / 256 < 592 ? (M + 255) / 256 : 592); }

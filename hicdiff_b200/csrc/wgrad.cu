@@ -301,6 +301,7 @@ wgrad_general_reduce_kernel(const float* __restrict__ part, int nsplit, int taps
     float* o = dw + (static_cast<size_t>(co) * cin_total + ci0 + ci) * taps;
     for (int tap = 0; tap < taps; ++tap) {
         float t = 0.f;
+#pragma unroll 8
         for (int sp = 0; sp < nsplit; ++sp) t += __ldg(part + (static_cast<size_t>(sp) * taps + tap) * plane + i);
         o[tap] = accumulate ? fmaf(scale, t, o[tap]) : scale * t;
     }
