@@ -57,6 +57,11 @@ SIGNATURES = {
     "hd_trainer_profile": (C.c_int, [_vp, _i32, C.c_char_p, _i64, _vp]),
     "hd_trainer_device_bytes": (_i64, [_vp]),
     "hd_trainer_destroy": (None, [_vp]),
+    "hd_adam_create": (C.c_int, [C.POINTER(_vp), C.POINTER(_i64), _i32, C.POINTER(_vp)]),
+    "hd_adam_step": (C.c_int, [_vp, C.POINTER(_vp), C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _vp]),
+    "hd_adam_state": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
+    "hd_adam_set_step": (C.c_int, [_vp, _i64]),
+    "hd_adam_destroy": (None, [_vp]),
     "hd_op_conv3x3_wgrad": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "hd_op_conv_wgrad": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "hd_op_groupnorm_silu_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),

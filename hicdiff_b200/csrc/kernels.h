@@ -366,6 +366,17 @@ cudaError_t linear_bwd_input_batched_run(const float* dY, int ldy, int rows, int
                                          float* dX, cudaStream_t s);
 cudaError_t act_apply_run(const float* x, float* y, long long n, int act, cudaStream_t s);   // act: 1 SiLU, 2 GELU(erf)
 cudaError_t act_grad_run(float* d, const float* x, long long n, int act, cudaStream_t s);
+// fused Adam: one block per chunk (<= ADAM_CHUNK elements of one parameter tensor); exp_avg / exp_avg_sq are flat state buffers
+struct AdamChunk {
+    float* param;
+    const float* grad;
+    long long state_off;
+    int n;
+    int pad;
+};
+constexpr int ADAM_CHUNK = 4096;
+cudaError_t adam_step_run(const AdamChunk* chunks, int nchunks, float* exp_avg, float* exp_avg_sq, double lr, double beta1, double beta2,
+                          double eps, double weight_decay, long long step, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------
 // norm_bwd.cu -- backward of GroupNorm(8)+FiLM+SiLU, channel LayerNorm, weight standardisation (Unet training blocks)

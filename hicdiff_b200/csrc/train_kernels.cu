@@ -489,6 +489,46 @@ __global__ void act_grad_kernel(float* __restrict__ d, const float* __restrict__
     if (i < n) d[i] *= act_grad_f(x[i], act);
 }
 
+// ---- fused Adam (train.py:111 torch.optim.Adam) over many parameter tensors in one launch ----
+// The arithmetic follows torch's own multi-tensor Adam operation by operation (lerp, mul, addcmul, sqrt, div, add, addcdiv with
+// the scalars rounded to fp32 the way its kernels receive them) so a model trained with either optimiser follows the same path.
+struct AdamScalars {
+    float w1, beta2, w2, bc2_sqrt, eps, neg_step, wd;
+};
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, const AdamScalars& a) {
+    if (a.wd != 0.f) g = fmaf(a.wd, p, g);
+    const float d = g - m;
+    m = a.w1 < 0.5f ? fmaf(a.w1, d, m) : g - d * (1.f - a.w1);
+    v = __fmul_rn(v, a.beta2);
+    v = fmaf(a.w2, __fmul_rn(g, g), v);
+    const float den = __fadd_rn(__fdiv_rn(sqrtf(v), a.bc2_sqrt), a.eps);
+    p = fmaf(a.neg_step, __fdiv_rn(m, den), p);
+}
+__global__ void __launch_bounds__(256) adam_step_kernel(const AdamChunk* __restrict__ chunks, float* __restrict__ exp_avg,
+                                                        float* __restrict__ exp_avg_sq, AdamScalars a) {
+    const AdamChunk c = chunks[blockIdx.x];
+    float* p = c.param;
+    const float* g = c.grad;
+    float* m = exp_avg + c.state_off;
+    float* v = exp_avg_sq + c.state_off;
+    const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                       reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+    const int n4 = vec ? c.n / 4 : 0;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        float4 pv = reinterpret_cast<float4*>(p)[i];
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+        float4 mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        adam_update(pv.x, gv.x, mv.x, vv.x, a);
+        adam_update(pv.y, gv.y, mv.y, vv.y, a);
+        adam_update(pv.z, gv.z, mv.z, vv.z, a);
+        adam_update(pv.w, gv.w, mv.w, vv.w, a);
+        reinterpret_cast<float4*>(p)[i] = pv;
+        reinterpret_cast<float4*>(m)[i] = mv;
+        reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    for (int i = n4 * 4 + threadIdx.x; i < c.n; i += blockDim.x) adam_update(p[i], g[i], m[i], v[i], a);
+}
+
 }  // namespace
 
 // ================================================================================================ launchers
@@ -595,6 +635,22 @@ cudaError_t linear_bwd_input_batched_run(const float* dY, int ldy, int rows, int
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return sum_parts_run(part, nslots, rows * in_f, 1.0f, 0, dX, s);
+}
+// one Adam update; hyper-parameters in double as Python holds them, rounded to fp32 exactly where torch rounds them
+cudaError_t adam_step_run(const AdamChunk* chunks, int nchunks, float* exp_avg, float* exp_avg_sq, double lr, double beta1, double beta2,
+                          double eps, double weight_decay, long long step, cudaStream_t s) {
+    if (nchunks <= 0) return cudaSuccess;
+    const double bc1 = 1.0 - pow(beta1, static_cast<double>(step)), bc2 = 1.0 - pow(beta2, static_cast<double>(step));
+    AdamScalars a;
+    a.w1 = static_cast<float>(1.0 - beta1);
+    a.beta2 = static_cast<float>(beta2);
+    a.w2 = static_cast<float>(1.0 - beta2);
+    a.bc2_sqrt = static_cast<float>(pow(bc2, 0.5));
+    a.eps = static_cast<float>(eps);
+    a.neg_step = static_cast<float>((lr / bc1) * -1.0);
+    a.wd = static_cast<float>(weight_decay);
+    adam_step_kernel<<<nchunks, 256, 0, s>>>(chunks, exp_avg, exp_avg_sq, a);
+    return cudaGetLastError();
 }
 cudaError_t act_apply_run(const float* x, float* y, long long n, int act, cudaStream_t s) {
     act_apply_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(x, y, n, act);

@@ -156,6 +156,20 @@ HD_API int hd_trainer_num_launches(hd_trainer* trainer);
 HD_API int hd_trainer_profile(hd_trainer* trainer, int32_t reps, char* buf, int64_t buflen, void* stream);
 HD_API int64_t hd_trainer_device_bytes(hd_trainer* trainer);
 HD_API void hd_trainer_destroy(hd_trainer* trainer);
+/* The optimiser of the training loop (train.py:111 `torch.optim.Adam(diffusion.parameters(), lr=2e-5)`, stepped at :129) as one
+ * launch over all parameter tensors; the arithmetic follows torch's multi-tensor Adam operation by operation (L2-style
+ * weight_decay added to the gradient; no amsgrad / maximize).  params: nparams device pointers (fp32, contiguous) with numels
+ * elements each, updated in place; the moments are owned by the handle (zero-initialised).  hd_adam_step takes this step's
+ * gradient pointers (same order, fp32, contiguous; the table is re-uploaded only when a pointer changed), counts the step
+ * itself and is asynchronous on `stream`.  hd_adam_state exposes parameter `index`'s moments (device pointers into the flat
+ * state) and the step count for checkpointing; hd_adam_set_step restores the count. */
+typedef struct hd_adam hd_adam;
+HD_API int hd_adam_create(const void* const* params, const int64_t* numels, int32_t nparams, hd_adam** out);
+HD_API int hd_adam_step(hd_adam* adam, const void* const* grads, double lr, double beta1, double beta2, double eps, double weight_decay,
+                 void* stream);
+HD_API int hd_adam_state(hd_adam* adam, int32_t index, float** exp_avg, float** exp_avg_sq, int64_t* step);
+HD_API int hd_adam_set_step(hd_adam* adam, int64_t step);
+HD_API void hd_adam_destroy(hd_adam* adam);
 /* The two conv gradients as single operators (256 -> 256, 3x3 "same", 64x64 tiles; activations bf16 NHWC as uint16):
  * dw fp32 [256,256,3,3] = d/dW of conv2d(x, W) given dy; dx = d/dx given dy and W (fp32, reference layout).  Synchronise. */
 HD_API int hd_op_conv3x3_wgrad(const uint16_t* x, const uint16_t* dy, float* dw, int32_t B, void* stream);

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--model", choices=["hicedrn", "unet"], default="hicedrn")
+    ap.add_argument("--optim", choices=["torch", "fused"], default="torch", help="torch.optim.Adam (train.py verbatim) or hicdiff_b200.optim.Adam")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -49,7 +50,13 @@ def main():
     diff.train()
     if world > 1:
         T.enable_gradient_allreduce(net)
-    opt = torch.optim.Adam(diff.parameters(), lr=2e-5)
+    optname = "fused Adam (hd_adam_step)" if a.optim == "fused" else "torch Adam"
+    if a.optim == "fused":
+        from hicdiff_b200.optim import Adam as FusedAdam
+
+        opt = FusedAdam(diff.parameters(), lr=2e-5)
+    else:
+        opt = torch.optim.Adam(diff.parameters(), lr=2e-5)
     clean, noisy = synthetic_tiles(a.batch, seed=1234 + rank)
     x = [noisy.cuda(), clean.cuda()]
     torch.manual_seed(1 + rank)
@@ -82,8 +89,8 @@ def main():
         out = {"metric": "train_tiles_per_sec", "value": a.batch * world / (ms * 1e-3), "unit": "tiles/s", "n_gpus": world,
                "ms_per_step": ms, "steps": a.steps, "warmup": a.warmup, "wall_s": time.time() - t0, "loss": float(loss.detach()),
                "dtype": "bf16 activations / fp32 parameters and gradients", "data": "synthetic",
-               "config": {"workload": (f"conditional Unet (dim 64, mults 1/2/4/8) p_losses l2 + backward + torch Adam, batch {a.batch}/GPU" if a.model == "unet" else
-                                       f"hicedrn_Diff({a.blocks} blocks, self_condition) p_losses l2 + backward + torch Adam, batch {a.batch}/GPU"),
+               "config": {"workload": (f"conditional Unet (dim 64, mults 1/2/4/8) p_losses l2 + backward + {optname}, batch {a.batch}/GPU" if a.model == "unet" else
+                                       f"hicedrn_Diff({a.blocks} blocks, self_condition) p_losses l2 + backward + {optname}, batch {a.batch}/GPU"),
                           "allreduce": "one NCCL all-reduce of the flat fp32 gradient buffer per step" if world > 1 else "none"},
                "model_tflops": 3 * fwd_flops * a.batch / (ms * 1e-3) / 1e12,
                "device_bytes": net._trainer.device_bytes(), "launch_groups": net._trainer.num_launch_groups()}

@@ -228,3 +228,19 @@ def test_gradient_allreduce_mean_world2_gloo():
     assert got[0] == want and got[1] == want
     solo = torch.ones(4)
     assert T.allreduce_mean_(solo) is solo and solo.tolist() == [1.0] * 4     # no process group: a no-op
+
+
+def test_fused_adam_has_no_cpu_path():
+    """hicdiff_b200.optim.Adam mirrors torch.optim.Adam's argument checks and refuses CPU parameters (no fallback)."""
+    from hicdiff_b200.optim import Adam
+
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    for bad in (dict(lr=-1.0), dict(eps=-1.0), dict(betas=(1.0, 0.9)), dict(betas=(0.9, 1.0)), dict(weight_decay=-1.0)):
+        with pytest.raises(ValueError):
+            Adam([p], **bad)
+    opt = Adam([p], lr=1e-3)
+    assert opt.param_groups[0]["lr"] == 1e-3 and opt.param_groups[0]["betas"] == (0.9, 0.999)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        opt.step()
+    assert torch.equal(p.detach(), torch.zeros(4))
