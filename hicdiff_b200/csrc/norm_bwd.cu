@@ -92,6 +92,7 @@ __device__ __forceinline__ float silu_grad(float h) {     // sigmoid through one
 }
 
 constexpr int GB_CHUNKS_MAX = 16;
+constexpr int GB_PIX = 4;          // pixels in flight per thread in the two streaming passes
 
 // ---------------------------------------------------------------------------------------------- pass 1: (U, V) partials
 // grid (nchunk, B); thread = (8-channel chunk cc, pixel lane pl), lanes = 256 / (C / 8)
@@ -116,18 +117,35 @@ gn_bwd_sums_kernel(const uint4* __restrict__ y, const uint4* __restrict__ ds, co
         U[j] = 0.f; V[j] = 0.f; Ws[j] = 0.f; Ys[j] = 0.f;
     }
     const size_t base = (static_cast<size_t>(b) * P + static_cast<size_t>(chunk) * ppc) * cpp + cc;
-    for (int p = pl; p < ppc; p += lanes) {
-        float yv[8], g[8];
-        unpack8(__ldg(y + base + static_cast<size_t>(p) * cpp), yv);
-        unpack8(__ldg(ds + base + static_cast<size_t>(p) * cpp), g);
+    // GB_PIX pixels' loads are issued before any of them is consumed (the pass is latency-bound at ~80 registers / 3 CTAs per SM);
+    // a pixel past the chunk reads as zeros and adds nothing, so the per-thread summation order is unchanged
+    for (int p0 = pl; p0 < ppc; p0 += lanes * GB_PIX) {
+        uint4 ry[GB_PIX], rg[GB_PIX];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float xh = (yv[j] - st.x) * st.y;
-            const float dh = g[j] * silu_grad(fmaf(xh, k1[j], k0[j]));
-            U[j] += dh;
-            V[j] = fmaf(dh, xh, V[j]);
-            Ws[j] += g[j];
-            Ys[j] += yv[j];
+        for (int k = 0; k < GB_PIX; ++k) {
+            const int p = p0 + k * lanes;
+            ry[k] = rg[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (p < ppc) {
+                ry[k] = __ldg(y + base + static_cast<size_t>(p) * cpp);
+                rg[k] = __ldg(ds + base + static_cast<size_t>(p) * cpp);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < GB_PIX; ++k) {
+            float yv[8], g[8];
+            unpack8(ry[k], yv);
+            unpack8(rg[k], g);
+            if (p0 + k * lanes < ppc) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float xh = (yv[j] - st.x) * st.y;
+                    const float dh = g[j] * silu_grad(fmaf(xh, k1[j], k0[j]));
+                    U[j] += dh;
+                    V[j] = fmaf(dh, xh, V[j]);
+                    Ws[j] += g[j];
+                    Ys[j] += yv[j];
+                }
+            }
         }
     }
 #pragma unroll
@@ -240,18 +258,31 @@ gn_bwd_dx_kernel(const uint4* __restrict__ y, const uint4* ds, const float2* __r
         k0[j] = fmaf(beta[c], sc1, sh);
     }
     const size_t base = (static_cast<size_t>(b) * P + static_cast<size_t>(chunk) * ppc) * cpp + cc;
-    for (int p = pl; p < ppc; p += lanes) {
-        const size_t i = base + static_cast<size_t>(p) * cpp;
-        float yv[8], gr[8];
-        unpack8(__ldg(y + i), yv);
-        unpack8(ds[i], gr);
+    for (int p0 = pl; p0 < ppc; p0 += lanes * GB_PIX) {
+        uint4 ry[GB_PIX], rg[GB_PIX];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float xh = (yv[j] - st.x) * st.y;
-            const float dh = gr[j] * silu_grad(fmaf(xh, k1[j], k0[j]));
-            gr[j] = st.y * (dh * k1[j] - m1 - xh * m2);
+        for (int k = 0; k < GB_PIX; ++k) {          // all loads first (dy may alias ds: each pixel is read before it is written)
+            const int p = p0 + k * lanes;
+            if (p < ppc) {
+                ry[k] = __ldg(y + base + static_cast<size_t>(p) * cpp);
+                rg[k] = ds[base + static_cast<size_t>(p) * cpp];
+            }
         }
-        dy[i] = pack8(gr);
+#pragma unroll
+        for (int k = 0; k < GB_PIX; ++k) {
+            const int p = p0 + k * lanes;
+            if (p >= ppc) break;
+            float yv[8], gr[8];
+            unpack8(ry[k], yv);
+            unpack8(rg[k], gr);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = (yv[j] - st.x) * st.y;
+                const float dh = gr[j] * silu_grad(fmaf(xh, k1[j], k0[j]));
+                gr[j] = st.y * (dh * k1[j] - m1 - xh * m2);
+            }
+            dy[base + static_cast<size_t>(p) * cpp] = pack8(gr);
+        }
     }
 }
 

@@ -291,6 +291,7 @@ wgrad_general_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
 }
 
 // dw[(co * cin_total + ci0 + ci) * taps + tap] (+)= scale * sum_split part[split][tap][co][ci]; one thread per (co, ci)
+// (1x1 convs: reads and writes are both contiguous in ci)
 __global__ void __launch_bounds__(256)
 wgrad_general_reduce_kernel(const float* __restrict__ part, int nsplit, int taps, int Cout, int Cin, int cin_total, int ci0,
                             float scale, int accumulate, float* __restrict__ dw) {
@@ -301,10 +302,31 @@ wgrad_general_reduce_kernel(const float* __restrict__ part, int nsplit, int taps
     float* o = dw + (static_cast<size_t>(co) * cin_total + ci0 + ci) * taps;
     for (int tap = 0; tap < taps; ++tap) {
         float t = 0.f;
-#pragma unroll 8
         for (int sp = 0; sp < nsplit; ++sp) t += __ldg(part + (static_cast<size_t>(sp) * taps + tap) * plane + i);
         o[tap] = accumulate ? fmaf(scale, t, o[tap]) : scale * t;
     }
+}
+
+// 3x3 form: one CTA per (co, 32 input channels), thread (tap, ci): nine times the parallelism of the kernel above (the split
+// loop is a chain of dependent loads per thread), 128-byte reads per warp, and the (ci, tap) transpose goes through shared
+// memory so the 288 outputs of the CTA -- contiguous in dw -- are written in order.  Same summation order: same bits.
+__global__ void __launch_bounds__(288)
+wgrad_general_reduce9_kernel(const float* __restrict__ part, int nsplit, int Cout, int Cin, int cin_total, int ci0, float scale,
+                             int accumulate, float* __restrict__ dw) {
+    __shared__ float s_t[32][9 + 1];
+    const int nci = Cin / 32;
+    const int co = blockIdx.x / nci, c0 = (blockIdx.x - co * nci) * 32;
+    const int tap = threadIdx.x >> 5, cl = threadIdx.x & 31;
+    const size_t plane = static_cast<size_t>(Cout) * Cin;
+    const float* src = part + static_cast<size_t>(tap) * plane + static_cast<size_t>(co) * Cin + c0 + cl;
+    float t = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) t += __ldg(src + static_cast<size_t>(sp) * 9 * plane);
+    s_t[cl][tap] = t;
+    __syncthreads();
+    const int j = threadIdx.x;                  // output (ci = j / 9, tap = j % 9) of this CTA's contiguous 288-float span
+    float* o = dw + (static_cast<size_t>(co) * cin_total + ci0 + c0) * 9 + j;
+    const float v = s_t[j / 9][j % 9];
+    *o = accumulate ? fmaf(scale, v, *o) : scale * v;
 }
 
 }  // namespace
@@ -391,7 +413,10 @@ cudaError_t wgrad_general_run(const WgradGenLaunch& l, cudaStream_t s) {
 cudaError_t wgrad_general_reduce_run(const WgradGenLaunch& l, int cin_total, int ci0, float scale, int accumulate, float* dw,
                                      cudaStream_t s) {
     const int n = l.Cout * l.Cin;
-    wgrad_general_reduce_kernel<<<(n + 255) / 256, 256, 0, s>>>(l.part, l.nsplit, l.taps, l.Cout, l.Cin, cin_total, ci0, scale, accumulate, dw);
+    if (l.taps == 9 && l.Cin % 32 == 0)
+        wgrad_general_reduce9_kernel<<<n / 32, 288, 0, s>>>(l.part, l.nsplit, l.Cout, l.Cin, cin_total, ci0, scale, accumulate, dw);
+    else
+        wgrad_general_reduce_kernel<<<(n + 255) / 256, 256, 0, s>>>(l.part, l.nsplit, l.taps, l.Cout, l.Cin, cin_total, ci0, scale, accumulate, dw);
     return cudaGetLastError();
 }
 
