@@ -273,6 +273,16 @@ cudaError_t step_advance_run(SampleCtl* ctl, int delta, cudaStream_t s);
 // prep.cu -- one-off weight preparation and the time-embedding tables
 // ---------------------------------------------------------------------------------------------
 // [Cout, Cin, k, k] fp32 -> [Npad, k*k*Cin] bf16 with K order (tap, cin); optional weight standardisation
+// training: every conv's forward (qf) and dgrad (qd) bf16 layouts + weight-standardisation statistics in two launches
+struct PrepSlot {
+    const float* w;
+    bf16* qf;
+    bf16* qd;
+    float2* stats;
+    int Cout, Cin, ksize, ws;
+};
+cudaError_t prep_weights_batched_run(const PrepSlot* slots, const int2* fwd_rows, int nfwd, const int2* bwd_rows, int nbwd, float eps,
+                                     cudaStream_t s);
 cudaError_t prep_conv_weight_run(const float* w, bf16* out, int Cout, int Cin, int ksize, int standardize, float eps,
                                  int Npad, cudaStream_t s);
 // Downsample 1x1 weight [Cout, 4*C] with K order (c, p1, p2) -> (p1, p2, c)
@@ -421,9 +431,6 @@ cudaError_t stem_wgrad_run(const bf16* G, const float* u0, const float* u1, int 
 int head_bwd_parts(long long M);
 cudaError_t head_bwd_run(const bf16* x, const float* d_eps, const float* w, long long M, int C, bf16* dx, float* part, float* dw,
                          cudaStream_t s);
-cudaError_t ws_stats_run(const float* w, int Cout, int K, float eps, float2* stats, cudaStream_t s);
-// [Cout, Cin, k, k] fp32 -> [Cin, (tap', cout)] bf16, tap' = k*k - 1 - tap; stats != nullptr: standardised with (mean, rstd)[Cout]
-cudaError_t prep_dgrad_weight_general_run(const float* w, const float2* stats, bf16* out, int Cout, int Cin, int ksize, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------
 // dataprep.cu -- contact triples -> dense matrix, empty-bin removal, exact percentile, normalisation, noise injection

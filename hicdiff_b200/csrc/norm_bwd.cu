@@ -391,22 +391,32 @@ ws_bwd_kernel(const float* __restrict__ w, const float* dwt, int K, float eps, f
     for (int i = threadIdx.x; i < K; i += 256) orow[i] = rstd * (gr[i] - a - (wr[i] - mean) * rstd * bsum);
 }
 
-// out[i] = sum_k part[k][i]: 32 columns per block, 8 threads per column over contiguous slices, fixed combination order
-__global__ void __launch_bounds__(256)
+// out[i] = sum_k part[k][i]: 32 columns per block, 32 threads per column over contiguous slices (eight loads in flight each), fixed combination order
+constexpr int SUM_SLICES = 32;      // threads per column (each sums a contiguous slice of the partials)
+__global__ void __launch_bounds__(32 * SUM_SLICES)
 sum_rows_kernel(const float* __restrict__ part, int nparts, int n, float* __restrict__ out) {
-    __shared__ float s_p[8][32];
+    __shared__ float s_p[SUM_SLICES][32];
     const int col = blockIdx.x * 32 + (threadIdx.x & 31), sl = threadIdx.x >> 5;
-    const int per = (nparts + 7) / 8;
+    const int per = (nparts + SUM_SLICES - 1) / SUM_SLICES;
     const int k0 = sl * per, k1 = min(nparts, k0 + per);
     float t = 0.f;
-    if (col < n)
-        for (int k = k0; k < k1; ++k) t += part[static_cast<size_t>(k) * n + col];
+    if (col < n) {
+        int k = k0;
+        for (; k + 8 <= k1; k += 8) {              // eight independent loads in flight, added in order
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(part + static_cast<size_t>(k + j) * n + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t += v[j];
+        }
+        for (; k < k1; ++k) t += __ldg(part + static_cast<size_t>(k) * n + col);
+    }
     s_p[sl][threadIdx.x & 31] = t;
     __syncthreads();
     if (sl == 0 && col < n) {
         float v = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v += s_p[k][threadIdx.x];
+        for (int k = 0; k < SUM_SLICES; ++k) v += s_p[k][threadIdx.x];
         out[col] = v;
     }
 }
@@ -463,7 +473,7 @@ cudaError_t channel_layernorm_bwd_run(const bf16* x, const bf16* dz, const float
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    sum_rows_kernel<<<(C + 31) / 32, 256, 0, s>>>(part, blocks, C, dgain);
+    sum_rows_kernel<<<(C + 31) / 32, 32 * SUM_SLICES, 0, s>>>(part, blocks, C, dgain);
     return cudaGetLastError();
 }
 

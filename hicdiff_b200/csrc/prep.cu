@@ -16,12 +16,11 @@
 namespace hd {
 namespace {
 
-__global__ void __launch_bounds__(256)
-prep_conv_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int ksize,
-                        int standardize, float eps, int Npad) {
+// one output channel (GEMM row) per CTA; stat_out (optional) receives the row's (mean, rstd) when standardising
+__device__ __forceinline__ void prep_conv_weight_row(const float* __restrict__ w, bf16* __restrict__ out, const int co, int Cout, int Cin,
+                                                     int ksize, int standardize, float eps, float2* stat_out) {
     __shared__ float s_red[8];
     __shared__ float s_stat[2];
-    const int co = blockIdx.x;
     const int tid = threadIdx.x;
     const int kk = ksize * ksize;
     const int K = Cin * kk;
@@ -58,12 +57,43 @@ prep_conv_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int
         }
         __syncthreads();
         rstd = s_stat[1];
+        if (stat_out != nullptr && tid == 0) *stat_out = make_float2(mean, rstd);
     }
     // reference layout [Cout][Cin][ky][kx]  ->  [Cout][(ky*ks + kx) * Cin + ci]
     for (int i = tid; i < K; i += blockDim.x) {
         const int tap = i / Cin;
         const int ci = i - tap * Cin;
         const float v = (wrow[ci * kk + tap] - mean) * rstd;
+        orow[i] = __float2bfloat16(v);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+prep_conv_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int ksize,
+                        int standardize, float eps, int Npad) {
+    prep_conv_weight_row(w, out, blockIdx.x, Cout, Cin, ksize, standardize, eps, nullptr);
+}
+
+// ---- the training step's per-step weight preparation for ALL convs in two launches (it was three short launches per conv:
+// ~180 graph nodes whose launch latency, not their work, was the cost).  rows[i] = (slot, row): forward rows are output
+// channels (the standardised bf16 GEMM layout + the (mean, rstd) the backward reuses), backward rows are input channels.
+__global__ void __launch_bounds__(256)
+prep_weights_fwd_batched_kernel(const PrepSlot* __restrict__ slots, const int2* __restrict__ rows, float eps) {
+    const int2 r = rows[blockIdx.x];
+    const PrepSlot sl = slots[r.x];
+    prep_conv_weight_row(sl.w, sl.qf, r.y, sl.Cout, sl.Cin, sl.ksize, sl.ws, eps, sl.ws ? sl.stats + r.y : nullptr);
+}
+// qd[ci][(tap', co)] = wt[co][ci][taps - 1 - tap'] (the flipped / transposed weight dgrad convolves with), wt standardised when ws
+__global__ void __launch_bounds__(256)
+prep_weights_bwd_batched_kernel(const PrepSlot* __restrict__ slots, const int2* __restrict__ rows) {
+    const int2 r = rows[blockIdx.x];
+    const PrepSlot sl = slots[r.x];
+    const int ci = r.y, taps = sl.ksize * sl.ksize, Cout = sl.Cout, Cin = sl.Cin;
+    bf16* orow = sl.qd + static_cast<size_t>(ci) * taps * Cout;
+    for (int i = threadIdx.x; i < taps * Cout; i += blockDim.x) {
+        const int tapp = i / Cout, co = i - tapp * Cout;
+        float v = sl.w[(static_cast<size_t>(co) * Cin + ci) * taps + (taps - 1 - tapp)];
+        if (sl.ws) { const float2 st = sl.stats[co]; v = (v - st.x) * st.y; }
         orow[i] = __float2bfloat16(v);
     }
 }
@@ -154,6 +184,12 @@ linear_rows_kernel(const float* __restrict__ x, int ldx, const float* __restrict
 
 }  // namespace
 
+cudaError_t prep_weights_batched_run(const PrepSlot* slots, const int2* fwd_rows, int nfwd, const int2* bwd_rows, int nbwd, float eps,
+                                     cudaStream_t s) {
+    if (nfwd > 0) prep_weights_fwd_batched_kernel<<<nfwd, 256, 0, s>>>(slots, fwd_rows, eps);
+    if (nbwd > 0) prep_weights_bwd_batched_kernel<<<nbwd, 256, 0, s>>>(slots, bwd_rows);
+    return cudaGetLastError();
+}
 cudaError_t prep_conv_weight_run(const float* w, bf16* out, int Cout, int Cin, int ksize, int standardize, float eps,
                                  int Npad, cudaStream_t s) {
     prep_conv_weight_kernel<<<Npad, 256, 0, s>>>(w, out, Cout, Cin, ksize, standardize, eps, Npad);

@@ -229,23 +229,33 @@ colsum_part_kernel(const uint4* __restrict__ x, float* __restrict__ part, long l
     }
 }
 
-// out[i] = scale * sum_k part[k][i] (+ out[i] when accumulate); n columns.  32 columns per block, 8 threads per column each
+// out[i] = scale * sum_k part[k][i] (+ out[i] when accumulate); n columns.  32 columns per block, 32 threads per column each
 // summing a contiguous slice of the partials, combined in a fixed order (a single thread per column was latency-bound).
-__global__ void __launch_bounds__(256)
+constexpr int SUM_SLICES = 32;      // threads per column (each sums a contiguous slice of the partials)
+__global__ void __launch_bounds__(32 * SUM_SLICES)
 sum_parts_kernel(const float* __restrict__ part, int nparts, int n, float scale, int accumulate, float* __restrict__ out) {
-    __shared__ float s_p[8][32];
+    __shared__ float s_p[SUM_SLICES][32];
     const int col = blockIdx.x * 32 + (threadIdx.x & 31), sl = threadIdx.x >> 5;
-    const int per = (nparts + 7) / 8;
+    const int per = (nparts + SUM_SLICES - 1) / SUM_SLICES;
     const int k0 = sl * per, k1 = min(nparts, k0 + per);
     float t = 0.f;
-    if (col < n)
-        for (int k = k0; k < k1; ++k) t += part[static_cast<size_t>(k) * n + col];
+    if (col < n) {
+        int k = k0;
+        for (; k + 8 <= k1; k += 8) {              // eight independent loads in flight, added in order
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(part + static_cast<size_t>(k + j) * n + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t += v[j];
+        }
+        for (; k < k1; ++k) t += __ldg(part + static_cast<size_t>(k) * n + col);
+    }
     s_p[sl][threadIdx.x & 31] = t;
     __syncthreads();
     if (sl == 0 && col < n) {
         float v = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v += s_p[k][threadIdx.x];
+        for (int k = 0; k < SUM_SLICES; ++k) v += s_p[k][threadIdx.x];
         out[col] = accumulate ? fmaf(scale, v, out[col]) : scale * v;
     }
 }
@@ -571,11 +581,11 @@ cudaError_t colsum_run(const bf16* x, long long M, int C, float* part, float sca
     colsum_part_kernel<<<nparts, 256, lanes * C * sizeof(float), s>>>(reinterpret_cast<const uint4*>(x), part, M, C, rpb);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    sum_parts_kernel<<<(C + 31) / 32, 256, 0, s>>>(part, nparts, C, scale, accumulate, out);
+    sum_parts_kernel<<<(C + 31) / 32, 32 * SUM_SLICES, 0, s>>>(part, nparts, C, scale, accumulate, out);
     return cudaGetLastError();
 }
 cudaError_t sum_parts_run(const float* part, int nparts, int n, float scale, int accumulate, float* out, cudaStream_t s) {
-    sum_parts_kernel<<<(n + 31) / 32, 256, 0, s>>>(part, nparts, n, scale, accumulate, out);
+    sum_parts_kernel<<<(n + 31) / 32, 32 * SUM_SLICES, 0, s>>>(part, nparts, n, scale, accumulate, out);
     return cudaGetLastError();
 }
 cudaError_t add_bf16_run(const bf16* a, const bf16* b, bf16* y, long long n, cudaStream_t s) {

@@ -138,42 +138,6 @@ head_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ d_eps, con
     }
 }
 
-// ---- per-output-channel (mean, rstd) of a conv weight, then the dgrad layout of the standardised weight
-__global__ void __launch_bounds__(256)
-ws_stats_kernel(const float* __restrict__ w, int K, float eps, float2* __restrict__ stats) {
-    __shared__ float s_red[8];
-    const float* wr = w + static_cast<size_t>(blockIdx.x) * K;
-    auto bsum = [&](float v) {
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        __syncthreads();
-        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-        __syncthreads();
-        float t = 0.f;
-        for (int k = 0; k < 8; ++k) t += s_red[k];
-        return t;
-    };
-    float s = 0.f;
-    for (int i = threadIdx.x; i < K; i += 256) s += wr[i];
-    const float mean = bsum(s) / K;
-    float v = 0.f;
-    for (int i = threadIdx.x; i < K; i += 256) { const float d = wr[i] - mean; v = fmaf(d, d, v); }
-    const float rstd = rsqrtf(bsum(v) / K + eps);
-    if (threadIdx.x == 0) stats[blockIdx.x] = make_float2(mean, rstd);
-}
-// out[ci][(tap', co)] = wt[co][ci][taps - 1 - tap'], wt = (w - mean_co) * rstd_co when stats != nullptr; grid Cin
-__global__ void __launch_bounds__(256)
-prep_dgrad_weight_general_kernel(const float* __restrict__ w, const float2* __restrict__ stats, bf16* __restrict__ out, int Cout, int Cin,
-                                 int taps) {
-    const int ci = blockIdx.x;
-    bf16* orow = out + static_cast<size_t>(ci) * taps * Cout;
-    for (int i = threadIdx.x; i < taps * Cout; i += blockDim.x) {
-        const int tapp = i / Cout, co = i - tapp * Cout;
-        float v = w[(static_cast<size_t>(co) * Cin + ci) * taps + (taps - 1 - tapp)];
-        if (stats != nullptr) { const float2 st = stats[co]; v = (v - st.x) * st.y; }
-        orow[i] = __float2bfloat16(v);
-    }
-}
-
 inline int grid_for(long long n) { return static_cast<int>(n / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16); }
 
 }  // namespace
@@ -213,14 +177,6 @@ cudaError_t head_bwd_run(const bf16* x, const float* d_eps, const float* w, long
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return sum_parts_run(part, nparts, C, 1.0f, 0, dw, s);
-}
-cudaError_t ws_stats_run(const float* w, int Cout, int K, float eps, float2* stats, cudaStream_t s) {
-    ws_stats_kernel<<<Cout, 256, 0, s>>>(w, K, eps, stats);
-    return cudaGetLastError();
-}
-cudaError_t prep_dgrad_weight_general_run(const float* w, const float2* stats, bf16* out, int Cout, int Cin, int ksize, cudaStream_t s) {
-    prep_dgrad_weight_general_kernel<<<Cin, 256, 0, s>>>(w, stats, out, Cout, Cin, ksize * ksize);
-    return cudaGetLastError();
 }
 
 }  // namespace hd

@@ -8,6 +8,7 @@
 // flipped / transposed, standardised filter) and wgrad.cu (general kernel); everything else: norm_bwd.cu, attention_bwd.cu,
 // train_kernels.cu, unet_train_kernels.cu.  Every gradient tensor has its own buffer; a tensor with several consumers
 // (skip connections, residual branches) accumulates through add_bf16 in a fixed order.
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -49,6 +50,9 @@ struct UB {
     bf16 *T1 = nullptr, *T2 = nullptr, *T3 = nullptr;    // gradient temporaries (largest activation)
     std::vector<std::function<void()>> bwd;              // backward emitters, run in reverse
     std::vector<ConvW*> convs;
+    std::vector<PrepSlot> prep_slots;                    // every conv's weight preparation, uploaded by finish_prep()
+    struct PrepTables { PrepSlot* slots = nullptr; int2 *fwd = nullptr, *bwd = nullptr; int nfwd = 0, nbwd = 0; };
+    std::shared_ptr<PrepTables> prep = std::make_shared<PrepTables>();
 
     // Graph schedule (see TOp::side / join): weight-gradient work (wgrad + split reduction, standardisation backward, bias column
     // sums) is a leaf of the backward graph, so it runs on the side stream next to the data-gradient chain; it reads the gradient
@@ -65,6 +69,29 @@ struct UB {
             pending_join = false;
         }
         t->ops.push_back(std::move(o));
+    }
+    // the step's first op: all weight layouts in two launches (tables are filled by finish_prep() once every conv is declared)
+    void push_prep() {
+        std::shared_ptr<PrepTables> pt = prep;
+        push("prep", "prep.all", [pt](cudaStream_t s) { return prep_weights_batched_run(pt->slots, pt->fwd, pt->nfwd, pt->bwd, pt->nbwd, EPS, s); });
+    }
+    bool finish_prep() {
+        std::vector<int2> fwd, bwd;
+        for (size_t i = 0; i < prep_slots.size(); ++i) {
+            for (int r = 0; r < prep_slots[i].Cout; ++r) fwd.push_back(make_int2(static_cast<int>(i), r));
+            for (int r = 0; r < prep_slots[i].Cin; ++r) bwd.push_back(make_int2(static_cast<int>(i), r));
+        }
+        if (prep_slots.empty()) return true;
+        if (dalloc(t, &prep->slots, prep_slots.size() * sizeof(PrepSlot)) || dalloc(t, &prep->fwd, fwd.size() * sizeof(int2)) ||
+            dalloc(t, &prep->bwd, bwd.size() * sizeof(int2)))
+            return false;
+        if (cudaMemcpy(prep->slots, prep_slots.data(), prep_slots.size() * sizeof(PrepSlot), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(prep->fwd, fwd.data(), fwd.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(prep->bwd, bwd.data(), bwd.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess)
+            return fail("weight preparation table upload failed");
+        prep->nfwd = static_cast<int>(fwd.size());
+        prep->nbwd = static_cast<int>(bwd.size());
+        return true;
     }
     bool fail(const std::string& m) { if (ok) { ok = false; tfail("%s", m.c_str()); } return false; }
     size_t elems(int H, int C) const { return static_cast<size_t>(B) * H * H * C; }
@@ -89,11 +116,7 @@ struct UB {
         bf16 *qf = c->qf, *qd = c->qd;
         float2* st = c->stats;
         const int wsi = ws ? 1 : 0;
-        push("prep", "prep." + wkey, [=](cudaStream_t s) {
-            cudaError_t e = prep_conv_weight_run(w, qf, Cout, Cin, k, wsi, EPS, Cout, s);
-            if (e == cudaSuccess && wsi) e = ws_stats_run(w, Cout, Cin * k * k, EPS, st, s);
-            return e != cudaSuccess ? e : prep_dgrad_weight_general_run(w, wsi ? st : nullptr, qd, Cout, Cin, k, s);
-        });
+        prep_slots.push_back(PrepSlot{w, qf, qd, st, Cout, Cin, k, wsi});   // prepared by the one batched "prep" op at the head of the step
         return c;
     }
 
@@ -481,11 +504,11 @@ int build_unet_trainer(hd_trainer* t) {
         t->ops.swap(keep);
     }
 
-    // ---------------------------------------------------------------- forward (prep ops and forward ops interleave in t->ops; fine:
-    // a layer's weights are prepared before the layer runs, and nothing else touches them)
+    // ---------------------------------------------------------------- forward ([prep.all][time ...][forward ...][loss][backward ...])
     const TParam *iw = find_p(t, "init_conv.weight", {dim, cin, 7, 7}), *ib = find_p(t, "init_conv.bias", {dim});
     const TParam *fw = find_p(t, "final_conv.weight", {1, dim, 1, 1}), *fb = find_p(t, "final_conv.bias", {1});
     if (!iw || !ib || !fw || !fb) return 1;
+    u.push_prep();
     t->ops.insert(t->ops.end(), time_ops.begin(), time_ops.end());
     TenP x = u.ten(S, dim);
     if (!u.ok) return 1;
@@ -607,6 +630,7 @@ int build_unet_trainer(hd_trainer* t) {
         });
     }
     for (ConvW* cw : u.convs) delete cw;
+    if (u.ok && !u.finish_prep()) return 1;
     return u.ok ? 0 : 1;
 }
 
