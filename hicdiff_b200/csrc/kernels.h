@@ -124,6 +124,7 @@ struct GroupNormArgs {
     const float* postadd = nullptr;   // same row addressing as film; value at postadd_off + c
     int postadd_off = 0;
     const bf16* res = nullptr;        // + res[b, p, c] after the activation (ResnetBlock skip)
+    float2* stats_out = nullptr;      // [B, 8] (optional) the (mean, rstd) this pass normalised with, kept for the training backward
 };
 cudaError_t groupnorm_film_silu_run(const GroupNormArgs& a, cudaStream_t s);
 // Stand-alone producer of the same partials from a bf16 tensor (used when the input does not come from conv_gemm).
@@ -408,6 +409,7 @@ struct GroupNormBwdArgs {
     float* dshift = nullptr;        // [B, C]
     float* dconv_bias = nullptr;    // [C] (optional) sum_{b,p} dy: the bias gradient of the conv that produced y, from the same sums
     float* dpost = nullptr;         // [B, C] (optional) sum_p ds: gradient of an SR3 embedding added AFTER the activation
+    const float2* stats_in = nullptr;   // [B, 8] (optional) the forward pass's (mean, rstd) (GroupNormArgs::stats_out); recomputed from y when absent
 };
 size_t gn_bwd_scratch_floats(int B, int P, int C);
 cudaError_t groupnorm_silu_bwd_run(const GroupNormBwdArgs& a, float* scratch, cudaStream_t s);

@@ -144,8 +144,11 @@ groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, off);
                 if (lane == 0) {
+                    const float rstd = rsqrtf(m2 / total + a.eps);
                     s_mean[warp] = mean;
-                    s_rstd[warp] = rsqrtf(m2 / total + a.eps);
+                    s_rstd[warp] = rstd;
+                    if (a.stats_out != nullptr && s == b * slabs_per_img)      // the CTA that owns the image's first slab records them
+                        a.stats_out[b * GN_GROUPS + warp] = make_float2(mean, rstd);
                 }
             }
             __syncthreads();

@@ -441,14 +441,17 @@ cudaError_t groupnorm_silu_bwd_run(const GroupNormBwdArgs& a, float* scratch, cu
     const int nchunk = gn_chunks(P, C);
     const int lanes = 256 / (C / 8);
     const int ld = a.ld > 0 ? a.ld : C;
-    float2* stats = reinterpret_cast<float2*>(scratch);
+    float2* stats_buf = reinterpret_cast<float2*>(scratch);
+    const float2* stats = a.stats_in != nullptr ? a.stats_in : stats_buf;
     float* part = scratch + static_cast<size_t>(B) * G * 2;
     float* UV = part + static_cast<size_t>(B) * nchunk * 4 * C;
     float* gm = UV + static_cast<size_t>(B) * 3 * C;
     const uint4* y = reinterpret_cast<const uint4*>(a.y);
     const uint4* ds = reinterpret_cast<const uint4*>(a.ds);
-    gn_stats_part_kernel<<<dim3(nchunk, B), 256, 0, s>>>(y, P, C, nchunk, reinterpret_cast<float2*>(gm));   // gm is free until the coefficient pass
-    gn_stats_finish_kernel<<<B, 32, 0, s>>>(reinterpret_cast<const float2*>(gm), nchunk, P, C, a.eps, stats);
+    if (a.stats_in == nullptr) {
+        gn_stats_part_kernel<<<dim3(nchunk, B), 256, 0, s>>>(y, P, C, nchunk, reinterpret_cast<float2*>(gm));   // gm is free until the coefficient pass
+        gn_stats_finish_kernel<<<B, 32, 0, s>>>(reinterpret_cast<const float2*>(gm), nchunk, P, C, a.eps, stats_buf);
+    }
     gn_bwd_sums_kernel<<<dim3(nchunk, B), 256, static_cast<size_t>(lanes) * 4 * C * sizeof(float), s>>>(
         y, ds, stats, a.gamma, a.beta, a.scale, a.shift, ld, P, C, nchunk, part);
     gn_bwd_coef_kernel<<<B, 512, 0, s>>>(part, nchunk, a.gamma, a.beta, a.scale, ld, P, C, UV, gm, a.dscale, a.dshift, a.dpost);

@@ -213,6 +213,8 @@ struct UB {
         const TParam *g2 = find_p(t, p + ".block2.norm.weight", {Cout}), *b2 = find_p(t, p + ".block2.norm.bias", {Cout});
         if (!ok || !g1 || !b1 || !g2 || !b2) { ok = false; return xa; }
         TenP y1 = ten(H, Cout), s1 = ten(H, Cout), y2 = ten(H, Cout), out = ten(H, Cout), rc = cr ? ten(H, Cout) : nullptr;
+        float2 *st1 = nullptr, *st2 = nullptr;      // the forward GroupNorms' (mean, rstd), reused by their backward
+        if (dalloc(t, &st1, static_cast<size_t>(B) * 8 * sizeof(float2)) || dalloc(t, &st2, static_cast<size_t>(B) * 8 * sizeof(float2))) ok = false;
         if (!ok) return out;
         const int P = H * H;
         if (!conv_fwd(p + ".block1.conv", c1, *xa, xb.get(), y1->p, ConvEpilogue(), true)) return out;
@@ -221,6 +223,7 @@ struct UB {
             a.x = y1->p; a.y = s1->p; a.B = B; a.P = P; a.C = Cout; a.part = gn_part; a.gamma = g1->w; a.beta = b1->w; a.eps = EPS;
             a.film_row = iota; a.film_row_stride = 1; a.film_ld = ld;
             if (sr3) { a.postadd = film; a.postadd_off = film_off; } else { a.film = film; a.film_off = film_off; }
+            a.stats_out = st1;
             push("groupnorm", p + ".block1.norm", [a](cudaStream_t s) { return groupnorm_film_silu_run(a, s); });
         }
         if (!conv_fwd(p + ".block2.conv", c2, *s1, nullptr, y2->p, ConvEpilogue(), true)) return out;
@@ -229,6 +232,7 @@ struct UB {
             GroupNormArgs a;
             a.x = y2->p; a.y = out->p; a.B = B; a.P = P; a.C = Cout; a.part = gn_part; a.gamma = g2->w; a.beta = b2->w; a.eps = EPS;
             a.res = cr ? rc->p : xa->p;
+            a.stats_out = st2;
             push("groupnorm", p + ".block2.norm", [a](cudaStream_t s) { return groupnorm_film_silu_run(a, s); });
         }
         bwd.push_back([=]() {
@@ -237,7 +241,7 @@ struct UB {
             {
                 GroupNormBwdArgs a;
                 a.y = y2->p; a.ds = g; a.dy = T1; a.B = B; a.P = P; a.C = Cout; a.gamma = g2->w; a.beta = b2->w; a.eps = EPS;
-                a.dgamma = g2->g; a.dbeta = b2->g; a.dconv_bias = c2->b->g;
+                a.dgamma = g2->g; a.dbeta = b2->g; a.dconv_bias = c2->b->g; a.stats_in = st2;
                 float* sc = gn_scratch;
                 push("groupnorm_bwd", p + ".block2.norm.bwd", [a, sc](cudaStream_t s) { return groupnorm_silu_bwd_run(a, sc, s); });
             }
@@ -250,7 +254,7 @@ struct UB {
                 a.ld = ld;
                 if (sr3) { a.dpost = dfilm + film_off; }
                 else { a.scale = film + film_off; a.shift = film + film_off + Cout; a.dscale = dfilm + film_off; a.dshift = dfilm + film_off + Cout; }
-                a.dgamma = g1->g; a.dbeta = b1->g; a.dconv_bias = c1->b->g;
+                a.dgamma = g1->g; a.dbeta = b1->g; a.dconv_bias = c1->b->g; a.stats_in = st1;
                 float* sc = gn_scratch;
                 push("groupnorm_bwd", p + ".block1.norm.bwd", [a, sc](cudaStream_t s) { return groupnorm_silu_bwd_run(a, sc, s); });
             }
