@@ -298,17 +298,29 @@ thin_wgrad_kernel(const bf16* __restrict__ G, const float* __restrict__ u0, cons
 #pragma unroll
         for (int t = 0; t < 9; ++t) acc[k][t] = 0.f;
     const bf16* g = G + ((static_cast<size_t>(b) * H + y0) * W) * C + c;
+    // eight pixels per step: their gradients are loaded together and the 3 x 10 window of u they touch is read from shared
+    // memory once (the per-(pixel, tap) broadcast reads made the loop LDS-issue bound: one LDS per FMA)
     for (int yl = 0; yl < ROWS; ++yl) {
-        for (int x = 0; x < W; ++x) {
-            const float gv = __bfloat162float(g[(static_cast<size_t>(yl) * W + x) * C]);
+        for (int x0 = 0; x0 < W; x0 += 8) {
+            float gv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gv[i] = __bfloat162float(g[(static_cast<size_t>(yl) * W + x0 + i) * C]);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 if (k < nk) {
+                    float uw[3][10];
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) {
-                        const int dy = sgn * (t / 3 - 1), dx = sgn * (t % 3 - 1);
-                        acc[k][t] = fmaf(gv, s_u[k][yl + 1 + dy][x + 1 + dx], acc[k][t]);
-                    }
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int j = 0; j < 10; ++j) uw[r][j] = s_u[k][yl + r][x0 + j];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) {
+                            const int dy = t / 3 - 1, dx = t % 3 - 1;
+                            const float uv = sgn > 0 ? uw[1 + dy][i + 1 + dx] : uw[1 - dy][i + 1 - dx];
+                            acc[k][t] = fmaf(gv[i], uv, acc[k][t]);
+                        }
                 }
             }
         }
@@ -319,15 +331,37 @@ thin_wgrad_kernel(const bf16* __restrict__ G, const float* __restrict__ u0, cons
         for (int t = 0; t < 9; ++t) o[(k * 9 + t) * C + c] = acc[k][t];
 }
 
-// dW[(c * nk + k) * 9 + tap] = sum_parts part[.][k][tap][c]
-__global__ void thin_wgrad_finish_kernel(const float* __restrict__ part, int nparts, int nk, float* __restrict__ dw) {
+// dW[(c * nk + k) * 9 + tap] = sum_parts part[.][k][tap][c]: 32 columns per block, 32 threads per column over contiguous slices
+// of the partials (eight loads in flight each), combined in a fixed order
+__global__ void __launch_bounds__(1024)
+thin_wgrad_finish_kernel(const float* __restrict__ part, int nparts, int nk, float* __restrict__ dw) {
     constexpr int C = 256;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;    // index into [k][tap][c]
-    if (i >= nk * 9 * C) return;
+    __shared__ float s_p[32][32];
+    const int n = nk * 9 * C;
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31), sl = threadIdx.x >> 5;    // i indexes [k][tap][c]
+    const int per = (nparts + 31) / 32;
+    const int k0 = sl * per, k1 = min(nparts, k0 + per);
     float t = 0.f;
-    for (int p = 0; p < nparts; ++p) t += part[static_cast<size_t>(p) * nk * 9 * C + i];
-    const int c = i % C, kt = i / C, k = kt / 9, tap = kt - k * 9;
-    dw[(c * nk + k) * 9 + tap] = t;
+    if (i < n) {
+        int k = k0;
+        for (; k + 8 <= k1; k += 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(part + static_cast<size_t>(k + j) * n + i);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t += v[j];
+        }
+        for (; k < k1; ++k) t += __ldg(part + static_cast<size_t>(k) * n + i);
+    }
+    s_p[sl][threadIdx.x & 31] = t;
+    __syncthreads();
+    if (sl == 0 && i < n) {
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v += s_p[k][threadIdx.x];
+        const int c = i % C, kt = i / C, kk = kt / 9, tap = kt - kk * 9;
+        dw[(c * nk + kk) * 9 + tap] = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ loss
@@ -599,7 +633,7 @@ cudaError_t thin_wgrad_run(const bf16* G, const float* u0, const float* u1, int 
     thin_wgrad_kernel<<<dim3(8, B), 256, 0, s>>>(G, u0, u1, sgn, part);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    thin_wgrad_finish_kernel<<<(nk * 9 * 256 + 255) / 256, 256, 0, s>>>(part, B * 8, nk, dw);
+    thin_wgrad_finish_kernel<<<(nk * 9 * 256 + 31) / 32, 1024, 0, s>>>(part, B * 8, nk, dw);
     return cudaGetLastError();
 }
 int loss_parts() { return 592; }

@@ -14,16 +14,42 @@ namespace hd {
 namespace {
 
 // out[b, h, w, c * 4 + p1 * 2 + p2] = in[b, 2h + p1, 2w + p2, c]   (inverse == 1: the scatter back, out is [B, 2H, 2W, C])
+// One thread per (low-resolution pixel, 8 channels): four 16-byte chunks on the high-resolution side (one per (p1, p2), 8
+// consecutive channels each) <-> four consecutive 16-byte chunks on the low-resolution side, transposed in registers.  (The
+// 2-byte-per-thread gather this replaces ran at a tenth of the copy bandwidth.)
 __global__ void __launch_bounds__(256)
-unshuffle_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C, int inverse) {
-    const long long total = static_cast<long long>(B) * H * W * 4 * C;
+unshuffle_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int C, int inverse) {
+    const int cpp = C / 8;
+    const long long total = static_cast<long long>(B) * H * W * cpp;
     for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
-        const int c4 = static_cast<int>(i % (4 * C));
-        const long long pix = i / (4 * C);
-        const int w = static_cast<int>(pix % W), h = static_cast<int>((pix / W) % H), b = static_cast<int>(pix / (static_cast<long long>(W) * H));
-        const int c = c4 >> 2, p1 = (c4 >> 1) & 1, p2 = c4 & 1;
-        const long long hi = ((static_cast<long long>(b) * 2 * H + 2 * h + p1) * 2 * W + 2 * w + p2) * C + c;
-        if (inverse) out[hi] = in[i]; else out[i] = in[hi];
+        const int cc = static_cast<int>(i % cpp);
+        const long long pix = i / cpp;
+        const int w = static_cast<int>(pix % W), h = static_cast<int>((pix / W) % H);
+        const long long b = pix / (static_cast<long long>(W) * H);
+        long long hi[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) hi[p] = ((b * 2 * H + 2 * h + (p >> 1)) * 2 * W + 2 * w + (p & 1)) * cpp + cc;
+        const long long lo = pix * 4 * cpp + cc * 4;          // chunk index of channel (cc * 8) * 4 in the [.., 4C] row
+        union { uint4 v[4]; unsigned short e[32]; } a, t;
+        if (!inverse) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) a.v[p] = __ldg(in + hi[p]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int p = 0; p < 4; ++p) t.e[k * 4 + p] = a.e[p * 8 + k];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) out[lo + q] = t.v[q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a.v[q] = __ldg(in + lo + q);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int p = 0; p < 4; ++p) t.e[p * 8 + k] = a.e[k * 4 + p];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) out[hi[p]] = t.v[p];
+        }
     }
 }
 
@@ -90,28 +116,61 @@ stem_wgrad_kernel(const bf16* __restrict__ G, const float* __restrict__ u0, cons
 #pragma unroll
         for (int t = 0; t < 7; ++t) acc[k][t] = 0.f;
     const bf16* g = G + ((static_cast<size_t>(b) * H + y0) * W) * C + c;
+    // eight pixels per step: their gradients are loaded together and the (8 + ksize - 1)-wide window of u is read from shared
+    // memory once per step instead of once per (pixel, tap) -- the loop was bound by broadcast LDS issue, one per FMA
     for (int yl = 0; yl < ROWS; ++yl)
-        for (int x = 0; x < W; ++x) {
-            const float gv = __bfloat162float(g[(static_cast<size_t>(yl) * W + x) * C]);
+        for (int x0 = 0; x0 < W; x0 += 8) {
+            float gv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gv[i] = __bfloat162float(g[(static_cast<size_t>(yl) * W + x0 + i) * C]);
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-                if (k < nk)
+                if (k < nk) {
+                    const float* ur = sw_u + (k * ROWS + yl) * pitch + x0;
+                    float uw[14];
 #pragma unroll
-                    for (int t = 0; t < 7; ++t)
-                        if (t < ksize) acc[k][t] = fmaf(gv, sw_u[(k * ROWS + yl) * pitch + x + t], acc[k][t]);
+                    for (int j = 0; j < 14; ++j) uw[j] = x0 + j < pitch ? ur[j] : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int t = 0; t < 7; ++t)
+                            if (t < ksize) acc[k][t] = fmaf(gv[i], uw[i + t], acc[k][t]);
+                }
         }
     float* o = part + ((static_cast<size_t>(b) * 8 + rg) * nk * ksize * ksize) * C;
     for (int k = 0; k < nk; ++k)
         for (int t = 0; t < ksize; ++t) o[((k * ksize + ky) * ksize + t) * C + c] = acc[k][t];
 }
-// dw[(c * nk + k) * taps + tap] = sum_parts part[.][k][tap][c]
-__global__ void stem_wgrad_finish_kernel(const float* __restrict__ part, int nparts, int nk, int taps, int C, float* __restrict__ dw) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nk * taps * C) return;
+// dw[(c * nk + k) * taps + tap] = sum_parts part[.][k][tap][c]: 32 columns per block, 32 threads per column over contiguous
+// slices of the partials (eight loads in flight each), combined in a fixed order
+__global__ void __launch_bounds__(1024)
+stem_wgrad_finish_kernel(const float* __restrict__ part, int nparts, int nk, int taps, int C, float* __restrict__ dw) {
+    __shared__ float s_p[32][32];
+    const int n = nk * taps * C;
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31), sl = threadIdx.x >> 5;
+    const int per = (nparts + 31) / 32;
+    const int k0 = sl * per, k1 = min(nparts, k0 + per);
     float t = 0.f;
-    for (int p = 0; p < nparts; ++p) t += part[static_cast<size_t>(p) * nk * taps * C + i];
-    const int c = i % C, kt = i / C, k = kt / taps, tap = kt - k * taps;
-    dw[(c * nk + k) * taps + tap] = t;
+    if (i < n) {
+        int k = k0;
+        for (; k + 8 <= k1; k += 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(part + static_cast<size_t>(k + j) * n + i);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t += v[j];
+        }
+        for (; k < k1; ++k) t += __ldg(part + static_cast<size_t>(k) * n + i);
+    }
+    s_p[sl][threadIdx.x & 31] = t;
+    __syncthreads();
+    if (sl == 0 && i < n) {
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v += s_p[k][threadIdx.x];
+        const int c = i % C, kt = i / C, kk = kt / taps, tap = kt - kk * taps;
+        dw[(c * nk + kk) * taps + tap] = v;
+    }
 }
 
 // ---- final_conv (C -> 1) backward: dx[m, c] = d_eps[m] * w[c];  dw partials part[blk][c] = sum_m d_eps[m] x[m, c]
@@ -143,7 +202,8 @@ inline int grid_for(long long n) { return static_cast<int>(n / 256 < 148 * 16 ? 
 }  // namespace
 
 cudaError_t unshuffle_run(const bf16* in, bf16* out, int B, int H, int W, int C, int inverse, cudaStream_t s) {
-    unshuffle_kernel<<<grid_for(static_cast<long long>(B) * H * W * 4 * C), 256, 0, s>>>(in, out, B, H, W, C, inverse);
+    if (C % 8 != 0) return cudaErrorInvalidValue;
+    unshuffle_kernel<<<grid_for(static_cast<long long>(B) * H * W * (C / 8)), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), B, H, W, C, inverse);
     return cudaGetLastError();
 }
 cudaError_t upsample2x_run(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t s) {
@@ -163,7 +223,7 @@ cudaError_t stem_wgrad_run(const bf16* G, const float* u0, const float* u1, int 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int n = nk * ksize * ksize * C;
-    stem_wgrad_finish_kernel<<<(n + 255) / 256, 256, 0, s>>>(part, B * 8, nk, ksize * ksize, C, dw);
+    stem_wgrad_finish_kernel<<<(n + 31) / 32, 1024, 0, s>>>(part, B * 8, nk, ksize * ksize, C, dw);
     return cudaGetLastError();
 }
 int head_bwd_parts(long long M) { return static_cast<int>(M / 64 < 592 ? (M + 63) / 64 : 592); }
