@@ -324,8 +324,9 @@ int wgrad_prepare(const bf16* g, const bf16* x, int B, int H, int W, int C, int 
 cudaError_t wgrad_run(const WgradLaunch& l, cudaStream_t s);
 // general form: dY [B,H,W,Cout], X [B,H,W,Cin] NHWC bf16 (Cout, Cin multiples of 64; W in {8,16,32,64}; ksize 1 or 3)
 struct WgradGenLaunch {
-    CUtensorMap tmG, tmX;
+    CUtensorMap tmG, tmX, tmXs;      // tmXs: the halo'd 66-pixel slab box of the filter-row form
     int B, H, W, rows_kb, Cout, Cin, Nt, taps, mtiles, ntiles, nsplit, kb_total;
+    int rowmode = 0;                 // 1: one CTA per (filter row, K split) with three accumulators (3x3, W = 64, Cin tile <= 128)
     float* part;            // [nsplit][taps][Cout][Cin] fp32, wgrad_general_part_bytes(); set by the caller after prepare
 };
 int wgrad_general_prepare(const bf16* g, const bf16* x, int B, int H, int W, int Cout, int Cin, int ksize, int num_sms,

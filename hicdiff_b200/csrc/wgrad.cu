@@ -15,6 +15,7 @@
 // 3 stages), two M = 128 x N = 256 fp32 accumulators = all 512 TMEM columns, 8 MMAs per stage.  Warp 0 produces (TMA), warp 1
 // issues, warps 2-5 drain the accumulators into a [split][tap][co][ci] fp32 workspace that wgrad_reduce_kernel sums in a
 // fixed order (deterministic; no atomics) into the reference's [Cout, Cin, 3, 3] layout.
+#include <cstdlib>
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -290,6 +291,125 @@ wgrad_general_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Filter-row form of the general kernel for 3x3 convs on 64-pixel-wide images with a Cin tile <= 128: one CTA = one
+// (filter row dy, Cout tile, Cin tile, K split) with THREE accumulators (dx = -1, 0, +1).  A K block is one image row: the G
+// tile is loaded once and X arrives as ONE halo'd slab {64 ch, 66 pixels starting at column -1} per 64-channel chunk; the
+// three taps are the same slab read from K row 0, 1, 2 (descriptor start + 128 bytes per pixel -- the tensor core derives the
+// swizzle phase from absolute address bits, see conv_gemm.cu).  L2 -> SM operand traffic per tap drops from (G + X) to
+// (G + 1.03 X) / 3: the per-tap kernel is operand-fetch bound at N = 64 (250 TFLOP/s).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t WGR_SLAB = 72 * 128;             // 66 pixel rows of a 64-channel chunk, padded to whole 8-row swizzle atoms
+constexpr uint32_t WGR_SLAB_TX = 66 * 128;          // bytes one slab box delivers
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmXs, const WgradGenKArgs a) {
+    extern __shared__ uint8_t wg_smem_raw[];
+    uint8_t* smem = wg_smem_raw + ((1024u - (ptx::smem_u32(wg_smem_raw) & 1023u)) & 1023u);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WGG_STAGES * WGG_STAGE_MAX);
+    uint64_t* empty_bar = full_bar + WGG_STAGES;
+    uint64_t* tfull_bar = empty_bar + WGG_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int id = blockIdx.x;
+    const int trow = id % 3; id /= 3;
+    const int mt = id % a.mtiles; id /= a.mtiles;
+    const int nt = id % a.ntiles; id /= a.ntiles;
+    const int split = id;
+    const int dy = trow - 1;
+    const int kb0 = static_cast<int>(static_cast<long long>(a.kb_total) * split / a.nsplit);
+    const int kb1 = static_cast<int>(static_cast<long long>(a.kb_total) * (split + 1) / a.nsplit);
+    const int nchunks = a.Nt / 64;
+    const uint32_t stage_bytes = WGG_A_BYTES + nchunks * WGR_SLAB_TX;
+    const uint32_t tmem_cols = 3 * a.Nt <= 256 ? 256u : 512u;
+
+    if (warp == 0) {
+        if (lane == 0) { ptx::prefetch_tmap(&tmG); ptx::prefetch_tmap(&tmXs); }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, tmem_cols);
+        ptx::tmem_relinquish();
+    } else if (warp == 1 && lane == 0) {
+        for (int i = 0; i < WGG_STAGES; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+        ptx::mbar_init(tfull_bar, 1);
+        ptx::fence_mbar_init();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            const int b = kb / a.H, y0 = kb - b * a.H;
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+            if (ptx::elect_one()) {
+                uint8_t* sA = smem + stage * WGG_STAGE_MAX;
+                ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+                ptx::tma_load_5d(sA, &tmG, &full_bar[stage], 0, 0, y0, b, mt * 2);
+                for (int c = 0; c < nchunks; ++c)
+                    ptx::tma_load_5d(sA + WGG_A_BYTES + c * WGR_SLAB, &tmXs, &full_bar[stage], 0, -1, y0 + dy, b, nt * nchunks + c);
+            }
+            __syncwarp();
+            if (++stage == WGG_STAGES) { stage = 0; phase ^= 1u; }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = ptx::make_idesc_bf16_mn(128, static_cast<uint32_t>(a.Nt));
+        constexpr uint32_t K16_STEP = 2048u >> 4;
+        const uint64_t descA0 = ptx::make_mnmajor_sw128_desc(ptx::smem_u32(smem), WGG_CHUNK, 1024);
+        const uint64_t descB0 = ptx::make_mnmajor_sw128_desc(ptx::smem_u32(smem) + WGG_A_BYTES, WGR_SLAB, 1024);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint64_t da = descA0 + static_cast<uint64_t>((stage * WGG_STAGE_MAX) >> 4);
+                const uint64_t db = descB0 + static_cast<uint64_t>((stage * WGG_STAGE_MAX) >> 4);
+#pragma unroll
+                for (int t = 0; t < 3; ++t)            // x + dx is slab K row (x + dx + 1): tap t = dx + 1 starts t pixels (128 B each) in
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_bf16(tmem_base + static_cast<uint32_t>(t * a.Nt), da + K16_STEP * k, db + (128u >> 4) * t + K16_STEP * k,
+                                       idesc, (kb == kb0 && k == 0) ? 0u : 1u);
+                ptx::umma_commit(&empty_bar[stage]);
+            }
+            __syncwarp();
+            if (++stage == WGG_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (ptx::elect_one()) ptx::umma_commit(tfull_bar);
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        ptx::mbar_wait(tfull_bar, 0);
+        ptx::tc_fence_after();
+        const int co = mt * 128 + q * 32 + lane;
+#pragma unroll 1
+        for (int t = 0; t < 3; ++t) {
+            float* orow = a.part + ((static_cast<size_t>(split) * 9 + trow * 3 + t) * a.Cout + co) * a.Cin + nt * a.Nt;
+#pragma unroll 1
+            for (int c = 0; c < a.Nt; c += 32) {
+                uint32_t v[32];
+                ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * a.Nt + c, v);
+                ptx::tmem_ld_wait();
+                if (co < a.Cout) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<uint4*>(orow + c + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            }
+        }
+        ptx::tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
 // dw[(co * cin_total + ci0 + ci) * taps + tap] (+)= scale * sum_split part[split][tap][co][ci]; one thread per (co, ci)
 // (1x1 convs: reads and writes are both contiguous in ci)
 __global__ void __launch_bounds__(256)
@@ -386,14 +506,29 @@ int wgrad_general_prepare(const bf16* g, const bf16* x, int B, int H, int W, int
     out->mtiles = (Cout + 127) / 128;
     out->ntiles = Cin / Nt;
     out->kb_total = B * H / rows;
-    const int units = out->taps * out->mtiles * out->ntiles;
-    int ns = (2 * num_sms + units - 1) / units;             // about two waves of CTAs
-    if (ns > out->kb_total / 32) ns = out->kb_total / 32;   // >= 32 K blocks per CTA: below that the fp32 partials (written, then re-read
-    if (ns < 1) ns = 1;                                      // by the reduction) cost more than the parallelism buys on the low-resolution levels
-    if (ns > 32) ns = 32;
+    static const bool rows_ok = [] { const char* v = getenv("HD_WGRAD_ROWS"); return !(v && v[0] == '0'); }();
+    out->rowmode = (rows_ok && ksize == 3 && W == 64 && Nt <= 128) ? 1 : 0;
+    int ns;
+    if (out->rowmode) {
+        // filter-row CTAs (three taps each): one full wave
+        cuuint32_t sb[5] = {64, 66, 1, 1, 1};
+        if (encode_tmap_bf16(&out->tmXs, x, 5, xd, xs, sb, err, errlen)) return 1;
+        const int units = 3 * out->mtiles * out->ntiles;
+        ns = num_sms / units;
+        if (ns > out->kb_total / 32) ns = out->kb_total / 32;
+        if (ns < 1) ns = 1;
+        if (ns > 64) ns = 64;
+    } else {
+        const int units = out->taps * out->mtiles * out->ntiles;
+        ns = (2 * num_sms + units - 1) / units;             // about two waves of CTAs
+        if (ns > out->kb_total / 32) ns = out->kb_total / 32;   // >= 32 K blocks per CTA: below that the fp32 partials (written, then re-read
+        if (ns < 1) ns = 1;                                      // by the reduction) cost more than the parallelism buys on the low-resolution levels
+        if (ns > 32) ns = 32;
+    }
     out->nsplit = ns;
     out->part = nullptr;
     cudaError_t e = cudaFuncSetAttribute(wgrad_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WGG_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WGG_SMEM);
     if (e != cudaSuccess) { snprintf(err, errlen, "wgrad: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return 1; }
     return 0;
 }
@@ -406,7 +541,8 @@ cudaError_t wgrad_general_run(const WgradGenLaunch& l, cudaStream_t s) {
     WgradGenKArgs a;
     a.B = l.B; a.H = l.H; a.W = l.W; a.rows_kb = l.rows_kb; a.Cout = l.Cout; a.Cin = l.Cin; a.Nt = l.Nt; a.taps = l.taps;
     a.mtiles = l.mtiles; a.ntiles = l.ntiles; a.nsplit = l.nsplit; a.kb_total = l.kb_total; a.part = l.part;
-    wgrad_general_kernel<<<l.taps * l.mtiles * l.ntiles * l.nsplit, WG_THREADS, WGG_SMEM, s>>>(l.tmG, l.tmX, a);
+    if (l.rowmode) wgrad_rows_kernel<<<3 * l.mtiles * l.ntiles * l.nsplit, WG_THREADS, WGG_SMEM, s>>>(l.tmG, l.tmXs, a);
+    else wgrad_general_kernel<<<l.taps * l.mtiles * l.ntiles * l.nsplit, WG_THREADS, WGG_SMEM, s>>>(l.tmG, l.tmX, a);
     return cudaGetLastError();
 }
 

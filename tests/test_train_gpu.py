@@ -173,6 +173,7 @@ def test_eval_path_needs_no_trainer():
 WGRAD_CASES = [
     # B, H, Cin, Cout, k      (the Unet's levels: 64x64 .. 8x8, 1x1 and 3x3, Cout = 64 rides on a zero-filled 128-row tile)
     (2, 64, 64, 64, 3), (2, 64, 128, 64, 3), (2, 32, 128, 128, 3), (3, 16, 256, 256, 3), (4, 8, 512, 512, 3),
+    (5, 64, 64, 128, 3), (3, 64, 192, 64, 3),          # filter-row form (W = 64): Cout tile 128, three Cin tiles, uneven K splits
     (2, 8, 256, 512, 3), (2, 64, 64, 384, 1), (2, 32, 128, 64, 1), (3, 16, 256, 128, 1), (2, 8, 512, 256, 1),
 ]
 
