@@ -299,8 +299,7 @@ wgrad_general_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
 // swizzle phase from absolute address bits, see conv_gemm.cu).  L2 -> SM operand traffic per tap drops from (G + X) to
 // (G + 1.03 X) / 3: the per-tap kernel is operand-fetch bound at N = 64 (250 TFLOP/s).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr uint32_t WGR_SLAB = 72 * 128;             // 66 pixel rows of a 64-channel chunk, padded to whole 8-row swizzle atoms
-constexpr uint32_t WGR_SLAB_TX = 66 * 128;          // bytes one slab box delivers
+// (W = 32 works the same way with a 32-pixel K block: slab of 34 pixel rows, two K = 16 steps.)
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmXs, const WgradGenKArgs a) {
@@ -321,7 +320,9 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     const int kb0 = static_cast<int>(static_cast<long long>(a.kb_total) * split / a.nsplit);
     const int kb1 = static_cast<int>(static_cast<long long>(a.kb_total) * (split + 1) / a.nsplit);
     const int nchunks = a.Nt / 64;
-    const uint32_t stage_bytes = WGG_A_BYTES + nchunks * WGR_SLAB_TX;
+    const uint32_t a_chunk = static_cast<uint32_t>(a.W) * 128u;               // one 64-channel chunk of the G tile (W pixel rows)
+    const uint32_t slab = ((static_cast<uint32_t>(a.W) + 2u + 7u) & ~7u) * 128u;   // W + 2 pixel rows padded to whole 8-row swizzle atoms
+    const uint32_t stage_bytes = 2u * a_chunk + nchunks * (static_cast<uint32_t>(a.W) + 2u) * 128u;
     const uint32_t tmem_cols = 3 * a.Nt <= 256 ? 256u : 512u;
 
     if (warp == 0) {
@@ -350,7 +351,7 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
                 ptx::tma_load_5d(sA, &tmG, &full_bar[stage], 0, 0, y0, b, mt * 2);
                 for (int c = 0; c < nchunks; ++c)
-                    ptx::tma_load_5d(sA + WGG_A_BYTES + c * WGR_SLAB, &tmXs, &full_bar[stage], 0, -1, y0 + dy, b, nt * nchunks + c);
+                    ptx::tma_load_5d(sA + WGG_A_BYTES + c * slab, &tmXs, &full_bar[stage], 0, -1, y0 + dy, b, nt * nchunks + c);
             }
             __syncwarp();
             if (++stage == WGG_STAGES) { stage = 0; phase ^= 1u; }
@@ -358,8 +359,9 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     } else if (warp == 1) {
         const uint32_t idesc = ptx::make_idesc_bf16_mn(128, static_cast<uint32_t>(a.Nt));
         constexpr uint32_t K16_STEP = 2048u >> 4;
-        const uint64_t descA0 = ptx::make_mnmajor_sw128_desc(ptx::smem_u32(smem), WGG_CHUNK, 1024);
-        const uint64_t descB0 = ptx::make_mnmajor_sw128_desc(ptx::smem_u32(smem) + WGG_A_BYTES, WGR_SLAB, 1024);
+        const uint64_t descA0 = ptx::make_mnmajor_sw128_desc(ptx::smem_u32(smem), a_chunk, 1024);
+        const uint64_t descB0 = ptx::make_mnmajor_sw128_desc(ptx::smem_u32(smem) + WGG_A_BYTES, slab, 1024);
+        const int ksteps = a.W / 16;
         int stage = 0;
         uint32_t phase = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -370,8 +372,7 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 const uint64_t db = descB0 + static_cast<uint64_t>((stage * WGG_STAGE_MAX) >> 4);
 #pragma unroll
                 for (int t = 0; t < 3; ++t)            // x + dx is slab K row (x + dx + 1): tap t = dx + 1 starts t pixels (128 B each) in
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    for (int k = 0; k < ksteps; ++k)
                         ptx::umma_bf16(tmem_base + static_cast<uint32_t>(t * a.Nt), da + K16_STEP * k, db + (128u >> 4) * t + K16_STEP * k,
                                        idesc, (kb == kb0 && k == 0) ? 0u : 1u);
                 ptx::umma_commit(&empty_bar[stage]);
@@ -506,13 +507,22 @@ int wgrad_general_prepare(const bf16* g, const bf16* x, int B, int H, int W, int
     out->mtiles = (Cout + 127) / 128;
     out->ntiles = Cin / Nt;
     out->kb_total = B * H / rows;
-    static const bool rows_ok = [] { const char* v = getenv("HD_WGRAD_ROWS"); return !(v && v[0] == '0'); }();
-    out->rowmode = (rows_ok && ksize == 3 && W == 64 && Nt <= 128) ? 1 : 0;
+    static const int rows_min_w = [] {        // HD_WGRAD_ROWS=0: per-tap form everywhere; =64: filter-row form on 64-pixel-wide images only
+        const char* v = getenv("HD_WGRAD_ROWS");
+        if (!v) return 32;
+        const int x = atoi(v);
+        return x == 0 ? 1 << 30 : (x == 64 ? 64 : 32);
+    }();
+    out->rowmode = (ksize == 3 && (W == 64 || W == 32) && W >= rows_min_w && Nt <= 128) ? 1 : 0;
     int ns;
     if (out->rowmode) {
         // filter-row CTAs (three taps each): one full wave
-        cuuint32_t sb[5] = {64, 66, 1, 1, 1};
+        cuuint32_t sb[5] = {64, (cuuint32_t)W + 2, 1, 1, 1};
         if (encode_tmap_bf16(&out->tmXs, x, 5, xd, xs, sb, err, errlen)) return 1;
+        cuuint32_t gr[5] = {64, (cuuint32_t)W, 1, 1, 2};              // a K block is ONE image row here
+        if (encode_tmap_bf16(&out->tmG, g, 5, gd, gs, gr, err, errlen)) return 1;
+        out->rows_kb = 1;
+        out->kb_total = B * H;
         const int units = 3 * out->mtiles * out->ntiles;
         ns = num_sms / units;
         if (ns > out->kb_total / 32) ns = out->kb_total / 32;
