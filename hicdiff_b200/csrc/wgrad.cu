@@ -529,9 +529,10 @@ int wgrad_general_prepare(const bf16* g, const bf16* x, int B, int H, int W, int
         if (ns < 1) ns = 1;
         if (ns > 64) ns = 64;
     } else {
+        static const int min_kb = [] { const char* v = getenv("HD_WGRAD_MINKB"); const int x = v ? atoi(v) : 0; return x > 0 ? x : 16; }();
         const int units = out->taps * out->mtiles * out->ntiles;
         ns = (2 * num_sms + units - 1) / units;             // about two waves of CTAs
-        if (ns > out->kb_total / 32) ns = out->kb_total / 32;   // >= 32 K blocks per CTA: below that the fp32 partials (written, then re-read
+        if (ns > out->kb_total / min_kb) ns = out->kb_total / min_kb;   // >= 16 K blocks per CTA: below that the fp32 partials (written, then re-read
         if (ns < 1) ns = 1;                                      // by the reduction) cost more than the parallelism buys on the low-resolution levels
         if (ns > 32) ns = 32;
     }
