@@ -129,6 +129,15 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
     cfg.abi_version = 999
     h = ctypes.c_void_p()
     assert lib.hd_plan_create(ctypes.byref(cfg), ctypes.byref(h)) != 0 and b"ABI" in lib.hd_last_error()
+    # argument validation of the optimiser / operator entry points happens before any CUDA call: exercisable without a GPU
+    assert lib.hd_adam_create(None, None, -1, ctypes.byref(h)) != 0 and b"hd_adam_create" in lib.hd_last_error()
+    assert lib.hd_adam_create(None, None, 0, None) != 0 and b"null out" in lib.hd_last_error()
+    assert lib.hd_adam_step(None, None, 1e-3, 0.9, 0.999, 1e-8, 0.0, None) != 0 and b"null optimiser" in lib.hd_last_error()
+    assert lib.hd_adam_state(None, 0, None, None, None) != 0
+    assert lib.hd_adam_set_step(None, 3) != 0
+    lib.hd_adam_destroy(None)                                  # a null handle is a no-op
+    assert lib.hd_add_noise(None, None, 0.1, -1, None, None) != 0 and b"hd_add_noise" in lib.hd_last_error()
+    assert lib.hd_tile_count(-1, 64, 4) == -1
 
 
 def test_shard_range_partitions_exactly():
