@@ -49,7 +49,7 @@ struct UB {
     float *gn_scratch = nullptr, *la_scratch = nullptr, *ln_part = nullptr, *cs_part = nullptr, *la_ctx = nullptr, *zero_bias = nullptr;
     bf16 *T1 = nullptr, *T2 = nullptr, *T3 = nullptr;    // gradient temporaries (largest activation)
     std::vector<std::function<void()>> bwd;              // backward emitters, run in reverse
-    std::vector<ConvW*> convs;
+    std::vector<std::unique_ptr<ConvW>> convs;           // build-time only: every launch closure captures values, not these
     std::vector<PrepSlot> prep_slots;                    // every conv's weight preparation, uploaded by finish_prep()
     struct PrepTables { PrepSlot* slots = nullptr; int2 *fwd = nullptr, *bwd = nullptr; int nfwd = 0, nbwd = 0; };
     std::shared_ptr<PrepTables> prep = std::make_shared<PrepTables>();
@@ -104,8 +104,8 @@ struct UB {
         return x;
     }
     ConvW* convw(const std::string& wkey, const std::string& bkey, int Cout, int Cin, int k, bool ws) {
-        ConvW* c = new ConvW();
-        convs.push_back(c);
+        convs.emplace_back(new ConvW());
+        ConvW* c = convs.back().get();
         c->Cout = Cout; c->Cin = Cin; c->k = k; c->ws = ws;
         c->w = find_p(t, wkey, {Cout, Cin, k, k});
         c->b = bkey.empty() ? nullptr : find_p(t, bkey, {Cout});
@@ -633,7 +633,6 @@ int build_unet_trainer(hd_trainer* t) {
             return e;
         });
     }
-    for (ConvW* cw : u.convs) delete cw;
     if (u.ok && !u.finish_prep()) return 1;
     return u.ok ? 0 : 1;
 }
