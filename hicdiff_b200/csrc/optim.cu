@@ -19,7 +19,23 @@ struct hd_adam {
     float* exp_avg_sq = nullptr;
     int64_t total = 0;
     int64_t step = 0;
+    int device = 0;                       // the device the state lives on (current at hd_adam_create)
+    bool zeroed = false;                  // the moments are zero-filled by the first step, on ITS stream
 };
+
+namespace {
+// Run the body with the optimiser's device current (the caller may have another one selected), restore on exit.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+}  // namespace
 
 extern "C" {
 
@@ -28,6 +44,15 @@ int hd_adam_create(const void* const* params, const int64_t* numels, int32_t npa
     *out = nullptr;
     if (nparams < 0 || (nparams > 0 && (!params || !numels))) return tfail("hd_adam_create: bad argument");
     hd_adam* a = new hd_adam();
+    if (nparams > 0) {
+        // the state lives next to the parameters: take the device from the first parameter pointer
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, params[0]) == cudaSuccess && at.type == cudaMemoryTypeDevice) a->device = at.device;
+        else cudaGetDevice(&a->device);
+    } else {
+        cudaGetDevice(&a->device);
+    }
+    DeviceGuard guard(a->device);
     for (int i = 0; i < nparams; ++i) {
         if (numels[i] < 0 || (numels[i] > 0 && !params[i])) {
             delete a;
@@ -57,8 +82,6 @@ int hd_adam_create(const void* const* params, const int64_t* numels, int32_t npa
     }
     if (e == cudaSuccess && sb) e = cudaMalloc(&a->exp_avg, sb);
     if (e == cudaSuccess && sb) e = cudaMalloc(&a->exp_avg_sq, sb);
-    if (e == cudaSuccess && sb) e = cudaMemset(a->exp_avg, 0, sb);
-    if (e == cudaSuccess && sb) e = cudaMemset(a->exp_avg_sq, 0, sb);
     if (e != cudaSuccess) {
         hd_adam_destroy(a);
         return tfail("hd_adam_create: %s", cudaGetErrorString(e));
@@ -75,6 +98,15 @@ int hd_adam_step(hd_adam* a, const void* const* grads, double lr, double beta1, 
         return tfail("hd_adam_step: invalid hyper-parameter (lr %g, betas %g %g, eps %g, weight_decay %g)", lr, beta1, beta2, eps,
                      weight_decay);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DeviceGuard guard(a->device);
+    if (!a->zeroed && a->total > 0) {
+        // ordered on the caller's stream (a legacy-stream cudaMemset is not ordered against a non-blocking stream)
+        const size_t sb = static_cast<size_t>(a->total) * sizeof(float);
+        cudaError_t ez = cudaMemsetAsync(a->exp_avg, 0, sb, s);
+        if (ez == cudaSuccess) ez = cudaMemsetAsync(a->exp_avg_sq, 0, sb, s);
+        if (ez != cudaSuccess) return tfail("hd_adam_step: %s", cudaGetErrorString(ez));
+    }
+    a->zeroed = true;
     const size_t np = a->params.size();
     bool changed = false;
     for (size_t i = 0; i < np; ++i) {
@@ -110,6 +142,16 @@ int hd_adam_step(hd_adam* a, const void* const* grads, double lr, double beta1, 
 int hd_adam_state(hd_adam* a, int32_t index, float** exp_avg, float** exp_avg_sq, int64_t* step) {
     if (!a) return tfail("hd_adam_state: null optimiser");
     if (index < 0 || index >= static_cast<int32_t>(a->params.size())) return tfail("hd_adam_state: index %d out of range", index);
+    if (!a->zeroed && a->total > 0) {
+        // state requested before the first step (checkpoint restore): define it now, synchronously
+        DeviceGuard guard(a->device);
+        const size_t sb = static_cast<size_t>(a->total) * sizeof(float);
+        cudaError_t ez = cudaMemset(a->exp_avg, 0, sb);
+        if (ez == cudaSuccess) ez = cudaMemset(a->exp_avg_sq, 0, sb);
+        if (ez == cudaSuccess) ez = cudaDeviceSynchronize();
+        if (ez != cudaSuccess) return tfail("hd_adam_state: %s", cudaGetErrorString(ez));
+        a->zeroed = true;
+    }
     int64_t off = 0;
     for (int i = 0; i < index; ++i) off += ((a->numels[i] + 3) / 4) * 4;
     if (exp_avg) *exp_avg = a->exp_avg + off;
@@ -126,6 +168,7 @@ int hd_adam_set_step(hd_adam* a, int64_t step) {
 
 void hd_adam_destroy(hd_adam* a) {
     if (!a) return;
+    DeviceGuard guard(a->device);
     if (a->staging) cudaFreeHost(a->staging);
     if (a->table) cudaFree(a->table);
     if (a->exp_avg) cudaFree(a->exp_avg);

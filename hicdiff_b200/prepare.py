@@ -59,42 +59,53 @@ def remove_empty_bins(mat: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return out[:m * m].view(m, m), idx[:m]
 
 
-def _np_quantile_module():
-    try:
-        from numpy.lib import _function_base_impl as fb      # numpy >= 2
-    except ImportError:                                      # numpy 1.x
-        from numpy.lib import function_base as fb
-    return fb
+_NUMPY_MAJOR = int(np.__version__.split(".")[0])
 
 
 def percentile(x: torch.Tensor, q: float) -> np.floating:
-    """np.percentile(x, q) ('linear' method) of a CUDA fp32 tensor.  The two neighbouring order statistics are selected
-    exactly on the device; the virtual index, the interpolation weight and the lerp are evaluated by the INSTALLED numpy's
-    own helpers, so the result is bit-identical to np.percentile on the same box (numpy 2 does this arithmetic in the
-    array's float32, numpy 1.x -- the reference's pinned 1.23 -- in float64: the rule travels with the numpy version)."""
+    """np.percentile(x, q) ('linear' method, the default the reference uses at :88) of a CUDA fp32 tensor.  The two
+    neighbouring order statistics are selected exactly on the device; the virtual index, the interpolation weight and the
+    lerp are restated here for numpy's two dtype rules -- numpy >= 2 does this arithmetic in the array's float32, numpy
+    1.x (the reference's pinned 1.23) in float64 -- and checked against np.percentile of the installed numpy in
+    tests/test_host_cpu.py and tests/test_prepare_gpu.py (no private numpy helpers involved)."""
     _cuda(x.device)
     x = x.to(torch.float32).contiguous()
     n = x.numel()
     if n == 0:
         raise ValueError("percentile of an empty tensor")
-    fb = _np_quantile_module()
-    if int(np.__version__.split(".")[0]) >= 2:
-        quant = np.true_divide(q, np.float32(100))           # numpy >= 2: the divisor takes the data's dtype
-    else:
-        quant = np.true_divide(q, 100)
-    quant = np.asanyarray(quant)
-    method = fb._QuantileMethods["linear"]
-    vi = np.asanyarray(method["get_virtual_index"](n, quant))
-    probe = np.empty(0, dtype=np.float32)                    # _get_indexes only looks at the dtype
-    prev_i, next_i = fb._get_indexes(probe, vi, n)
-    lo, hi = int(prev_i) % n, int(next_i) % n                # -1 (above the last index) wraps to n - 1 like numpy's take
+    lo, hi, gamma = percentile_plan(n, q)
     ranks = (C.c_int64 * 2)(lo, hi)
     outv = (C.c_float * 2)()
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().hd_select_ranks(x.data_ptr(), n, ranks, 2, outv, _lib.stream_ptr()), "hd_select_ranks")
-    prev_v, next_v = np.float32(outv[0]), np.float32(outv[1])
-    gamma = fb._get_gamma(vi, prev_i, method)
-    return fb._lerp(prev_v, next_v, gamma)
+    return percentile_lerp(np.float32(outv[0]), np.float32(outv[1]), gamma)
+
+
+def percentile_plan(n: int, q: float):
+    """(lower rank, upper rank, interpolation weight) of np.percentile(a, q) for len(a) == n, 'linear' method:
+    virtual index (n - 1) * q / 100, floor / floor + 1 as the neighbours (clamped to the last index), gamma = the
+    fractional part, all in the float type numpy itself uses for a float32 array."""
+    ft = np.float32 if _NUMPY_MAJOR >= 2 else np.float64
+    quant = np.true_divide(ft(q), ft(100))
+    vi = ft(n - 1) * quant                                   # _compute_virtual_index for alpha = beta = 1
+    prev = np.floor(vi)
+    lo = int(prev)
+    hi = lo + 1
+    if vi >= n - 1:                                          # at / above the last index: both neighbours are the maximum
+        lo = hi = n - 1
+    if vi < 0:
+        lo = hi = 0
+    gamma = ft(vi - prev)
+    return lo, min(hi, n - 1), gamma
+
+
+def percentile_lerp(a, b, t):
+    """numpy's `_lerp`: a + (b - a) * t, switched to b - (b - a) * (1 - t) for t >= 0.5 (monotone at both ends);
+    evaluated in the dtype numpy promotes to (float32 data with a float32 / float64 weight)."""
+    diff = np.subtract(b, a)
+    if t >= 0.5:
+        return np.subtract(b, diff * (1 - t))
+    return np.add(a, diff * t)
 
 
 def normalize_contacts_(mat: torch.Tensor, per) -> torch.Tensor:
@@ -123,15 +134,23 @@ def load_both_constraints(stria: ArrayOrPath, strib: ArrayOrPath, res: int, devi
     return normalize_contacts_(mat, per)
 
 
-def add_noise(tiles: torch.Tensor, sigma_0: float, noise: Optional[torch.Tensor] = None, seed: int = 0) -> torch.Tensor:
+def _fresh_seed() -> int:
+    """A Philox key drawn from torch's global CPU generator: every call advances it, so consecutive chromosomes get
+    independent noise (the reference draws a fresh `torch.randn_like` per chromosome, :203-204) and `torch.manual_seed`
+    still makes a whole run reproducible."""
+    return int(torch.randint(0, 2 ** 62, (1,), device="cpu").item())
+
+
+def add_noise(tiles: torch.Tensor, sigma_0: float, noise: Optional[torch.Tensor] = None, seed: Optional[int] = None) -> torch.Tensor:
     """`data + sigma_0 * torch.randn_like(data)` (:203-204, 'deno').  `noise` injects the draws (parity); otherwise the
-    in-kernel Philox generator of the sampling path supplies them (one stream per tile, keyed by `seed`)."""
+    in-kernel Philox generator of the sampling path supplies them (one stream per tile, keyed by `seed`; `seed=None`
+    draws a fresh key from torch's generator per call, so no two calls share a noise field)."""
     _cuda(tiles.device)
     x = tiles.detach().to(torch.float32).contiguous()
     if noise is None:
         if x.dim() != 4 or tuple(x.shape[1:]) != (1, 64, 64):
             raise ValueError("Philox noise is generated per 64x64 tile: pass [B,1,64,64] or explicit `noise`")
-        noise = ops.philox_normal(x.shape[0], seed, 0, device=x.device)
+        noise = ops.philox_normal(x.shape[0], _fresh_seed() if seed is None else int(seed), 0, device=x.device)
     z = noise.detach().to(device=x.device, dtype=torch.float32).contiguous()
     if z.shape != x.shape:
         raise ValueError("noise must have the shape of the tiles")
@@ -142,7 +161,8 @@ def add_noise(tiles: torch.Tensor, sigma_0: float, noise: Optional[torch.Tensor]
     return out
 
 
-def make_splits(mat: torch.Tensor, res: int = 40000, piece_size: int = 64, sigma_0: float = 0.1, noise=None, seed: int = 0):
+def make_splits(mat: torch.Tensor, res: int = 40000, piece_size: int = 64, sigma_0: float = 0.1, noise=None,
+                seed: Optional[int] = None):
     """split_numpy (:183-213) for one chromosome and the 'deno' degradation: (target tiles, noisy tiles), both
     [n_tiles, 1, 64, 64] on the device -- what the reference stores as `*_full_chr_*` / `*_noisy_chr_*`."""
     band = 4 * int(40000 / res)

@@ -253,3 +253,40 @@ def test_fused_adam_has_no_cpu_path():
     with pytest.raises(RuntimeError, match="no CPU path"):
         opt.step()
     assert torch.equal(p.detach(), torch.zeros(4))
+
+
+def test_percentile_plan_matches_numpy():
+    """the 'linear' percentile rule is restated locally (no private numpy helpers); ranks + weight + lerp
+    reproduce np.percentile of the installed numpy bit for bit, dtype included."""
+    import numpy as np
+
+    from hicdiff_b200.prepare import percentile_lerp, percentile_plan
+
+    rng = np.random.default_rng(0)
+    for trial in range(1500):
+        n = int(rng.integers(1, 4000))
+        a = rng.standard_normal(n).astype(np.float32)
+        if trial % 5 == 0:
+            a = np.round(a, 1)                      # ties
+        q = float(rng.choice([99.0, 99.9, 99.99, 50.0, 0.0, 100.0, rng.uniform(0, 100)]))
+        ref = np.percentile(a, q)
+        lo, hi, gamma = percentile_plan(n, q)
+        srt = np.sort(a)
+        got = percentile_lerp(srt[lo], srt[hi], gamma)
+        assert ref == got and ref.dtype == got.dtype, (n, q, ref, got)
+
+
+def test_add_noise_default_seed_is_fresh_per_call():
+    """`seed=None` draws a new Philox key from torch's generator on every call (the reference draws a
+    fresh randn_like per chromosome, PrepareData_linear.py:203-204); torch.manual_seed makes the sequence reproducible."""
+    from hicdiff_b200 import prepare
+
+    torch.manual_seed(5)
+    a = [prepare._fresh_seed() for _ in range(3)]
+    torch.manual_seed(5)
+    b = [prepare._fresh_seed() for _ in range(3)]
+    assert a == b and len(set(a)) == 3
+    import inspect
+
+    assert inspect.signature(prepare.add_noise).parameters["seed"].default is None
+    assert inspect.signature(prepare.make_splits).parameters["seed"].default is None

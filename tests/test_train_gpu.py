@@ -595,3 +595,106 @@ def test_fused_adam_rejects_what_it_cannot_do():
         q = torch.nn.Parameter(torch.zeros(8))
         q.grad = torch.zeros(8)
         FusedAdam([q]).step()
+
+
+def test_forward_after_fused_adam_step_sees_the_new_weights():
+    """hd_adam_step updates the parameters through raw pointers; the sampling plan caches its own copies of
+    the weights keyed on `Tensor._version`, so the optimiser must bump the versions.  After a fused step, `net(x, t)`, a
+    no-grad validation `diffusion(x)` (train.py:150-170) and `super_resolution` must all run on the UPDATED weights, i.e.
+    equal a fresh net loaded from the same state_dict."""
+    from hicdiff_b200.hicdiff_condition import GaussianDiffusion
+    from hicdiff_b200.model.hicedrn_Diff import hicedrn_Diff
+    from hicdiff_b200.optim import Adam as FusedAdam
+
+    torch.manual_seed(3)
+    net = hicedrn_Diff(number_resnet=2, self_condition=True)
+    diff = GaussianDiffusion(net, image_size=64, timesteps=20, loss_type="l2", beta_schedule="sigmoid", auto_normalize=False).to(DEV)
+    diff.train()
+    opt = FusedAdam(diff.parameters(), lr=5e-3)          # large enough that stale weights give a visibly different eps
+    clean, noisy = O.synthetic_tiles(4, seed=5)
+    x = [noisy.to(DEV), clean.to(DEV)]
+    g = torch.Generator().manual_seed(9)
+    xt = torch.randn(4, 1, 64, 64, generator=g).to(DEV)
+    tt = torch.tensor([3, 7, 11, 19], device=DEV)
+    before = net(xt, tt, noisy.to(DEV)).clone()            # builds the plan (and its weight copies) BEFORE the update
+    versions = [p._version for p in net.parameters()]
+    for _ in range(2):
+        loss = diff.p_losses(x, t=torch.randint(0, 20, (4,), generator=g).to(DEV), noise=torch.randn(4, 1, 64, 64, generator=g).to(DEV))
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+    assert all(p._version > v for p, v in zip(net.parameters(), versions)), "fused Adam must bump Tensor._version"
+    after = net(xt, tt, noisy.to(DEV))
+    torch.manual_seed(4)
+    fresh_net = hicedrn_Diff(number_resnet=2, self_condition=True)
+    fresh = GaussianDiffusion(fresh_net, image_size=64, timesteps=20, loss_type="l2", beta_schedule="sigmoid", auto_normalize=False).to(DEV)
+    fresh.load_state_dict(diff.state_dict(), strict=True)
+    want = fresh_net(xt, tt, noisy.to(DEV))
+    assert torch.equal(after, want), f"stale weights after a fused step: {float((after - want).abs().max()):.3e}"
+    assert not torch.equal(after, before)
+    noise = O.synthetic_noise(20, 4, seed=8).to(DEV)
+    diff.eval()
+    fresh.eval()
+    assert torch.equal(diff.super_resolution(noisy.to(DEV), noise=noise), fresh.super_resolution(noisy.to(DEV), noise=noise))
+    with torch.no_grad():
+        nz = torch.randn(4, 1, 64, 64, generator=g).to(DEV)
+        assert torch.equal(diff.p_losses(x, t=tt, noise=nz), fresh.p_losses(x, t=tt, noise=nz))
+
+
+def test_fused_adam_state_dict_round_trip():
+    """moments and the step count live in the C handle; state_dict / load_state_dict carry them in
+    torch.optim.Adam's own layout, so a resumed run continues instead of restarting from zero moments, and a checkpoint
+    written by torch.optim.Adam loads into the fused optimiser (and vice versa)."""
+    from hicdiff_b200.optim import Adam as FusedAdam
+
+    g = torch.Generator().manual_seed(21)
+    shapes = [(5,), (3 * 4096 + 1,), (16, 8, 3, 3)]
+    base = [torch.randn(s, generator=g) for s in shapes]
+    grads = [[torch.randn(s, generator=g) for s in shapes] for _ in range(5)]
+
+    def run(opt_cls, params, its):
+        for it in its:
+            for p, gr in zip(params, grads[it]):
+                p.grad = gr.clone().to(DEV)
+            opt_cls.step()
+
+    kw = dict(lr=2e-3, weight_decay=0.01)
+    # uninterrupted fused run of 5 steps
+    pa = [torch.nn.Parameter(b.clone().to(DEV)) for b in base]
+    oa = FusedAdam(pa, **kw)
+    run(oa, pa, range(5))
+    # 3 steps, checkpoint, fresh optimiser (no step taken yet -> state is applied when the handle is created), 2 more
+    pb = [torch.nn.Parameter(b.clone().to(DEV)) for b in base]
+    ob = FusedAdam(pb, **kw)
+    run(ob, pb, range(3))
+    ck = ob.state_dict()
+    assert set(ck["state"]) == {0, 1, 2} and float(ck["state"][0]["step"]) == 3.0
+    pc = [torch.nn.Parameter(p.detach().clone()) for p in pb]
+    oc = FusedAdam(pc, **kw)
+    oc.load_state_dict(ck)
+    run(oc, pc, range(3, 5))
+    for p, q in zip(pa, pc):
+        assert torch.equal(p, q), "resumed run differs from the uninterrupted one"
+    assert oc.moments(pc[1])[2] == 5
+    # the same checkpoint drives torch.optim.Adam to the same place (layout compatibility)
+    pd = [torch.nn.Parameter(p.detach().clone()) for p in pb]
+    od = torch.optim.Adam(pd, foreach=True, **kw)
+    od.load_state_dict(ck)
+    run(od, pd, range(3, 5))
+    for p, q in zip(pa, pd):
+        assert torch.allclose(p, q, rtol=1e-6, atol=1e-9)
+    # and torch's checkpoint loads into a fused optimiser that has already stepped (handle exists)
+    pe = [torch.nn.Parameter(b.clone().to(DEV)) for b in base]
+    oe = FusedAdam(pe, **kw)
+    run(oe, pe, range(1))
+    pt = [torch.nn.Parameter(b.clone().to(DEV)) for b in base]
+    ot = torch.optim.Adam(pt, foreach=True, **kw)
+    run(ot, pt, range(3))
+    oe.load_state_dict(ot.state_dict())
+    with torch.no_grad():
+        for p, q in zip(pe, pt):
+            p.copy_(q)
+    run(oe, pe, range(3, 5))
+    run(ot, pt, range(3, 5))
+    for p, q in zip(pe, pt):
+        assert torch.allclose(p, q, rtol=1e-6, atol=1e-9)
