@@ -60,6 +60,11 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-reps", type=int, default=5)
     ap.add_argument("--profile-out", default="", help="write the per-launch profile of one step (JSON) to this file")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: --total-tiles tiles split over the N ranks (BASELINE config 3: 4096 SR3 tiles over 2/4/8 GPUs)")
+    ap.add_argument("--total-tiles", type=int, default=4096, help="job size for --scaling strong")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the secondary results (conditional Unet at B = 256 and at B = 16) of the default N = 1 run")
     return ap.parse_args()
 
 
@@ -146,11 +151,14 @@ def run_reference_arm(args, rank):
     sample = f"{args.steps} p_sample steps of {b} tiles after {args.warmup} warm-up, extrapolated to T={T_FULL}"
     line = {
         "impl": "reference", "metric": "tiles_per_sec_T1000", "value": tiles_s, "unit": "tiles/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 * (wl["batch"] if not args.batch else args.batch) / b,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "ms_per_step_scaled_to_gpu_batch": sec * 1e3 * (wl["batch"] if not args.batch else args.batch) / b,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": f"{wl['desc']}, CPU oracle (port of the reference, torch fp32, {cores} threads)",
+        "config": {"workload": f"{wl['desc']}, CPU oracle PORT of the reference algorithm (torch fp32, {cores} threads); the "
+                               "reference itself cannot travel to the GPU box",
                    "tiles_per_step": b, "timesteps": T_FULL, "schedule": wl["schedule"],
-                   "note": "ms_per_step is scaled to the GPU arm's per-GPU batch for comparability"},
+                   "note": "ms_per_step is the measured wall time of one p_sample step over tiles_per_step tiles; "
+                           "ms_per_step_scaled_to_gpu_batch rescales it linearly to the GPU arm's per-GPU batch"},
         "cpu_baseline": {"value": tiles_s, "unit": "tiles/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": tiles_s, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -244,6 +252,7 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.rows = []
+        self.windows = {}
         self.proc = None
         self.thread = None
 
@@ -262,7 +271,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) >= 7:
-                self.rows.append(parts)
+                self.rows.append((time.perf_counter(), parts))
+
+    def mark(self, name):
+        """Open / close a named window (perf_counter timestamps) -- samples are attributed to windows afterwards."""
+        self.windows.setdefault(name, []).append(time.perf_counter())
 
     def stop(self):
         if self.proc is None:
@@ -272,22 +285,87 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        busy = [s for s in sm if s > 0]
-        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+
+        def summarise(rows):
+            sm, mx, pw, reasons = [], [], [], set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[0]))
+                    mx.append(float(r[1]))
+                    pw.append(float(r[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            busy = [v for v in sm if v > 0]
+            return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                    "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+        def inside(name):
+            w = self.windows.get(name, [])
+            return [row for row in self.rows if any(a <= row[0] <= b for a, b in zip(w[0::2], w[1::2]))]
+
+        # under load = the timed region plus the e2e leg (the same kernels for a full T = 1000 chain); the timed region
+        # alone can be shorter than one nvidia-smi sampling period
+        load = inside("timed") + inside("e2e")
+        out = summarise(load if load else self.rows)
+        out["samples_timed_region"] = len(inside("timed"))
+        out["samples_e2e_leg"] = len(inside("e2e"))
+        out["window"] = "timed region + e2e leg (identical kernel sequence)" if load else "whole process (no sample fell inside a window)"
+        return out
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
+def secondary_result(name, B, K, dev, peaks):
+    """Device-timed steps of another workload / batch on this GPU (same timing rules as the headline: W >= 3 warm-up steps,
+    CUDA events on the launching stream, a sync either side) + the per-launch profile summed by family.  `kernel_sum_ms` is
+    the sum of the launches' own durations (each timed alone, back to back); what the graph step costs beyond it is launch
+    gaps / tails: `gap_share`."""
+    import torch
+
+    wl = WORKLOADS[name]
+    net, okw, Diffusion = build_variant(name)
+    diff = Diffusion(net, image_size=64, timesteps=T_FULL, loss_type="l2", beta_schedule=wl["schedule"]).to(dev)
+    from hicdiff_b200.synthetic import synthetic_tiles
+
+    cond = None
+    if okw["self_condition"]:
+        _, noisy = synthetic_tiles(B, seed=1234)
+        cond = noisy.to(dev)
+    plan = diff._sync_plan()
+    plan.sample(B, cond=cond, seed=1, t_start=T_FULL - 1, t_end=T_FULL - 5)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    x = plan.sample(B, cond=cond, seed=2, t_start=T_FULL - 1, t_end=T_FULL - K)
+    e1.record()
+    torch.cuda.synchronize()
+    assert torch.isfinite(x).all()
+    ms_step = e0.elapsed_time(e1) / K
+    prof = plan.profile_step(B, reps=5)
+    fam = {}
+    for p in prof:
+        f = fam.setdefault(p["kernel"], dict(ms=0.0, flops=0.0, launches=0))
+        f["ms"] += p["ms"]; f["flops"] += p["flops"]; f["launches"] += 1
+    ksum = sum(f["ms"] for f in fam.values())
+    conv = fam.get("conv_gemm", dict(ms=1.0, flops=0.0))
+    eps_l, step_l = plan.launches_per_step(B)
+    flops_step = FLOPS_PER_TILE_STEP[name] * B
+    out = {
+        "workload": f"{wl['desc']}, batch {B}, schedule {wl['schedule']}", "tiles_per_gpu": B, "steps_timed": K,
+        "value": B / (ms_step * 1e-3 * T_FULL), "unit": "tiles/s", "ms_per_step": ms_step, "launches_per_step": step_l,
+        "kernel_sum_ms": ksum, "gap_share": max(0.0, 1.0 - ksum / ms_step) if ms_step > 0 else None,
+        "step_floor_ms_at_sustained_peak": flops_step / (peaks["bf16_sustained"] * 1e12) * 1e3,
+        "whole_step_frac": flops_step / (ms_step * 1e-3) / 1e12 / peaks["bf16_sustained"],
+        "conv_gemm": {"ms": conv["ms"], "tflops": conv["flops"] / (conv["ms"] * 1e-3) / 1e12,
+                      "frac": conv["flops"] / (conv["ms"] * 1e-3) / 1e12 / peaks["bf16_sustained"]},
+        "families_ms": {k: round(f["ms"], 4) for k, f in fam.items()},
+    }
+    plan.destroy()
+    return out
+
+
 def run_b200_arm(args, rank, world):
     import torch
     import torch.distributed as dist
@@ -301,6 +379,12 @@ def run_b200_arm(args, rank, world):
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
     B = args.batch or wl["batch"]
+    if args.scaling == "strong":
+        # fixed job: total_tiles split contiguously over the ranks (hicdiff_b200/shard.py's rule); every rank must get
+        # the same count so that the per-step graph is identical (4096 = 2^12 divides by 1 / 2 / 4 / 8)
+        if args.total_tiles % world:
+            raise SystemExit(f"--scaling strong: {args.total_tiles} tiles do not split evenly over {world} ranks")
+        B = args.total_tiles // world
     K, W = args.steps, max(args.warmup, 3)
     name = args.workload
 
@@ -334,8 +418,10 @@ def run_b200_arm(args, rank, world):
     sampler = ClockSampler(local)
     stream = torch.cuda.current_stream()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     sampler.start()
+    time.sleep(0.35)          # nvidia-smi needs a few hundred ms before its first row
+    barrier()
+    sampler.mark("timed")
     e0.record(stream)
     # exactly K steps: chains of up to T steps each, starting at t = T-1 (x_T drawn by the in-kernel Philox)
     done = 0
@@ -345,7 +431,7 @@ def run_b200_arm(args, rank, world):
         done += n
     e1.record(stream)
     barrier()
-    clocks = sampler.stop()
+    sampler.mark("timed")
     ms = e0.elapsed_time(e1)
     t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -401,6 +487,7 @@ def run_b200_arm(args, rank, world):
         host_out = torch.empty(B * world if rank == 0 else B, 1, 64, 64).pin_memory()
         torch.manual_seed(7 + rank)
         barrier()
+        sampler.mark("e2e")
         t0 = time.perf_counter()
         dev_in = host_in.to(dev, non_blocking=True)
         if okw["self_condition"]:
@@ -416,6 +503,7 @@ def run_b200_arm(args, rank, world):
             host_out.copy_(out, non_blocking=True)
         barrier()
         wall = time.perf_counter() - t0
+        sampler.mark("e2e")
         tw = torch.tensor([wall], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
@@ -425,6 +513,19 @@ def run_b200_arm(args, rank, world):
                "call": ("GaussianDiffusion.super_resolution" if okw["self_condition"] else "GaussianDiffusion.sample")
                        + f" (one call = {T_FULL} steps)", "seconds_per_call": wall, "steps_per_call": T_FULL,
                "h2d_bytes_per_call": host_in.numel() * 4, "d2h_bytes_per_call": B * world * 64 * 64 * 4}
+
+    clocks = sampler.stop()
+
+    # ---- secondary results of the default run (N = 1, weak): the workload the north star's target sentence names (conditional
+    # Unet, B = 256) and BASELINE config 1's batch (B = 16), where the step is launch- / latency-bound rather than tensor-bound
+    secondary = None
+    if rank == 0 and world == 1 and args.scaling == "weak" and not args.no_secondary and name == "unet_uncond" and not args.batch:
+        secondary = {}
+        for key, sname, sb, sk in (("unet_cond_b256", "unet_cond", 256, 100), ("unet_cond_b16", "unet_cond", 16, 300)):
+            try:
+                secondary[key] = secondary_result(sname, sb, sk, dev, peaks)
+            except Exception as exc:      # a secondary result must never take the headline line down
+                secondary[key] = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample)
     cpu = None
@@ -439,7 +540,7 @@ def run_b200_arm(args, rank, world):
     if rank == 0:
         line = {
             "metric": "tiles_per_sec_T1000", "value": tiles_s, "unit": "tiles/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": f"{wl['desc']}, batch {B} synthetic 64x64 tiles per GPU, random-init weights (seed 0)",
                        "tiles_per_gpu": B, "timesteps": T_FULL, "schedule": wl["schedule"], "parallelism": f"tile-shard x{world}",
@@ -448,8 +549,11 @@ def run_b200_arm(args, rank, world):
                        "step": "one reverse-diffusion step (eps-net + posterior) as one CUDA graph launch"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": step_launches * K + (K + T_FULL - 1) // T_FULL, "launches_per_step": step_launches, "clocks": clocks,
-            "device_bytes": plan.device_bytes(),
+            "device_bytes": plan.device_bytes(), "secondary": secondary,
         }
+        if args.scaling == "strong":
+            line["config"]["total_tiles"] = args.total_tiles
+            line["config"]["parallelism"] = f"tile-shard x{world}: {args.total_tiles} tiles split contiguously, {B} per GPU"
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -10,7 +10,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: the calls are no-ops unless a tool (nsys / ncu --nvtx) is attached
+
 namespace hd {
+
+// NVTX range around a host-side phase (plan finalize, graph capture, one sampling chain, one training step, ...), so a
+// timeline shows which C-ABI call a launch belongs to (the reference has no profiler hooks at all).
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 
 typedef __nv_bfloat16 bf16;
 

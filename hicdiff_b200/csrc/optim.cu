@@ -92,6 +92,7 @@ int hd_adam_create(const void* const* params, const int64_t* numels, int32_t npa
 
 int hd_adam_step(hd_adam* a, const void* const* grads, double lr, double beta1, double beta2, double eps, double weight_decay,
                  void* stream) {
+    NvtxRange range("hd_adam_step");
     if (!a) return tfail("hd_adam_step: null optimiser");
     if (!grads && !a->params.empty()) return tfail("hd_adam_step: null gradient list");
     if (!(lr >= 0) || !(beta1 >= 0 && beta1 < 1) || !(beta2 >= 0 && beta2 < 1) || !(eps >= 0) || !(weight_decay >= 0))

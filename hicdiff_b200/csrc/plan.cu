@@ -649,6 +649,7 @@ int run_ops(const std::vector<Op>& ops, cudaStream_t s) {
 // Capture happens on a plan-private stream: the caller's stream may be the legacy default stream, which cannot be
 // captured; the instantiated graph is then launched on whatever stream the caller passes.
 int capture(const std::vector<Op>& ops, cudaStream_t s, cudaGraphExec_t* out) {
+    NvtxRange range("hd: graph capture");
     CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     int rc = run_ops(ops, s);
     cudaGraph_t g = nullptr;
@@ -666,6 +667,7 @@ int get_exec(hd_plan* P, int B, cudaStream_t s, Exec** out) {
     if (B <= 0) return fail("batch size must be positive (got %d)", B);
     auto it = P->execs.find(B);
     if (it != P->execs.end()) { *out = it->second.get(); return 0; }
+    NvtxRange range("hd: build executor (arena, launch list, graphs)");
     std::unique_ptr<Exec> ex(new Exec());
     ex->B = B;
     const int S = P->cfg.image_size;
@@ -862,6 +864,7 @@ int hd_plan_set_schedule(hd_plan* P, const float* sqrt_recip, const float* sqrt_
 }
 
 int hd_plan_finalize(hd_plan* P, void* stream) {
+    NvtxRange range("hd_plan_finalize (weight standardisation, GEMM layouts, FiLM table)");
     if (!P) return fail("hd_plan_finalize: null plan");
     if (ensure_device(P)) return 1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1034,6 +1037,7 @@ void hd_plan_destroy(hd_plan* P) {
 }
 
 int hd_eps_forward(hd_plan* P, const float* x, const float* cond, const float* time, float* eps, int32_t B, void* stream) {
+    NvtxRange range("hd_eps_forward");
     if (!P || !x || !time || !eps) return fail("hd_eps_forward: null argument");
     if (P->cfg.self_condition && !cond) return fail("hd_eps_forward: the plan is self-conditioned, cond must not be NULL");
     if (ensure_device(P)) return 1;
@@ -1051,6 +1055,7 @@ int hd_eps_forward(hd_plan* P, const float* x, const float* cond, const float* t
 
 int hd_ddpm_step(hd_plan* P, float* x, const float* eps, const float* noise, float* x0_out, int32_t t, int32_t B,
                  uint64_t seed, uint64_t tile_offset, void* stream) {
+    NvtxRange range("hd_ddpm_step");
     if (!P || !x || !eps) return fail("hd_ddpm_step: null argument");
     if (!P->coef || !P->ctl_one) return fail("hd_ddpm_step: plan not finalized");
     if (t < 0 || t >= P->T) return fail("hd_ddpm_step: t = %d out of range [0, %d)", t, P->T);
@@ -1066,6 +1071,7 @@ int hd_ddpm_step(hd_plan* P, float* x, const float* eps, const float* noise, flo
 
 int hd_sample(hd_plan* P, const float* cond, const float* noise, float* out, float* trace, int32_t B, uint64_t seed,
               uint64_t tile_offset, int32_t t_start, int32_t t_end, void* stream) {
+    NvtxRange range("hd_sample (reverse chain)");
     if (!P || !out) return fail("hd_sample: null argument");
     if (P->cfg.self_condition && !cond) return fail("hd_sample: the plan is self-conditioned, cond must not be NULL");
     if (t_start >= P->T || t_end < 0 || t_end > t_start) return fail("hd_sample: bad step range [%d, %d] for T = %d", t_start, t_end, P->T);

@@ -347,6 +347,7 @@ int hd_trainer_bind(hd_trainer* t, const char* key, const float* param, float* g
 }
 
 int hd_trainer_finalize(hd_trainer* t, void* stream) {
+    NvtxRange range("hd_trainer_finalize");
     if (!t) return tfail("hd_trainer_finalize: null trainer");
     if (t->finalized) return 0;
     T_TRY(cudaSetDevice(t->device));
@@ -358,6 +359,7 @@ int hd_trainer_finalize(hd_trainer* t, void* stream) {
 
 int hd_trainer_step(hd_trainer* t, const float* x_t, const float* cond, const float* time, const float* target,
                     const float* weight, int32_t loss_type, float* eps_out, float* loss_out, void* stream) {
+    NvtxRange range("hd_trainer_step (forward + loss + backward)");
     if (!t || !x_t || !time || !target || !weight || !loss_out) return tfail("hd_trainer_step: null argument");
     if (!t->finalized) return tfail("hd_trainer_finalize has not been called");
     if (t->cfg.self_condition && !cond) return tfail("hd_trainer_step: the net is self-conditioned, cond must not be NULL");

@@ -10,7 +10,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import ops
-from .shard import gather_tiles, shard_range
+from .shard import gather_tiles, nvtx_range, shard_range
 
 
 def band_blocks_for(res: int, piece: int = 64) -> int:
@@ -54,7 +54,8 @@ def denoise_chromosomes(diffusion, mats: Sequence[torch.Tensor], res: int = 4000
     local = torch.cat(outs, dim=0) if outs else all_tiles[:0]
     full = gather_tiles(local, n_total, group)
     res_mats, k = [], 0
-    for m, c in zip(mats, counts):
-        res_mats.append(ops.tile_scatter(full[k:k + c], m.shape[0], 64, band))
-        k += c
+    with nvtx_range("hicdiff_b200: reassemble chromosomes (tile_scatter)", full.is_cuda):
+        for m, c in zip(mats, counts):
+            res_mats.append(ops.tile_scatter(full[k:k + c], m.shape[0], 64, band))
+            k += c
     return res_mats

@@ -22,7 +22,28 @@ def shard_range(n_tiles: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
+class nvtx_range:
+    """NVTX range on CUDA tensors' phases (tile gather / reassembly); a no-op on CPU-only runs (the gloo tests)."""
+
+    def __init__(self, name: str, enabled: bool):
+        self.name, self.enabled = name, enabled and torch.cuda.is_available()
+
+    def __enter__(self):
+        if self.enabled:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if self.enabled:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def gather_tiles(local: torch.Tensor, n_tiles: int, group=None) -> torch.Tensor:
+    with nvtx_range("hicdiff_b200: gather tiles (all_gather)", local.is_cuda):
+        return _gather_tiles(local, n_tiles, group)
+
+
+def _gather_tiles(local: torch.Tensor, n_tiles: int, group=None) -> torch.Tensor:
     """All-gather the per-rank slices produced under `shard_range` back into the global [n_tiles, 1, H, W] order.
     Ragged slices are padded to the largest slice for the collective and trimmed afterwards."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
