@@ -143,7 +143,7 @@ def chain(name, log):
         else:
             trace = list(diff.sample(noisy, return_all_timesteps=True).unbind(1))   # stacked [B, T+1, ...]: [x_T, ..., x_0]
     assert len(trace) == T + 1
-    final = trace[-1]
+    final = trace[-1].clone()          # (the unconditional trace is a view of one stacked tensor: never save views)
     snaps = {t: trace[T - t].clone() for t in SNAP_T}    # trace[1 + (T-1-t)] = x after the step at t
     assert torch.equal(snaps[0], final)
     log(f"   {name}: reference chain T={T} in {time.time() - t0:.0f}s, final range [{float(final.min()):.3f}, {float(final.max()):.3f}], "
