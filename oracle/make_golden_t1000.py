@@ -13,7 +13,7 @@ Chains (reference `GaussianDiffusion(timesteps=1000)`, SURVEY.md 8(d) inputs: ti
 Tuned tail.  The reference ships no checkpoint, and random-init weights drive every chain into the clamp (x0 = +-1
 everywhere), which tests sign flips only.  A trained-like weight set that fits in the repository: the reference's own
 `p_losses` objective (src/hicdiff_condition.py:715-746) is minimised with Adam over ONLY `final_res_block.*` and
-`final_conv.*` (177 k of the 35.7 M parameters; everything else stays at the seeded default init) on seeded synthetic
+`final_conv.*` (152 k of the 35.7 M parameters; everything else stays at the seeded default init) on seeded synthetic
 tiles.  The tuned tensors are stored in the fixture; seed + fixture reproduce the full weight set anywhere.
 
 Every stored chain also carries snapshots x_t at a few t (to localise a divergence) and the reference-side quality
