@@ -79,6 +79,7 @@ struct Cfg {
 
 struct KArgs {
     int M, N, num_m_tiles, num_n_tiles, num_tiles, nkb, chunks0, chunks1, mode, W, P, kh, kw, pad, stages;
+    int passes;                    // passes over the source chunks per tap: 1, or 2 with split weights (hi, then lo)
     int Wl_box, rows_box;          // CONV_UPSAMPLE store box: low-res pixels per row / rows per 32-pixel warp block
     uint32_t slab_bytes;           // bytes of one slab TMA box
     uint32_t slab_dy_bytes;        // W * 128: A-descriptor advance per dy tap
@@ -277,7 +278,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int chunks = a.chunks0 + a.chunks1;
+    // K-loop chunks per tap: one pass over the sources' 64-channel chunks, or two with split (hi + lo) weights -- the second
+    // pass re-reads the same activations (source chunk = chunk % wrap) against the lo half of the tap's weight columns
+    const int src_chunks = a.chunks0 + a.chunks1;
+    const int chunks = src_chunks * a.passes;
 
     // Stage hand-off helpers (called by the elected producer lane).  CG == 2: both CTAs' loads complete on the LEADER's barrier.
     auto arm = [&](uint64_t* bar, uint32_t bytes) -> uint32_t {
@@ -338,9 +342,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 const int b = tc.mt / a.tiles_per_img;
                 const int y0 = ((tc.mt - b * a.tiles_per_img) * BLOCK_M) / a.PW;
                 for (int chunk = 0; chunk < chunks; ++chunk) {
-                    const bool second = chunk >= a.chunks0;
+                    const int cs = chunk >= src_chunks ? chunk - src_chunks : chunk;
+                    const bool second = cs >= a.chunks0;
                     const CUtensorMap* tm = second ? &tmA1 : &tmA0;
-                    const int c0 = (second ? chunk - a.chunks0 : chunk) * BLOCK_K;
+                    const int c0 = (second ? cs - a.chunks0 : cs) * BLOCK_K;
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
                     if (ptx::elect_one()) {
                         ptx::mbar_arrive_expect_tx(&full_bar[stage], a.slab_bytes);
@@ -360,9 +365,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
                             if (ptx::elect_one()) {
                                 const uint32_t lb = arm(&full_bar[stage], C::STAGE_BYTES);
-                                const bool second = chunk >= a.chunks0;
+                                const int cs = chunk >= src_chunks ? chunk - src_chunks : chunk;
+                                const bool second = cs >= a.chunks0;
                                 const CUtensorMap* tm = second ? &tmA1 : &tmA0;
-                                const int c0 = (second ? chunk - a.chunks0 : chunk) * BLOCK_K;
+                                const int c0 = (second ? cs - a.chunks0 : cs) * BLOCK_K;
                                 uint8_t* dstA = sA + stage * C::A_STAGE_BYTES;
                                 if (a.mode == CONV_UNSHUFFLE)
                                     ld5(dstA, tm, &full_bar[stage], lb, c0, kx, 0, ky, row0);
@@ -378,9 +384,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 }
             } else {
                 for (int chunk = 0; chunk < chunks; ++chunk) {
-                    const bool second = chunk >= a.chunks0;
+                    const int cs = chunk >= src_chunks ? chunk - src_chunks : chunk;
+                    const bool second = cs >= a.chunks0;
                     const CUtensorMap* tm = second ? &tmA1 : &tmA0;
-                    const int c0 = (second ? chunk - a.chunks0 : chunk) * BLOCK_K;
+                    const int c0 = (second ? cs - a.chunks0 : cs) * BLOCK_K;
                     for (int dxi = 0; dxi < 3; ++dxi) {
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
                         if (ptx::elect_one()) {
@@ -510,7 +517,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         int buf = 0;
 
         // pack 32 fp32 -> bf16, stage, TMA-store as the 32 x 32 box at (column ncol, row block of this warp)
-        auto stage_and_store = [&](const float (&f)[32], int ncol, const TileCoord& tc) {
+        auto stage_and_store = [&](const float (&f)[32], int ncol, const TileCoord& tc, const CUtensorMap* tmOut = nullptr) {
+            if (tmOut == nullptr) tmOut = &tmD;
             if (lane == 0) {
                 if constexpr (C::EPI_BUFS == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
             }
@@ -533,9 +541,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     // low-res pixel block -> output phase (pa, pb) through the [N, 2, W/2, 2, B*H/2] view
                     const int rowl = mrow / a.Wl_box;              // merged (b, low-res row)
                     const int wl = a.rows_box > 1 ? 0 : mrow - rowl * a.Wl_box;
-                    ptx::tma_store_5d(&tmD, my_stage + buf * EPI_BUF_BYTES, ncol, tc.phase & 1, wl, tc.phase >> 1, rowl);
+                    ptx::tma_store_5d(tmOut, my_stage + buf * EPI_BUF_BYTES, ncol, tc.phase & 1, wl, tc.phase >> 1, rowl);
                 } else {
-                    ptx::tma_store_2d(&tmD, my_stage + buf * EPI_BUF_BYTES, ncol, mrow);
+                    ptx::tma_store_2d(tmOut, my_stage + buf * EPI_BUF_BYTES, ncol, mrow);
                 }
                 ptx::bulk_commit();
             }
@@ -912,9 +920,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                 f[j] += sh.x; f[j + 1] += sh.y; f[j + 2] += sh.z; f[j + 3] += sh.w;
                             }
                         }
-                        if (e.silu) {
+                        if (e.silu == 1) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+                        } else if (e.silu == 2) {          // exact form (ex2 + rcp): "bf16w2" precision
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
                         }
                         if (e.out_scale != 1.0f) {
 #pragma unroll
@@ -934,6 +945,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         }
                         if (e.gn_part != nullptr && mt < a.m_tiles_real) write_partials(f, ncol, mt);   // rows are all valid: M % 32 == 0
                         stage_and_store(f, ncol, tc);
+                        if (e.out_lo != nullptr) {       // low half through the second output map (tmD31 doubles as it)
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] -= __bfloat162float(__float2bfloat16(f[j]));
+                            stage_and_store(f, ncol, tc, &tmD31);
+                        }
                     }
                 }
             }
@@ -1029,6 +1045,7 @@ cudaError_t launch_cfg(const ConvGemmLaunch& l, cudaStream_t s) {
     k.M = l.M; k.N = l.N; k.num_m_tiles = l.num_m_tiles; k.num_n_tiles = l.num_n_tiles; k.num_tiles = l.num_tiles;
     k.nkb = l.nkb; k.chunks0 = l.chunks0; k.chunks1 = l.chunks1; k.mode = l.mode; k.W = l.W; k.P = l.P;
     k.kh = l.kh; k.kw = l.kw; k.pad = l.pad; k.stages = l.stages; k.Wl_box = l.Wl_box; k.rows_box = l.rows_box;
+    k.passes = l.passes;
     k.slab_bytes = l.slab_bytes; k.slab_dy_bytes = l.slab_dy_bytes; k.res_b_bytes = l.res_b_bytes;
     k.PW = l.PW; k.tiles_per_img = l.tiles_per_img; k.H = l.Hh; k.m_tiles_real = l.m_tiles_real;
     k.epi = l.epi;
@@ -1127,7 +1144,8 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
     while (bn > 64 && out->num_m_tiles * (d.N / bn) * phases < num_sms && d.N % (bn / 2) == 0) bn /= 2;
     out->chunks0 = d.src0.C / BLOCK_K;
     out->chunks1 = d.src1.ptr ? d.src1.C / BLOCK_K : 0;
-    const int chunks = out->chunks0 + out->chunks1;
+    out->passes = d.wsplit ? 2 : 1;
+    const int chunks = (out->chunks0 + out->chunks1) * out->passes;
     int pad_slab_rows = 0;
     uint32_t pad_slab_bytes = 0;
     const int taps = d.mode == CONV_TAPS ? d.ksize * d.ksize : 4;
@@ -1268,6 +1286,11 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
             cuuint64_t os[1] = {(cuuint64_t)d.N * 2};
             cuuint32_t ob[2] = {32, 32};     // one epilogue warp: 32 rows x 32 columns, 64-byte rows, 64B swizzle
             if (encode_map(&out->tmD, d.out, 2, od, os, ob, err, errlen, 64)) return 1;
+            if (d.epi.out_lo != nullptr && encode_map(&out->tmD31, d.epi.out_lo, 2, od, os, ob, err, errlen, 64)) return 1;
+        }
+        if (d.epi.out_lo != nullptr && (out->kind == K_PAD || up || d.epi.gn_gamma != nullptr)) {
+            snprintf(err, errlen, "conv_gemm: the hi + lo output is built for the plain dense epilogue");
+            return 1;
         }
     } else {
         if (bn >= 64 || up) {

@@ -49,12 +49,16 @@ struct ConvEpilogue {
     int film_ld = 0;
     int film_off = 0;                 // column offset of this layer's slice inside a row
     int film_has_scale = 0;           // 1: [scale(N) | shift(N)], 0: [shift(N)] only
-    int silu = 0;                     // v = v * sigmoid(v)
+    int silu = 0;                     // 1: v = v * sigmoid(v) with one tanh.approx; 2: the same through ex2 + rcp ("bf16w2" precision)
     float out_scale = 1.0f;           // v *= out_scale
     const bf16* res = nullptr;        // v += res[m, c]   (row stride ldr)
     int ldr = 0;
     float* out_f32 = nullptr;         // if set: write fp32 [M, n_valid] instead of bf16
     int n_valid = 0;
+    // optional second bf16 output [M, N]: lo = bf16(v - bf16(v)), so out + out_lo carries ~16 mantissa bits.  Used where the
+    // consumer cancels a large common component (to_out conv -> channel LayerNorm; scripts/precision_study.py: rounding
+    // that one tensor to bf16 shifts the T = 1000 PSNR by 1.3e-2 dB, every other activation rounding together by 3e-4 dB).
+    bf16* out_lo = nullptr;
     // GroupNorm statistics of THIS conv's output, from the fp32 accumulators (+bias): one (sum, M2) pair per
     // (32-row warp block, 8-channel piece), M2 = sum of squared deviations from the piece-block's own mean (merged
     // stably, in a fixed order, by groupnorm_apply_kernel).
@@ -80,6 +84,8 @@ struct ConvGemmDesc {
     ConvEpilogue epi;
     int cg2_mode = 0;         // 1: run on CTA pairs (tcgen05 cta_group::2) where the kind supports it
     int pad_mode = 0;         // 3x3, N == 64: 1 = padded-slab form where >= 2 stages fit, 2 = wherever it fits, 0 = never
+    int wsplit = 0;           // 1: `weight` holds hi + lo bf16 pairs (rows of 2 * Ktot, per tap [hi | lo]): the K loop walks the
+                              // input channels twice per tap (x * hi + x * lo), "bf16w2" precision
 };
 
 // Opaque prepared launch (tensor maps encoded once, replayed inside CUDA graphs).
@@ -95,6 +101,7 @@ struct ConvGemmLaunch {
     int smem_bytes;
     // kernel scalar arguments
     int M, N, num_m_tiles, num_n_tiles, num_tiles, nkb, chunks0, chunks1, mode, W, P, kh, kw, pad, stages;
+    int passes;         // passes over the sources' channel chunks per tap: 1, or 2 with split (hi + lo) weights
     int Wl_box, rows_box;
     int PW, tiles_per_img, Hh;   // padded-slab kind: row pitch W + 2, 128-position tiles per image, image height
     uint32_t slab_bytes, slab_dy_bytes, res_b_bytes;
@@ -137,6 +144,7 @@ struct GroupNormArgs {
     int postadd_off = 0;
     const bf16* res = nullptr;        // + res[b, p, c] after the activation (ResnetBlock skip)
     float2* stats_out = nullptr;      // [B, 8] (optional) the (mean, rstd) this pass normalised with, kept for the training backward
+    int exact_act = 0;                // 1: SiLU through ex2 + rcp instead of one tanh.approx ("bf16w2" precision)
 };
 cudaError_t groupnorm_film_silu_run(const GroupNormArgs& a, cudaStream_t s);
 // Stand-alone producer of the same partials from a bf16 tensor (used when the input does not come from conv_gemm).
@@ -149,6 +157,7 @@ struct LayerNormArgs {
     const float* g;   // [C]
     float eps;
     const bf16* res = nullptr;  // + res[m, c] (Residual wrapper)
+    const bf16* x_lo = nullptr; // optional low half of x (x = x + x_lo, ConvEpilogue::out_lo): "bf16w2" precision
     int upsample2x = 0;         // nearest x2: write each pixel to its 2x2 block
     int H = 0, W = 0;           // needed for upsample2x
 };
@@ -209,6 +218,7 @@ struct StemConvArgs {
     const float* bias; // [Cout]
     bf16* y;           // [B, H, W, Cout]
     int B, H, W, Cout, Cin, ksize;
+    int precise = 0;   // 1: fp32 inputs and weights on the FMA pipe (stem_conv_kernel) instead of bf16 mma.sync fragments
 };
 cudaError_t stem_conv_run(const StemConvArgs& a, cudaStream_t s);
 
@@ -296,13 +306,14 @@ struct PrepSlot {
 };
 cudaError_t prep_weights_batched_run(const PrepSlot* slots, const int2* fwd_rows, int nfwd, const int2* bwd_rows, int nbwd, float eps,
                                      cudaStream_t s);
+// split = 1: hi + lo bf16 pairs, rows of 2K with per-tap [hi | lo] halves (the "bf16w2" precision mode, prep.cu)
 cudaError_t prep_conv_weight_run(const float* w, bf16* out, int Cout, int Cin, int ksize, int standardize, float eps,
-                                 int Npad, cudaStream_t s);
+                                 int Npad, cudaStream_t s, int split = 0);
 // Downsample 1x1 weight [Cout, 4*C] with K order (c, p1, p2) -> (p1, p2, c)
-cudaError_t prep_unshuffle_weight_run(const float* w, bf16* out, int Cout, int C, cudaStream_t s);
+cudaError_t prep_unshuffle_weight_run(const float* w, bf16* out, int Cout, int C, cudaStream_t s, int split = 0);
 // Upsample's 3x3 weight [Cout, Cin, 3, 3] -> four phase matrices [4][Cout][(u, v, cin)] of the equivalent 2x2 convs
 // over the low-resolution input (taps that land on the same low-res pixel are summed in fp32)
-cudaError_t prep_upsample_weight_run(const float* w, bf16* out, int Cout, int Cin, cudaStream_t s);
+cudaError_t prep_upsample_weight_run(const float* w, bf16* out, int Cout, int Cin, cudaStream_t s, int split = 0);
 
 // y[r, ldy*r + off + j] = bias[j] + sum_k act(x[r, k]) * W[j, k];  in_act: 0 none, 1 SiLU, 2 GELU(erf) (on the input), out_act: 0 none, 1 GELU(erf)
 cudaError_t linear_rows_run(const float* x, int ldx, const float* W, const float* bias, float* y, int ldy, int off,

@@ -40,7 +40,11 @@ __device__ __forceinline__ float silu_f(float v) {
 // order -> every CTA derives bit-identical statistics), and keeps the next slab's loads in flight while it normalises /
 // modulates / activates the current one.  (The one-CTA-per-64-KiB version paid the statistics prologue and a partial
 // last wave on every launch: 3.9 TB/s at batch 256.)
-template <bool HAS_RES, bool HAS_POST>   // compile out the residual stream and the SR3 post-add where a launch has none (issue-bound kernel)
+// exact form for the "bf16w2" precision mode: ex2 + rcp (each ~2^-22).  tanh.approx's 2^-11 is a FIXED function error -- like a
+// rounded weight it perturbs every step of a chain the same way (measured: it alone kept the T = 1000 PSNR 1.4e-2 dB off).
+__device__ __forceinline__ float silu_exact(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+template <bool HAS_RES, bool HAS_POST, bool EXACT = false>   // compile out the residual stream and the SR3 post-add where a launch has none (issue-bound kernel)
 __global__ void __launch_bounds__(GN_THREADS, 2)
 groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int total_slabs, const int slabs_per_cta) {
     __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
@@ -195,7 +199,7 @@ groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int
             t = ptx::unpack_bf16x2(u[k].w); v[6] = t.x; v[7] = t.y;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                v[j] = silu_f(fmaf(v[j], mul[j], add[j]));
+                v[j] = EXACT ? silu_exact(fmaf(v[j], mul[j], add[j])) : silu_f(fmaf(v[j], mul[j], add[j]));
                 if constexpr (HAS_POST) v[j] += post[j];
             }
             if constexpr (HAS_RES) {
@@ -281,6 +285,7 @@ channel_layernorm_kernel(const LayerNormArgs a) {
     }
 
     uint4 raw[LN_UNROLL][CPL];
+    uint4 rlo[LN_UNROLL][CPL];
     uint4 rres[LN_UNROLL][CPL];
 #pragma unroll
     for (int u = 0; u < LN_UNROLL; ++u) {
@@ -288,9 +293,11 @@ channel_layernorm_kernel(const LayerNormArgs a) {
 #pragma unroll
         for (int q = 0; q < CPL; ++q) {
             raw[u][q] = make_uint4(0, 0, 0, 0);
+            rlo[u][q] = make_uint4(0, 0, 0, 0);        // bf16 zeros: x + 0 when there is no low half
             rres[u][q] = make_uint4(0, 0, 0, 0);
             if (m < a.M) {
                 raw[u][q] = __ldg(reinterpret_cast<const uint4*>(a.x + m * C) + cl + q * LPP);
+                if (a.x_lo != nullptr) rlo[u][q] = __ldg(reinterpret_cast<const uint4*>(a.x_lo + m * C) + cl + q * LPP);
                 if (a.res != nullptr) rres[u][q] = __ldg(reinterpret_cast<const uint4*>(a.res + m * C) + cl + q * LPP);
             }
         }
@@ -307,6 +314,10 @@ channel_layernorm_kernel(const LayerNormArgs a) {
             t = ptx::unpack_bf16x2(raw[u][q].y); v[q][2] = t.x; v[q][3] = t.y;
             t = ptx::unpack_bf16x2(raw[u][q].z); v[q][4] = t.x; v[q][5] = t.y;
             t = ptx::unpack_bf16x2(raw[u][q].w); v[q][6] = t.x; v[q][7] = t.y;
+            t = ptx::unpack_bf16x2(rlo[u][q].x); v[q][0] += t.x; v[q][1] += t.y;
+            t = ptx::unpack_bf16x2(rlo[u][q].y); v[q][2] += t.x; v[q][3] += t.y;
+            t = ptx::unpack_bf16x2(rlo[u][q].z); v[q][4] += t.x; v[q][5] += t.y;
+            t = ptx::unpack_bf16x2(rlo[u][q].w); v[q][6] += t.x; v[q][7] += t.y;
 #pragma unroll
             for (int j = 0; j < 8; ++j) s += v[q][j];
         }
@@ -378,6 +389,13 @@ cudaError_t groupnorm_film_silu_run(const GroupNormArgs& a, cudaStream_t s) {
     const int per_cta = (total + grid - 1) / grid;
     grid = (total + per_cta - 1) / per_cta;
     const bool res = a.res != nullptr, post = a.postadd != nullptr;
+    if (a.exact_act) {
+        if (res && post) groupnorm_apply_kernel<true, true, true><<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
+        else if (res) groupnorm_apply_kernel<true, false, true><<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
+        else if (post) groupnorm_apply_kernel<false, true, true><<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
+        else groupnorm_apply_kernel<false, false, true><<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
+        return cudaGetLastError();
+    }
     if (res && post) groupnorm_apply_kernel<true, true><<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
     else if (res) groupnorm_apply_kernel<true, false><<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
     else if (post) groupnorm_apply_kernel<false, true><<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);

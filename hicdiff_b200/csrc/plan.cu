@@ -172,6 +172,7 @@ struct hd_plan {
     int film_ld = 0;
     int fourier_dim = 0, time_dim = 0;
     bool sr3 = false, hicedrn = false;
+    bool wsplit = false;          // "bf16w2" precision: conv weights kept as hi + lo bf16 pairs (hd_config.reserved[0] bits 4-5 == 1)
     int T = 0;
     float* coef = nullptr;        // [T, 8]
     float* time_values = nullptr; // [T]
@@ -294,6 +295,7 @@ struct Builder {
         d.weight = wq(wkey);
         d.pad_mode = (P->cfg.reserved[0] >> 1) & 3;
         d.cg2_mode = (P->cfg.reserved[0] >> 3) & 1;
+        d.wsplit = P->wsplit ? 1 : 0;
         d.N = N;
         d.out = y.p;
         d.epi = epi;
@@ -343,6 +345,7 @@ struct Builder {
         if (film_off >= 0) { g.film = film.base; g.film_off = film_off; }
         if (postadd_off >= 0) { g.postadd = film.base; g.postadd_off = postadd_off; }
         if (res) g.res = res->p;
+        g.exact_act = P->wsplit ? 1 : 0;
         if (!ok || dry) return;
         Op op{[g](cudaStream_t s) { return groupnorm_film_silu_run(g, s); }, prefix};
         op.kernel = "groupnorm_film_silu";
@@ -350,11 +353,12 @@ struct Builder {
         ops->push_back(op);
     }
 
-    Act layernorm(const Act& x, const std::string& gkey, const Act* res, bool up2x) {
+    Act layernorm(const Act& x, const std::string& gkey, const Act* res, bool up2x, const Act* x_lo = nullptr) {
         Act y = up2x ? alloc_act(x.H * 2, x.W * 2, x.C) : alloc_act(x.H, x.W, x.C);
         LayerNormArgs l;
         l.x = x.p; l.y = y.p; l.M = B * x.H * x.W; l.C = x.C; l.g = wf(gkey); l.eps = 1e-5f;
         l.res = res ? res->p : nullptr; l.upsample2x = up2x ? 1 : 0; l.H = x.H; l.W = x.W;
+        l.x_lo = x_lo ? x_lo->p : nullptr;
         if (ok && !dry) {
             Op op{[l](cudaStream_t s) { return channel_layernorm_run(l, s); }, gkey};
             op.kernel = "channel_layernorm";
@@ -417,7 +421,9 @@ struct Builder {
     // Residual(PreNorm(dim, LinearAttention(dim)))  (hicdiff_condition.py:199-227,319)
     Act linattn(const std::string& p, const Act& x, bool up2x) {
         auto lp = P->lattn.find(p);
-        if (!up2x && lp != P->lattn.end() && lp->second.bound <= LA_MAX_BOUND && lp->second.C == x.C &&
+        // (the fused block keeps its own bf16 copies of to_qkv / to_out: with split weights the block runs unfused, where both
+        // projections are conv_gemm launches over the hi + lo weights)
+        if (!P->wsplit && !up2x && lp != P->lattn.end() && lp->second.bound <= LA_MAX_BOUND && lp->second.C == x.C &&
             x.H * x.W >= 128 && (x.H * x.W) % 128 == 0) {
             // whole Residual(PreNorm(LinearAttention)) block in three launches; qkv never reaches HBM
             Act y = alloc_act(x.H, x.W, x.C);
@@ -457,10 +463,16 @@ struct Builder {
         }
         free_act(qkv);
         note(p + ".attn_core", att);
-        Act o = conv(p + ".fn.fn.to_out.0.weight", p + ".fn.fn.to_out.0.bias", att, nullptr, x.C, 1, CONV_TAPS, ConvEpilogue());
+        // "bf16w2" precision: the to_out conv keeps its output as hi + lo bf16 (the LayerNorm behind it cancels a large
+        // per-pixel common component, which amplifies that one tensor's rounding; kernels.h, ConvEpilogue::out_lo)
+        ConvEpilogue eo;
+        Act o_lo;
+        if (P->wsplit) { o_lo = alloc_act(x.H, x.W, x.C); eo.out_lo = o_lo.p; }
+        Act o = conv(p + ".fn.fn.to_out.0.weight", p + ".fn.fn.to_out.0.bias", att, nullptr, x.C, 1, CONV_TAPS, eo);
         free_act(att);
-        Act y = layernorm(o, p + ".fn.fn.to_out.1.g", &x, up2x);
+        Act y = layernorm(o, p + ".fn.fn.to_out.1.g", &x, up2x, P->wsplit ? &o_lo : nullptr);
         free_act(o);
+        if (P->wsplit) free_act(o_lo);
         note(p, y);
         return y;
     }
@@ -498,6 +510,7 @@ struct Builder {
         a.x1 = P->cfg.self_condition ? (dry ? nullptr : ex->x) : nullptr;
         a.w = wf(wkey); a.bias = wf(bkey); a.y = y.p;
         a.B = B; a.H = S; a.W = S; a.Cout = Cout; a.Cin = P->cfg.self_condition ? 2 : 1; a.ksize = ksize;
+        a.precise = P->wsplit ? 1 : 0;      // fp32 weights (and inputs) on the FMA pipe instead of bf16 fragments
         if (ok && !dry) {
             Op op{[a](cudaStream_t s) { return stem_conv_run(a, s); }, wkey};
             op.kernel = "stem_conv";
@@ -596,7 +609,7 @@ struct Builder {
             if (slot < 0) { bad("no time-embedding slot for block " + p); return; }
             ConvEpilogue e1;
             e1.film = film.base; e1.film_row = film.row; e1.film_row_stride = film.row_stride; e1.film_ld = P->film_ld;
-            e1.film_off = P->film[slot].off; e1.film_has_scale = P->sr3 ? 0 : 1; e1.silu = 1;
+            e1.film_off = P->film[slot].off; e1.film_has_scale = P->sr3 ? 0 : 1; e1.silu = P->wsplit ? 2 : 1;
             Act h = conv(p + ".conv.proj.weight", p + ".conv.proj.bias", x, nullptr, F, 3, CONV_TAPS, e1);
             ConvEpilogue e2;
             e2.out_scale = 0.1f; e2.res = x.p; e2.ldr = F;
@@ -821,6 +834,11 @@ int hd_plan_create(const hd_config* cfg, hd_plan** out) {
     P->num_sms = sms;
     P->sr3 = cfg->variant == HD_UNET_SR3 || cfg->variant == HD_HICEDRN_SR3;
     P->hicedrn = hic;
+    {
+        const int precision = (cfg->reserved[0] >> 4) & 3;
+        if (precision > 1) { delete P; return fail("unknown precision mode %d (0 = bf16, 1 = bf16 activations + split hi/lo weights)", precision); }
+        P->wsplit = precision == 1;
+    }
     P->T = cfg->timesteps;
     P->fourier_dim = hic ? 256 : cfg->dim;
     P->time_dim = hic ? 1024 : cfg->dim * 4;
@@ -937,7 +955,8 @@ int hd_plan_finalize(hd_plan* P, void* stream) {
         if (Cin % 64 != 0) return fail("conv weight '%s': Cin = %d is not a multiple of 64", key.c_str(), Cin);
         const int Npad = Cout < 16 ? 16 : Cout;
         bf16* q = nullptr;
-        const size_t bytes = static_cast<size_t>(Npad) * Cin * k * k * 2;
+        const int split = P->wsplit ? 1 : 0;
+        const size_t bytes = static_cast<size_t>(Npad) * Cin * k * k * 2 * (split + 1);
         CUDA_TRY(cudaMalloc(&q, bytes));
         wq_bytes += bytes;
         P->wq[key] = q;
@@ -946,16 +965,16 @@ int hd_plan_finalize(hd_plan* P, void* stream) {
         if (is_up) {
             if (k != 3) return fail("Upsample weight '%s' has an unexpected shape", key.c_str());
             cudaFree(q);
-            const size_t ub = static_cast<size_t>(4) * Cout * 4 * Cin * 2;   // four phase matrices [Cout, 4*Cin]
+            const size_t ub = static_cast<size_t>(4) * Cout * 4 * Cin * 2 * (split + 1);   // four phase matrices [Cout, 4*Cin]
             CUDA_TRY(cudaMalloc(&q, ub));
             P->wq[key] = q;
-            CUDA_TRY(prep_upsample_weight_run(w.d, q, Cout, Cin, s));
+            CUDA_TRY(prep_upsample_weight_run(w.d, q, Cout, Cin, s, split));
         } else if (is_down) {
             if (k != 1 || Cin % 4 != 0) return fail("Downsample weight '%s' has an unexpected shape", key.c_str());
-            CUDA_TRY(prep_unshuffle_weight_run(w.d, q, Cout, Cin / 4, s));
+            CUDA_TRY(prep_unshuffle_weight_run(w.d, q, Cout, Cin / 4, s, split));
         } else {
             const int standardize = (!P->hicedrn && ends_with(key, ".proj.weight")) ? 1 : 0;
-            CUDA_TRY(prep_conv_weight_run(w.d, q, Cout, Cin, k, standardize, 1e-5f, Npad, s));
+            CUDA_TRY(prep_conv_weight_run(w.d, q, Cout, Cin, k, standardize, 1e-5f, Npad, s, split));
         }
         if (Npad != Cout) {
             const std::string bkey = key.substr(0, key.size() - 6) + "bias";

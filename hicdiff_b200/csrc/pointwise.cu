@@ -431,6 +431,19 @@ cudaError_t stem_conv_run(const StemConvArgs& a, cudaStream_t s) {
         return cudaErrorInvalidValue;
     const int pad = a.ksize / 2;
     const int K = a.Cin * a.ksize * a.ksize;
+    if (a.precise) {
+        // direct fp32 form ("bf16w2" precision): 4 image rows per CTA, weights and the input window in shared memory as fp32
+        if (a.H % STEM_ROWS != 0 || a.Cout % (4 * STEM_CO) != 0) return cudaErrorInvalidValue;
+        const size_t smem1 = (static_cast<size_t>(K) * a.Cout + static_cast<size_t>(a.Cin) * (STEM_ROWS + 2 * pad) * STEM_PITCH) * 4;
+        static size_t max_set1 = 0;
+        if (smem1 > 48 * 1024 && smem1 > max_set1) {
+            cudaError_t e = cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+            if (e != cudaSuccess) return e;
+            max_set1 = smem1;
+        }
+        stem_conv_kernel<<<a.B * (a.H / STEM_ROWS), STEM_THREADS, smem1, s>>>(a);
+        return cudaGetLastError();
+    }
     const int KP = (K + 15) & ~15;                       // <= 112: seven m16n8k16 steps
     const int x_elems = (a.Cin * (STEM_ROWS + 2 * pad) * STEM2_PITCH + 7) & ~7;
     const size_t smem = static_cast<size_t>(x_elems) * 2 + static_cast<size_t>(KP) * 4 + static_cast<size_t>(64) * (KP + 8) * 2 +

@@ -17,16 +17,31 @@ namespace hd {
 namespace {
 
 // one output channel (GEMM row) per CTA; stat_out (optional) receives the row's (mean, rstd) when standardising
+//
+// split = 1 ("bf16w2" precision): every weight is kept as hi + lo, hi = bf16(v), lo = bf16(v - hi) (together ~16
+// mantissa bits); a GEMM row is then 2K long, per tap [hi(0..Cin) | lo(0..Cin)] -- the conv walks its input channels twice per
+// tap (conv_gemm.cu, KArgs::wrap), so the product is x * hi + x * lo with fp32 accumulation.
+__device__ __forceinline__ void store_weight(bf16* __restrict__ orow, int tap, int ci, int Cin, float v, int split) {
+    const bf16 hi = __float2bfloat16(v);
+    if (split) {
+        orow[(2 * tap) * Cin + ci] = hi;
+        orow[(2 * tap + 1) * Cin + ci] = __float2bfloat16(v - __bfloat162float(hi));
+    } else {
+        orow[tap * Cin + ci] = hi;
+    }
+}
+
 __device__ __forceinline__ void prep_conv_weight_row(const float* __restrict__ w, bf16* __restrict__ out, const int co, int Cout, int Cin,
-                                                     int ksize, int standardize, float eps, float2* stat_out) {
+                                                     int ksize, int standardize, float eps, float2* stat_out, int split = 0) {
     __shared__ float s_red[8];
     __shared__ float s_stat[2];
     const int tid = threadIdx.x;
     const int kk = ksize * ksize;
     const int K = Cin * kk;
-    bf16* orow = out + static_cast<size_t>(co) * K;
+    const int Kout = split ? 2 * K : K;
+    bf16* orow = out + static_cast<size_t>(co) * Kout;
     if (co >= Cout) {   // zero padding rows (N padded up to the GEMM tile)
-        for (int i = tid; i < K; i += blockDim.x) orow[i] = __float2bfloat16(0.f);
+        for (int i = tid; i < Kout; i += blockDim.x) orow[i] = __float2bfloat16(0.f);
         return;
     }
     const float* wrow = w + static_cast<size_t>(co) * K;
@@ -64,14 +79,14 @@ __device__ __forceinline__ void prep_conv_weight_row(const float* __restrict__ w
         const int tap = i / Cin;
         const int ci = i - tap * Cin;
         const float v = (wrow[ci * kk + tap] - mean) * rstd;
-        orow[i] = __float2bfloat16(v);
+        store_weight(orow, tap, ci, Cin, v, split);
     }
 }
 
 __global__ void __launch_bounds__(256)
 prep_conv_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int ksize,
-                        int standardize, float eps, int Npad) {
-    prep_conv_weight_row(w, out, blockIdx.x, Cout, Cin, ksize, standardize, eps, nullptr);
+                        int standardize, float eps, int Npad, int split) {
+    prep_conv_weight_row(w, out, blockIdx.x, Cout, Cin, ksize, standardize, eps, nullptr, split);
 }
 
 // ---- the training step's per-step weight preparation for ALL convs in two launches (it was three short launches per conv:
@@ -99,13 +114,14 @@ prep_weights_bwd_batched_kernel(const PrepSlot* __restrict__ slots, const int2* 
 }
 
 __global__ void __launch_bounds__(256)
-prep_unshuffle_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int C) {
+prep_unshuffle_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int C, int split) {
     const int co = blockIdx.x;
     const int K = 4 * C;
+    bf16* orow = out + static_cast<size_t>(co) * (split ? 2 * K : K);
     for (int i = threadIdx.x; i < K; i += blockDim.x) {
         const int tap = i / C;        // p1 * 2 + p2
         const int c = i - tap * C;
-        out[static_cast<size_t>(co) * K + i] = __float2bfloat16(w[static_cast<size_t>(co) * K + c * 4 + tap]);
+        store_weight(orow, tap, c, C, w[static_cast<size_t>(co) * K + c * 4 + tap], split);
     }
 }
 
@@ -114,12 +130,12 @@ prep_unshuffle_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out
 // lands on u = (a + ky + 1) / 2 - a  (a = 0: ky 0 -> u 0, ky 1,2 -> u 1;  a = 1: ky 0,1 -> u 0, ky 2 -> u 1).
 // out[phase = a*2 + b][co][(u*2 + v) * Cin + ci] = sum of the original taps that collapse onto (u, v), in fp32.
 __global__ void __launch_bounds__(256)
-prep_upsample_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin) {
+prep_upsample_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int split) {
     const int co = blockIdx.x;
     const int phase = blockIdx.y;
     const int a = phase >> 1, b = phase & 1;
     const int K = 4 * Cin;
-    bf16* orow = out + (static_cast<size_t>(phase) * Cout + co) * K;
+    bf16* orow = out + (static_cast<size_t>(phase) * Cout + co) * (split ? 2 * K : K);
     const float* wrow = w + static_cast<size_t>(co) * Cin * 9;
     for (int i = threadIdx.x; i < K; i += blockDim.x) {
         const int tap = i / Cin;
@@ -133,7 +149,7 @@ prep_upsample_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out,
                 acc += wrow[ci * 9 + ky * 3 + kx];
             }
         }
-        orow[i] = __float2bfloat16(acc);
+        store_weight(orow, tap, ci, Cin, acc, split);
     }
 }
 
@@ -191,18 +207,18 @@ cudaError_t prep_weights_batched_run(const PrepSlot* slots, const int2* fwd_rows
     return cudaGetLastError();
 }
 cudaError_t prep_conv_weight_run(const float* w, bf16* out, int Cout, int Cin, int ksize, int standardize, float eps,
-                                 int Npad, cudaStream_t s) {
-    prep_conv_weight_kernel<<<Npad, 256, 0, s>>>(w, out, Cout, Cin, ksize, standardize, eps, Npad);
+                                 int Npad, cudaStream_t s, int split) {
+    prep_conv_weight_kernel<<<Npad, 256, 0, s>>>(w, out, Cout, Cin, ksize, standardize, eps, Npad, split);
     return cudaGetLastError();
 }
 
-cudaError_t prep_unshuffle_weight_run(const float* w, bf16* out, int Cout, int C, cudaStream_t s) {
-    prep_unshuffle_weight_kernel<<<Cout, 256, 0, s>>>(w, out, Cout, C);
+cudaError_t prep_unshuffle_weight_run(const float* w, bf16* out, int Cout, int C, cudaStream_t s, int split) {
+    prep_unshuffle_weight_kernel<<<Cout, 256, 0, s>>>(w, out, Cout, C, split);
     return cudaGetLastError();
 }
 
-cudaError_t prep_upsample_weight_run(const float* w, bf16* out, int Cout, int Cin, cudaStream_t s) {
-    prep_upsample_weight_kernel<<<dim3(Cout, 4), 256, 0, s>>>(w, out, Cout, Cin);
+cudaError_t prep_upsample_weight_run(const float* w, bf16* out, int Cout, int Cin, cudaStream_t s, int split) {
+    prep_upsample_weight_kernel<<<dim3(Cout, 4), 256, 0, s>>>(w, out, Cout, Cin, split);
     return cudaGetLastError();
 }
 

@@ -7,11 +7,27 @@ Replaces, for the sampling path, what `nn.Module.to(device)` + ATen dispatch do 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
 
 from . import _lib
+
+
+# GEMM precision of the sampling path.  The reference computes in fp32 (hicdiff_condition.py:90,105 pick the fp32
+# eps); bf16 operands are the fast default.  "bf16w2" keeps every conv weight as a hi + lo bf16 pair (two MMAs per product,
+# ~16 mantissa bits on the weights; activations stay bf16): rounding the WEIGHTS is a fixed perturbation of the model that a
+# 1000-step chain accumulates coherently, rounding activations is not (scripts/precision_study.py).  Select per net with
+# `net.precision = "bf16w2"` or process-wide with HICDIFF_B200_PRECISION.
+PRECISIONS = {"bf16": 0, "bf16w2": 1}
+
+
+def precision_of(net) -> str:
+    p = getattr(net, "precision", None) or os.environ.get("HICDIFF_B200_PRECISION", "bf16")
+    if p not in PRECISIONS:
+        raise ValueError(f"unknown precision {p!r}: choose one of {sorted(PRECISIONS)}")
+    return p
 
 
 def _params_version(module: torch.nn.Module) -> int:
@@ -74,7 +90,8 @@ class EpsPlan:
             one = torch.ones(1)
             self.set_schedule(one, one * 0, one, one * 0, one * 0, one * 0)
         T = int(self._schedule["sqrt_recip"].numel())
-        key = (str(dev), _params_version(self._net), self._schedule_id, T, self.debug_keep)
+        prec = precision_of(self._net)
+        key = (str(dev), _params_version(self._net), self._schedule_id, T, self.debug_keep, prec)
         if self._handle is not None and key == self._key:
             return self._handle
         with torch.cuda.device(dev):
@@ -94,6 +111,7 @@ class EpsPlan:
                 cfg.timesteps = T
                 cfg.num_blocks = cfgd["num_blocks"]
                 cfg.debug_keep = 1 if self.debug_keep else 0
+                cfg.reserved[0] = PRECISIONS[prec] << 4          # bits 4-5: precision (include/hicdiff_b200.h)
                 h = C.c_void_p()
                 _lib.check(lib.hd_plan_create(C.byref(cfg), C.byref(h)), "hd_plan_create")
                 self._handle = h.value

@@ -53,7 +53,11 @@ typedef struct hd_config {
     int32_t timesteps;        /* T (GaussianDiffusion.num_timesteps)                                                 */
     int32_t num_blocks;       /* HiCEDRN number_resnet (32); ignored for Unet                                        */
     int32_t debug_keep;       /* 1: keep every intermediate activation addressable via hd_debug_read               */
-    int32_t reserved[8];
+    int32_t reserved[8];      /* reserved[0]: option bits, 0 = defaults.  bit 0: GroupNorm applied in the conv epilogue;
+                               * bits 1-2: padded-slab conv form; bit 3: CTA pairs (tcgen05 cta_group::2);
+                               * bits 4-5: GEMM precision -- 0 = bf16 operands (default), 1 = "bf16w2": bf16 activations,
+                               * conv weights as hi + lo bf16 pairs (two MMAs per product; the reference computes in fp32,
+                               * src/hicdiff_condition.py:90,105).  Other words: 0.                                     */
 } hd_config;
 
 /* -------------------------------------------------------------------------------------------------------------

@@ -74,6 +74,36 @@ def test_eps_matches_reference_golden(nets, name):
         assert r <= EPS_TOL, f"{name} t={t}: eps rel-RMS {r:.3e} > {EPS_TOL}"
 
 
+@pytest.mark.parametrize("name", VARIANTS)
+def test_eps_split_weight_precision(nets, name):
+    """`net.precision = "bf16w2"` (conv weights as hi + lo bf16 pairs, every eps-net flavour incl. the folded Upsample, the
+    pixel-unshuffle Downsample, channel concats and HiCEDRN's padded tail conv): eps against the reference fixtures is no
+    worse than, and for the Unets clearly better than, the bf16 default; switching back restores the default's bits."""
+    net, v, _ = nets(name)
+    gold = torch.load(helpers.GOLD / f"{name}.pt")
+    B = gold["x_t"].shape[0]
+    _, noisy = O.synthetic_tiles(B, seed=gold["tile_seed"])
+    cond = noisy.cuda() if v["oracle"]["self_condition"] else None
+    t, ref = sorted(gold["eps"].items())[0]
+    base = net(gold["x_t"].cuda(), _time(v, t, B).cuda(), cond)
+    r0 = helpers.rel_rms(base, ref)
+    try:
+        net.precision = "bf16w2"
+        eps = net(gold["x_t"].cuda(), _time(v, t, B).cuda(), cond)
+        r1 = helpers.rel_rms(eps, ref)
+    finally:
+        net.precision = "bf16"
+    again = net(gold["x_t"].cuda(), _time(v, t, B).cuda(), cond)
+    _record(test="eps_precision", variant=name, t=t, rel_rms_bf16=r0, rel_rms_bf16w2=r1)
+    assert torch.isfinite(eps).all() and r1 <= EPS_TOL
+    assert r1 <= r0 * 1.05 + 1e-4, f"{name}: bf16w2 {r1:.3e} vs bf16 {r0:.3e}"
+    assert torch.equal(again, base)
+    with pytest.raises(ValueError):
+        net.precision = "fp64"
+        net(gold["x_t"].cuda(), _time(v, t, B).cuda(), cond)
+    net.precision = "bf16"
+
+
 @pytest.mark.parametrize("name,B", [("unet_cond", 3), ("unet_uncond", 1), ("unet_sr3", 5)])
 def test_eps_matches_oracle_fresh_inputs_per_sample_t(nets, name, B):
     """Different t per sample (the training-time call pattern), odd batch sizes (partial M tiles at 8x8)."""
