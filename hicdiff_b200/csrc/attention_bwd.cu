@@ -10,6 +10,8 @@
 //   with lane = d (or e), 32 x 32 matrices in registers, partial sums per pixel chunk combined in a fixed order.
 // Attention.forward (8x8 only, n = 64)  :239-251: P = softmax_j(s q k^T), O = P v; the textbook backward in shared memory,
 //   one CTA per (image, head).
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -363,6 +365,9 @@ cudaError_t linear_attention_bwd_run(const bf16* qkv, const bf16* dout, bf16* dq
     float* ksum = kmax + static_cast<size_t>(bh) * DH;
     float* cpart = ksum + static_cast<size_t>(bh) * DH;
     float* cd = cpart + static_cast<size_t>(bh) * LAB_SPLIT * 2 * DH * DH;
+    // tensor-core form (attention_bwd_mma.cu): two launches instead of six.  HD_LA_BWD_LEGACY=1 keeps the CUDA-core passes below.
+    static const bool legacy = [] { const char* v = getenv("HD_LA_BWD_LEGACY"); return v && atoi(v) != 0; }();
+    if (!legacy) return linear_attention_bwd_mma_run(qkv, dout, dqkv, B, n, kmax, ksum, cd, s);
     float* tpart = cd + static_cast<size_t>(bh) * 2 * DH * DH;
     float* tv = tpart + static_cast<size_t>(bh) * LAB_SPLIT * DH;
     la_kstats_kernel<<<bh, 256, 0, s>>>(qkv, n, kmax, ksum);

@@ -447,6 +447,9 @@ cudaError_t weight_standardize_bwd_run(const float* w, const float* dwt, int Cou
 // attention_bwd.cu -- backward of the linear-attention core and of the 8x8 softmax attention; qkv / dqkv [B, n, 384], dout [B, n, 128]
 size_t linattn_bwd_scratch_floats(int B);
 cudaError_t linear_attention_bwd_run(const bf16* qkv, const bf16* dout, bf16* dqkv, int B, int n, float* scratch, cudaStream_t s);
+// the same through mma.sync tiles (attention_bwd_mma.cu); kmax / ksum [B*4][32], cd [B*4][2][32][32] fp32 scratch
+cudaError_t linear_attention_bwd_mma_run(const bf16* qkv, const bf16* dout, bf16* dqkv, int B, int n, float* kmax, float* ksum,
+                                         float* cd, cudaStream_t s);
 cudaError_t full_attention_bwd_run(const bf16* qkv, const bf16* dout, bf16* dqkv, int B, int n, cudaStream_t s);
 
 // unet_train_kernels.cu -- resampling copies, thin convs at the ends of the Unet, standardised dgrad weights

@@ -34,7 +34,3 @@ cut -c1-260 gpurun_out/${TAG}_bench_unet_cond.json
 echo "=== strong scaling form at N=1 (SR3, 4096 tiles)"
 timeout 600 python bench.py --workload unet_sr3 --scaling strong --total-tiles 4096 --steps 20 --no-e2e --no-cpu-baseline > gpurun_out/${TAG}_bench_sr3_strong_n1.json 2> gpurun_out/${TAG}_bench_sr3_strong_n1.err
 tail -2 gpurun_out/${TAG}_bench_sr3_strong_n1.err; cut -c1-260 gpurun_out/${TAG}_bench_sr3_strong_n1.json
-echo "=== experimental stand-alone self-checks (linear-attention backward drafts)"
-for f in la_grad_mma la_ctx_mma; do
-  timeout 120 scripts/bin/$f > gpurun_out/${TAG}_$f.log 2>&1; echo "$f rc=$?"; tail -6 gpurun_out/${TAG}_$f.log
-done
