@@ -53,6 +53,8 @@ SIGNATURES = {
     "hd_trainer_bind": (C.c_int, [_vp, C.c_char_p, _vp, _vp, C.POINTER(_i64), _i32]),
     "hd_trainer_finalize": (C.c_int, [_vp, _vp]),
     "hd_trainer_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "hd_trainer_set_grad_buckets": (C.c_int, [_vp, C.POINTER(C.c_char_p), _i32]),
+    "hd_trainer_wait_grad_bucket": (C.c_int, [_vp, _i32, _vp]),
     "hd_trainer_num_launches": (C.c_int, [_vp]),
     "hd_trainer_profile": (C.c_int, [_vp, _i32, C.c_char_p, _i64, _vp]),
     "hd_trainer_device_bytes": (_i64, [_vp]),

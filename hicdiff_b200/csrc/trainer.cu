@@ -401,6 +401,8 @@ int hd_trainer_step(hd_trainer* t, const float* x_t, const float* cond, const fl
             } else {
                 if (op.join) le = join_side();
                 if (le == cudaSuccess) le = op.fn(t->cap_stream);
+                if (le == cudaSuccess && op.bucket >= 0)      // visible to streams outside the graph: an external record node
+                    le = cudaEventRecordWithFlags(t->bucket_ev[op.bucket], t->cap_stream, cudaEventRecordExternal);
             }
             if (le != cudaSuccess) { bad = op.tag.c_str(); break; }
         }
@@ -419,12 +421,38 @@ int hd_trainer_step(hd_trainer* t, const float* x_t, const float* cond, const fl
     } else {
         for (const TOp& op : t->ops) {
             cudaError_t e = op.fn(s);
+            if (e == cudaSuccess && op.bucket >= 0) e = cudaEventRecord(t->bucket_ev[op.bucket], s);
             if (e != cudaSuccess) return tfail("launch of '%s' failed: %s", op.tag.c_str(), cudaGetErrorString(e));
         }
         t->eager_steps[loss_type] += 1;
     }
     if (eps_out) T_TRY(cudaMemcpyAsync(eps_out, t->eps, tb, cudaMemcpyDeviceToDevice, s));
     T_TRY(cudaMemcpyAsync(loss_out, t->loss, 4, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+int hd_trainer_set_grad_buckets(hd_trainer* t, const char* const* first_module_prefix, int32_t n) {
+    if (!t || n < 0 || (n > 0 && !first_module_prefix)) return tfail("hd_trainer_set_grad_buckets: bad argument");
+    if (t->finalized) return tfail("hd_trainer_set_grad_buckets must be called before hd_trainer_finalize");
+    if (t->cfg.variant != HD_UNET && t->cfg.variant != HD_UNET_SR3) return tfail("gradient buckets are built for the Unet trainers");
+    T_TRY(cudaSetDevice(t->device));
+    for (cudaEvent_t e : t->bucket_ev) cudaEventDestroy(e);
+    t->bucket_ev.clear();
+    t->bucket_prefix.clear();
+    for (int i = 0; i < n; ++i) {
+        if (!first_module_prefix[i] || !first_module_prefix[i][0]) return tfail("hd_trainer_set_grad_buckets: empty prefix %d", i);
+        cudaEvent_t e = nullptr;
+        T_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        t->bucket_ev.push_back(e);
+        t->bucket_prefix.push_back(first_module_prefix[i]);
+    }
+    return 0;
+}
+
+int hd_trainer_wait_grad_bucket(hd_trainer* t, int32_t bucket, void* stream) {
+    if (!t || bucket < 0 || bucket >= static_cast<int32_t>(t->bucket_ev.size())) return tfail("hd_trainer_wait_grad_bucket: no bucket %d", bucket);
+    T_TRY(cudaSetDevice(t->device));
+    T_TRY(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), t->bucket_ev[bucket], 0));
     return 0;
 }
 
@@ -485,6 +513,7 @@ int64_t hd_trainer_device_bytes(hd_trainer* t) { return t ? static_cast<int64_t>
 
 void hd_trainer_destroy(hd_trainer* t) {
     if (!t) return;
+    for (cudaEvent_t e : t->bucket_ev) cudaEventDestroy(e);
     cudaSetDevice(t->device);
     for (int k = 0; k < 2; ++k) if (t->graph[k]) cudaGraphExecDestroy(t->graph[k]);
     if (t->cap_stream) cudaStreamDestroy(t->cap_stream);

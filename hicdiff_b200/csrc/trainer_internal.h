@@ -39,6 +39,9 @@ struct TOp {
     // join = 1 makes a main-stream op wait for all side work issued so far.  Lets HBM-bound reductions overlap the tensor-bound GEMMs.
     int side = 0;
     int join = 0;
+    // >= 0: a gradient-bucket marker (no kernel): every gradient of bucket `bucket` is final once the ops before it -- side
+    // stream included -- have run; the step records the bucket's event here so a communication stream can start its all-reduce
+    int bucket = -1;
 };
 }  // namespace hd
 
@@ -59,6 +62,10 @@ struct hd_trainer {
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     cudaStream_t cap_stream = nullptr, side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // data-parallel training (hd_trainer_set_grad_buckets): bucket k is complete when the backward reaches the first module whose
+    // name starts with bucket_prefix[k]; bucket_ev[k] is recorded there (an external event-record node inside the step's graph)
+    std::vector<std::string> bucket_prefix;
+    std::vector<cudaEvent_t> bucket_ev;
 };
 
 namespace hd {

@@ -49,6 +49,7 @@ struct UB {
     float *gn_scratch = nullptr, *la_scratch = nullptr, *ln_part = nullptr, *cs_part = nullptr, *la_ctx = nullptr, *zero_bias = nullptr;
     bf16 *T1 = nullptr, *T2 = nullptr, *T3 = nullptr;    // gradient temporaries (largest activation)
     std::vector<std::function<void()>> bwd;              // backward emitters, run in reverse
+    std::vector<std::string> bwd_name;                   // module prefix of each emitter (gradient-bucket boundaries)
     std::vector<std::unique_ptr<ConvW>> convs;           // build-time only: every launch closure captures values, not these
     std::vector<PrepSlot> prep_slots;                    // every conv's weight preparation, uploaded by finish_prep()
     struct PrepTables { PrepSlot* slots = nullptr; int2 *fwd = nullptr, *bwd = nullptr; int nfwd = 0, nbwd = 0; };
@@ -235,6 +236,7 @@ struct UB {
             a.stats_out = st2;
             push("groupnorm", p + ".block2.norm", [a](cudaStream_t s) { return groupnorm_film_silu_run(a, s); });
         }
+        bwd_name.push_back(p);
         bwd.push_back([=]() {
             const bf16* g = out->g;      // d out
             // block2: GroupNorm + SiLU, conv2
@@ -322,6 +324,7 @@ struct UB {
             e.res = x->p; e.ldr = C;
             if (!conv_fwd(p + ".to_out", co, *att, nullptr, out->p, e, false)) return out;
         }
+        bwd_name.push_back(p);
         bwd.push_back([=]() {
             const bf16* g = out->g;
             const bf16* d_o = g;                    // gradient w.r.t. the to_out conv's output
@@ -366,6 +369,7 @@ struct UB {
         TenP out = ten(x->H, Cout);
         if (!ok) return out;
         if (!conv_fwd(p, c, *x, nullptr, out->p, ConvEpilogue(), false)) return out;
+        bwd_name.push_back(p);
         bwd.push_back([=]() {
             if (!conv_wgrad(p + ".wgrad", c, out->g, x->H, *x, nullptr)) return;
             bf16* where = target(*x, T1);
@@ -386,6 +390,7 @@ struct UB {
             push("resample", p + ".unshuffle", [=](cudaStream_t s) { return unshuffle_run(in, up, Bn, Hl, Hl, C, 0, s); });
         }
         if (!conv_fwd(p + ".conv", c, *u, nullptr, out->p, ConvEpilogue(), false)) return out;
+        bwd_name.push_back(p);
         bwd.push_back([=]() {
             if (!conv_wgrad(p + ".wgrad", c, out->g, Hl, *u, nullptr)) return;
             if (!conv_dgrad(p + ".dgrad", c, out->g, Hl, 0, 4 * C, u->g, nullptr)) return;
@@ -408,6 +413,7 @@ struct UB {
             push("resample", p + ".nearest", [=](cudaStream_t s) { return upsample2x_run(in, up, Bn, Hl, Hl, C, s); });
         }
         if (!conv_fwd(p + ".conv", c, *u, nullptr, out->p, ConvEpilogue(), false)) return out;
+        bwd_name.push_back(p);
         bwd.push_back([=]() {
             if (!conv_wgrad(p + ".wgrad", c, out->g, 2 * Hl, *u, nullptr)) return;
             if (!conv_dgrad(p + ".dgrad", c, out->g, 2 * Hl, 0, C, u->g, nullptr)) return;
@@ -581,10 +587,23 @@ int build_unet_trainer(hd_trainer* t) {
         });
         x->gset = true;
     }
-    for (auto it = u.bwd.rbegin(); it != u.bwd.rend(); ++it) {
-        u.pending_join = true;
-        (*it)();
-        if (!u.ok) return 1;
+    {
+        size_t next_bucket = 0;
+        for (size_t i = u.bwd.size(); i-- > 0;) {
+            u.pending_join = true;
+            // gradient buckets: everything emitted so far (the modules AFTER this one in forward order) is final once the side
+            // stream has joined -- a marker op (join, then an event record) in front of the first module of the next bucket
+            while (next_bucket < t->bucket_prefix.size() && u.bwd_name[i].compare(0, t->bucket_prefix[next_bucket].size(), t->bucket_prefix[next_bucket]) == 0) {
+                const int b = static_cast<int>(next_bucket++);
+                u.push("marker", "grad_bucket." + std::to_string(b), [](cudaStream_t) { return cudaSuccess; });
+                t->ops.back().bucket = b;
+                t->ops.back().join = 1;
+            }
+            u.bwd[i]();
+            if (!u.ok) return 1;
+        }
+        if (next_bucket != t->bucket_prefix.size())
+            return tfail("gradient bucket boundary '%s' matches no module of this net (in backward order)", t->bucket_prefix[next_bucket].c_str());
     }
     u.pending_join = true;      // init_conv's column sums share cs_part with the side stream
     {   // init_conv: weight / bias gradient (its input needs none)

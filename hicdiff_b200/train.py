@@ -19,6 +19,37 @@ from . import _lib
 
 _TRAINABLE = (_lib.HD_HICEDRN, _lib.HD_HICEDRN_SR3, _lib.HD_UNET, _lib.HD_UNET_SR3)
 
+# Gradient buckets of the Unet's backward (data-parallel training).  The backward walks the modules in reverse:
+# bucket k is final when it reaches the first module starting with BUCKET_BOUNDARIES[k] (include/hicdiff_b200.h,
+# hd_trainer_set_grad_buckets); the last bucket (the rest, plus everything that depends on the time embedding and init_conv,
+# whose gradients accumulate until the end of the step) is reduced after the step.
+BUCKET_BOUNDARIES = ("ups.2.", "ups.0.", "downs.2.")
+_BUCKET_MODULES = (("final_conv.", "final_res_block.", "ups.3."), ("ups.2.", "ups.1."), ("ups.0.", "mid_", "downs.3."))
+
+
+def grad_bucket_of(name: str) -> int:
+    """Bucket of parameter `name` (state_dict key without `model.`): 0 .. len(BUCKET_BOUNDARIES); the last one is 'late'."""
+    late = len(_BUCKET_MODULES)
+    if ".mlp." in name or "noise_func" in name or name.startswith(("time_mlp.", "init_conv.")):
+        return late        # FiLM / noise-level Linears and the time MLP: back-propagated in one batch at the end of the step
+    for k, prefixes in enumerate(_BUCKET_MODULES):
+        if name.startswith(prefixes):
+            return k
+    return late
+
+
+def grad_bucket_layout(names, numels):
+    """(order, ranges): parameter indices in flat-buffer order (bucket by bucket, module order inside a bucket) and the
+    [lo, hi) element range of every bucket.  Pure host logic (tests/test_host_cpu.py)."""
+    nb = len(_BUCKET_MODULES) + 1
+    order = sorted(range(len(names)), key=lambda i: (grad_bucket_of(names[i]), i))
+    ranges, off = [], 0
+    for b in range(nb):
+        lo = off
+        off += sum(numels[i] for i in order if grad_bucket_of(names[i]) == b)
+        ranges.append((lo, off))
+    return order, ranges
+
 
 class Trainer:
     """One `hd_trainer` for a parameter-holder net (nets.hicedrn_Diff) at a fixed batch size."""
@@ -42,10 +73,23 @@ class Trainer:
         total = sum(p.numel() for p in params.values())
         self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
         self.grads: Dict[str, torch.Tensor] = {}
+        names = list(params)
+        # Unet: the flat buffer is laid out bucket by bucket in the order the backward completes them, so that each bucket is
+        # ONE contiguous all-reduce that can start while the backward is still running (enable_gradient_allreduce)
+        self.bucket_ranges = None
+        if cfgd["variant"] in (_lib.HD_UNET, _lib.HD_UNET_SR3):
+            order, self.bucket_ranges = grad_bucket_layout(names, [params[k].numel() for k in names])
+        else:
+            order = range(len(names))
         off = 0
-        for k, p in params.items():
-            self.grads[k] = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        views = {}
+        for i in order:
+            k = names[i]
+            views[k] = self.flat_grad[off:off + params[k].numel()].view_as(params[k])
+            off += params[k].numel()
+        for k in names:                       # `grads` keeps named_parameters order (the autograd node returns them in it)
+            self.grads[k] = views[k]
+        self._comm_stream = None
         cfg = _lib.hd_config()
         cfg.abi_version = _lib.HD_ABI_VERSION
         cfg.variant = cfgd["variant"]
@@ -61,6 +105,9 @@ class Trainer:
         with torch.cuda.device(dev):
             _lib.check(lib.hd_trainer_create(C.byref(cfg), self.batch, C.byref(h)), "hd_trainer_create")
             self._handle: Optional[int] = h.value
+            if self.bucket_ranges is not None:
+                arr = (C.c_char_p * len(BUCKET_BOUNDARIES))(*[b.encode() for b in BUCKET_BOUNDARIES])
+                _lib.check(lib.hd_trainer_set_grad_buckets(self._handle, arr, len(BUCKET_BOUNDARIES)), "hd_trainer_set_grad_buckets")
             for k, p in params.items():
                 shape = (C.c_int64 * max(p.dim(), 1))(*p.shape)
                 _lib.check(lib.hd_trainer_bind(self._handle, k.encode(), p.data_ptr(), self.grads[k].data_ptr(), shape, p.dim()),
@@ -135,10 +182,42 @@ def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
     return flat
 
 
-def enable_gradient_allreduce(net, group=None, enabled: bool = True) -> None:
+def enable_gradient_allreduce(net, group=None, enabled: bool = True, overlap: bool = True) -> None:
     """Data-parallel replicas (one process per GPU, torch.distributed initialised by the caller): average the gradients
-    across ranks inside every training step, as DistributedDataParallel would."""
-    object.__setattr__(net, "_grad_allreduce", (group,) if enabled else None)
+    across ranks inside every training step, as DistributedDataParallel would.  overlap=True (Unet trainers): the flat gradient
+    buffer is reduced in buckets on a communication stream, each bucket as soon as the backward has finished it (an event the
+    step's CUDA graph records), so NCCL runs next to the remaining backward kernels; overlap=False (and the hicedrn trainers): one
+    all-reduce of the whole buffer after the step."""
+    object.__setattr__(net, "_grad_allreduce", (group, bool(overlap)) if enabled else None)
+
+
+def allreduce_buckets_(trainer, group=None) -> None:
+    """Bucketed, overlapped form of allreduce_mean_ for a trainer whose step has just been enqueued on the current stream."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    world = dist.get_world_size(group)
+    flat, ranges = trainer.flat_grad, trainer.bucket_ranges
+    main = torch.cuda.current_stream(trainer.device)
+    if trainer._comm_stream is None:
+        trainer._comm_stream = torch.cuda.Stream(device=trainer.device)
+    comm = trainer._comm_stream
+    lib = _lib.load()
+    with torch.cuda.device(trainer.device):
+        for k, (lo, hi) in enumerate(ranges[:-1]):
+            if hi == lo:
+                continue
+            # the communication stream waits for bucket k's event inside the step that was just launched -- not for the step
+            _lib.check(lib.hd_trainer_wait_grad_bucket(trainer._handle, k, comm.cuda_stream), "hd_trainer_wait_grad_bucket")
+            with torch.cuda.stream(comm):
+                dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=group)
+                flat[lo:hi].div_(world)
+        lo, hi = ranges[-1]
+        if hi > lo:                       # the late bucket: final only when the step is (main stream order)
+            dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=group)
+            flat[lo:hi].div_(world)
+        main.wait_stream(comm)
 
 
 class _TrainStep(torch.autograd.Function):
@@ -149,20 +228,20 @@ class _TrainStep(torch.autograd.Function):
         loss, _ = trainer.step(x_t, cond, time, target, weight, loss_type)
         ar = getattr(trainer.net, "_grad_allreduce", None)
         if ar is not None:
-            allreduce_mean_(trainer.flat_grad, ar[0])
+            if len(ar) > 1 and ar[1] and trainer.bucket_ranges is not None:
+                allreduce_buckets_(trainer, ar[0])
+            else:
+                allreduce_mean_(trainer.flat_grad, ar[0])
         # snapshot: the trainer's buffer is rewritten by the next step, and a caller may run several forwards before any
         # backward (e.g. (loss1 + loss2).backward()) -- every loss must keep ITS gradients (one flat copy, ~0.05 ms)
         ctx.flat = trainer.flat_grad.clone()
-        ctx.shapes = [(k, g.shape, g.numel()) for k, g in trainer.grads.items()]
+        ctx.shapes = [(g.storage_offset(), g.shape, g.numel()) for g in trainer.grads.values()]   # named_parameters order
         return loss
 
     @staticmethod
     def backward(ctx, gout):
         flat = gout * ctx.flat                # ONE launch; a fresh tensor
-        grads, off = [], 0
-        for _, shape, numel in ctx.shapes:
-            grads.append(flat[off:off + numel].view(shape))
-            off += numel
+        grads = [flat[off:off + numel].view(shape) for off, shape, numel in ctx.shapes]
         return (None,) * 7 + tuple(grads)
 
 

@@ -156,6 +156,15 @@ HD_API int hd_trainer_finalize(hd_trainer* trainer, void* stream);
 HD_API int hd_trainer_step(hd_trainer* trainer, const float* x_t, const float* cond, const float* time, const float* target,
                     const float* weight, int32_t loss_type, float* eps_out, float* loss_out, void* stream);
 /* Launch groups of one step / per-kernel-family timing of one step as JSON {"family": {"ms", "flops", "ops"}} / bytes held */
+/* Data-parallel replicas (BASELINE config 5; DistributedDataParallel's bucketed, overlapped gradient all-reduce -- the reference
+ * itself has no distributed code).  Call BEFORE hd_trainer_finalize with n module-name prefixes in BACKWARD order
+ * (e.g. "ups.2.", "ups.0.", "downs.2."): bucket k holds the gradients of the modules the backward pass finishes before it reaches
+ * the first module whose name starts with prefix k (time-embedding and init_conv gradients are only final at the end of the
+ * step and belong to no bucket).  Every step then records one event per bucket inside its CUDA graph;
+ * hd_trainer_wait_grad_bucket makes `stream` (the caller's communication stream) wait for bucket k of the step most recently
+ * enqueued, so its all-reduce overlaps the rest of the backward.  Unet trainers only. */
+HD_API int hd_trainer_set_grad_buckets(hd_trainer* trainer, const char* const* first_module_prefix, int32_t n);
+HD_API int hd_trainer_wait_grad_bucket(hd_trainer* trainer, int32_t bucket, void* stream);
 HD_API int hd_trainer_num_launches(hd_trainer* trainer);
 HD_API int hd_trainer_profile(hd_trainer* trainer, int32_t reps, char* buf, int64_t buflen, void* stream);
 HD_API int64_t hd_trainer_device_bytes(hd_trainer* trainer);

@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--model", choices=["hicedrn", "unet"], default="hicedrn")
     ap.add_argument("--optim", choices=["torch", "fused"], default="torch", help="torch.optim.Adam (train.py verbatim) or hicdiff_b200.optim.Adam")
+    ap.add_argument("--allreduce", choices=["overlap", "flat"], default="overlap",
+                    help="N > 1: bucketed all-reduce overlapped with the backward (Unet), or one all-reduce of the flat buffer after the step")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -49,7 +51,7 @@ def main():
         diff = GaussianDiffusion(net, image_size=64, timesteps=1000, loss_type="l2", beta_schedule="linear", auto_normalize=False).cuda()
     diff.train()
     if world > 1:
-        T.enable_gradient_allreduce(net)
+        T.enable_gradient_allreduce(net, overlap=a.allreduce == "overlap")
     optname = "fused Adam (hd_adam_step)" if a.optim == "fused" else "torch Adam"
     if a.optim == "fused":
         from hicdiff_b200.optim import Adam as FusedAdam
@@ -91,7 +93,10 @@ def main():
                "dtype": "bf16 activations / fp32 parameters and gradients", "data": "synthetic",
                "config": {"workload": (f"conditional Unet (dim 64, mults 1/2/4/8) p_losses l2 + backward + {optname}, batch {a.batch}/GPU" if a.model == "unet" else
                                        f"hicedrn_Diff({a.blocks} blocks, self_condition) p_losses l2 + backward + {optname}, batch {a.batch}/GPU"),
-                          "allreduce": "one NCCL all-reduce of the flat fp32 gradient buffer per step" if world > 1 else "none"},
+                          "allreduce": ("none" if world == 1 else
+                                        "4 buckets in backward-completion order, NCCL on a communication stream overlapped with the backward"
+                                        if (a.allreduce == "overlap" and a.model == "unet") else
+                                        "one NCCL all-reduce of the flat fp32 gradient buffer after the step")},
                "model_tflops": 3 * fwd_flops * a.batch / (ms * 1e-3) / 1e12,
                "device_bytes": net._trainer.device_bytes(), "launch_groups": net._trainer.num_launch_groups()}
         if a.profile:

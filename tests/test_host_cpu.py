@@ -290,3 +290,35 @@ def test_add_noise_default_seed_is_fresh_per_call():
 
     assert inspect.signature(prepare.add_noise).parameters["seed"].default is None
     assert inspect.signature(prepare.make_splits).parameters["seed"].default is None
+
+
+def test_gradient_bucket_layout_partitions_the_parameters():
+    """the Unet trainer's flat gradient buffer is laid out bucket by bucket in backward-completion order
+    (hicdiff_b200/train.py).  Pure host logic: every parameter lands in exactly one bucket, buckets are contiguous and cover the
+    buffer, everything that depends on the time embedding is in the last ('late') bucket, and the C side's boundaries
+    (BUCKET_BOUNDARIES) are the first modules of the following bucket in backward order."""
+    from hicdiff_b200 import hicdiff_condition, hicdiff_sr3
+    from hicdiff_b200 import train as T
+
+    for net in (hicdiff_condition.Unet(dim=64, dim_mults=(1, 2, 4, 8), self_condition=True),
+                hicdiff_sr3.Unet(dim=64, dim_mults=(1, 2, 4, 8), self_condition=True, noise_level_emb=True)):
+        names = [k for k, _ in net.named_parameters()]
+        numels = [p.numel() for _, p in net.named_parameters()]
+        order, ranges = T.grad_bucket_layout(names, numels)
+        assert sorted(order) == list(range(len(names)))
+        assert ranges[0][0] == 0 and ranges[-1][1] == sum(numels)
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:])) and all(hi > lo for lo, hi in ranges)
+        assert len(ranges) == len(T.BUCKET_BOUNDARIES) + 1
+        late = len(ranges) - 1
+        for n in names:
+            b = T.grad_bucket_of(n)
+            if ".mlp." in n or "noise_func" in n or n.startswith(("time_mlp.", "init_conv.")):
+                assert b == late, n
+            if n.startswith(("final_res_block.block", "ups.3.0.block", "final_conv")):
+                assert b == 0, n
+            if n.startswith(("downs.0.", "downs.1.", "downs.2.")):
+                assert b == late, n
+        # buckets appear in the flat buffer in the order the backward completes them
+        pos = {i: k for k, i in enumerate(order)}
+        first_of = [min(pos[i] for i in range(len(names)) if T.grad_bucket_of(names[i]) == b) for b in range(len(ranges))]
+        assert first_of == sorted(first_of)
