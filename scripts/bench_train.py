@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--model", choices=["hicedrn", "unet"], default="hicedrn")
     ap.add_argument("--optim", choices=["torch", "fused"], default="torch", help="torch.optim.Adam (train.py verbatim) or hicdiff_b200.optim.Adam")
-    ap.add_argument("--allreduce", choices=["overlap", "flat"], default="overlap",
+    ap.add_argument("--allreduce", choices=["overlap", "flat"], default="flat",
                     help="N > 1: bucketed all-reduce overlapped with the backward (Unet), or one all-reduce of the flat buffer after the step")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
