@@ -47,6 +47,8 @@ linattn_context_kernel(const LinAttnArgs a) {
     __shared__ __align__(16) unsigned char s_buf[CTX_WARPS * DH * DH * 4];   // staging (20 KB) / reduction (32 KB)
     __shared__ float s_max[DH];
     __shared__ float s_wsum[CTX_WARPS][DH];
+    ptx::grid_dep_launch();     // PDL (ptx.cuh): the successor may be scheduled; then wait for the predecessor grid and its memory
+    ptx::grid_dep_wait();
     bf16* sP = reinterpret_cast<bf16*>(s_buf);
     bf16* sV = sP + CTX_TILE * CTX_PITCH;
     float* s_red = reinterpret_cast<float*>(s_buf);
@@ -207,6 +209,8 @@ __global__ void __launch_bounds__(OUT_THREADS)
 linattn_output_kernel(const LinAttnArgs a) {
     __shared__ __align__(16) bf16 s_q[OUT_PIX * OUT_PITCH];
     __shared__ __align__(16) bf16 s_ctx[HEADS * DH * CTXT_PITCH];
+    ptx::grid_dep_launch();     // PDL (ptx.cuh): the successor may be scheduled; then wait for the predecessor grid and its memory
+    ptx::grid_dep_wait();
     const int blocks_per_img = a.n / OUT_PIX;
     const int b = blockIdx.x / blocks_per_img;
     const int pix0 = (blockIdx.x - b * blocks_per_img) * OUT_PIX;
@@ -296,6 +300,8 @@ __global__ void __launch_bounds__(FA_MAXN)
 full_attention_kernel(const FullAttnArgs a) {
     __shared__ float s_k[FA_MAXN][DH];
     __shared__ float s_v[FA_MAXN][DH];
+    ptx::grid_dep_launch();     // PDL (ptx.cuh): the successor may be scheduled; then wait for the predecessor grid and its memory
+    ptx::grid_dep_wait();
     const int b = blockIdx.x / HEADS;
     const int h = blockIdx.x - b * HEADS;
     const int i = threadIdx.x;
@@ -364,17 +370,14 @@ full_attention_kernel(const FullAttnArgs a) {
 
 cudaError_t linear_attention_run(const LinAttnArgs& a, cudaStream_t s) {
     if (a.n % OUT_PIX != 0) return cudaErrorInvalidValue;
-    linattn_context_kernel<<<a.B * HEADS, CTX_THREADS, 0, s>>>(a);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(linattn_context_kernel, dim3(a.B * HEADS), dim3(CTX_THREADS), 0, s, a);
     if (e != cudaSuccess) return e;
-    linattn_output_kernel<<<a.B * (a.n / OUT_PIX), OUT_THREADS, 0, s>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(linattn_output_kernel, dim3(a.B * (a.n / OUT_PIX)), dim3(OUT_THREADS), 0, s, a);
 }
 
 cudaError_t full_attention_run(const FullAttnArgs& a, cudaStream_t s) {
     if (a.n > FA_MAXN) return cudaErrorInvalidValue;
-    full_attention_kernel<<<a.B * HEADS, FA_MAXN, 0, s>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(full_attention_kernel, dim3(a.B * HEADS), dim3(FA_MAXN), 0, s, a);
 }
 
 }  // namespace hd

@@ -80,6 +80,7 @@ struct Cfg {
 struct KArgs {
     int M, N, num_m_tiles, num_n_tiles, num_tiles, nkb, chunks0, chunks1, mode, W, P, kh, kw, pad, stages;
     int passes;                    // passes over the source chunks per tap: 1, or 2 with split weights (hi, then lo)
+    int static_weights;            // 1: the weights are constants of the graph (their load may precede the PDL wait)
     int Wl_box, rows_box;          // CONV_UPSAMPLE store box: low-res pixels per row / rows per 32-pixel warp block
     uint32_t slab_bytes;           // bytes of one slab TMA box
     uint32_t slab_dy_bytes;        // W * 128: A-descriptor advance per dy tap
@@ -277,6 +278,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if constexpr (TWO) ptx::cluster_sync_all(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // PDL: from here on our successor in the stream may be scheduled (its CTAs take the SMs as ours retire and run their own
+    // prologue meanwhile); each role below waits for the PREDECESSOR grid right before it first touches activations
+    ptx::grid_dep_launch();
 
     // K-loop chunks per tap: one pass over the sources' 64-channel chunks, or two with split (hi + lo) weights -- the second
     // pass re-reads the same activations (source chunk = chunk % wrap) against the lo half of the tap's weight columns
@@ -320,6 +324,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (warp-uniform, one lane issues)
+        if (!a.static_weights) ptx::grid_dep_wait();     // the trainer's weight layouts are written earlier in the same graph
         if constexpr (KIND == K_SLAB_RES || KIND == K_PAD) {
             if (ptx::elect_one()) {
                 const uint32_t lb = arm(res_bar, a.res_b_bytes);
@@ -328,6 +333,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
             __syncwarp();
         }
+        ptx::grid_dep_wait();      // weights above are constants of the plan; the activation loads below are not
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = tile0; tile < a.num_tiles; tile += tile_stride) {
@@ -508,6 +514,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // kernel epilogue-bound: one warp per scheduler issues ~1 instruction per 4-5 cycles).  bf16 output goes through a
         // per-warp, 64B-swizzled staging buffer and leaves as TMA tensor stores of 32 rows x 32 columns (rows past M
         // are clipped by the TMA unit); the fp32 head path (N padded to 16, one valid column) stores directly.
+        ptx::grid_dep_wait();       // residual reads and every store must follow the predecessor grid (the arena is reused)
         const int q = warp & 3;
         const int hc = (warp - 2) >> 2;
         const int r = q * 32 + lane;            // accumulator row == pixel within the tile
@@ -1046,6 +1053,7 @@ cudaError_t launch_cfg(const ConvGemmLaunch& l, cudaStream_t s) {
     k.nkb = l.nkb; k.chunks0 = l.chunks0; k.chunks1 = l.chunks1; k.mode = l.mode; k.W = l.W; k.P = l.P;
     k.kh = l.kh; k.kw = l.kw; k.pad = l.pad; k.stages = l.stages; k.Wl_box = l.Wl_box; k.rows_box = l.rows_box;
     k.passes = l.passes;
+    k.static_weights = l.static_weights;
     k.slab_bytes = l.slab_bytes; k.slab_dy_bytes = l.slab_dy_bytes; k.res_b_bytes = l.res_b_bytes;
     k.PW = l.PW; k.tiles_per_img = l.tiles_per_img; k.H = l.Hh; k.m_tiles_real = l.m_tiles_real;
     k.epi = l.epi;
@@ -1064,8 +1072,8 @@ cudaError_t launch_cfg(const ConvGemmLaunch& l, cudaStream_t s) {
         cfg.numAttrs = 1;
         return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, KIND, GNF, CG>, l.tmA0, l.tmA1, l.tmB, l.tmD, l.tmD31, l.tmD30, k);
     } else {
-        conv_gemm_kernel<BN, KIND, GNF, CG><<<l.grid, NUM_THREADS, l.smem_bytes, s>>>(l.tmA0, l.tmA1, l.tmB, l.tmD, l.tmD31, l.tmD30, k);
-        return cudaGetLastError();
+        return launch_pdl(conv_gemm_kernel<BN, KIND, GNF, CG>, dim3(l.grid), dim3(NUM_THREADS), l.smem_bytes, s, l.tmA0, l.tmA1, l.tmB, l.tmD,
+                          l.tmD31, l.tmD30, k);
     }
 }
 
@@ -1145,6 +1153,7 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
     out->chunks0 = d.src0.C / BLOCK_K;
     out->chunks1 = d.src1.ptr ? d.src1.C / BLOCK_K : 0;
     out->passes = d.wsplit ? 2 : 1;
+    out->static_weights = d.static_weights ? 1 : 0;
     const int chunks = (out->chunks0 + out->chunks1) * out->passes;
     int pad_slab_rows = 0;
     uint32_t pad_slab_bytes = 0;

@@ -14,6 +14,31 @@
 
 namespace hd {
 
+// Launch with programmatic stream serialization (PDL): the kernel's CTAs may be scheduled while the previous kernel of the stream
+// drains; the kernel itself calls ptx::grid_dep_wait() before it touches anything an earlier kernel wrote (ptx.cuh).  Inside a
+// stream capture this becomes a programmatic dependency edge of the graph.
+bool pdl_enabled();   // plan.cu: HD_PDL = 0 | 1; default: only inside a PdlScope (the training step), see there
+struct PdlScope {
+    PdlScope();
+    ~PdlScope();
+    PdlScope(const PdlScope&) = delete;
+    PdlScope& operator=(const PdlScope&) = delete;
+};
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // NVTX range around a host-side phase (plan finalize, graph capture, one sampling chain, one training step, ...), so a
 // timeline shows which C-ABI call a launch belongs to (the reference has no profiler hooks at all).
 struct NvtxRange {
@@ -84,6 +109,9 @@ struct ConvGemmDesc {
     ConvEpilogue epi;
     int cg2_mode = 0;         // 1: run on CTA pairs (tcgen05 cta_group::2) where the kind supports it
     int pad_mode = 0;         // 3x3, N == 64: 1 = padded-slab form where >= 2 stages fit, 2 = wherever it fits, 0 = never
+    int static_weights = 0;   // 1: `weight` is not written by any kernel of the graph this launch belongs to (the sampling plan's
+                              // weights, prepared at finalize): the resident-weight load may then precede the PDL wait (ptx.cuh).
+                              // The trainer re-derives its bf16 layouts every step -> 0.
     int wsplit = 0;           // 1: `weight` holds hi + lo bf16 pairs (rows of 2 * Ktot, per tap [hi | lo]): the K loop walks the
                               // input channels twice per tap (x * hi + x * lo), "bf16w2" precision
 };
@@ -102,6 +130,7 @@ struct ConvGemmLaunch {
     // kernel scalar arguments
     int M, N, num_m_tiles, num_n_tiles, num_tiles, nkb, chunks0, chunks1, mode, W, P, kh, kw, pad, stages;
     int passes;         // passes over the sources' channel chunks per tap: 1, or 2 with split (hi + lo) weights
+    int static_weights; // see ConvGemmDesc
     int Wl_box, rows_box;
     int PW, tiles_per_img, Hh;   // padded-slab kind: row pitch W + 2, 128-position tiles per image, image height
     uint32_t slab_bytes, slab_dy_bytes, res_b_bytes;

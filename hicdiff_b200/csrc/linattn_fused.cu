@@ -181,6 +181,8 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_launch();     // PDL (ptx.cuh): the successor may be scheduled; then wait for the predecessor grid and its memory
+    ptx::grid_dep_wait();
     constexpr uint32_t COL_K = 0, COL_V = 64, COL_CTX = 128;
 
     const int unit = blockIdx.x;
@@ -357,6 +359,8 @@ linattn_mix_kernel(const float* __restrict__ ctx_part, const float* __restrict__
                    bf16* __restrict__ mb, int parts, int C, float inv_n_scale) {
     __shared__ float s_ctx[HD][33];
     __shared__ __align__(16) float s_wo[32 * HD];   // this block's rows of Wo (C / 4 <= 32 output channels)
+    ptx::grid_dep_launch();     // PDL (ptx.cuh): the successor may be scheduled; then wait for the predecessor grid and its memory
+    ptx::grid_dep_wait();
     const int b = blockIdx.x;
     const int t = threadIdx.x;          // hd = h*32 + d
     const int h = t >> 5;
@@ -485,6 +489,8 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_launch();     // PDL (ptx.cuh): the successor may be scheduled; then wait for the predecessor grid and its memory
+    ptx::grid_dep_wait();
     constexpr uint32_t COL_Q = 0, COL_Y = 128;
     const int ntile = a.num_tiles > static_cast<int>(blockIdx.x) ? (a.num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;   // tiles of this CTA
 
@@ -762,18 +768,15 @@ static cudaError_t run_c(const LinAttnFusedLaunch& l, cudaStream_t s) {
     KvArgs ka;
     ka.n = d.n; ka.tiles_per_unit = l.tiles_per_unit * (TILE / KV_PX); ka.parts = l.parts; ka.rowsum = d.rowsum; ka.kshift = d.kshift;
     ka.ctx_part = d.ctx_part; ka.s_part = d.s_part; ka.eps = d.eps;
-    linattn_kv_kernel<C><<<d.B * l.parts, KV_THREADS, KvCfg<C>::SMEM_BYTES, s>>>(l.tmXk, l.tmW, ka);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(linattn_kv_kernel<C>, dim3(d.B * l.parts), dim3(KV_THREADS), KvCfg<C>::SMEM_BYTES, s, l.tmXk, l.tmW, ka);
     if (e != cudaSuccess) return e;
-    linattn_mix_kernel<<<dim3(d.B, 4), 128, 0, s>>>(d.ctx_part, d.s_part, d.wo, d.mb, l.parts, C,
-                                           0.17677669529663687f / static_cast<float>(d.n));   // 32^-0.5 / n
-    e = cudaGetLastError();
+    e = launch_pdl(linattn_mix_kernel, dim3(d.B, 4), dim3(128), 0, s, d.ctx_part, d.s_part, d.wo, d.mb, l.parts, C,
+                   0.17677669529663687f / static_cast<float>(d.n));   // 32^-0.5 / n
     if (e != cudaSuccess) return e;
     OutArgs oa;
     oa.n = d.n; oa.tiles_per_img = d.n / TILE; oa.num_tiles = l.num_tiles; oa.rowsum = d.rowsum; oa.bo = d.bo; oa.g2 = d.g2;
     oa.eps = d.eps;
-    linattn_out_kernel<C><<<l.out_grid, OUT_THREADS, OutCfg<C>::SMEM_BYTES, s>>>(l.tmX, l.tmW, l.tmM, l.tmY, oa);
-    return cudaGetLastError();
+    return launch_pdl(linattn_out_kernel<C>, dim3(l.out_grid), dim3(OUT_THREADS), OutCfg<C>::SMEM_BYTES, s, l.tmX, l.tmW, l.tmM, l.tmY, oa);
 }
 
 cudaError_t linattn_fused_run(const LinAttnFusedLaunch& l, cudaStream_t s) {

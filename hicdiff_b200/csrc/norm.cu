@@ -48,6 +48,8 @@ template <bool HAS_RES, bool HAS_POST, bool EXACT = false>   // compile out the 
 __global__ void __launch_bounds__(GN_THREADS, 2)
 groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int total_slabs, const int slabs_per_cta) {
     __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+    ptx::grid_dep_launch();     // PDL (ptx.cuh): the successor may be scheduled; then wait for the predecessor grid and its memory
+    ptx::grid_dep_wait();
     const int s0 = blockIdx.x * slabs_per_cta;
     const int s1 = min(s0 + slabs_per_cta, total_slabs);
     if (s0 >= s1) return;
@@ -265,6 +267,8 @@ constexpr int LN_UNROLL = 4;
 template <int C>
 __global__ void __launch_bounds__(256)
 channel_layernorm_kernel(const LayerNormArgs a) {
+    ptx::grid_dep_launch();     // PDL (ptx.cuh): the successor may be scheduled; then wait for the predecessor grid and its memory
+    ptx::grid_dep_wait();
     constexpr int CH = C / 8;                       // 16-byte chunks per pixel: 8, 16, 32, 64
     constexpr int LPP = CH < 32 ? CH : 32;          // lanes per pixel
     constexpr int CPL = CH / LPP;                   // chunks per lane (1, or 2 for C = 512)
@@ -390,16 +394,16 @@ cudaError_t groupnorm_film_silu_run(const GroupNormArgs& a, cudaStream_t s) {
     grid = (total + per_cta - 1) / per_cta;
     const bool res = a.res != nullptr, post = a.postadd != nullptr;
     if (a.exact_act) {
-        if (res && post) groupnorm_apply_kernel<true, true, true><<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
-        else if (res) groupnorm_apply_kernel<true, false, true><<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
-        else if (post) groupnorm_apply_kernel<false, true, true><<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
-        else groupnorm_apply_kernel<false, false, true><<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
+        if (res && post) return launch_pdl(groupnorm_apply_kernel<true, true, true>, dim3(grid), dim3(GN_THREADS), 0, s, a, slabs_per_img, total, per_cta);
+        else if (res) return launch_pdl(groupnorm_apply_kernel<true, false, true>, dim3(grid), dim3(GN_THREADS), 0, s, a, slabs_per_img, total, per_cta);
+        else if (post) return launch_pdl(groupnorm_apply_kernel<false, true, true>, dim3(grid), dim3(GN_THREADS), 0, s, a, slabs_per_img, total, per_cta);
+        else return launch_pdl(groupnorm_apply_kernel<false, false, true>, dim3(grid), dim3(GN_THREADS), 0, s, a, slabs_per_img, total, per_cta);
         return cudaGetLastError();
     }
-    if (res && post) groupnorm_apply_kernel<true, true><<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
-    else if (res) groupnorm_apply_kernel<true, false><<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
-    else if (post) groupnorm_apply_kernel<false, true><<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
-    else groupnorm_apply_kernel<false, false><<<grid, GN_THREADS, 0, s>>>(a, slabs_per_img, total, per_cta);
+    if (res && post) return launch_pdl(groupnorm_apply_kernel<true, true, false>, dim3(grid), dim3(GN_THREADS), 0, s, a, slabs_per_img, total, per_cta);
+    else if (res) return launch_pdl(groupnorm_apply_kernel<true, false, false>, dim3(grid), dim3(GN_THREADS), 0, s, a, slabs_per_img, total, per_cta);
+    else if (post) return launch_pdl(groupnorm_apply_kernel<false, true, false>, dim3(grid), dim3(GN_THREADS), 0, s, a, slabs_per_img, total, per_cta);
+    else return launch_pdl(groupnorm_apply_kernel<false, false, false>, dim3(grid), dim3(GN_THREADS), 0, s, a, slabs_per_img, total, per_cta);
     return cudaGetLastError();
 }
 
@@ -416,10 +420,10 @@ cudaError_t channel_layernorm_run(const LayerNormArgs& a, cudaStream_t s) {
     const int rows_per_block = (threads / 32) * (32 / lpp) * LN_UNROLL;
     const int grid = (a.M + rows_per_block - 1) / rows_per_block;
     switch (a.C) {
-        case 64: channel_layernorm_kernel<64><<<grid, threads, 0, s>>>(a); break;
-        case 128: channel_layernorm_kernel<128><<<grid, threads, 0, s>>>(a); break;
-        case 256: channel_layernorm_kernel<256><<<grid, threads, 0, s>>>(a); break;
-        case 512: channel_layernorm_kernel<512><<<grid, threads, 0, s>>>(a); break;
+        case 64: return launch_pdl(channel_layernorm_kernel<64>, dim3(grid), dim3(threads), 0, s, a);
+        case 128: return launch_pdl(channel_layernorm_kernel<128>, dim3(grid), dim3(threads), 0, s, a);
+        case 256: return launch_pdl(channel_layernorm_kernel<256>, dim3(grid), dim3(threads), 0, s, a);
+        case 512: return launch_pdl(channel_layernorm_kernel<512>, dim3(grid), dim3(threads), 0, s, a);
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -7,6 +7,7 @@
 // (p_sample_loop, hicdiff_condition.py:600-623).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -296,6 +297,7 @@ struct Builder {
         d.pad_mode = (P->cfg.reserved[0] >> 1) & 3;
         d.cg2_mode = (P->cfg.reserved[0] >> 3) & 1;
         d.wsplit = P->wsplit ? 1 : 0;
+        d.static_weights = 1;       // prepared at hd_plan_finalize, constant for every graph of the plan
         d.N = N;
         d.out = y.p;
         d.epi = epi;
@@ -798,7 +800,20 @@ int set_ctl(SampleCtl* dev, int step, int single, const float* noise, uint64_t s
 }  // namespace
 
 namespace hd {
-int set_error(const char* msg) { g_err = msg ? msg : ""; return 1; }   // trainer.cu reports through the same hd_last_error()
+int set_error(const char* msg) { g_err = msg ? msg : ""; return 1; }
+// Programmatic dependent launch (kernels.h::launch_pdl) of the forward-path kernels (conv_gemm, GroupNorm / LayerNorm apply, the
+// attention kernels, stem / head convs, the posterior step).  Measured on B200, same box, three repeats (profiles/r02_notes.md 8):
+//   training step (Unet, ~820 launches):  plain 11.96 - 11.98 ms | these kernels as programmatic dependents 11.78 - 11.80 ms | EVERY kernel
+//     of the step (a mechanical pass over the 63 backward launch sites, not kept) 12.1 - 13.6 ms;  hicedrn_Diff 58.29 / 58.29 / 59.16 ms
+//   sampling step (134 launches of mostly persistent kernels):  plain 5.99 ms | programmatic 6.15 ms
+// -> default: on only while a trainer enqueues its step (PdlScope); HD_PDL=1 forces it on everywhere, HD_PDL=0 off.
+static thread_local int g_pdl_scope = 0;
+PdlScope::PdlScope() { ++g_pdl_scope; }
+PdlScope::~PdlScope() { --g_pdl_scope; }
+bool pdl_enabled() {
+    static const int mode = [] { const char* v = getenv("HD_PDL"); return !v ? -1 : (v[0] == '0' ? 0 : 1); }();
+    return mode < 0 ? g_pdl_scope > 0 : mode == 1;
+}   // trainer.cu reports through the same hd_last_error()
 }
 
 // ================================================================================================= C ABI

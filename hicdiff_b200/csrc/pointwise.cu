@@ -29,6 +29,9 @@ constexpr int STEM_CO = 16;         // output channels per thread per pass
 
 __global__ void __launch_bounds__(STEM_THREADS)
 stem_conv_kernel(const StemConvArgs a) {
+    ptx::grid_dep_launch();     // PDL (ptx.cuh): the successor may be scheduled; then wait for the predecessor grid and its memory
+    ptx::grid_dep_wait();
+
     extern __shared__ __align__(16) float stem_smem[];
     const int k = a.ksize;
     const int pad = k / 2;
@@ -130,6 +133,9 @@ constexpr int STEM2_CTA_ROWS = 16;       // image rows per CTA: weights are stag
 
 __global__ void __launch_bounds__(STEM2_THREADS, 2)
 stem_conv_mma_kernel(const StemConvArgs a, const int KP) {
+    ptx::grid_dep_launch();     // PDL (ptx.cuh): the successor may be scheduled; then wait for the predecessor grid and its memory
+    ptx::grid_dep_wait();
+
     extern __shared__ __align__(16) unsigned char stem2_smem[];
     const int k = a.ksize;
     const int pad = k / 2;
@@ -237,6 +243,9 @@ stem_conv_mma_kernel(const StemConvArgs a, const int KP) {
 // ------------------------------------------------------------------------------------------ 1x1 head
 __global__ void __launch_bounds__(256)
 head_conv1x1_kernel(const HeadConvArgs a) {
+    ptx::grid_dep_launch();     // PDL (ptx.cuh): the successor may be scheduled; then wait for the predecessor grid and its memory
+    ptx::grid_dep_wait();
+
     const int lanes_per_pixel = a.C / 8;   // 8 for C = 64
     const long long gt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const long long m = gt / lanes_per_pixel;
@@ -309,6 +318,8 @@ philox_normal_kernel(float* out, long long n, unsigned long long seed, unsigned 
 // ------------------------------------------------------------------------------------------ posterior
 __global__ void __launch_bounds__(256)
 posterior_step_kernel(const PosteriorArgs a) {
+    ptx::grid_dep_launch();     // PDL (ptx.cuh): the successor may be scheduled; then wait for the predecessor grid and its memory
+    ptx::grid_dep_wait();
     const long long i4 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
     if (i4 >= a.n) return;
     const int t = a.ctl->step;
@@ -347,7 +358,10 @@ posterior_step_kernel(const PosteriorArgs a) {
     if (a.x0_out != nullptr) *reinterpret_cast<float4*>(a.x0_out + i4) = make_float4(x0s[0], x0s[1], x0s[2], x0s[3]);
 }
 
-__global__ void step_advance_kernel(SampleCtl* ctl, int delta) { ctl->step += delta; }
+__global__ void step_advance_kernel(SampleCtl* ctl, int delta) {
+    ptx::grid_dep_wait();          // the step's kernels read ctl->step: advance it only after they are done
+    ctl->step += delta;
+}
 
 // ------------------------------------------------------------------------------------------ DDRM step (denoising operator)
 // efficient_generalized_steps (/root/reference/src/functions/denoising.py:49-104) for H = Denoising (svd_replacement.py:148-168:
@@ -441,8 +455,7 @@ cudaError_t stem_conv_run(const StemConvArgs& a, cudaStream_t s) {
             if (e != cudaSuccess) return e;
             max_set1 = smem1;
         }
-        stem_conv_kernel<<<a.B * (a.H / STEM_ROWS), STEM_THREADS, smem1, s>>>(a);
-        return cudaGetLastError();
+        return launch_pdl(stem_conv_kernel, dim3(a.B * (a.H / STEM_ROWS)), dim3(STEM_THREADS), smem1, s, a);
     }
     const int KP = (K + 15) & ~15;                       // <= 112: seven m16n8k16 steps
     const int x_elems = (a.Cin * (STEM_ROWS + 2 * pad) * STEM2_PITCH + 7) & ~7;
@@ -454,8 +467,7 @@ cudaError_t stem_conv_run(const StemConvArgs& a, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         max_set = smem;
     }
-    stem_conv_mma_kernel<<<a.B * (a.H / STEM2_CTA_ROWS), STEM2_THREADS, smem, s>>>(a, KP);
-    return cudaGetLastError();
+    return launch_pdl(stem_conv_mma_kernel, dim3(a.B * (a.H / STEM2_CTA_ROWS)), dim3(STEM2_THREADS), smem, s, a, KP);
 }
 
 cudaError_t ddrm_step_run(const DdrmArgs& a, cudaStream_t s) {
@@ -469,15 +481,13 @@ cudaError_t head_conv1x1_run(const HeadConvArgs& a, cudaStream_t s) {
     if (a.C % 8 != 0 || a.C > 256 || (32 % (a.C / 8)) != 0) return cudaErrorInvalidValue;
     const long long threads = static_cast<long long>(a.M) * (a.C / 8);
     const int grid = static_cast<int>((threads + 255) / 256);
-    head_conv1x1_kernel<<<grid, 256, 0, s>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(head_conv1x1_kernel, dim3(grid), dim3(256), 0, s, a);
 }
 
 cudaError_t posterior_step_run(const PosteriorArgs& a, cudaStream_t s) {
     if (a.n % 4 != 0 || a.tile_elems % 4 != 0) return cudaErrorInvalidValue;
     const int grid = static_cast<int>((a.n / 4 + 255) / 256);
-    posterior_step_kernel<<<grid, 256, 0, s>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(posterior_step_kernel, dim3(grid), dim3(256), 0, s, a);
 }
 
 cudaError_t philox_normal_run(float* out, long long n, unsigned long long seed, unsigned long long tile_offset,
@@ -489,8 +499,7 @@ cudaError_t philox_normal_run(float* out, long long n, unsigned long long seed, 
 }
 
 cudaError_t step_advance_run(SampleCtl* ctl, int delta, cudaStream_t s) {
-    step_advance_kernel<<<1, 1, 0, s>>>(ctl, delta);
-    return cudaGetLastError();
+    return launch_pdl(step_advance_kernel, dim3(1), dim3(1), 0, s, ctl, delta);
 }
 
 }  // namespace hd

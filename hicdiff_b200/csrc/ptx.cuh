@@ -35,6 +35,15 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization (kernels.h::launch_pdl) may start while its
+// predecessor in the stream is still draining: grid_dep_launch() lets OUR successor be scheduled as soon as every CTA of this grid
+// has started, grid_dep_wait() blocks until the predecessor grid has completed and its memory is visible.  Everything before the
+// wait may only touch data that no kernel of the same graph writes (constants, weights, this CTA's own shared memory / TMEM).
+// Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

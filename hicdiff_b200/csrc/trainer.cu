@@ -373,6 +373,7 @@ int hd_trainer_step(hd_trainer* t, const float* x_t, const float* cond, const fl
     T_TRY(cudaMemcpyAsync(t->time, time, t->B * 4, cudaMemcpyDeviceToDevice, s));
     T_TRY(cudaMemcpyAsync(t->weight, weight, t->B * 4, cudaMemcpyDeviceToDevice, s));
     t->loss_kind = loss_type;
+    PdlScope pdl;     // the forward's kernels (conv_gemm, GroupNorm, attention ...) become programmatic dependents inside the step
     static const bool use_graph = [] { const char* v = getenv("HD_TRAIN_GRAPH"); return !(v && v[0] == '0'); }();
     if (use_graph && t->graph[loss_type] == nullptr && t->eager_steps[loss_type] >= 1) {
         // capture (nothing executes) on the private stream: the caller's stream may be the legacy default stream
