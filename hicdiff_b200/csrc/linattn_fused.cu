@@ -437,7 +437,7 @@ struct OutCfg {
     static constexpr uint32_t MB_SPAN = C * 128;                 // one 64-wide K span of Mb [C rows]
     static constexpr uint32_t MB_BYTES = 2 * MB_SPAN;
     static constexpr uint32_t A2_BYTES = 2 * SPAN_BYTES;
-    static constexpr uint32_t SMALL_BYTES = 512 + 2 * 4 * C + 128;
+    static constexpr uint32_t SMALL_BYTES = 512 + 2 * 4 * C + 128 + 1024;    // rowsum, bo, g2, barriers, [2][128] half-row exchange
     static constexpr int SMEM_BYTES = WQ_BYTES + 2 * X_BYTES + MB_BYTES + A2_BYTES + SMALL_BYTES + 1024;
     static constexpr int CTAS_PER_SM = C == 64 ? 2 : 1;
     static constexpr int X_EMPTY_ARRIVALS = C == 64 ? 4 : 8;     // storing warps per tile
@@ -459,7 +459,8 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     float* s_sq = reinterpret_cast<float*>(sA2 + Cf::A2_BYTES);
     float* s_bo = s_sq + 128;
     float* s_g2 = s_bo + C;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_g2 + C);
+    float* s_xch = s_g2 + C;                         // [2][128]: the two column halves of a row exchange their LayerNorm partials
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_xch + 256);
     uint64_t* wq_bar = bars;
     uint64_t* x_full = bars + 1;                     // [2]
     uint64_t* x_empty = bars + 3;                    // [2]
@@ -590,18 +591,21 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 ptx::tmem_ld_wait();
                 float f[32];
                 float mx = -INFINITY;
+                // q = rstd * (acc - mean * rowsum) and exp(q - max) = exp2(q * log2e - max'): one FMA per element with
+                // al = rstd * log2e, cl = mean * al (softmax is invariant to the common shift, the max is taken after scaling)
+                const float al = rstd * 1.4426950408889634f, cl = mean * al;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const float4 s4 = *reinterpret_cast<const float4*>(s_sq + h * 32 + j);
-                    f[j] = rstd * (__uint_as_float(v[j]) - mean * s4.x);
-                    f[j + 1] = rstd * (__uint_as_float(v[j + 1]) - mean * s4.y);
-                    f[j + 2] = rstd * (__uint_as_float(v[j + 2]) - mean * s4.z);
-                    f[j + 3] = rstd * (__uint_as_float(v[j + 3]) - mean * s4.w);
+                    f[j] = fmaf(__uint_as_float(v[j]), al, -(cl * s4.x));
+                    f[j + 1] = fmaf(__uint_as_float(v[j + 1]), al, -(cl * s4.y));
+                    f[j + 2] = fmaf(__uint_as_float(v[j + 2]), al, -(cl * s4.z));
+                    f[j + 3] = fmaf(__uint_as_float(v[j + 3]), al, -(cl * s4.w));
                     mx = fmaxf(fmaxf(fmaxf(mx, f[j]), fmaxf(f[j + 1], f[j + 2])), f[j + 3]);
                 }
                 float ssum = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { f[j] = ptx::ex2((f[j] - mx) * 1.4426950408889634f); ssum += f[j]; }
+                for (int j = 0; j < 32; ++j) { f[j] = ptx::ex2(f[j] - mx); ssum += f[j]; }
                 const float inv = 1.0f / ssum;
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
@@ -619,38 +623,42 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 
             ptx::mbar_wait(y_full, it & 1u);
             ptx::tc_fence_after();
-            // LayerNorm over the C output channels of this pixel: statistics from two cheap passes over the whole TMEM row
+            // LayerNorm over the C output channels of this pixel.  This thread owns the channels [hf * C/2, (hf + 1) * C/2) of row r:
+            // one TMEM read into registers (+ bias), then the two halves of the row exchange their partial sums through shared
+            // memory (mean first, then the centred sum of squares: two-pass accuracy without reading the other half).
+            constexpr int HALF = C / 2;
+            float y[HALF];
             float sum = 0.f;
-#pragma unroll 1
-            for (int c32 = 0; c32 < C / 32; ++c32) {
-                uint32_t v[32];
-                ptx::tmem_ld32(tlane + COL_Y + c32 * 32, v);
-                ptx::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sum += __uint_as_float(v[j]) + s_bo[c32 * 32 + j];
-            }
-            const float ymean = sum * (1.0f / C);
-            float ss = 0.f;
-#pragma unroll 1
-            for (int c32 = 0; c32 < C / 32; ++c32) {
+            for (int cc = 0; cc < HALF / 32; ++cc) {
+                const int c32 = hf * (HALF / 32) + cc;
                 uint32_t v[32];
                 ptx::tmem_ld32(tlane + COL_Y + c32 * 32, v);
                 ptx::tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float d = __uint_as_float(v[j]) + s_bo[c32 * 32 + j] - ymean;
-                    ss = fmaf(d, d, ss);
+                    y[cc * 32 + j] = __uint_as_float(v[j]) + s_bo[c32 * 32 + j];
+                    sum += y[cc * 32 + j];
                 }
             }
-            const float yrstd = rsqrtf(ss * (1.0f / C) + a.eps);
-            // this warp's half of the channels: normalise, + x, and write the result IN PLACE over the x tile (same row, same
-            // swizzled chunk), which then doubles as the TMA-store staging buffer
-#pragma unroll 1
-            for (int cc = 0; cc < C / 64; ++cc) {
-                const int c32 = hf * (C / 64) + cc;
-                uint32_t v[32];
-                ptx::tmem_ld32(tlane + COL_Y + c32 * 32, v);
-                ptx::tmem_ld_wait();
+            s_xch[hf * 128 + r] = sum;
+            named_bar_sync(2 + q, 64);
+            const float ymean = (sum + s_xch[(hf ^ 1) * 128 + r]) * (1.0f / C);
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) {
+                y[j] -= ymean;
+                ss = fmaf(y[j], y[j], ss);
+            }
+            named_bar_sync(2 + q, 64);                   // the partner has read this row's sum: the slot may be reused
+            s_xch[hf * 128 + r] = ss;
+            named_bar_sync(2 + q, 64);
+            const float yrstd = rsqrtf((ss + s_xch[(hf ^ 1) * 128 + r]) * (1.0f / C) + a.eps);
+            // normalise, + x, and write the result IN PLACE over the x tile (same row, same swizzled chunk), which then doubles
+            // as the TMA-store staging buffer
+#pragma unroll
+            for (int cc = 0; cc < HALF / 32; ++cc) {
+                const int c32 = hf * (HALF / 32) + cc;
                 const int sp = c32 >> 1;
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
@@ -662,7 +670,7 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int c = c32 * 32 + jj * 8 + j;
-                        o[j] = (__uint_as_float(v[jj * 8 + j]) + s_bo[c] - ymean) * yrstd * s_g2[c] + xr[j];
+                        o[j] = fmaf(y[cc * 32 + jj * 8 + j] * yrstd, s_g2[c], xr[j]);
                     }
                     uint4 u;
                     u.x = ptx::pack_bf16x2(o[0], o[1]);

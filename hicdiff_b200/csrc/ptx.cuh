@@ -66,16 +66,20 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                  : "memory");
 }
 
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or ~10 ms pass, whichever is first, so a
+// waiting warp costs no issue slots.  Without the hint the default window is short and the retry loop below spun: ncu's source page
+// attributed 18 - 21 % of ALL executed instructions of the fused attention kernels to it (profiles/r02_notes.md 9) -- issue slots taken
+// from the epilogue warps that share the scheduler.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, P;\n\t"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
@@ -86,13 +90,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     uint64_t t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3ffu) == 0) {
-            uint64_t t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 4000000000ull) __trap();
-        }
+    while (!mbar_try_wait(bar, parity)) {          // each retry has been parked for up to the hint: iterations are rare
+        uint64_t t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ull) __trap();
     }
 }
 
