@@ -223,7 +223,7 @@ struct LinAttnFusedDesc {
 struct LinAttnFusedLaunch {
     LinAttnFusedDesc d;
     CUtensorMap tmX, tmXk, tmW, tmM, tmY;
-    int parts, tiles_per_unit, num_tiles, out_grid;
+    int parts, tiles_per_unit, num_tiles, out_grid, num_sms;
 };
 cudaError_t linattn_prep_run(const float* wqkv, const float* g1, bf16* out, float* rowsum, float* kshift,
                              int* max_bound_bits, int C, cudaStream_t s);

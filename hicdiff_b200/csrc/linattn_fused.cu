@@ -22,6 +22,7 @@
 //       LayerNorm fix-up + softmax over each head's 32 columns in registers -> bf16 A operand -> Y[px, co] = Q Mb^T
 //       (tcgen05) -> + bias, LayerNorm g2, + x (still in shared memory) -> TMA store.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -40,39 +41,84 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // byte offset of 16-byte chunk c of row r inside a K-major, 128B-swizzled tile with 128-byte rows
 __device__ __forceinline__ uint32_t sw_off(int r, int c) { return static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(c ^ (r & 7)) << 4); }
 
-__device__ __forceinline__ void unpack8(const uint4 u, float (&v)[8]) {
-    float2 t;
-    t = ptx::unpack_bf16x2(u.x); v[0] = t.x; v[1] = t.y;
-    t = ptx::unpack_bf16x2(u.y); v[2] = t.x; v[3] = t.y;
-    t = ptx::unpack_bf16x2(u.z); v[4] = t.x; v[5] = t.y;
-    t = ptx::unpack_bf16x2(u.w); v[6] = t.x; v[7] = t.y;
+// LayerNorm statistics of the KV_PX = 64 pixels of a kv tile, spread over NT epilogue threads: NT / 64 consecutive lanes share a
+// pixel, each keeps its share of the row's channels in registers (two-pass), the partial sums meet in xor-shuffles (a + b == b + a:
+// every lane of a pixel ends with the same bits).  The one-thread-per-pixel form left 3/4 (7/8) of the epilogue threads idle in
+// front of the tile's named barrier for ~700 clk of dependent adds.  Writes rstd * mean, rstd, rstd * log2(e) of pixel p.
+template <int C, int NT, uint32_t SPAN_STRIDE>
+__device__ __forceinline__ void tile_stats(const uint8_t* sx, int te, float eps, float* s_mu, float* s_rstd, float* s_rl) {
+    constexpr int TPP = NT / 64;                 // threads per pixel: 4 or 8
+    constexpr int NCH = (C / 8) / TPP;           // 16-byte chunks per thread
+    static_assert(NCH >= 1, "tile_stats: more threads than chunks");
+    const int p = te / TPP, sub = te % TPP;
+    ptx::f32x2 xh[NCH * 4];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int c = sub + i * TPP;             // chunk of the row: span c >> 3, chunk c & 7 inside it
+        const uint4 u = *reinterpret_cast<const uint4*>(sx + (c >> 3) * SPAN_STRIDE + sw_off(p, c & 7));
+        xh[i * 4] = ptx::bf16x2_to_f32x2(u.x); xh[i * 4 + 1] = ptx::bf16x2_to_f32x2(u.y);
+        xh[i * 4 + 2] = ptx::bf16x2_to_f32x2(u.z); xh[i * 4 + 3] = ptx::bf16x2_to_f32x2(u.w);
+    }
+    ptx::f32x2 s0 = xh[0], s1 = xh[1];
+#pragma unroll
+    for (int i = 2; i < NCH * 4; i += 2) { s0 = ptx::add2(s0, xh[i]); s1 = ptx::add2(s1, xh[i + 1]); }
+    s0 = ptx::add2(s0, s1);
+    float sum = ptx::lo(s0) + ptx::hi(s0);
+#pragma unroll
+    for (int off = 1; off < TPP; off <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const float mean = sum * (1.0f / C);
+    const ptx::f32x2 nm = ptx::dup2(-mean);
+    ptx::f32x2 q0 = ptx::mk2(0.f, 0.f), q1 = q0;
+#pragma unroll
+    for (int i = 0; i < NCH * 4; i += 2) {
+        const ptx::f32x2 d0 = ptx::add2(xh[i], nm), d1 = ptx::add2(xh[i + 1], nm);
+        q0 = ptx::fma2(d0, d0, q0);
+        q1 = ptx::fma2(d1, d1, q1);
+    }
+    q0 = ptx::add2(q0, q1);
+    float ss = ptx::lo(q0) + ptx::hi(q0);
+#pragma unroll
+    for (int off = 1; off < TPP; off <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    if (sub == 0) {
+        const float rstd = rsqrtf(ss * (1.0f / C) + eps);
+        s_mu[p] = rstd * mean;               // W LN(x) = rstd * (W'x) - (rstd * mean) * rowsum(W')
+        s_rstd[p] = rstd;
+        s_rl[p] = rstd * 1.4426950408889634f;
+    }
 }
 
-// mean / rstd over the C channels of row r of a [128 x C] swizzled x tile (two passes over shared memory)
-template <int C, uint32_t SPAN_STRIDE = SPAN_BYTES>
-__device__ __forceinline__ void row_stats(const uint8_t* sx, int r, float eps, float& mean, float& rstd) {
-    float s = 0.f;
+// Eight pixels (one 16-byte shared-memory chunk) of the kv epilogue, packed fp32 (ptx.cuh): v = accumulator registers OFF .. OFF + 7.
+//   K path: p = exp2(rl * acc - (mu * sk + shift)), sk / shift pre-multiplied by log2(e); NSK / NSHIFT are their negations
+//           (fma(mu, -sk, -shift) == -(fma(mu, sk, shift)) bit for bit); ssum2 accumulates the unrounded p
+//   V path: v = rstd * acc - mu * sv; NSV = -sv
+template <int OFF, int N>
+__device__ __forceinline__ uint4 k_chunk8(const uint32_t (&v)[N], const float* mu8, const float* rl8, ptx::f32x2 NSK,
+                                          ptx::f32x2 NSHIFT, ptx::f32x2& ssum2) {
+    const float4 ma = *reinterpret_cast<const float4*>(mu8), mb = *reinterpret_cast<const float4*>(mu8 + 4);
+    const float4 la = *reinterpret_cast<const float4*>(rl8), lb = *reinterpret_cast<const float4*>(rl8 + 4);
+    const ptx::f32x2 M[4] = {ptx::mk2(ma.x, ma.y), ptx::mk2(ma.z, ma.w), ptx::mk2(mb.x, mb.y), ptx::mk2(mb.z, mb.w)};
+    const ptx::f32x2 L[4] = {ptx::mk2(la.x, la.y), ptx::mk2(la.z, la.w), ptx::mk2(lb.x, lb.y), ptx::mk2(lb.z, lb.w)};
+    uint32_t o[4];
 #pragma unroll
-    for (int sp = 0; sp < C / 64; ++sp)
+    for (int e = 0; e < 4; ++e) {
+        const ptx::f32x2 arg = ptx::fma2(L[e], ptx::mk2(v[OFF + 2 * e], v[OFF + 2 * e + 1]), ptx::fma2(M[e], NSK, NSHIFT));
+        const ptx::f32x2 pp = ptx::mk2(ptx::ex2(ptx::lo(arg)), ptx::ex2(ptx::hi(arg)));
+        ssum2 = ptx::add2(ssum2, pp);
+        o[e] = ptx::pack_bf16x2(pp);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+template <int OFF, int N>
+__device__ __forceinline__ uint4 v_chunk8(const uint32_t (&v)[N], const float* mu8, const float* rs8, ptx::f32x2 NSV) {
+    const float4 ma = *reinterpret_cast<const float4*>(mu8), mb = *reinterpret_cast<const float4*>(mu8 + 4);
+    const float4 ra = *reinterpret_cast<const float4*>(rs8), rb = *reinterpret_cast<const float4*>(rs8 + 4);
+    const ptx::f32x2 M[4] = {ptx::mk2(ma.x, ma.y), ptx::mk2(ma.z, ma.w), ptx::mk2(mb.x, mb.y), ptx::mk2(mb.z, mb.w)};
+    const ptx::f32x2 R[4] = {ptx::mk2(ra.x, ra.y), ptx::mk2(ra.z, ra.w), ptx::mk2(rb.x, rb.y), ptx::mk2(rb.z, rb.w)};
+    uint32_t o[4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float v[8];
-            unpack8(*reinterpret_cast<const uint4*>(sx + sp * SPAN_STRIDE + sw_off(r, c)), v);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s += v[j];
-        }
-    mean = s * (1.0f / C);
-    float ss = 0.f;
-#pragma unroll
-    for (int sp = 0; sp < C / 64; ++sp)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float v[8];
-            unpack8(*reinterpret_cast<const uint4*>(sx + sp * SPAN_STRIDE + sw_off(r, c)), v);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ss = fmaf(v[j] - mean, v[j] - mean, ss);
-        }
-    rstd = rsqrtf(ss * (1.0f / C) + eps);
+    for (int e = 0; e < 4; ++e)
+        o[e] = ptx::pack_bf16x2(ptx::fma2(R[e], ptx::mk2(v[OFF + 2 * e], v[OFF + 2 * e + 1]), ptx::mul2(M[e], NSV)));
+    return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // ------------------------------------------------------------------------------------------------ weight prep
@@ -129,7 +175,7 @@ struct KvCfg {
     static constexpr uint32_t XSPAN_BYTES = KV_PX * 128;             // one 64-channel span of a 64-pixel x tile
     static constexpr uint32_t X_BYTES = SPANS * XSPAN_BYTES;
     static constexpr uint32_t PV_BYTES = SPAN_BYTES;                 // [128 rows][64 px]
-    static constexpr uint32_t SMALL_BYTES = 3 * 256 + 5 * 512 + 128;
+    static constexpr uint32_t SMALL_BYTES = 3 * 512 + 5 * 512 + 128;
     static constexpr int SMEM_BYTES = 2 * W_BYTES + 2 * X_BYTES + 2 * PV_BYTES + SMALL_BYTES + 1024;
     static constexpr int CTAS_PER_SM = C == 64 ? 2 : 1;
 };
@@ -147,10 +193,10 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint8_t* sX = sWv + Cf::W_BYTES;                 // 2 stages
     uint8_t* sP = sX + 2 * Cf::X_BYTES;
     uint8_t* sV = sP + Cf::PV_BYTES;
-    float* s_mu = reinterpret_cast<float*>(sV + Cf::PV_BYTES);   // [64] rstd * mean per pixel
-    float* s_rstd = s_mu + KV_PX;                    // [64]
-    float* s_rl = s_rstd + KV_PX;                    // [64] rstd * log2(e): the K path's multiplier, so an exponent is two FMAs
-    float* s_sk = s_rl + KV_PX;                      // [128]
+    float* s_mu = reinterpret_cast<float*>(sV + Cf::PV_BYTES);   // [2][64] rstd * mean per pixel (double-buffered by tile parity)
+    float* s_rstd = s_mu + 2 * KV_PX;                // [2][64]
+    float* s_rl = s_rstd + 2 * KV_PX;                // [2][64] rstd * log2(e): the K path's multiplier, so an exponent is two FMAs
+    float* s_sk = s_rl + 2 * KV_PX;                  // [128]
     float* s_sv = s_sk + 128;
     float* s_shift = s_sv + 128;
     float* s_S = s_shift + 128;                      // [2][128]
@@ -268,20 +314,20 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
         named_bar_sync(1, 256);
         constexpr float LOG2E = 1.4426950408889634f;
-        const float sk_r = s_sk[r] * LOG2E, sv_r = s_sv[r], shift_r = s_shift[r] * LOG2E;   // exp(k) = exp2(k * log2 e)
+        // exp(k) = exp2(k * log2 e); negated per-row constants for the packed forms (k_chunk8 / v_chunk8)
+        const ptx::f32x2 NSK = ptx::dup2(-(s_sk[r] * LOG2E)), NSHIFT = ptx::dup2(-(s_shift[r] * LOG2E)), NSV = ptx::dup2(-s_sv[r]);
         const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const int px0 = hcol * 32;
-        float ssum = 0.f;
+        ptx::f32x2 ssum2 = ptx::mk2(0.f, 0.f);
         for (int t = 0; t < T; ++t) {
             const int st = t & 1;
             ptx::mbar_wait(&x_full[st], (t >> 1) & 1u);          // x tile visible to this thread
-            if (te < KV_PX) {                                     // per-pixel LayerNorm statistics while the MMAs run
-                float mean, rstd;
-                row_stats<C, Cf::XSPAN_BYTES>(sX + st * Cf::X_BYTES, te, a.eps, mean, rstd);
-                s_mu[te] = rstd * mean;          // W LN(x) = rstd * (W'x) - (rstd * mean) * rowsum(W')
-                s_rstd[te] = rstd;
-                s_rl[te] = rstd * 1.4426950408889634f;
-            }
+            // per-pixel LayerNorm statistics while the MMAs run; double-buffered by tile parity (a fast warp writes tile t + 1's
+            // while a slow one still reads tile t's)
+            float* mu_t = s_mu + st * KV_PX;
+            float* rs_t = s_rstd + st * KV_PX;
+            float* rl_t = s_rl + st * KV_PX;
+            tile_stats<C, 256, Cf::XSPAN_BYTES>(sX + st * Cf::X_BYTES, te, a.eps, mu_t, rs_t, rl_t);
             ptx::mbar_wait(d_full, t & 1u);                       // K^T / V^T of tile t ready (and P / V of tile t-1 consumed)
             ptx::tc_fence_after();
             named_bar_sync(1, 256);
@@ -289,51 +335,23 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             uint32_t v[32];
             ptx::tmem_ld32(tlane + COL_K + px0, v);
             ptx::tmem_ld_wait();
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const float4 ma = *reinterpret_cast<const float4*>(s_mu + px0 + jj * 8);
-                const float4 mb = *reinterpret_cast<const float4*>(s_mu + px0 + jj * 8 + 4);
-                const float4 ra = *reinterpret_cast<const float4*>(s_rl + px0 + jj * 8);
-                const float4 rb = *reinterpret_cast<const float4*>(s_rl + px0 + jj * 8 + 4);
-                const float mu[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
-                const float rs[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};      // rstd * log2(e)
-                uint32_t pk[4];
-#pragma unroll
-                for (int e2 = 0; e2 < 4; ++e2) {
-                    const int j = e2 * 2;
-                    const float p0 = ptx::ex2(fmaf(rs[j], __uint_as_float(v[jj * 8 + j]), -fmaf(mu[j], sk_r, shift_r)));
-                    const float p1 = ptx::ex2(fmaf(rs[j + 1], __uint_as_float(v[jj * 8 + j + 1]), -fmaf(mu[j + 1], sk_r, shift_r)));
-                    // the denominator sums the unrounded p: the bf16 rounding of the MMA operand is unbiased, over n >= 1024 pixels
-                    // the two sums agree to ~1e-5 (the unpack round trip was 7 % of the kernel's instructions)
-                    ssum += p0 + p1;
-                    pk[e2] = ptx::pack_bf16x2(p0, p1);
-                }
-                *reinterpret_cast<uint4*>(sP + sw_off(r, hcol * 4 + jj)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
+            // the denominator sums the unrounded p: the bf16 rounding of the MMA operand is unbiased, over n >= 1024 pixels
+            // the two sums agree to ~1e-5
+            *reinterpret_cast<uint4*>(sP + sw_off(r, hcol * 4 + 0)) = k_chunk8<0>(v, mu_t + px0, rl_t + px0, NSK, NSHIFT, ssum2);
+            *reinterpret_cast<uint4*>(sP + sw_off(r, hcol * 4 + 1)) = k_chunk8<8>(v, mu_t + px0 + 8, rl_t + px0 + 8, NSK, NSHIFT, ssum2);
+            *reinterpret_cast<uint4*>(sP + sw_off(r, hcol * 4 + 2)) = k_chunk8<16>(v, mu_t + px0 + 16, rl_t + px0 + 16, NSK, NSHIFT, ssum2);
+            *reinterpret_cast<uint4*>(sP + sw_off(r, hcol * 4 + 3)) = k_chunk8<24>(v, mu_t + px0 + 24, rl_t + px0 + 24, NSK, NSHIFT, ssum2);
             ptx::tmem_ld32(tlane + COL_V + px0, v);
             ptx::tmem_ld_wait();
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const float4 ma = *reinterpret_cast<const float4*>(s_mu + px0 + jj * 8);
-                const float4 mb = *reinterpret_cast<const float4*>(s_mu + px0 + jj * 8 + 4);
-                const float4 ra = *reinterpret_cast<const float4*>(s_rstd + px0 + jj * 8);
-                const float4 rb = *reinterpret_cast<const float4*>(s_rstd + px0 + jj * 8 + 4);
-                const float mu[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
-                const float rs[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-                uint32_t pk[4];
-#pragma unroll
-                for (int e2 = 0; e2 < 4; ++e2) {
-                    const int j = e2 * 2;
-                    const float v0 = fmaf(rs[j], __uint_as_float(v[jj * 8 + j]), -mu[j] * sv_r);
-                    const float v1 = fmaf(rs[j + 1], __uint_as_float(v[jj * 8 + j + 1]), -mu[j + 1] * sv_r);
-                    pk[e2] = ptx::pack_bf16x2(v0, v1);
-                }
-                *reinterpret_cast<uint4*>(sV + sw_off(r, hcol * 4 + jj)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
+            *reinterpret_cast<uint4*>(sV + sw_off(r, hcol * 4 + 0)) = v_chunk8<0>(v, mu_t + px0, rs_t + px0, NSV);
+            *reinterpret_cast<uint4*>(sV + sw_off(r, hcol * 4 + 1)) = v_chunk8<8>(v, mu_t + px0 + 8, rs_t + px0 + 8, NSV);
+            *reinterpret_cast<uint4*>(sV + sw_off(r, hcol * 4 + 2)) = v_chunk8<16>(v, mu_t + px0 + 16, rs_t + px0 + 16, NSV);
+            *reinterpret_cast<uint4*>(sV + sw_off(r, hcol * 4 + 3)) = v_chunk8<24>(v, mu_t + px0 + 24, rs_t + px0 + 24, NSV);
             ptx::tc_fence_before();
             ptx::fence_proxy_async_smem();
             ptx::mbar_arrive(pv_ready);
         }
+        const float ssum = ptx::lo(ssum2) + ptx::hi(ssum2);
         s_S[hcol * 128 + r] = ssum;
         named_bar_sync(1, 256);
         if (hcol == 0) {
@@ -355,18 +373,273 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     if (warp == 0) ptx::tmem_dealloc(tmem_base, 256);
 }
 
+// ------------------------------------------------------------------------------------------------ kernel 1, pipelined form
+// linattn_kv2_kernel: the same math as linattn_kv_kernel, restructured so that the MMAs of tile g + 1 run while the epilogue warps
+// work on tile g: K^T / V^T accumulators and the P / V shared-memory tiles are double-buffered, the CTA is
+// persistent over its units (image, pixel range) -- weights and TMEM are set up once -- and sixteen epilogue warps (TMEM lane
+// quarter x 16-pixel column quarter) give the SM the warps that two co-resident CTAs of the first form provided.
+//   TMEM (512 columns, one CTA per SM): [K0 | V0 | K1 | V1] 4 x 64, ctx 128 at column 256.
+//   barriers: x_full / x_empty[3] (TMA <-> MMA + statistics), kv_full / kv_empty[2] (accumulators), pv_full / pv_empty[2] (P / V
+//   tiles), ctx_full / ctx_empty (context accumulator of one unit).  g counts tiles across units (buffer = g & 1, x stage = g % 3).
+template <int C>
+struct Kv2Cfg {
+    static constexpr int SPANS = C / 64;
+    static constexpr uint32_t W_BYTES = SPANS * SPAN_BYTES;
+    static constexpr uint32_t XSPAN_BYTES = KV_PX * 128;
+    static constexpr uint32_t X_BYTES = SPANS * XSPAN_BYTES;
+    static constexpr int X_STAGES = 3;
+    static constexpr uint32_t PV_BYTES = SPAN_BYTES;                 // [128 rows][64 px]
+    static constexpr uint32_t SMALL_BYTES = 2 * 3 * 256 + 3 * 512 + 4 * 512 + 256;
+    static constexpr int SMEM_BYTES = 2 * W_BYTES + X_STAGES * X_BYTES + 4 * PV_BYTES + SMALL_BYTES + 1024;
+};
+constexpr int KV2_EPI_WARPS = 16;
+constexpr int KV2_THREADS = 64 + KV2_EPI_WARPS * 32;      // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
+
+template <int C>
+__global__ void __launch_bounds__(KV2_THREADS, 1)
+linattn_kv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const KvArgs a, const int units) {
+    using Cf = Kv2Cfg<C>;
+    constexpr int SPANS = Cf::SPANS;
+    constexpr int XS = Cf::X_STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sWk = smem;
+    uint8_t* sWv = sWk + Cf::W_BYTES;
+    uint8_t* sX = sWv + Cf::W_BYTES;                 // X_STAGES stages
+    uint8_t* sP = sX + XS * Cf::X_BYTES;             // [2]
+    uint8_t* sV = sP + 2 * Cf::PV_BYTES;             // [2]
+    float* s_mu = reinterpret_cast<float*>(sV + 2 * Cf::PV_BYTES);   // [2][64] rstd * mean per pixel (double-buffered by tile parity)
+    float* s_rstd = s_mu + 2 * KV_PX;                // [2][64]
+    float* s_rl = s_rstd + 2 * KV_PX;                // [2][64] rstd * log2(e)
+    float* s_sk = s_rl + 2 * KV_PX;                  // [128]
+    float* s_sv = s_sk + 128;
+    float* s_shift = s_sv + 128;
+    float* s_S = s_shift + 128;                      // [4][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_S + 512);
+    uint64_t* w_bar = bars;
+    uint64_t* x_full = bars + 1;                     // [3]
+    uint64_t* x_empty = bars + 4;                    // [3]
+    uint64_t* kv_full = bars + 7;                    // [2]
+    uint64_t* kv_empty = bars + 9;                   // [2]
+    uint64_t* pv_full = bars + 11;                   // [2]
+    uint64_t* pv_empty = bars + 13;                  // [2]
+    uint64_t* ctx_full = bars + 15;
+    uint64_t* ctx_empty = bars + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp == 0) {
+        if (lane == 0) { ptx::prefetch_tmap(&tmX); ptx::prefetch_tmap(&tmW); }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    } else if (warp == 1 && lane == 0) {
+        ptx::mbar_init(w_bar, 1);
+        for (int i = 0; i < XS; ++i) { ptx::mbar_init(&x_full[i], 1); ptx::mbar_init(&x_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&kv_full[i], 1);
+            ptx::mbar_init(&kv_empty[i], KV2_EPI_WARPS);
+            ptx::mbar_init(&pv_full[i], KV2_EPI_WARPS);
+            ptx::mbar_init(&pv_empty[i], 1);
+        }
+        ptx::mbar_init(ctx_full, 1);
+        ptx::mbar_init(ctx_empty, 4);
+        ptx::fence_mbar_init();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_launch();
+    constexpr uint32_t COL_CTX = 256;
+
+    const int T = a.tiles_per_unit;                  // 64-pixel tiles per unit
+    // units of this CTA: blockIdx.x, + gridDim.x, ...
+    if (warp == 0) {
+        if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(w_bar, 2 * Cf::W_BYTES);
+            for (int sp = 0; sp < SPANS; ++sp) {
+                ptx::tma_load_2d(sWk + sp * SPAN_BYTES, &tmW, w_bar, sp * 64, HD);
+                ptx::tma_load_2d(sWv + sp * SPAN_BYTES, &tmW, w_bar, sp * 64, 2 * HD);
+            }
+        }
+        __syncwarp();
+        ptx::grid_dep_wait();
+        int g = 0;
+        for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+            const int b = unit / a.parts;
+            const int part = unit - b * a.parts;
+            const int m0 = b * a.n + part * T * KV_PX;
+            for (int t = 0; t < T; ++t, ++g) {
+                const int st = g % XS;
+                ptx::mbar_wait(&x_empty[st], ((g / XS) & 1u) ^ 1u);
+                if (ptx::elect_one()) {
+                    ptx::mbar_arrive_expect_tx(&x_full[st], Cf::X_BYTES);
+                    for (int sp = 0; sp < SPANS; ++sp)
+                        ptx::tma_load_2d(sX + st * Cf::X_BYTES + sp * Cf::XSPAN_BYTES, &tmX, &x_full[st], sp * 64, m0 + t * KV_PX);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc_kv = ptx::make_idesc_bf16(128, KV_PX);
+        constexpr uint32_t idesc_ctx = ptx::make_idesc_bf16(128, 128);
+        const uint64_t dWk = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sWk));
+        const uint64_t dWv = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sWv));
+        const uint64_t dX = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sX));
+        const uint64_t dP = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sP));
+        const uint64_t dV = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sV));
+        ptx::mbar_wait(w_bar, 0);
+        int g = 0, u = 0;
+        auto issue_ctx = [&](int gp, bool first, bool last) {       // ctx += P V^T of tile gp (its P / V are in buffer gp & 1)
+            const int bb = gp & 1;
+            ptx::mbar_wait(&pv_full[bb], (gp >> 1) & 1u);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint64_t off = static_cast<uint64_t>((bb * Cf::PV_BYTES) >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    ptx::umma_bf16(tmem_base + COL_CTX, dP + off + 2u * k, dV + off + 2u * k, idesc_ctx, (!first || k != 0) ? 1u : 0u);
+                ptx::umma_commit(&pv_empty[bb]);
+                if (last) ptx::umma_commit(ctx_full);
+            }
+            __syncwarp();
+        };
+        for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++u) {
+            for (int t = 0; t < T; ++t, ++g) {
+                const int st = g % XS, bb = g & 1;
+                ptx::mbar_wait(&x_full[st], (g / XS) & 1u);
+                ptx::mbar_wait(&kv_empty[bb], ((g >> 1) & 1u) ^ 1u);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint64_t xoff = static_cast<uint64_t>((st * Cf::X_BYTES) >> 4);
+                    const uint32_t colk = tmem_base + bb * 128, colv = colk + 64;
+#pragma unroll
+                    for (int sp = 0; sp < SPANS; ++sp)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t offw = static_cast<uint64_t>((sp * SPAN_BYTES) >> 4) + 2u * k;
+                            const uint64_t offx = static_cast<uint64_t>((sp * Cf::XSPAN_BYTES) >> 4) + 2u * k;
+                            ptx::umma_bf16(colk, dWk + offw, dX + xoff + offx, idesc_kv, (sp | k) != 0 ? 1u : 0u);
+                        }
+#pragma unroll
+                    for (int sp = 0; sp < SPANS; ++sp)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t offw = static_cast<uint64_t>((sp * SPAN_BYTES) >> 4) + 2u * k;
+                            const uint64_t offx = static_cast<uint64_t>((sp * Cf::XSPAN_BYTES) >> 4) + 2u * k;
+                            ptx::umma_bf16(colv, dWv + offw, dX + xoff + offx, idesc_kv, (sp | k) != 0 ? 1u : 0u);
+                        }
+                    ptx::umma_commit(&kv_full[bb]);
+                }
+                __syncwarp();
+                if (t == 1) {                        // the unit's first context MMA overwrites the accumulator: the previous unit's
+                    ptx::mbar_wait(ctx_empty, (u & 1u) ^ 1u);       // context must have been read out
+                    ptx::tc_fence_after();
+                }
+                if (t >= 1) issue_ctx(g - 1, t == 1, false);
+            }
+            if (T == 1) {
+                ptx::mbar_wait(ctx_empty, (u & 1u) ^ 1u);
+                ptx::tc_fence_after();
+            }
+            issue_ctx(g - 1, T == 1, true);
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: 16 warps, thread = (row, 16-pixel quarter)
+        const int te = (warp - 2) * 32 + lane;          // 0..511
+        const int q = warp & 3;                         // TMEM lane quarter
+        const int cq = (warp - 2) >> 2;                 // which 16 pixels of the tile
+        const int r = q * 32 + lane;                    // d (K^T, ctx) / e (V^T) row
+        if (te < 128) {
+            s_sk[te] = a.rowsum[HD + te];
+            s_sv[te] = a.rowsum[2 * HD + te];
+            s_shift[te] = a.kshift[te];
+        }
+        named_bar_sync(1, KV2_EPI_WARPS * 32);
+        constexpr float LOG2E = 1.4426950408889634f;
+        const ptx::f32x2 NSK = ptx::dup2(-(s_sk[r] * LOG2E)), NSHIFT = ptx::dup2(-(s_shift[r] * LOG2E)), NSV = ptx::dup2(-s_sv[r]);
+        const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const int px0 = cq * 16;
+        ptx::grid_dep_wait();
+        int g = 0, u = 0;
+        for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++u) {
+            ptx::f32x2 ssum2 = ptx::mk2(0.f, 0.f);
+            for (int t = 0; t < T; ++t, ++g) {
+                const int st = g % XS, bb = g & 1;
+                ptx::mbar_wait(&x_full[st], (g / XS) & 1u);          // x tile visible to this thread
+                // per-pixel LayerNorm statistics while the MMAs run, eight threads per pixel
+                tile_stats<C, KV2_EPI_WARPS * 32, Cf::XSPAN_BYTES>(sX + st * Cf::X_BYTES, te, a.eps, s_mu + bb * KV_PX,
+                                                                   s_rstd + bb * KV_PX, s_rl + bb * KV_PX);
+                ptx::mbar_wait(&kv_full[bb], (g >> 1) & 1u);         // K^T / V^T of tile g ready
+                ptx::tc_fence_after();
+                named_bar_sync(1, KV2_EPI_WARPS * 32);
+                if (te == 0) ptx::mbar_arrive(&x_empty[st]);          // MMAs done (kv_full) and statistics read: stage free
+                const float* mu_b = s_mu + bb * KV_PX + px0;
+                const float* rs_b = s_rstd + bb * KV_PX + px0;
+                const float* rl_b = s_rl + bb * KV_PX + px0;
+                uint32_t vk[16], vv[16];
+                ptx::tmem_ld16(tlane + bb * 128 + px0, vk);
+                ptx::tmem_ld16(tlane + bb * 128 + 64 + px0, vv);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&kv_empty[bb]);       // accumulators drained: tile g + 2's MMAs may overwrite them
+                const uint4 p0 = k_chunk8<0>(vk, mu_b, rl_b, NSK, NSHIFT, ssum2);
+                const uint4 p1 = k_chunk8<8>(vk, mu_b + 8, rl_b + 8, NSK, NSHIFT, ssum2);
+                const uint4 v0 = v_chunk8<0>(vv, mu_b, rs_b, NSV);
+                const uint4 v1 = v_chunk8<8>(vv, mu_b + 8, rs_b + 8, NSV);
+                ptx::mbar_wait(&pv_empty[bb], ((g >> 1) & 1u) ^ 1u); // the context MMA of tile g - 2 has consumed this P / V buffer
+                uint8_t* pb = sP + bb * Cf::PV_BYTES;
+                uint8_t* vb = sV + bb * Cf::PV_BYTES;
+                *reinterpret_cast<uint4*>(pb + sw_off(r, cq * 2)) = p0;
+                *reinterpret_cast<uint4*>(pb + sw_off(r, cq * 2 + 1)) = p1;
+                *reinterpret_cast<uint4*>(vb + sw_off(r, cq * 2)) = v0;
+                *reinterpret_cast<uint4*>(vb + sw_off(r, cq * 2 + 1)) = v1;
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&pv_full[bb]);
+            }
+            const float ssum = ptx::lo(ssum2) + ptx::hi(ssum2);
+            // ---- end of the unit: softmax denominators and the context accumulator
+            s_S[cq * 128 + r] = ssum;
+            named_bar_sync(1, KV2_EPI_WARPS * 32);
+            if (cq == 0) {
+                a.s_part[static_cast<size_t>(unit) * HD + r] = (s_S[r] + s_S[128 + r]) + (s_S[256 + r] + s_S[384 + r]);
+                ptx::mbar_wait(ctx_full, u & 1u);
+                ptx::tc_fence_after();
+                uint32_t v[32];
+                ptx::tmem_ld32(tlane + COL_CTX + q * 32, v);     // row d = q*32 + lane belongs to head q: columns e of head q
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(ctx_empty);
+                float4* dst = reinterpret_cast<float4*>(a.ctx_part + (static_cast<size_t>(unit) * HD + r) * 32);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    dst[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                              __uint_as_float(v[j + 3]));
+            }
+            named_bar_sync(1, KV2_EPI_WARPS * 32);               // s_S may be rewritten by the next unit
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) ptx::tmem_dealloc(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------------------------------------ kernel 2: mix
 __global__ void __launch_bounds__(128)
 linattn_mix_kernel(const float* __restrict__ ctx_part, const float* __restrict__ s_part, const float* __restrict__ wo,
                    bf16* __restrict__ mb, int parts, int C, float inv_n_scale) {
-    __shared__ float s_ctx[HD][33];
     __shared__ __align__(16) float s_wo[32 * HD];   // this block's rows of Wo (C / 4 <= 32 output channels)
     ptx::grid_dep_launch();     // PDL (ptx.cuh): the successor may be scheduled; then wait for the predecessor grid and its memory
     ptx::grid_dep_wait();
     const int b = blockIdx.x;
     const int t = threadIdx.x;          // hd = h*32 + d
     const int h = t >> 5;
-    const int per = C / gridDim.y;      // output channels of this block
+    const int per = C / gridDim.y;      // output channels of this block (a multiple of 4)
     {   // coalesced copy of Wo[blockIdx.y * per .. +per][128]; its latency overlaps the partial loads below
         const float4* src = reinterpret_cast<const float4*>(wo + static_cast<size_t>(blockIdx.y) * per * HD);
         for (int i = t; i < per * HD / 4; i += 128) reinterpret_cast<float4*>(s_wo)[i] = __ldg(src + i);
@@ -399,26 +672,30 @@ linattn_mix_kernel(const float* __restrict__ ctx_part, const float* __restrict__
 #pragma unroll
     for (int p = 0; p < 8; ++p) S += sp[p];
     const float norm = inv_n_scale / S;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        s_ctx[t][4 * j] = acc4[j].x * norm; s_ctx[t][4 * j + 1] = acc4[j].y * norm;
-        s_ctx[t][4 * j + 2] = acc4[j].z * norm; s_ctx[t][4 * j + 3] = acc4[j].w * norm;
-    }
-    __syncthreads();
+    // row hd = t of the normalised context stays in this thread's registers (each thread only ever needs its own row)
     float c[32];
 #pragma unroll
-    for (int e = 0; e < 32; ++e) c[e] = s_ctx[t][e];
-    for (int cl = 0; cl < per; ++cl) {
-        const int co = blockIdx.y * per + cl;
-        const float4* w = reinterpret_cast<const float4*>(s_wo + cl * HD + h * 32);   // broadcast reads
-        float acc = 0.f;
+    for (int j = 0; j < 8; ++j) {
+        c[4 * j] = acc4[j].x * norm; c[4 * j + 1] = acc4[j].y * norm;
+        c[4 * j + 2] = acc4[j].z * norm; c[4 * j + 3] = acc4[j].w * norm;
+    }
+    __syncthreads();                    // s_wo complete
+    // four output channels at a time: four independent FMA chains (one chain per channel left the kernel issue-latency bound
+    // at 0.24 IPC per scheduler, 27 us per launch: profiles/r02_notes.md 10); the sum order inside a channel is unchanged
+    for (int cl = 0; cl < per; cl += 4) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const float4 w4 = w[e];
-            acc = fmaf(w4.x, c[4 * e], acc); acc = fmaf(w4.y, c[4 * e + 1], acc);
-            acc = fmaf(w4.z, c[4 * e + 2], acc); acc = fmaf(w4.w, c[4 * e + 3], acc);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 w4 = *reinterpret_cast<const float4*>(s_wo + (cl + u) * HD + h * 32 + 4 * e);   // broadcast reads
+                acc[u] = fmaf(w4.x, c[4 * e], acc[u]); acc[u] = fmaf(w4.y, c[4 * e + 1], acc[u]);
+                acc[u] = fmaf(w4.z, c[4 * e + 2], acc[u]); acc[u] = fmaf(w4.w, c[4 * e + 3], acc[u]);
+            }
         }
-        mb[(static_cast<size_t>(b) * C + co) * HD + t] = __float2bfloat16(acc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            mb[(static_cast<size_t>(b) * C + blockIdx.y * per + cl + u) * HD + t] = __float2bfloat16(acc[u]);
     }
 }
 
@@ -439,7 +716,7 @@ struct OutCfg {
     static constexpr uint32_t MB_SPAN = C * 128;                 // one 64-wide K span of Mb [C rows]
     static constexpr uint32_t MB_BYTES = 2 * MB_SPAN;
     static constexpr uint32_t A2_BYTES = 2 * SPAN_BYTES;
-    static constexpr uint32_t SMALL_BYTES = 512 + 2 * 4 * C + 128 + 1024;    // rowsum, bo, g2, barriers, [2][128] half-row exchange
+    static constexpr uint32_t SMALL_BYTES = 512 + 2 * 4 * C + 128 + 4096;    // rowsum, bo, g2, barriers, four [2][128] half-row exchange slots
     static constexpr int SMEM_BYTES = WQ_BYTES + 2 * X_BYTES + MB_BYTES + A2_BYTES + SMALL_BYTES + 1024;
     static constexpr int CTAS_PER_SM = C == 64 ? 2 : 1;
     static constexpr int X_EMPTY_ARRIVALS = C == 64 ? 4 : 8;     // storing warps per tile
@@ -461,8 +738,8 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     float* s_sq = reinterpret_cast<float*>(sA2 + Cf::A2_BYTES);
     float* s_bo = s_sq + 128;
     float* s_g2 = s_bo + C;
-    float* s_xch = s_g2 + C;                         // [2][128]: the two column halves of a row exchange their LayerNorm partials
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_xch + 256);
+    float* s_xch = s_g2 + C;                         // [4][2][128]: the two column halves of a row exchange their LayerNorm partials
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_xch + 1024);
     uint64_t* wq_bar = bars;
     uint64_t* x_full = bars + 1;                     // [2]
     uint64_t* x_empty = bars + 3;                    // [2]
@@ -567,7 +844,7 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         }
     } else {
         // epilogue warp (q, hf): pixel row r = q*32 + lane of the tile; hf picks two of the four heads (softmax) and half
-        // of the output channels (LayerNorm); both halves recompute the cheap per-row statistics instead of exchanging them
+        // of the output channels (both LayerNorms); the halves exchange partial sums through shared memory
         const int q = warp & 3;
         const int hf = (warp - 2) >> 2;
         const int te = (warp - 2) * 32 + lane;          // 0..255
@@ -576,46 +853,94 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         if (te < C) { s_bo[te] = a.bo[te]; s_g2[te] = a.g2[te]; }
         named_bar_sync(1, 256);
         const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        // Arithmetic below uses the packed fp32 forms (ptx.cuh: two IEEE lanes per FFMA2 / FADD2 / FMUL2): the epilogue is issue-bound.
+        constexpr int HALF = C / 2;                      // channels of a row this thread owns: [hf * HALF, (hf + 1) * HALF)
+        constexpr int HCH = HALF / 8;                    // ... as 16-byte chunks: half of span 0 (C = 64) or span hf (C = 128)
+        constexpr float LOG2E = 1.4426950408889634f;
+        float* xa = s_xch;                               // four [2][128] exchange slots: x sum, x centred squares, y sum, y squares
+        float* xb = s_xch + 256;
+        float* xc = s_xch + 512;
+        float* xd = s_xch + 768;
+        const int mine = hf * 128 + r, other = (hf ^ 1) * 128 + r;
         for (int it = 0; it < ntile; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int st = it & 1;
             uint8_t* xs = sX + st * Cf::X_BYTES;
             ptx::mbar_wait(&x_full[st], (it >> 1) & 1u);
+            // ---- LayerNorm statistics of pixel row r (two-pass): each of the row's two threads reduces its half of the channels
+            // from registers and the halves exchange their partial sums through shared memory (a + b == b + a: both get the same bits)
             float mean, rstd;
-            row_stats<C>(xs, r, a.eps, mean, rstd);
+            {
+                const uint8_t* xrow = xs + (C == 64 ? 0 : hf * SPAN_BYTES);
+                const int ch0 = C == 64 ? hf * 4 : 0;
+                ptx::f32x2 xh[HALF / 2];
+#pragma unroll
+                for (int c = 0; c < HCH; ++c) {
+                    const uint4 u = *reinterpret_cast<const uint4*>(xrow + sw_off(r, ch0 + c));
+                    xh[c * 4] = ptx::bf16x2_to_f32x2(u.x); xh[c * 4 + 1] = ptx::bf16x2_to_f32x2(u.y);
+                    xh[c * 4 + 2] = ptx::bf16x2_to_f32x2(u.z); xh[c * 4 + 3] = ptx::bf16x2_to_f32x2(u.w);
+                }
+                ptx::f32x2 s0 = xh[0], s1 = xh[1];
+#pragma unroll
+                for (int i = 2; i < HALF / 2; i += 2) { s0 = ptx::add2(s0, xh[i]); s1 = ptx::add2(s1, xh[i + 1]); }
+                s0 = ptx::add2(s0, s1);
+                const float psum = ptx::lo(s0) + ptx::hi(s0);
+                xa[mine] = psum;
+                named_bar_sync(2 + q, 64);
+                mean = (psum + xa[other]) * (1.0f / C);
+                const ptx::f32x2 nm = ptx::dup2(-mean);
+                ptx::f32x2 q0 = ptx::mk2(0.f, 0.f), q1 = q0;
+#pragma unroll
+                for (int i = 0; i < HALF / 2; i += 2) {
+                    const ptx::f32x2 d0 = ptx::add2(xh[i], nm), d1 = ptx::add2(xh[i + 1], nm);
+                    q0 = ptx::fma2(d0, d0, q0);
+                    q1 = ptx::fma2(d1, d1, q1);
+                }
+                q0 = ptx::add2(q0, q1);
+                const float pss = ptx::lo(q0) + ptx::hi(q0);
+                xb[mine] = pss;
+                named_bar_sync(2 + q, 64);
+                rstd = rsqrtf((pss + xb[other]) * (1.0f / C) + a.eps);
+            }
             ptx::mbar_wait(q_full, it & 1u);
             ptx::tc_fence_after();
+            // q = rstd * (acc - mean * rowsum) and exp(q - max) = exp2(q * log2e - max'): al = rstd * log2e, ncl = -mean * al
+            // (softmax is invariant to the common shift, the max is taken after scaling)
+            const ptx::f32x2 AL = ptx::dup2(rstd * LOG2E), NCL = ptx::dup2(-(mean * (rstd * LOG2E)));
 #pragma unroll 1
             for (int hh = 0; hh < 2; ++hh) {
                 const int h = 2 * hf + hh;
                 uint32_t v[32];
                 ptx::tmem_ld32(tlane + COL_Q + h * 32, v);
                 ptx::tmem_ld_wait();
-                float f[32];
+                ptx::f32x2 f[16];
                 float mx = -INFINITY;
-                // q = rstd * (acc - mean * rowsum) and exp(q - max) = exp2(q * log2e - max'): one FMA per element with
-                // al = rstd * log2e, cl = mean * al (softmax is invariant to the common shift, the max is taken after scaling)
-                const float al = rstd * 1.4426950408889634f, cl = mean * al;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 s4 = *reinterpret_cast<const float4*>(s_sq + h * 32 + j);
-                    f[j] = fmaf(__uint_as_float(v[j]), al, -(cl * s4.x));
-                    f[j + 1] = fmaf(__uint_as_float(v[j + 1]), al, -(cl * s4.y));
-                    f[j + 2] = fmaf(__uint_as_float(v[j + 2]), al, -(cl * s4.z));
-                    f[j + 3] = fmaf(__uint_as_float(v[j + 3]), al, -(cl * s4.w));
-                    mx = fmaxf(fmaxf(fmaxf(mx, f[j]), fmaxf(f[j + 1], f[j + 2])), f[j + 3]);
+                for (int j = 0; j < 16; j += 2) {
+                    const float4 s4 = *reinterpret_cast<const float4*>(s_sq + h * 32 + 2 * j);
+                    f[j] = ptx::fma2(ptx::mk2(v[2 * j], v[2 * j + 1]), AL, ptx::mul2(NCL, ptx::mk2(s4.x, s4.y)));
+                    f[j + 1] = ptx::fma2(ptx::mk2(v[2 * j + 2], v[2 * j + 3]), AL, ptx::mul2(NCL, ptx::mk2(s4.z, s4.w)));
+                    mx = fmaxf(fmaxf(fmaxf(mx, ptx::lo(f[j])), fmaxf(ptx::hi(f[j]), ptx::lo(f[j + 1]))), ptx::hi(f[j + 1]));
                 }
-                float ssum = 0.f;
+                const ptx::f32x2 NMX = ptx::dup2(-mx);
+                ptx::f32x2 a0 = ptx::mk2(0.f, 0.f), a1 = a0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { f[j] = ptx::ex2(f[j] - mx); ssum += f[j]; }
-                const float inv = 1.0f / ssum;
+                for (int j = 0; j < 16; j += 2) {
+                    const ptx::f32x2 d0 = ptx::add2(f[j], NMX), d1 = ptx::add2(f[j + 1], NMX);
+                    f[j] = ptx::mk2(ptx::ex2(ptx::lo(d0)), ptx::ex2(ptx::hi(d0)));
+                    f[j + 1] = ptx::mk2(ptx::ex2(ptx::lo(d1)), ptx::ex2(ptx::hi(d1)));
+                    a0 = ptx::add2(a0, f[j]);
+                    a1 = ptx::add2(a1, f[j + 1]);
+                }
+                a0 = ptx::add2(a0, a1);
+                const ptx::f32x2 INV = ptx::dup2(ptx::rcp(ptx::lo(a0) + ptx::hi(a0)));   // the sum is in [1, 32]
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     uint4 o;
-                    o.x = ptx::pack_bf16x2(f[jj * 8] * inv, f[jj * 8 + 1] * inv);
-                    o.y = ptx::pack_bf16x2(f[jj * 8 + 2] * inv, f[jj * 8 + 3] * inv);
-                    o.z = ptx::pack_bf16x2(f[jj * 8 + 4] * inv, f[jj * 8 + 5] * inv);
-                    o.w = ptx::pack_bf16x2(f[jj * 8 + 6] * inv, f[jj * 8 + 7] * inv);
+                    o.x = ptx::pack_bf16x2(ptx::mul2(f[jj * 4], INV));
+                    o.y = ptx::pack_bf16x2(ptx::mul2(f[jj * 4 + 1], INV));
+                    o.z = ptx::pack_bf16x2(ptx::mul2(f[jj * 4 + 2], INV));
+                    o.w = ptx::pack_bf16x2(ptx::mul2(f[jj * 4 + 3], INV));
                     *reinterpret_cast<uint4*>(sA2 + hf * SPAN_BYTES + sw_off(r, hh * 4 + jj)) = o;   // span = h >> 1 = hf
                 }
             }
@@ -628,9 +953,8 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             // LayerNorm over the C output channels of this pixel.  This thread owns the channels [hf * C/2, (hf + 1) * C/2) of row r:
             // one TMEM read into registers (+ bias), then the two halves of the row exchange their partial sums through shared
             // memory (mean first, then the centred sum of squares: two-pass accuracy without reading the other half).
-            constexpr int HALF = C / 2;
-            float y[HALF];
-            float sum = 0.f;
+            ptx::f32x2 y[HALF / 2];
+            ptx::f32x2 ys0 = ptx::mk2(0.f, 0.f), ys1 = ys0;
 #pragma unroll
             for (int cc = 0; cc < HALF / 32; ++cc) {
                 const int c32 = hf * (HALF / 32) + cc;
@@ -638,24 +962,33 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 ptx::tmem_ld32(tlane + COL_Y + c32 * 32, v);
                 ptx::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    y[cc * 32 + j] = __uint_as_float(v[j]) + s_bo[c32 * 32 + j];
-                    sum += y[cc * 32 + j];
+                for (int j = 0; j < 16; j += 2) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(s_bo + c32 * 32 + 2 * j);
+                    y[cc * 16 + j] = ptx::add2(ptx::mk2(v[2 * j], v[2 * j + 1]), ptx::mk2(b4.x, b4.y));
+                    y[cc * 16 + j + 1] = ptx::add2(ptx::mk2(v[2 * j + 2], v[2 * j + 3]), ptx::mk2(b4.z, b4.w));
+                    ys0 = ptx::add2(ys0, y[cc * 16 + j]);
+                    ys1 = ptx::add2(ys1, y[cc * 16 + j + 1]);
                 }
             }
-            s_xch[hf * 128 + r] = sum;
+            ys0 = ptx::add2(ys0, ys1);
+            const float sum = ptx::lo(ys0) + ptx::hi(ys0);
+            xc[mine] = sum;
             named_bar_sync(2 + q, 64);
-            const float ymean = (sum + s_xch[(hf ^ 1) * 128 + r]) * (1.0f / C);
-            float ss = 0.f;
+            const float ymean = (sum + xc[other]) * (1.0f / C);
+            const ptx::f32x2 NYM = ptx::dup2(-ymean);
+            ptx::f32x2 yq0 = ptx::mk2(0.f, 0.f), yq1 = yq0;
 #pragma unroll
-            for (int j = 0; j < HALF; ++j) {
-                y[j] -= ymean;
-                ss = fmaf(y[j], y[j], ss);
+            for (int j = 0; j < HALF / 2; j += 2) {
+                y[j] = ptx::add2(y[j], NYM);
+                y[j + 1] = ptx::add2(y[j + 1], NYM);
+                yq0 = ptx::fma2(y[j], y[j], yq0);
+                yq1 = ptx::fma2(y[j + 1], y[j + 1], yq1);
             }
-            named_bar_sync(2 + q, 64);                   // the partner has read this row's sum: the slot may be reused
-            s_xch[hf * 128 + r] = ss;
+            yq0 = ptx::add2(yq0, yq1);
+            const float ss = ptx::lo(yq0) + ptx::hi(yq0);
+            xd[mine] = ss;
             named_bar_sync(2 + q, 64);
-            const float yrstd = rsqrtf((ss + s_xch[(hf ^ 1) * 128 + r]) * (1.0f / C) + a.eps);
+            const ptx::f32x2 YR = ptx::dup2(rsqrtf((ss + xd[other]) * (1.0f / C) + a.eps));
             // normalise, + x, and write the result IN PLACE over the x tile (same row, same swizzled chunk), which then doubles
             // as the TMA-store staging buffer
 #pragma unroll
@@ -666,19 +999,15 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 for (int jj = 0; jj < 4; ++jj) {
                     const int ch = (c32 & 1) * 4 + jj;                       // 16-byte chunk inside the span
                     uint4* px = reinterpret_cast<uint4*>(xs + sp * SPAN_BYTES + sw_off(r, ch));
-                    float xr[8];
-                    unpack8(*px, xr);
-                    float o[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int c = c32 * 32 + jj * 8 + j;
-                        o[j] = fmaf(y[cc * 32 + jj * 8 + j] * yrstd, s_g2[c], xr[j]);
-                    }
-                    uint4 u;
-                    u.x = ptx::pack_bf16x2(o[0], o[1]);
-                    u.y = ptx::pack_bf16x2(o[2], o[3]);
-                    u.z = ptx::pack_bf16x2(o[4], o[5]);
-                    u.w = ptx::pack_bf16x2(o[6], o[7]);
+                    const uint4 xu = *px;
+                    const float4 ga = *reinterpret_cast<const float4*>(s_g2 + c32 * 32 + jj * 8);
+                    const float4 gb = *reinterpret_cast<const float4*>(s_g2 + c32 * 32 + jj * 8 + 4);
+                    const int k = cc * 16 + jj * 4;
+                    uint4 u;                                                  // o = (y * rstd) * g2 + x
+                    u.x = ptx::pack_bf16x2(ptx::fma2(ptx::mul2(y[k], YR), ptx::mk2(ga.x, ga.y), ptx::bf16x2_to_f32x2(xu.x)));
+                    u.y = ptx::pack_bf16x2(ptx::fma2(ptx::mul2(y[k + 1], YR), ptx::mk2(ga.z, ga.w), ptx::bf16x2_to_f32x2(xu.y)));
+                    u.z = ptx::pack_bf16x2(ptx::fma2(ptx::mul2(y[k + 2], YR), ptx::mk2(gb.x, gb.y), ptx::bf16x2_to_f32x2(xu.z)));
+                    u.w = ptx::pack_bf16x2(ptx::fma2(ptx::mul2(y[k + 3], YR), ptx::mk2(gb.z, gb.w), ptx::bf16x2_to_f32x2(xu.w)));
                     *px = u;
                 }
             }
@@ -729,6 +1058,7 @@ int linattn_fused_prepare(const LinAttnFusedDesc& d, int num_sms, LinAttnFusedLa
         return 1;
     }
     out->d = d;
+    out->num_sms = num_sms;
     const int tiles_per_img = d.n / TILE;
     int parts = 1;                      // split images until there are >= ~4 CTAs per SM or one tile per CTA
     while (parts < tiles_per_img && d.B * parts < 4 * num_sms && tiles_per_img % (parts * 2) == 0) parts *= 2;
@@ -770,6 +1100,8 @@ static cudaError_t run_c(const LinAttnFusedLaunch& l, cudaStream_t s) {
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(linattn_kv_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, KvCfg<C>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(linattn_kv2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Kv2Cfg<C>::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(linattn_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, OutCfg<C>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr = true;
@@ -778,7 +1110,15 @@ static cudaError_t run_c(const LinAttnFusedLaunch& l, cudaStream_t s) {
     KvArgs ka;
     ka.n = d.n; ka.tiles_per_unit = l.tiles_per_unit * (TILE / KV_PX); ka.parts = l.parts; ka.rowsum = d.rowsum; ka.kshift = d.kshift;
     ka.ctx_part = d.ctx_part; ka.s_part = d.s_part; ka.eps = d.eps;
-    cudaError_t e = launch_pdl(linattn_kv_kernel<C>, dim3(d.B * l.parts), dim3(KV_THREADS), KvCfg<C>::SMEM_BYTES, s, l.tmXk, l.tmW, ka);
+    static const bool kv_v1 = [] { const char* v = getenv("HD_LA_KV"); return v && v[0] == '1'; }();
+    cudaError_t e;
+    if (kv_v1) {
+        e = launch_pdl(linattn_kv_kernel<C>, dim3(d.B * l.parts), dim3(KV_THREADS), KvCfg<C>::SMEM_BYTES, s, l.tmXk, l.tmW, ka);
+    } else {
+        const int units = d.B * l.parts;
+        const int grid = units < l.num_sms ? units : l.num_sms;     // persistent: one CTA per SM walks its units
+        e = launch_pdl(linattn_kv2_kernel<C>, dim3(grid), dim3(KV2_THREADS), Kv2Cfg<C>::SMEM_BYTES, s, l.tmXk, l.tmW, ka, units);
+    }
     if (e != cudaSuccess) return e;
     e = launch_pdl(linattn_mix_kernel, dim3(d.B, 4), dim3(128), 0, s, d.ctx_part, d.s_part, d.wo, d.mb, l.parts, C,
                    0.17677669529663687f / static_cast<float>(d.n));   // 32^-0.5 / n

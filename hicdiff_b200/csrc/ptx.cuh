@@ -70,8 +70,12 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // waiting warp costs no issue slots.  Without the hint the default window is short and the retry loop below spun: ncu's source page
 // attributed 18 - 21 % of ALL executed instructions of the fused attention kernels to it (profiles/r02_notes.md 9) -- issue slots taken
 // from the epilogue warps that share the scheduler.
+#ifndef HD_MBAR_HINT_NS
+#define HD_MBAR_HINT_NS 0x989680u       // 10 ms; 0 = no hint (A/B builds: scripts/build_variant.sh)
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+#if HD_MBAR_HINT_NS > 0
     asm volatile(
         "{\n\t"
         ".reg .pred P;\n\t"
@@ -79,8 +83,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, P;\n\t"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(HD_MBAR_HINT_NS)
         : "memory");
+#else
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+#endif
     return ok != 0;
 }
 
@@ -353,6 +368,12 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
+__device__ __forceinline__ float rcp(float x) {      // 1 / x to ~1 ulp, no range / denormal slow path (for x known to be normal)
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // ---------------------------------------------------------------- packing
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -362,6 +383,42 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
     return __bfloat1622float2(v);
 }
+
+// ---------------------------------------------------------------- packed fp32 (sm_100: FFMA2 / FADD2 / FMUL2)
+// Two IEEE fp32 lanes per instruction, each rounded exactly like the scalar form -- results are bit-identical to fmaf / + / *,
+// the issue slots are halved.  The epilogues of the fused attention kernels are issue-bound (profiles/r02_notes.md 9).
+struct f32x2 { unsigned long long u; };
+__device__ __forceinline__ f32x2 mk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.u) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 mk2(uint32_t lo, uint32_t hi) {      // raw fp32 bit patterns (TMEM loads)
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.u) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 dup2(float v) { return mk2(v, v); }
+__device__ __forceinline__ float lo(f32x2 v) { float a; asm("{\n\t.reg .b32 t;\n\tmov.b64 {%0, t}, %1;\n\t}" : "=f"(a) : "l"(v.u)); return a; }
+__device__ __forceinline__ float hi(f32x2 v) { float b; asm("{\n\t.reg .b32 t;\n\tmov.b64 {t, %0}, %1;\n\t}" : "=f"(b) : "l"(v.u)); return b; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.u) : "l"(a.u), "l"(b.u), "l"(c.u));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.u) : "l"(a.u), "l"(b.u));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d.u) : "l"(a.u), "l"(b.u));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(f32x2 v) { return pack_bf16x2(lo(v), hi(v)); }
+// bf16x2 word -> the two fp32 values it encodes (exact): low half shifted up, high half masked
+__device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t w) { return mk2(w << 16, w & 0xffff0000u); }
 
 }  // namespace ptx
 }  // namespace hd

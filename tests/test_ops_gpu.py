@@ -296,7 +296,9 @@ def _linattn_block_ref(x_nchw, g1, wqkv, wo, bo, g2):
 
 
 @pytest.mark.parametrize("B,H,C,kscale", [(2, 64, 64, 1.0), (3, 32, 64, 1.0), (2, 32, 128, 1.0), (5, 16, 128, 1.0),
-                                          (2, 32, 64, 8.0), (300, 16, 64, 1.0)])
+                                          (2, 32, 64, 8.0), (300, 16, 64, 1.0),
+                                          # long units (16 / 4 pixel tiles per unit) and several units per persistent CTA
+                                          (160, 64, 64, 1.0), (150, 32, 128, 1.0)])
 def test_linattn_block_fused(B, H, C, kscale):
     """The fused three-launch block vs the fp64 reference on the same bf16 input.  Error sources: bf16 rounding of the
     gain-folded weights, of exp(k - shift), of the softmaxed q, of the mixed to_out matrix, and of the output (the
