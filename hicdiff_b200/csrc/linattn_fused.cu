@@ -8,10 +8,10 @@
 // The unfused chain (LayerNorm, to_qkv GEMM, two attention kernels, to_out GEMM, LayerNorm + residual) moves
 // ~27 B per input byte through HBM because the [B, n, 384] qkv tensor is 6x wider than x; here qkv never leaves the SM:
 //
-//   linattn_kv_kernel   (one CTA per (image, pixel range)): for every 128-pixel tile, TMA-load x, tcgen05 GEMMs
-//       K^T[d, px] = Wk' x^T and V^T[e, px] = Wv' x^T (weights pre-multiplied by the LayerNorm gain, the LayerNorm's mean /
-//       rstd applied per pixel COLUMN in the epilogue: W LN(x) = rstd * (W' x - mu * rowsum(W'))), p = exp(k - shift_d)
-//       written bf16 K-major to shared memory, then ctx[d, e] += P V^T as a third tcgen05 GEMM accumulating in TMEM over
+//   linattn_kv_kernel   (one CTA per (image, pixel range); linattn_kv2_kernel is its persistent, double-buffered form): for every
+//       64-pixel tile, TMA-load x, LayerNorm it IN PLACE in shared memory (gain folded into the weights, statistics by shuffles),
+//       tcgen05 GEMMs K^T[d, px] = Wk' z^T and V^T[e, px] = Wv' z^T, p = exp(k - shift_d) written bf16 K-major to shared
+//       memory, then ctx[d, e] += P V^T as a third tcgen05 GEMM accumulating in TMEM over
 //       the CTA's tiles.  Writing the GEMMs transposed makes every operand K-major and gives each epilogue thread one
 //       (d or e) row, so the softmax denominators are in-thread sums.  softmax_n is shift-invariant: instead of the
 //       data-dependent max it uses the analytic bound |k_d| <= sqrt(C) * ||Wk'_d||_2 (shift_d = max(0, bound_d - 40)),
@@ -40,86 +40,6 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 // byte offset of 16-byte chunk c of row r inside a K-major, 128B-swizzled tile with 128-byte rows
 __device__ __forceinline__ uint32_t sw_off(int r, int c) { return static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(c ^ (r & 7)) << 4); }
-
-// LayerNorm statistics of the KV_PX = 64 pixels of a kv tile, spread over NT epilogue threads: NT / 64 consecutive lanes share a
-// pixel, each keeps its share of the row's channels in registers (two-pass), the partial sums meet in xor-shuffles (a + b == b + a:
-// every lane of a pixel ends with the same bits).  The one-thread-per-pixel form left 3/4 (7/8) of the epilogue threads idle in
-// front of the tile's named barrier for ~700 clk of dependent adds.  Writes rstd * mean, rstd, rstd * log2(e) of pixel p.
-template <int C, int NT, uint32_t SPAN_STRIDE>
-__device__ __forceinline__ void tile_stats(const uint8_t* sx, int te, float eps, float* s_mu, float* s_rstd, float* s_rl) {
-    constexpr int TPP = NT / 64;                 // threads per pixel: 4 or 8
-    constexpr int NCH = (C / 8) / TPP;           // 16-byte chunks per thread
-    static_assert(NCH >= 1, "tile_stats: more threads than chunks");
-    const int p = te / TPP, sub = te % TPP;
-    ptx::f32x2 xh[NCH * 4];
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-        const int c = sub + i * TPP;             // chunk of the row: span c >> 3, chunk c & 7 inside it
-        const uint4 u = *reinterpret_cast<const uint4*>(sx + (c >> 3) * SPAN_STRIDE + sw_off(p, c & 7));
-        xh[i * 4] = ptx::bf16x2_to_f32x2(u.x); xh[i * 4 + 1] = ptx::bf16x2_to_f32x2(u.y);
-        xh[i * 4 + 2] = ptx::bf16x2_to_f32x2(u.z); xh[i * 4 + 3] = ptx::bf16x2_to_f32x2(u.w);
-    }
-    ptx::f32x2 s0 = xh[0], s1 = xh[1];
-#pragma unroll
-    for (int i = 2; i < NCH * 4; i += 2) { s0 = ptx::add2(s0, xh[i]); s1 = ptx::add2(s1, xh[i + 1]); }
-    s0 = ptx::add2(s0, s1);
-    float sum = ptx::lo(s0) + ptx::hi(s0);
-#pragma unroll
-    for (int off = 1; off < TPP; off <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-    const float mean = sum * (1.0f / C);
-    const ptx::f32x2 nm = ptx::dup2(-mean);
-    ptx::f32x2 q0 = ptx::mk2(0.f, 0.f), q1 = q0;
-#pragma unroll
-    for (int i = 0; i < NCH * 4; i += 2) {
-        const ptx::f32x2 d0 = ptx::add2(xh[i], nm), d1 = ptx::add2(xh[i + 1], nm);
-        q0 = ptx::fma2(d0, d0, q0);
-        q1 = ptx::fma2(d1, d1, q1);
-    }
-    q0 = ptx::add2(q0, q1);
-    float ss = ptx::lo(q0) + ptx::hi(q0);
-#pragma unroll
-    for (int off = 1; off < TPP; off <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-    if (sub == 0) {
-        const float rstd = rsqrtf(ss * (1.0f / C) + eps);
-        s_mu[p] = rstd * mean;               // W LN(x) = rstd * (W'x) - (rstd * mean) * rowsum(W')
-        s_rstd[p] = rstd;
-        s_rl[p] = rstd * 1.4426950408889634f;
-    }
-}
-
-// Eight pixels (one 16-byte shared-memory chunk) of the kv epilogue, packed fp32 (ptx.cuh): v = accumulator registers OFF .. OFF + 7.
-//   K path: p = exp2(rl * acc - (mu * sk + shift)), sk / shift pre-multiplied by log2(e); NSK / NSHIFT are their negations
-//           (fma(mu, -sk, -shift) == -(fma(mu, sk, shift)) bit for bit); ssum2 accumulates the unrounded p
-//   V path: v = rstd * acc - mu * sv; NSV = -sv
-template <int OFF, int N>
-__device__ __forceinline__ uint4 k_chunk8(const uint32_t (&v)[N], const float* mu8, const float* rl8, ptx::f32x2 NSK,
-                                          ptx::f32x2 NSHIFT, ptx::f32x2& ssum2) {
-    const float4 ma = *reinterpret_cast<const float4*>(mu8), mb = *reinterpret_cast<const float4*>(mu8 + 4);
-    const float4 la = *reinterpret_cast<const float4*>(rl8), lb = *reinterpret_cast<const float4*>(rl8 + 4);
-    const ptx::f32x2 M[4] = {ptx::mk2(ma.x, ma.y), ptx::mk2(ma.z, ma.w), ptx::mk2(mb.x, mb.y), ptx::mk2(mb.z, mb.w)};
-    const ptx::f32x2 L[4] = {ptx::mk2(la.x, la.y), ptx::mk2(la.z, la.w), ptx::mk2(lb.x, lb.y), ptx::mk2(lb.z, lb.w)};
-    uint32_t o[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const ptx::f32x2 arg = ptx::fma2(L[e], ptx::mk2(v[OFF + 2 * e], v[OFF + 2 * e + 1]), ptx::fma2(M[e], NSK, NSHIFT));
-        const ptx::f32x2 pp = ptx::mk2(ptx::ex2(ptx::lo(arg)), ptx::ex2(ptx::hi(arg)));
-        ssum2 = ptx::add2(ssum2, pp);
-        o[e] = ptx::pack_bf16x2(pp);
-    }
-    return make_uint4(o[0], o[1], o[2], o[3]);
-}
-template <int OFF, int N>
-__device__ __forceinline__ uint4 v_chunk8(const uint32_t (&v)[N], const float* mu8, const float* rs8, ptx::f32x2 NSV) {
-    const float4 ma = *reinterpret_cast<const float4*>(mu8), mb = *reinterpret_cast<const float4*>(mu8 + 4);
-    const float4 ra = *reinterpret_cast<const float4*>(rs8), rb = *reinterpret_cast<const float4*>(rs8 + 4);
-    const ptx::f32x2 M[4] = {ptx::mk2(ma.x, ma.y), ptx::mk2(ma.z, ma.w), ptx::mk2(mb.x, mb.y), ptx::mk2(mb.z, mb.w)};
-    const ptx::f32x2 R[4] = {ptx::mk2(ra.x, ra.y), ptx::mk2(ra.z, ra.w), ptx::mk2(rb.x, rb.y), ptx::mk2(rb.z, rb.w)};
-    uint32_t o[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-        o[e] = ptx::pack_bf16x2(ptx::fma2(R[e], ptx::mk2(v[OFF + 2 * e], v[OFF + 2 * e + 1]), ptx::mul2(M[e], NSV)));
-    return make_uint4(o[0], o[1], o[2], o[3]);
-}
 
 // ------------------------------------------------------------------------------------------------ weight prep
 // out[row, c] = bf16(w[row, c] * g1[c]); rowsum[row] = sum_c out[row, c]; for the k rows additionally the softmax shift.
@@ -158,25 +78,100 @@ linattn_prep_kernel(const float* __restrict__ wqkv, const float* __restrict__ g1
 // ------------------------------------------------------------------------------------------------ kernel 1: context
 struct KvArgs {
     int n, tiles_per_unit, parts;
-    const float* rowsum;     // [384]
     const float* kshift;     // [128]
     float* ctx_part;         // [B * parts][128 (h*32+d)][32 (e)]
     float* s_part;           // [B * parts][128]
     float eps;
 };
 
-constexpr int KV_PX = 64;                // pixels per kv tile: K^T / V^T accumulators are 64 columns each, so the CTA needs
-                                         // 256 TMEM columns and two CTAs share an SM (their serial MMA <-> epilogue chains
-                                         // interleave; one 128-pixel CTA per SM left the tensor pipe and the SFUs idle half the time)
+constexpr int KV_PX = 64;                // pixels per kv tile: K^T / V^T accumulators are 64 columns each
+
+// LayerNorm of the 64 pixels of a kv tile IN PLACE in shared memory (the gain is folded into the weights), by NT epilogue threads:
+// NT / 64 consecutive lanes share a pixel, each keeps its share of the row's channels in registers (two-pass statistics), the partial
+// sums meet in xor-shuffles (a + b == b + a: every lane of a pixel ends with the same bits), and the normalised row goes back to the
+// same swizzled chunks as bf16.  The MMAs then produce k and v themselves -- the epilogue needs no per-pixel constants (the earlier
+// form corrected the raw-x products per element: W LN(x) = rstd * (W'x - mean * rowsum(W')), ~60 % of its instructions and, through
+// the shared-memory loads of the per-pixel constants, most of its exposed latency: profiles/r02_notes.md 10).
+template <int C, int NT, uint32_t SPAN_STRIDE>
+__device__ __forceinline__ void tile_normalize(uint8_t* sx, int te, float eps) {
+    constexpr int TPP = NT / KV_PX;              // threads per pixel: 4 or 8
+    constexpr int NCH = (C / 8) / TPP;           // 16-byte chunks per thread
+    static_assert(NCH >= 1, "tile_normalize: more threads than chunks");
+    const int p = te / TPP, sub = te % TPP;
+    ptx::f32x2 xh[NCH * 4];
+    uint4* src[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int c = sub + i * TPP;             // chunk of the row: span c >> 3, chunk c & 7 inside it
+        src[i] = reinterpret_cast<uint4*>(sx + (c >> 3) * SPAN_STRIDE + sw_off(p, c & 7));
+        const uint4 u = *src[i];
+        xh[i * 4] = ptx::bf16x2_to_f32x2(u.x); xh[i * 4 + 1] = ptx::bf16x2_to_f32x2(u.y);
+        xh[i * 4 + 2] = ptx::bf16x2_to_f32x2(u.z); xh[i * 4 + 3] = ptx::bf16x2_to_f32x2(u.w);
+    }
+    ptx::f32x2 s0 = xh[0], s1 = xh[1];
+#pragma unroll
+    for (int i = 2; i < NCH * 4; i += 2) { s0 = ptx::add2(s0, xh[i]); s1 = ptx::add2(s1, xh[i + 1]); }
+    s0 = ptx::add2(s0, s1);
+    float sum = ptx::lo(s0) + ptx::hi(s0);
+#pragma unroll
+    for (int off = 1; off < TPP; off <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const ptx::f32x2 nm = ptx::dup2(-(sum * (1.0f / C)));
+    ptx::f32x2 q0 = ptx::mk2(0.f, 0.f), q1 = q0;
+#pragma unroll
+    for (int i = 0; i < NCH * 4; i += 2) {
+        xh[i] = ptx::add2(xh[i], nm);
+        xh[i + 1] = ptx::add2(xh[i + 1], nm);
+        q0 = ptx::fma2(xh[i], xh[i], q0);
+        q1 = ptx::fma2(xh[i + 1], xh[i + 1], q1);
+    }
+    q0 = ptx::add2(q0, q1);
+    float ss = ptx::lo(q0) + ptx::hi(q0);
+#pragma unroll
+    for (int off = 1; off < TPP; off <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    const ptx::f32x2 RS = ptx::dup2(rsqrtf(ss * (1.0f / C) + eps));
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+        *src[i] = make_uint4(ptx::pack_bf16x2(ptx::mul2(xh[i * 4], RS)), ptx::pack_bf16x2(ptx::mul2(xh[i * 4 + 1], RS)),
+                             ptx::pack_bf16x2(ptx::mul2(xh[i * 4 + 2], RS)), ptx::pack_bf16x2(ptx::mul2(xh[i * 4 + 3], RS)));
+}
+
+// Eight pixels (one 16-byte shared-memory chunk) of the kv epilogue, packed fp32 (ptx.cuh): v = accumulator registers OFF .. OFF + 7.
+//   K path: p = exp(k - shift) = exp2(k * log2e - shift * log2e); ssum2 accumulates the unrounded p (the bf16 rounding of the MMA
+//           operand is unbiased: over n >= 1024 pixels the two sums agree to ~1e-5)
+//   V path: the accumulator is v
+template <int OFF, int N>
+__device__ __forceinline__ uint4 k_chunk8(const uint32_t (&v)[N], ptx::f32x2 L2E, ptx::f32x2 NSHIFT, ptx::f32x2& ssum2) {
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const ptx::f32x2 arg = ptx::fma2(ptx::mk2(v[OFF + 2 * e], v[OFF + 2 * e + 1]), L2E, NSHIFT);
+        const ptx::f32x2 pp = ptx::mk2(ptx::ex2(ptx::lo(arg)), ptx::ex2(ptx::hi(arg)));
+        ssum2 = ptx::add2(ssum2, pp);
+        o[e] = ptx::pack_bf16x2(pp);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+template <int OFF, int N>
+__device__ __forceinline__ uint4 v_chunk8(const uint32_t (&v)[N]) {
+    return make_uint4(ptx::pack_bf16x2(__uint_as_float(v[OFF]), __uint_as_float(v[OFF + 1])),
+                      ptx::pack_bf16x2(__uint_as_float(v[OFF + 2]), __uint_as_float(v[OFF + 3])),
+                      ptx::pack_bf16x2(__uint_as_float(v[OFF + 4]), __uint_as_float(v[OFF + 5])),
+                      ptx::pack_bf16x2(__uint_as_float(v[OFF + 6]), __uint_as_float(v[OFF + 7])));
+}
+
+// linattn_kv_kernel: one CTA per unit (image, pixel range), two CTAs per SM at C = 64 (one CTA's MMAs run under the other's epilogue).
+// K^T / V^T accumulators 64 columns each + ctx 128 = 256 TMEM columns.  Per tile t the epilogue warps first normalise tile t + 1 in
+// place (under the MMAs of tile t), then drain tile t.
 template <int C>
 struct KvCfg {
     static constexpr int SPANS = C / 64;
     static constexpr uint32_t W_BYTES = SPANS * SPAN_BYTES;          // one of Wk' / Wv' [128 rows][C]
     static constexpr uint32_t XSPAN_BYTES = KV_PX * 128;             // one 64-channel span of a 64-pixel x tile
     static constexpr uint32_t X_BYTES = SPANS * XSPAN_BYTES;
+    static constexpr int X_STAGES = 3;
     static constexpr uint32_t PV_BYTES = SPAN_BYTES;                 // [128 rows][64 px]
-    static constexpr uint32_t SMALL_BYTES = 3 * 512 + 5 * 512 + 128;
-    static constexpr int SMEM_BYTES = 2 * W_BYTES + 2 * X_BYTES + 2 * PV_BYTES + SMALL_BYTES + 1024;
+    static constexpr uint32_t SMALL_BYTES = 2 * 512 + 256;           // s_S [2][128], barriers
+    static constexpr int SMEM_BYTES = 2 * W_BYTES + X_STAGES * X_BYTES + 2 * PV_BYTES + SMALL_BYTES + 1024;
     static constexpr int CTAS_PER_SM = C == 64 ? 2 : 1;
 };
 constexpr int KV_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue: (TMEM lane quarter, 32-pixel half)
@@ -186,28 +181,24 @@ __global__ void __launch_bounds__(KV_THREADS, KvCfg<C>::CTAS_PER_SM)
 linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const KvArgs a) {
     using Cf = KvCfg<C>;
     constexpr int SPANS = Cf::SPANS;
+    constexpr int XS = Cf::X_STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
     uint8_t* sWk = smem;
     uint8_t* sWv = sWk + Cf::W_BYTES;
-    uint8_t* sX = sWv + Cf::W_BYTES;                 // 2 stages
-    uint8_t* sP = sX + 2 * Cf::X_BYTES;
+    uint8_t* sX = sWv + Cf::W_BYTES;                 // X_STAGES stages
+    uint8_t* sP = sX + XS * Cf::X_BYTES;
     uint8_t* sV = sP + Cf::PV_BYTES;
-    float* s_mu = reinterpret_cast<float*>(sV + Cf::PV_BYTES);   // [2][64] rstd * mean per pixel (double-buffered by tile parity)
-    float* s_rstd = s_mu + 2 * KV_PX;                // [2][64]
-    float* s_rl = s_rstd + 2 * KV_PX;                // [2][64] rstd * log2(e): the K path's multiplier, so an exponent is two FMAs
-    float* s_sk = s_rl + 2 * KV_PX;                  // [128]
-    float* s_sv = s_sk + 128;
-    float* s_shift = s_sv + 128;
-    float* s_S = s_shift + 128;                      // [2][128]
+    float* s_S = reinterpret_cast<float*>(sV + Cf::PV_BYTES);        // [2][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_S + 256);
     uint64_t* w_bar = bars;
-    uint64_t* x_full = bars + 1;                     // [2]
-    uint64_t* x_empty = bars + 3;                    // [2]
-    uint64_t* d_full = bars + 5;
-    uint64_t* pv_ready = bars + 6;
-    uint64_t* ctx_full = bars + 7;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* x_full = bars + 1;                     // [3] TMA -> normaliser
+    uint64_t* xn_full = bars + 4;                    // [3] normaliser -> MMA
+    uint64_t* x_empty = bars + 7;                    // [3] MMA done with the stage -> TMA
+    uint64_t* d_full = bars + 10;
+    uint64_t* pv_ready = bars + 11;
+    uint64_t* ctx_full = bars + 12;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -218,9 +209,9 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         ptx::tmem_relinquish();
     } else if (warp == 1 && lane == 0) {
         ptx::mbar_init(w_bar, 1);
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&x_full[i], 1); ptx::mbar_init(&x_empty[i], 1); }
+        for (int i = 0; i < XS; ++i) { ptx::mbar_init(&x_full[i], 1); ptx::mbar_init(&xn_full[i], 8); ptx::mbar_init(&x_empty[i], 1); }
         ptx::mbar_init(d_full, 1);
-        ptx::mbar_init(pv_ready, 256);
+        ptx::mbar_init(pv_ready, 8);
         ptx::mbar_init(ctx_full, 1);
         ptx::fence_mbar_init();
     }
@@ -248,8 +239,8 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
         __syncwarp();
         for (int t = 0; t < T; ++t) {
-            const int st = t & 1;
-            ptx::mbar_wait(&x_empty[st], ((t >> 1) & 1u) ^ 1u);
+            const int st = t % XS;
+            ptx::mbar_wait(&x_empty[st], ((t / XS) & 1u) ^ 1u);
             if (ptx::elect_one()) {
                 ptx::mbar_arrive_expect_tx(&x_full[st], Cf::X_BYTES);
                 for (int sp = 0; sp < SPANS; ++sp)
@@ -267,7 +258,7 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint64_t dV = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sV));
         ptx::mbar_wait(w_bar, 0);
         for (int t = 0; t <= T; ++t) {
-            if (t < T) ptx::mbar_wait(&x_full[t & 1], (t >> 1) & 1u);
+            if (t < T) ptx::mbar_wait(&xn_full[t % XS], (t / XS) & 1u);   // tile t normalised in place
             if (t > 0) ptx::mbar_wait(pv_ready, (t - 1) & 1u);     // epilogue t-1: D_K / D_V drained, P / V written
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
@@ -276,8 +267,8 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     for (int k = 0; k < 4; ++k)
                         ptx::umma_bf16(tmem_base + COL_CTX, dP + 2u * k, dV + 2u * k, idesc_ctx, (t > 1 || k != 0) ? 1u : 0u);
                 }
-                if (t < T) {                                        // K^T = Wk' x^T, V^T = Wv' x^T of tile t
-                    const uint64_t xoff = static_cast<uint64_t>(((t & 1) * Cf::X_BYTES) >> 4);
+                if (t < T) {                                        // K^T = Wk' z^T, V^T = Wv' z^T of tile t (z = normalised x)
+                    const uint64_t xoff = static_cast<uint64_t>(((t % XS) * Cf::X_BYTES) >> 4);
 #pragma unroll
                     for (int sp = 0; sp < SPANS; ++sp)
 #pragma unroll
@@ -307,52 +298,44 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int q = warp & 3;                         // TMEM lane quarter
         const int hcol = (warp - 2) >> 2;               // which 32 pixels of the tile
         const int r = q * 32 + lane;                    // d (K^T, ctx) / e (V^T) row
-        if (te < 128) {
-            s_sk[te] = a.rowsum[HD + te];
-            s_sv[te] = a.rowsum[2 * HD + te];
-            s_shift[te] = a.kshift[te];
-        }
-        named_bar_sync(1, 256);
         constexpr float LOG2E = 1.4426950408889634f;
-        // exp(k) = exp2(k * log2 e); negated per-row constants for the packed forms (k_chunk8 / v_chunk8)
-        const ptx::f32x2 NSK = ptx::dup2(-(s_sk[r] * LOG2E)), NSHIFT = ptx::dup2(-(s_shift[r] * LOG2E)), NSV = ptx::dup2(-s_sv[r]);
+        const ptx::f32x2 L2E = ptx::dup2(LOG2E), NSHIFT = ptx::dup2(-(a.kshift[r] * LOG2E));
         const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const int px0 = hcol * 32;
         ptx::f32x2 ssum2 = ptx::mk2(0.f, 0.f);
+        auto normalise = [&](int t) {                   // tile t: wait for the TMA, LayerNorm in place, hand the stage to the MMA warp
+            const int st = t % XS;
+            ptx::mbar_wait(&x_full[st], (t / XS) & 1u);
+            tile_normalize<C, 256, Cf::XSPAN_BYTES>(sX + st * Cf::X_BYTES, te, a.eps);
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&xn_full[st]);
+        };
+        normalise(0);
         for (int t = 0; t < T; ++t) {
-            const int st = t & 1;
-            ptx::mbar_wait(&x_full[st], (t >> 1) & 1u);          // x tile visible to this thread
-            // per-pixel LayerNorm statistics while the MMAs run; double-buffered by tile parity (a fast warp writes tile t + 1's
-            // while a slow one still reads tile t's)
-            float* mu_t = s_mu + st * KV_PX;
-            float* rs_t = s_rstd + st * KV_PX;
-            float* rl_t = s_rl + st * KV_PX;
-            tile_stats<C, 256, Cf::XSPAN_BYTES>(sX + st * Cf::X_BYTES, te, a.eps, mu_t, rs_t, rl_t);
+            if (t + 1 < T) normalise(t + 1);                      // under the MMAs of tile t
             ptx::mbar_wait(d_full, t & 1u);                       // K^T / V^T of tile t ready (and P / V of tile t-1 consumed)
             ptx::tc_fence_after();
-            named_bar_sync(1, 256);
-            if (te == 0) ptx::mbar_arrive(&x_empty[st]);          // MMAs done (d_full) and statistics read: stage free
+            if (te == 0) ptx::mbar_arrive(&x_empty[t % XS]);      // the MMAs have read the stage
             uint32_t v[32];
             ptx::tmem_ld32(tlane + COL_K + px0, v);
             ptx::tmem_ld_wait();
-            // the denominator sums the unrounded p: the bf16 rounding of the MMA operand is unbiased, over n >= 1024 pixels
-            // the two sums agree to ~1e-5
-            *reinterpret_cast<uint4*>(sP + sw_off(r, hcol * 4 + 0)) = k_chunk8<0>(v, mu_t + px0, rl_t + px0, NSK, NSHIFT, ssum2);
-            *reinterpret_cast<uint4*>(sP + sw_off(r, hcol * 4 + 1)) = k_chunk8<8>(v, mu_t + px0 + 8, rl_t + px0 + 8, NSK, NSHIFT, ssum2);
-            *reinterpret_cast<uint4*>(sP + sw_off(r, hcol * 4 + 2)) = k_chunk8<16>(v, mu_t + px0 + 16, rl_t + px0 + 16, NSK, NSHIFT, ssum2);
-            *reinterpret_cast<uint4*>(sP + sw_off(r, hcol * 4 + 3)) = k_chunk8<24>(v, mu_t + px0 + 24, rl_t + px0 + 24, NSK, NSHIFT, ssum2);
+            *reinterpret_cast<uint4*>(sP + sw_off(r, hcol * 4 + 0)) = k_chunk8<0>(v, L2E, NSHIFT, ssum2);
+            *reinterpret_cast<uint4*>(sP + sw_off(r, hcol * 4 + 1)) = k_chunk8<8>(v, L2E, NSHIFT, ssum2);
+            *reinterpret_cast<uint4*>(sP + sw_off(r, hcol * 4 + 2)) = k_chunk8<16>(v, L2E, NSHIFT, ssum2);
+            *reinterpret_cast<uint4*>(sP + sw_off(r, hcol * 4 + 3)) = k_chunk8<24>(v, L2E, NSHIFT, ssum2);
             ptx::tmem_ld32(tlane + COL_V + px0, v);
             ptx::tmem_ld_wait();
-            *reinterpret_cast<uint4*>(sV + sw_off(r, hcol * 4 + 0)) = v_chunk8<0>(v, mu_t + px0, rs_t + px0, NSV);
-            *reinterpret_cast<uint4*>(sV + sw_off(r, hcol * 4 + 1)) = v_chunk8<8>(v, mu_t + px0 + 8, rs_t + px0 + 8, NSV);
-            *reinterpret_cast<uint4*>(sV + sw_off(r, hcol * 4 + 2)) = v_chunk8<16>(v, mu_t + px0 + 16, rs_t + px0 + 16, NSV);
-            *reinterpret_cast<uint4*>(sV + sw_off(r, hcol * 4 + 3)) = v_chunk8<24>(v, mu_t + px0 + 24, rs_t + px0 + 24, NSV);
+            *reinterpret_cast<uint4*>(sV + sw_off(r, hcol * 4 + 0)) = v_chunk8<0>(v);
+            *reinterpret_cast<uint4*>(sV + sw_off(r, hcol * 4 + 1)) = v_chunk8<8>(v);
+            *reinterpret_cast<uint4*>(sV + sw_off(r, hcol * 4 + 2)) = v_chunk8<16>(v);
+            *reinterpret_cast<uint4*>(sV + sw_off(r, hcol * 4 + 3)) = v_chunk8<24>(v);
             ptx::tc_fence_before();
             ptx::fence_proxy_async_smem();
-            ptx::mbar_arrive(pv_ready);
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(pv_ready);
         }
-        const float ssum = ptx::lo(ssum2) + ptx::hi(ssum2);
-        s_S[hcol * 128 + r] = ssum;
+        s_S[hcol * 128 + r] = ptx::lo(ssum2) + ptx::hi(ssum2);
         named_bar_sync(1, 256);
         if (hcol == 0) {
             a.s_part[static_cast<size_t>(unit) * HD + r] = s_S[r] + s_S[128 + r];
@@ -374,26 +357,31 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------ kernel 1, pipelined form
-// linattn_kv2_kernel: the same math as linattn_kv_kernel, restructured so that the MMAs of tile g + 1 run while the epilogue warps
-// work on tile g: K^T / V^T accumulators and the P / V shared-memory tiles are double-buffered, the CTA is
-// persistent over its units (image, pixel range) -- weights and TMEM are set up once -- and sixteen epilogue warps (TMEM lane
-// quarter x 16-pixel column quarter) give the SM the warps that two co-resident CTAs of the first form provided.
-//   TMEM (512 columns, one CTA per SM): [K0 | V0 | K1 | V1] 4 x 64, ctx 128 at column 256.
-//   barriers: x_full / x_empty[3] (TMA <-> MMA + statistics), kv_full / kv_empty[2] (accumulators), pv_full / pv_empty[2] (P / V
-//   tiles), ctx_full / ctx_empty (context accumulator of one unit).  g counts tiles across units (buffer = g & 1, x stage = g % 3).
+// linattn_kv2_kernel: the same math, one persistent CTA per SM walking its units, as three decoupled pipelines that only meet in
+// mbarriers: eight LayerNorm warps normalise the x stages in place (two groups on alternating tiles at C = 64), the MMA warp runs one
+// tile ahead into double-buffered K^T / V^T accumulators, sixteen epilogue warps (TMEM lane quarter x 16-pixel column quarter) drain
+// tile g into double-buffered P / V tiles while the MMAs of tile g + 1 run; weights and TMEM are set up once per CTA.  (In the
+// one-CTA-per-unit form every tile is a serial chain normalise -> MMA -> drain whose latencies only the second CTA of the SM hides.)
+//   TMEM (512 columns): [K0 | V0 | K1 | V1] 4 x 64, ctx 128 at column 256.
+//   barriers: x_full / xn_full / x_empty[3] (TMA -> normaliser -> MMA -> TMA), kv_full / kv_empty[2] (accumulators), pv_full /
+//   pv_empty[2] (P / V tiles), ctx_full / ctx_empty (context accumulator of one unit).  g counts tiles across units.
 template <int C>
 struct Kv2Cfg {
     static constexpr int SPANS = C / 64;
     static constexpr uint32_t W_BYTES = SPANS * SPAN_BYTES;
     static constexpr uint32_t XSPAN_BYTES = KV_PX * 128;
     static constexpr uint32_t X_BYTES = SPANS * XSPAN_BYTES;
-    static constexpr int X_STAGES = 3;
+    static constexpr int X_STAGES = 4;
+    static constexpr int NORM_GROUPS = C == 64 ? 2 : 1;              // normaliser warp groups, alternating tiles (C = 128: one group,
+                                                                     // four threads per pixel, so that a row share fits the registers)
     static constexpr uint32_t PV_BYTES = SPAN_BYTES;                 // [128 rows][64 px]
-    static constexpr uint32_t SMALL_BYTES = 2 * 3 * 256 + 3 * 512 + 4 * 512 + 256;
+    static constexpr uint32_t SMALL_BYTES = 8 * 512 + 256;           // s_S [2][4][128] (by unit parity), barriers
     static constexpr int SMEM_BYTES = 2 * W_BYTES + X_STAGES * X_BYTES + 4 * PV_BYTES + SMALL_BYTES + 1024;
 };
 constexpr int KV2_EPI_WARPS = 16;
-constexpr int KV2_THREADS = 64 + KV2_EPI_WARPS * 32;      // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
+constexpr int KV2_NORM_WARPS = 8;
+constexpr int KV2_CTX_WARP = 2 + KV2_EPI_WARPS + KV2_NORM_WARPS;            // warp 26: issues the context MMAs
+constexpr int KV2_THREADS = (KV2_CTX_WARP + 1) * 32;      // warp 0 TMA, warp 1 K^T / V^T MMAs, 2..17 epilogue, 18..25 LayerNorm, 26 context MMAs
 
 template <int C>
 __global__ void __launch_bounds__(KV2_THREADS, 1)
@@ -408,24 +396,19 @@ linattn_kv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     uint8_t* sX = sWv + Cf::W_BYTES;                 // X_STAGES stages
     uint8_t* sP = sX + XS * Cf::X_BYTES;             // [2]
     uint8_t* sV = sP + 2 * Cf::PV_BYTES;             // [2]
-    float* s_mu = reinterpret_cast<float*>(sV + 2 * Cf::PV_BYTES);   // [2][64] rstd * mean per pixel (double-buffered by tile parity)
-    float* s_rstd = s_mu + 2 * KV_PX;                // [2][64]
-    float* s_rl = s_rstd + 2 * KV_PX;                // [2][64] rstd * log2(e)
-    float* s_sk = s_rl + 2 * KV_PX;                  // [128]
-    float* s_sv = s_sk + 128;
-    float* s_shift = s_sv + 128;
-    float* s_S = s_shift + 128;                      // [4][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_S + 512);
+    float* s_S = reinterpret_cast<float*>(sV + 2 * Cf::PV_BYTES);    // [2][4][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_S + 1024);
     uint64_t* w_bar = bars;
-    uint64_t* x_full = bars + 1;                     // [3]
-    uint64_t* x_empty = bars + 4;                    // [3]
-    uint64_t* kv_full = bars + 7;                    // [2]
-    uint64_t* kv_empty = bars + 9;                   // [2]
-    uint64_t* pv_full = bars + 11;                   // [2]
-    uint64_t* pv_empty = bars + 13;                  // [2]
-    uint64_t* ctx_full = bars + 15;
-    uint64_t* ctx_empty = bars + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    uint64_t* x_full = bars + 1;                     // [4]
+    uint64_t* xn_full = bars + 5;                    // [4]
+    uint64_t* x_empty = bars + 9;                    // [4]
+    uint64_t* kv_full = bars + 13;                   // [2]
+    uint64_t* kv_empty = bars + 15;                  // [2]
+    uint64_t* pv_full = bars + 17;                   // [2]
+    uint64_t* pv_empty = bars + 19;                  // [2]
+    uint64_t* ctx_full = bars + 21;
+    uint64_t* ctx_empty = bars + 22;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -436,11 +419,15 @@ linattn_kv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         ptx::tmem_relinquish();
     } else if (warp == 1 && lane == 0) {
         ptx::mbar_init(w_bar, 1);
-        for (int i = 0; i < XS; ++i) { ptx::mbar_init(&x_full[i], 1); ptx::mbar_init(&x_empty[i], 1); }
+        for (int i = 0; i < XS; ++i) {
+            ptx::mbar_init(&x_full[i], 1);
+            ptx::mbar_init(&xn_full[i], KV2_NORM_WARPS / Cf::NORM_GROUPS);
+            ptx::mbar_init(&x_empty[i], 1);
+        }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&kv_full[i], 1);
-            ptx::mbar_init(&kv_empty[i], KV2_EPI_WARPS);
-            ptx::mbar_init(&pv_full[i], KV2_EPI_WARPS);
+            ptx::mbar_init(&kv_empty[i], KV2_EPI_WARPS / 2);     // the eight warps of epilogue group i
+            ptx::mbar_init(&pv_full[i], KV2_EPI_WARPS / 2);
             ptx::mbar_init(&pv_empty[i], 1);
         }
         ptx::mbar_init(ctx_full, 1);
@@ -455,7 +442,8 @@ linattn_kv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     constexpr uint32_t COL_CTX = 256;
 
     const int T = a.tiles_per_unit;                  // 64-pixel tiles per unit
-    // units of this CTA: blockIdx.x, + gridDim.x, ...
+    const int my_units = units > static_cast<int>(blockIdx.x) ? (units - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int G = my_units * T;                      // tiles of this CTA: g = (unit index of this CTA) * T + t
     if (warp == 0) {
         if (ptx::elect_one()) {
             ptx::mbar_arrive_expect_tx(w_bar, 2 * Cf::W_BYTES);
@@ -484,133 +472,138 @@ linattn_kv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc_kv = ptx::make_idesc_bf16(128, KV_PX);
-        constexpr uint32_t idesc_ctx = ptx::make_idesc_bf16(128, 128);
         const uint64_t dWk = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sWk));
         const uint64_t dWv = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sWv));
         const uint64_t dX = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sX));
-        const uint64_t dP = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sP));
-        const uint64_t dV = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sV));
         ptx::mbar_wait(w_bar, 0);
-        int g = 0, u = 0;
-        auto issue_ctx = [&](int gp, bool first, bool last) {       // ctx += P V^T of tile gp (its P / V are in buffer gp & 1)
-            const int bb = gp & 1;
-            ptx::mbar_wait(&pv_full[bb], (gp >> 1) & 1u);
+        for (int g = 0; g < G; ++g) {                // K^T / V^T of tile g into accumulator pair g & 1, as far ahead as the buffers allow
+            const int st = g % XS, bb = g & 1;
+            ptx::mbar_wait(&xn_full[st], (g / XS) & 1u);         // tile g normalised in place
+            ptx::mbar_wait(&kv_empty[bb], ((g >> 1) & 1u) ^ 1u);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
-                const uint64_t off = static_cast<uint64_t>((bb * Cf::PV_BYTES) >> 4);
+                const uint64_t xoff = static_cast<uint64_t>((st * Cf::X_BYTES) >> 4);
+                const uint32_t colk = tmem_base + bb * 128, colv = colk + 64;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    ptx::umma_bf16(tmem_base + COL_CTX, dP + off + 2u * k, dV + off + 2u * k, idesc_ctx, (!first || k != 0) ? 1u : 0u);
-                ptx::umma_commit(&pv_empty[bb]);
-                if (last) ptx::umma_commit(ctx_full);
+                for (int sp = 0; sp < SPANS; ++sp)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t offw = static_cast<uint64_t>((sp * SPAN_BYTES) >> 4) + 2u * k;
+                        const uint64_t offx = static_cast<uint64_t>((sp * Cf::XSPAN_BYTES) >> 4) + 2u * k;
+                        ptx::umma_bf16(colk, dWk + offw, dX + xoff + offx, idesc_kv, (sp | k) != 0 ? 1u : 0u);
+                    }
+#pragma unroll
+                for (int sp = 0; sp < SPANS; ++sp)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t offw = static_cast<uint64_t>((sp * SPAN_BYTES) >> 4) + 2u * k;
+                        const uint64_t offx = static_cast<uint64_t>((sp * Cf::XSPAN_BYTES) >> 4) + 2u * k;
+                        ptx::umma_bf16(colv, dWv + offw, dX + xoff + offx, idesc_kv, (sp | k) != 0 ? 1u : 0u);
+                    }
+                ptx::umma_commit(&kv_full[bb]);
+                ptx::umma_commit(&x_empty[st]);                  // the stage may be refilled once these MMAs have read it
             }
             __syncwarp();
-        };
-        for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++u) {
+        }
+    } else if (warp == KV2_CTX_WARP) {
+        // ------------------------------------------------------------------ context MMAs: ctx += P V^T of tile g (its own issuing warp,
+        // so that waiting for an epilogue never holds back the K^T / V^T MMAs of the tiles behind it)
+        constexpr uint32_t idesc_ctx = ptx::make_idesc_bf16(128, 128);
+        const uint64_t dP = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sP));
+        const uint64_t dV = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sV));
+        int g = 0;
+        for (int u = 0; u < my_units; ++u) {
             for (int t = 0; t < T; ++t, ++g) {
-                const int st = g % XS, bb = g & 1;
-                ptx::mbar_wait(&x_full[st], (g / XS) & 1u);
-                ptx::mbar_wait(&kv_empty[bb], ((g >> 1) & 1u) ^ 1u);
+                const int bb = g & 1;
+                ptx::mbar_wait(&pv_full[bb], (g >> 1) & 1u);
+                if (t == 0) ptx::mbar_wait(ctx_empty, (u & 1u) ^ 1u);   // the previous unit's context has been read out
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
-                    const uint64_t xoff = static_cast<uint64_t>((st * Cf::X_BYTES) >> 4);
-                    const uint32_t colk = tmem_base + bb * 128, colv = colk + 64;
+                    const uint64_t off = static_cast<uint64_t>((bb * Cf::PV_BYTES) >> 4);
 #pragma unroll
-                    for (int sp = 0; sp < SPANS; ++sp)
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t offw = static_cast<uint64_t>((sp * SPAN_BYTES) >> 4) + 2u * k;
-                            const uint64_t offx = static_cast<uint64_t>((sp * Cf::XSPAN_BYTES) >> 4) + 2u * k;
-                            ptx::umma_bf16(colk, dWk + offw, dX + xoff + offx, idesc_kv, (sp | k) != 0 ? 1u : 0u);
-                        }
-#pragma unroll
-                    for (int sp = 0; sp < SPANS; ++sp)
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t offw = static_cast<uint64_t>((sp * SPAN_BYTES) >> 4) + 2u * k;
-                            const uint64_t offx = static_cast<uint64_t>((sp * Cf::XSPAN_BYTES) >> 4) + 2u * k;
-                            ptx::umma_bf16(colv, dWv + offw, dX + xoff + offx, idesc_kv, (sp | k) != 0 ? 1u : 0u);
-                        }
-                    ptx::umma_commit(&kv_full[bb]);
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_bf16(tmem_base + COL_CTX, dP + off + 2u * k, dV + off + 2u * k, idesc_ctx, (t | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(&pv_empty[bb]);
+                    if (t == T - 1) ptx::umma_commit(ctx_full);
                 }
                 __syncwarp();
-                if (t == 1) {                        // the unit's first context MMA overwrites the accumulator: the previous unit's
-                    ptx::mbar_wait(ctx_empty, (u & 1u) ^ 1u);       // context must have been read out
-                    ptx::tc_fence_after();
-                }
-                if (t >= 1) issue_ctx(g - 1, t == 1, false);
             }
-            if (T == 1) {
-                ptx::mbar_wait(ctx_empty, (u & 1u) ^ 1u);
-                ptx::tc_fence_after();
-            }
-            issue_ctx(g - 1, T == 1, true);
+        }
+    } else if (warp >= 2 + KV2_EPI_WARPS) {
+        // ------------------------------------------------------------------ LayerNorm warps: tile g of group (g % NORM_GROUPS), in place
+        constexpr int NG = Cf::NORM_GROUPS;
+        constexpr int NT = KV2_NORM_WARPS * 32 / NG;    // threads per tile: 128 (two per pixel) or 256 (four per pixel)
+        const int wn = warp - 2 - KV2_EPI_WARPS;
+        const int grp = wn / (KV2_NORM_WARPS / NG);
+        const int tn = (wn % (KV2_NORM_WARPS / NG)) * 32 + lane;
+        for (int g = grp; g < G; g += NG) {
+            const int st = g % XS;
+            ptx::mbar_wait(&x_full[st], (g / XS) & 1u);
+            tile_normalize<C, NT, Cf::XSPAN_BYTES>(sX + st * Cf::X_BYTES, tn, a.eps);
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&xn_full[st]);
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: 16 warps, thread = (row, 16-pixel quarter)
-        const int te = (warp - 2) * 32 + lane;          // 0..511
+        // ------------------------------------------------------------------ epilogue: two groups of eight warps on alternating tiles
+        // (group = tile parity = accumulator / P-V buffer index; T is even).  Thread = (row, 32-pixel half).
+        const int wd = warp - 2;
+        const int grp = wd >> 3;
         const int q = warp & 3;                         // TMEM lane quarter
-        const int cq = (warp - 2) >> 2;                 // which 16 pixels of the tile
+        const int half = (wd >> 2) & 1;                 // which 32 pixels of the tile
         const int r = q * 32 + lane;                    // d (K^T, ctx) / e (V^T) row
-        if (te < 128) {
-            s_sk[te] = a.rowsum[HD + te];
-            s_sv[te] = a.rowsum[2 * HD + te];
-            s_shift[te] = a.kshift[te];
-        }
-        named_bar_sync(1, KV2_EPI_WARPS * 32);
         constexpr float LOG2E = 1.4426950408889634f;
-        const ptx::f32x2 NSK = ptx::dup2(-(s_sk[r] * LOG2E)), NSHIFT = ptx::dup2(-(s_shift[r] * LOG2E)), NSV = ptx::dup2(-s_sv[r]);
-        const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        const int px0 = cq * 16;
+        const ptx::f32x2 L2E = ptx::dup2(LOG2E), NSHIFT = ptx::dup2(-(a.kshift[r] * LOG2E));
+        const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + grp * 128;
+        uint8_t* pb = sP + grp * Cf::PV_BYTES;
+        uint8_t* vb = sV + grp * Cf::PV_BYTES;
         ptx::grid_dep_wait();
-        int g = 0, u = 0;
+        int u = 0;
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++u) {
             ptx::f32x2 ssum2 = ptx::mk2(0.f, 0.f);
-            for (int t = 0; t < T; ++t, ++g) {
-                const int st = g % XS, bb = g & 1;
-                ptx::mbar_wait(&x_full[st], (g / XS) & 1u);          // x tile visible to this thread
-                // per-pixel LayerNorm statistics while the MMAs run, eight threads per pixel
-                tile_stats<C, KV2_EPI_WARPS * 32, Cf::XSPAN_BYTES>(sX + st * Cf::X_BYTES, te, a.eps, s_mu + bb * KV_PX,
-                                                                   s_rstd + bb * KV_PX, s_rl + bb * KV_PX);
-                ptx::mbar_wait(&kv_full[bb], (g >> 1) & 1u);         // K^T / V^T of tile g ready
+            for (int t = grp; t < T; t += 2) {
+                const uint32_t n = static_cast<uint32_t>(u * T + t) >> 1;     // uses of this group's buffers so far
+                ptx::mbar_wait(&kv_full[grp], n & 1u);               // K^T / V^T of the tile ready
                 ptx::tc_fence_after();
-                named_bar_sync(1, KV2_EPI_WARPS * 32);
-                if (te == 0) ptx::mbar_arrive(&x_empty[st]);          // MMAs done (kv_full) and statistics read: stage free
-                const float* mu_b = s_mu + bb * KV_PX + px0;
-                const float* rs_b = s_rstd + bb * KV_PX + px0;
-                const float* rl_b = s_rl + bb * KV_PX + px0;
-                uint32_t vk[16], vv[16];
-                ptx::tmem_ld16(tlane + bb * 128 + px0, vk);
-                ptx::tmem_ld16(tlane + bb * 128 + 64 + px0, vv);
+                // all TMEM reads first, so that the accumulators go back to the MMA warp (tile g + 2) before the exponentials start:
+                // V^T (only packed: 32 -> 16 registers), then K^T
+                uint32_t vt[32];
+                ptx::tmem_ld32(tlane + 64 + half * 32, vt);
+                ptx::tmem_ld_wait();
+                const uint4 v0 = v_chunk8<0>(vt), v1 = v_chunk8<8>(vt), v2 = v_chunk8<16>(vt), v3 = v_chunk8<24>(vt);
+                ptx::tmem_ld32(tlane + half * 32, vt);
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&kv_empty[bb]);       // accumulators drained: tile g + 2's MMAs may overwrite them
-                const uint4 p0 = k_chunk8<0>(vk, mu_b, rl_b, NSK, NSHIFT, ssum2);
-                const uint4 p1 = k_chunk8<8>(vk, mu_b + 8, rl_b + 8, NSK, NSHIFT, ssum2);
-                const uint4 v0 = v_chunk8<0>(vv, mu_b, rs_b, NSV);
-                const uint4 v1 = v_chunk8<8>(vv, mu_b + 8, rs_b + 8, NSV);
-                ptx::mbar_wait(&pv_empty[bb], ((g >> 1) & 1u) ^ 1u); // the context MMA of tile g - 2 has consumed this P / V buffer
-                uint8_t* pb = sP + bb * Cf::PV_BYTES;
-                uint8_t* vb = sV + bb * Cf::PV_BYTES;
-                *reinterpret_cast<uint4*>(pb + sw_off(r, cq * 2)) = p0;
-                *reinterpret_cast<uint4*>(pb + sw_off(r, cq * 2 + 1)) = p1;
-                *reinterpret_cast<uint4*>(vb + sw_off(r, cq * 2)) = v0;
-                *reinterpret_cast<uint4*>(vb + sw_off(r, cq * 2 + 1)) = v1;
+                if (lane == 0) ptx::mbar_arrive(&kv_empty[grp]);
+                const uint4 p0 = k_chunk8<0>(vt, L2E, NSHIFT, ssum2);
+                const uint4 p1 = k_chunk8<8>(vt, L2E, NSHIFT, ssum2);
+                const uint4 p2 = k_chunk8<16>(vt, L2E, NSHIFT, ssum2);
+                const uint4 p3 = k_chunk8<24>(vt, L2E, NSHIFT, ssum2);
+                ptx::mbar_wait(&pv_empty[grp], (n & 1u) ^ 1u);       // the context MMA two tiles back has consumed P / V
+                const int ch = half * 4;
+                *reinterpret_cast<uint4*>(vb + sw_off(r, ch)) = v0;
+                *reinterpret_cast<uint4*>(vb + sw_off(r, ch + 1)) = v1;
+                *reinterpret_cast<uint4*>(vb + sw_off(r, ch + 2)) = v2;
+                *reinterpret_cast<uint4*>(vb + sw_off(r, ch + 3)) = v3;
+                *reinterpret_cast<uint4*>(pb + sw_off(r, ch)) = p0;
+                *reinterpret_cast<uint4*>(pb + sw_off(r, ch + 1)) = p1;
+                *reinterpret_cast<uint4*>(pb + sw_off(r, ch + 2)) = p2;
+                *reinterpret_cast<uint4*>(pb + sw_off(r, ch + 3)) = p3;
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&pv_full[bb]);
+                if (lane == 0) ptx::mbar_arrive(&pv_full[grp]);
             }
-            const float ssum = ptx::lo(ssum2) + ptx::hi(ssum2);
             // ---- end of the unit: softmax denominators and the context accumulator
-            s_S[cq * 128 + r] = ssum;
+            float* sS = s_S + (u & 1) * 512;            // by unit parity: the slots are rewritten two units on, behind the next barrier
+            sS[(grp * 2 + half) * 128 + r] = ptx::lo(ssum2) + ptx::hi(ssum2);
             named_bar_sync(1, KV2_EPI_WARPS * 32);
-            if (cq == 0) {
-                a.s_part[static_cast<size_t>(unit) * HD + r] = (s_S[r] + s_S[128 + r]) + (s_S[256 + r] + s_S[384 + r]);
+            if (wd < 4) {
+                a.s_part[static_cast<size_t>(unit) * HD + r] = (sS[r] + sS[128 + r]) + (sS[256 + r] + sS[384 + r]);
                 ptx::mbar_wait(ctx_full, u & 1u);
                 ptx::tc_fence_after();
                 uint32_t v[32];
-                ptx::tmem_ld32(tlane + COL_CTX + q * 32, v);     // row d = q*32 + lane belongs to head q: columns e of head q
+                ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + COL_CTX + q * 32, v);   // row d of head q: columns e of head q
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -621,7 +614,6 @@ linattn_kv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     dst[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                                               __uint_as_float(v[j + 3]));
             }
-            named_bar_sync(1, KV2_EPI_WARPS * 32);               // s_S may be rewritten by the next unit
         }
     }
     ptx::tc_fence_before();
@@ -630,72 +622,81 @@ linattn_kv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------ kernel 2: mix
-__global__ void __launch_bounds__(128)
+// One CTA per image, 256 threads, two CTAs per SM: the whole grid (B <= 296 images) is one wave.  Phase 1: the image's partial
+// contexts ([parts][128][32] fp32, contiguous) are summed with coalesced 16-byte loads (thread i owns float4 i + 256 k of the 16 KiB
+// block; the loads of four parts are in flight together), normalised and parked in shared memory.  Phase 2: thread (hd = t % 128,
+// group t / 128) computes C / 2 output channels of column hd; Wo is read through warp-uniform __ldg (one transaction per warp).
+// The first form (grid (B, 4), a thread per context ROW) read every partial four times with 128-byte-strided loads and ran as
+// 1.4 waves: 24 us per launch, five launches a step (profiles/r02_notes.md 10).
+constexpr int MIX_THREADS = 256;
+__global__ void __launch_bounds__(MIX_THREADS, 2)
 linattn_mix_kernel(const float* __restrict__ ctx_part, const float* __restrict__ s_part, const float* __restrict__ wo,
                    bf16* __restrict__ mb, int parts, int C, float inv_n_scale) {
-    __shared__ __align__(16) float s_wo[32 * HD];   // this block's rows of Wo (C / 4 <= 32 output channels)
+    __shared__ float s_ctx[HD][33];
     ptx::grid_dep_launch();     // PDL (ptx.cuh): the successor may be scheduled; then wait for the predecessor grid and its memory
     ptx::grid_dep_wait();
     const int b = blockIdx.x;
-    const int t = threadIdx.x;          // hd = h*32 + d
-    const int h = t >> 5;
-    const int per = C / gridDim.y;      // output channels of this block (a multiple of 4)
-    {   // coalesced copy of Wo[blockIdx.y * per .. +per][128]; its latency overlaps the partial loads below
-        const float4* src = reinterpret_cast<const float4*>(wo + static_cast<size_t>(blockIdx.y) * per * HD);
-        for (int i = t; i < per * HD / 4; i += 128) reinterpret_cast<float4*>(s_wo)[i] = __ldg(src + i);
-    }
-    // all partial loads of this thread (<= 8 parts x (S + eight 16-byte ctx chunks)) are issued before any is consumed
-    float S = 0.f;
-    float4 acc4[8];
+    const int t = threadIdx.x;
+    {
+        const float4* base = reinterpret_cast<const float4*>(ctx_part + static_cast<size_t>(b) * parts * HD * 32);
+        const float* sbase = s_part + static_cast<size_t>(b) * parts * HD;
+        float4 acc[4];
+        float S[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float sp[8];
+        for (int k = 0; k < 4; ++k) { acc[k] = make_float4(0.f, 0.f, 0.f, 0.f); S[k] = 0.f; }
+        for (int p0 = 0; p0 < parts; p0 += 4) {            // parts in a fixed order: bit-reproducible
+            float4 v[4][4];
+            float sv[4][4];
 #pragma unroll
-    for (int p = 0; p < 8; ++p) sp[p] = p < parts ? __ldg(s_part + (static_cast<size_t>(b) * parts + p) * HD + t) : 0.f;
+            for (int pp = 0; pp < 4; ++pp) {
+                const bool on = p0 + pp < parts;
+                const int p = on ? p0 + pp : p0;
 #pragma unroll
-    for (int p0 = 0; p0 < 8; p0 += 2) {
-        float4 v[2][8];
+                for (int k = 0; k < 4; ++k) {
+                    const int f = t + k * MIX_THREADS;     // float4 index inside one [128][32] block: row f >> 3, columns (f & 7) * 4 ..
+                    v[pp][k] = on ? __ldg(base + static_cast<size_t>(p) * (HD * 8) + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    sv[pp][k] = on ? __ldg(sbase + p * HD + (f >> 3)) : 0.f;
+                }
+            }
 #pragma unroll
-        for (int pp = 0; pp < 2; ++pp) {
-            const int p = p0 + pp;
-            const float4* src = reinterpret_cast<const float4*>(ctx_part + ((static_cast<size_t>(b) * parts + (p < parts ? p : 0)) * HD + t) * 32);
+            for (int pp = 0; pp < 4; ++pp)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[pp][j] = p < parts ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < 4; ++k) {
+                    acc[k].x += v[pp][k].x; acc[k].y += v[pp][k].y; acc[k].z += v[pp][k].z; acc[k].w += v[pp][k].w;
+                    S[k] += sv[pp][k];
+                }
         }
 #pragma unroll
-        for (int pp = 0; pp < 2; ++pp)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                acc4[j].x += v[pp][j].x; acc4[j].y += v[pp][j].y; acc4[j].z += v[pp][j].z; acc4[j].w += v[pp][j].w;
-            }
+        for (int k = 0; k < 4; ++k) {
+            const int f = t + k * MIX_THREADS;
+            const float norm = inv_n_scale / S[k];
+            float* dst = &s_ctx[f >> 3][(f & 7) * 4];
+            dst[0] = acc[k].x * norm; dst[1] = acc[k].y * norm; dst[2] = acc[k].z * norm; dst[3] = acc[k].w * norm;
+        }
     }
-#pragma unroll
-    for (int p = 0; p < 8; ++p) S += sp[p];
-    const float norm = inv_n_scale / S;
-    // row hd = t of the normalised context stays in this thread's registers (each thread only ever needs its own row)
+    __syncthreads();
+    const int hd = t & (HD - 1);
+    const int h = hd >> 5;
+    const int per = C >> 1;                                // output channels of this thread group (a multiple of 4)
+    const int co0 = (t >> 7) * per;
     float c[32];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        c[4 * j] = acc4[j].x * norm; c[4 * j + 1] = acc4[j].y * norm;
-        c[4 * j + 2] = acc4[j].z * norm; c[4 * j + 3] = acc4[j].w * norm;
-    }
-    __syncthreads();                    // s_wo complete
-    // four output channels at a time: four independent FMA chains (one chain per channel left the kernel issue-latency bound
-    // at 0.24 IPC per scheduler, 27 us per launch: profiles/r02_notes.md 10); the sum order inside a channel is unchanged
+    for (int e = 0; e < 32; ++e) c[e] = s_ctx[hd][e];
+    // four output channels at a time: four independent FMA chains; the sum order inside a channel is e = 0 .. 31
     for (int cl = 0; cl < per; cl += 4) {
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const float4 w4 = *reinterpret_cast<const float4*>(s_wo + (cl + u) * HD + h * 32 + 4 * e);   // broadcast reads
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(wo + static_cast<size_t>(co0 + cl + u) * HD + h * 32 + 4 * e));
                 acc[u] = fmaf(w4.x, c[4 * e], acc[u]); acc[u] = fmaf(w4.y, c[4 * e + 1], acc[u]);
                 acc[u] = fmaf(w4.z, c[4 * e + 2], acc[u]); acc[u] = fmaf(w4.w, c[4 * e + 3], acc[u]);
             }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-            mb[(static_cast<size_t>(b) * C + blockIdx.y * per + cl + u) * HD + t] = __float2bfloat16(acc[u]);
+            mb[(static_cast<size_t>(b) * C + co0 + cl + u) * HD + hd] = __float2bfloat16(acc[u]);
     }
 }
 
@@ -1039,6 +1040,369 @@ linattn_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     if (warp == 0) ptx::tmem_dealloc(tmem_base, 256);
 }
 
+// ------------------------------------------------------------------------------------------------ kernel 3, pipelined form (C = 64)
+// linattn_out2_kernel: the same math as linattn_out_kernel as five decoupled pipelines inside one persistent CTA per SM, meeting only
+// in mbarriers, so that no role's latency chain is on another's critical path (the first form runs LayerNorm statistics -> MMA ->
+// softmax -> MMA -> LayerNorm -> store of a tile back to back in the same eight warps, and only the second CTA of the SM fills the gaps):
+//   warp 0        TMA: x tiles (3 stages; a stage doubles as the output staging buffer) and the tile's image matrix Mb (2 buffers)
+//   warps 19..26  LayerNorm of the tile, two threads per pixel row, written as bf16 z = LN(x) / gain into a second buffer (2 buffers):
+//                 Q = z Wq'^T then needs no per-row correction, and x itself stays intact for the residual
+//   warp 1        MMA 1: Q[i & 1] = z Wq'^T                (TMEM columns 0 / 128)
+//   warps 3..10   softmax over each head's 32 columns of Q (thread = pixel row, two heads) -> bf16 A2[i & 1]
+//   warp 2        MMA 2: Y[i & 1] = A2 Mb^T                (TMEM columns 256 / 320)
+//   warps 11..18  + bias, LayerNorm g2, + x, in place into the x stage -> TMA store (thread = pixel row, half of the channels)
+constexpr int OUT2_C = 64;
+struct Out2Cfg {
+    static constexpr uint32_t WQ_BYTES = SPAN_BYTES;
+    static constexpr uint32_t X_BYTES = SPAN_BYTES;                   // one stage: [128 px][64 ch] bf16
+    static constexpr int X_STAGES = 3;
+    static constexpr uint32_t MB_SPAN = OUT2_C * 128;                 // one 64-wide K span of Mb [C rows]
+    static constexpr uint32_t MB_BYTES = 2 * MB_SPAN;
+    static constexpr uint32_t A2_BYTES = 2 * SPAN_BYTES;
+    static constexpr uint32_t SMALL_BYTES = 2 * 4 * OUT2_C + 2048 + 256;     // bo, g2, two [2][128] exchange slots, barriers
+    static constexpr int SMEM_BYTES = WQ_BYTES + X_STAGES * X_BYTES + 2 * X_BYTES + 2 * MB_BYTES + 2 * A2_BYTES + SMALL_BYTES + 1024;
+};
+constexpr int OUT2_SM_WARP0 = 3, OUT2_LN_WARP0 = 11, OUT2_NORM_WARP0 = 19;
+constexpr int OUT2_THREADS = 27 * 32;
+
+// LayerNorm (no gain) of ROWS pixel rows of a swizzled [ROWS x C] bf16 tile by NT threads (NT / ROWS consecutive lanes per row), from
+// src to dst (same layout; dst == src works in place); see tile_normalize.
+template <int C, int NT, int ROWS, uint32_t SPAN_STRIDE>
+__device__ __forceinline__ void rows_normalize(const uint8_t* src, uint8_t* dst, int te, float eps) {
+    constexpr int TPP = NT / ROWS;
+    constexpr int NCH = (C / 8) / TPP;
+    static_assert(NCH >= 1 && TPP >= 1 && TPP <= 8, "rows_normalize: thread split");
+    const int p = te / TPP, sub = te % TPP;
+    ptx::f32x2 xh[NCH * 4];
+    uint32_t off[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int c = sub + i * TPP;
+        off[i] = (c >> 3) * SPAN_STRIDE + sw_off(p, c & 7);
+        const uint4 u = *reinterpret_cast<const uint4*>(src + off[i]);
+        xh[i * 4] = ptx::bf16x2_to_f32x2(u.x); xh[i * 4 + 1] = ptx::bf16x2_to_f32x2(u.y);
+        xh[i * 4 + 2] = ptx::bf16x2_to_f32x2(u.z); xh[i * 4 + 3] = ptx::bf16x2_to_f32x2(u.w);
+    }
+    ptx::f32x2 s0 = xh[0], s1 = xh[1];
+#pragma unroll
+    for (int i = 2; i < NCH * 4; i += 2) { s0 = ptx::add2(s0, xh[i]); s1 = ptx::add2(s1, xh[i + 1]); }
+    s0 = ptx::add2(s0, s1);
+    float sum = ptx::lo(s0) + ptx::hi(s0);
+#pragma unroll
+    for (int o = 1; o < TPP; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const ptx::f32x2 nm = ptx::dup2(-(sum * (1.0f / C)));
+    ptx::f32x2 q0 = ptx::mk2(0.f, 0.f), q1 = q0;
+#pragma unroll
+    for (int i = 0; i < NCH * 4; i += 2) {
+        xh[i] = ptx::add2(xh[i], nm);
+        xh[i + 1] = ptx::add2(xh[i + 1], nm);
+        q0 = ptx::fma2(xh[i], xh[i], q0);
+        q1 = ptx::fma2(xh[i + 1], xh[i + 1], q1);
+    }
+    q0 = ptx::add2(q0, q1);
+    float ss = ptx::lo(q0) + ptx::hi(q0);
+#pragma unroll
+    for (int o = 1; o < TPP; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const ptx::f32x2 RS = ptx::dup2(rsqrtf(ss * (1.0f / C) + eps));
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+        *reinterpret_cast<uint4*>(dst + off[i]) =
+            make_uint4(ptx::pack_bf16x2(ptx::mul2(xh[i * 4], RS)), ptx::pack_bf16x2(ptx::mul2(xh[i * 4 + 1], RS)),
+                       ptx::pack_bf16x2(ptx::mul2(xh[i * 4 + 2], RS)), ptx::pack_bf16x2(ptx::mul2(xh[i * 4 + 3], RS)));
+}
+
+__global__ void __launch_bounds__(OUT2_THREADS, 1)
+linattn_out2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmY, const OutArgs a) {
+    using Cf = Out2Cfg;
+    constexpr int C = OUT2_C;
+    constexpr int XS = Cf::X_STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sWq = smem;
+    uint8_t* sX = sWq + Cf::WQ_BYTES;                // [3] raw x / output staging
+    uint8_t* sZ = sX + XS * Cf::X_BYTES;             // [2] normalised x
+    uint8_t* sMb = sZ + 2 * Cf::X_BYTES;             // [2]
+    uint8_t* sA2 = sMb + 2 * Cf::MB_BYTES;           // [2]
+    float* s_bo = reinterpret_cast<float*>(sA2 + 2 * Cf::A2_BYTES);
+    float* s_g2 = s_bo + C;
+    float* s_xch = s_g2 + C;                         // [2 slots][2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_xch + 512);
+    uint64_t* wq_bar = bars;
+    uint64_t* x_full = bars + 1;                     // [3] TMA -> LayerNorm warps (and the epilogue's residual read)
+    uint64_t* x_empty = bars + 4;                    // [3] output store has read the stage -> TMA
+    uint64_t* z_full = bars + 7;                     // [2] LayerNorm warps -> MMA 1
+    uint64_t* z_empty = bars + 9;                    // [2] MMA 1 -> LayerNorm warps
+    uint64_t* q_full = bars + 11;                    // [2] MMA 1 -> softmax warps
+    uint64_t* q_empty = bars + 13;                   // [2] softmax warps -> MMA 1
+    uint64_t* a2_full = bars + 15;                   // [2] softmax warps -> MMA 2
+    uint64_t* a2_empty = bars + 17;                  // [2] MMA 2 -> softmax warps
+    uint64_t* mb_full = bars + 19;                   // [2] TMA -> MMA 2
+    uint64_t* mb_empty = bars + 21;                  // [2] MMA 2 -> TMA
+    uint64_t* y_full = bars + 23;                    // [2] MMA 2 -> epilogue warps
+    uint64_t* y_empty = bars + 25;                   // [2] epilogue warps -> MMA 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp == 0) {
+        if (lane == 0) { ptx::prefetch_tmap(&tmX); ptx::prefetch_tmap(&tmW); ptx::prefetch_tmap(&tmM); ptx::prefetch_tmap(&tmY); }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    } else if (warp == 1 && lane == 0) {
+        ptx::mbar_init(wq_bar, 1);
+        for (int i = 0; i < XS; ++i) { ptx::mbar_init(&x_full[i], 1); ptx::mbar_init(&x_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&z_full[i], 8);  ptx::mbar_init(&z_empty[i], 1);
+            ptx::mbar_init(&q_full[i], 1);  ptx::mbar_init(&q_empty[i], 8);
+            ptx::mbar_init(&a2_full[i], 8); ptx::mbar_init(&a2_empty[i], 1);
+            ptx::mbar_init(&mb_full[i], 1); ptx::mbar_init(&mb_empty[i], 1);
+            ptx::mbar_init(&y_full[i], 1);  ptx::mbar_init(&y_empty[i], 8);
+        }
+        ptx::fence_mbar_init();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_launch();     // PDL (ptx.cuh): the successor may be scheduled; each role waits for the predecessor before global memory
+    constexpr uint32_t COL_Q = 0, COL_Y = 256;
+    const int ntile = a.num_tiles > static_cast<int>(blockIdx.x) ? (a.num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;   // tiles of this CTA
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(wq_bar, Cf::WQ_BYTES);
+            ptx::tma_load_2d(sWq, &tmW, wq_bar, 0, 0);
+        }
+        __syncwarp();
+        ptx::grid_dep_wait();
+        for (int it = 0; it < ntile; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int st = it % XS, mb = it & 1;
+            ptx::mbar_wait(&x_empty[st], ((it / XS) & 1u) ^ 1u);
+            if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(&x_full[st], Cf::X_BYTES);
+                ptx::tma_load_2d(sX + st * Cf::X_BYTES, &tmX, &x_full[st], 0, tile * TILE);
+            }
+            __syncwarp();
+            ptx::mbar_wait(&mb_empty[mb], ((it >> 1) & 1u) ^ 1u);
+            if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(&mb_full[mb], Cf::MB_BYTES);
+                const int b = tile / a.tiles_per_img;
+                for (int sp = 0; sp < 2; ++sp) ptx::tma_load_2d(sMb + mb * Cf::MB_BYTES + sp * Cf::MB_SPAN, &tmM, &mb_full[mb], sp * 64, b * C);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA 1: Q = z Wq'^T
+        constexpr uint32_t idesc_q = ptx::make_idesc_bf16(128, 128);
+        const uint64_t dZ = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sZ));
+        const uint64_t dWq = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sWq));
+        ptx::mbar_wait(wq_bar, 0);
+        for (int it = 0; it < ntile; ++it) {
+            const int bb = it & 1;
+            const uint32_t ph = (it >> 1) & 1u;
+            ptx::mbar_wait(&z_full[bb], ph);
+            ptx::mbar_wait(&q_empty[bb], ph ^ 1u);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint64_t zoff = static_cast<uint64_t>((bb * Cf::X_BYTES) >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    ptx::umma_bf16(tmem_base + COL_Q + bb * 128, dZ + zoff + 2u * k, dWq + 2u * k, idesc_q, k != 0 ? 1u : 0u);
+                ptx::umma_commit(&q_full[bb]);
+                ptx::umma_commit(&z_empty[bb]);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 2) {
+        // ------------------------------------------------------------------ MMA 2: Y = A2 Mb^T
+        constexpr uint32_t idesc_y = ptx::make_idesc_bf16(128, C);
+        const uint64_t dA2 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sA2));
+        const uint64_t dMb = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sMb));
+        for (int it = 0; it < ntile; ++it) {
+            const int bb = it & 1;
+            const uint32_t ph = (it >> 1) & 1u;
+            ptx::mbar_wait(&a2_full[bb], ph);
+            ptx::mbar_wait(&mb_full[bb], ph);
+            ptx::mbar_wait(&y_empty[bb], ph ^ 1u);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint64_t aoff = static_cast<uint64_t>((bb * Cf::A2_BYTES) >> 4);
+                const uint64_t moff = static_cast<uint64_t>((bb * Cf::MB_BYTES) >> 4);
+#pragma unroll
+                for (int sp = 0; sp < 2; ++sp)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t offa = aoff + static_cast<uint64_t>((sp * SPAN_BYTES) >> 4) + 2u * k;
+                        const uint64_t offb = moff + static_cast<uint64_t>((sp * Cf::MB_SPAN) >> 4) + 2u * k;
+                        ptx::umma_bf16(tmem_base + COL_Y + bb * 64, dA2 + offa, dMb + offb, idesc_y, (sp | k) != 0 ? 1u : 0u);
+                    }
+                ptx::umma_commit(&y_full[bb]);
+                ptx::umma_commit(&a2_empty[bb]);
+                ptx::umma_commit(&mb_empty[bb]);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= OUT2_NORM_WARP0) {
+        // ------------------------------------------------------------------ LayerNorm warps: z = (x - mean) * rstd, two threads per row
+        const int tn = (warp - OUT2_NORM_WARP0) * 32 + lane;       // 0..255
+        for (int it = 0; it < ntile; ++it) {
+            const int st = it % XS, bb = it & 1;
+            ptx::mbar_wait(&x_full[st], (it / XS) & 1u);
+            ptx::mbar_wait(&z_empty[bb], ((it >> 1) & 1u) ^ 1u);
+            rows_normalize<C, 256, TILE, SPAN_BYTES>(sX + st * Cf::X_BYTES, sZ + bb * Cf::X_BYTES, tn, a.eps);
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&z_full[bb]);
+        }
+    } else if (warp < OUT2_LN_WARP0) {
+        // ------------------------------------------------------------------ softmax warps: thread = (pixel row, two heads)
+        const int q = warp & 3;
+        const int hf = (warp - OUT2_SM_WARP0) >> 2;
+        const int r = q * 32 + lane;
+        const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        constexpr float LOG2E = 1.4426950408889634f;
+        const ptx::f32x2 L2E = ptx::dup2(LOG2E);
+        for (int it = 0; it < ntile; ++it) {
+            const int bb = it & 1;
+            const uint32_t ph = (it >> 1) & 1u;
+            uint8_t* a2 = sA2 + bb * Cf::A2_BYTES + hf * SPAN_BYTES;      // span = head >> 1 = hf
+            ptx::mbar_wait(&q_full[bb], ph);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t v[32];
+                ptx::tmem_ld32(tlane + COL_Q + bb * 128 + (2 * hf + hh) * 32, v);
+                ptx::tmem_ld_wait();
+                if (hh == 1) {
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&q_empty[bb]);       // this warp has read its part of Q: MMA 1 two tiles on may overwrite
+                }
+                float mx = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+#pragma unroll
+                for (int j = 2; j < 32; j += 2) mx = fmaxf(fmaxf(mx, __uint_as_float(v[j])), __uint_as_float(v[j + 1]));
+                // exp(q - max) = exp2(q * log2e - max * log2e)
+                const ptx::f32x2 NMX = ptx::dup2(-(mx * LOG2E));
+                ptx::f32x2 f[16];
+                ptx::f32x2 a0 = ptx::mk2(0.f, 0.f), a1 = a0;
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    const ptx::f32x2 d0 = ptx::fma2(ptx::mk2(v[2 * j], v[2 * j + 1]), L2E, NMX);
+                    const ptx::f32x2 d1 = ptx::fma2(ptx::mk2(v[2 * j + 2], v[2 * j + 3]), L2E, NMX);
+                    f[j] = ptx::mk2(ptx::ex2(ptx::lo(d0)), ptx::ex2(ptx::hi(d0)));
+                    f[j + 1] = ptx::mk2(ptx::ex2(ptx::lo(d1)), ptx::ex2(ptx::hi(d1)));
+                    a0 = ptx::add2(a0, f[j]);
+                    a1 = ptx::add2(a1, f[j + 1]);
+                }
+                a0 = ptx::add2(a0, a1);
+                const ptx::f32x2 INV = ptx::dup2(ptx::rcp(ptx::lo(a0) + ptx::hi(a0)));   // the sum is in [1, 32]
+                if (hh == 0) ptx::mbar_wait(&a2_empty[bb], ph ^ 1u);     // MMA 2 two tiles back has consumed this A2 buffer
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    uint4 o;
+                    o.x = ptx::pack_bf16x2(ptx::mul2(f[jj * 4], INV));
+                    o.y = ptx::pack_bf16x2(ptx::mul2(f[jj * 4 + 1], INV));
+                    o.z = ptx::pack_bf16x2(ptx::mul2(f[jj * 4 + 2], INV));
+                    o.w = ptx::pack_bf16x2(ptx::mul2(f[jj * 4 + 3], INV));
+                    *reinterpret_cast<uint4*>(a2 + sw_off(r, hh * 4 + jj)) = o;
+                }
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&a2_full[bb]);
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue warps: thread = (pixel row, half of the channels)
+        const int q = warp & 3;
+        const int hf = (warp - OUT2_LN_WARP0) >> 2;
+        const int te = (warp - OUT2_LN_WARP0) * 32 + lane;
+        const int r = q * 32 + lane;
+        if (te < C) { s_bo[te] = a.bo[te]; s_g2[te] = a.g2[te]; }
+        named_bar_sync(1, 256);
+        const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        float* xc = s_xch;                               // two [2][128] exchange slots: y sum, y centred squares
+        float* xd = s_xch + 256;
+        const int mine = hf * 128 + r, other = (hf ^ 1) * 128 + r;
+        ptx::grid_dep_wait();
+        for (int it = 0; it < ntile; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int st = it % XS, bb = it & 1;
+            uint8_t* xs = sX + st * Cf::X_BYTES;
+            ptx::mbar_wait(&x_full[st], (it / XS) & 1u);             // long complete: makes the TMA's writes visible to this thread
+            ptx::mbar_wait(&y_full[bb], (it >> 1) & 1u);
+            ptx::tc_fence_after();
+            uint32_t v[32];
+            ptx::tmem_ld32(tlane + COL_Y + bb * 64 + hf * 32, v);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&y_empty[bb]);
+            // LayerNorm over the C output channels of this pixel: the two halves of the row exchange their partial sums through
+            // shared memory (mean first, then the centred sum of squares)
+            ptx::f32x2 y[16];
+            ptx::f32x2 ys0 = ptx::mk2(0.f, 0.f), ys1 = ys0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                const float4 b4 = *reinterpret_cast<const float4*>(s_bo + hf * 32 + 2 * j);
+                y[j] = ptx::add2(ptx::mk2(v[2 * j], v[2 * j + 1]), ptx::mk2(b4.x, b4.y));
+                y[j + 1] = ptx::add2(ptx::mk2(v[2 * j + 2], v[2 * j + 3]), ptx::mk2(b4.z, b4.w));
+                ys0 = ptx::add2(ys0, y[j]);
+                ys1 = ptx::add2(ys1, y[j + 1]);
+            }
+            ys0 = ptx::add2(ys0, ys1);
+            const float sum = ptx::lo(ys0) + ptx::hi(ys0);
+            xc[mine] = sum;
+            named_bar_sync(2 + q, 64);
+            const ptx::f32x2 NYM = ptx::dup2(-((sum + xc[other]) * (1.0f / C)));
+            ptx::f32x2 yq0 = ptx::mk2(0.f, 0.f), yq1 = yq0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                y[j] = ptx::add2(y[j], NYM);
+                y[j + 1] = ptx::add2(y[j + 1], NYM);
+                yq0 = ptx::fma2(y[j], y[j], yq0);
+                yq1 = ptx::fma2(y[j + 1], y[j + 1], yq1);
+            }
+            yq0 = ptx::add2(yq0, yq1);
+            const float ss = ptx::lo(yq0) + ptx::hi(yq0);
+            xd[mine] = ss;
+            named_bar_sync(2 + q, 64);
+            const ptx::f32x2 YR = ptx::dup2(rsqrtf((ss + xd[other]) * (1.0f / C) + a.eps));
+            // normalise, + x, and write the result IN PLACE over the x tile (same row, same swizzled chunk): the TMA-store staging
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                uint4* px = reinterpret_cast<uint4*>(xs + sw_off(r, hf * 4 + jj));
+                const uint4 xu = *px;
+                const float4 ga = *reinterpret_cast<const float4*>(s_g2 + hf * 32 + jj * 8);
+                const float4 gb = *reinterpret_cast<const float4*>(s_g2 + hf * 32 + jj * 8 + 4);
+                const int k = jj * 4;
+                uint4 u;                                                  // o = (y * rstd) * g2 + x
+                u.x = ptx::pack_bf16x2(ptx::fma2(ptx::mul2(y[k], YR), ptx::mk2(ga.x, ga.y), ptx::bf16x2_to_f32x2(xu.x)));
+                u.y = ptx::pack_bf16x2(ptx::fma2(ptx::mul2(y[k + 1], YR), ptx::mk2(ga.z, ga.w), ptx::bf16x2_to_f32x2(xu.y)));
+                u.z = ptx::pack_bf16x2(ptx::fma2(ptx::mul2(y[k + 2], YR), ptx::mk2(gb.x, gb.y), ptx::bf16x2_to_f32x2(xu.z)));
+                u.w = ptx::pack_bf16x2(ptx::fma2(ptx::mul2(y[k + 3], YR), ptx::mk2(gb.z, gb.w), ptx::bf16x2_to_f32x2(xu.w)));
+                *px = u;
+            }
+            ptx::fence_proxy_async_smem();
+            named_bar_sync(2 + q, 64);                   // both halves of this 32-row block are in place
+            if (hf == 0 && lane == 0) {
+                ptx::tma_store_2d(&tmY, xs + (q * 32) * 128, 0, tile * TILE + q * 32);
+                ptx::bulk_commit();
+                ptx::bulk_wait_read<0>();                 // the store has read the stage: it may be refilled
+                ptx::mbar_arrive(&x_empty[st]);
+            }
+        }
+        if (hf == 0 && lane == 0) ptx::bulk_wait_all();
+        __syncwarp();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) ptx::tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -1104,11 +1468,13 @@ static cudaError_t run_c(const LinAttnFusedLaunch& l, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(linattn_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, OutCfg<C>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(linattn_out2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Out2Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
         attr = true;
     }
     const LinAttnFusedDesc& d = l.d;
     KvArgs ka;
-    ka.n = d.n; ka.tiles_per_unit = l.tiles_per_unit * (TILE / KV_PX); ka.parts = l.parts; ka.rowsum = d.rowsum; ka.kshift = d.kshift;
+    ka.n = d.n; ka.tiles_per_unit = l.tiles_per_unit * (TILE / KV_PX); ka.parts = l.parts; ka.kshift = d.kshift;
     ka.ctx_part = d.ctx_part; ka.s_part = d.s_part; ka.eps = d.eps;
     static const bool kv_v1 = [] { const char* v = getenv("HD_LA_KV"); return v && v[0] == '1'; }();
     cudaError_t e;
@@ -1120,12 +1486,17 @@ static cudaError_t run_c(const LinAttnFusedLaunch& l, cudaStream_t s) {
         e = launch_pdl(linattn_kv2_kernel<C>, dim3(grid), dim3(KV2_THREADS), Kv2Cfg<C>::SMEM_BYTES, s, l.tmXk, l.tmW, ka, units);
     }
     if (e != cudaSuccess) return e;
-    e = launch_pdl(linattn_mix_kernel, dim3(d.B, 4), dim3(128), 0, s, d.ctx_part, d.s_part, d.wo, d.mb, l.parts, C,
+    e = launch_pdl(linattn_mix_kernel, dim3(d.B), dim3(MIX_THREADS), 0, s, d.ctx_part, d.s_part, d.wo, d.mb, l.parts, C,
                    0.17677669529663687f / static_cast<float>(d.n));   // 32^-0.5 / n
     if (e != cudaSuccess) return e;
     OutArgs oa;
     oa.n = d.n; oa.tiles_per_img = d.n / TILE; oa.num_tiles = l.num_tiles; oa.rowsum = d.rowsum; oa.bo = d.bo; oa.g2 = d.g2;
     oa.eps = d.eps;
+    static const bool out_v1 = [] { const char* v = getenv("HD_LA_OUT"); return v && v[0] == '1'; }();
+    if (C == OUT2_C && !out_v1) {
+        const int grid = l.num_tiles < l.num_sms ? l.num_tiles : l.num_sms;     // persistent: one CTA per SM
+        return launch_pdl(linattn_out2_kernel, dim3(grid), dim3(OUT2_THREADS), Out2Cfg::SMEM_BYTES, s, l.tmX, l.tmW, l.tmM, l.tmY, oa);
+    }
     return launch_pdl(linattn_out_kernel<C>, dim3(l.out_grid), dim3(OUT_THREADS), OutCfg<C>::SMEM_BYTES, s, l.tmX, l.tmW, l.tmM, l.tmY, oa);
 }
 

@@ -3,7 +3,7 @@
 # (library variants built by scripts/build_variant.sh), and one --set full capture (source view) of each fused attention kernel.
 TAG=${1:-r02l}
 mkdir -p gpurun_out
-for lib in default nohint hint2us; do
+for lib in default; do
   for mode in 0 1; do
     if [ $lib = default ]; then unset HICDIFF_B200_LIB; else export HICDIFF_B200_LIB=$PWD/hicdiff_b200/lib/variants/lib$lib.so; fi
     HD_LA_KV=$mode timeout 300 python bench.py --steps 200 --no-e2e --no-cpu-baseline --no-secondary > gpurun_out/${TAG}_bench_${lib}_kv$mode.json 2> gpurun_out/${TAG}_bench_${lib}_kv$mode.err
