@@ -48,13 +48,17 @@ constexpr uint32_t EPI_BUF_BYTES = 32 * 64;           // 32 rows x 32 bf16, 64B-
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int BAR_BYTES = 256;
 
-enum Kind : int { K_GENERAL = 0, K_SLAB = 1, K_SLAB_RES = 2, K_PAD = 3 };
+enum Kind : int { K_GENERAL = 0, K_SLAB = 1, K_SLAB_RES = 2, K_PAD = 3, K_DX3 = 4 };
+constexpr int DX3_N = 192;                             // K_DX3: MMA width = 3 dx taps x 64 output channels
+constexpr uint32_t DX3_ACC_STRIDE = 256;               // TMEM columns between the two 192-column accumulator stages
+constexpr uint32_t DX3_XCHG_BYTES = 1024;              // 4 warp pairs x 2 directions x 32 fp32: boundary rows between lane quarters
 constexpr uint32_t PAD_SLAB_CAP_BYTES = 42 * 1024;     // (rows + 2) * (W + 2) pixels * 128 B: 42240 B at W = 64, 30464 B at W = 32
 
 template <int BN, int KIND, bool GNF = false, int CG = 1>
 struct Cfg {
     // one (N tile, K block) of weights; a CTA pair (CG == 2, tcgen05 cta_group::2) splits the N rows between its two CTAs
     static constexpr uint32_t B_BLOCK_BYTES = (BN / CG) * BLOCK_K * 2;
+    static_assert(KIND != K_DX3 || (BN == 64 && !GNF && CG == 1), "the dx-stacked kind is built for N == 64, plain epilogue, one CTA");
     static constexpr uint32_t A_STAGE_BYTES = KIND == K_GENERAL ? A_TILE_BYTES : (KIND == K_PAD ? PAD_SLAB_CAP_BYTES : SLAB_CAP_BYTES);
     static constexpr uint32_t B_STAGE_BYTES = KIND == K_GENERAL ? B_BLOCK_BYTES : (KIND == K_SLAB ? 3 * B_BLOCK_BYTES : 0);
     static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -63,10 +67,12 @@ struct Cfg {
     // accumulator ring in TMEM: 2 stages, or 4 when the epilogue also applies GroupNorm (its second phase trails by one
     // tile while it waits for the image's statistics)
     static constexpr int ACC_STAGES = GNF ? 4 : 2;
-    static constexpr uint32_t ACC_COLS = ACC_STAGES * BN;
+    static constexpr uint32_t ACC_STRIDE = KIND == K_DX3 ? DX3_ACC_STRIDE : BN;  // TMEM columns from one accumulator stage to the next
+    static constexpr uint32_t ACC_COLS = ACC_STAGES * ACC_STRIDE;
     static constexpr uint32_t TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
     static constexpr uint32_t GN_AUX_BYTES = GNF ? (128 + 2 * 3 * BN * 4) : 0;    // (mean, rstd)[2][8] + (mul, add, post)[2][BN]
-    static constexpr int AUX_BYTES = BAR_BYTES + static_cast<int>(GN_AUX_BYTES);
+    static constexpr uint32_t XCHG_BYTES = KIND == K_DX3 ? DX3_XCHG_BYTES : 0;
+    static constexpr int AUX_BYTES = BAR_BYTES + static_cast<int>(GN_AUX_BYTES) + static_cast<int>(XCHG_BYTES);
     static int stages(uint32_t res_b_bytes) {
         const int avail = SMEM_LIMIT - 1024 - AUX_BYTES - static_cast<int>(EPI_BYTES) - static_cast<int>(res_b_bytes);
         int s = avail / static_cast<int>(STAGE_BYTES);
@@ -239,7 +245,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint8_t* sA = KIND == K_PAD ? smem + a.res_b_bytes : smem;
     uint8_t* sB = KIND == K_PAD ? smem : smem + stages * C::A_STAGE_BYTES;    // per-stage weights, or the resident matrix
     uint8_t* sEpi = smem + stages * C::A_STAGE_BYTES +
-                    ((KIND == K_SLAB_RES || KIND == K_PAD) ? a.res_b_bytes : stages * C::B_STAGE_BYTES);   // all sizes are KiB multiples
+                    ((KIND == K_SLAB_RES || KIND == K_PAD || KIND == K_DX3) ? a.res_b_bytes : stages * C::B_STAGE_BYTES);   // all sizes are KiB multiples
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpi + C::EPI_BYTES);
     uint64_t* empty_bar = full_bar + MAX_STAGES;
     uint64_t* tfull_bar = empty_bar + MAX_STAGES;
@@ -248,6 +254,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
     float* s_gn = reinterpret_cast<float*>(sEpi + C::EPI_BYTES + BAR_BYTES);   // GNF: [2][16] (mean[8], rstd[8])
     float* s_ma = s_gn + 32;                                                   // GNF: [2][3 * BN] (mul, add, post)
+    float* s_xchg = s_gn;                                                      // K_DX3 (never GNF): [4 pairs][2][32] boundary rows
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -332,6 +339,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     ld2(sB + kb * B_BLOCK, &tmB, res_bar, lb, kb * BLOCK_K, brow_off);
             }
             __syncwarp();
+        } else if constexpr (KIND == K_DX3) {
+            // resident weights, re-ordered on the way in: the three dx blocks of one (dy, chunk) sit back to back, so that
+            // they read as ONE K-major tile of 192 rows (row = dx * 64 + cout); global K order stays (tap, chunk)
+            if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(res_bar, a.res_b_bytes);
+                for (int kb = 0; kb < a.nkb; ++kb) {
+                    const int tap = kb / chunks, chunk = kb - tap * chunks;
+                    const int dyi = tap / 3, dxi = tap - dyi * 3;
+                    ptx::tma_load_2d(sB + ((dyi * chunks + chunk) * 3 + dxi) * B_BLOCK, &tmB, res_bar, kb * BLOCK_K, 0);
+                }
+            }
+            __syncwarp();
         }
         ptx::grid_dep_wait();      // weights above are constants of the plan; the activation loads below are not
         int stage = 0;
@@ -388,6 +407,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         }
                     }
                 }
+            } else if constexpr (KIND == K_DX3) {
+                // ONE un-shifted slab {64 ch, W, rows + 2} per chunk: the dy taps are descriptor offsets into it, the dx taps
+                // are the three 64-column groups of the 192-wide accumulator (shifted by one pixel in the epilogue)
+                for (int chunk = 0; chunk < chunks; ++chunk) {
+                    const int cs = chunk >= src_chunks ? chunk - src_chunks : chunk;
+                    const bool second = cs >= a.chunks0;
+                    const CUtensorMap* tm = second ? &tmA1 : &tmA0;
+                    const int c0 = (second ? cs - a.chunks0 : cs) * BLOCK_K;
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_arrive_expect_tx(&full_bar[stage], a.slab_bytes);
+                        ptx::tma_load_4d(sA + stage * C::A_STAGE_BYTES, tm, &full_bar[stage], c0, 0, h0 - 1, b0);
+                    }
+                    __syncwarp();
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                }
             } else {
                 for (int chunk = 0; chunk < chunks; ++chunk) {
                     const int cs = chunk >= src_chunks ? chunk - src_chunks : chunk;
@@ -415,10 +450,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
     } else if (warp == 1 && rank == 0) {
         // ------------------------------------------------------------------ MMA issuer (warp-uniform, one lane issues)
-        constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M * CG, BN);
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M * CG, KIND == K_DX3 ? DX3_N : BN);
         const uint64_t descA0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sA));
         const uint64_t descB0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sB));
-        if constexpr (KIND == K_SLAB_RES || KIND == K_PAD) {
+        if constexpr (KIND == K_SLAB_RES || KIND == K_PAD || KIND == K_DX3) {
             ptx::mbar_wait(res_bar, 0);
             ptx::tc_fence_after();
         }
@@ -430,8 +465,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const uint32_t aphase = (iter / ACC) & 1u;
             ptx::mbar_wait(&tempty_bar[as], aphase ^ 1u);
             ptx::tc_fence_after();
-            const uint32_t tmem_d = tmem_base + as * BN;
-            if constexpr (KIND == K_PAD) {
+            const uint32_t tmem_d = tmem_base + as * C::ACC_STRIDE;
+            if constexpr (KIND == K_DX3) {
+                const uint32_t dy_step = a.slab_dy_bytes >> 4;
+                for (int chunk = 0; chunk < chunks; ++chunk) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    if (ptx::elect_one()) {
+                        const uint64_t da = descA0 + static_cast<uint64_t>((stage * C::A_STAGE_BYTES) >> 4);
+#pragma unroll
+                        for (int dyi = 0; dyi < 3; ++dyi) {
+                            const uint64_t db = descB0 + static_cast<uint64_t>((((dyi * chunks + chunk) * 3) * B_BLOCK) >> 4);
+                            const uint64_t dad = da + static_cast<uint64_t>(dyi * dy_step);
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k)
+                                ptx::umma_bf16(tmem_d, dad + 2u * k, db + 2u * k, idesc, (chunk | dyi | k) != 0 ? 1u : 0u);
+                        }
+                        ptx::umma_commit(&empty_bar[stage]);
+                        if (chunk == chunks - 1) ptx::umma_commit(&tfull_bar[as]);
+                    }
+                    __syncwarp();
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                }
+            } else if constexpr (KIND == K_PAD) {
                 const TileCoord tc = decode_tile(a, tile);
                 const int p0 = (tc.mt % a.tiles_per_img) * BLOCK_M;
                 const int o0 = p0 - (p0 / a.PW) * a.PW;             // padded column of the tile's first position
@@ -871,7 +927,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
                 ptx::mbar_wait(&tfull_bar[as], aphase);
                 ptx::tc_fence_after();
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::ACC_STRIDE;
 
                 if constexpr (BN < 64) {
                     // fp32 head (tail conv of HiCEDRN): 16 accumulator columns, n_valid of them real; column half 0 does the work
@@ -894,16 +950,69 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll 1
                     for (int c = 0; c < BN; c += 64) {
                         const int ncol = n0 + c + hc * 32;
-                        uint32_t v[32];
-                        ptx::tmem_ld32(taddr + c + hc * 32, v);
-                        ptx::tmem_ld_wait();
-                        if (c + 64 == BN) {          // accumulator fully drained: hand the TMEM stage back to the MMA warp
-                            ptx::tc_fence_before();
-                            release_acc(&tempty_bar[as]);
-                        }
                         float f[32];
+                        if constexpr (KIND == K_DX3) {
+                            // accumulator column groups: [0, 64) = dx -1, [64, 128) = dx 0, [128, 192) = dx +1, all computed on the
+                            // UN-shifted pixel rows: out[r] = D0[r - 1] + D1[r] + D2[r + 1], the neighbours dropped where the tap
+                            // falls on the conv's zero padding (x == 0 / x == W - 1).  A tile is whole image rows, so r - 1 / r + 1
+                            // never leave it; across the 32-lane TMEM quarters the rows travel through shared memory (only at
+                            // W = 64: with W <= 32 every quarter boundary is a row boundary).
+                            uint32_t v0[32], v1[32], v2[32];
+                            ptx::tmem_ld32(taddr + hc * 32, v0);
+                            ptx::tmem_ld32(taddr + 64 + hc * 32, v1);
+                            ptx::tmem_ld32(taddr + 128 + hc * 32, v2);
+                            ptx::tmem_ld_wait();
+                            ptx::tc_fence_before();
+                            ptx::mbar_arrive(&tempty_bar[as]);
+                            const int xw = r & (a.W - 1);
+                            const bool has_l = xw != 0, has_r = xw != a.W - 1;
+                            const bool cross = a.W > 32;                      // warp-uniform
+                            float4 edge[8];
+                            if (cross) {
+                                const int pair = hc * 2 + (q >> 1);
+                                float* xs = s_xchg + pair * 64;            // [0, 32): D0 of the lower warp's last row; [32, 64): D2 of the upper warp's first row
+                                if ((q & 1) == 0 && lane == 31) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                                    for (int j = 0; j < 32; j += 4)
+                                        *reinterpret_cast<float4*>(xs + j) = make_float4(__uint_as_float(v0[j]), __uint_as_float(v0[j + 1]),
+                                                                                           __uint_as_float(v0[j + 2]), __uint_as_float(v0[j + 3]));
+                                }
+                                if ((q & 1) == 1 && lane == 0) {
+#pragma unroll
+                                    for (int j = 0; j < 32; j += 4)
+                                        *reinterpret_cast<float4*>(xs + 32 + j) = make_float4(__uint_as_float(v2[j]), __uint_as_float(v2[j + 1]),
+                                                                                                __uint_as_float(v2[j + 2]), __uint_as_float(v2[j + 3]));
+                                }
+                                named_bar_sync(3 + pair, 64);
+                                const float* ep = xs + ((q & 1) ? 0 : 32);    // upper warp reads the lower one's D0, and vice versa
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) edge[j] = *reinterpret_cast<const float4*>(ep + 4 * j);
+                                named_bar_sync(3 + pair, 64);                 // the rows are consumed: the next tile may overwrite them
+                            }
+                            const bool take_edge_l = cross && (q & 1) == 1 && lane == 0;
+                            const bool take_edge_r = cross && (q & 1) == 0 && lane == 31;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float up = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);
+                                float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);
+                                if (cross) {
+                                    const float ev = reinterpret_cast<const float*>(edge)[j];
+                                    if (take_edge_l) up = ev;
+                                    if (take_edge_r) dn = ev;
+                                }
+                                f[j] = __uint_as_float(v1[j]) + (has_l ? up : 0.f) + (has_r ? dn : 0.f);
+                            }
+                        } else {
+                            uint32_t v[32];
+                            ptx::tmem_ld32(taddr + c + hc * 32, v);
+                            ptx::tmem_ld_wait();
+                            if (c + 64 == BN) {          // accumulator fully drained: hand the TMEM stage back to the MMA warp
+                                ptx::tc_fence_before();
+                                release_acc(&tempty_bar[as]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                        }
                         // bias / FiLM / SiLU / scale / residual on this warp's 32 columns
                         if (e.bias != nullptr) {
 #pragma unroll
@@ -1099,6 +1208,7 @@ void size_cfg(ConvGemmLaunch* l) {
         case K_SLAB: if (l->gnf) size_one<BN, K_SLAB, true>(l); else size_one<BN, K_SLAB, false>(l); break;
         case K_SLAB_RES: if (l->gnf) size_one<BN, K_SLAB_RES, true>(l); else size_one<BN, K_SLAB_RES, false>(l); break;
         case K_PAD: size_one<BN, K_PAD, false>(l); break;
+        case K_DX3: if constexpr (BN == 64) size_one<BN, K_DX3, false>(l); break;
         default: size_one<BN, K_GENERAL, false>(l); break;
     }
 }
@@ -1210,6 +1320,15 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
             if (out->kind == K_SLAB_RES) out->res_b_bytes /= 2;
             out->num_m_tiles = (out->num_m_tiles + 1) / 2;          // M-tile PAIRS from here on
         }
+    }
+    // dx-stacked form of the resident-weight kind (default where it applies): one un-shifted slab per chunk, MMAs of N = 192
+    // = 3 dx taps x 64 channels, the one-pixel shifts in the epilogue.  By the measured issue law (N/2 + 43 clk per K = 16 step,
+    // profiles/r02_ubench_tcgen05.md) three taps cost 139 clk instead of 3 x 75.  HD_CONV_DX3=0 / ConvGemmDesc::dx3_mode = 0
+    // fall back to one MMA per tap.
+    {
+        static const int dx3_env = [] { const char* v = getenv("HD_CONV_DX3"); return v ? atoi(v) : -1; }();
+        const int want = dx3_env >= 0 ? dx3_env : d.dx3_mode;
+        if (want > 0 && out->kind == K_SLAB_RES && out->cg == 1 && d.epi.gn_gamma == nullptr && Ws <= 64) out->kind = K_DX3;
     }
     out->num_tiles = out->num_m_tiles * out->num_n_tiles * phases;
     out->mode = d.mode;
@@ -1363,6 +1482,8 @@ cudaError_t conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t s) {
         case K_SLAB_RES:
             if (l.bn != 64) return cudaErrorInvalidValue;
             return l.gnf ? launch_cfg<64, K_SLAB_RES, true>(l, s) : launch_cfg<64, K_SLAB_RES>(l, s);
+        case K_DX3:
+            return (l.bn == 64 && !l.gnf) ? launch_cfg<64, K_DX3>(l, s) : cudaErrorInvalidValue;
         default: return cudaErrorInvalidValue;
     }
 }

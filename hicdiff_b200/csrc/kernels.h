@@ -109,6 +109,7 @@ struct ConvGemmDesc {
     ConvEpilogue epi;
     int cg2_mode = 0;         // 1: run on CTA pairs (tcgen05 cta_group::2) where the kind supports it
     int pad_mode = 0;         // 3x3, N == 64: 1 = padded-slab form where >= 2 stages fit, 2 = wherever it fits, 0 = never
+    int dx3_mode = 1;         // 3x3, N == 64, resident weights: 1 = dx-stacked form (N = 192 MMAs, shifts in the epilogue), 0 = one MMA per tap
     int static_weights = 0;   // 1: `weight` is not written by any kernel of the graph this launch belongs to (the sampling plan's
                               // weights, prepared at finalize): the resident-weight load may then precede the PDL wait (ptx.cuh).
                               // The trainer re-derives its bf16 layouts every step -> 0.
@@ -125,6 +126,7 @@ struct ConvGemmLaunch {
     int m_tiles_real;   // real 128-row M tiles
     int kind;           // 0 general, 1 slab (3x3, one A box per (chunk, dx)), 2 slab + shared-memory resident weights,
                         // 3 padded slab (one A box per chunk serves all nine taps; GroupNorm partials use the padded layout)
+                        // 4 dx-stacked resident slab (N == 64: MMAs of 192 columns = 3 dx taps, shifted and summed in the epilogue)
     int grid;
     int smem_bytes;
     // kernel scalar arguments

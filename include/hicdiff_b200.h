@@ -57,7 +57,8 @@ typedef struct hd_config {
                                * bits 1-2: padded-slab conv form; bit 3: CTA pairs (tcgen05 cta_group::2);
                                * bits 4-5: GEMM precision -- 0 = bf16 operands (default), 1 = "bf16w2": bf16 activations,
                                * conv weights as hi + lo bf16 pairs (two MMAs per product; the reference computes in fp32,
-                               * src/hicdiff_condition.py:90,105).  Other words: 0.                                     */
+                               * src/hicdiff_condition.py:90,105); bit 6: the 3x3, Cout = 64 convs issue one MMA per filter tap
+                               * instead of the default dx-stacked form (three taps per N = 192 MMA).  Other words: 0.    */
 } hd_config;
 
 /* -------------------------------------------------------------------------------------------------------------
@@ -248,7 +249,9 @@ HD_API int hd_tile_scatter(const float* tiles, float* mat, int64_t n, int32_t pi
  * ------------------------------------------------------------------------------------------------------------- */
 /* conv: w fp32 [Cout,Cin,k,k] in reference layout; standardize=1 applies WeightStandardizedConv2d's transform.
  * x1 (second concat operand, C1 channels) may be NULL.  mode 0: k x k "same" conv; mode 1: Downsample (pixel
- * unshuffle + 1x1, w is [Cout, 4*C0, 1, 1]; x0 is [B,2H,2W,C0], output [B,H,W,Cout]).  res (optional) is added. */
+ * unshuffle + 1x1, w is [Cout, 4*C0, 1, 1]; x0 is [B,2H,2W,C0], output [B,H,W,Cout]).  res (optional) is added.
+ * Bits above bit 0 of `standardize` select opt-in kernel forms for the parity tests: bits 1-2 padded slab, bit 3 CTA pairs,
+ * bit 4 one MMA per tap instead of the dx-stacked form of the 3x3, Cout = 64 conv. */
 HD_API int hd_op_conv2d(const uint16_t* x0, int32_t C0, const uint16_t* x1, int32_t C1, const float* w, const float* bias,
                  const uint16_t* res, uint16_t* out, int32_t B, int32_t H, int32_t W, int32_t Cout, int32_t ksize,
                  int32_t mode, int32_t standardize, void* stream);

@@ -127,6 +127,37 @@ def test_conv_gemm_padded_slab(B, H, C0, C1):
     assert (out.float() - same.float()).abs().max().item() <= 2e-2 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("B,H,C0,C1,res", [(2, 64, 64, 0, False), (5, 64, 64, 64, True), (16, 64, 64, 64, False), (24, 64, 64, 0, True),
+                                           (3, 32, 64, 0, False), (9, 32, 64, 64, True), (8, 16, 64, 0, False), (40, 16, 64, 64, True)])
+def test_conv_gemm_dx_stacked(B, H, C0, C1, res):
+    """Default form of the 3x3, Cout = 64 conv (hicdiff_condition.py:84-97 at the 64-channel level): the three dx taps of a filter
+    row are ONE tcgen05.mma of N = 192 over the un-shifted pixel slab, and the epilogue adds the three 64-column groups shifted by
+    -1 / 0 / +1 pixel (neighbours dropped on the zero padding; across TMEM lane quarters the rows go through shared memory at
+    W = 64).  Checked against fp64 torch and against the one-MMA-per-tap form; several tiles per persistent CTA (accumulator and
+    slab rings wrap), concat sources, residual epilogue, W = 64 / 32 / 16."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(5150 + B + H + C1)
+    x0 = _rand_nhwc(B, H, H, C0, g)
+    x1 = _rand_nhwc(B, H, H, C1, g) if C1 else None
+    r = _rand_nhwc(B, H, H, 64, g) if res else None
+    Cin = C0 + C1
+    w = (torch.randn(64, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)).to(DEV)
+    bias = (torch.randn(64, generator=g) * 0.1).to(DEV)
+    out = ops.conv2d_nhwc(x0, w, bias, x1=x1, res=r, standardize=True)
+    torch.cuda.synchronize()
+    xin = _nchw64(x0) if x1 is None else torch.cat((_nchw64(x0), _nchw64(x1)), dim=1)
+    ref = F.conv2d(xin, _bf16_round(_ws(w).float()), bias.to(torch.float64), padding=1)
+    if res:
+        ref = ref + _nchw64(r)
+    _check(out, ref, f"dx-stacked conv {Cin}->64 @{H}")
+    per_tap = ops.conv2d_nhwc(x0, w, bias, x1=x1, res=r, standardize=True, dx_stack=False)
+    _check(per_tap, ref, f"per-tap conv {Cin}->64 @{H}")
+    # same products, fp32 accumulation in a different order, one bf16 rounding at the end: at most one bf16 ulp apart
+    assert (out.float() - per_tap.float()).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item()
+    again = ops.conv2d_nhwc(x0, w, bias, x1=x1, res=r, standardize=True)
+    assert torch.equal(out, again), "dx-stacked conv is not bit-reproducible"
+
+
 @pytest.mark.parametrize("B,H,C0,C1,Cout,k", [(2, 64, 64, 0, 64, 3), (3, 32, 128, 64, 128, 3), (3, 8, 512, 256, 512, 3), (2, 16, 256, 0, 256, 3),
                                                (2, 64, 64, 0, 384, 1), (1, 8, 256, 0, 512, 3)])
 def test_conv_gemm_cta_pairs(B, H, C0, C1, Cout, k):
