@@ -48,7 +48,8 @@ constexpr uint32_t EPI_BUF_BYTES = 32 * 64;           // 32 rows x 32 bf16, 64B-
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int BAR_BYTES = 256;
 
-enum Kind : int { K_GENERAL = 0, K_SLAB = 1, K_SLAB_RES = 2, K_PAD = 3, K_DX3 = 4 };
+enum Kind : int { K_GENERAL = 0, K_SLAB = 1, K_SLAB_RES = 2, K_PAD = 3, K_DX3 = 4, K_DX3G = 5 };
+constexpr int NUM_THREADS_2G = 576;                    // K_DX3G: warps 2..9 and 10..17 are two epilogue groups on alternating tiles
 constexpr int DX3_N = 192;                             // K_DX3: MMA width = 3 dx taps x 64 output channels
 constexpr uint32_t DX3_ACC_STRIDE = 256;               // TMEM columns between the two 192-column accumulator stages
 constexpr uint32_t DX3_XCHG_BYTES = 1024;              // 4 warp pairs x 2 directions x 32 fp32: boundary rows between lane quarters
@@ -58,20 +59,22 @@ template <int BN, int KIND, bool GNF = false, int CG = 1>
 struct Cfg {
     // one (N tile, K block) of weights; a CTA pair (CG == 2, tcgen05 cta_group::2) splits the N rows between its two CTAs
     static constexpr uint32_t B_BLOCK_BYTES = (BN / CG) * BLOCK_K * 2;
-    static_assert(KIND != K_DX3 || (BN == 64 && !GNF && CG == 1), "the dx-stacked kind is built for N == 64, plain epilogue, one CTA");
+    static constexpr bool DX = KIND == K_DX3 || KIND == K_DX3G;      // dx-stacked kinds: MMAs of N = 192 over the un-shifted slab
+    static_assert(!DX || (BN == 64 && !GNF && CG == 1), "the dx-stacked kinds are built for N == 64, plain epilogue, one CTA");
+    static constexpr int THREADS = KIND == K_DX3G ? NUM_THREADS_2G : NUM_THREADS;
     static constexpr uint32_t A_STAGE_BYTES = KIND == K_GENERAL ? A_TILE_BYTES : (KIND == K_PAD ? PAD_SLAB_CAP_BYTES : SLAB_CAP_BYTES);
     static constexpr uint32_t B_STAGE_BYTES = KIND == K_GENERAL ? B_BLOCK_BYTES : (KIND == K_SLAB ? 3 * B_BLOCK_BYTES : 0);
     static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int EPI_BUFS = BN <= 64 ? 1 : 2;                             // staging buffers per epilogue warp
-    static constexpr uint32_t EPI_BYTES = EPI_WARPS * EPI_BUFS * EPI_BUF_BYTES;
+    static constexpr uint32_t EPI_BYTES = KIND == K_DX3G ? 0 : EPI_WARPS * EPI_BUFS * EPI_BUF_BYTES;   // K_DX3G stores straight from registers
     // accumulator ring in TMEM: 2 stages, or 4 when the epilogue also applies GroupNorm (its second phase trails by one
     // tile while it waits for the image's statistics)
     static constexpr int ACC_STAGES = GNF ? 4 : 2;
-    static constexpr uint32_t ACC_STRIDE = KIND == K_DX3 ? DX3_ACC_STRIDE : BN;  // TMEM columns from one accumulator stage to the next
+    static constexpr uint32_t ACC_STRIDE = DX ? DX3_ACC_STRIDE : BN;  // TMEM columns from one accumulator stage to the next
     static constexpr uint32_t ACC_COLS = ACC_STAGES * ACC_STRIDE;
     static constexpr uint32_t TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
     static constexpr uint32_t GN_AUX_BYTES = GNF ? (128 + 2 * 3 * BN * 4) : 0;    // (mean, rstd)[2][8] + (mul, add, post)[2][BN]
-    static constexpr uint32_t XCHG_BYTES = KIND == K_DX3 ? DX3_XCHG_BYTES : 0;
+    static constexpr uint32_t XCHG_BYTES = KIND == K_DX3 ? DX3_XCHG_BYTES : (KIND == K_DX3G ? 2 * DX3_XCHG_BYTES : 0);
     static constexpr int AUX_BYTES = BAR_BYTES + static_cast<int>(GN_AUX_BYTES) + static_cast<int>(XCHG_BYTES);
     static int stages(uint32_t res_b_bytes) {
         const int avail = SMEM_LIMIT - 1024 - AUX_BYTES - static_cast<int>(EPI_BYTES) - static_cast<int>(res_b_bytes);
@@ -93,6 +96,9 @@ struct KArgs {
     uint32_t res_b_bytes;          // resident weight bytes (K_SLAB_RES, K_PAD)
     int PW, tiles_per_img, H;      // K_PAD: padded row pitch W + 2, 128-position tiles per image, image height
     int m_tiles_real;              // number of real 128-row M tiles (a CTA pair may own one phantom tile at the end)
+    bf16* out_ptr;                 // K_DX3G: the output as a plain pointer (its epilogue stores from registers)
+    int diag;                      // K_DX3 measurement-only ablations (HD_DX3_DIAG, results are WRONG when set): 1 no exchange,
+                                   // 2 no shifts, 4 one TMEM load instead of three, 8 no GroupNorm partials, 16 no output store
     ConvEpilogue epi;
 };
 
@@ -222,7 +228,7 @@ __device__ __forceinline__ float transpose_reduce8(float (&v)[8], int lane) {
 }
 
 template <int BN, int KIND, bool GNF, int CG>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__((Cfg<BN, KIND, GNF, CG>::THREADS), 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
                  const __grid_constant__ CUtensorMap tmD31, const __grid_constant__ CUtensorMap tmD30, const KArgs a) {
@@ -245,7 +251,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint8_t* sA = KIND == K_PAD ? smem + a.res_b_bytes : smem;
     uint8_t* sB = KIND == K_PAD ? smem : smem + stages * C::A_STAGE_BYTES;    // per-stage weights, or the resident matrix
     uint8_t* sEpi = smem + stages * C::A_STAGE_BYTES +
-                    ((KIND == K_SLAB_RES || KIND == K_PAD || KIND == K_DX3) ? a.res_b_bytes : stages * C::B_STAGE_BYTES);   // all sizes are KiB multiples
+                    ((KIND == K_SLAB_RES || KIND == K_PAD || C::DX) ? a.res_b_bytes : stages * C::B_STAGE_BYTES);   // all sizes are KiB multiples
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpi + C::EPI_BYTES);
     uint64_t* empty_bar = full_bar + MAX_STAGES;
     uint64_t* tfull_bar = empty_bar + MAX_STAGES;
@@ -339,7 +345,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     ld2(sB + kb * B_BLOCK, &tmB, res_bar, lb, kb * BLOCK_K, brow_off);
             }
             __syncwarp();
-        } else if constexpr (KIND == K_DX3) {
+        } else if constexpr (C::DX) {
             // resident weights, re-ordered on the way in: the three dx blocks of one (dy, chunk) sit back to back, so that
             // they read as ONE K-major tile of 192 rows (row = dx * 64 + cout); global K order stays (tap, chunk)
             if (ptx::elect_one()) {
@@ -407,7 +413,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         }
                     }
                 }
-            } else if constexpr (KIND == K_DX3) {
+            } else if constexpr (C::DX) {
                 // ONE un-shifted slab {64 ch, W, rows + 2} per chunk: the dy taps are descriptor offsets into it, the dx taps
                 // are the three 64-column groups of the 192-wide accumulator (shifted by one pixel in the epilogue)
                 for (int chunk = 0; chunk < chunks; ++chunk) {
@@ -450,10 +456,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
     } else if (warp == 1 && rank == 0) {
         // ------------------------------------------------------------------ MMA issuer (warp-uniform, one lane issues)
-        constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M * CG, KIND == K_DX3 ? DX3_N : BN);
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M * CG, C::DX ? DX3_N : BN);
         const uint64_t descA0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sA));
         const uint64_t descB0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sB));
-        if constexpr (KIND == K_SLAB_RES || KIND == K_PAD || KIND == K_DX3) {
+        if constexpr (KIND == K_SLAB_RES || KIND == K_PAD || C::DX) {
             ptx::mbar_wait(res_bar, 0);
             ptx::tc_fence_after();
         }
@@ -466,7 +472,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             ptx::mbar_wait(&tempty_bar[as], aphase ^ 1u);
             ptx::tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * C::ACC_STRIDE;
-            if constexpr (KIND == K_DX3) {
+            if constexpr (C::DX) {
                 const uint32_t dy_step = a.slab_dy_bytes >> 4;
                 for (int chunk = 0; chunk < chunks; ++chunk) {
                     ptx::mbar_wait(&full_bar[stage], phase);
@@ -572,7 +578,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // are clipped by the TMA unit); the fp32 head path (N padded to 16, one valid column) stores directly.
         ptx::grid_dep_wait();       // residual reads and every store must follow the predecessor grid (the arena is reused)
         const int q = warp & 3;
-        const int hc = (warp - 2) >> 2;
+        const int hc = ((warp - 2) >> 2) & 1;
         const int r = q * 32 + lane;            // accumulator row == pixel within the tile
         const ConvEpilogue& e = a.epi;
         uint8_t* my_stage = sEpi + (hc * 4 + q) * (C::EPI_BUFS * EPI_BUF_BYTES);
@@ -813,6 +819,132 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 prev_tile = tile;
                 prev_iter = iter;
             }
+        } else if constexpr (KIND == K_DX3G) {
+            // ---- dx-stacked conv, TWO epilogue groups of 8 warps on alternating tiles (group g owns accumulator stage g).
+            // Measured on the one-group form (profiles/r02_notes.md 10): at K = 576 the MMAs of a tile take ~2050 clk but one
+            // warp's epilogue chain ~3600 clk (659 instructions issued at 1 per ~5 clk: in-order dependent chains, two warps per
+            // scheduler) -- the kernel was epilogue-latency bound.  Two tiles in flight hide that chain.  To fit 576 threads
+            // (<= 112 registers) a warp walks its 32 columns in two halves of 16; the shifted sums are FMAs against 0 / 1 lane
+            // masks (no selects), the output leaves as 16-byte global stores straight from registers (no staging buffer, no
+            // async-proxy fence), and the boundary rows between lane quarters use one barrier per half (two buffers).
+            const int grp = (warp - 2) >> 3;
+            const int xw = r & (a.W - 1);
+            const bool cross = a.W > 32;                                  // warp-uniform: quarter boundaries inside an image row
+            const float m_l = (xw != 0 && lane != 0) ? 1.f : 0.f;         // take D0 of the previous lane
+            const float m_r = (xw != a.W - 1 && lane != 31) ? 1.f : 0.f;  // take D2 of the next lane
+            const float m_e = (cross && ((lane == 0 && xw != 0) || (lane == 31 && xw != a.W - 1))) ? 1.f : 0.f;   // take the exchanged row
+            const int pair = hc * 2 + (q >> 1);
+            float* xs0 = s_xchg + grp * 256 + pair * 32;                  // [2 halves][4 pairs][D0 row: 16 | D2 row: 16] per group
+            const int bar_id = 3 + grp * 4 + pair;
+            for (int iter = grp;; iter += 2) {
+                const int tile = tile0 + iter * tile_stride;
+                if (tile >= a.num_tiles) break;
+                const TileCoord tc = decode_tile(a, tile);
+                const int mt = tc.mt;
+                const int m = mt * BLOCK_M + r;
+                ptx::mbar_wait(&tfull_bar[grp], (iter >> 1) & 1u);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + grp * C::ACC_STRIDE + hc * 32;
+                float sq[8];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int ncol = hc * 32 + half * 16;                 // BN == N == 64: one N tile
+                    uint32_t v0[16], v1[16], v2[16];
+                    ptx::tmem_ld16(taddr + half * 16, v0);
+                    ptx::tmem_ld16(taddr + 64 + half * 16, v1);
+                    ptx::tmem_ld16(taddr + 128 + half * 16, v2);
+                    ptx::tmem_ld_wait();
+                    if (half == 1) {                                      // accumulator drained: the MMA warp may start tile iter + 2
+                        ptx::tc_fence_before();
+                        ptx::mbar_arrive(&tempty_bar[grp]);
+                    }
+                    float4 edge[4];
+                    if (cross) {
+                        float* xs = xs0 + half * 128;
+                        if ((q & 1) == 0 && lane == 31) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4)
+                                *reinterpret_cast<float4*>(xs + j) = make_float4(__uint_as_float(v0[j]), __uint_as_float(v0[j + 1]),
+                                                                                   __uint_as_float(v0[j + 2]), __uint_as_float(v0[j + 3]));
+                        }
+                        if ((q & 1) == 1 && lane == 0) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4)
+                                *reinterpret_cast<float4*>(xs + 16 + j) = make_float4(__uint_as_float(v2[j]), __uint_as_float(v2[j + 1]),
+                                                                                        __uint_as_float(v2[j + 2]), __uint_as_float(v2[j + 3]));
+                        }
+                        named_bar_sync(bar_id, 64);
+                        // the buffer of this half is rewritten one tile later, after both warps passed the other half's barrier
+                        const float* ep = xs + ((q & 1) ? 0 : 16);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) edge[j] = *reinterpret_cast<const float4*>(ep + 4 * j);
+                    }
+                    float f[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 bb = e.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(e.bias + ncol + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        f[j] = __uint_as_float(v1[j]) + bb.x; f[j + 1] = __uint_as_float(v1[j + 1]) + bb.y;
+                        f[j + 2] = __uint_as_float(v1[j + 2]) + bb.z; f[j + 3] = __uint_as_float(v1[j + 3]) + bb.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);
+                        const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);
+                        f[j] = fmaf(up, m_l, f[j]);
+                        f[j] = fmaf(dn, m_r, f[j]);
+                    }
+                    if (cross) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = fmaf(reinterpret_cast<const float*>(edge)[j], m_e, f[j]);
+                    }
+                    if (e.out_scale != 1.0f) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] *= e.out_scale;
+                    }
+                    if (e.res != nullptr) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(e.res + static_cast<size_t>(m) * e.ldr + ncol);
+#pragma unroll
+                        for (int j = 0; j < 16; j += 8) {
+                            const uint4 rr = __ldg(rp + j / 8);
+                            float2 t;
+                            t = ptx::unpack_bf16x2(rr.x); f[j] += t.x; f[j + 1] += t.y;
+                            t = ptx::unpack_bf16x2(rr.y); f[j + 2] += t.x; f[j + 3] += t.y;
+                            t = ptx::unpack_bf16x2(rr.z); f[j + 4] += t.x; f[j + 5] += t.y;
+                            t = ptx::unpack_bf16x2(rr.w); f[j + 6] += t.x; f[j + 7] += t.y;
+                        }
+                    }
+                    // this half's two 8-channel pieces: (sum, sum of squares) per lane, reduced over the warp after both halves
+#pragma unroll
+                    for (int p8 = 0; p8 < 2; ++p8) {
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            s1 += f[8 * p8 + j];
+                            s2 = fmaf(f[8 * p8 + j], f[8 * p8 + j], s2);
+                        }
+                        sq[half * 4 + 2 * p8] = s1;
+                        sq[half * 4 + 2 * p8 + 1] = s2;
+                    }
+                    uint4* op = reinterpret_cast<uint4*>(a.out_ptr + static_cast<size_t>(m) * a.N + ncol);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        uint4 o;
+                        o.x = ptx::pack_bf16x2(f[8 * j], f[8 * j + 1]);
+                        o.y = ptx::pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                        o.z = ptx::pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+                        o.w = ptx::pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                        op[j] = o;
+                    }
+                }
+                if (e.gn_part != nullptr) {
+                    const float mine = transpose_reduce8(sq, lane);                   // lane L: value (L >> 2)
+                    const float other = __shfl_down_sync(0xffffffffu, mine, 4);
+                    if ((lane & 7) == 0) {                                            // lane 8p: sum and sum of squares of piece p
+                        const float m2 = fmaxf(other - mine * mine * (1.0f / 256.0f), 0.f);
+                        e.gn_part[(static_cast<size_t>(mt) * 4 + q) * (a.N >> 3) + (hc * 4) + (lane >> 3)] = make_float2(mine, m2);
+                    }
+                }
+            }
         } else if constexpr (KIND == K_PAD) {
             // ---- padded-slab epilogue: GEMM row i of tile mt is PADDED position p0 + i of image b (row pitch W + 2); the
             // positions that fall on a halo column (or past the image) carry garbage and are masked out of the statistics
@@ -958,15 +1090,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             // never leave it; across the 32-lane TMEM quarters the rows travel through shared memory (only at
                             // W = 64: with W <= 32 every quarter boundary is a row boundary).
                             uint32_t v0[32], v1[32], v2[32];
-                            ptx::tmem_ld32(taddr + hc * 32, v0);
                             ptx::tmem_ld32(taddr + 64 + hc * 32, v1);
-                            ptx::tmem_ld32(taddr + 128 + hc * 32, v2);
+                            if (!(a.diag & 4)) {
+                                ptx::tmem_ld32(taddr + hc * 32, v0);
+                                ptx::tmem_ld32(taddr + 128 + hc * 32, v2);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) { v0[j] = v1[j]; v2[j] = v1[j]; }
+                            }
                             ptx::tmem_ld_wait();
                             ptx::tc_fence_before();
                             ptx::mbar_arrive(&tempty_bar[as]);
                             const int xw = r & (a.W - 1);
                             const bool has_l = xw != 0, has_r = xw != a.W - 1;
-                            const bool cross = a.W > 32;                      // warp-uniform
+                            const bool cross = a.W > 32 && !(a.diag & 1);     // warp-uniform
                             float4 edge[8];
                             if (cross) {
                                 const int pair = hc * 2 + (q >> 1);
@@ -991,6 +1128,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             }
                             const bool take_edge_l = cross && (q & 1) == 1 && lane == 0;
                             const bool take_edge_r = cross && (q & 1) == 0 && lane == 31;
+                            if (a.diag & 2) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v1[j]) + __uint_as_float(v0[j]) + __uint_as_float(v2[j]);
+                            } else
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
                                 float up = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);
@@ -1059,8 +1200,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                 t = ptx::unpack_bf16x2(rr.w); f[j + 6] += t.x; f[j + 7] += t.y;
                             }
                         }
-                        if (e.gn_part != nullptr && mt < a.m_tiles_real) write_partials(f, ncol, mt);   // rows are all valid: M % 32 == 0
-                        stage_and_store(f, ncol, tc);
+                        if (e.gn_part != nullptr && mt < a.m_tiles_real && !(KIND == K_DX3 && (a.diag & 8))) write_partials(f, ncol, mt);   // rows are all valid: M % 32 == 0
+                        if (!(KIND == K_DX3 && (a.diag & 16))) stage_and_store(f, ncol, tc);
                         if (e.out_lo != nullptr) {       // low half through the second output map (tmD31 doubles as it)
 #pragma unroll
                             for (int j = 0; j < 32; ++j) f[j] -= __bfloat162float(__float2bfloat16(f[j]));
@@ -1165,11 +1306,16 @@ cudaError_t launch_cfg(const ConvGemmLaunch& l, cudaStream_t s) {
     k.static_weights = l.static_weights;
     k.slab_bytes = l.slab_bytes; k.slab_dy_bytes = l.slab_dy_bytes; k.res_b_bytes = l.res_b_bytes;
     k.PW = l.PW; k.tiles_per_img = l.tiles_per_img; k.H = l.Hh; k.m_tiles_real = l.m_tiles_real;
+    k.out_ptr = l.out;
+    {
+        static const int diag_env = [] { const char* v = getenv("HD_DX3_DIAG"); return v ? atoi(v) : 0; }();
+        k.diag = diag_env;
+    }
     k.epi = l.epi;
     if constexpr (CG == 2) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(l.grid);
-        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.blockDim = dim3(Cfg<BN, KIND, GNF, CG>::THREADS);
         cfg.dynamicSmemBytes = l.smem_bytes;
         cfg.stream = s;
         cudaLaunchAttribute attr[1];
@@ -1181,7 +1327,7 @@ cudaError_t launch_cfg(const ConvGemmLaunch& l, cudaStream_t s) {
         cfg.numAttrs = 1;
         return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, KIND, GNF, CG>, l.tmA0, l.tmA1, l.tmB, l.tmD, l.tmD31, l.tmD30, k);
     } else {
-        return launch_pdl(conv_gemm_kernel<BN, KIND, GNF, CG>, dim3(l.grid), dim3(NUM_THREADS), l.smem_bytes, s, l.tmA0, l.tmA1, l.tmB, l.tmD,
+        return launch_pdl(conv_gemm_kernel<BN, KIND, GNF, CG>, dim3(l.grid), dim3(Cfg<BN, KIND, GNF, CG>::THREADS), l.smem_bytes, s, l.tmA0, l.tmA1, l.tmB, l.tmD,
                           l.tmD31, l.tmD30, k);
     }
 }
@@ -1209,6 +1355,7 @@ void size_cfg(ConvGemmLaunch* l) {
         case K_SLAB_RES: if (l->gnf) size_one<BN, K_SLAB_RES, true>(l); else size_one<BN, K_SLAB_RES, false>(l); break;
         case K_PAD: size_one<BN, K_PAD, false>(l); break;
         case K_DX3: if constexpr (BN == 64) size_one<BN, K_DX3, false>(l); break;
+        case K_DX3G: if constexpr (BN == 64) size_one<BN, K_DX3G, false>(l); break;
         default: size_one<BN, K_GENERAL, false>(l); break;
     }
 }
@@ -1328,7 +1475,11 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
     {
         static const int dx3_env = [] { const char* v = getenv("HD_CONV_DX3"); return v ? atoi(v) : -1; }();
         const int want = dx3_env >= 0 ? dx3_env : d.dx3_mode;
-        if (want > 0 && out->kind == K_SLAB_RES && out->cg == 1 && d.epi.gn_gamma == nullptr && Ws <= 64) out->kind = K_DX3;
+        if (want > 0 && out->kind == K_SLAB_RES && out->cg == 1 && d.epi.gn_gamma == nullptr && Ws <= 64) {
+            // 2 (default): two epilogue groups on alternating tiles, register-direct stores; 1: one group, TMA-store staging
+            const bool simple_epi = d.epi.film == nullptr && !d.epi.silu && d.epi.out_lo == nullptr && d.epi.out_f32 == nullptr && d.out != nullptr;
+            out->kind = (want >= 2 && simple_epi) ? K_DX3G : K_DX3;
+        }
     }
     out->num_tiles = out->num_m_tiles * out->num_n_tiles * phases;
     out->mode = d.mode;
@@ -1484,6 +1635,8 @@ cudaError_t conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t s) {
             return l.gnf ? launch_cfg<64, K_SLAB_RES, true>(l, s) : launch_cfg<64, K_SLAB_RES>(l, s);
         case K_DX3:
             return (l.bn == 64 && !l.gnf) ? launch_cfg<64, K_DX3>(l, s) : cudaErrorInvalidValue;
+        case K_DX3G:
+            return (l.bn == 64 && !l.gnf) ? launch_cfg<64, K_DX3G>(l, s) : cudaErrorInvalidValue;
         default: return cudaErrorInvalidValue;
     }
 }

@@ -109,7 +109,8 @@ struct ConvGemmDesc {
     ConvEpilogue epi;
     int cg2_mode = 0;         // 1: run on CTA pairs (tcgen05 cta_group::2) where the kind supports it
     int pad_mode = 0;         // 3x3, N == 64: 1 = padded-slab form where >= 2 stages fit, 2 = wherever it fits, 0 = never
-    int dx3_mode = 1;         // 3x3, N == 64, resident weights: 1 = dx-stacked form (N = 192 MMAs, shifts in the epilogue), 0 = one MMA per tap
+    int dx3_mode = 2;         // 3x3, N == 64, resident weights: dx-stacked form (N = 192 MMAs, shifts in the epilogue) with 2 = two epilogue
+                              // groups on alternating tiles, 1 = one epilogue group; 0 = one MMA per tap
     int static_weights = 0;   // 1: `weight` is not written by any kernel of the graph this launch belongs to (the sampling plan's
                               // weights, prepared at finalize): the resident-weight load may then precede the PDL wait (ptx.cuh).
                               // The trainer re-derives its bf16 layouts every step -> 0.

@@ -296,7 +296,7 @@ struct Builder {
         d.weight = wq(wkey);
         d.pad_mode = (P->cfg.reserved[0] >> 1) & 3;
         d.cg2_mode = (P->cfg.reserved[0] >> 3) & 1;
-        d.dx3_mode = ((P->cfg.reserved[0] >> 6) & 1) ? 0 : 1;   // bit 6: one MMA per tap in the N = 64 3x3 convs
+        d.dx3_mode = ((P->cfg.reserved[0] >> 6) & 1) ? 0 : 2;   // bit 6: one MMA per tap in the N = 64 3x3 convs
         d.wsplit = P->wsplit ? 1 : 0;
         d.static_weights = 1;       // prepared at hd_plan_finalize, constant for every graph of the plan
         d.N = N;
@@ -1279,7 +1279,10 @@ int hd_op_conv2d(const uint16_t* x0, int32_t C0, const uint16_t* x1, int32_t C1,
     d.weight = q; d.N = Cout; d.out = reinterpret_cast<bf16*>(out);
     d.pad_mode = (standardize >> 1) & 3;   // bits 1-2 of `standardize`: opt into the padded-slab conv form (parity tests)
     d.cg2_mode = (standardize >> 3) & 1;   // bit 3: run on CTA pairs (tcgen05 cta_group::2)
-    d.dx3_mode = ((standardize >> 4) & 1) ? 0 : 1;   // bit 4: one MMA per tap instead of the dx-stacked N = 192 form
+    {   // bits 4-5: form of the 3x3, Cout = 64 conv: 0 = default (dx-stacked, two epilogue groups), 1 = one MMA per tap, 2 = dx-stacked, one group
+        const int f = (standardize >> 4) & 3;
+        d.dx3_mode = f == 1 ? 0 : (f == 2 ? 1 : 2);
+    }
     d.epi.bias = bias;
     if (res) { d.epi.res = reinterpret_cast<const bf16*>(res); d.epi.ldr = Cout; }
     ConvGemmLaunch l;

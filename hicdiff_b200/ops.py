@@ -36,7 +36,8 @@ def conv2d_nhwc(x0, w, bias=None, x1=None, res=None, ksize=None, standardize=Fal
     `upsample=True` is Upsample (nearest x2 + 3x3, folded into four 2x2 phase convs over the low-res input).
     `pad_mode` 1/2 opts 3x3, Cout == 64 convs into the padded-slab form (one halo'd box per chunk serves all nine taps);
     `cta_pairs` runs the GEMM on clusters of two CTAs (tcgen05 cta_group::2, M = 256 tiles, each CTA holds half of B);
-    `dx_stack=False` makes the 3x3, Cout == 64 conv issue one MMA per tap instead of the default N = 192 (three dx taps) form."""
+    `dx_stack=False` makes the 3x3, Cout == 64 conv issue one MMA per tap instead of the default N = 192 (three dx taps) form;
+    `dx_stack=1` selects that form's one-epilogue-group variant (default: two groups on alternating tiles)."""
     lib = _lib.load()
     _need_cuda(x0, w)
     x0, x1, res = _bf16c(x0), _bf16c(x1), _bf16c(res)
@@ -49,7 +50,7 @@ def conv2d_nhwc(x0, w, bias=None, x1=None, res=None, ksize=None, standardize=Fal
     out = torch.empty(B, Ho, Wo, Cout, device=x0.device, dtype=torch.bfloat16)
     _lib.check(
         lib.hd_op_conv2d(_lib.ptr(x0), C0, _lib.ptr(x1), C1, _lib.ptr(w), _lib.ptr(bias), _lib.ptr(res), _lib.ptr(out),
-                         B, Ho, Wo, Cout, k, 1 if unshuffle else (2 if upsample else 0), (1 if standardize else 0) | (int(pad_mode) << 1) | ((1 if cta_pairs else 0) << 3) | ((0 if dx_stack else 1) << 4),
+                         B, Ho, Wo, Cout, k, 1 if unshuffle else (2 if upsample else 0), (1 if standardize else 0) | (int(pad_mode) << 1) | ((1 if cta_pairs else 0) << 3) | ((2 if dx_stack == 1 and dx_stack is not True else (0 if dx_stack else 1)) << 4),
                          _lib.stream_ptr()),
         "hd_op_conv2d",
     )

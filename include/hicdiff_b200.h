@@ -251,7 +251,7 @@ HD_API int hd_tile_scatter(const float* tiles, float* mat, int64_t n, int32_t pi
  * x1 (second concat operand, C1 channels) may be NULL.  mode 0: k x k "same" conv; mode 1: Downsample (pixel
  * unshuffle + 1x1, w is [Cout, 4*C0, 1, 1]; x0 is [B,2H,2W,C0], output [B,H,W,Cout]).  res (optional) is added.
  * Bits above bit 0 of `standardize` select opt-in kernel forms for the parity tests: bits 1-2 padded slab, bit 3 CTA pairs,
- * bit 4 one MMA per tap instead of the dx-stacked form of the 3x3, Cout = 64 conv. */
+ * bits 4-5 form of the 3x3, Cout = 64 conv (0 default: dx-stacked with two epilogue groups, 1: one MMA per tap, 2: dx-stacked, one group). */
 HD_API int hd_op_conv2d(const uint16_t* x0, int32_t C0, const uint16_t* x1, int32_t C1, const float* w, const float* bias,
                  const uint16_t* res, uint16_t* out, int32_t B, int32_t H, int32_t W, int32_t Cout, int32_t ksize,
                  int32_t mode, int32_t standardize, void* stream);

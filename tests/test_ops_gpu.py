@@ -156,6 +156,9 @@ def test_conv_gemm_dx_stacked(B, H, C0, C1, res):
     assert (out.float() - per_tap.float()).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item()
     again = ops.conv2d_nhwc(x0, w, bias, x1=x1, res=r, standardize=True)
     assert torch.equal(out, again), "dx-stacked conv is not bit-reproducible"
+    one_group = ops.conv2d_nhwc(x0, w, bias, x1=x1, res=r, standardize=True, dx_stack=1)
+    _check(one_group, ref, f"dx-stacked (one epilogue group) conv {Cin}->64 @{H}")
+    assert (out.float() - one_group.float()).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item()
 
 
 @pytest.mark.parametrize("B,H,C0,C1,Cout,k", [(2, 64, 64, 0, 64, 3), (3, 32, 128, 64, 128, 3), (3, 8, 512, 256, 512, 3), (2, 16, 256, 0, 256, 3),
