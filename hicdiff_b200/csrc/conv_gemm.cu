@@ -66,7 +66,8 @@ struct Cfg {
     static constexpr uint32_t B_STAGE_BYTES = KIND == K_GENERAL ? B_BLOCK_BYTES : (KIND == K_SLAB ? 3 * B_BLOCK_BYTES : 0);
     static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int EPI_BUFS = BN <= 64 ? 1 : 2;                             // staging buffers per epilogue warp
-    static constexpr uint32_t EPI_BYTES = KIND == K_DX3G ? 0 : EPI_WARPS * EPI_BUFS * EPI_BUF_BYTES;   // K_DX3G stores straight from registers
+    // K_DX3G: 16 epilogue warps, each with two 32 rows x 16 columns (32-byte rows, unswizzled) TMA-store boxes, one per column half
+    static constexpr uint32_t EPI_BYTES = KIND == K_DX3G ? 16 * 2 * 1024 : EPI_WARPS * EPI_BUFS * EPI_BUF_BYTES;
     // accumulator ring in TMEM: 2 stages, or 4 when the epilogue also applies GroupNorm (its second phase trails by one
     // tile while it waits for the image's statistics)
     static constexpr int ACC_STAGES = GNF ? 4 : 2;
@@ -96,9 +97,6 @@ struct KArgs {
     uint32_t res_b_bytes;          // resident weight bytes (K_SLAB_RES, K_PAD)
     int PW, tiles_per_img, H;      // K_PAD: padded row pitch W + 2, 128-position tiles per image, image height
     int m_tiles_real;              // number of real 128-row M tiles (a CTA pair may own one phantom tile at the end)
-    bf16* out_ptr;                 // K_DX3G: the output as a plain pointer (its epilogue stores from registers)
-    int diag;                      // K_DX3 measurement-only ablations (HD_DX3_DIAG, results are WRONG when set): 1 no exchange,
-                                   // 2 no shifts, 4 one TMEM load instead of three, 8 no GroupNorm partials, 16 no output store
     ConvEpilogue epi;
 };
 
@@ -824,9 +822,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             // Measured on the one-group form (profiles/r02_notes.md 10): at K = 576 the MMAs of a tile take ~2050 clk but one
             // warp's epilogue chain ~3600 clk (659 instructions issued at 1 per ~5 clk: in-order dependent chains, two warps per
             // scheduler) -- the kernel was epilogue-latency bound.  Two tiles in flight hide that chain.  To fit 576 threads
-            // (<= 112 registers) a warp walks its 32 columns in two halves of 16; the shifted sums are FMAs against 0 / 1 lane
-            // masks (no selects), the output leaves as 16-byte global stores straight from registers (no staging buffer, no
-            // async-proxy fence), and the boundary rows between lane quarters use one barrier per half (two buffers).
+            // (<= 112 registers) a warp walks its 32 columns in two halves of 16, each leaving through its own 1 KiB staging box
+            // and a TMA store (16-byte stores straight from registers were measured 1.7x SLOWER: 32 lines per instruction); the
+            // shifted sums are FMAs against 0 / 1 lane masks, the boundary rows between lane quarters use one barrier per half.
             const int grp = (warp - 2) >> 3;
             const int xw = r & (a.W - 1);
             const bool cross = a.W > 32;                                  // warp-uniform: quarter boundaries inside an image row
@@ -836,6 +834,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int pair = hc * 2 + (q >> 1);
             float* xs0 = s_xchg + grp * 256 + pair * 32;                  // [2 halves][4 pairs][D0 row: 16 | D2 row: 16] per group
             const int bar_id = 3 + grp * 4 + pair;
+            uint8_t* my_box = sEpi + (warp - 2) * 2048;                   // [2 halves][32 rows][32 B]
             for (int iter = grp;; iter += 2) {
                 const int tile = tile0 + iter * tile_stride;
                 if (tile >= a.num_tiles) break;
@@ -858,9 +857,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         ptx::tc_fence_before();
                         ptx::mbar_arrive(&tempty_bar[grp]);
                     }
-                    float4 edge[4];
+                    float* xs = xs0 + half * 128;
                     if (cross) {
-                        float* xs = xs0 + half * 128;
                         if ((q & 1) == 0 && lane == 31) {
 #pragma unroll
                             for (int j = 0; j < 16; j += 4)
@@ -874,10 +872,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                                                                         __uint_as_float(v2[j + 2]), __uint_as_float(v2[j + 3]));
                         }
                         named_bar_sync(bar_id, 64);
-                        // the buffer of this half is rewritten one tile later, after both warps passed the other half's barrier
-                        const float* ep = xs + ((q & 1) ? 0 : 16);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) edge[j] = *reinterpret_cast<const float4*>(ep + 4 * j);
+                        // (the buffer of this half is rewritten one tile later, after both warps passed the other half's barrier)
                     }
                     float f[16];
 #pragma unroll
@@ -894,8 +889,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         f[j] = fmaf(dn, m_r, f[j]);
                     }
                     if (cross) {
+                        const float* ep = xs + ((q & 1) ? 0 : 16);       // upper warp: the lower one's D0 row, and vice versa
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) f[j] = fmaf(reinterpret_cast<const float*>(edge)[j], m_e, f[j]);
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 ev = *reinterpret_cast<const float4*>(ep + j);
+                            f[j] = fmaf(ev.x, m_e, f[j]); f[j + 1] = fmaf(ev.y, m_e, f[j + 1]);
+                            f[j + 2] = fmaf(ev.z, m_e, f[j + 2]); f[j + 3] = fmaf(ev.w, m_e, f[j + 3]);
+                        }
                     }
                     if (e.out_scale != 1.0f) {
 #pragma unroll
@@ -925,7 +925,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         sq[half * 4 + 2 * p8] = s1;
                         sq[half * 4 + 2 * p8 + 1] = s2;
                     }
-                    uint4* op = reinterpret_cast<uint4*>(a.out_ptr + static_cast<size_t>(m) * a.N + ncol);
+                    // the box of this half was handed to the TMA unit one tile ago; at most the other half's store is younger
+                    if (lane == 0) ptx::bulk_wait_read<1>();
+                    __syncwarp();
+                    uint8_t* box = my_box + half * 1024;
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         uint4 o;
@@ -933,7 +936,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         o.y = ptx::pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
                         o.z = ptx::pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
                         o.w = ptx::pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-                        op[j] = o;
+                        *reinterpret_cast<uint4*>(box + lane * 32 + j * 16) = o;
+                    }
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_2d(&tmD30, box, ncol, mt * BLOCK_M + q * 32);
+                        ptx::bulk_commit();
                     }
                 }
                 if (e.gn_part != nullptr) {
@@ -1090,20 +1099,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             // never leave it; across the 32-lane TMEM quarters the rows travel through shared memory (only at
                             // W = 64: with W <= 32 every quarter boundary is a row boundary).
                             uint32_t v0[32], v1[32], v2[32];
+                            ptx::tmem_ld32(taddr + hc * 32, v0);
                             ptx::tmem_ld32(taddr + 64 + hc * 32, v1);
-                            if (!(a.diag & 4)) {
-                                ptx::tmem_ld32(taddr + hc * 32, v0);
-                                ptx::tmem_ld32(taddr + 128 + hc * 32, v2);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) { v0[j] = v1[j]; v2[j] = v1[j]; }
-                            }
+                            ptx::tmem_ld32(taddr + 128 + hc * 32, v2);
                             ptx::tmem_ld_wait();
                             ptx::tc_fence_before();
                             ptx::mbar_arrive(&tempty_bar[as]);
                             const int xw = r & (a.W - 1);
-                            const bool has_l = xw != 0, has_r = xw != a.W - 1;
-                            const bool cross = a.W > 32 && !(a.diag & 1);     // warp-uniform
+                            const bool cross = a.W > 32;                      // warp-uniform
+                            // 0 / 1 lane masks: the shifted sums are FMAs (a select per term made the one-group epilogue 659
+                            // instructions per tile, profiles/r02_notes.md 10); lanes 0 / 31 take the exchanged row instead
+                            const float m_l = (xw != 0 && lane != 0) ? 1.f : 0.f;
+                            const float m_r = (xw != a.W - 1 && lane != 31) ? 1.f : 0.f;
+                            const float m_e = (cross && ((lane == 0 && xw != 0) || (lane == 31 && xw != a.W - 1))) ? 1.f : 0.f;
                             float4 edge[8];
                             if (cross) {
                                 const int pair = hc * 2 + (q >> 1);
@@ -1126,22 +1134,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                 for (int j = 0; j < 8; ++j) edge[j] = *reinterpret_cast<const float4*>(ep + 4 * j);
                                 named_bar_sync(3 + pair, 64);                 // the rows are consumed: the next tile may overwrite them
                             }
-                            const bool take_edge_l = cross && (q & 1) == 1 && lane == 0;
-                            const bool take_edge_r = cross && (q & 1) == 0 && lane == 31;
-                            if (a.diag & 2) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v1[j]) + __uint_as_float(v0[j]) + __uint_as_float(v2[j]);
-                            } else
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
-                                float up = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);
-                                float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);
-                                if (cross) {
-                                    const float ev = reinterpret_cast<const float*>(edge)[j];
-                                    if (take_edge_l) up = ev;
-                                    if (take_edge_r) dn = ev;
-                                }
-                                f[j] = __uint_as_float(v1[j]) + (has_l ? up : 0.f) + (has_r ? dn : 0.f);
+                                const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);
+                                const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);
+                                f[j] = fmaf(dn, m_r, fmaf(up, m_l, __uint_as_float(v1[j])));
+                            }
+                            if (cross) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) f[j] = fmaf(reinterpret_cast<const float*>(edge)[j], m_e, f[j]);
                             }
                         } else {
                             uint32_t v[32];
@@ -1200,8 +1201,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                 t = ptx::unpack_bf16x2(rr.w); f[j + 6] += t.x; f[j + 7] += t.y;
                             }
                         }
-                        if (e.gn_part != nullptr && mt < a.m_tiles_real && !(KIND == K_DX3 && (a.diag & 8))) write_partials(f, ncol, mt);   // rows are all valid: M % 32 == 0
-                        if (!(KIND == K_DX3 && (a.diag & 16))) stage_and_store(f, ncol, tc);
+                        if (e.gn_part != nullptr && mt < a.m_tiles_real) write_partials(f, ncol, mt);   // rows are all valid: M % 32 == 0
+                        stage_and_store(f, ncol, tc);
                         if (e.out_lo != nullptr) {       // low half through the second output map (tmD31 doubles as it)
 #pragma unroll
                             for (int j = 0; j < 32; ++j) f[j] -= __bfloat162float(__float2bfloat16(f[j]));
@@ -1250,7 +1251,8 @@ int encode_tmap_bf16(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_
     }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle_bytes == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -1306,11 +1308,6 @@ cudaError_t launch_cfg(const ConvGemmLaunch& l, cudaStream_t s) {
     k.static_weights = l.static_weights;
     k.slab_bytes = l.slab_bytes; k.slab_dy_bytes = l.slab_dy_bytes; k.res_b_bytes = l.res_b_bytes;
     k.PW = l.PW; k.tiles_per_img = l.tiles_per_img; k.H = l.Hh; k.m_tiles_real = l.m_tiles_real;
-    k.out_ptr = l.out;
-    {
-        static const int diag_env = [] { const char* v = getenv("HD_DX3_DIAG"); return v ? atoi(v) : 0; }();
-        k.diag = diag_env;
-    }
     k.epi = l.epi;
     if constexpr (CG == 2) {
         cudaLaunchConfig_t cfg = {};
@@ -1478,7 +1475,8 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
         if (want > 0 && out->kind == K_SLAB_RES && out->cg == 1 && d.epi.gn_gamma == nullptr && Ws <= 64) {
             // 2 (default): two epilogue groups on alternating tiles, register-direct stores; 1: one group, TMA-store staging
             const bool simple_epi = d.epi.film == nullptr && !d.epi.silu && d.epi.out_lo == nullptr && d.epi.out_f32 == nullptr && d.out != nullptr;
-            out->kind = (want >= 2 && simple_epi) ? K_DX3G : K_DX3;
+            const bool fits = Cfg<64, K_DX3G>::stages(out->res_b_bytes) >= 2;    // K = 1152: no room for the second group's boxes
+            out->kind = (want >= 2 && simple_epi && fits) ? K_DX3G : K_DX3;
         }
     }
     out->num_tiles = out->num_m_tiles * out->num_n_tiles * phases;
@@ -1566,6 +1564,10 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
             cuuint32_t ob[2] = {32, 32};     // one epilogue warp: 32 rows x 32 columns, 64-byte rows, 64B swizzle
             if (encode_map(&out->tmD, d.out, 2, od, os, ob, err, errlen, 64)) return 1;
             if (d.epi.out_lo != nullptr && encode_map(&out->tmD31, d.epi.out_lo, 2, od, os, ob, err, errlen, 64)) return 1;
+            if (out->kind == K_DX3G) {       // 32 rows x 16 columns, dense 32-byte rows in shared memory
+                cuuint32_t ob16[2] = {16, 32};
+                if (encode_map(&out->tmD30, d.out, 2, od, os, ob16, err, errlen, 0)) return 1;
+            }
         }
         if (d.epi.out_lo != nullptr && (out->kind == K_PAD || up || d.epi.gn_gamma != nullptr)) {
             snprintf(err, errlen, "conv_gemm: the hi + lo output is built for the plain dense epilogue");
