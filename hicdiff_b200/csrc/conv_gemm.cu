@@ -1189,7 +1189,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
                             for (int j = 0; j < 32; ++j) f[j] *= e.out_scale;
                         }
-                        if (e.res != nullptr && valid) {
+                        if (e.res != nullptr && valid && e.gnres != nullptr) {
+                            // ResnetBlock tail: res is block2's RAW conv output; add SiLU(GroupNorm(res)) with the folded affine
+                            const uint4* rp = reinterpret_cast<const uint4*>(e.res + static_cast<size_t>(m) * e.ldr + ncol);
+                            const float4* mp = reinterpret_cast<const float4*>(e.gnres + static_cast<size_t>(m / a.P) * a.N + ncol);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                const uint4 rr = __ldg(rp + j / 8);
+                                const float4 q0 = __ldg(mp + j / 2), q1 = __ldg(mp + j / 2 + 1), q2 = __ldg(mp + j / 2 + 2), q3 = __ldg(mp + j / 2 + 3);
+                                float2 t;
+                                t = ptx::unpack_bf16x2(rr.x); f[j] += silu_f(fmaf(t.x, q0.x, q0.y)); f[j + 1] += silu_f(fmaf(t.y, q0.z, q0.w));
+                                t = ptx::unpack_bf16x2(rr.y); f[j + 2] += silu_f(fmaf(t.x, q1.x, q1.y)); f[j + 3] += silu_f(fmaf(t.y, q1.z, q1.w));
+                                t = ptx::unpack_bf16x2(rr.z); f[j + 4] += silu_f(fmaf(t.x, q2.x, q2.y)); f[j + 5] += silu_f(fmaf(t.y, q2.z, q2.w));
+                                t = ptx::unpack_bf16x2(rr.w); f[j + 6] += silu_f(fmaf(t.x, q3.x, q3.y)); f[j + 7] += silu_f(fmaf(t.y, q3.z, q3.w));
+                            }
+                        } else if (e.res != nullptr && valid) {
                             const uint4* rp = reinterpret_cast<const uint4*>(e.res + static_cast<size_t>(m) * e.ldr + ncol);
 #pragma unroll
                             for (int j = 0; j < 32; j += 8) {
@@ -1474,7 +1488,8 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
         const int want = dx3_env >= 0 ? dx3_env : d.dx3_mode;
         if (want > 0 && out->kind == K_SLAB_RES && out->cg == 1 && d.epi.gn_gamma == nullptr && Ws <= 64) {
             // 2 (default): two epilogue groups on alternating tiles, register-direct stores; 1: one group, TMA-store staging
-            const bool simple_epi = d.epi.film == nullptr && !d.epi.silu && d.epi.out_lo == nullptr && d.epi.out_f32 == nullptr && d.out != nullptr;
+            const bool simple_epi = d.epi.film == nullptr && !d.epi.silu && d.epi.out_lo == nullptr && d.epi.out_f32 == nullptr && d.out != nullptr &&
+                                    d.epi.gnres == nullptr;
             const bool fits = Cfg<64, K_DX3G>::stages(out->res_b_bytes) >= 2;    // K = 1152: no room for the second group's boxes
             out->kind = (want >= 2 && simple_epi && fits) ? K_DX3G : K_DX3;
         }
@@ -1509,6 +1524,10 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
     }
     if (up && (d.epi.res != nullptr || d.epi.film != nullptr || d.epi.gn_part != nullptr || d.epi.out_f32 != nullptr)) {
         snprintf(err, errlen, "conv_gemm: the upsample conv supports the bias epilogue only");
+        return 1;
+    }
+    if (d.epi.gnres != nullptr && (d.epi.res == nullptr || d.epi.gn_gamma != nullptr || d.epi.out_f32 != nullptr || up || out->kind == K_PAD)) {
+        snprintf(err, errlen, "conv_gemm: the GroupNorm'd residual operand needs the dense bf16 epilogue");
         return 1;
     }
     out->gnf = d.epi.gn_gamma != nullptr ? 1 : 0;

@@ -78,6 +78,11 @@ struct ConvEpilogue {
     float out_scale = 1.0f;           // v *= out_scale
     const bf16* res = nullptr;        // v += res[m, c]   (row stride ldr)
     int ldr = 0;
+    // ResnetBlock tail in one pass (hicdiff_condition.py:191-197): when set, `res` is the RAW output of block2's conv and
+    // gnres[b * N + c] = (mul, add) folds its GroupNorm(8) affine (groupnorm_finalize_run): v += SiLU(res * mul + add).  The
+    // launch is then res_conv(x) + block2's norm / activation / skip add: the separate groupnorm_apply pass and the
+    // res_conv output tensor disappear (one 1x1 conv launch instead of conv + a 3-stream elementwise pass).
+    const float2* gnres = nullptr;
     float* out_f32 = nullptr;         // if set: write fp32 [M, n_valid] instead of bf16
     int n_valid = 0;
     // optional second bf16 output [M, N]: lo = bf16(v - bf16(v)), so out + out_lo carries ~16 mantissa bits.  Used where the
@@ -179,6 +184,10 @@ struct GroupNormArgs {
     int exact_act = 0;                // 1: SiLU through ex2 + rcp instead of one tanh.approx ("bf16w2" precision)
 };
 cudaError_t groupnorm_film_silu_run(const GroupNormArgs& a, cudaStream_t s);
+// Statistics only: merges the conv's partials exactly like groupnorm_film_silu_run (same order, same arithmetic) and writes the folded
+// per-(image, channel) affine ma[b * C + c] = (gamma * rstd, beta - mean * gamma * rstd); dense partial layout, no FiLM.
+cudaError_t groupnorm_finalize_run(const float2* part, const float* gamma, const float* beta, float eps, float2* ma, int B, int P, int C,
+                                   cudaStream_t s);
 // Stand-alone producer of the same partials from a bf16 tensor (used when the input does not come from conv_gemm).
 cudaError_t groupnorm_stats_run(const bf16* x, float2* part, int B, int P, int C, cudaStream_t s);
 

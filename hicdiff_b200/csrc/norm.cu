@@ -227,6 +227,47 @@ groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int
     }
 }
 
+// Statistics-only twin of the merge above (dense partial layout): one CTA per image, warp g merges group g in the same order
+// with the same arithmetic, then the group's channels get their folded affine.  Consumer: the conv epilogue's `gnres` operand.
+__global__ void __launch_bounds__(GN_THREADS)
+groupnorm_finalize_kernel(const float2* __restrict__ part, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          const float eps, float2* __restrict__ ma, const int P, const int C) {
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cpg = C / GN_GROUPS;
+    const int nwb = P / 32;
+    const int ppg = C / 64;
+    const int ppr = C / 8;
+    const int nent = nwb * ppg;
+    const float2* pp = part + (static_cast<size_t>(b) * nwb) * ppr + warp * ppg;
+    const float total = static_cast<float>(P) * static_cast<float>(cpg);
+    float sm = 0.f;
+    for (int idx = lane; idx < nent; idx += 32) {
+        const int blk = idx / ppg;
+        sm += __ldg(pp + static_cast<size_t>(blk) * ppr + (idx - blk * ppg)).x;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, off);
+    const float mean = sm / total;
+    float m2 = 0.f;
+    for (int idx = lane; idx < nent; idx += 32) {
+        const int blk = idx / ppg;
+        const float2 e = __ldg(pp + static_cast<size_t>(blk) * ppr + (idx - blk * ppg));
+        const float dm = e.x / 256.0f - mean;
+        m2 += e.y + 256.0f * dm * dm;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, off);
+    const float rstd = rsqrtf(m2 / total + eps);
+    for (int j = lane; j < cpg; j += 32) {
+        const int c = warp * cpg + j;
+        const float gm = __ldg(gamma + c) * rstd;
+        ma[static_cast<size_t>(b) * C + c] = make_float2(gm, __ldg(beta + c) - mean * gm);
+    }
+}
+
 // Stand-alone partial producer (same layout as the conv epilogue's): one warp per 32-pixel block, lanes = pixels,
 // one (sum, M2) pair per 8-channel piece.
 __global__ void __launch_bounds__(256)
@@ -405,6 +446,12 @@ cudaError_t groupnorm_film_silu_run(const GroupNormArgs& a, cudaStream_t s) {
     else if (post) return launch_pdl(groupnorm_apply_kernel<false, true, false>, dim3(grid), dim3(GN_THREADS), 0, s, a, slabs_per_img, total, per_cta);
     else return launch_pdl(groupnorm_apply_kernel<false, false, false>, dim3(grid), dim3(GN_THREADS), 0, s, a, slabs_per_img, total, per_cta);
     return cudaGetLastError();
+}
+
+cudaError_t groupnorm_finalize_run(const float2* part, const float* gamma, const float* beta, float eps, float2* ma, int B, int P, int C,
+                                   cudaStream_t s) {
+    if (B <= 0 || C % 64 != 0 || C > 512 || P % 32 != 0) return cudaErrorInvalidValue;
+    return launch_pdl(groupnorm_finalize_kernel, dim3(B), dim3(GN_THREADS), 0, s, part, gamma, beta, eps, ma, P, C);
 }
 
 cudaError_t groupnorm_stats_run(const bf16* x, float2* part, int B, int P, int C, cudaStream_t s) {

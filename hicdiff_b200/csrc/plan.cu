@@ -139,6 +139,7 @@ struct Exec {
     float* ctx = nullptr;    // linear-attention scratch [B,4,32,32]
     float2* gn_part = nullptr;  // GroupNorm partial statistics [B*P/32][C/8], rewritten by every GN-feeding conv
     int* gn_cnt = nullptr;      // per-image arrival counters of the GroupNorm-fused conv epilogue [B]
+    float2* gn_ma = nullptr;    // folded GroupNorm affine (mul, add) per (image, channel) of a block2 conv [B][C <= 512] (resblock tail fusion)
     float* la_ctx = nullptr;    // fused linear attention: partial contexts [B*8][128][32]
     float* la_s = nullptr;      //                          partial softmax denominators [B*8][128]
     bf16* la_mb = nullptr;      //                          per-image to_out * ctx matrices [B][128][128]
@@ -405,6 +406,37 @@ struct Builder {
         const int off = slot >= 0 ? P->film[slot].off : 0;
         Act h = conv_norm(p + ".block1", x0, x1, Cout, P->sr3 ? -1 : off, P->sr3 ? off : -1, nullptr);
         note(p + ".block1", h);
+        // Blocks with a res_conv (Cin != Cout): ONE launch for the tail.  block2's conv leaves its raw output + GroupNorm partials,
+        // a one-CTA-per-image kernel folds the statistics into a per-(image, channel) affine, and res_conv's epilogue adds
+        // SiLU(GN(raw)) to its own 1x1 result -- instead of res_conv -> r, then a 3-stream groupnorm_apply (raw, r -> out): the
+        // r tensor is never written or re-read (2/3 of the two launches' HBM traffic).  HD_RESBLOCK_TAIL=0 / option bit 7 keep
+        // the two-launch form; debug_keep (named intermediates), the GroupNorm-in-epilogue option and split weights do too.
+        static const int tail_env = [] { const char* v = getenv("HD_RESBLOCK_TAIL"); return v ? atoi(v) : -1; }();
+        const bool tail_opt = tail_env >= 0 ? tail_env != 0 : !((P->cfg.reserved[0] >> 7) & 1);
+        if (Cin != Cout && tail_opt && !P->cfg.debug_keep && !(P->cfg.reserved[0] & 1) && !P->wsplit && ((P->cfg.reserved[0] >> 1) & 3) == 0 &&
+            (x0.H * x0.W) % 32 == 0 && Cout % 64 == 0) {
+            Act raw = conv(p + ".block2.proj.weight", p + ".block2.proj.bias", h, nullptr, Cout, 3, CONV_TAPS, ConvEpilogue(), 0, true);
+            free_act(h);
+            if (ok && !dry && last_part_tpi != 0) bad(p + ": the fused ResnetBlock tail needs the dense GroupNorm partial layout (HD_CONV_PAD is set?)");
+            if (ok && !dry) {
+                const float2* part = ex->gn_part;
+                float2* ma = ex->gn_ma;
+                const float* gamma = wf(p + ".block2.norm.weight");
+                const float* beta = wf(p + ".block2.norm.bias");
+                const int Bn = B, Pn = raw.H * raw.W, Cn = raw.C;
+                Op op{[=](cudaStream_t s) { return groupnorm_finalize_run(part, gamma, beta, 1e-5f, ma, Bn, Pn, Cn, s); }, p + ".block2.norm"};
+                op.kernel = "groupnorm_finalize";
+                op.bytes = 8.0 * B * (Pn / 32) * (Cn / 8);
+                ops->push_back(op);
+            }
+            ConvEpilogue e;
+            e.res = raw.p; e.ldr = Cout;
+            e.gnres = dry ? reinterpret_cast<const float2*>(8) : ex->gn_ma;
+            Act out = conv(p + ".res_conv.weight", p + ".res_conv.bias", x0, x1, Cout, 1, CONV_TAPS, e);
+            free_act(raw);
+            note(p, out);
+            return out;
+        }
         // res_conv first: block2's conv must be the last writer of the shared partial-statistics buffer before its norm
         Act r;
         bool own_r = false;
@@ -651,7 +683,7 @@ void free_exec(Exec* ex) {
     if (ex->g_step) cudaGraphExecDestroy(ex->g_step);
     cudaFree(ex->arena); cudaFree(ex->x); cudaFree(ex->cond); cudaFree(ex->eps); cudaFree(ex->time);
     cudaFree(ex->posenc); cudaFree(ex->temb0); cudaFree(ex->temb); cudaFree(ex->film_rows); cudaFree(ex->iota);
-    cudaFree(ex->ctx); cudaFree(ex->gn_part); cudaFree(ex->la_ctx); cudaFree(ex->la_s); cudaFree(ex->la_mb); cudaFree(ex->gn_cnt);
+    cudaFree(ex->ctx); cudaFree(ex->gn_part); cudaFree(ex->la_ctx); cudaFree(ex->la_s); cudaFree(ex->la_mb); cudaFree(ex->gn_cnt); cudaFree(ex->gn_ma);
 }
 
 int run_ops(const std::vector<Op>& ops, cudaStream_t s) {
@@ -719,6 +751,7 @@ int get_exec(hd_plan* P, int B, cudaStream_t s, Exec** out) {
     EX_TRY(cudaMalloc(&ex->ctx, static_cast<size_t>(B) * 4 * 32 * 32 * 4));
     EX_TRY(cudaMalloc(&ex->gn_part, static_cast<size_t>(B) * (tile / 32) * 64 * sizeof(float2)));   // [M/32][C/8], C <= 512
     EX_TRY(cudaMalloc(&ex->gn_cnt, static_cast<size_t>(B) * 4));
+    EX_TRY(cudaMalloc(&ex->gn_ma, static_cast<size_t>(B) * 512 * sizeof(float2)));
     if (!P->lattn.empty()) {
         EX_TRY(cudaMalloc(&ex->la_ctx, static_cast<size_t>(B) * LA_MAX_PARTS * 128 * 32 * 4));
         EX_TRY(cudaMalloc(&ex->la_s, static_cast<size_t>(B) * LA_MAX_PARTS * 128 * 4));

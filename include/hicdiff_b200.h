@@ -58,7 +58,9 @@ typedef struct hd_config {
                                * bits 4-5: GEMM precision -- 0 = bf16 operands (default), 1 = "bf16w2": bf16 activations,
                                * conv weights as hi + lo bf16 pairs (two MMAs per product; the reference computes in fp32,
                                * src/hicdiff_condition.py:90,105); bit 6: the 3x3, Cout = 64 convs issue one MMA per filter tap
-                               * instead of the default dx-stacked form (three taps per N = 192 MMA).  Other words: 0.    */
+                               * instead of the default dx-stacked form (three taps per N = 192 MMA); bit 7: ResnetBlocks with
+                               * a res_conv keep res_conv and block2's GroupNorm apply as two launches (default: one launch,
+                               * hicdiff_condition.py:191-197).  Other words: 0.                                        */
 } hd_config;
 
 /* -------------------------------------------------------------------------------------------------------------
