@@ -406,13 +406,15 @@ struct Builder {
         const int off = slot >= 0 ? P->film[slot].off : 0;
         Act h = conv_norm(p + ".block1", x0, x1, Cout, P->sr3 ? -1 : off, P->sr3 ? off : -1, nullptr);
         note(p + ".block1", h);
-        // Blocks with a res_conv (Cin != Cout): ONE launch for the tail.  block2's conv leaves its raw output + GroupNorm partials,
-        // a one-CTA-per-image kernel folds the statistics into a per-(image, channel) affine, and res_conv's epilogue adds
-        // SiLU(GN(raw)) to its own 1x1 result -- instead of res_conv -> r, then a 3-stream groupnorm_apply (raw, r -> out): the
-        // r tensor is never written or re-read (2/3 of the two launches' HBM traffic).  HD_RESBLOCK_TAIL=0 / option bit 7 keep
-        // the two-launch form; debug_keep (named intermediates), the GroupNorm-in-epilogue option and split weights do too.
+        // Opt-in (HD_RESBLOCK_TAIL=1 / option bit 7) for blocks with a res_conv (Cin != Cout): ONE launch for the tail.  block2's conv
+        // leaves its raw output + GroupNorm partials, a one-CTA-per-image kernel folds the statistics into a per-(image, channel)
+        // affine, and res_conv's epilogue adds SiLU(GN(raw)) to its own 1x1 result -- instead of res_conv -> r, then a 3-stream
+        // groupnorm_apply (raw, r -> out): the r tensor is never written or re-read (2/3 of the two launches' HBM traffic).
+        // Measured (profiles/r02_notes.md 11): parity-green, but NOT faster -- at 64x64 the fused launch takes 134.6 us against
+        // 67.4 + 67.4 us, because the 8-warp conv epilogue is a latency chain (~5 clk per instruction) and the extra SiLU / affine
+        // work lands on it, while groupnorm_apply streams with 16 warps per SM.  So the two-launch form stays the default.
         static const int tail_env = [] { const char* v = getenv("HD_RESBLOCK_TAIL"); return v ? atoi(v) : -1; }();
-        const bool tail_opt = tail_env >= 0 ? tail_env != 0 : !((P->cfg.reserved[0] >> 7) & 1);
+        const bool tail_opt = tail_env >= 0 ? tail_env != 0 : ((P->cfg.reserved[0] >> 7) & 1) != 0;
         if (Cin != Cout && tail_opt && !P->cfg.debug_keep && !(P->cfg.reserved[0] & 1) && !P->wsplit && ((P->cfg.reserved[0] >> 1) & 3) == 0 &&
             (x0.H * x0.W) % 32 == 0 && Cout % 64 == 0) {
             Act raw = conv(p + ".block2.proj.weight", p + ".block2.proj.bias", h, nullptr, Cout, 3, CONV_TAPS, ConvEpilogue(), 0, true);

@@ -91,7 +91,12 @@ class EpsPlan:
             self.set_schedule(one, one * 0, one, one * 0, one * 0, one * 0)
         T = int(self._schedule["sqrt_recip"].numel())
         prec = precision_of(self._net)
-        key = (str(dev), _params_version(self._net), self._schedule_id, T, self.debug_keep, prec)
+        # kernel-form option bits of hd_config.reserved[0] (include/hicdiff_b200.h; the precision bits 4-5 belong to `precision`):
+        # `net.plan_options = 0x80` or HICDIFF_B200_PLAN_OPTIONS=0x80 -- read per plan, used by the parity tests for the opt-in forms
+        po = getattr(self._net, "plan_options", None)
+        opts = int(po) if po is not None else int(os.environ.get("HICDIFF_B200_PLAN_OPTIONS", "0"), 0)
+        opts &= ~0x30
+        key = (str(dev), _params_version(self._net), self._schedule_id, T, self.debug_keep, prec, opts)
         if self._handle is not None and key == self._key:
             return self._handle
         with torch.cuda.device(dev):
@@ -111,7 +116,7 @@ class EpsPlan:
                 cfg.timesteps = T
                 cfg.num_blocks = cfgd["num_blocks"]
                 cfg.debug_keep = 1 if self.debug_keep else 0
-                cfg.reserved[0] = PRECISIONS[prec] << 4          # bits 4-5: precision (include/hicdiff_b200.h)
+                cfg.reserved[0] = (PRECISIONS[prec] << 4) | opts  # bits 4-5: precision (include/hicdiff_b200.h)
                 h = C.c_void_p()
                 _lib.check(lib.hd_plan_create(C.byref(cfg), C.byref(h)), "hd_plan_create")
                 self._handle = h.value

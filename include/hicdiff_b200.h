@@ -59,8 +59,8 @@ typedef struct hd_config {
                                * conv weights as hi + lo bf16 pairs (two MMAs per product; the reference computes in fp32,
                                * src/hicdiff_condition.py:90,105); bit 6: the 3x3, Cout = 64 convs issue one MMA per filter tap
                                * instead of the default dx-stacked form (three taps per N = 192 MMA); bit 7: ResnetBlocks with
-                               * a res_conv keep res_conv and block2's GroupNorm apply as two launches (default: one launch,
-                               * hicdiff_condition.py:191-197).  Other words: 0.                                        */
+                               * a res_conv run res_conv + block2's GroupNorm apply as ONE launch (opt-in, measured not
+                               * faster; hicdiff_condition.py:191-197).  Other words: 0.                                 */
 } hd_config;
 
 /* -------------------------------------------------------------------------------------------------------------

@@ -74,6 +74,33 @@ def test_eps_matches_reference_golden(nets, name):
         assert r <= EPS_TOL, f"{name} t={t}: eps rel-RMS {r:.3e} > {EPS_TOL}"
 
 
+@pytest.mark.parametrize("name", ["unet_cond", "unet_uncond", "unet_sr3"])
+@pytest.mark.parametrize("opts,what", [(0x80, "one-launch ResnetBlock tail"), (0x40, "one MMA per tap in the 64-channel 3x3 convs")])
+def test_eps_kernel_form_options(nets, name, opts, what):
+    """Opt-in / fall-back kernel forms selected per plan (hd_config.reserved[0], include/hicdiff_b200.h): bit 7 runs res_conv +
+    block2's GroupNorm / SiLU / skip add as ONE conv launch (groupnorm_finalize + the `gnres` epilogue operand), bit 6 makes the
+    3x3, Cout = 64 convs issue one MMA per tap instead of the dx-stacked default.  Same tolerance against the reference fixtures
+    as the default plan, and the two plans agree with each other far inside it."""
+    _, v, sd = nets(name)
+    net, _ = helpers.build_net(name)
+    net.load_state_dict(sd)
+    net = net.cuda()
+    net.plan_options = opts
+    base, _, _ = nets(name)
+    gold = torch.load(helpers.GOLD / f"{name}.pt")
+    B = gold["x_t"].shape[0]
+    _, noisy = O.synthetic_tiles(B, seed=gold["tile_seed"])
+    cond = noisy.cuda() if v["oracle"]["self_condition"] else None
+    for t, ref in gold["eps"].items():
+        eps = net(gold["x_t"].cuda(), _time(v, t, B).cuda(), cond)
+        r = helpers.rel_rms(eps, ref)
+        _record(test="eps_golden_option", variant=name, option=hex(opts), t=t, rel_rms=r)
+        assert torch.isfinite(eps).all() and r <= EPS_TOL, f"{name} ({what}) t={t}: eps rel-RMS {r:.3e} > {EPS_TOL}"
+        dflt = base(gold["x_t"].cuda(), _time(v, t, B).cuda(), cond)
+        d = helpers.rel_rms(eps, dflt.cpu())
+        assert d <= 1.5e-2, f"{name} ({what}) t={t}: differs from the default plan by rel-RMS {d:.3e}"
+
+
 @pytest.mark.parametrize("name", VARIANTS)
 def test_eps_split_weight_precision(nets, name):
     """`net.precision = "bf16w2"` (conv weights as hi + lo bf16 pairs, every eps-net flavour incl. the folded Upsample, the
