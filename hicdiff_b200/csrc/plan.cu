@@ -336,9 +336,9 @@ struct Builder {
         return it->second;
     }
 
-    void groupnorm(const Act& x, const std::string& prefix, int film_off, int postadd_off, const Act* res) {
+    void groupnorm(const Act& x, const std::string& prefix, int film_off, int postadd_off, const Act* res, const Act* y = nullptr) {
         GroupNormArgs g;
-        g.x = x.p; g.y = x.p;   // in place: each CTA stages its own slab in smem before writing it back
+        g.x = x.p; g.y = y ? y->p : x.p;   // default in place: every thread rewrites exactly the 16-byte chunks it read
         g.B = B; g.P = x.H * x.W; g.C = x.C;
         g.part = dry ? nullptr : ex->gn_part;
         g.part_tpi = last_part_tpi; g.part_W = last_part_W;
@@ -394,6 +394,14 @@ struct Builder {
         }
         Act h = conv(p + ".proj.weight", p + ".proj.bias", x0, x1, Cout, 3, CONV_TAPS, ConvEpilogue(), 0, true);
         note(p + ".proj", h);
+        // HD_GN_OUT_OF_PLACE=1 (A/B switch): the 2-stream GroupNorm pass writes a second buffer instead of rewriting its input
+        static const int oop_env = [] { const char* v = getenv("HD_GN_OUT_OF_PLACE"); return v ? atoi(v) : 0; }();
+        if (oop_env && res == nullptr && !P->cfg.debug_keep) {
+            Act y = alloc_act(h.H, h.W, h.C);
+            groupnorm(h, p + ".norm", film_off, postadd_off, res, &y);
+            free_act(h);
+            return y;
+        }
         groupnorm(h, p + ".norm", film_off, postadd_off, res);
         return h;
     }
