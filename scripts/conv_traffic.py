@@ -25,7 +25,7 @@ a, b = stems[-2], stems[-1]          # the last complete step in the capture
 fam = {}
 for e in rows[a:b]:
     n = e["name"]
-    key = ("conv_gemm" if "conv_gemm" in n else "groupnorm" if "groupnorm" in n else "linattn_fused" if re.search(r"linattn_(kv|mix|out)_kernel", n)
+    key = ("conv_gemm" if "conv_gemm" in n else "groupnorm" if "groupnorm" in n else "linattn_fused" if re.search(r"linattn_(kv|mix|out)2?_kernel", n)
            else "other")
     f = fam.setdefault(key, {"launches": 0, "dram_bytes": 0.0, "ncu_ms": 0.0})
     f["launches"] += 1
