@@ -133,6 +133,7 @@ struct ConvGemmLaunch {
     int kind;           // 0 general, 1 slab (3x3, one A box per (chunk, dx)), 2 slab + shared-memory resident weights,
                         // 3 padded slab (one A box per chunk serves all nine taps; GroupNorm partials use the padded layout)
                         // 4 dx-stacked resident slab (N == 64: MMAs of 192 columns = 3 dx taps, shifted and summed in the epilogue)
+                        // 5 the same with two epilogue groups of 8 warps on alternating tiles (576 threads; where shared memory allows)
     int grid;
     int smem_bytes;
     // kernel scalar arguments
