@@ -16,6 +16,13 @@
 //     aligned) into the slab.  One pipeline stage then carries 12 MMAs instead of 4, and the L2 -> SM traffic of the
 //     A operand drops from 9 to 3 * (R + 2) / R loads per pixel.  When the whole weight matrix fits (N == 64,
 //     K <= 1152: 72 / 144 KiB) it is loaded into shared memory ONCE per persistent CTA (SLAB_RES).
+//   * DX-STACKED path (3x3, N == 64, resident weights; the default there): the measured issue law of tcgen05 on B200 is
+//     N/2 + 43 clk per K = 16 MMA (scripts/ubench_tcgen05.cu), i.e. the fixed part is paid per MMA, not per column.  So the
+//     three dx taps of a filter row are stacked along N: ONE un-shifted slab per chunk, B tile of 192 rows (3 x 64 output
+//     channels), one MMA per (dy, K = 16) -- 139 clk instead of 3 x 75 -- and the epilogue adds the accumulator's three
+//     64-column groups shifted by -1 / 0 / +1 pixel (whole image rows per tile, so the shifts stay inside it).  With the
+//     MMAs that short the epilogue chain became the limiter; where shared memory allows the kernel runs 18 warps with two
+//     epilogue groups on alternating tiles (K_DX3G), else 10 warps (K_DX3).  profiles/r02_notes.md 11.
 //   * A channel concat (torch.cat((x, skip), 1)) is two tensor maps walked back to back inside each tap.
 //   * Downsample's pixel-unshuffle is a 5-D view [C, p2, W/2, p1, B*H/2] of the same NHWC buffer.
 //   * Upsample's nearest x2 is folded into the conv: output phase (a, b) = (y & 1, x & 1) is a 2x2 conv over the
@@ -66,7 +73,7 @@ struct Cfg {
     static constexpr uint32_t B_STAGE_BYTES = KIND == K_GENERAL ? B_BLOCK_BYTES : (KIND == K_SLAB ? 3 * B_BLOCK_BYTES : 0);
     static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int EPI_BUFS = BN <= 64 ? 1 : 2;                             // staging buffers per epilogue warp
-    // K_DX3G: 16 epilogue warps, each with two 32 rows x 16 columns (32-byte rows, unswizzled) TMA-store boxes, one per column half
+    // K_DX3G: 16 epilogue warps, each with one 32 rows x 32 columns TMA-store box (2 KiB, 64B swizzle) filled in two column halves
     static constexpr uint32_t EPI_BYTES = KIND == K_DX3G ? 16 * 2 * 1024 : EPI_WARPS * EPI_BUFS * EPI_BUF_BYTES;
     // accumulator ring in TMEM: 2 stages, or 4 when the epilogue also applies GroupNorm (its second phase trails by one
     // tile while it waits for the image's statistics)
@@ -822,8 +829,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             // Measured on the one-group form (profiles/r02_notes.md 10): at K = 576 the MMAs of a tile take ~2050 clk but one
             // warp's epilogue chain ~3600 clk (659 instructions issued at 1 per ~5 clk: in-order dependent chains, two warps per
             // scheduler) -- the kernel was epilogue-latency bound.  Two tiles in flight hide that chain.  To fit 576 threads
-            // (<= 112 registers) a warp walks its 32 columns in two halves of 16, each leaving through its own 1 KiB staging box
-            // and a TMA store (16-byte stores straight from registers were measured 1.7x SLOWER: 32 lines per instruction); the
+            // (<= 112 registers) a warp walks its 32 columns in two halves of 16 that fill one 2 KiB staging box, stored by TMA
+            // once per tile (16-byte stores straight from registers were measured 1.7x SLOWER: 32 lines per instruction); the
             // shifted sums are FMAs against 0 / 1 lane masks, the boundary rows between lane quarters use one barrier per half.
             const int grp = (warp - 2) >> 3;
             const int xw = r & (a.W - 1);
@@ -834,7 +841,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int pair = hc * 2 + (q >> 1);
             float* xs0 = s_xchg + grp * 256 + pair * 32;                  // [2 halves][4 pairs][D0 row: 16 | D2 row: 16] per group
             const int bar_id = 3 + grp * 4 + pair;
-            uint8_t* my_box = sEpi + (warp - 2) * 2048;                   // [2 halves][32 rows][32 B]
+            uint8_t* my_box = sEpi + (warp - 2) * 2048;                   // 32 rows x 32 columns bf16, 64-byte rows, 64B swizzle (as tmD expects)
             for (int iter = grp;; iter += 2) {
                 const int tile = tile0 + iter * tile_stride;
                 if (tile >= a.num_tiles) break;
@@ -925,10 +932,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         sq[half * 4 + 2 * p8] = s1;
                         sq[half * 4 + 2 * p8 + 1] = s2;
                     }
-                    // the box of this half was handed to the TMA unit one tile ago; at most the other half's store is younger
-                    if (lane == 0) ptx::bulk_wait_read<1>();
-                    __syncwarp();
-                    uint8_t* box = my_box + half * 1024;
+                    // both halves go into ONE 32 x 32 box (this half = 16-byte chunks 2 * half, 2 * half + 1 of the 64-byte row) and
+                    // leave with one fence + one TMA store per tile; the box was handed to the TMA unit a whole tile pair ago
+                    if (half == 0) {
+                        if (lane == 0) ptx::bulk_wait_read<0>();
+                        __syncwarp();
+                    }
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         uint4 o;
@@ -936,13 +945,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         o.y = ptx::pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
                         o.z = ptx::pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
                         o.w = ptx::pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-                        *reinterpret_cast<uint4*>(box + lane * 32 + j * 16) = o;
+                        *reinterpret_cast<uint4*>(my_box + lane * 64 + (((2 * half + j) ^ swz) << 4)) = o;
                     }
-                    ptx::fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        ptx::tma_store_2d(&tmD30, box, ncol, mt * BLOCK_M + q * 32);
-                        ptx::bulk_commit();
+                    if (half == 1) {
+                        ptx::fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::tma_store_2d(&tmD, my_box, hc * 32, mt * BLOCK_M + q * 32);
+                            ptx::bulk_commit();
+                        }
                     }
                 }
                 if (e.gn_part != nullptr) {
@@ -1583,10 +1594,7 @@ int conv_gemm_prepare(const ConvGemmDesc& d, int num_sms, ConvGemmLaunch* out, c
             cuuint32_t ob[2] = {32, 32};     // one epilogue warp: 32 rows x 32 columns, 64-byte rows, 64B swizzle
             if (encode_map(&out->tmD, d.out, 2, od, os, ob, err, errlen, 64)) return 1;
             if (d.epi.out_lo != nullptr && encode_map(&out->tmD31, d.epi.out_lo, 2, od, os, ob, err, errlen, 64)) return 1;
-            if (out->kind == K_DX3G) {       // 32 rows x 16 columns, dense 32-byte rows in shared memory
-                cuuint32_t ob16[2] = {16, 32};
-                if (encode_map(&out->tmD30, d.out, 2, od, os, ob16, err, errlen, 0)) return 1;
-            }
+
         }
         if (d.epi.out_lo != nullptr && (out->kind == K_PAD || up || d.epi.gn_gamma != nullptr)) {
             snprintf(err, errlen, "conv_gemm: the hi + lo output is built for the plain dense epilogue");
