@@ -14,6 +14,8 @@
 // channel_layernorm: LayerNorm over channels with gain g (eps 1e-5), optional residual add and optional
 //   nearest-neighbour 2x upsample on the way out.
 //   reference: LayerNorm :99-108, PreNorm :110-118, Residual :64-70, Upsample's nn.Upsample :74
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -22,8 +24,11 @@ namespace {
 
 constexpr int GN_THREADS = 256;
 constexpr int GN_GROUPS = 8;
-constexpr int GN_CHUNKS_PER_THREAD = 4;                                  // 16-byte chunks in flight per thread
-constexpr int GN_SLAB_CHUNKS = GN_THREADS * GN_CHUNKS_PER_THREAD;        // 16 KiB of the image per CTA
+// 16-byte chunks in flight per thread and stream (template parameter CH of the apply kernel): 4 with a residual stream, 8 without --
+// the 2-stream form then keeps as many loads in flight as the 3-stream form (which ran at 91 % of the copy bandwidth against 76 %:
+// at 512 threads per SM, 4 chunks are 32 KiB in flight per SM, below what the loaded HBM latency asks for at 6.5 TB/s)
+constexpr int GN_CHUNKS_PER_THREAD = 4;
+constexpr int GN_SLAB_CHUNKS = GN_THREADS * GN_CHUNKS_PER_THREAD;        // 16 KiB of the image per CTA and iteration (CH = 4)
 
 // x * sigmoid(x) = h + h * tanh(h), h = x / 2: ONE SFU op (tanh.approx, rel. error 2^-11) instead of ex2 + rcp.  ncu showed the
 // apply kernel at ~50% issue utilisation with 2 SFU ops per element (134 M per 128 MiB tensor = 29 us of SFU time alone); the
@@ -44,7 +49,7 @@ __device__ __forceinline__ float silu_f(float v) {
 // rounded weight it perturbs every step of a chain the same way (measured: it alone kept the T = 1000 PSNR 1.4e-2 dB off).
 __device__ __forceinline__ float silu_exact(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
-template <bool HAS_RES, bool HAS_POST, bool EXACT = false>   // compile out the residual stream and the SR3 post-add where a launch has none (issue-bound kernel)
+template <bool HAS_RES, bool HAS_POST, bool EXACT = false, int CH = GN_CHUNKS_PER_THREAD>   // compile out the residual stream and the SR3 post-add where a launch has none (issue-bound kernel)
 __global__ void __launch_bounds__(GN_THREADS, 2)
 groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int total_slabs, const int slabs_per_cta) {
     __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
@@ -64,11 +69,11 @@ groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int
     const int my_c = my_cp * 8;
     const int my_g = my_c / cpg;
 
-    uint4 u[GN_CHUNKS_PER_THREAD], r[GN_CHUNKS_PER_THREAD];
-    auto load_slab = [&](int s, uint4 (&uu)[GN_CHUNKS_PER_THREAD], uint4 (&rr)[GN_CHUNKS_PER_THREAD]) {
-        const size_t base = static_cast<size_t>(s) * GN_SLAB_CHUNKS + tid;
+    uint4 u[CH], r[CH];
+    auto load_slab = [&](int s, uint4 (&uu)[CH], uint4 (&rr)[CH]) {
+        const size_t base = static_cast<size_t>(s) * (GN_THREADS * CH) + tid;
 #pragma unroll
-        for (int k = 0; k < GN_CHUNKS_PER_THREAD; ++k) {
+        for (int k = 0; k < CH; ++k) {
             uu[k] = __ldg(xin + base + k * GN_THREADS);
             if constexpr (HAS_RES) rr[k] = __ldg(rin + base + k * GN_THREADS);
         }
@@ -188,11 +193,11 @@ groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int
                 post[j] = prow != nullptr ? __ldg(prow + c) : 0.f;
             }
         }
-        uint4 un[GN_CHUNKS_PER_THREAD], rn[GN_CHUNKS_PER_THREAD];
+        uint4 un[CH], rn[CH];
         if (s + 1 < s1) load_slab(s + 1, un, rn);            // next slab in flight while this one is processed
-        const size_t obase = static_cast<size_t>(s) * GN_SLAB_CHUNKS + tid;
+        const size_t obase = static_cast<size_t>(s) * (GN_THREADS * CH) + tid;
 #pragma unroll
-        for (int k = 0; k < GN_CHUNKS_PER_THREAD; ++k) {
+        for (int k = 0; k < CH; ++k) {
             float v[8];
             float2 t;
             t = ptx::unpack_bf16x2(u[k].x); v[0] = t.x; v[1] = t.y;
@@ -219,7 +224,7 @@ groupnorm_apply_kernel(const GroupNormArgs a, const int slabs_per_img, const int
         }
         if (s + 1 < s1) {
 #pragma unroll
-            for (int k = 0; k < GN_CHUNKS_PER_THREAD; ++k) {
+            for (int k = 0; k < CH; ++k) {
                 u[k] = un[k];
                 if constexpr (HAS_RES) r[k] = rn[k];
             }
@@ -421,19 +426,27 @@ cudaError_t groupnorm_film_silu_run(const GroupNormArgs& a, cudaStream_t s) {
         return cudaErrorInvalidValue;
     const size_t img_chunks = static_cast<size_t>(a.P) * a.C / 8;
     if (img_chunks % GN_SLAB_CHUNKS != 0) return cudaErrorInvalidValue;   // images are 32 KiB .. 2 MiB here
+    const bool res = a.res != nullptr, post = a.postadd != nullptr;
+    // 8 chunks per thread for the 2-stream launches (HD_GN_CH8=0: 4 everywhere, A/B switch)
+    static const int ch8_env = [] { const char* v = getenv("HD_GN_CH8"); return v ? atoi(v) : 1; }();
+    const bool wide = ch8_env != 0 && !res && !a.exact_act && img_chunks % (2 * GN_SLAB_CHUNKS) == 0;
+    const int slab_chunks = wide ? 2 * GN_SLAB_CHUNKS : GN_SLAB_CHUNKS;
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
             num_sms = 148;
     }
-    const int slabs_per_img = static_cast<int>(img_chunks / GN_SLAB_CHUNKS);
+    const int slabs_per_img = static_cast<int>(img_chunks / slab_chunks);
     const int total = a.B * slabs_per_img;
     int grid = 2 * num_sms;                              // two resident CTAs per SM, one contiguous run of slabs each
     if (grid > total) grid = total;
     const int per_cta = (total + grid - 1) / grid;
     grid = (total + per_cta - 1) / per_cta;
-    const bool res = a.res != nullptr, post = a.postadd != nullptr;
+    if (wide) {
+        if (post) return launch_pdl(groupnorm_apply_kernel<false, true, false, 8>, dim3(grid), dim3(GN_THREADS), 0, s, a, slabs_per_img, total, per_cta);
+        return launch_pdl(groupnorm_apply_kernel<false, false, false, 8>, dim3(grid), dim3(GN_THREADS), 0, s, a, slabs_per_img, total, per_cta);
+    }
     if (a.exact_act) {
         if (res && post) return launch_pdl(groupnorm_apply_kernel<true, true, true>, dim3(grid), dim3(GN_THREADS), 0, s, a, slabs_per_img, total, per_cta);
         else if (res) return launch_pdl(groupnorm_apply_kernel<true, false, true>, dim3(grid), dim3(GN_THREADS), 0, s, a, slabs_per_img, total, per_cta);
