@@ -1,5 +1,7 @@
 #!/bin/bash
 # Round-2 GPU pass O: what bounds the dx-stacked conv at K = 576 (3600 clk per tile against 2052 clk of MMAs)?
+# NOTE: HD_DX3_DIAG was a measurement-only switch (results wrong by construction); it exists in commit 63b567c (one-group form) and was
+# removed afterwards -- re-running this script on a later tree measures the unablated kernel seven times.
 # Measurement-only ablations of its epilogue (HD_DX3_DIAG, wrong results by construction) and one --set full capture with source.
 TAG=${1:-r02o}
 mkdir -p gpurun_out

@@ -1,5 +1,7 @@
 #!/bin/bash
 # Round-2 GPU pass Q: why the two-group dx-stacked epilogue is no faster than one group -- ablations + one --set full capture.
+# NOTE: HD_DX3_DIAG was a measurement-only switch (results wrong by construction); it exists in commit 63b567c (one-group form) and was
+# removed afterwards -- re-running this script on a later tree measures the unablated kernel seven times.
 TAG=${1:-r02q}
 mkdir -p gpurun_out
 for diag in 0 1 2 8 16 27; do
